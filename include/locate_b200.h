@@ -1,0 +1,180 @@
+/*
+ * locate_b200 -- C ABI of the B200-native LocAtE hot path (generator/discriminator block
+ * forward + backward).  Plain C: borrowed device pointers, sizes, a cudaStream_t; no torch
+ * types.  Every entry point returns 0 on success, a positive cudaError_t on a CUDA failure or
+ * a negative LB_E* code on an argument error.  No entry point allocates or synchronises;
+ * work is enqueued on `stream` and all pointers must stay valid until it drains.
+ *
+ * The reference (ClashLuke/LocAtE, /root/reference) has no FFI: its operator boundary is the
+ * Python API of libs/ (SURVEY.md section 8b).  Each entry point below names the reference
+ * arithmetic (file:line) it replaces; locate_b200/*.py rebuilds the reference's nn.Module tree
+ * on top of these calls and INTEGRATION.md shows the ctypes stub a maintainer of the
+ * reference would add.
+ *
+ * Activation layout: channels-last.  A logical [B,C,H,W] tensor is stored [B][H][W][C]
+ * (fp32 unless stated); "rows" below are pixels (b,h,w) and "ld" is the channel stride of a
+ * row, so a channel slice of a wider tensor is (ptr + channel_offset, ld = full C).
+ */
+#ifndef LOCATE_B200_H
+#define LOCATE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* lb_stream_t; /* == cudaStream_t */
+
+enum {
+  LB_OK = 0,
+  LB_EINVAL = -1,   /* bad size / null pointer / unsupported combination */
+  LB_EALIGN = -2,   /* pointer or leading dimension not aligned as the kernel needs */
+  LB_EUNSUPPORTED = -3
+};
+
+/* Library / device info. lb_version returns e.g. 100 for 0.1.0; lb_sm_arch the compiled arch (100). */
+int lb_version(void);
+int lb_sm_arch(void);
+int lb_last_launch_count(void);   /* kernels launched by this library since lb_reset_launch_count */
+void lb_reset_launch_count(void);
+
+/* ---- RootTanh activation: y = (x^2+1)^(1/growth) * tanh(x)          libs/activation.py:9-16
+ *      bwd: dx = g * (2(x^2+1) sech^2 x + x tanh x) / (2 (x^2+1)^((growth-1)/growth))  :20-36 */
+int lb_roottanh_fwd(const float* x, float* y, size_t n, int growth, lb_stream_t stream);
+int lb_roottanh_bwd(const float* x, const float* g, float* dx, size_t n, int growth, lb_stream_t stream);
+/* tanh on the generator output                                          libs/models.py:66 */
+int lb_tanh_fwd(const float* x, float* y, size_t n, lb_stream_t stream);
+int lb_tanh_bwd(const float* y, const float* g, float* dx, size_t n, lb_stream_t stream);
+
+/* hinge(t) = max(1 - t, 0) elementwise                                   libs/utils.py:133-134 */
+int lb_hinge_fwd(const float* x, float* y, size_t n, lb_stream_t stream);
+int lb_hinge_bwd(const float* x, const float* g, float* dx, size_t n, lb_stream_t stream);
+
+/* ---- whole-tensor norm ("InPlaceNorm")                                libs/inplace_norm.py:7-45
+ * stats pipeline: lb_norm_stats accumulates (sum, sum of squares) of x into sums[2] (double,
+ * caller zeroes it; in data parallel the caller all-reduces sums across ranks), then
+ * lb_norm_finalize turns (sums, n_total) into stats[4] = {mean, std(unbiased), 1/std, n_total}. */
+int lb_norm_stats(const float* x, size_t n, double* sums, lb_stream_t stream);
+int lb_norm_finalize(const double* sums, double n_total, float* stats, lb_stream_t stream);
+/* y = (x-mean)*gain/std + bias ; gain is [C] (gain_batch_stride = 0) or [B][C] (stride = C). */
+int lb_norm_apply(const float* x, const float* stats, const float* gain, int gain_batch_stride,
+                  const float* bias, float* y, int batch, int pixels, int channels, lb_stream_t stream);
+/* backward, 3 steps (inplace_norm.py:17-27 composed with d std/dx):
+ *  1. lb_norm_bwd_reduce: p1[b][c] += sum_hw g, p2[b][c] += sum_hw (x-mean)*g      (caller zeroes p1,p2)
+ *  2. lb_norm_bwd_finalize: dgain (+=, [C] or [B][C]), dbias (+=, [C]), s[2] = {sum gain*p1, sum gain*p2}
+ *     (double; in data parallel the caller all-reduces s)
+ *  3. lb_norm_bwd_apply: dx = gain*g/std - s0/(std*N) - s1*(x-mean)/((N-1)*std^3)                   */
+int lb_norm_bwd_reduce(const float* x, const float* g, const float* stats, float* p1, float* p2,
+                       int batch, int pixels, int channels, lb_stream_t stream);
+int lb_norm_bwd_finalize(const float* p1, const float* p2, const float* gain, int gain_batch_stride,
+                         const float* stats, int batch, int channels, float* dgain, float* dbias,
+                         double* s, lb_stream_t stream);
+int lb_norm_bwd_apply(const float* x, const float* g, const float* stats, const float* gain,
+                      int gain_batch_stride, const double* s, float* dx, int batch, int pixels,
+                      int channels, lb_stream_t stream);
+
+/* ---- gated residual: out = (gamma*y + 1)*x                            libs/merge.py:19-39
+ * y is a full tensor (y_bcast = 0) or a per-(b,c) gate [B][C] broadcast over pixels (y_bcast = 1;
+ * the Expand of feature attention, libs/util_modules.py:6-12, never materialised).
+ * bwd: dx = (gamma*y+1)*g ; dy = gamma*x*g (summed over pixels when y_bcast; caller zeroes dy then);
+ *      dgamma += sum x*x*g when strict_reference (the reference's formula, merge.py:33-38)
+ *                or sum x*y*g otherwise.  gamma is a device scalar. */
+int lb_gate_fwd(const float* x, const float* y, const float* gamma, float* out, int batch, int pixels,
+                int channels, int y_bcast, lb_stream_t stream);
+int lb_gate_bwd(const float* x, const float* y, const float* gamma, const float* g, float* dx, float* dy,
+                float* dgamma, int batch, int pixels, int channels, int y_bcast, int strict_reference,
+                lb_stream_t stream);
+
+/* ---- spectral norm power iteration, one per forward                   libs/spectral_norm.py:21-32
+ * W is the row-major [height][width] view of weight_bar.  u,v updated in place; sigma_out[0] = sigma,
+ * sigma_out[1] = 1/sigma.  work: height + width + 4 floats of scratch. */
+int lb_sn_power_iter(const float* w, int height, int width, float* u, float* v, float* sigma_out,
+                     float* work, lb_stream_t stream);
+/* weight-gradient epilogue: with dwn = dL/d(W/sigma) (same layout as W) and the LIVE u,v:
+ *   grad += dwn/sigma - (sum dwn*W)/sigma^2 * u v^T       (SURVEY.md section 8c identity)
+ * work: 2 doubles of scratch (zeroed by the call). */
+int lb_sn_weight_grad(const float* dwn, const float* w, const float* u, const float* v,
+                      const float* sigma, float* grad, int height, int width, double* work,
+                      lb_stream_t stream);
+
+/* ---- convolution family as a gather-GEMM                              libs/conv.py:11-24, libs/attention.py:9-54,
+ *                                                                       libs/scale.py:25-34, libs/linear.py:10
+ * out[b,oy,ox,n] = alpha * sum_{ty,tx,k} in[b,iy,ix,k] * W(ty,tx,k,n)  (+ bias[n])
+ *   mode 0 (strided):    iy = oy*stride - pad + ty            -> Conv fwd, ConvTranspose dgrad
+ *   mode 1 (transposed): iy = (oy + pad - ty)/stride if exact -> ConvTranspose fwd, Conv dgrad
+ * W(ty,tx,k,n) = w[k*w_sk + n*w_sn + ty*w_sty + tx*w_stx]: the master weight is read in place in
+ * whatever layout the reference stores it ((Cout,Cin,kh,kw) or (Cin,Cout,kh,kw)).
+ * alpha is a device scalar (1/sigma) or NULL for 1. */
+typedef struct {
+  int batch, in_h, in_w, in_c;     /* gathered operand */
+  int out_h, out_w, out_c;         /* produced operand */
+  int kh, kw, stride, pad, mode;
+  int ld_in, ld_out;               /* channel strides of the two operands' rows */
+  int64_t w_sk, w_sn, w_sty, w_stx;
+} lb_conv_geom;
+
+int lb_conv_gemm(const float* in, const float* w, const float* alpha, const float* bias, float* out,
+                 const lb_conv_geom* g, lb_stream_t stream);
+/* weight gradient: dw(ty,tx,kg,kd) += sum_m gathered[m@tap, kg] * dense[m, kd] with mode-0 gather
+ * around the DENSE operand's pixel grid (dense = dy for Conv, x for ConvTranspose).
+ * geom: in_* describes the gathered operand, out_* the dense one; w_sk strides the gathered
+ * channel, w_sn the dense channel.  dw must be zeroed by the caller (atomic accumulation). */
+int lb_conv_wgrad(const float* gathered, const float* dense, float* dw, const lb_conv_geom* g,
+                  lb_stream_t stream);
+/* column sum: out[c] += sum_rows x[row*ld + c]  (bias gradients) */
+int lb_colsum(const float* x, int64_t rows, int cols, int ld, float* out, lb_stream_t stream);
+
+/* ---- softmax                                                          libs/attention.py:35,47 */
+/* over pixels for every (b,c) of a channels-last [B][P][C] tensor (SelfAttention, dim=-1 of [B,F,HW]) */
+int lb_softmax_pixels_fwd(const float* x, float* y, int batch, int pixels, int channels, lb_stream_t stream);
+int lb_softmax_pixels_bwd(const float* y, const float* g, float* dx, int batch, int pixels, int channels,
+                          lb_stream_t stream);
+/* over the contiguous last axis of [rows][cols] (feature attention, Softmax(dim=1) on [B,F,1,1]) */
+int lb_softmax_rows_fwd(const float* x, float* y, int rows, int cols, lb_stream_t stream);
+int lb_softmax_rows_bwd(const float* y, const float* g, float* dx, int rows, int cols, lb_stream_t stream);
+
+/* ---- skip path resampling                                             libs/scale.py:7-45, libs/merge.py:4-16 */
+/* FeaturePooling: flat NCHW-memory regrouping mean (scale.py:12-16) evaluated on channels-last data */
+int lb_featpool_fwd(const float* x, float* y, int batch, int h, int w, int c_in, int c_out, lb_stream_t stream);
+int lb_featpool_bwd(const float* g, float* dx, int batch, int h, int w, int c_in, int c_out, lb_stream_t stream);
+/* bilinear x2, align_corners = False (scale.py:37-38) */
+int lb_upsample2x_fwd(const float* x, float* y, int batch, int h, int w, int c, lb_stream_t stream);
+int lb_upsample2x_bwd(const float* g, float* dx, int batch, int h, int w, int c, lb_stream_t stream);
+/* AvgPool 2x2 stride 2 (scale.py:40); h,w are the INPUT sizes (even) */
+int lb_avgpool2_fwd(const float* x, float* y, int batch, int h, int w, int c, lb_stream_t stream);
+int lb_avgpool2_bwd(const float* g, float* dx, int batch, int h, int w, int c, lb_stream_t stream);
+/* strided row copy dst[row*ld_dst + c] (=|+=) src[row*ld_src + c]: channel concat / slice (merge.py:15) */
+int lb_copy_rows(const float* src, int ld_src, float* dst, int ld_dst, int64_t rows, int cols, int accumulate,
+                 lb_stream_t stream);
+/* layout change at the model boundary: NCHW <-> channels-last */
+int lb_nchw_to_nhwc(const float* x, float* y, int batch, int c, int hw, lb_stream_t stream);
+int lb_nhwc_to_nchw(const float* x, float* y, int batch, int c, int hw, lb_stream_t stream);
+
+/* ---- losses                                                           libs/utils.py:133-134, libs/grad_penalty.py:1-2, main.py:149-156,616-621
+ * D step: loss = mean(hinge(d_true) + hinge(-d_fake)) + gamma*(mean(d_true) - mean(d_aug))^2.
+ * means[2] = {sum d_true, sum d_aug} over the GLOBAL batch n_global (lb_loss_sums computes the local
+ * sums; data parallel all-reduces them).  out[3] = {hinge part (local mean), penalty, 0};
+ * grads are dL/d(d_true), dL/d(d_fake), dL/d(d_aug) for a loss averaged over n_global. */
+int lb_loss_sums(const float* d_true, const float* d_aug, int n_local, double* sums, lb_stream_t stream);
+int lb_d_loss(const float* d_true, const float* d_fake, const float* d_aug, const double* sums, int n_local,
+              double n_global, float gamma, float* out, float* g_true, float* g_fake, float* g_aug,
+              lb_stream_t stream);
+/* G step: loss = mean(hinge(d_fake)); out[1]; grad dL/d(d_fake) */
+int lb_g_loss(const float* d_fake, int n_local, double n_global, float* out, float* g_fake, lb_stream_t stream);
+
+/* ---- Nadam over a flat parameter arena                                libs/nadam.py:56-87
+ * c_grad = lr*(1-mu_t)/(1-m_schedule_new), c_mom = lr*mu_{t+1}/(1-m_schedule_next),
+ * bias2 = 1 - beta2^t are computed on the host (scalars of the step counter). */
+int lb_nadam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n,
+                  float beta1, float beta2, float eps, float c_grad, float c_mom, float bias2,
+                  lb_stream_t stream);
+/* fill / scale helpers used around the step */
+int lb_fill(float* x, size_t n, float value, lb_stream_t stream);
+int lb_scale(float* x, size_t n, float factor, lb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LOCATE_B200_H */

@@ -1,0 +1,113 @@
+// Shared device helpers for the locate_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include "locate_b200.h"
+
+#define LB_SMS 148                     // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+
+extern int g_lb_launches;              // kernels launched by the library (bench.py "gpu_launches")
+
+#define LB_LAUNCH_CHECK()                                   \
+  do {                                                      \
+    ++g_lb_launches;                                        \
+    cudaError_t lb_e_ = cudaGetLastError();                 \
+    if (lb_e_ != cudaSuccess) return (int)lb_e_;            \
+  } while (0)
+
+#define LB_REQUIRE(cond) do { if (!(cond)) return LB_EINVAL; } while (0)
+
+static inline cudaStream_t lb_s(lb_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// grid for a grid-stride elementwise kernel: enough CTAs to cover n, capped at `waves` full waves
+static inline int lb_grid_1d(size_t work_items, int block, int waves = 8) {
+  size_t need = (work_items + block - 1) / block;
+  size_t cap = (size_t)LB_SMS * waves;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+
+static inline bool lb_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <typename T>
+__device__ __forceinline__ T lb_warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float lb_warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// block-wide sum; result valid in thread 0. `scratch` holds >= 32 T's.
+template <typename T>
+__device__ __forceinline__ T lb_block_sum(T v, T* scratch) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int nw = (blockDim.x * blockDim.y + 31) >> 5;
+  v = lb_warp_sum(v);
+  __syncthreads();
+  if (lane == 0) scratch[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    v = lane < nw ? scratch[lane] : T(0);
+    v = lb_warp_sum(v);
+  }
+  return v;
+}
+
+// 128-bit streaming accessors (each activation is touched once per kernel: keep it out of L1)
+__device__ __forceinline__ float4 lb_ld4(const float* p) {
+  return __ldg(reinterpret_cast<const float4*>(p));
+}
+__device__ __forceinline__ void lb_st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+// ---- RootTanh scalar math (libs/activation.py:9-36), fp32 ---------------------------------
+// tanh and sech^2 from one exp(-2|x|): exact limits, no cosh overflow (the reference's
+// 1/cosh^2 -> 0 for |x| > 44 is reproduced because e underflows to 0 there).
+__device__ __forceinline__ void lb_tanh_sech2(float x, float& th, float& sech2) {
+  const float e = __expf(-2.0f * fabsf(x));
+  const float r = __frcp_rn(1.0f + e);
+  th = tanhf(x);                       // (1-e)/(1+e) cancels for small |x|; tanhf is 2 ulp
+  sech2 = 4.0f * e * r * r;            // no cancellation for large |x| (1 - th^2 would)
+}
+__device__ __forceinline__ float lb_roottanh(float x) {   // growth == 4
+  float th, s2;
+  lb_tanh_sech2(x, th, s2);
+  return sqrtf(sqrtf(fmaf(x, x, 1.0f))) * th;
+}
+__device__ __forceinline__ float lb_roottanh_grad(float x) {   // growth == 4: q^(3/4) = q / q^(1/4)
+  float th, s2;
+  lb_tanh_sech2(x, th, s2);
+  const float q = fmaf(x, x, 1.0f);
+  const float r4 = sqrtf(sqrtf(q));
+  return (2.0f * q * s2 + x * th) * r4 / (2.0f * q);
+}
+__device__ __forceinline__ float lb_roottanh_g(float x, float inv_growth) {
+  float th, s2;
+  lb_tanh_sech2(x, th, s2);
+  return powf(fmaf(x, x, 1.0f), inv_growth) * th;
+}
+__device__ __forceinline__ float lb_roottanh_grad_g(float x, float inv_growth) {
+  // the reference's formula keeps the literal 2's of growth = 4 for every growth (activation.py:28,33)
+  float th, s2;
+  lb_tanh_sech2(x, th, s2);
+  const float q = fmaf(x, x, 1.0f);
+  return (2.0f * q * s2 + x * th) / (2.0f * powf(q, 1.0f - inv_growth));
+}
+
+// channel-column thread shape for channels-last reductions: tc lanes over channels (a divisor of C,
+// <= 256) x tp lanes over pixels.
+// `threads` = tc*tp rounded up to whole warps; lanes >= tc*tp idle but join block reductions.
+struct LbColShape { int tc, tp, threads; };
+static inline LbColShape lb_col_shape(int channels, int max_threads = 256) {
+  int tc = 1;
+  for (int d = 1; d <= max_threads && d <= channels; ++d)
+    if (channels % d == 0) tc = d;
+  int tp = max_threads / tc;
+  if (tp < 1) tp = 1;
+  return LbColShape{tc, tp, (tc * tp + 31) / 32 * 32};
+}

@@ -1,0 +1,199 @@
+// Whole-tensor normalisation ("InPlaceNorm", libs/inplace_norm.py:7-45): ONE mean and ONE unbiased
+// std over all B*C*H*W elements, then per-channel (or per-sample-per-channel) gain and per-channel bias.
+// HBM-bound.  Statistics are accumulated in double so N ~ 1e8 elements survive; the (sum, sumsq) pair
+// and the two backward scalars are exposed so data parallel can all-reduce them between phases.
+#include "common.cuh"
+
+__global__ void __launch_bounds__(256) k_norm_stats(const float* __restrict__ x, size_t n, double* __restrict__ sums, int vec) {
+  __shared__ double scratch[32];
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  double s1 = 0.0, s2 = 0.0;
+  if (vec) {
+    const size_t n4 = n >> 2;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+      const float4 v = lb_ld4(x + 4 * i);
+      s1 += (double)((v.x + v.y) + (v.z + v.w));
+      s2 += (double)(fmaf(v.x, v.x, v.y * v.y) + fmaf(v.z, v.z, v.w * v.w));
+    }
+    for (size_t i = (n4 << 2) + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+      const float v = x[i];
+      s1 += v; s2 += (double)v * v;
+    }
+  } else {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+      const float v = x[i];
+      s1 += v; s2 += (double)v * v;
+    }
+  }
+  s1 = lb_block_sum(s1, scratch);
+  s2 = lb_block_sum(s2, scratch);
+  if (threadIdx.x == 0) { atomicAdd(sums, s1); atomicAdd(sums + 1, s2); }
+}
+
+extern "C" int lb_norm_stats(const float* x, size_t n, double* sums, lb_stream_t s) {
+  LB_REQUIRE(x && sums && n > 0);
+  k_norm_stats<<<lb_grid_1d((n + 3) / 4, 256, 4), 256, 0, lb_s(s)>>>(x, n, sums, lb_aligned16(x) ? 1 : 0);
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
+
+__global__ void k_norm_finalize(const double* __restrict__ sums, double n, float* __restrict__ stats) {
+  const double mean = sums[0] / n;
+  double var = (sums[1] - sums[0] * mean) / (n - 1.0);      // unbiased, torch.std default
+  if (var < 0.0) var = 0.0;
+  const double sd = sqrt(var);
+  stats[0] = (float)mean;
+  stats[1] = (float)sd;
+  stats[2] = (float)(1.0 / sd);                             // no eps in the reference: inf if sd == 0
+  stats[3] = (float)n;
+}
+extern "C" int lb_norm_finalize(const double* sums, double n_total, float* stats, lb_stream_t s) {
+  LB_REQUIRE(sums && stats && n_total > 1.0);
+  k_norm_finalize<<<1, 1, 0, lb_s(s)>>>(sums, n_total, stats);
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
+
+// y = (x - mean) * gain[b?,c] * rstd + bias[c]; one thread = 4 consecutive channels of one pixel
+__global__ void __launch_bounds__(256) k_norm_apply4(const float* __restrict__ x, const float* __restrict__ stats,
+                                                    const float* __restrict__ gain, int gain_bs, const float* __restrict__ bias,
+                                                    float* __restrict__ y, size_t n4, int pc4, int c4) {
+  const float mean = __ldg(stats), rstd = __ldg(stats + 2);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const size_t b = i / (size_t)pc4;
+    const int c = (int)(i % (size_t)c4) * 4;
+    const float4 v = lb_ld4(x + 4 * i);
+    const float4 gn = lb_ld4(gain + b * gain_bs + c);
+    const float4 bs = lb_ld4(bias + c);
+    float4 r;
+    r.x = fmaf((v.x - mean) * rstd, gn.x, bs.x);
+    r.y = fmaf((v.y - mean) * rstd, gn.y, bs.y);
+    r.z = fmaf((v.z - mean) * rstd, gn.z, bs.z);
+    r.w = fmaf((v.w - mean) * rstd, gn.w, bs.w);
+    lb_st4(y + 4 * i, r);
+  }
+}
+__global__ void __launch_bounds__(256) k_norm_apply1(const float* __restrict__ x, const float* __restrict__ stats,
+                                                    const float* __restrict__ gain, int gain_bs, const float* __restrict__ bias,
+                                                    float* __restrict__ y, size_t n, int pc, int channels) {
+  const float mean = __ldg(stats), rstd = __ldg(stats + 2);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const size_t b = i / (size_t)pc;
+    const int c = (int)(i % (size_t)channels);
+    y[i] = fmaf((x[i] - mean) * rstd, __ldg(gain + b * gain_bs + c), __ldg(bias + c));
+  }
+}
+
+extern "C" int lb_norm_apply(const float* x, const float* stats, const float* gain, int gain_batch_stride, const float* bias,
+                             float* y, int batch, int pixels, int channels, lb_stream_t s) {
+  LB_REQUIRE(x && stats && gain && bias && y && batch > 0 && pixels > 0 && channels > 0);
+  LB_REQUIRE(gain_batch_stride == 0 || gain_batch_stride == channels);
+  const size_t n = (size_t)batch * pixels * channels;
+  if ((channels & 3) == 0 && lb_aligned16(x) && lb_aligned16(y) && lb_aligned16(gain) && lb_aligned16(bias)) {
+    k_norm_apply4<<<lb_grid_1d(n / 4, 256), 256, 0, lb_s(s)>>>(x, stats, gain, gain_batch_stride, bias, y, n / 4,
+                                                              pixels * channels / 4, channels / 4);
+  } else {
+    k_norm_apply1<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(x, stats, gain, gain_batch_stride, bias, y, n, pixels * channels, channels);
+  }
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
+
+// backward phase 1: per-(b,c) column sums over pixels.  CTA = (pixel chunk, b); thread = (channel lane, pixel lane)
+__global__ void k_norm_bwd_reduce(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ stats,
+                                  float* __restrict__ p1, float* __restrict__ p2, int pixels, int channels, int chunk, int tc, int tp) {
+  if (threadIdx.x >= tc * tp) return;
+  const float mean = __ldg(stats);
+  const int cl = threadIdx.x % tc, pl = threadIdx.x / tc;
+  const int b = blockIdx.y;
+  const int q0 = blockIdx.x * chunk, q1 = min(pixels, q0 + chunk);
+  const size_t base = (size_t)b * pixels * channels;
+  for (int c = cl; c < channels; c += tc) {
+    float a1 = 0.0f, a2 = 0.0f;
+    for (int p = q0 + pl; p < q1; p += tp) {
+      const size_t i = base + (size_t)p * channels + c;
+      const float gv = g[i];
+      a1 += gv;
+      a2 = fmaf(x[i] - mean, gv, a2);
+    }
+    atomicAdd(p1 + (size_t)b * channels + c, a1);
+    atomicAdd(p2 + (size_t)b * channels + c, a2);
+  }
+}
+extern "C" int lb_norm_bwd_reduce(const float* x, const float* g, const float* stats, float* p1, float* p2, int batch,
+                                  int pixels, int channels, lb_stream_t s) {
+  LB_REQUIRE(x && g && stats && p1 && p2 && batch > 0 && pixels > 0 && channels > 0);
+  const LbColShape sh = lb_col_shape(channels);
+  int chunks = (LB_SMS * 4 + batch - 1) / batch;
+  int chunk = (pixels + chunks - 1) / chunks;
+  if (chunk < sh.tp) chunk = sh.tp;
+  chunks = (pixels + chunk - 1) / chunk;
+  k_norm_bwd_reduce<<<dim3(chunks, batch), sh.threads, 0, lb_s(s)>>>(x, g, stats, p1, p2, pixels, channels, chunk, sh.tc, sh.tp);
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
+
+// backward phase 2 (tiny): scalars + parameter gradients.  One CTA.
+__global__ void __launch_bounds__(256) k_norm_bwd_finalize(const float* __restrict__ p1, const float* __restrict__ p2,
+                                                          const float* __restrict__ gain, int gain_bs,
+                                                          const float* __restrict__ stats, int batch, int channels,
+                                                          float* __restrict__ dgain, float* __restrict__ dbias,
+                                                          double* __restrict__ sout) {
+  __shared__ double scratch[32];
+  const float rstd = stats[2];
+  double s1 = 0.0, s2 = 0.0;
+  for (int c = threadIdx.x; c < channels; c += blockDim.x) {
+    float db = 0.0f, dg_shared = 0.0f;
+    for (int b = 0; b < batch; ++b) {
+      const float a1 = p1[(size_t)b * channels + c], a2 = p2[(size_t)b * channels + c];
+      const float gn = gain[(size_t)b * gain_bs + c];
+      s1 += (double)gn * a1;
+      s2 += (double)gn * a2;
+      db += a1;
+      if (gain_bs) dgain[(size_t)b * channels + c] += a2 * rstd; else dg_shared += a2;
+    }
+    if (dbias) dbias[c] += db;
+    if (!gain_bs && dgain) dgain[c] += dg_shared * rstd;
+  }
+  s1 = lb_block_sum(s1, scratch);
+  s2 = lb_block_sum(s2, scratch);
+  if (threadIdx.x == 0) { sout[0] = s1; sout[1] = s2; }
+}
+extern "C" int lb_norm_bwd_finalize(const float* p1, const float* p2, const float* gain, int gain_batch_stride,
+                                    const float* stats, int batch, int channels, float* dgain, float* dbias, double* sout,
+                                    lb_stream_t s) {
+  LB_REQUIRE(p1 && p2 && gain && stats && sout && batch > 0 && channels > 0);
+  LB_REQUIRE(gain_batch_stride == 0 || (gain_batch_stride == channels && dgain));
+  k_norm_bwd_finalize<<<1, 256, 0, lb_s(s)>>>(p1, p2, gain, gain_batch_stride, stats, batch, channels, dgain, dbias, sout);
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
+
+// backward phase 3: dx = gain*g*rstd - s0*rstd/N - s1*(x-mean)*rstd^3/(N-1)
+__global__ void __launch_bounds__(256) k_norm_bwd_apply(const float* __restrict__ x, const float* __restrict__ g,
+                                                       const float* __restrict__ stats, const float* __restrict__ gain,
+                                                       int gain_bs, const double* __restrict__ sc, float* __restrict__ dx,
+                                                       size_t n, int pc, int channels) {
+  const float mean = __ldg(stats), rstd = __ldg(stats + 2);
+  const double nn = (double)__ldg(stats + 3);
+  const double r = (double)rstd;
+  const float k0 = (float)(sc[0] * r / nn);
+  const float k1 = (float)(sc[1] * r * r * r / (nn - 1.0));
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const size_t b = i / (size_t)pc;
+    const int c = (int)(i % (size_t)channels);
+    const float gn = __ldg(gain + b * gain_bs + c);
+    dx[i] = fmaf(gn * rstd, g[i], -k0) - k1 * (x[i] - mean);
+  }
+}
+extern "C" int lb_norm_bwd_apply(const float* x, const float* g, const float* stats, const float* gain, int gain_batch_stride,
+                                 const double* sc, float* dx, int batch, int pixels, int channels, lb_stream_t s) {
+  LB_REQUIRE(x && g && stats && gain && sc && dx && batch > 0 && pixels > 0 && channels > 0);
+  const size_t n = (size_t)batch * pixels * channels;
+  k_norm_bwd_apply<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(x, g, stats, gain, gain_batch_stride, sc, dx, n, pixels * channels, channels);
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}

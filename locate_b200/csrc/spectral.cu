@@ -1,0 +1,110 @@
+// Spectral norm (libs/spectral_norm.py:21-32): one power iteration per forward call, and the weight
+// gradient epilogue that folds d(1/sigma)/dW back in.  Two passes over W per forward, HBM-bound:
+//   pass 1  t = W^T u  (column sums weighted by u)     -> v = t / (|t| + eps)
+//   pass 2  s = W v    (row dot products)              -> u = s / (|s| + eps), sigma = u.s = |s|^2/(|s|+eps)
+// The GEMMs read W_bar untouched and apply 1/sigma in their epilogue (conv(x, W/sigma) == conv(x, W)/sigma).
+#include "common.cuh"
+
+#define SN_EPS 1e-12f
+
+// t[j] += sum_{i in row split} W[i][j] * u[i];   grid = (col tiles of 256, row splits)
+__global__ void __launch_bounds__(256) k_sn_wt_u(const float* __restrict__ w, const float* __restrict__ u, float* __restrict__ t,
+                                                int height, int width, int rows_per_split) {
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= width) return;
+  const int i0 = blockIdx.y * rows_per_split, i1 = min(height, i0 + rows_per_split);
+  float acc = 0.0f;
+  for (int i = i0; i < i1; ++i) acc = fmaf(w[(size_t)i * width + j], __ldg(u + i), acc);
+  atomicAdd(t + j, acc);
+}
+
+// dst = src / (|src| + eps); also writes |src| to norm_out if non-null.  One CTA.
+__global__ void __launch_bounds__(1024) k_sn_normalize(const float* __restrict__ src, float* __restrict__ dst, int n,
+                                                      float* __restrict__ sigma_out) {
+  __shared__ float scratch[32];
+  __shared__ float s_norm;
+  float acc = 0.0f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { const float v = src[i]; acc = fmaf(v, v, acc); }
+  acc = lb_block_sum(acc, scratch);
+  if (threadIdx.x == 0) s_norm = sqrtf(acc);
+  __syncthreads();
+  const float nrm = s_norm;
+  const float inv = 1.0f / (nrm + SN_EPS);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i] * inv;
+  if (sigma_out && threadIdx.x == 0) {
+    const float sigma = nrm * nrm * inv;                 // u.(W v) with u = s/(|s|+eps)
+    sigma_out[0] = sigma;
+    sigma_out[1] = 1.0f / sigma;
+  }
+}
+
+// s[i] = sum_j W[i][j] v[j]; one warp per row (rows are contiguous)
+__global__ void __launch_bounds__(256) k_sn_w_v(const float* __restrict__ w, const float* __restrict__ v, float* __restrict__ sv,
+                                               int height, int width) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= height) return;
+  const float* wr = w + (size_t)row * width;
+  float acc = 0.0f;
+  for (int j = lane; j < width; j += 32) acc = fmaf(wr[j], __ldg(v + j), acc);
+  acc = lb_warp_sum(acc);
+  if (lane == 0) sv[row] = acc;
+}
+
+extern "C" int lb_sn_power_iter(const float* w, int height, int width, float* u, float* v, float* sigma_out, float* work,
+                                lb_stream_t s) {
+  LB_REQUIRE(w && u && v && sigma_out && work && height > 0 && width > 0);
+  float* t = work;            // [width]
+  float* sv = work + width;   // [height]
+  cudaError_t e = cudaMemsetAsync(t, 0, sizeof(float) * width, lb_s(s));
+  if (e != cudaSuccess) return (int)e;
+  const int col_tiles = (width + 255) / 256;
+  int splits = (LB_SMS * 2 + col_tiles - 1) / col_tiles;
+  if (splits > height) splits = height;
+  if (splits < 1) splits = 1;
+  const int rps = (height + splits - 1) / splits;
+  splits = (height + rps - 1) / rps;
+  k_sn_wt_u<<<dim3(col_tiles, splits), 256, 0, lb_s(s)>>>(w, u, t, height, width, rps);
+  LB_LAUNCH_CHECK();
+  k_sn_normalize<<<1, 1024, 0, lb_s(s)>>>(t, v, width, nullptr);
+  LB_LAUNCH_CHECK();
+  k_sn_w_v<<<(height + 7) / 8, 256, 0, lb_s(s)>>>(w, v, sv, height, width);
+  LB_LAUNCH_CHECK();
+  k_sn_normalize<<<1, 1024, 0, lb_s(s)>>>(sv, u, height, sigma_out);
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
+
+// ---- weight gradient epilogue --------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_sn_dot(const float* __restrict__ a, const float* __restrict__ b, size_t n, double* __restrict__ out) {
+  __shared__ double scratch[32];
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  double acc = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) acc += (double)(a[i] * b[i]);
+  acc = lb_block_sum(acc, scratch);
+  if (threadIdx.x == 0) atomicAdd(out, acc);
+}
+// grad[i][j] += dwn[i][j]/sigma - dot/sigma^2 * u[i] v[j]
+__global__ void __launch_bounds__(256) k_sn_wgrad(const float* __restrict__ dwn, const float* __restrict__ u, const float* __restrict__ v,
+                                                 const float* __restrict__ sigma, const double* __restrict__ dot,
+                                                 float* __restrict__ grad, size_t n, int width) {
+  const float inv = __ldg(sigma + 1);
+  const float coef = (float)(dot[0] * (double)inv * (double)inv);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+    const size_t i = k / width;
+    const int j = (int)(k % width);
+    grad[k] += fmaf(dwn[k], inv, -coef * __ldg(u + i) * __ldg(v + j));
+  }
+}
+extern "C" int lb_sn_weight_grad(const float* dwn, const float* w, const float* u, const float* v, const float* sigma,
+                                 float* grad, int height, int width, double* work, lb_stream_t s) {
+  LB_REQUIRE(dwn && w && u && v && sigma && grad && work && height > 0 && width > 0);
+  const size_t n = (size_t)height * width;
+  cudaError_t e = cudaMemsetAsync(work, 0, sizeof(double) * 2, lb_s(s));
+  if (e != cudaSuccess) return (int)e;
+  k_sn_dot<<<lb_grid_1d(n, 256, 2), 256, 0, lb_s(s)>>>(dwn, w, n, work);
+  LB_LAUNCH_CHECK();
+  k_sn_wgrad<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(dwn, u, v, sigma, work, grad, n, width);
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}

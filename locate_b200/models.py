@@ -1,0 +1,88 @@
+"""Generator / Discriminator with the reference's constructors and forward signatures
+(libs/models.py:12-97).  Pure graph assembly over locate_b200.layers; state_dict keys equal the
+reference's, so its checkpoints (netG.torch / netD.torch, main.py:235-236) load unchanged."""
+import torch
+from torch import nn
+
+from . import ops
+from .config import CFG
+from .layers import BlockBlock, DeepResidualConv, ResModule, Scale, identity
+
+
+def quadnorm(number: int):
+    return number // 4 * 4
+
+
+def generator_feature_list():
+    """[Z, f(L-2), ..., f(0)] with f(i) = quadnorm(GEN_FEATURES * FACTOR**(i - (L-1)))  (models.py:16-22,37-52)."""
+    clayers = CFG.LAYERS - 1
+    feats = [quadnorm(int(CFG.GEN_FEATURES * CFG.FACTOR ** (i - clayers))) for i in range(clayers - 1, -1, -1)]
+    return [CFG.INPUT_VECTOR_Z] + feats
+
+
+def discriminator_feature_list():
+    """[d(0), ..., d(L-2), d(L-2)] with d(i) = quadnorm(DIS_FEATURES * FACTOR**(i + 1 - (L-1)))  (models.py:25-31,72-78)."""
+    n = CFG.LAYERS - 1
+    feats = [quadnorm(int(CFG.DIS_FEATURES * CFG.FACTOR ** ((i + 1) - n))) for i in range(n)]
+    return feats + [feats[-1]]
+
+
+class _ArenaModel(nn.Module):
+    """zero_grad() keeps the optimizer's flat gradient arena attached (one fill kernel) instead of
+    dropping every .grad to None."""
+
+    _lb_optimizer = None
+
+    def zero_grad(self, set_to_none=True):
+        opt = self.__dict__.get("_lb_optimizer")
+        if opt is not None:
+            opt.zero_grad()
+        else:
+            super().zero_grad(set_to_none=set_to_none)
+
+
+class Generator(_ArenaModel):
+    def __init__(self):
+        super().__init__()
+        if CFG.START_LAYER >= 1:
+            raise NotImplementedError("START_LAYER >= 1 is SURVEY.md 'next' row N3")
+        if CFG.G_STRIDE != 2:
+            raise NotImplementedError("G_STRIDE != 2")
+        strides = [2] * (CFG.LAYERS - 1)
+        feature_list = generator_feature_list()
+        self.input_block = identity
+        self.conv_block = BlockBlock(len(strides), 2, feature_list, strides, True, True)
+        self.out_conv = DeepResidualConv(self.conv_block.out_features, 3, False, 1, False, 2, 1)
+        self.g_in = feature_list[0]
+        self.noise = torch.randn(1, CFG.INPUT_VECTOR_Z, 2, 2)      # plain attribute, not in state_dict (models.py:59)
+
+    def _apply(self, fn, *args, **kwargs):
+        super()._apply(fn, *args, **kwargs)
+        self.noise = fn(self.noise)
+        return self
+
+    def forward(self, function_input):
+        expanded_noise = self.noise.expand(function_input.size(0), -1, -1, -1)
+        conv_out = self.input_block(expanded_noise)
+        conv_out = self.conv_block(conv_out, function_input)
+        conv_out = self.out_conv(conv_out)
+        return ops.TanhFn.apply(conv_out)
+
+
+class Discriminator(_ArenaModel):
+    def __init__(self):
+        super().__init__()
+        if CFG.END_LAYER != 1:
+            raise NotImplementedError("END_LAYER != 1")
+        if CFG.D_STRIDE != 2:
+            raise NotImplementedError("D_STRIDE != 2")
+        strides = [2] * (CFG.LAYERS - 1)
+        feature_list = discriminator_feature_list()
+        first = feature_list[0]
+        cat_module = ResModule(Scale(3, first, 2, False), DeepResidualConv(3, first, False, 2, False, 2, 1))
+        block_block = BlockBlock(len(strides), CFG.IMAGE_SIZE // 2, feature_list, strides, False)
+        tail = DeepResidualConv(block_block.out_features, 1, False, 1, False, 2, 1)
+        self.main = nn.Sequential(cat_module, block_block, tail)
+
+    def forward(self, function_input):
+        return self.main(function_input)

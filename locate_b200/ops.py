@@ -1,0 +1,539 @@
+"""torch.autograd.Function wrappers around the C-ABI kernels (include/locate_b200.h).
+
+Conventions
+ * activations are fp32 CUDA tensors, logical [B,C,H,W] with channels-last strides (physically
+   [B][H][W][C]); vectors are [B,C].  Anything else is converted once at the boundary.
+ * parameter gradients: every kernel accumulates (+=).  If the parameter carries an arena view
+   (`param._lb_grad`, attached by locate_b200.optim.Nadam) the kernel adds straight into it and
+   autograd receives None for that input; otherwise a fresh zero tensor is returned to autograd.
+ * data-parallel hooks (global norm statistics) come from locate_b200.dist.
+
+Each Function names the reference lines whose arithmetic the kernels replace.
+"""
+import math
+
+import torch
+
+from . import _lib, dist
+from ._lib import ConvGeom, call, ptr
+
+_CL = torch.channels_last
+
+
+def _as_act(t):
+    """fp32, CUDA, channels-last (4-D) or contiguous (other ranks)."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    if t.dim() == 4:
+        return t if t.is_contiguous(memory_format=_CL) else _to_channels_last(t)
+    return t.contiguous()
+
+
+def _to_channels_last(t):
+    """NCHW-contiguous -> channels-last through lb_nchw_to_nhwc (no torch copy kernel)."""
+    if not t.is_contiguous():
+        t = t.contiguous()
+    b, c, h, w = t.shape
+    out = torch.empty_strided((b, c, h, w), (h * w * c, 1, w * c, c), dtype=t.dtype, device=t.device)
+    call("lb_nchw_to_nhwc", ptr(t), ptr(out), b, c, h * w)
+    return out
+
+
+def to_nchw(t):
+    """channels-last -> NCHW-contiguous copy (model boundary, e.g. image dumps)."""
+    t = _as_act(t)
+    b, c, h, w = t.shape
+    out = torch.empty((b, c, h, w), dtype=t.dtype, device=t.device)
+    call("lb_nhwc_to_nchw", ptr(t), ptr(out), b, c, h * w)
+    return out
+
+
+def _new_act(shape, like):
+    if len(shape) == 4:
+        b, c, h, w = shape
+        return torch.empty_strided((b, c, h, w), (h * w * c, 1, w * c, c), dtype=torch.float32, device=like.device)
+    return torch.empty(shape, dtype=torch.float32, device=like.device)
+
+
+def _bpc(t):
+    """(batch, pixels, channels) of an activation."""
+    if t.dim() == 4:
+        return t.shape[0], t.shape[2] * t.shape[3], t.shape[1]
+    if t.dim() == 3:           # [B, C, L] handled by callers via reshape to 4-D
+        raise ValueError("3-D activations must be viewed as [B,C,L,1] first")
+    return t.shape[0], 1, t.shape[1]
+
+
+def _grad_sink(param):
+    """(buffer the kernels accumulate into, value to hand back to autograd)."""
+    arena = getattr(param, "_lb_grad", None)
+    if arena is not None:
+        if param.grad is None:
+            param.grad = arena
+        return arena, None
+    fresh = torch.zeros_like(param, memory_format=torch.contiguous_format)
+    return fresh, fresh
+
+
+# ------------------------------------------------------------------------------------------
+# activations
+# ------------------------------------------------------------------------------------------
+class RootTanhFn(torch.autograd.Function):
+    """libs/activation.py:9-36."""
+
+    @staticmethod
+    def forward(ctx, x, growth):
+        x = _as_act(x)
+        y = torch.empty_like(x)
+        call("lb_roottanh_fwd", ptr(x), ptr(y), x.numel(), growth)
+        ctx.save_for_backward(x)
+        ctx.growth = growth
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        g = _match(g, x)
+        dx = torch.empty_like(x)
+        call("lb_roottanh_bwd", ptr(x), ptr(g), ptr(dx), x.numel(), ctx.growth)
+        return dx, None
+
+
+class TanhFn(torch.autograd.Function):
+    """libs/models.py:66."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _as_act(x)
+        y = torch.empty_like(x)
+        call("lb_tanh_fwd", ptr(x), ptr(y), x.numel())
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (y,) = ctx.saved_tensors
+        g = _match(g, y)
+        dx = torch.empty_like(y)
+        call("lb_tanh_bwd", ptr(y), ptr(g), ptr(dx), y.numel())
+        return dx
+
+
+class HingeFn(torch.autograd.Function):
+    """libs/utils.py:133-134."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        call("lb_hinge_fwd", ptr(x), ptr(y), x.numel())
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        g = g.contiguous()
+        dx = torch.empty_like(x)
+        call("lb_hinge_bwd", ptr(x), ptr(g), ptr(dx), x.numel())
+        return dx
+
+
+def _match(g, ref):
+    """Bring an incoming gradient to the layout of `ref` (same logical shape)."""
+    if g.shape != ref.shape:
+        g = g.expand_as(ref)
+    if g.stride() != ref.stride() or g.dtype != torch.float32:
+        g = _as_act(g.float())
+        if g.stride() != ref.stride():          # size-1 dims make strides ambiguous; data is identical
+            g = g.as_strided(ref.shape, ref.stride())
+    return g
+
+
+# ------------------------------------------------------------------------------------------
+# whole-tensor norm
+# ------------------------------------------------------------------------------------------
+class WholeNormFn(torch.autograd.Function):
+    """libs/inplace_norm.py:7-45 (MeanSubMulDivAdd + x.std() folded into one op).
+
+    gain: [1,C,1,1] parameter or [B,C,1,1] style tensor; bias: [1,C,1,1]."""
+
+    @staticmethod
+    def forward(ctx, x, gain, bias):
+        x = _as_act(x)
+        b, p, c = _bpc(x)
+        per_sample = gain.shape[0] != 1          # [B,C,1,1] style gain (B == 1 degenerates to the shared form)
+        if gain.numel() != (b if per_sample else 1) * c or bias.numel() != c:
+            raise ValueError(f"norm: gain {tuple(gain.shape)} / bias {tuple(bias.shape)} do not fit {tuple(x.shape)}")
+        gain_c = gain.contiguous()
+        sums = torch.zeros(2, dtype=torch.float64, device=x.device)
+        call("lb_norm_stats", ptr(x), x.numel(), ptr(sums))
+        n_total = float(x.numel()) * dist.all_reduce_sum_(sums)
+        stats = torch.empty(4, dtype=torch.float32, device=x.device)
+        call("lb_norm_finalize", ptr(sums), n_total, ptr(stats))
+        y = torch.empty_like(x)
+        call("lb_norm_apply", ptr(x), ptr(stats), ptr(gain_c), c if per_sample else 0, ptr(bias), ptr(y), b, p, c)
+        ctx.save_for_backward(x, gain_c, stats)
+        ctx.per_sample = per_sample
+        ctx.gain_param, ctx.bias_param = gain, bias
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, gain, stats = ctx.saved_tensors
+        g = _match(g, x)
+        b, p, c = _bpc(x)
+        part = torch.zeros((2, b, c), dtype=torch.float32, device=x.device)
+        call("lb_norm_bwd_reduce", ptr(x), ptr(g), ptr(stats), ptr(part[0]), ptr(part[1]), b, p, c)
+        need_gain, need_bias = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        if ctx.per_sample:
+            dgain = torch.zeros_like(gain)           # the kernel always writes the per-sample slots
+            dgain_ret = dgain.view(ctx.gain_param.shape) if need_gain else None
+        elif need_gain:
+            dgain, dgain_ret = _grad_sink(ctx.gain_param)
+        else:
+            dgain, dgain_ret = None, None
+        if need_bias:
+            dbias, dbias_ret = _grad_sink(ctx.bias_param)
+        else:
+            dbias, dbias_ret = None, None
+        sc = torch.empty(2, dtype=torch.float64, device=x.device)
+        call("lb_norm_bwd_finalize", ptr(part[0]), ptr(part[1]), ptr(gain), c if ctx.per_sample else 0, ptr(stats), b, c,
+             ptr(dgain), ptr(dbias), ptr(sc))
+        dist.all_reduce_sum_(sc)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            call("lb_norm_bwd_apply", ptr(x), ptr(g), ptr(stats), ptr(gain), c if ctx.per_sample else 0, ptr(sc), ptr(dx), b, p, c)
+        return dx, dgain_ret, dbias_ret
+
+
+# ------------------------------------------------------------------------------------------
+# gated residual
+# ------------------------------------------------------------------------------------------
+class GateFn(torch.autograd.Function):
+    """libs/merge.py:19-39.  y is full-shape, or a [B,C,1,1] gate broadcast over pixels."""
+
+    @staticmethod
+    def forward(ctx, x, y, gamma, strict_reference):
+        x = _as_act(x)
+        b, p, c = _bpc(x)
+        bcast = y.shape != x.shape
+        if bcast:
+            if tuple(y.shape[:2]) != (b, c) or y.numel() != b * c:
+                raise ValueError(f"gate: cannot broadcast {tuple(y.shape)} over {tuple(x.shape)}")
+            y = y.contiguous()
+        else:
+            y = _match(y, x)
+        out = torch.empty_like(x)
+        call("lb_gate_fwd", ptr(x), ptr(y), ptr(gamma), ptr(out), b, p, c, int(bcast))
+        ctx.save_for_backward(x, y, gamma)
+        ctx.bcast, ctx.strict, ctx.gamma_param = bcast, strict_reference, gamma
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, y, gamma = ctx.saved_tensors
+        g = _match(g, x)
+        b, p, c = _bpc(x)
+        dx = torch.empty_like(x)
+        dy = torch.zeros_like(y) if ctx.bcast else torch.empty_like(y)
+        if ctx.needs_input_grad[2]:
+            dgamma, dgamma_ret = _grad_sink(ctx.gamma_param)
+        else:
+            dgamma, dgamma_ret = None, None
+        call("lb_gate_bwd", ptr(x), ptr(y), ptr(gamma), ptr(g), ptr(dx), ptr(dy), ptr(dgamma), b, p, c, int(ctx.bcast),
+             int(ctx.strict))
+        return dx, dy, dgamma_ret, None
+
+
+# ------------------------------------------------------------------------------------------
+# spectral-normed convolution family
+# ------------------------------------------------------------------------------------------
+class ConvSpec:
+    """Static description of one spectral-normed linear map.
+
+    kind: 'conv' (weight [Cout,Cin,kh,kw]), 'convT' (weight [Cin,Cout,kh,kw]), 'linear'
+    (weight [out,in]), 'conv1d' (weight [Cout,Cin,1] applied per pixel)."""
+
+    def __init__(self, kind, cin, cout, kh=1, kw=1, stride=1, pad=0):
+        self.kind, self.cin, self.cout = kind, cin, cout
+        self.kh, self.kw, self.stride, self.pad = kh, kw, stride, pad
+
+    def out_hw(self, h, w):
+        if self.kind == "convT":
+            return (h - 1) * self.stride - 2 * self.pad + self.kh, (w - 1) * self.stride - 2 * self.pad + self.kw
+        return (h + 2 * self.pad - self.kh) // self.stride + 1, (w + 2 * self.pad - self.kw) // self.stride + 1
+
+    @property
+    def sn_shape(self):
+        """(height, width) of the matrix view spectral norm iterates on (spectral_norm.py:26)."""
+        taps = self.kh * self.kw
+        if self.kind == "convT":
+            return self.cin, self.cout * taps
+        return self.cout, self.cin * taps
+
+    # (w_sk, w_sn, w_sty, w_stx) of W(tap,k,n) for the three GEMMs
+    def strides_fwd(self):
+        t = self.kh * self.kw
+        if self.kind == "convT":
+            return self.cout * t, t, self.kw, 1          # k = cin, n = cout
+        return t, self.cin * t, self.kw, 1               # k = cin, n = cout
+
+    def strides_dgrad(self):
+        t = self.kh * self.kw
+        if self.kind == "convT":
+            return t, self.cout * t, self.kw, 1          # k = cout, n = cin
+        return self.cin * t, t, self.kw, 1               # k = cout, n = cin
+
+
+def _geom(batch, ih, iw, ic, oh, ow, oc, spec, mode, ld_in, ld_out, strides):
+    g = ConvGeom()
+    g.batch, g.in_h, g.in_w, g.in_c = batch, ih, iw, ic
+    g.out_h, g.out_w, g.out_c = oh, ow, oc
+    g.kh, g.kw, g.stride, g.pad, g.mode = spec.kh, spec.kw, spec.stride, spec.pad, mode
+    g.ld_in, g.ld_out = ld_in, ld_out
+    g.w_sk, g.w_sn, g.w_sty, g.w_stx = strides
+    return g
+
+
+def power_iterate(w_bar, u, v, spec):
+    """One in-place power iteration (spectral_norm.py:21-32); returns the [sigma, 1/sigma] buffer."""
+    height, width = spec.sn_shape
+    sigma = torch.empty(2, dtype=torch.float32, device=w_bar.device)
+    work = torch.empty(height + width + 4, dtype=torch.float32, device=w_bar.device)
+    call("lb_sn_power_iter", ptr(w_bar), height, width, ptr(u), ptr(v), ptr(sigma), ptr(work))
+    return sigma
+
+
+class SNConvFn(torch.autograd.Function):
+    """y = conv(x, W_bar)/sigma (+bias) with the power iteration run inside, i.e.
+    SpectralNorm.forward (spectral_norm.py:57-59) around Conv2d / ConvTranspose2d / Conv1d(k=1) /
+    Linear (conv.py:14-20, attention.py:26-34,44-46, scale.py:25-34, linear.py:10).
+
+    If `cat_input` the result is cat([x, y], channels) (CatModule with an identity residual,
+    merge.py:10-16): the GEMM writes straight into the channel slice of the wider output."""
+
+    @staticmethod
+    def forward(ctx, x, w_bar, u, v, bias, spec, cat_input):
+        x = _as_act(x)
+        is_vec = x.dim() == 2
+        if is_vec:
+            b, h, w_, cin = x.shape[0], 1, 1, x.shape[1]
+        else:
+            b, cin, h, w_ = x.shape
+        if cin != spec.cin:
+            raise ValueError(f"expected {spec.cin} input channels, got {cin}")
+        sigma = power_iterate(w_bar, u.data, v.data, spec)
+        oh, ow = spec.out_hw(h, w_)
+        ctot = spec.cout + (cin if cat_input else 0)
+        out = _new_act((b, ctot) if is_vec else (b, ctot, oh, ow), x)
+        mode = 1 if spec.kind == "convT" else 0
+        g = _geom(b, h, w_, cin, oh, ow, spec.cout, spec, mode, cin, ctot, spec.strides_fwd())
+        off = cin * 4 if cat_input else 0
+        call("lb_conv_gemm", ptr(x), ptr(w_bar), sigma.data_ptr() + 4, ptr(bias), out.data_ptr() + off, g)
+        if cat_input:
+            if (oh, ow) != (h, w_):
+                raise ValueError("cat_input needs a size-preserving conv")
+            call("lb_copy_rows", ptr(x), cin, ptr(out), ctot, b * h * w_, cin, 0)
+        ctx.save_for_backward(x, w_bar, sigma)
+        ctx.u, ctx.v = u, v                      # LIVE u/v: the reference's backward reads them at backward time
+        ctx.bias_param, ctx.w_param = bias, w_bar
+        ctx.spec, ctx.cat_input, ctx.dims = spec, cat_input, (b, h, w_, cin, oh, ow, ctot, is_vec)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, w_bar, sigma = ctx.saved_tensors
+        spec = ctx.spec
+        b, h, w_, cin, oh, ow, ctot, is_vec = ctx.dims
+        gout = _as_act(gout)
+        off = cin * 4 if ctx.cat_input else 0
+        gy_ptr = gout.data_ptr() + off            # gradient of the conv output slice, row stride ctot
+        dx = dw_ret = dbias_ret = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            mode = 0 if spec.kind == "convT" else 1
+            g = _geom(b, oh, ow, spec.cout, h, w_, cin, spec, mode, ctot, cin, spec.strides_dgrad())
+            call("lb_conv_gemm", gy_ptr, ptr(w_bar), sigma.data_ptr() + 4, None, ptr(dx), g)
+            if ctx.cat_input:
+                call("lb_copy_rows", ptr(gout), ctot, ptr(dx), cin, b * h * w_, cin, 1)
+        if ctx.needs_input_grad[1]:
+            dwn = torch.zeros_like(w_bar, memory_format=torch.contiguous_format)
+            t = spec.kh * spec.kw
+            if spec.kind == "convT":
+                # dense = x (cin), gathered = dy (cout): dw[ci][co][ty][tx]
+                g = _geom(b, oh, ow, spec.cout, h, w_, cin, spec, 0, ctot, cin, (t, spec.cout * t, spec.kw, 1))
+                call("lb_conv_wgrad", gy_ptr, ptr(x), ptr(dwn), g)
+            else:
+                # dense = dy (cout), gathered = x (cin): dw[co][ci][ty][tx]
+                g = _geom(b, h, w_, cin, oh, ow, spec.cout, spec, 0, cin, ctot, (t, cin * t, spec.kw, 1))
+                call("lb_conv_wgrad", ptr(x), gy_ptr, ptr(dwn), g)
+            grad_w, dw_ret = _grad_sink(ctx.w_param)
+            height, width = spec.sn_shape
+            work = torch.empty(2, dtype=torch.float64, device=x.device)
+            call("lb_sn_weight_grad", ptr(dwn), ptr(w_bar), ptr(ctx.u.data), ptr(ctx.v.data), ptr(sigma), ptr(grad_w),
+                 height, width, ptr(work))
+        if ctx.bias_param is not None and ctx.needs_input_grad[4]:
+            dbias, dbias_ret = _grad_sink(ctx.bias_param)
+            call("lb_colsum", gy_ptr, b * oh * ow, spec.cout, ctot, ptr(dbias))
+        return dx, dw_ret, None, None, dbias_ret, None, None
+
+
+# ------------------------------------------------------------------------------------------
+# softmax
+# ------------------------------------------------------------------------------------------
+class SoftmaxPixelsFn(torch.autograd.Function):
+    """Softmax over HW for every (b,c) (attention.py:47 on the [B,F,HW] view)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _as_act(x)
+        b, p, c = _bpc(x)
+        y = torch.empty_like(x)
+        call("lb_softmax_pixels_fwd", ptr(x), ptr(y), b, p, c)
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (y,) = ctx.saved_tensors
+        g = _match(g, y)
+        b, p, c = _bpc(y)
+        dx = torch.empty_like(y)
+        call("lb_softmax_pixels_bwd", ptr(y), ptr(g), ptr(dx), b, p, c)
+        return dx
+
+
+class SoftmaxChannelsFn(torch.autograd.Function):
+    """Softmax(dim=1) (attention.py:35).  Pixel count is 1 on the reference's path ([B,F,1,1])."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _as_act(x)
+        b, p, c = _bpc(x)
+        y = torch.empty_like(x)
+        call("lb_softmax_rows_fwd", ptr(x), ptr(y), b * p, c)
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (y,) = ctx.saved_tensors
+        g = _match(g, y)
+        b, p, c = _bpc(y)
+        dx = torch.empty_like(y)
+        call("lb_softmax_rows_bwd", ptr(y), ptr(g), ptr(dx), b * p, c)
+        return dx
+
+
+# ------------------------------------------------------------------------------------------
+# skip-path resampling
+# ------------------------------------------------------------------------------------------
+class FeaturePoolFn(torch.autograd.Function):
+    """libs/scale.py:12-16."""
+
+    @staticmethod
+    def forward(ctx, x, c_out):
+        x = _as_act(x)
+        b, c, h, w = x.shape
+        y = _new_act((b, c_out, h, w), x)
+        call("lb_featpool_fwd", ptr(x), ptr(y), b, h, w, c, c_out)
+        ctx.dims = (b, c, h, w, c_out)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        b, c, h, w, c_out = ctx.dims
+        g = _as_act(g)
+        dx = _new_act((b, c, h, w), g)
+        call("lb_featpool_bwd", ptr(g), ptr(dx), b, h, w, c, c_out)
+        return dx, None
+
+
+class Upsample2xFn(torch.autograd.Function):
+    """nn.Upsample(mode='bilinear', scale_factor=2, align_corners=False) (scale.py:37-38)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _as_act(x)
+        b, c, h, w = x.shape
+        y = _new_act((b, c, 2 * h, 2 * w), x)
+        call("lb_upsample2x_fwd", ptr(x), ptr(y), b, h, w, c)
+        ctx.dims = (b, c, h, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        b, c, h, w = ctx.dims
+        g = _as_act(g)
+        dx = _new_act((b, c, h, w), g)
+        call("lb_upsample2x_bwd", ptr(g), ptr(dx), b, h, w, c)
+        return dx
+
+
+class AvgPool2Fn(torch.autograd.Function):
+    """nn.AvgPool2d(2, 2) (scale.py:40)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _as_act(x)
+        b, c, h, w = x.shape
+        y = _new_act((b, c, h // 2, w // 2), x)
+        call("lb_avgpool2_fwd", ptr(x), ptr(y), b, h, w, c)
+        ctx.dims = (b, c, h, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        b, c, h, w = ctx.dims
+        g = _as_act(g)
+        dx = _new_act((b, c, h, w), g)
+        call("lb_avgpool2_bwd", ptr(g), ptr(dx), b, h, w, c)
+        return dx
+
+
+class CatFn(torch.autograd.Function):
+    """torch.cat([a, b], dim=1) (style chain block.py:123; CatModule merge.py:15) via lb_copy_rows:
+    channels are the contiguous axis of both [B,C] vectors and channels-last [B,C,H,W] maps."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = _as_act(a), _as_act(b)
+        ca, cb = a.shape[1], b.shape[1]
+        rows = a.numel() // ca
+        out = _new_act((a.shape[0], ca + cb, *a.shape[2:]), a)
+        call("lb_copy_rows", ptr(a), ca, ptr(out), ca + cb, rows, ca, 0)
+        call("lb_copy_rows", ptr(b), cb, out.data_ptr() + 4 * ca, ca + cb, rows, cb, 0)
+        ctx.meta = (ca, cb, rows, tuple(a.shape), tuple(b.shape))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        ca, cb, rows, sa, sb = ctx.meta
+        g = _as_act(g)
+        da = db = None
+        if ctx.needs_input_grad[0]:
+            da = _new_act(sa, g)
+            call("lb_copy_rows", ptr(g), ca + cb, ptr(da), ca, rows, ca, 0)
+        if ctx.needs_input_grad[1]:
+            db = _new_act(sb, g)
+            call("lb_copy_rows", g.data_ptr() + 4 * ca, ca + cb, ptr(db), cb, rows, cb, 0)
+        return da, db
+
+
+# functional aliases -------------------------------------------------------------------------
+def roottanh(x, growth=4):
+    return RootTanhFn.apply(x, growth)
+
+
+def whole_norm(x, gain, bias):
+    return WholeNormFn.apply(x, gain, bias)
+
+
+def gate(x, y, gamma, strict_reference=True):
+    return GateFn.apply(x, y, gamma, strict_reference)
+
+
+def sn_conv(x, w_bar, u, v, bias, spec, cat_input=False):
+    return SNConvFn.apply(x, w_bar, u, v, bias, spec, cat_input)

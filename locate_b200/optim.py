@@ -1,0 +1,103 @@
+"""Nadam (libs/nadam.py:5-89) as ONE kernel over a flat parameter arena.
+
+The reference loops over ~145 tensors in Python with ~8 ATen launches each.  Here the trainable
+parameters of a group are re-homed into one flat fp32 buffer (param / grad / exp_avg / exp_avg_sq);
+`step()` is a single lb_nadam_step launch, `zero_grad()` a single fill, and the data-parallel
+all-reduce runs over contiguous buckets of the same buffer.  Backward kernels accumulate straight
+into the grad arena (`param._lb_grad`, see ops._grad_sink).
+"""
+import torch
+from torch.optim import Optimizer
+
+from ._lib import call, ptr
+
+_ALIGN = 4   # floats: keeps every view 16-byte aligned for the vectorised kernels
+
+
+class Nadam(Optimizer):
+    def __init__(self, params, lr=2e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, schedule_decay=4e-3):
+        if weight_decay != 0:
+            raise NotImplementedError("weight_decay is never used by the reference (utils.py:149)")
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, schedule_decay=schedule_decay)
+        super().__init__(params, defaults)
+        self._arenas = None
+        if all(p.is_cuda for g in self.param_groups for p in g["params"]):
+            self._attach()
+
+    # -- arena ---------------------------------------------------------------------------------
+    def _attach(self):
+        arenas = []
+        for group in self.param_groups:
+            train = [p for p in group["params"] if p.requires_grad]
+            if not train:
+                arenas.append(None)
+                continue
+            if any(p.dtype != torch.float32 or not p.is_cuda for p in train):
+                raise RuntimeError("Nadam arena needs fp32 CUDA parameters (no CPU fallback)")
+            offsets, total = [], 0
+            for p in train:
+                offsets.append(total)
+                total += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+            dev = train[0].device
+            flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
+            flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
+            with torch.no_grad():
+                for p, off in zip(train, offsets):
+                    n = p.numel()
+                    flat_p[off:off + n].copy_(p.data.reshape(-1))          # one-time setup copy
+                    gview = flat_g[off:off + n].view(p.shape)
+                    if p.grad is not None:
+                        gview.copy_(p.grad)
+                    p.data = flat_p[off:off + n].view(p.shape)
+                    p._lb_grad = gview
+                    p.grad = gview
+            arenas.append(dict(param=flat_p, grad=flat_g, exp_avg=torch.zeros_like(flat_p),
+                               exp_avg_sq=torch.zeros_like(flat_p), step=0, m_schedule=1.0, n=total))
+        self._arenas = arenas
+
+    def _ensure(self):
+        if self._arenas is None:
+            self._attach()
+
+    @property
+    def flat_grads(self):
+        self._ensure()
+        return [a["grad"] for a in self._arenas if a is not None]
+
+    @property
+    def flat_params(self):
+        self._ensure()
+        return [a["param"] for a in self._arenas if a is not None]
+
+    def zero_grad(self, set_to_none=False):
+        self._ensure()
+        for a in self._arenas:
+            if a is not None:
+                call("lb_fill", ptr(a["grad"]), a["n"], 0.0)
+        for group in self.param_groups:
+            for p in group["params"]:
+                if p.requires_grad and p.grad is None and getattr(p, "_lb_grad", None) is not None:
+                    p.grad = p._lb_grad
+
+    # -- step (nadam.py:56-87) ------------------------------------------------------------------
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        self._ensure()
+        for group, a in zip(self.param_groups, self._arenas):
+            if a is None:
+                continue
+            beta1, beta2 = group["betas"]
+            decay = group["schedule_decay"]
+            a["step"] += 1
+            t = a["step"]
+            mu_t = beta1 * (1.0 - 0.5 * (0.96 ** (t * decay)))
+            mu_next = beta1 * (1.0 - 0.5 * (0.96 ** ((t + 1) * decay)))
+            sched_new = a["m_schedule"] * mu_t
+            sched_next = sched_new * mu_next
+            a["m_schedule"] = sched_new
+            c_grad = group["lr"] * (1.0 - mu_t) / (1.0 - sched_new)
+            c_mom = group["lr"] * mu_next / (1.0 - sched_next)
+            call("lb_nadam_step", ptr(a["param"]), ptr(a["grad"]), ptr(a["exp_avg"]), ptr(a["exp_avg_sq"]), a["n"],
+                 beta1, beta2, group["eps"], c_grad, c_mom, 1.0 - beta2 ** t)
+        return loss

@@ -1,0 +1,104 @@
+"""The G+D training step (main.py:142-172 with miniter = MINIBATCHES = DITERS = 1)
+and the reference's loss / model helpers (utils.py:116-150, grad_penalty.py:1-2)."""
+import torch
+from torch import nn
+
+from . import dist, ops
+from ._lib import call, ptr
+from .config import CFG
+from .optim import Nadam
+
+
+def hinge(output_tensor):
+    """(1 - t).clamp(min=0)  (utils.py:133-134)."""
+    return ops.HingeFn.apply(output_tensor)
+
+
+def penalty(d_true, aug_data, dis, device, gamma=100):
+    """gamma * (mean D(real) - mean D(aug))^2 (grad_penalty.py:1-2).  Composition of [B]-sized torch
+    scalars for API compatibility; train_step uses the fused lb_d_loss kernel instead."""
+    return gamma * (d_true.mean() - dis(aug_data.to(device)).view(-1).mean()) ** 2
+
+
+def init(module: nn.Module):
+    """utils.py:116-130: only InPlaceNorm.weight ~ U(0.998, 1.002) and bias = 0 take effect, because
+    every conv/linear `weight` was re-registered as weight_bar by SpectralNorm."""
+    if "norm" not in module.__class__.__name__.lower():
+        w = getattr(module, "weight", None)
+        if isinstance(w, torch.Tensor):
+            nn.init.orthogonal_(w.data)
+    else:
+        w = getattr(module, "weight", None)
+        if isinstance(w, torch.Tensor):
+            nn.init.uniform_(w.data, 0.998, 1.002)
+    b = getattr(module, "bias", None)
+    if isinstance(b, torch.Tensor):
+        nn.init.constant_(b.data, 0)
+
+
+def parameter_count(net):
+    return sum(p.numel() for p in net.parameters() if p.requires_grad)
+
+
+def get_model(model, learning_rate, device):
+    """(model on device with reference init, Nadam)  (utils.py:146-150).  Init draws happen on the CPU
+    copy so the RNG stream equals the reference's CPU stream, then the model moves to `device`."""
+    model.apply(init)
+    model = model.to(device)
+    opt = Nadam(model.parameters(), lr=learning_rate, betas=(CFG.BETA_1, CFG.BETA_2))
+    if hasattr(model, "zero_grad") and hasattr(type(model), "_lb_optimizer"):
+        model.__dict__["_lb_optimizer"] = opt
+    return model, opt
+
+
+class GanTrainer:
+    """One object per process (per GPU).  `step(real, aug, z)` = one discriminator update followed by
+    one generator update; in data parallel the three exchanges of locate_b200.dist happen inside."""
+
+    def __init__(self, gen, dis, g_opt, d_opt, penalty_gamma=100.0):
+        self.gen, self.dis, self.g_opt, self.d_opt = gen, dis, g_opt, d_opt
+        self.penalty_gamma = float(penalty_gamma)
+
+    def _reduce_and_step(self, opt):
+        for h in [h for flat in opt.flat_grads for h in dist.all_reduce_grads_(flat)]:
+            h.wait()
+        opt.step()
+
+    def d_step(self, real, aug, z):
+        dev = real.device
+        with torch.no_grad():
+            fake = self.gen(z)
+        self.dis.zero_grad()
+        d_true = self.dis(real).view(-1)
+        d_fake = self.dis(fake).view(-1)
+        d_aug = self.dis(aug).view(-1)
+        n = d_true.numel()
+        sums = torch.empty(2, dtype=torch.float64, device=dev)
+        call("lb_loss_sums", ptr(d_true), ptr(d_aug), n, ptr(sums))
+        n_global = float(n * dist.all_reduce_sum_(sums, norm_stat=False))
+        out = torch.empty(3, dtype=torch.float32, device=dev)
+        grads = torch.empty((3, n), dtype=torch.float32, device=dev)
+        call("lb_d_loss", ptr(d_true), ptr(d_fake), ptr(d_aug), ptr(sums), n, n_global, self.penalty_gamma, ptr(out),
+             ptr(grads[0]), ptr(grads[1]), ptr(grads[2]))
+        torch.autograd.backward([d_true, d_fake, d_aug], [grads[0], grads[1], grads[2]])
+        self._reduce_and_step(self.d_opt)
+        return out            # [hinge part (local share of the global mean), penalty, 0]
+
+    def g_step(self, z):
+        dev = z.device
+        self.dis.requires_grad_(False)
+        self.gen.zero_grad()
+        d_fake = self.dis(self.gen(z)).view(-1)
+        n = d_fake.numel()
+        out = torch.empty(1, dtype=torch.float32, device=dev)
+        grad = torch.empty(n, dtype=torch.float32, device=dev)
+        call("lb_g_loss", ptr(d_fake), n, float(n * dist.world_size()), ptr(out), ptr(grad))
+        torch.autograd.backward([d_fake], [grad])
+        self._reduce_and_step(self.g_opt)
+        self.dis.requires_grad_(True)
+        return out
+
+    def step(self, real, aug, z):
+        d_out = self.d_step(real, aug, z)
+        g_out = self.g_step(z)
+        return d_out, g_out
