@@ -19,6 +19,55 @@ from ._lib import ConvGeom, call, ptr
 
 _CL = torch.channels_last
 
+# ---- optional per-kernel timing (bench.py roofline): CUDA events on the launching stream -----------
+_TIMER = None
+
+
+class KernelTimer:
+    """`with KernelTimer() as t:` records (kernel family, algorithmic flops, bytes) + an event pair per
+    launch of the GEMM-class kernels; `t.summary()` (after a synchronize) gives totals per family."""
+
+    def __init__(self):
+        self.records = []
+
+    def __enter__(self):
+        global _TIMER
+        _TIMER = self
+        return self
+
+    def __exit__(self, *exc):
+        global _TIMER
+        _TIMER = None
+
+    def summary(self):
+        out = {}
+        for name, flops, nbytes, e0, e1 in self.records:
+            d = out.setdefault(name, dict(launches=0, flops=0.0, bytes=0.0, ms=0.0))
+            d["launches"] += 1
+            d["flops"] += flops
+            d["bytes"] += nbytes
+            d["ms"] += e0.elapsed_time(e1)
+        return out
+
+
+def _timed_call(family, flops, nbytes, name, *args):
+    if _TIMER is None:
+        return call(name, *args)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    call(name, *args)
+    e1.record()
+    _TIMER.records.append((family, flops, nbytes, e0, e1))
+
+
+def _conv_work(spec, b, h, w_, oh, ow):
+    """Algorithmic (flops, activation+weight bytes at fp32) of one conv GEMM (SURVEY.md section 8d:
+    MAC x 2, padding taps counted; the transposed conv does kh*kw MACs per INPUT pixel)."""
+    pixels = b * (h * w_ if spec.kind == "convT" else oh * ow)
+    flops = 2.0 * pixels * spec.kh * spec.kw * spec.cin * spec.cout
+    nbytes = 4.0 * (b * h * w_ * spec.cin + b * oh * ow * spec.cout + spec.kh * spec.kw * spec.cin * spec.cout)
+    return flops, nbytes
+
 
 def _as_act(t):
     """fp32, CUDA, channels-last (4-D) or contiguous (other ranks)."""
@@ -331,7 +380,9 @@ class SNConvFn(torch.autograd.Function):
         mode = 1 if spec.kind == "convT" else 0
         g = _geom(b, h, w_, cin, oh, ow, spec.cout, spec, mode, cin, ctot, spec.strides_fwd())
         off = cin * 4 if cat_input else 0
-        call("lb_conv_gemm", ptr(x), ptr(w_bar), sigma.data_ptr() + 4, ptr(bias), out.data_ptr() + off, g)
+        fl, by = _conv_work(spec, b, h, w_, oh, ow)
+        _timed_call("conv_gemm", fl, by, "lb_conv_gemm", ptr(x), ptr(w_bar), sigma.data_ptr() + 4, ptr(bias),
+                    out.data_ptr() + off, g)
         if cat_input:
             if (oh, ow) != (h, w_):
                 raise ValueError("cat_input needs a size-preserving conv")
@@ -351,11 +402,12 @@ class SNConvFn(torch.autograd.Function):
         off = cin * 4 if ctx.cat_input else 0
         gy_ptr = gout.data_ptr() + off            # gradient of the conv output slice, row stride ctot
         dx = dw_ret = dbias_ret = None
+        fl, by = _conv_work(spec, b, h, w_, oh, ow)
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             mode = 0 if spec.kind == "convT" else 1
             g = _geom(b, oh, ow, spec.cout, h, w_, cin, spec, mode, ctot, cin, spec.strides_dgrad())
-            call("lb_conv_gemm", gy_ptr, ptr(w_bar), sigma.data_ptr() + 4, None, ptr(dx), g)
+            _timed_call("conv_gemm", fl, by, "lb_conv_gemm", gy_ptr, ptr(w_bar), sigma.data_ptr() + 4, None, ptr(dx), g)
             if ctx.cat_input:
                 call("lb_copy_rows", ptr(gout), ctot, ptr(dx), cin, b * h * w_, cin, 1)
         if ctx.needs_input_grad[1]:
@@ -364,11 +416,11 @@ class SNConvFn(torch.autograd.Function):
             if spec.kind == "convT":
                 # dense = x (cin), gathered = dy (cout): dw[ci][co][ty][tx]
                 g = _geom(b, oh, ow, spec.cout, h, w_, cin, spec, 0, ctot, cin, (t, spec.cout * t, spec.kw, 1))
-                call("lb_conv_wgrad", gy_ptr, ptr(x), ptr(dwn), g)
+                _timed_call("conv_wgrad", fl, by, "lb_conv_wgrad", gy_ptr, ptr(x), ptr(dwn), g)
             else:
                 # dense = dy (cout), gathered = x (cin): dw[co][ci][ty][tx]
                 g = _geom(b, h, w_, cin, oh, ow, spec.cout, spec, 0, cin, ctot, (t, cin * t, spec.kw, 1))
-                call("lb_conv_wgrad", ptr(x), gy_ptr, ptr(dwn), g)
+                _timed_call("conv_wgrad", fl, by, "lb_conv_wgrad", ptr(x), gy_ptr, ptr(dwn), g)
             grad_w, dw_ret = _grad_sink(ctx.w_param)
             height, width = spec.sn_shape
             work = torch.empty(2, dtype=torch.float64, device=x.device)
