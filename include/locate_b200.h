@@ -123,6 +123,20 @@ int lb_conv_gemm(const float* in, const float* w, const float* alpha, const floa
  * channel, w_sn the dense channel.  dw must be zeroed by the caller (atomic accumulation). */
 int lb_conv_wgrad(const float* gathered, const float* dense, float* dw, const lb_conv_geom* g,
                   lb_stream_t stream);
+/* ---- the same GEMM on the 5th-gen tensor cores (tcgen05.mma, TMEM accumulator, TMA tiles), bf16 operands,
+ * fp32 accumulate/output.  `in` is the bf16 channels-last activation, `w_packed` the weight packed by
+ * lb_conv_tc_pack as [tap][n][k] bf16 (lb_conv_tc_packed_elems elements).  lb_conv_tc_supported says
+ * whether a geometry is covered (channels % 8, stride 1|2, <= 32 taps); everything else stays on
+ * lb_conv_gemm. */
+int lb_conv_tc_supported(const lb_conv_geom* g);
+size_t lb_conv_tc_packed_elems(const lb_conv_geom* g);
+int lb_conv_tc_pack(const float* w, void* packed, const lb_conv_geom* g, lb_stream_t stream);
+int lb_conv_tc_gemm(const void* in_bf16, const void* w_packed, const float* alpha, const float* bias, float* out,
+                    const lb_conv_geom* g, lb_stream_t stream);
+/* fp32 -> bf16 producers of GEMM operands: plain cast, and RootTanh fused with the cast (activation.py:9-16) */
+int lb_cast_bf16(const float* x, void* y, size_t n, lb_stream_t stream);
+int lb_roottanh_fwd_bf16(const float* x, void* y, size_t n, int growth, lb_stream_t stream);
+
 /* column sum: out[c] += sum_rows x[row*ld + c]  (bias gradients) */
 int lb_colsum(const float* x, int64_t rows, int cols, int ld, float* out, lb_stream_t stream);
 

@@ -1,0 +1,373 @@
+// tcgen05 / TMEM / TMA implicit-GEMM for the convolution family (bf16 operands, fp32 accumulate).
+//
+//   out[pixel][n] = alpha * sum_taps sum_k A_tap[pixel][k] * Wp[tap][n][k]  (+ bias[n])
+//
+// * A is the bf16 channels-last activation.  For each tap the 128 rows of a tile are a DENSE box of
+//   a (possibly parity-strided) view of the source tensor, so one 4-D TMA load per (tap, 64-channel
+//   chunk) stages the tile, 128-byte swizzled, with out-of-range pixels/channels zero-filled by the
+//   TMA unit (= the convolution padding):
+//     mode 0 (Conv fwd / ConvT dgrad, stride s): in = out*s - pad + t = s*(out + a) + q,
+//             (a, q) = divmod(t - pad, s): box at out + a in parity view q (s*s tensor maps);
+//     mode 1 (ConvT fwd / Conv dgrad): the CTA owns one output parity phase (py,px) and visits only
+//             the taps t = (py + pad) mod s (4 of 16 for 4x4/s2); in = j + (py + pad - t)/s.
+// * Wp is the bf16 weight packed per forward call as [tap][n][k] (K-major rows, TMA 2-D tiles).
+// * One elected thread issues tcgen05.mma (M=128, N=block_n, K=16) into a TMEM accumulator; smem ring
+//   of kStages stages guarded by full/empty mbarriers; tcgen05.commit releases stages and signals the
+//   epilogue, which reads TMEM with tcgen05.ld (lane = row) and writes fp32 rows.
+// Warp roles (192 threads): 0 = TMA producer, 1 = TMEM alloc + MMA issuer, 2-5 = epilogue.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;                      // bf16 elements = 128 bytes = one swizzle row
+constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KB
+constexpr int kMaxViews = 4;
+
+struct TcMaps {
+  CUtensorMap a[kMaxViews];
+  CUtensorMap b;
+};
+
+struct TcParams {
+  int batch, dst_w, dst_h;            // extents of the destination (phase) grid the tiles cover
+  int out_w, out_h, out_c, ld_out;
+  int sp;                             // destination parity step (stride in mode 1, else 1)
+  int tile_w, tile_h, tile_b;         // box dims, product = 128
+  int tiles_w, tiles_h;
+  int block_n, kchunks, stages;
+  int kh, kw, stride, pad, mode;
+  int rows_per_tap;                   // rows of Wp per tap (= out_c)
+  int view_empty;                     // bit v set: parity view v has no pixels
+  const float* alpha; const float* bias; float* out;
+};
+
+__device__ __forceinline__ void tap_span(int mode, int s, int pad, int k, int parity, int& t0, int& step, int& cnt) {
+  if (mode == 1) {
+    t0 = (parity + pad) % s;
+    step = s;
+    cnt = t0 < k ? (k - t0 + s - 1) / s : 0;
+  } else {
+    t0 = 0; step = 1; cnt = k;
+  }
+}
+__device__ __forceinline__ int floordiv(int a, int b) { int q = a / b; return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q; }
+
+__global__ void __launch_bounds__(192, 1) k_conv_tc(const __grid_constant__ TcMaps maps, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[8], bar_empty[8], bar_acc;
+  __shared__ uint32_t tmem_slot;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int b_bytes = p.block_n * kBlockK * 2;
+  const int stage_bytes = kABytes + b_bytes;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // tile coordinates
+  int t = blockIdx.x;
+  const int tw = t % p.tiles_w; t /= p.tiles_w;
+  const int th = t % p.tiles_h; t /= p.tiles_h;
+  const int x0 = tw * p.tile_w, y0 = th * p.tile_h, b0 = t * p.tile_b;
+  const int n0 = blockIdx.y * p.block_n;
+  const int py = blockIdx.z / p.sp, px = blockIdx.z % p.sp;
+
+  int ty0, tys, tyc, tx0, txs, txc;
+  tap_span(p.mode, p.stride, p.pad, p.kh, py, ty0, tys, tyc);
+  tap_span(p.mode, p.stride, p.pad, p.kw, px, tx0, txs, txc);
+  const int iters = tyc * txc * p.kchunks;
+  const uint32_t tmem_cols = p.block_n <= 32 ? 32 : p.block_n <= 64 ? 64 : p.block_n <= 128 ? 128 : 256;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { tc::mbar_init(&bar_full[s], 1); tc::mbar_init(&bar_empty[s], 1); }
+    tc::mbar_init(&bar_acc, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    for (int v = 0; v < kMaxViews; ++v) tc::tma_prefetch_desc(&maps.a[v]);
+    tc::tma_prefetch_desc(&maps.b);
+  }
+  if (warp == 1) tc::tmem_alloc(&tmem_slot, tmem_cols);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (tc::elect_one()) {
+      int it = 0;
+      for (int iy = 0; iy < tyc; ++iy) {
+        const int ty = ty0 + iy * tys;
+        for (int ix = 0; ix < txc; ++ix) {
+          const int tx = tx0 + ix * txs;
+          int view = 0, dy, dx;
+          if (p.mode == 0) {
+            const int ay = floordiv(ty - p.pad, p.stride), ax = floordiv(tx - p.pad, p.stride);
+            const int qy = (ty - p.pad) - ay * p.stride, qx = (tx - p.pad) - ax * p.stride;
+            view = qy * p.stride + qx;
+            dy = ay; dx = ax;
+          } else {
+            dy = (py + p.pad - ty) / p.stride;
+            dx = (px + p.pad - tx) / p.stride;
+          }
+          const int cb = ((p.view_empty >> view) & 1) ? p.batch : b0;     // empty view: force the box out of range -> zeros
+          const int wrow = (ty * p.kw + tx) * p.rows_per_tap + n0;
+          for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
+            const int s = it % p.stages;
+            const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+            tc::mbar_wait(&bar_empty[s], ph ^ 1u);
+            uint8_t* sa = smem + s * stage_bytes;
+            tc::mbar_arrive_expect_tx(&bar_full[s], (uint32_t)stage_bytes);
+            tc::tma_load_4d(sa, &maps.a[view], &bar_full[s], kc * kBlockK, x0 + dx, y0 + dy, cb);
+            tc::tma_load_2d(sa + kABytes, &maps.b, &bar_full[s], kc * kBlockK, wrow);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (tc::elect_one()) {
+      const uint32_t idesc = tc::idesc_bf16(kBlockM, p.block_n, 0, 0);
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+        tc::mbar_wait(&bar_full[s], ph);
+        tc::tc_fence_after();
+        const uint32_t sa = tc::smem_u32(smem + s * stage_bytes);
+        const uint32_t sb = sa + kABytes;
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k) {
+          const uint64_t ad = tc::smem_desc_sw128(sa + k * 32, 16, 1024);
+          const uint64_t bd = tc::smem_desc_sw128(sb + k * 32, 16, 1024);
+          tc::umma_bf16(tmem_base, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+        }
+        tc::umma_commit(&bar_empty[s]);          // stage reusable once these MMAs have read it
+      }
+      if (iters > 0) tc::umma_commit(&bar_acc);   // accumulator complete
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                       // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;
+    const int wl = row % p.tile_w, hl = (row / p.tile_w) % p.tile_h, bl = row / (p.tile_w * p.tile_h);
+    const int x = x0 + wl, y = y0 + hl, b = b0 + bl;
+    const int oy = y * p.sp + py, ox = x * p.sp + px;
+    const bool valid = x < p.dst_w && y < p.dst_h && b < p.batch && oy < p.out_h && ox < p.out_w;
+    float* dst = p.out + ((size_t)(b * p.out_h + oy) * p.out_w + ox) * p.ld_out;
+    const float alpha = p.alpha ? __ldg(p.alpha) : 1.0f;
+    const bool vec = (p.ld_out & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+    if (iters > 0) {
+      tc::mbar_wait(&bar_acc, 0);
+      tc::tc_fence_after();
+    }
+    for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+      float v[16];
+      __syncwarp();                                // tcgen05.ld is .sync.aligned: the whole warp issues it together
+      if (iters > 0) {
+        tc::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = 0.0f;
+      }
+      const int n = n0 + c0;
+      if (valid && n < p.out_c) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = v[i] * alpha + ((p.bias && n + i < p.out_c) ? __ldg(p.bias + n + i) : 0.0f);
+        if (vec && n + 15 < p.out_c) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst + n + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) if (n + i < p.out_c) dst[n + i] = v[i];
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// ---- host: tensor maps -----------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return LB_EUNSUPPORTED;
+  cuuint64_t gdim[5]; cuuint64_t gstr[4]; cuuint32_t bx[5]; cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? LB_OK : LB_EINVAL;
+}
+
+int pow2_ceil(int v) { int r = 1; while (r < v) r <<= 1; return r; }
+
+bool tc_geom_ok(const lb_conv_geom* g) {
+  if (!g) return false;
+  if (g->stride != 1 && g->stride != 2) return false;
+  if (g->in_c % 8 || g->ld_in % 8) return false;           // TMA: 16-byte global strides
+  if (g->in_c < 16 || g->out_c < 8) return false;
+  if (g->kh * g->kw > 32) return false;                    // full-extent feature-attention convs stay on the SIMT path
+  return true;
+}
+
+}  // namespace
+
+extern "C" int lb_conv_tc_supported(const lb_conv_geom* g) { return tc_geom_ok(g) ? 1 : 0; }
+
+// packed weight rows are padded to a multiple of 8 bf16 (16 bytes)
+extern "C" size_t lb_conv_tc_packed_elems(const lb_conv_geom* g) {
+  if (!g) return 0;
+  const size_t kpad = (size_t)(g->in_c + 7) / 8 * 8;
+  return (size_t)g->kh * g->kw * g->out_c * kpad;
+}
+
+__global__ void k_pack_weight(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int taps_w, int n_rows, int k, int kpad,
+                              long long w_sk, long long w_sn, long long w_sty, long long w_stx, size_t total) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int kk = (int)(i % kpad);
+    const size_t r = i / kpad;
+    const int n = (int)(r % n_rows);
+    const int tap = (int)(r / n_rows);
+    const int ty = tap / taps_w, tx = tap % taps_w;
+    const float v = kk < k ? w[kk * w_sk + n * w_sn + ty * w_sty + tx * w_stx] : 0.0f;
+    out[i] = __float2bfloat16(v);
+  }
+}
+extern "C" int lb_conv_tc_pack(const float* w, void* packed, const lb_conv_geom* g, lb_stream_t s) {
+  LB_REQUIRE(w && packed && g);
+  const int kpad = (g->in_c + 7) / 8 * 8;
+  const size_t total = lb_conv_tc_packed_elems(g);
+  k_pack_weight<<<lb_grid_1d(total, 256), 256, 0, lb_s(s)>>>(w, reinterpret_cast<__nv_bfloat16*>(packed), g->kw, g->out_c, g->in_c,
+                                                            kpad, g->w_sk, g->w_sn, g->w_sty, g->w_stx, total);
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
+
+extern "C" int lb_conv_tc_gemm(const void* in_bf16, const void* w_packed, const float* alpha, const float* bias, float* out,
+                               const lb_conv_geom* g, lb_stream_t s) {
+  LB_REQUIRE(in_bf16 && w_packed && out && g);
+  if (!tc_geom_ok(g)) return LB_EUNSUPPORTED;
+  if (reinterpret_cast<uintptr_t>(in_bf16) & 15 || reinterpret_cast<uintptr_t>(w_packed) & 15) return LB_EALIGN;
+  TcMaps maps;
+  TcParams p;
+  p.mode = g->mode; p.stride = g->stride; p.pad = g->pad; p.kh = g->kh; p.kw = g->kw;
+  p.sp = g->mode == 1 ? g->stride : 1;
+  p.batch = g->batch;
+  p.out_w = g->out_w; p.out_h = g->out_h; p.out_c = g->out_c; p.ld_out = g->ld_out;
+  p.dst_w = (g->out_w + p.sp - 1) / p.sp; p.dst_h = (g->out_h + p.sp - 1) / p.sp;
+  p.tile_w = pow2_ceil(p.dst_w) < kBlockM ? pow2_ceil(p.dst_w) : kBlockM;
+  int rest = kBlockM / p.tile_w;
+  p.tile_h = pow2_ceil(p.dst_h) < rest ? pow2_ceil(p.dst_h) : rest;
+  p.tile_b = rest / p.tile_h;
+  p.tiles_w = (p.dst_w + p.tile_w - 1) / p.tile_w;
+  p.tiles_h = (p.dst_h + p.tile_h - 1) / p.tile_h;
+  const int tiles_b = (g->batch + p.tile_b - 1) / p.tile_b;
+  int bn = (g->out_c + 15) / 16 * 16;
+  if (bn > 128) bn = 128;
+  p.block_n = bn;
+  p.kchunks = (g->in_c + kBlockK - 1) / kBlockK;
+  p.rows_per_tap = g->out_c;
+  p.alpha = alpha; p.bias = bias; p.out = out;
+  const int stage_bytes = kABytes + bn * kBlockK * 2;
+  p.stages = 4;
+  const int smem_bytes = p.stages * stage_bytes + 1024;
+
+  // source views: mode 0 with stride 2 -> 4 parity views; otherwise one dense view
+  const int nv = (g->mode == 0) ? g->stride * g->stride : 1;
+  const int vs = (g->mode == 0) ? g->stride : 1;
+  p.view_empty = 0;
+  const char* base = reinterpret_cast<const char*>(in_bf16);
+  for (int v = 0; v < kMaxViews; ++v) {
+    const int vv = v < nv ? v : 0;
+    const int qy = vv / vs, qx = vv % vs;
+    int vw = (g->in_w - qx + vs - 1) / vs, vh = (g->in_h - qy + vs - 1) / vs;
+    if (vw <= 0 || vh <= 0) { if (v < nv) p.view_empty |= 1 << v; vw = vw > 0 ? vw : 1; vh = vh > 0 ? vh : 1; }
+    const uint64_t dims[4] = {(uint64_t)g->in_c, (uint64_t)vw, (uint64_t)vh, (uint64_t)g->batch};
+    const uint64_t strides[3] = {(uint64_t)vs * g->ld_in * 2, (uint64_t)vs * g->in_w * g->ld_in * 2,
+                                 (uint64_t)g->in_h * g->in_w * g->ld_in * 2};
+    const uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)p.tile_w, (uint32_t)p.tile_h, (uint32_t)p.tile_b};
+    const char* vbase = ((p.view_empty >> v) & 1) ? base : base + ((size_t)qy * g->in_w + qx) * g->ld_in * 2;
+    int rc = make_map(&maps.a[v], vbase, 4, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    const int kpad = (g->in_c + 7) / 8 * 8;
+    const uint64_t dims[2] = {(uint64_t)g->in_c, (uint64_t)g->kh * g->kw * g->out_c};
+    const uint64_t strides[1] = {(uint64_t)kpad * 2};
+    const uint32_t box[2] = {(uint32_t)kBlockK, (uint32_t)bn};
+    int rc = make_map(&maps.b, w_packed, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  dim3 grid(p.tiles_w * p.tiles_h * tiles_b, (g->out_c + bn - 1) / bn, p.sp * p.sp);
+  LB_REQUIRE(grid.y <= 65535);
+  k_conv_tc<<<grid, 192, smem_bytes, lb_s(s)>>>(maps, p);
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
+
+// ---- fp32 -> bf16 producers ---------------------------------------------------------------------------
+template <typename F>
+__global__ void __launch_bounds__(256) k_to_bf16(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, size_t n, F f) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t n4 = n >> 2;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = lb_ld4(x + 4 * i);
+    __nv_bfloat162 lo = __floats2bfloat162_rn(f(v.x), f(v.y)), hi = __floats2bfloat162_rn(f(v.z), f(v.w));
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&lo);
+    pk.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(y + 4 * i) = pk;
+  }
+  for (size_t i = (n4 << 2) + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] = __float2bfloat16(f(x[i]));
+}
+struct IdentF { __device__ float operator()(float v) const { return v; } };
+struct RootTanh4F { __device__ float operator()(float v) const { return lb_roottanh(v); } };
+struct RootTanhGF { float ig; __device__ float operator()(float v) const { return lb_roottanh_g(v, ig); } };
+
+extern "C" int lb_cast_bf16(const float* x, void* y, size_t n, lb_stream_t s) {
+  LB_REQUIRE(x && y);
+  if (n == 0) return LB_OK;
+  if (!lb_aligned16(x) || (reinterpret_cast<uintptr_t>(y) & 7)) return LB_EALIGN;
+  k_to_bf16<<<lb_grid_1d((n + 3) / 4, 256), 256, 0, lb_s(s)>>>(x, reinterpret_cast<__nv_bfloat16*>(y), n, IdentF{});
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
+extern "C" int lb_roottanh_fwd_bf16(const float* x, void* y, size_t n, int growth, lb_stream_t s) {
+  LB_REQUIRE(x && y && growth >= 1);
+  if (n == 0) return LB_OK;
+  if (!lb_aligned16(x) || (reinterpret_cast<uintptr_t>(y) & 7)) return LB_EALIGN;
+  if (growth == 4)
+    k_to_bf16<<<lb_grid_1d((n + 3) / 4, 256), 256, 0, lb_s(s)>>>(x, reinterpret_cast<__nv_bfloat16*>(y), n, RootTanh4F{});
+  else
+    k_to_bf16<<<lb_grid_1d((n + 3) / 4, 256), 256, 0, lb_s(s)>>>(x, reinterpret_cast<__nv_bfloat16*>(y), n, RootTanhGF{1.0f / growth});
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}

@@ -25,7 +25,7 @@ def _cfg():
 def _header_symbols():
     with open(os.path.join(ROOT, "include", "locate_b200.h")) as fh:
         text = re.sub(r"/\*.*?\*/", "", fh.read(), flags=re.S)
-    return sorted(set(re.findall(r"\b(?:int|void)\s+(lb_\w+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(?:int|void|size_t)\s+(lb_\w+)\s*\(", text)))
 
 
 def test_library_builds_and_exports_every_declared_symbol():

@@ -1,0 +1,85 @@
+"""tcgen05 / TMA implicit-GEMM (lb_conv_tc_gemm) against the fp32 SIMT gather-GEMM (lb_conv_gemm) on the SAME
+bf16-rounded operands: any difference beyond fp32 accumulation order is a layout / descriptor bug."""
+import ctypes
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from locate_b200 import _lib                     # noqa: E402
+from locate_b200._lib import ConvGeom, call, ptr  # noqa: E402
+
+DEV = "cuda:0"
+
+
+def geom(b, ih, iw, ic, oh, ow, oc, kh, kw, s, p, mode, ld_in, ld_out, strides):
+    g = ConvGeom()
+    g.batch, g.in_h, g.in_w, g.in_c, g.out_h, g.out_w, g.out_c = b, ih, iw, ic, oh, ow, oc
+    g.kh, g.kw, g.stride, g.pad, g.mode, g.ld_in, g.ld_out = kh, kw, s, p, mode, ld_in, ld_out
+    g.w_sk, g.w_sn, g.w_sty, g.w_stx = strides
+    return g
+
+
+CASES = {
+    # name: (kind, b, h, w, cin, cout, k, s, p, direction)
+    "1x1_64": ("conv", 2, 16, 16, 64, 64, 1, 1, 0, "fwd"),
+    "1x1_96_48": ("conv", 3, 16, 16, 96, 48, 1, 1, 0, "fwd"),
+    "1x1_wide": ("conv", 5, 4, 4, 1536, 768, 1, 1, 0, "fwd"),
+    "3x3_48": ("conv", 2, 16, 16, 48, 48, 3, 1, 1, "fwd"),
+    "3x3_odd": ("conv", 2, 9, 9, 40, 24, 3, 1, 1, "fwd"),
+    "5x5s2": ("conv", 2, 32, 32, 64, 64, 5, 2, 2, "fwd"),
+    "5x5s2_c32": ("conv", 3, 64, 64, 32, 32, 5, 2, 2, "fwd"),
+    "5x5s2_dgrad": ("conv", 2, 32, 32, 64, 64, 5, 2, 2, "dgrad"),
+    "3x3_dgrad": ("conv", 2, 16, 16, 48, 48, 3, 1, 1, "dgrad"),
+    "convT4": ("convT", 2, 8, 8, 96, 96, 4, 2, 1, "fwd"),
+    "convT4_big": ("convT", 4, 4, 4, 1536, 1536, 4, 2, 1, "fwd"),
+    "convT4_b2x2": ("convT", 40, 2, 2, 128, 128, 4, 2, 1, "fwd"),
+    "convT4_dgrad": ("convT", 2, 8, 8, 96, 96, 4, 2, 1, "dgrad"),
+    "convT1x1": ("convT", 3, 8, 8, 192, 96, 1, 1, 0, "fwd"),
+    "5x5s2_tiny": ("conv", 6, 2, 2, 1024, 1024, 5, 2, 2, "fwd"),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_tc_matches_simt(name):
+    kind, b, h, w, cin, cout, k, s, p, direction = CASES[name]
+    gen = torch.Generator().manual_seed(hash(name) % 1000)
+    t = k * k
+    if kind == "conv":
+        wt = torch.randn((cout, cin, k, k), generator=gen)
+        oh, ow = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
+        fwd = (t, cin * t, k, 1)          # k=cin, n=cout
+        dgr = (cin * t, t, k, 1)          # k=cout, n=cin
+        mode_f, mode_d = 0, 1
+    else:
+        wt = torch.randn((cin, cout, k, k), generator=gen)
+        oh, ow = (h - 1) * s - 2 * p + k, (w - 1) * s - 2 * p + k
+        fwd = (cout * t, t, k, 1)
+        dgr = (t, cout * t, k, 1)
+        mode_f, mode_d = 1, 0
+    wt = (wt / (cin * t) ** 0.5).bfloat16().float().to(DEV)
+    pad_out = 8                              # write into a channel slice of a wider tensor
+    if direction == "fwd":
+        src = torch.randn((b, h, w, cin), generator=gen).bfloat16().to(DEV)
+        g = geom(b, h, w, cin, oh, ow, cout, k, k, s, p, mode_f, cin, cout + pad_out, fwd)
+        out_shape = (b, oh, ow, cout + pad_out)
+    else:
+        src = torch.randn((b, oh, ow, cout), generator=gen).bfloat16().to(DEV)
+        g = geom(b, oh, ow, cout, h, w, cin, k, k, s, p, mode_d, cout, cin + pad_out, dgr)
+        out_shape = (b, h, w, cin + pad_out)
+    alpha = torch.tensor([0.37], device=DEV)
+    bias = torch.randn(g.out_c, generator=gen).to(DEV)
+    ref = torch.full(out_shape, -7.0, device=DEV)
+    got = torch.full(out_shape, -7.0, device=DEV)
+    srcf = src.float().contiguous()
+    call("lb_conv_gemm", ptr(srcf), ptr(wt), ptr(alpha), ptr(bias), ptr(ref), ctypes.byref(g))
+    assert _lib.lib().lb_conv_tc_supported(ctypes.byref(g)) == 1
+    packed = torch.empty(_lib.lib().lb_conv_tc_packed_elems(ctypes.byref(g)), dtype=torch.bfloat16, device=DEV)
+    call("lb_conv_tc_pack", ptr(wt), ptr(packed), ctypes.byref(g))
+    call("lb_conv_tc_gemm", ptr(src), ptr(packed), ptr(alpha), ptr(bias), ptr(got), ctypes.byref(g))
+    torch.cuda.synchronize()
+    assert torch.equal(got[..., g.out_c:], ref[..., g.out_c:]), "wrote outside its channel slice"
+    err = (got - ref).abs().max().item()
+    scale = ref[..., :g.out_c].abs().max().item()
+    assert err <= 2e-4 * scale + 1e-5, f"{name}: max err {err:.3e} vs scale {scale:.3e}"
