@@ -92,12 +92,13 @@ int lb_gate_bwd(const float* x, const float* y, const float* gamma, const float*
  * sigma_out[1] = 1/sigma.  work: height + width + 4 floats of scratch. */
 int lb_sn_power_iter(const float* w, int height, int width, float* u, float* v, float* sigma_out,
                      float* work, lb_stream_t stream);
-/* weight-gradient epilogue: with dwn = dL/d(W/sigma) (same layout as W) and the LIVE u,v:
+/* weight-gradient epilogue: with dwn = dL/d(W/sigma) and the LIVE u,v:
  *   grad += dwn/sigma - (sum dwn*W)/sigma^2 * u v^T       (SURVEY.md section 8c identity)
- * work: 2 doubles of scratch (zeroed by the call). */
+ * dwn has W's layout (packed_taps = 0) or is the tap-major [taps][d0][d1] buffer of lb_wgrad_tc
+ * (packed_taps = kh*kw).  work: 2 doubles of scratch (zeroed by the call). */
 int lb_sn_weight_grad(const float* dwn, const float* w, const float* u, const float* v,
-                      const float* sigma, float* grad, int height, int width, double* work,
-                      lb_stream_t stream);
+                      const float* sigma, float* grad, int height, int width, int packed_taps,
+                      double* work, lb_stream_t stream);
 
 /* ---- convolution family as a gather-GEMM                              libs/conv.py:11-24, libs/attention.py:9-54,
  *                                                                       libs/scale.py:25-34, libs/linear.py:10
@@ -133,6 +134,11 @@ size_t lb_conv_tc_packed_elems(const lb_conv_geom* g);
 int lb_conv_tc_pack(const float* w, void* packed, const lb_conv_geom* g, lb_stream_t stream);
 int lb_conv_tc_gemm(const void* in_bf16, const void* w_packed, const float* alpha, const float* bias, float* out,
                     const lb_conv_geom* g, lb_stream_t stream);
+/* weight gradient on the tensor cores: dwp[tap][n][m] += sum_pixels gathered[pixel@tap][m] * dense[pixel][n]
+ * (geometry as lb_conv_wgrad; both operands bf16 channels-last; dwp fp32, zeroed by the caller; feed it to
+ * lb_sn_weight_grad with packed_taps = kh*kw). */
+int lb_wgrad_tc_supported(const lb_conv_geom* g);
+int lb_wgrad_tc(const void* gathered_bf16, const void* dense_bf16, float* dwp, const lb_conv_geom* g, lb_stream_t stream);
 /* fp32 -> bf16 producers of GEMM operands: plain cast, and RootTanh fused with the cast (activation.py:9-16) */
 int lb_cast_bf16(const float* x, void* y, size_t n, lb_stream_t stream);
 int lb_roottanh_fwd_bf16(const float* x, void* y, size_t n, int growth, lb_stream_t stream);

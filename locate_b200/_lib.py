@@ -42,7 +42,9 @@ _SIGNATURES = {
     "lb_gate_fwd": ([P, P, P, P, c_int, c_int, c_int, c_int, P], c_int),
     "lb_gate_bwd": ([P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P], c_int),
     "lb_sn_power_iter": ([P, c_int, c_int, P, P, P, P, P], c_int),
-    "lb_sn_weight_grad": ([P, P, P, P, P, P, c_int, c_int, P, P], c_int),
+    "lb_sn_weight_grad": ([P, P, P, P, P, P, c_int, c_int, c_int, P, P], c_int),
+    "lb_wgrad_tc_supported": ([POINTER(ConvGeom)], c_int),
+    "lb_wgrad_tc": ([P, P, P, POINTER(ConvGeom), P], c_int),
     "lb_conv_gemm": ([P, P, P, P, P, POINTER(ConvGeom), P], c_int),
     "lb_conv_wgrad": ([P, P, P, POINTER(ConvGeom), P], c_int),
     "lb_conv_tc_supported": ([POINTER(ConvGeom)], c_int),

@@ -75,36 +75,48 @@ extern "C" int lb_sn_power_iter(const float* w, int height, int width, float* u,
 }
 
 // ---- weight gradient epilogue --------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_sn_dot(const float* __restrict__ a, const float* __restrict__ b, size_t n, double* __restrict__ out) {
+// dwn is either in the master layout (packed_taps = 0) or tap-major packed [taps][d0][d1] as written by
+// lb_wgrad_tc (master [d0][d1][taps]); the master index k maps to the packed offset below.
+__device__ __forceinline__ size_t dwn_offset(size_t k, int width, int height, int taps) {
+  if (taps == 0) return k;
+  const size_t i = k / width;
+  const int j = (int)(k % width);
+  const int d1 = width / taps;
+  return ((size_t)(j % taps) * height + i) * d1 + j / taps;
+}
+__global__ void __launch_bounds__(256) k_sn_dot(const float* __restrict__ a, const float* __restrict__ b, size_t n, int width, int height,
+                                               int taps, double* __restrict__ out) {
   __shared__ double scratch[32];
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   double acc = 0.0;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) acc += (double)(a[i] * b[i]);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    acc += (double)(a[dwn_offset(i, width, height, taps)] * b[i]);
   acc = lb_block_sum(acc, scratch);
   if (threadIdx.x == 0) atomicAdd(out, acc);
 }
 // grad[i][j] += dwn[i][j]/sigma - dot/sigma^2 * u[i] v[j]
 __global__ void __launch_bounds__(256) k_sn_wgrad(const float* __restrict__ dwn, const float* __restrict__ u, const float* __restrict__ v,
                                                  const float* __restrict__ sigma, const double* __restrict__ dot,
-                                                 float* __restrict__ grad, size_t n, int width) {
+                                                 float* __restrict__ grad, size_t n, int width, int height, int taps) {
   const float inv = __ldg(sigma + 1);
   const float coef = (float)(dot[0] * (double)inv * (double)inv);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
     const size_t i = k / width;
     const int j = (int)(k % width);
-    grad[k] += fmaf(dwn[k], inv, -coef * __ldg(u + i) * __ldg(v + j));
+    grad[k] += fmaf(dwn[dwn_offset(k, width, height, taps)], inv, -coef * __ldg(u + i) * __ldg(v + j));
   }
 }
 extern "C" int lb_sn_weight_grad(const float* dwn, const float* w, const float* u, const float* v, const float* sigma,
-                                 float* grad, int height, int width, double* work, lb_stream_t s) {
-  LB_REQUIRE(dwn && w && u && v && sigma && grad && work && height > 0 && width > 0);
+                                 float* grad, int height, int width, int packed_taps, double* work, lb_stream_t s) {
+  LB_REQUIRE(dwn && w && u && v && sigma && grad && work && height > 0 && width > 0 && packed_taps >= 0);
+  LB_REQUIRE(packed_taps == 0 || width % packed_taps == 0);
   const size_t n = (size_t)height * width;
   cudaError_t e = cudaMemsetAsync(work, 0, sizeof(double) * 2, lb_s(s));
   if (e != cudaSuccess) return (int)e;
-  k_sn_dot<<<lb_grid_1d(n, 256, 2), 256, 0, lb_s(s)>>>(dwn, w, n, work);
+  k_sn_dot<<<lb_grid_1d(n, 256, 2), 256, 0, lb_s(s)>>>(dwn, w, n, width, height, packed_taps, work);
   LB_LAUNCH_CHECK();
-  k_sn_wgrad<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(dwn, u, v, sigma, work, grad, n, width);
+  k_sn_wgrad<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(dwn, u, v, sigma, work, grad, n, width, height, packed_taps);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }

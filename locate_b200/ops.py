@@ -425,7 +425,7 @@ class SNConvFn(torch.autograd.Function):
             height, width = spec.sn_shape
             work = torch.empty(2, dtype=torch.float64, device=x.device)
             call("lb_sn_weight_grad", ptr(dwn), ptr(w_bar), ptr(ctx.u.data), ptr(ctx.v.data), ptr(sigma), ptr(grad_w),
-                 height, width, ptr(work))
+                 height, width, 0, ptr(work))
         if ctx.bias_param is not None and ctx.needs_input_grad[4]:
             dbias, dbias_ret = _grad_sink(ctx.bias_param)
             call("lb_colsum", gy_ptr, b * oh * ow, spec.cout, ctot, ptr(dbias))

@@ -83,3 +83,61 @@ def test_tc_matches_simt(name):
     err = (got - ref).abs().max().item()
     scale = ref[..., :g.out_c].abs().max().item()
     assert err <= 2e-4 * scale + 1e-5, f"{name}: max err {err:.3e} vs scale {scale:.3e}"
+
+
+WG_CASES = {
+    # name: (kind, b, h, w, cin, cout, k, s, p)   h,w = layer INPUT size
+    "wg_1x1": ("conv", 2, 16, 16, 64, 64, 1, 1, 0),
+    "wg_1x1_96_48": ("conv", 3, 16, 16, 96, 48, 1, 1, 0),
+    "wg_3x3": ("conv", 2, 16, 16, 48, 48, 3, 1, 1),
+    "wg_5x5s2": ("conv", 2, 32, 32, 64, 64, 5, 2, 2),
+    "wg_5x5s2_c32": ("conv", 3, 64, 64, 32, 32, 5, 2, 2),
+    "wg_convT4": ("convT", 2, 8, 8, 96, 96, 4, 2, 1),
+    "wg_convT4_wide": ("convT", 4, 4, 4, 384, 384, 4, 2, 1),
+    "wg_convT1x1": ("convT", 3, 8, 8, 192, 96, 1, 1, 0),
+    "wg_3x3_odd": ("conv", 2, 9, 9, 40, 24, 3, 1, 1),
+    "wg_5x5s2_tiny": ("conv", 6, 2, 2, 256, 320, 5, 2, 2),
+}
+
+
+@pytest.mark.parametrize("name", sorted(WG_CASES))
+def test_tc_wgrad_matches_simt(name):
+    kind, b, h, w, cin, cout, k, s, p = WG_CASES[name]
+    gen = torch.Generator().manual_seed(hash(name) % 1000)
+    t = k * k
+    if kind == "conv":
+        oh, ow = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
+        x = torch.randn((b, h, w, cin), generator=gen).bfloat16().to(DEV)
+        dy = torch.randn((b, oh, ow, cout), generator=gen).bfloat16().to(DEV)
+        gathered, dense = x, dy
+        g = geom(b, h, w, cin, oh, ow, cout, k, k, s, p, 0, cin, cout, (t, cin * t, k, 1))
+        shape, d0, d1 = (cout, cin, k, k), cout, cin
+    else:
+        oh, ow = (h - 1) * s - 2 * p + k, (w - 1) * s - 2 * p + k
+        x = torch.randn((b, h, w, cin), generator=gen).bfloat16().to(DEV)
+        dy = torch.randn((b, oh, ow, cout), generator=gen).bfloat16().to(DEV)
+        gathered, dense = dy, x
+        g = geom(b, oh, ow, cout, h, w, cin, k, k, s, p, 0, cout, cin, (t, cout * t, k, 1))
+        shape, d0, d1 = (cin, cout, k, k), cin, cout
+    ref = torch.zeros(shape, device=DEV)
+    gath_f, dense_f = gathered.float().contiguous(), dense.float().contiguous()      # keep alive across the async launch
+    call("lb_conv_wgrad", ptr(gath_f), ptr(dense_f), ptr(ref), ctypes.byref(g))
+    assert _lib.lib().lb_wgrad_tc_supported(ctypes.byref(g)) == 1
+    dwp = torch.zeros((t, d0, d1), device=DEV)
+    call("lb_wgrad_tc", ptr(gathered), ptr(dense), ptr(dwp), ctypes.byref(g))
+    torch.cuda.synchronize()
+    got = dwp.permute(1, 2, 0).reshape(shape)
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= 3e-4 * scale + 1e-5, f"{name}: max err {err:.3e} vs scale {scale:.3e}"
+    # the packed read path of the spectral-norm epilogue
+    wbar = torch.randn(shape, generator=gen).to(DEV)
+    u = torch.randn(d0, generator=gen).to(DEV)
+    v = torch.randn(d1 * t, generator=gen).to(DEV)
+    sigma = torch.tensor([2.0, 0.5], device=DEV)
+    ga, gb = torch.zeros(shape, device=DEV), torch.zeros(shape, device=DEV)
+    work = torch.empty(2, dtype=torch.float64, device=DEV)
+    call("lb_sn_weight_grad", ptr(ref), ptr(wbar), ptr(u), ptr(v), ptr(sigma), ptr(ga), d0, d1 * t, 0, ptr(work))
+    call("lb_sn_weight_grad", ptr(dwp), ptr(wbar), ptr(u), ptr(v), ptr(sigma), ptr(gb), d0, d1 * t, t, ptr(work))
+    torch.cuda.synchronize()
+    assert (ga - gb).abs().max().item() <= 3e-4 * ga.abs().max().item() + 1e-5
