@@ -141,7 +141,7 @@ def run_cuda(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    L.configure(IMAGE_SIZE=RES)
+    L.configure(IMAGE_SIZE=RES, PRECISION=args.precision)
     torch.manual_seed(999)                      # replicas start identical (same seed, same RNG stream as the reference)
     gen, g_opt = L.get_model(L.Generator(), L.CFG.GLR, dev)
     dis, d_opt = L.get_model(L.Discriminator(), L.CFG.DLR, dev)
@@ -218,7 +218,8 @@ def run_cuda(args):
         if os.path.exists(tpath):
             with open(tpath) as fh:
                 traffic = json.load(fh).get(fam)
-        roofline = {"kernel": {"conv_gemm": "k_conv_gemm (fwd+dgrad gather-GEMM)", "conv_wgrad": "k_conv_wgrad"}.get(fam, fam),
+        roofline = {"kernel": {"conv_gemm": "k_conv_gemm (fp32 SIMT fwd+dgrad gather-GEMM)", "conv_wgrad": "k_conv_wgrad (fp32 SIMT)",
+                               "conv_tc": "k_conv_tc (tcgen05 implicit GEMM fwd+dgrad)", "wgrad_tc": "k_wgrad_tc (tcgen05 wgrad)"}.get(fam, fam),
                     "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
                     "frac": achieved / peaks["tflops"], "traffic": traffic, "peak_source": peaks["source"],
                     "launches_per_step": k["launches"] / args.steps, "avg_launch_ms": per_launch_ms,
@@ -228,8 +229,10 @@ def run_cuda(args):
     line = {
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        "dtype": "bf16" if L.CFG.PRECISION == "bf16" else "f32", "data": "synthetic",
         "config": {"workload": f"G+D train step {RES}x{RES}, default flags (DEPTH=1, attention on), Nadam included",
+                   "precision": "bf16 tcgen05 GEMM operands, fp32 accumulate / activations / reductions / optimizer"
+                   if L.CFG.PRECISION == "bf16" else "fp32 everywhere",
                    "resolution": RES, "per_gpu_batch": b, "global_batch": b * world, "parallelism": f"dp{world}",
                    "l2": "per-step working set (saved activations, several GB) exceeds the 126 MB L2; no explicit flush",
                    "norm_statistics": "global batch (all-reduced)" if world > 1 else "single process"},
@@ -261,6 +264,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="per-GPU batch")
     ap.add_argument("--ref-batch", type=int, default=4, help="batch of the CPU reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

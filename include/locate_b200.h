@@ -141,6 +141,7 @@ int lb_wgrad_tc_supported(const lb_conv_geom* g);
 int lb_wgrad_tc(const void* gathered_bf16, const void* dense_bf16, float* dwp, const lb_conv_geom* g, lb_stream_t stream);
 /* fp32 -> bf16 producers of GEMM operands: plain cast, and RootTanh fused with the cast (activation.py:9-16) */
 int lb_cast_bf16(const float* x, void* y, size_t n, lb_stream_t stream);
+int lb_cast_bf16_rows(const float* src, int ld_src, void* dst, int ld_dst, int64_t rows, int cols, lb_stream_t stream);
 int lb_roottanh_fwd_bf16(const float* x, void* y, size_t n, int growth, lb_stream_t stream);
 
 /* column sum: out[c] += sum_rows x[row*ld + c]  (bias gradients) */

@@ -33,6 +33,9 @@ class Config:
     BETA_1: float = 0.5
     BETA_2: float = 0.9
     STRICT_REFERENCE: bool = True      # reproduce the reference's d-gamma = sum(x*x*g) (merge.py:33-38)
+    # "bf16": conv/linear GEMMs on the tcgen05 tensor cores (bf16 operands, fp32 accumulate) wherever the
+    # geometry allows; "fp32": every GEMM on the fp32 SIMT kernel (bit-for-bit the reference's precision class)
+    PRECISION: str = "bf16"
 
     @property
     def LAYERS(self):

@@ -1,0 +1,226 @@
+"""The spectral-normed convolution family as one autograd Function (fwd, dgrad, wgrad + the power iteration).
+
+Two kernel paths, chosen per layer:
+  * CFG.PRECISION == "bf16" and the geometry is covered by the tensor-core kernels (channels % 8, stride 1|2,
+    <= 32 taps): tcgen05 implicit GEMM (lb_conv_tc_gemm / lb_wgrad_tc), bf16 operands, fp32 accumulate + output.
+    Operands are produced in bf16 by the kernel that computes them (RootTanh fused with the cast).
+  * otherwise: the fp32 SIMT gather-GEMM (lb_conv_gemm / lb_conv_wgrad).
+`pre_act` fuses the RootTanh that precedes every conv of ActivatedBaseConv (conv.py:22-24) into this Function.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import ConvGeom, call, ptr
+from .config import CFG
+from .ops import _as_act, _conv_work, _grad_sink, _new_act, _timed_call
+
+# weight packs are reused while the weights are unchanged (3 discriminator passes per D step);
+# optim.Nadam.step / load_state_dict bump the epoch, torch's version counter covers in-place torch ops.
+_PACK_EPOCH = [0]
+
+
+def invalidate_packs():
+    _PACK_EPOCH[0] += 1
+
+
+class ConvSpec:
+    """Static description of one spectral-normed linear map.
+
+    kind: 'conv' (weight [Cout,Cin,kh,kw]), 'convT' (weight [Cin,Cout,kh,kw]), 'linear'
+    (weight [out,in]), 'conv1d' (weight [Cout,Cin,1] applied per pixel)."""
+
+    def __init__(self, kind, cin, cout, kh=1, kw=1, stride=1, pad=0):
+        self.kind, self.cin, self.cout = kind, cin, cout
+        self.kh, self.kw, self.stride, self.pad = kh, kw, stride, pad
+
+    def out_hw(self, h, w):
+        if self.kind == "convT":
+            return (h - 1) * self.stride - 2 * self.pad + self.kh, (w - 1) * self.stride - 2 * self.pad + self.kw
+        return (h + 2 * self.pad - self.kh) // self.stride + 1, (w + 2 * self.pad - self.kw) // self.stride + 1
+
+    @property
+    def taps(self):
+        return self.kh * self.kw
+
+    @property
+    def sn_shape(self):
+        """(height, width) of the matrix view spectral norm iterates on (spectral_norm.py:26)."""
+        if self.kind == "convT":
+            return self.cin, self.cout * self.taps
+        return self.cout, self.cin * self.taps
+
+    # (w_sk, w_sn, w_sty, w_stx) of W(tap,k,n) in the master layout
+    def strides_fwd(self):            # k = cin, n = cout
+        t = self.taps
+        return (self.cout * t, t, self.kw, 1) if self.kind == "convT" else (t, self.cin * t, self.kw, 1)
+
+    def strides_dgrad(self):          # k = cout, n = cin
+        t = self.taps
+        return (t, self.cout * t, self.kw, 1) if self.kind == "convT" else (self.cin * t, t, self.kw, 1)
+
+
+def _geom(batch, ih, iw, ic, oh, ow, oc, spec, mode, ld_in, ld_out, strides):
+    g = ConvGeom()
+    g.batch, g.in_h, g.in_w, g.in_c = batch, ih, iw, ic
+    g.out_h, g.out_w, g.out_c = oh, ow, oc
+    g.kh, g.kw, g.stride, g.pad, g.mode = spec.kh, spec.kw, spec.stride, spec.pad, mode
+    g.ld_in, g.ld_out = ld_in, ld_out
+    g.w_sk, g.w_sn, g.w_sty, g.w_stx = strides
+    return g
+
+
+def power_iterate(w_bar, u, v, spec):
+    """One in-place power iteration (spectral_norm.py:21-32); returns the [sigma, 1/sigma] buffer."""
+    height, width = spec.sn_shape
+    sigma = torch.empty(2, dtype=torch.float32, device=w_bar.device)
+    work = torch.empty(height + width + 4, dtype=torch.float32, device=w_bar.device)
+    call("lb_sn_power_iter", ptr(w_bar), height, width, ptr(u), ptr(v), ptr(sigma), ptr(work))
+    return sigma
+
+
+def _bf16_like(t):
+    return torch.empty_strided(t.shape, t.stride(), dtype=torch.bfloat16, device=t.device)
+
+
+def _packed_weight(w_bar, g, tag):
+    """bf16 [tap][n][k] copy of the master weight for geometry g (cached per weight version)."""
+    key = (_PACK_EPOCH[0], w_bar._version, w_bar.data_ptr())
+    cache = getattr(w_bar, "_lb_pack", None)
+    if cache is None or cache[0] != key:
+        cache = (key, {})
+        w_bar._lb_pack = cache
+    pk = cache[1].get(tag)
+    if pk is None:
+        n = _lib.lib().lb_conv_tc_packed_elems(ctypes.byref(g))
+        pk = torch.empty(n, dtype=torch.bfloat16, device=w_bar.device)
+        call("lb_conv_tc_pack", ptr(w_bar), ptr(pk), g)
+        cache[1][tag] = pk
+    return pk
+
+
+class SNConvFn(torch.autograd.Function):
+    """y = conv(act?(x), W_bar)/sigma (+bias) with the power iteration run inside, i.e. SpectralNorm.forward
+    (spectral_norm.py:57-59) around Conv2d / ConvTranspose2d / Conv1d(k=1) / Linear (conv.py:14-20,
+    attention.py:26-34,44-46, scale.py:25-34, linear.py:10), optionally preceded by RootTanh (conv.py:23-24).
+
+    If `cat_input` the result is cat([x, y], channels) (CatModule with an identity residual, merge.py:10-16):
+    the GEMM writes straight into the channel slice of the wider output."""
+
+    @staticmethod
+    def forward(ctx, x, w_bar, u, v, bias, spec, cat_input, pre_act):
+        x = _as_act(x)
+        is_vec = x.dim() == 2
+        if is_vec:
+            b, h, w_, cin = x.shape[0], 1, 1, x.shape[1]
+        else:
+            b, cin, h, w_ = x.shape
+        if cin != spec.cin:
+            raise ValueError(f"expected {spec.cin} input channels, got {cin}")
+        if cat_input and pre_act:
+            raise ValueError("cat_input and pre_act are exclusive")
+        sigma = power_iterate(w_bar, u.data, v.data, spec)
+        oh, ow = spec.out_hw(h, w_)
+        if cat_input and (oh, ow) != (h, w_):
+            raise ValueError("cat_input needs a size-preserving conv")
+        ctot = spec.cout + (cin if cat_input else 0)
+        out = _new_act((b, ctot) if is_vec else (b, ctot, oh, ow), x)
+        off = cin * 4 if cat_input else 0
+        t = spec.taps
+        mode = 1 if spec.kind == "convT" else 0
+        g_fwd = _geom(b, h, w_, cin, oh, ow, spec.cout, spec, mode, cin, ctot, spec.strides_fwd())
+        g_dgrad = _geom(b, oh, ow, spec.cout, h, w_, cin, spec, 1 - mode, spec.cout, cin, spec.strides_dgrad())
+        if spec.kind == "convT":      # dense = x (cin), gathered = dy (cout): dw[ci][co][tap]
+            g_wgrad = _geom(b, oh, ow, spec.cout, h, w_, cin, spec, 0, spec.cout, cin, (t, spec.cout * t, spec.kw, 1))
+        else:                         # dense = dy (cout), gathered = x (cin): dw[co][ci][tap]
+            g_wgrad = _geom(b, h, w_, cin, oh, ow, spec.cout, spec, 0, cin, spec.cout, (t, cin * t, spec.kw, 1))
+        lib = _lib.lib()
+        tc = (CFG.PRECISION == "bf16" and lib.lb_conv_tc_supported(ctypes.byref(g_fwd)) == 1
+              and lib.lb_conv_tc_supported(ctypes.byref(g_dgrad)) == 1 and lib.lb_wgrad_tc_supported(ctypes.byref(g_wgrad)) == 1)
+        fl, by = _conv_work(spec, b, h, w_, oh, ow)
+        n = x.numel()
+        if tc:
+            a = _bf16_like(x)
+            if pre_act:
+                call("lb_roottanh_fwd_bf16", ptr(x), ptr(a), n, CFG.ROOTTANH_GROWTH)
+            else:
+                call("lb_cast_bf16", ptr(x), ptr(a), n)
+            pk = _packed_weight(w_bar, g_fwd, "fwd")
+            _timed_call("conv_tc", fl, by / 2, "lb_conv_tc_gemm", ptr(a), ptr(pk), sigma.data_ptr() + 4, ptr(bias),
+                        out.data_ptr() + off, g_fwd)
+        else:
+            if pre_act:
+                a = torch.empty_like(x)
+                call("lb_roottanh_fwd", ptr(x), ptr(a), n, CFG.ROOTTANH_GROWTH)
+            else:
+                a = x
+            _timed_call("conv_gemm", fl, by, "lb_conv_gemm", ptr(a), ptr(w_bar), sigma.data_ptr() + 4, ptr(bias),
+                        out.data_ptr() + off, g_fwd)
+        if cat_input:
+            call("lb_copy_rows", ptr(x), cin, ptr(out), ctot, b * h * w_, cin, 0)
+        ctx.save_for_backward(x if pre_act else None, a, w_bar, sigma)
+        ctx.u, ctx.v = u, v                      # LIVE u/v: the reference's backward reads them at backward time
+        ctx.bias_param, ctx.w_param = bias, w_bar
+        ctx.meta = (spec, cat_input, pre_act, tc, (b, h, w_, cin, oh, ow, ctot), g_dgrad, g_wgrad, (fl, by))
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, a, w_bar, sigma = ctx.saved_tensors
+        spec, cat_input, pre_act, tc, (b, h, w_, cin, oh, ow, ctot), g_dgrad, g_wgrad, (fl, by) = ctx.meta
+        gout = _as_act(gout)
+        off = cin * 4 if cat_input else 0
+        rows = b * oh * ow
+        need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        dx = dw_ret = dbias_ret = None
+        t = spec.taps
+        height, width = spec.sn_shape
+        if tc:
+            gy = torch.empty((rows, spec.cout), dtype=torch.bfloat16, device=gout.device)
+            call("lb_cast_bf16_rows", gout.data_ptr() + off, ctot, ptr(gy), spec.cout, rows, spec.cout)
+            if need_dx:
+                dx = _new_act(tuple(a.shape), gout)
+                pk = _packed_weight(w_bar, g_dgrad, "dgrad")
+                _timed_call("conv_tc", fl, by / 2, "lb_conv_tc_gemm", ptr(gy), ptr(pk), sigma.data_ptr() + 4, None, ptr(dx), g_dgrad)
+            if need_dw:
+                dwp = torch.zeros(w_bar.numel(), dtype=torch.float32, device=gout.device)
+                if spec.kind == "convT":
+                    _timed_call("wgrad_tc", fl, by / 2, "lb_wgrad_tc", ptr(gy), ptr(a), ptr(dwp), g_wgrad)
+                else:
+                    _timed_call("wgrad_tc", fl, by / 2, "lb_wgrad_tc", ptr(a), ptr(gy), ptr(dwp), g_wgrad)
+                grad_w, dw_ret = _grad_sink(ctx.w_param)
+                work = torch.empty(2, dtype=torch.float64, device=gout.device)
+                call("lb_sn_weight_grad", ptr(dwp), ptr(w_bar), ptr(ctx.u.data), ptr(ctx.v.data), ptr(sigma), ptr(grad_w),
+                     height, width, t, ptr(work))
+        else:
+            gy_ptr = gout.data_ptr() + off        # gradient of the conv output slice, row stride ctot
+            g_dgrad.ld_in = ctot
+            if need_dx:
+                dx = torch.empty_like(a)
+                _timed_call("conv_gemm", fl, by, "lb_conv_gemm", gy_ptr, ptr(w_bar), sigma.data_ptr() + 4, None, ptr(dx), g_dgrad)
+            if need_dw:
+                dwn = torch.zeros_like(w_bar, memory_format=torch.contiguous_format)
+                if spec.kind == "convT":
+                    g_wgrad.ld_in = ctot
+                    _timed_call("conv_wgrad", fl, by, "lb_conv_wgrad", gy_ptr, ptr(a), ptr(dwn), g_wgrad)
+                else:
+                    g_wgrad.ld_out = ctot
+                    _timed_call("conv_wgrad", fl, by, "lb_conv_wgrad", ptr(a), gy_ptr, ptr(dwn), g_wgrad)
+                grad_w, dw_ret = _grad_sink(ctx.w_param)
+                work = torch.empty(2, dtype=torch.float64, device=gout.device)
+                call("lb_sn_weight_grad", ptr(dwn), ptr(w_bar), ptr(ctx.u.data), ptr(ctx.v.data), ptr(sigma), ptr(grad_w),
+                     height, width, 0, ptr(work))
+        if need_dx:
+            if pre_act:
+                call("lb_roottanh_bwd", ptr(x), ptr(dx), ptr(dx), dx.numel(), CFG.ROOTTANH_GROWTH)   # in place
+            if cat_input:
+                call("lb_copy_rows", ptr(gout), ctot, ptr(dx), cin, b * h * w_, cin, 1)
+        if ctx.bias_param is not None and ctx.needs_input_grad[4]:
+            dbias, dbias_ret = _grad_sink(ctx.bias_param)
+            call("lb_colsum", gout.data_ptr() + off, rows, spec.cout, ctot, ptr(dbias))
+        return dx, dw_ret, None, None, dbias_ret, None, None, None
+
+
+def sn_conv(x, w_bar, u, v, bias, spec, cat_input=False, pre_act=False):
+    return SNConvFn.apply(x, w_bar, u, v, bias, spec, cat_input, pre_act)

@@ -360,6 +360,31 @@ extern "C" int lb_cast_bf16(const float* x, void* y, size_t n, lb_stream_t s) {
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
+// row-strided cast: dst[r*ld_dst + c] = bf16(src[r*ld_src + c]) (gradient of a concat slice -> dense GEMM operand)
+__global__ void __launch_bounds__(256) k_cast_rows(const float* __restrict__ src, int ld_src, __nv_bfloat16* __restrict__ dst, int ld_dst,
+                                                  size_t rows, int cols4) {
+  const size_t total = rows * (size_t)cols4;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const size_t r = i / cols4;
+    const int c = (int)(i % cols4) * 4;
+    const float4 v = lb_ld4(src + r * ld_src + c);
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&lo);
+    pk.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(dst + r * ld_dst + c) = pk;
+  }
+}
+extern "C" int lb_cast_bf16_rows(const float* src, int ld_src, void* dst, int ld_dst, int64_t rows, int cols, lb_stream_t s) {
+  LB_REQUIRE(src && dst && rows >= 0 && cols > 0 && ld_src >= cols && ld_dst >= cols);
+  if (rows == 0) return LB_OK;
+  if ((cols & 3) || (ld_src & 3) || (ld_dst & 3) || !lb_aligned16(src) || (reinterpret_cast<uintptr_t>(dst) & 7)) return LB_EALIGN;
+  k_cast_rows<<<lb_grid_1d((size_t)rows * (cols / 4), 256), 256, 0, lb_s(s)>>>(src, ld_src, reinterpret_cast<__nv_bfloat16*>(dst), ld_dst,
+                                                                           (size_t)rows, cols / 4);
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
 extern "C" int lb_roottanh_fwd_bf16(const float* x, void* y, size_t n, int growth, lb_stream_t s) {
   LB_REQUIRE(x && y && growth >= 1);
   if (n == 0) return LB_OK;

@@ -113,7 +113,9 @@ class SpectralNorm(nn.Module):
         self.module.register_parameter(self.name + "_v", v)
         self.module.register_parameter(self.name + "_bar", w_bar)
 
-    def forward(self, *args, cat_input=False):
+    def forward(self, *args, cat_input=False, pre_act=False):
+        """pre_act=True applies RootTanh to the input inside the same kernel sequence (the activation that
+        precedes both convs of ActivatedBaseConv, conv.py:23-24)."""
         (x,) = args
         m = self.module
         for _ in range(self.power_iterations - 1):        # extra iterations only move u/v
@@ -121,7 +123,7 @@ class SpectralNorm(nn.Module):
         squeeze = x.dim() == 3                            # Conv1d input [B,F,L]
         if squeeze:
             x = x.unsqueeze(-1)
-        out = ops.sn_conv(x, m.weight_bar, m.weight_u, m.weight_v, getattr(m, "bias", None), self.spec, cat_input)
+        out = ops.sn_conv(x, m.weight_bar, m.weight_u, m.weight_v, getattr(m, "bias", None), self.spec, cat_input, pre_act)
         return out.squeeze(-1) if squeeze else out
 
 
@@ -316,7 +318,7 @@ class ActivatedBaseConv(nn.Module):
                                         in_channels=mid))
 
     def forward(self, function_input):
-        return self.conv_1(nonlinear_function(self.conv_0(nonlinear_function(function_input))))
+        return self.conv_1(self.conv_0(function_input, pre_act=True), pre_act=True)
 
 
 class DeepResidualConv(nn.Module):

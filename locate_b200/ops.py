@@ -15,7 +15,7 @@ import math
 import torch
 
 from . import _lib, dist
-from ._lib import ConvGeom, call, ptr
+from ._lib import call, ptr
 
 _CL = torch.channels_last
 
@@ -297,142 +297,6 @@ class GateFn(torch.autograd.Function):
 
 
 # ------------------------------------------------------------------------------------------
-# spectral-normed convolution family
-# ------------------------------------------------------------------------------------------
-class ConvSpec:
-    """Static description of one spectral-normed linear map.
-
-    kind: 'conv' (weight [Cout,Cin,kh,kw]), 'convT' (weight [Cin,Cout,kh,kw]), 'linear'
-    (weight [out,in]), 'conv1d' (weight [Cout,Cin,1] applied per pixel)."""
-
-    def __init__(self, kind, cin, cout, kh=1, kw=1, stride=1, pad=0):
-        self.kind, self.cin, self.cout = kind, cin, cout
-        self.kh, self.kw, self.stride, self.pad = kh, kw, stride, pad
-
-    def out_hw(self, h, w):
-        if self.kind == "convT":
-            return (h - 1) * self.stride - 2 * self.pad + self.kh, (w - 1) * self.stride - 2 * self.pad + self.kw
-        return (h + 2 * self.pad - self.kh) // self.stride + 1, (w + 2 * self.pad - self.kw) // self.stride + 1
-
-    @property
-    def sn_shape(self):
-        """(height, width) of the matrix view spectral norm iterates on (spectral_norm.py:26)."""
-        taps = self.kh * self.kw
-        if self.kind == "convT":
-            return self.cin, self.cout * taps
-        return self.cout, self.cin * taps
-
-    # (w_sk, w_sn, w_sty, w_stx) of W(tap,k,n) for the three GEMMs
-    def strides_fwd(self):
-        t = self.kh * self.kw
-        if self.kind == "convT":
-            return self.cout * t, t, self.kw, 1          # k = cin, n = cout
-        return t, self.cin * t, self.kw, 1               # k = cin, n = cout
-
-    def strides_dgrad(self):
-        t = self.kh * self.kw
-        if self.kind == "convT":
-            return t, self.cout * t, self.kw, 1          # k = cout, n = cin
-        return self.cin * t, t, self.kw, 1               # k = cout, n = cin
-
-
-def _geom(batch, ih, iw, ic, oh, ow, oc, spec, mode, ld_in, ld_out, strides):
-    g = ConvGeom()
-    g.batch, g.in_h, g.in_w, g.in_c = batch, ih, iw, ic
-    g.out_h, g.out_w, g.out_c = oh, ow, oc
-    g.kh, g.kw, g.stride, g.pad, g.mode = spec.kh, spec.kw, spec.stride, spec.pad, mode
-    g.ld_in, g.ld_out = ld_in, ld_out
-    g.w_sk, g.w_sn, g.w_sty, g.w_stx = strides
-    return g
-
-
-def power_iterate(w_bar, u, v, spec):
-    """One in-place power iteration (spectral_norm.py:21-32); returns the [sigma, 1/sigma] buffer."""
-    height, width = spec.sn_shape
-    sigma = torch.empty(2, dtype=torch.float32, device=w_bar.device)
-    work = torch.empty(height + width + 4, dtype=torch.float32, device=w_bar.device)
-    call("lb_sn_power_iter", ptr(w_bar), height, width, ptr(u), ptr(v), ptr(sigma), ptr(work))
-    return sigma
-
-
-class SNConvFn(torch.autograd.Function):
-    """y = conv(x, W_bar)/sigma (+bias) with the power iteration run inside, i.e.
-    SpectralNorm.forward (spectral_norm.py:57-59) around Conv2d / ConvTranspose2d / Conv1d(k=1) /
-    Linear (conv.py:14-20, attention.py:26-34,44-46, scale.py:25-34, linear.py:10).
-
-    If `cat_input` the result is cat([x, y], channels) (CatModule with an identity residual,
-    merge.py:10-16): the GEMM writes straight into the channel slice of the wider output."""
-
-    @staticmethod
-    def forward(ctx, x, w_bar, u, v, bias, spec, cat_input):
-        x = _as_act(x)
-        is_vec = x.dim() == 2
-        if is_vec:
-            b, h, w_, cin = x.shape[0], 1, 1, x.shape[1]
-        else:
-            b, cin, h, w_ = x.shape
-        if cin != spec.cin:
-            raise ValueError(f"expected {spec.cin} input channels, got {cin}")
-        sigma = power_iterate(w_bar, u.data, v.data, spec)
-        oh, ow = spec.out_hw(h, w_)
-        ctot = spec.cout + (cin if cat_input else 0)
-        out = _new_act((b, ctot) if is_vec else (b, ctot, oh, ow), x)
-        mode = 1 if spec.kind == "convT" else 0
-        g = _geom(b, h, w_, cin, oh, ow, spec.cout, spec, mode, cin, ctot, spec.strides_fwd())
-        off = cin * 4 if cat_input else 0
-        fl, by = _conv_work(spec, b, h, w_, oh, ow)
-        _timed_call("conv_gemm", fl, by, "lb_conv_gemm", ptr(x), ptr(w_bar), sigma.data_ptr() + 4, ptr(bias),
-                    out.data_ptr() + off, g)
-        if cat_input:
-            if (oh, ow) != (h, w_):
-                raise ValueError("cat_input needs a size-preserving conv")
-            call("lb_copy_rows", ptr(x), cin, ptr(out), ctot, b * h * w_, cin, 0)
-        ctx.save_for_backward(x, w_bar, sigma)
-        ctx.u, ctx.v = u, v                      # LIVE u/v: the reference's backward reads them at backward time
-        ctx.bias_param, ctx.w_param = bias, w_bar
-        ctx.spec, ctx.cat_input, ctx.dims = spec, cat_input, (b, h, w_, cin, oh, ow, ctot, is_vec)
-        return out
-
-    @staticmethod
-    def backward(ctx, gout):
-        x, w_bar, sigma = ctx.saved_tensors
-        spec = ctx.spec
-        b, h, w_, cin, oh, ow, ctot, is_vec = ctx.dims
-        gout = _as_act(gout)
-        off = cin * 4 if ctx.cat_input else 0
-        gy_ptr = gout.data_ptr() + off            # gradient of the conv output slice, row stride ctot
-        dx = dw_ret = dbias_ret = None
-        fl, by = _conv_work(spec, b, h, w_, oh, ow)
-        if ctx.needs_input_grad[0]:
-            dx = torch.empty_like(x)
-            mode = 0 if spec.kind == "convT" else 1
-            g = _geom(b, oh, ow, spec.cout, h, w_, cin, spec, mode, ctot, cin, spec.strides_dgrad())
-            _timed_call("conv_gemm", fl, by, "lb_conv_gemm", gy_ptr, ptr(w_bar), sigma.data_ptr() + 4, None, ptr(dx), g)
-            if ctx.cat_input:
-                call("lb_copy_rows", ptr(gout), ctot, ptr(dx), cin, b * h * w_, cin, 1)
-        if ctx.needs_input_grad[1]:
-            dwn = torch.zeros_like(w_bar, memory_format=torch.contiguous_format)
-            t = spec.kh * spec.kw
-            if spec.kind == "convT":
-                # dense = x (cin), gathered = dy (cout): dw[ci][co][ty][tx]
-                g = _geom(b, oh, ow, spec.cout, h, w_, cin, spec, 0, ctot, cin, (t, spec.cout * t, spec.kw, 1))
-                _timed_call("conv_wgrad", fl, by, "lb_conv_wgrad", gy_ptr, ptr(x), ptr(dwn), g)
-            else:
-                # dense = dy (cout), gathered = x (cin): dw[co][ci][ty][tx]
-                g = _geom(b, h, w_, cin, oh, ow, spec.cout, spec, 0, cin, ctot, (t, cin * t, spec.kw, 1))
-                _timed_call("conv_wgrad", fl, by, "lb_conv_wgrad", ptr(x), gy_ptr, ptr(dwn), g)
-            grad_w, dw_ret = _grad_sink(ctx.w_param)
-            height, width = spec.sn_shape
-            work = torch.empty(2, dtype=torch.float64, device=x.device)
-            call("lb_sn_weight_grad", ptr(dwn), ptr(w_bar), ptr(ctx.u.data), ptr(ctx.v.data), ptr(sigma), ptr(grad_w),
-                 height, width, 0, ptr(work))
-        if ctx.bias_param is not None and ctx.needs_input_grad[4]:
-            dbias, dbias_ret = _grad_sink(ctx.bias_param)
-            call("lb_colsum", gy_ptr, b * oh * ow, spec.cout, ctot, ptr(dbias))
-        return dx, dw_ret, None, None, dbias_ret, None, None
-
-
-# ------------------------------------------------------------------------------------------
 # softmax
 # ------------------------------------------------------------------------------------------
 class SoftmaxPixelsFn(torch.autograd.Function):
@@ -587,5 +451,5 @@ def gate(x, y, gamma, strict_reference=True):
     return GateFn.apply(x, y, gamma, strict_reference)
 
 
-def sn_conv(x, w_bar, u, v, bias, spec, cat_input=False):
-    return SNConvFn.apply(x, w_bar, u, v, bias, spec, cat_input)
+# the convolution family lives in conv_fn.py (imports helpers from this module, hence the late import)
+from .conv_fn import ConvSpec, SNConvFn, invalidate_packs, power_iterate, sn_conv  # noqa: E402,F401

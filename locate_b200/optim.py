@@ -10,6 +10,7 @@ import torch
 from torch.optim import Optimizer
 
 from ._lib import call, ptr
+from .conv_fn import invalidate_packs
 
 _ALIGN = 4   # floats: keeps every view 16-byte aligned for the vectorised kernels
 
@@ -84,6 +85,7 @@ class Nadam(Optimizer):
     def step(self, closure=None):
         loss = closure() if closure is not None else None
         self._ensure()
+        invalidate_packs()                 # the raw-pointer update below does not bump torch's version counters
         for group, a in zip(self.param_groups, self._arenas):
             if a is None:
                 continue

@@ -31,6 +31,7 @@ def dev(t):
 @pytest.fixture(autouse=True)
 def _cfg():
     L.config.reset()
+    L.configure(PRECISION="fp32")       # this file pins the fp32 path; tests/test_gpu_bf16.py covers the tensor-core path
     yield
     L.config.reset()
 
