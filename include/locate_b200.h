@@ -141,7 +141,9 @@ int lb_wgrad_tc_supported(const lb_conv_geom* g);
 int lb_wgrad_tc(const void* gathered_bf16, const void* dense_bf16, float* dwp, const lb_conv_geom* g, lb_stream_t stream);
 /* fp32 -> bf16 producers of GEMM operands: plain cast, and RootTanh fused with the cast (activation.py:9-16) */
 int lb_cast_bf16(const float* x, void* y, size_t n, lb_stream_t stream);
-int lb_cast_bf16_rows(const float* src, int ld_src, void* dst, int ld_dst, int64_t rows, int cols, lb_stream_t stream);
+/* row-strided variant: dst[r*ld_dst + c] = bf16(f(src[r*ld_src + c])); f = identity (growth 0) or RootTanh (growth >= 1) */
+int lb_cast_bf16_rows(const float* src, int ld_src, void* dst, int ld_dst, int64_t rows, int cols, int growth,
+                      lb_stream_t stream);
 int lb_roottanh_fwd_bf16(const float* x, void* y, size_t n, int growth, lb_stream_t stream);
 
 /* column sum: out[c] += sum_rows x[row*ld + c]  (bias gradients) */

@@ -52,7 +52,7 @@ _SIGNATURES = {
     "lb_conv_tc_pack": ([P, P, POINTER(ConvGeom), P], c_int),
     "lb_conv_tc_gemm": ([P, P, P, P, P, POINTER(ConvGeom), P], c_int),
     "lb_cast_bf16": ([P, P, c_size_t, P], c_int),
-    "lb_cast_bf16_rows": ([P, c_int, P, c_int, c_int64, c_int, P], c_int),
+    "lb_cast_bf16_rows": ([P, c_int, P, c_int, c_int64, c_int, c_int, P], c_int),
     "lb_roottanh_fwd_bf16": ([P, P, c_size_t, c_int, P], c_int),
     "lb_colsum": ([P, c_int64, c_int, c_int, P, P], c_int),
     "lb_softmax_pixels_fwd": ([P, P, c_int, c_int, c_int, P], c_int),

@@ -86,7 +86,8 @@ def _bf16_like(t):
 
 def _packed_weight(w_bar, g, tag):
     """bf16 [tap][n][k] copy of the master weight for geometry g (cached per weight version)."""
-    key = (_PACK_EPOCH[0], w_bar._version, w_bar.data_ptr())
+    epoch = getattr(w_bar, "_lb_epoch", _PACK_EPOCH)       # per-optimizer counter when the weight lives in a Nadam arena
+    key = (_PACK_EPOCH[0], epoch[0], w_bar._version, w_bar.data_ptr())
     cache = getattr(w_bar, "_lb_pack", None)
     if cache is None or cache[0] != key:
         cache = (key, {})
@@ -129,23 +130,39 @@ class SNConvFn(torch.autograd.Function):
         off = cin * 4 if cat_input else 0
         t = spec.taps
         mode = 1 if spec.kind == "convT" else 0
-        g_fwd = _geom(b, h, w_, cin, oh, ow, spec.cout, spec, mode, cin, ctot, spec.strides_fwd())
-        g_dgrad = _geom(b, oh, ow, spec.cout, h, w_, cin, spec, 1 - mode, spec.cout, cin, spec.strides_dgrad())
-        if spec.kind == "convT":      # dense = x (cin), gathered = dy (cout): dw[ci][co][tap]
-            g_wgrad = _geom(b, oh, ow, spec.cout, h, w_, cin, spec, 0, spec.cout, cin, (t, spec.cout * t, spec.kw, 1))
-        else:                         # dense = dy (cout), gathered = x (cin): dw[co][ci][tap]
-            g_wgrad = _geom(b, h, w_, cin, oh, ow, spec.cout, spec, 0, cin, spec.cout, (t, cin * t, spec.kw, 1))
         lib = _lib.lib()
-        tc = (CFG.PRECISION == "bf16" and lib.lb_conv_tc_supported(ctypes.byref(g_fwd)) == 1
-              and lib.lb_conv_tc_supported(ctypes.byref(g_dgrad)) == 1 and lib.lb_wgrad_tc_supported(ctypes.byref(g_wgrad)) == 1)
+
+        def geoms(ld_x, ld_dy):
+            gf = _geom(b, h, w_, cin, oh, ow, spec.cout, spec, mode, ld_x, ctot, spec.strides_fwd())
+            gd = _geom(b, oh, ow, spec.cout, h, w_, cin, spec, 1 - mode, ld_dy, cin, spec.strides_dgrad())
+            if spec.kind == "convT":      # dense = x (cin), gathered = dy (cout): dw[ci][co][tap]
+                gw = _geom(b, oh, ow, spec.cout, h, w_, cin, spec, 0, ld_dy, ld_x, (t, spec.cout * t, spec.kw, 1))
+            else:                         # dense = dy (cout), gathered = x (cin): dw[co][ci][tap]
+                gw = _geom(b, h, w_, cin, oh, ow, spec.cout, spec, 0, ld_x, ld_dy, (t, cin * t, spec.kw, 1))
+            return gf, gd, gw
+
+        # tensor-core operands are bf16 rows padded to 16 bytes (TMA stride rule); channel counts are arbitrary
+        cin_p, cout_p = (cin + 7) // 8 * 8, (spec.cout + 7) // 8 * 8
+        tc = False
+        if CFG.PRECISION == "bf16":
+            g_fwd, g_dgrad, g_wgrad = geoms(cin_p, cout_p)
+            tc = (lib.lb_conv_tc_supported(ctypes.byref(g_fwd)) == 1 and lib.lb_conv_tc_supported(ctypes.byref(g_dgrad)) == 1
+                  and lib.lb_wgrad_tc_supported(ctypes.byref(g_wgrad)) == 1)
+        if not tc:
+            g_fwd, g_dgrad, g_wgrad = geoms(cin, spec.cout)
         fl, by = _conv_work(spec, b, h, w_, oh, ow)
         n = x.numel()
         if tc:
-            a = _bf16_like(x)
-            if pre_act:
-                call("lb_roottanh_fwd_bf16", ptr(x), ptr(a), n, CFG.ROOTTANH_GROWTH)
+            growth = CFG.ROOTTANH_GROWTH if pre_act else 0
+            if cin_p == cin:
+                a = _bf16_like(x)
+                if pre_act:
+                    call("lb_roottanh_fwd_bf16", ptr(x), ptr(a), n, growth)
+                else:
+                    call("lb_cast_bf16", ptr(x), ptr(a), n)
             else:
-                call("lb_cast_bf16", ptr(x), ptr(a), n)
+                a = torch.empty((n // cin, cin_p), dtype=torch.bfloat16, device=x.device)
+                call("lb_cast_bf16_rows", ptr(x), cin, ptr(a), cin_p, n // cin, cin, growth)
             pk = _packed_weight(w_bar, g_fwd, "fwd")
             _timed_call("conv_tc", fl, by / 2, "lb_conv_tc_gemm", ptr(a), ptr(pk), sigma.data_ptr() + 4, ptr(bias),
                         out.data_ptr() + off, g_fwd)
@@ -177,10 +194,11 @@ class SNConvFn(torch.autograd.Function):
         t = spec.taps
         height, width = spec.sn_shape
         if tc:
-            gy = torch.empty((rows, spec.cout), dtype=torch.bfloat16, device=gout.device)
-            call("lb_cast_bf16_rows", gout.data_ptr() + off, ctot, ptr(gy), spec.cout, rows, spec.cout)
+            cout_p = (spec.cout + 7) // 8 * 8
+            gy = torch.empty((rows, cout_p), dtype=torch.bfloat16, device=gout.device)
+            call("lb_cast_bf16_rows", gout.data_ptr() + off, ctot, ptr(gy), cout_p, rows, spec.cout, 0)
             if need_dx:
-                dx = _new_act(tuple(a.shape), gout)
+                dx = _new_act((b, cin) if gout.dim() == 2 else (b, cin, h, w_), gout)
                 pk = _packed_weight(w_bar, g_dgrad, "dgrad")
                 _timed_call("conv_tc", fl, by / 2, "lb_conv_tc_gemm", ptr(gy), ptr(pk), sigma.data_ptr() + 4, None, ptr(dx), g_dgrad)
             if need_dw:

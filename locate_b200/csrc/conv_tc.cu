@@ -36,7 +36,7 @@ struct TcParams {
   int sp;                             // destination parity step (stride in mode 1, else 1)
   int tile_w, tile_h, tile_b;         // box dims, product = 128
   int tiles_w, tiles_h;
-  int block_n, kchunks, stages;
+  int block_n, kchunks, stages, splits;
   int kh, kw, stride, pad, mode;
   int rows_per_tap;                   // rows of Wp per tap (= out_c)
   int view_empty;                     // bit v set: parity view v has no pixels
@@ -54,7 +54,7 @@ __device__ __forceinline__ void tap_span(int mode, int s, int pad, int k, int pa
 }
 __device__ __forceinline__ int floordiv(int a, int b) { int q = a / b; return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q; }
 
-__global__ void __launch_bounds__(192, 1) k_conv_tc(const __grid_constant__ TcMaps maps, const TcParams p) {
+__global__ void __launch_bounds__(192, 2) k_conv_tc(const __grid_constant__ TcMaps maps, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[8], bar_empty[8], bar_acc;
   __shared__ uint32_t tmem_slot;
@@ -70,12 +70,17 @@ __global__ void __launch_bounds__(192, 1) k_conv_tc(const __grid_constant__ TcMa
   const int th = t % p.tiles_h; t /= p.tiles_h;
   const int x0 = tw * p.tile_w, y0 = th * p.tile_h, b0 = t * p.tile_b;
   const int n0 = blockIdx.y * p.block_n;
-  const int py = blockIdx.z / p.sp, px = blockIdx.z % p.sp;
+  const int phase = blockIdx.z / p.splits, split = blockIdx.z % p.splits;
+  const int py = phase / p.sp, px = phase % p.sp;
 
   int ty0, tys, tyc, tx0, txs, txc;
   tap_span(p.mode, p.stride, p.pad, p.kh, py, ty0, tys, tyc);
   tap_span(p.mode, p.stride, p.pad, p.kw, px, tx0, txs, txc);
-  const int iters = tyc * txc * p.kchunks;
+  // split-K: this CTA reduces the flat (tap, k-chunk) range [it_begin, it_end) and adds its partial sum atomically
+  const int iters_all = tyc * txc * p.kchunks;
+  const int per_split = (iters_all + p.splits - 1) / p.splits;
+  const int it_begin = min(iters_all, split * per_split);
+  const int iters = min(iters_all, it_begin + per_split) - it_begin;
   const uint32_t tmem_cols = p.block_n <= 32 ? 32 : p.block_n <= 64 ? 64 : p.block_n <= 128 ? 128 : 256;
 
   if (threadIdx.x == 0) {
@@ -96,33 +101,29 @@ __global__ void __launch_bounds__(192, 1) k_conv_tc(const __grid_constant__ TcMa
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (tc::elect_one()) {
-      int it = 0;
-      for (int iy = 0; iy < tyc; ++iy) {
-        const int ty = ty0 + iy * tys;
-        for (int ix = 0; ix < txc; ++ix) {
-          const int tx = tx0 + ix * txs;
-          int view = 0, dy, dx;
-          if (p.mode == 0) {
-            const int ay = floordiv(ty - p.pad, p.stride), ax = floordiv(tx - p.pad, p.stride);
-            const int qy = (ty - p.pad) - ay * p.stride, qx = (tx - p.pad) - ax * p.stride;
-            view = qy * p.stride + qx;
-            dy = ay; dx = ax;
-          } else {
-            dy = (py + p.pad - ty) / p.stride;
-            dx = (px + p.pad - tx) / p.stride;
-          }
-          const int cb = ((p.view_empty >> view) & 1) ? p.batch : b0;     // empty view: force the box out of range -> zeros
-          const int wrow = (ty * p.kw + tx) * p.rows_per_tap + n0;
-          for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
-            const int s = it % p.stages;
-            const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-            tc::mbar_wait(&bar_empty[s], ph ^ 1u);
-            uint8_t* sa = smem + s * stage_bytes;
-            tc::mbar_arrive_expect_tx(&bar_full[s], (uint32_t)stage_bytes);
-            tc::tma_load_4d(sa, &maps.a[view], &bar_full[s], kc * kBlockK, x0 + dx, y0 + dy, cb);
-            tc::tma_load_2d(sa + kABytes, &maps.b, &bar_full[s], kc * kBlockK, wrow);
-          }
+      for (int it = 0; it < iters; ++it) {
+        const int flat = it_begin + it;
+        const int kc = flat % p.kchunks, tap = flat / p.kchunks;
+        const int ty = ty0 + (tap / txc) * tys, tx = tx0 + (tap % txc) * txs;
+        int view = 0, dy, dx;
+        if (p.mode == 0) {
+          const int ay = floordiv(ty - p.pad, p.stride), ax = floordiv(tx - p.pad, p.stride);
+          const int qy = (ty - p.pad) - ay * p.stride, qx = (tx - p.pad) - ax * p.stride;
+          view = qy * p.stride + qx;
+          dy = ay; dx = ax;
+        } else {
+          dy = (py + p.pad - ty) / p.stride;
+          dx = (px + p.pad - tx) / p.stride;
         }
+        const int cb = ((p.view_empty >> view) & 1) ? p.batch : b0;     // empty view: force the box out of range -> zeros
+        const int wrow = (ty * p.kw + tx) * p.rows_per_tap + n0;
+        const int s = it % p.stages;
+        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+        tc::mbar_wait(&bar_empty[s], ph ^ 1u);
+        uint8_t* sa = smem + s * stage_bytes;
+        tc::mbar_arrive_expect_tx(&bar_full[s], (uint32_t)stage_bytes);
+        tc::tma_load_4d(sa, &maps.a[view], &bar_full[s], kc * kBlockK, x0 + dx, y0 + dy, cb);
+        tc::tma_load_2d(sa + kABytes, &maps.b, &bar_full[s], kc * kBlockK, wrow);
       }
     }
   } else if (warp == 1) {
@@ -172,9 +173,15 @@ __global__ void __launch_bounds__(192, 1) k_conv_tc(const __grid_constant__ TcMa
       }
       const int n = n0 + c0;
       if (valid && n < p.out_c) {
+        const bool add_bias = p.bias && split == 0;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = v[i] * alpha + ((p.bias && n + i < p.out_c) ? __ldg(p.bias + n + i) : 0.0f);
-        if (vec && n + 15 < p.out_c) {
+        for (int i = 0; i < 16; ++i) v[i] = v[i] * alpha + ((add_bias && n + i < p.out_c) ? __ldg(p.bias + n + i) : 0.0f);
+        if (p.splits > 1) {
+          if (iters > 0 || add_bias) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) if (n + i < p.out_c) atomicAdd(dst + n + i, v[i]);
+          }
+        } else if (vec && n + 15 < p.out_c) {
 #pragma unroll
           for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst + n + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
         } else {
@@ -225,9 +232,8 @@ int pow2_ceil(int v) { int r = 1; while (r < v) r <<= 1; return r; }
 bool tc_geom_ok(const lb_conv_geom* g) {
   if (!g) return false;
   if (g->stride != 1 && g->stride != 2) return false;
-  if (g->in_c % 8 || g->ld_in % 8) return false;           // TMA: 16-byte global strides
-  if (g->in_c < 16 || g->out_c < 8) return false;
-  if (g->kh * g->kw > 32) return false;                    // full-extent feature-attention convs stay on the SIMT path
+  if (g->ld_in % 8) return false;                          // TMA: 16-byte global strides (pad the row, not the channels)
+  if (g->in_c < 1 || g->out_c < 1 || g->kh * g->kw > 1024) return false;
   return true;
 }
 
@@ -291,7 +297,7 @@ extern "C" int lb_conv_tc_gemm(const void* in_bf16, const void* w_packed, const 
   p.rows_per_tap = g->out_c;
   p.alpha = alpha; p.bias = bias; p.out = out;
   const int stage_bytes = kABytes + bn * kBlockK * 2;
-  p.stages = 4;
+  p.stages = stage_bytes >= 32 * 1024 ? 3 : 4;             // <= ~97 KB per CTA: two CTAs per SM overlap epilogue and mainloop
   const int smem_bytes = p.stages * stage_bytes + 1024;
 
   // source views: mode 0 with stride 2 -> 4 parity views; otherwise one dense view
@@ -326,8 +332,25 @@ extern "C" int lb_conv_tc_gemm(const void* in_bf16, const void* w_packed, const 
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  dim3 grid(p.tiles_w * p.tiles_h * tiles_b, (g->out_c + bn - 1) / bn, p.sp * p.sp);
-  LB_REQUIRE(grid.y <= 65535);
+  // split-K for weight-bound layers whose output tiling cannot fill the GPU (e.g. 5x5 1024->1024 at 2x2)
+  const int n_tiles = (g->out_c + bn - 1) / bn;
+  const long long ctas = (long long)p.tiles_w * p.tiles_h * tiles_b * n_tiles * p.sp * p.sp;
+  const int taps_eff = g->mode == 1 ? ((g->kh + p.sp - 1) / p.sp) * ((g->kw + p.sp - 1) / p.sp) : g->kh * g->kw;
+  const int iters_est = taps_eff * p.kchunks;
+  p.splits = 1;
+  if (ctas * 2 <= LB_SMS && iters_est >= 8) {
+    long long want = (LB_SMS * 2 + ctas - 1) / ctas;
+    if (want > iters_est / 4) want = iters_est / 4;
+    if (want > 64) want = 64;
+    if (want > 1) p.splits = (int)want;
+  }
+  if (p.splits > 1) {
+    cudaError_t e = cudaMemset2DAsync(out, (size_t)g->ld_out * 4, 0, (size_t)g->out_c * 4,
+                                      (size_t)g->batch * g->out_h * g->out_w, lb_s(s));
+    if (e != cudaSuccess) return (int)e;
+  }
+  dim3 grid(p.tiles_w * p.tiles_h * tiles_b, n_tiles, p.sp * p.sp * p.splits);
+  LB_REQUIRE(grid.y <= 65535 && grid.z <= 65535);
   k_conv_tc<<<grid, 192, smem_bytes, lb_s(s)>>>(maps, p);
   LB_LAUNCH_CHECK();
   return LB_OK;
@@ -360,28 +383,44 @@ extern "C" int lb_cast_bf16(const float* x, void* y, size_t n, lb_stream_t s) {
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
-// row-strided cast: dst[r*ld_dst + c] = bf16(src[r*ld_src + c]) (gradient of a concat slice -> dense GEMM operand)
-__global__ void __launch_bounds__(256) k_cast_rows(const float* __restrict__ src, int ld_src, __nv_bfloat16* __restrict__ dst, int ld_dst,
-                                                  size_t rows, int cols4) {
-  const size_t total = rows * (size_t)cols4;
+// row-strided producers: dst[r*ld_dst + c] = bf16(f(src[r*ld_src + c])), c < cols.  Used for the gradient of a concat
+// slice and for operands whose channel count is not a multiple of 8 (rows padded to 16 bytes for TMA).
+template <typename F>
+__global__ void __launch_bounds__(256) k_rows_to_bf16(const float* __restrict__ src, int ld_src, __nv_bfloat16* __restrict__ dst,
+                                                     int ld_dst, size_t rows, int cols, int vec, F f) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const size_t r = i / cols4;
-    const int c = (int)(i % cols4) * 4;
-    const float4 v = lb_ld4(src + r * ld_src + c);
-    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-    uint2 pk;
-    pk.x = *reinterpret_cast<uint32_t*>(&lo);
-    pk.y = *reinterpret_cast<uint32_t*>(&hi);
-    *reinterpret_cast<uint2*>(dst + r * ld_dst + c) = pk;
+  if (vec) {
+    const int cols4 = cols >> 2;
+    const size_t total = rows * (size_t)cols4;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+      const size_t r = i / cols4;
+      const int c = (int)(i % cols4) * 4;
+      const float4 v = lb_ld4(src + r * ld_src + c);
+      __nv_bfloat162 lo = __floats2bfloat162_rn(f(v.x), f(v.y)), hi = __floats2bfloat162_rn(f(v.z), f(v.w));
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(dst + r * ld_dst + c) = pk;
+    }
+  } else {
+    const size_t total = rows * (size_t)cols;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+      const size_t r = i / cols;
+      const int c = (int)(i % cols);
+      dst[r * ld_dst + c] = __float2bfloat16(f(src[r * ld_src + c]));
+    }
   }
 }
-extern "C" int lb_cast_bf16_rows(const float* src, int ld_src, void* dst, int ld_dst, int64_t rows, int cols, lb_stream_t s) {
-  LB_REQUIRE(src && dst && rows >= 0 && cols > 0 && ld_src >= cols && ld_dst >= cols);
+// growth = 0: plain cast; growth >= 1: RootTanh fused with the cast
+extern "C" int lb_cast_bf16_rows(const float* src, int ld_src, void* dst, int ld_dst, int64_t rows, int cols, int growth, lb_stream_t s) {
+  LB_REQUIRE(src && dst && rows >= 0 && cols > 0 && ld_src >= cols && ld_dst >= cols && growth >= 0);
   if (rows == 0) return LB_OK;
-  if ((cols & 3) || (ld_src & 3) || (ld_dst & 3) || !lb_aligned16(src) || (reinterpret_cast<uintptr_t>(dst) & 7)) return LB_EALIGN;
-  k_cast_rows<<<lb_grid_1d((size_t)rows * (cols / 4), 256), 256, 0, lb_s(s)>>>(src, ld_src, reinterpret_cast<__nv_bfloat16*>(dst), ld_dst,
-                                                                           (size_t)rows, cols / 4);
+  const int vec = (!(cols & 3) && !(ld_src & 3) && !(ld_dst & 3) && lb_aligned16(src) && !(reinterpret_cast<uintptr_t>(dst) & 7)) ? 1 : 0;
+  const int grid = lb_grid_1d((size_t)rows * (vec ? cols / 4 : cols), 256);
+  __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dst);
+  if (growth == 0) k_rows_to_bf16<<<grid, 256, 0, lb_s(s)>>>(src, ld_src, d, ld_dst, (size_t)rows, cols, vec, IdentF{});
+  else if (growth == 4) k_rows_to_bf16<<<grid, 256, 0, lb_s(s)>>>(src, ld_src, d, ld_dst, (size_t)rows, cols, vec, RootTanh4F{});
+  else k_rows_to_bf16<<<grid, 256, 0, lb_s(s)>>>(src, ld_src, d, ld_dst, (size_t)rows, cols, vec, RootTanhGF{1.0f / growth});
   LB_LAUNCH_CHECK();
   return LB_OK;
 }

@@ -170,9 +170,8 @@ int wg_pow2_ceil(int v) { int r = 1; while (r < v) r <<= 1; return r; }
 bool wg_geom_ok(const lb_conv_geom* g) {
   if (!g || g->mode != 0) return false;
   if (g->stride != 1 && g->stride != 2) return false;
-  if (g->in_c % 8 || g->ld_in % 8 || g->out_c % 8 || g->ld_out % 8) return false;
-  if (g->in_c < 16 || g->out_c < 16) return false;
-  if (g->kh * g->kw > 32) return false;
+  if (g->ld_in % 8 || g->ld_out % 8) return false;         // TMA: 16-byte global strides (rows padded, channels arbitrary)
+  if (g->in_c < 1 || g->out_c < 1 || g->kh * g->kw > 1024) return false;
   return true;
 }
 

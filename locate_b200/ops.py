@@ -39,10 +39,10 @@ class KernelTimer:
         global _TIMER
         _TIMER = None
 
-    def summary(self):
+    def summary(self, by_label=False):
         out = {}
-        for name, flops, nbytes, e0, e1 in self.records:
-            d = out.setdefault(name, dict(launches=0, flops=0.0, bytes=0.0, ms=0.0))
+        for name, flops, nbytes, e0, e1, label in self.records:
+            d = out.setdefault((name, label) if by_label else name, dict(launches=0, flops=0.0, bytes=0.0, ms=0.0))
             d["launches"] += 1
             d["flops"] += flops
             d["bytes"] += nbytes
@@ -57,7 +57,10 @@ def _timed_call(family, flops, nbytes, name, *args):
     e0.record()
     call(name, *args)
     e1.record()
-    _TIMER.records.append((family, flops, nbytes, e0, e1))
+    g = args[-1]
+    label = (f"{g.kh}x{g.kw}s{g.stride}m{g.mode} {g.in_c}->{g.out_c} in{g.in_h}x{g.in_w} out{g.out_h}x{g.out_w} b{g.batch}"
+             if hasattr(g, "in_c") else "")
+    _TIMER.records.append((family, flops, nbytes, e0, e1, label))
 
 
 def _conv_work(spec, b, h, w_, oh, ow):

@@ -10,7 +10,7 @@ import torch
 from torch.optim import Optimizer
 
 from ._lib import call, ptr
-from .conv_fn import invalidate_packs
+from .conv_fn import invalidate_packs  # noqa: F401  (re-exported for manual weight edits)
 
 _ALIGN = 4   # floats: keeps every view 16-byte aligned for the vectorised kernels
 
@@ -40,6 +40,7 @@ class Nadam(Optimizer):
                 offsets.append(total)
                 total += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
             dev = train[0].device
+            epoch = [0]                    # bumped by step(): invalidates the bf16 weight packs of THIS arena only
             flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
             flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
             with torch.no_grad():
@@ -51,9 +52,10 @@ class Nadam(Optimizer):
                         gview.copy_(p.grad)
                     p.data = flat_p[off:off + n].view(p.shape)
                     p._lb_grad = gview
+                    p._lb_epoch = epoch
                     p.grad = gview
             arenas.append(dict(param=flat_p, grad=flat_g, exp_avg=torch.zeros_like(flat_p),
-                               exp_avg_sq=torch.zeros_like(flat_p), step=0, m_schedule=1.0, n=total))
+                               exp_avg_sq=torch.zeros_like(flat_p), step=0, m_schedule=1.0, n=total, epoch=epoch))
         self._arenas = arenas
 
     def _ensure(self):
@@ -85,10 +87,10 @@ class Nadam(Optimizer):
     def step(self, closure=None):
         loss = closure() if closure is not None else None
         self._ensure()
-        invalidate_packs()                 # the raw-pointer update below does not bump torch's version counters
         for group, a in zip(self.param_groups, self._arenas):
             if a is None:
                 continue
+            a["epoch"][0] += 1             # the raw-pointer update below does not bump torch's version counters
             beta1, beta2 = group["betas"]
             decay = group["schedule_decay"]
             a["step"] += 1

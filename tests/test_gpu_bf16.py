@@ -106,3 +106,64 @@ def test_step_bf16_vs_oracle_default_width():
         assert total < 1.5e-2, f"{tag}: relative gradient-norm error {total:.3e}"
         worst = max((rel_l2(mine[tag][k], grads[tag][k]), k) for k in keys if grads[tag][k].norm() > 1e-6 * b.norm())
         assert worst[0] < 5e-2, worst
+
+
+@pytest.mark.parametrize("args,shape", [
+    ((3, 32, False, 2, False, 2, 1), (3, 3, 32, 32)),        # D stem: 5x5 s2 3->3 + 1x1 3->32 (3-channel rows padded to 8)
+    ((48, 3, False, 1, False, 2, 1), (2, 48, 16, 16)),       # G out conv: 3x3 48->48 + 1x1 48->3
+    ((256, 1, False, 1, False, 2, 1), (4, 256, 1, 1)),       # D head at 1x1: split-K path, Cout = 1
+])
+def test_odd_channel_layers_on_tensor_cores(args, shape):
+    from locate_b200 import ops
+    torch.manual_seed(5)
+    m = layers.DeepResidualConv(*args)
+    state = {k: v.clone() for k, v in m.state_dict().items()}
+    gen = torch.Generator().manual_seed(6)
+    x = torch.randn(shape, generator=gen)
+    st = O.load_state({k: v.double() for k, v in state.items()})
+    xo = x.double().requires_grad_(True)
+    yo = O.deep_conv(st, "", xo, O.OracleConfig(), args[0], args[1], args[2], args[3], args[4], args[6])
+    g = torch.randn(yo.shape, generator=gen)
+    yo.backward(g.double())
+    m = m.to(DEV)
+    xd = x.to(DEV).requires_grad_(True)
+    with ops.KernelTimer() as t:
+        yd = m(xd)
+        yd.backward(g.to(DEV))
+    torch.cuda.synchronize()
+    assert "conv_gemm" not in t.summary() and "conv_wgrad" not in t.summary(), t.summary().keys()
+    assert rel_l2(yd, yo) < 1e-2
+    assert rel_l2(xd.grad, xo.grad) < 1.5e-2
+    for k, p in m.named_parameters():
+        if p.requires_grad:
+            assert rel_l2(p.grad, st[k].grad) < 2e-2, k
+
+
+def test_cat_skip_and_feature_attention_on_tensor_cores():
+    """CatModule conv 3->29 written into the concat slice, and the full-extent (S x 1)/(1 x S) feature-attention convs."""
+    from locate_b200 import ops
+    torch.manual_seed(7)
+    gen = torch.Generator().manual_seed(8)
+    for build, shape, run in (
+            (lambda: layers.Scale(3, 32, 2, False), (2, 3, 16, 16), lambda st, x: O.skip_path(st, "", x, 3, 32, 2, False)),
+            (lambda: layers.feature_attention(16, 64), (2, 64, 16, 16), lambda st, x: O.feature_attention(st, "", x, 16, 64, 4)),
+    ):
+        m = build()
+        st = O.load_state({k: v.double().clone() for k, v in m.state_dict().items()})
+        x = torch.randn(shape, generator=gen)
+        xo = x.double().requires_grad_(True)
+        yo = run(st, xo)
+        g = torch.randn(yo.shape, generator=gen)
+        yo.backward(g.double())
+        m = m.to(DEV)
+        xd = x.to(DEV).requires_grad_(True)
+        with ops.KernelTimer() as t:
+            yd = m(xd)
+            yd.backward(g.to(DEV))
+        torch.cuda.synchronize()
+        assert "conv_gemm" not in t.summary(), t.summary().keys()
+        assert rel_l2(yd, yo) < 1e-2
+        assert rel_l2(xd.grad, xo.grad) < 2e-2
+        for k, p in m.named_parameters():
+            if p.requires_grad:
+                assert rel_l2(p.grad, st[k].grad) < 3e-2, k
