@@ -188,11 +188,14 @@ int lb_d_loss(const float* d_true, const float* d_fake, const float* d_aug, cons
 int lb_g_loss(const float* d_fake, int n_local, double n_global, float* out, float* g_fake, lb_stream_t stream);
 
 /* ---- Nadam over a flat parameter arena                                libs/nadam.py:56-87
- * c_grad = lr*(1-mu_t)/(1-m_schedule_new), c_mom = lr*mu_{t+1}/(1-m_schedule_next),
- * bias2 = 1 - beta2^t are computed on the host (scalars of the step counter). */
+ * hyper (device float[3]) = {c_grad = lr*(1-mu_t)/(1-m_schedule_new), c_mom = lr*mu_{t+1}/(1-m_schedule_next),
+ * 1/(1 - beta2^t)}, produced by lb_nadam_schedule. */
 int lb_nadam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n,
-                  float beta1, float beta2, float eps, float c_grad, float c_mom, float bias2,
-                  lb_stream_t stream);
+                  float beta1, float beta2, float eps, const float* hyper, lb_stream_t stream);
+/* advances the device-resident schedule state = {t, m_schedule} (double[2], start {0, 1}) by one step and writes
+ * hyper = {c_grad, c_mom, 1/bias2} (float[3]) -- on the device so a captured CUDA graph of the step replays. */
+int lb_nadam_schedule(double* state, float* hyper, double lr, double beta1, double beta2, double schedule_decay,
+                      lb_stream_t stream);
 /* fill / scale helpers used around the step */
 int lb_fill(float* x, size_t n, float value, lb_stream_t stream);
 int lb_scale(float* x, size_t n, float factor, lb_stream_t stream);

@@ -71,7 +71,8 @@ _SIGNATURES = {
     "lb_loss_sums": ([P, P, c_int, P, P], c_int),
     "lb_d_loss": ([P, P, P, P, c_int, c_double, c_float, P, P, P, P, P], c_int),
     "lb_g_loss": ([P, c_int, c_double, P, P, P], c_int),
-    "lb_nadam_step": ([P, P, P, P, c_size_t, c_float, c_float, c_float, c_float, c_float, c_float, P], c_int),
+    "lb_nadam_step": ([P, P, P, P, c_size_t, c_float, c_float, c_float, P, P], c_int),
+    "lb_nadam_schedule": ([P, P, c_double, c_double, c_double, c_double, P], c_int),
     "lb_fill": ([P, c_size_t, c_float, P], c_int),
     "lb_scale": ([P, c_size_t, c_float, P], c_int),
 }

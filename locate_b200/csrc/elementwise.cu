@@ -213,9 +213,33 @@ extern "C" int lb_gate_bwd(const float* x, const float* y, const float* gamma, c
 // ------------------------------------------------------------------------------------------
 // Nadam over a flat arena (libs/nadam.py:75-87)
 // ------------------------------------------------------------------------------------------
+// The step-dependent scalars live on the device so a captured CUDA graph of the whole training step replays
+// correctly: k_nadam_schedule advances state = {t, m_schedule} and writes hyper = {c_grad, c_mom, 1/bias2}
+// (nadam.py:62-73,78,82,85) in double precision; k_nadam reads them.
+__global__ void k_nadam_schedule(double* __restrict__ state, float* __restrict__ hyper, double lr, double b1, double b2, double decay) {
+  const double t = state[0] + 1.0;
+  const double mu_t = b1 * (1.0 - 0.5 * pow(0.96, t * decay));
+  const double mu_next = b1 * (1.0 - 0.5 * pow(0.96, (t + 1.0) * decay));
+  const double sched_new = state[1] * mu_t;
+  const double sched_next = sched_new * mu_next;
+  state[0] = t;
+  state[1] = sched_new;
+  hyper[0] = (float)(lr * (1.0 - mu_t) / (1.0 - sched_new));
+  hyper[1] = (float)(lr * mu_next / (1.0 - sched_next));
+  hyper[2] = (float)(1.0 / (1.0 - pow(b2, t)));
+}
+extern "C" int lb_nadam_schedule(double* state, float* hyper, double lr, double beta1, double beta2, double schedule_decay,
+                                 lb_stream_t s) {
+  LB_REQUIRE(state && hyper);
+  k_nadam_schedule<<<1, 1, 0, lb_s(s)>>>(state, hyper, lr, beta1, beta2, schedule_decay);
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
+
 __global__ void __launch_bounds__(256) k_nadam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                float* __restrict__ v, size_t n, float b1, float b2, float eps,
-                                               float c_grad, float c_mom, float inv_bias2) {
+                                               const float* __restrict__ hyper) {
+  const float c_grad = __ldg(hyper), c_mom = __ldg(hyper + 1), inv_bias2 = __ldg(hyper + 2);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const float gv = g[i];
@@ -231,11 +255,10 @@ __global__ void __launch_bounds__(256) k_nadam(float* __restrict__ p, const floa
   }
 }
 extern "C" int lb_nadam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float beta1,
-                             float beta2, float eps, float c_grad, float c_mom, float bias2, lb_stream_t s) {
-  LB_REQUIRE(param && grad && exp_avg && exp_avg_sq && bias2 > 0.0f);
+                             float beta2, float eps, const float* hyper, lb_stream_t s) {
+  LB_REQUIRE(param && grad && exp_avg && exp_avg_sq && hyper);
   if (n == 0) return LB_OK;
-  k_nadam<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(param, grad, exp_avg, exp_avg_sq, n, beta1, beta2, eps, c_grad, c_mom,
-                                                   1.0f / bias2);
+  k_nadam<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(param, grad, exp_avg, exp_avg_sq, n, beta1, beta2, eps, hyper);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }

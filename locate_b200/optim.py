@@ -55,7 +55,9 @@ class Nadam(Optimizer):
                     p._lb_epoch = epoch
                     p.grad = gview
             arenas.append(dict(param=flat_p, grad=flat_g, exp_avg=torch.zeros_like(flat_p),
-                               exp_avg_sq=torch.zeros_like(flat_p), step=0, m_schedule=1.0, n=total, epoch=epoch))
+                               exp_avg_sq=torch.zeros_like(flat_p), step=0, n=total, epoch=epoch,
+                               sched=torch.tensor([0.0, 1.0], dtype=torch.float64, device=dev),   # {t, m_schedule}
+                               hyper=torch.zeros(3, dtype=torch.float32, device=dev)))
         self._arenas = arenas
 
     def _ensure(self):
@@ -92,16 +94,8 @@ class Nadam(Optimizer):
                 continue
             a["epoch"][0] += 1             # the raw-pointer update below does not bump torch's version counters
             beta1, beta2 = group["betas"]
-            decay = group["schedule_decay"]
-            a["step"] += 1
-            t = a["step"]
-            mu_t = beta1 * (1.0 - 0.5 * (0.96 ** (t * decay)))
-            mu_next = beta1 * (1.0 - 0.5 * (0.96 ** ((t + 1) * decay)))
-            sched_new = a["m_schedule"] * mu_t
-            sched_next = sched_new * mu_next
-            a["m_schedule"] = sched_new
-            c_grad = group["lr"] * (1.0 - mu_t) / (1.0 - sched_new)
-            c_mom = group["lr"] * mu_next / (1.0 - sched_next)
+            a["step"] += 1                 # host mirror only; the authoritative counter is a["sched"][0] on the device
+            call("lb_nadam_schedule", ptr(a["sched"]), ptr(a["hyper"]), group["lr"], beta1, beta2, group["schedule_decay"])
             call("lb_nadam_step", ptr(a["param"]), ptr(a["grad"]), ptr(a["exp_avg"]), ptr(a["exp_avg_sq"]), a["n"],
-                 beta1, beta2, group["eps"], c_grad, c_mom, 1.0 - beta2 ** t)
+                 beta1, beta2, group["eps"], ptr(a["hyper"]))
         return loss

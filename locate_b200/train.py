@@ -58,6 +58,7 @@ class GanTrainer:
     def __init__(self, gen, dis, g_opt, d_opt, penalty_gamma=100.0):
         self.gen, self.dis, self.g_opt, self.d_opt = gen, dis, g_opt, d_opt
         self.penalty_gamma = float(penalty_gamma)
+        self._graph = self._static_in = self._static_out = None
 
     def _reduce_and_step(self, opt):
         for h in [h for flat in opt.flat_grads for h in dist.all_reduce_grads_(flat)]:
@@ -98,7 +99,49 @@ class GanTrainer:
         self.dis.requires_grad_(True)
         return out
 
-    def step(self, real, aug, z):
+    def _eager_step(self, real, aug, z):
         d_out = self.d_step(real, aug, z)
         g_out = self.g_step(z)
         return d_out, g_out
+
+    def step(self, real, aug, z):
+        """One D update + one G update.  After `capture()` the whole step (about 3.7 k kernel launches, both
+        backward passes, the collectives and both Nadam updates) is ONE cudaGraphLaunch: inputs are copied into
+        the captured static buffers and the graph is replayed."""
+        if self._graph is None:
+            return self._eager_step(real, aug, z)
+        for dst, src in zip(self._static_in, (real, aug, z)):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        self._graph.replay()
+        for opt in (self.d_opt, self.g_opt):          # host mirrors of the device-side step counters
+            for a in opt._arenas:
+                if a is not None:
+                    a["step"] += 1
+                    a["epoch"][0] += 1
+        return self._static_out
+
+    def capture(self, real, aug, z, warmup=3):
+        """Capture the step into a CUDA graph (CUDA streams and graphs instead of a tracing compiler).  Everything
+        step-dependent lives on the device (Nadam schedule, spectral-norm u/v, statistics), tensor maps and launch
+        geometry are baked into the graph, so shapes are frozen to those of (real, aug, z).  Runs `warmup` eager
+        steps first (lazy initialisation, allocator warm-up), which train the model like any other step."""
+        from .conv_fn import invalidate_packs
+        shapes = tuple(tuple(t.shape) for t in (real, aug, z))
+        self._static_in = tuple(torch.empty_like(t).copy_(t) for t in (real, aug, z))
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._eager_step(*self._static_in)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        invalidate_packs()                            # every replay starts with stale weight packs; capture the same
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = self._eager_step(*self._static_in)
+        self._graph, self._static_out, self._graph_shapes = graph, out, shapes
+        return self
+
+    def release_graph(self):
+        self._graph = self._static_in = self._static_out = None
