@@ -15,6 +15,7 @@
 //   of kStages stages guarded by full/empty mbarriers; tcgen05.commit releases stages and signals the
 //   epilogue, which reads TMEM with tcgen05.ld (lane = row) and writes fp32 rows.
 // Warp roles (192 threads): 0 = TMA producer, 1 = TMEM alloc + MMA issuer, 2-5 = epilogue.
+#include <stdlib.h>
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -54,7 +55,7 @@ __device__ __forceinline__ void tap_span(int mode, int s, int pad, int k, int pa
 }
 __device__ __forceinline__ int floordiv(int a, int b) { int q = a / b; return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q; }
 
-__global__ void __launch_bounds__(192, 2) k_conv_tc(const __grid_constant__ TcMaps maps, const TcParams p) {
+__global__ void __launch_bounds__(192, 4) k_conv_tc(const __grid_constant__ TcMaps maps, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[8], bar_empty[8], bar_acc;
   __shared__ uint32_t tmem_slot;
@@ -297,8 +298,6 @@ extern "C" int lb_conv_tc_gemm(const void* in_bf16, const void* w_packed, const 
   p.rows_per_tap = g->out_c;
   p.alpha = alpha; p.bias = bias; p.out = out;
   const int stage_bytes = kABytes + bn * kBlockK * 2;
-  p.stages = stage_bytes >= 32 * 1024 ? 3 : 4;             // <= ~97 KB per CTA: two CTAs per SM overlap epilogue and mainloop
-  const int smem_bytes = p.stages * stage_bytes + 1024;
 
   // source views: mode 0 with stride 2 -> 4 parity views; otherwise one dense view
   const int nv = (g->mode == 0) ? g->stride * g->stride : 1;
@@ -326,6 +325,20 @@ extern "C" int lb_conv_tc_gemm(const void* in_bf16, const void* w_packed, const 
     int rc = make_map(&maps.b, w_packed, 2, dims, strides, box);
     if (rc) return rc;
   }
+  // Several CTAs per SM hide each other's fixed latencies (TMEM alloc, first TMA round trip, epilogue stores).
+  // Shallow-K tiles (few taps x channel chunks): 2-3 stages, up to 4 CTAs per SM (4 x 128 TMEM columns);
+  // deep-K tiles: >= 3 stages, 2 CTAs per SM.
+  const int taps_eff = g->mode == 1 ? ((g->kh + p.sp - 1) / p.sp) * ((g->kw + p.sp - 1) / p.sp) : g->kh * g->kw;
+  const int iters_est = taps_eff * p.kchunks;
+  {
+    const int budget = iters_est >= 24 ? 100 * 1024 : 56 * 1024;
+    int st = budget / stage_bytes;
+    if (st < 2) st = 2;
+    if (st > 6) st = 6;
+    const char* env = getenv("LB_TC_STAGES");
+    p.stages = env ? atoi(env) : st;
+  }
+  const int smem_bytes = p.stages * stage_bytes + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -335,8 +348,6 @@ extern "C" int lb_conv_tc_gemm(const void* in_bf16, const void* w_packed, const 
   // split-K for weight-bound layers whose output tiling cannot fill the GPU (e.g. 5x5 1024->1024 at 2x2)
   const int n_tiles = (g->out_c + bn - 1) / bn;
   const long long ctas = (long long)p.tiles_w * p.tiles_h * tiles_b * n_tiles * p.sp * p.sp;
-  const int taps_eff = g->mode == 1 ? ((g->kh + p.sp - 1) / p.sp) * ((g->kw + p.sp - 1) / p.sp) : g->kh * g->kw;
-  const int iters_est = taps_eff * p.kchunks;
   p.splits = 1;
   if (ctas * 2 <= LB_SMS && iters_est >= 8) {
     long long want = (LB_SMS * 2 + ctas - 1) / ctas;

@@ -135,18 +135,22 @@ extern "C" int lb_norm_bwd_reduce(const float* x, const float* g, const float* s
   return LB_OK;
 }
 
-// backward phase 2 (tiny): scalars + parameter gradients.  One CTA.
+// backward phase 2 (small): scalars + parameter gradients.  CTA = 32 channels x 8 batch lanes, so the [B][C]
+// partials are read coalesced and in parallel (a single CTA looping over the batch is latency-bound).
 __global__ void __launch_bounds__(256) k_norm_bwd_finalize(const float* __restrict__ p1, const float* __restrict__ p2,
                                                           const float* __restrict__ gain, int gain_bs,
                                                           const float* __restrict__ stats, int batch, int channels,
                                                           float* __restrict__ dgain, float* __restrict__ dbias,
                                                           double* __restrict__ sout) {
   __shared__ double scratch[32];
+  __shared__ float s_db[8][33], s_dg[8][33];
   const float rstd = stats[2];
+  const int cl = threadIdx.x & 31, bl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
   double s1 = 0.0, s2 = 0.0;
-  for (int c = threadIdx.x; c < channels; c += blockDim.x) {
-    float db = 0.0f, dg_shared = 0.0f;
-    for (int b = 0; b < batch; ++b) {
+  float db = 0.0f, dg_shared = 0.0f;
+  if (c < channels) {
+    for (int b = bl; b < batch; b += 8) {
       const float a1 = p1[(size_t)b * channels + c], a2 = p2[(size_t)b * channels + c];
       const float gn = gain[(size_t)b * gain_bs + c];
       s1 += (double)gn * a1;
@@ -154,19 +158,30 @@ __global__ void __launch_bounds__(256) k_norm_bwd_finalize(const float* __restri
       db += a1;
       if (gain_bs) dgain[(size_t)b * channels + c] += a2 * rstd; else dg_shared += a2;
     }
-    if (dbias) dbias[c] += db;
-    if (!gain_bs && dgain) dgain[c] += dg_shared * rstd;
+  }
+  s_db[bl][cl] = db;
+  s_dg[bl][cl] = dg_shared;
+  __syncthreads();
+  if (bl == 0 && c < channels) {
+    float tb = 0.0f, tg = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { tb += s_db[i][cl]; tg += s_dg[i][cl]; }
+    if (dbias) dbias[c] += tb;
+    if (!gain_bs && dgain) dgain[c] += tg * rstd;
   }
   s1 = lb_block_sum(s1, scratch);
   s2 = lb_block_sum(s2, scratch);
-  if (threadIdx.x == 0) { sout[0] = s1; sout[1] = s2; }
+  if (threadIdx.x == 0) { atomicAdd(sout, s1); atomicAdd(sout + 1, s2); }
 }
 extern "C" int lb_norm_bwd_finalize(const float* p1, const float* p2, const float* gain, int gain_batch_stride,
                                     const float* stats, int batch, int channels, float* dgain, float* dbias, double* sout,
                                     lb_stream_t s) {
   LB_REQUIRE(p1 && p2 && gain && stats && sout && batch > 0 && channels > 0);
   LB_REQUIRE(gain_batch_stride == 0 || (gain_batch_stride == channels && dgain));
-  k_norm_bwd_finalize<<<1, 256, 0, lb_s(s)>>>(p1, p2, gain, gain_batch_stride, stats, batch, channels, dgain, dbias, sout);
+  cudaError_t e = cudaMemsetAsync(sout, 0, 2 * sizeof(double), lb_s(s));
+  if (e != cudaSuccess) return (int)e;
+  k_norm_bwd_finalize<<<(channels + 31) / 32, 256, 0, lb_s(s)>>>(p1, p2, gain, gain_batch_stride, stats, batch, channels, dgain,
+                                                               dbias, sout);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }

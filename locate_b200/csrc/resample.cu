@@ -61,7 +61,29 @@ __device__ __forceinline__ void lb_up2_src(int d, int n, int& i0, int& i1, float
   i1 = min(i0 + 1, n - 1);
   lam = src - i0;
 }
-__global__ void k_up2_fwd(const float* __restrict__ x, float* __restrict__ y, size_t n_out, int h, int w, int c) {
+// V = 4: one thread = 4 consecutive channels (128-bit accesses, 4x fewer index computations); V = 1: any layout
+template <int V> struct VecT;
+template <> struct VecT<1> { typedef float type; };
+template <> struct VecT<4> { typedef float4 type; };
+__device__ __forceinline__ float vmix(float a, float b, float c, float d, float w0, float w1, float w2, float w3) {
+  return w0 * a + w1 * b + w2 * c + w3 * d;
+}
+__device__ __forceinline__ float4 vmix(float4 a, float4 b, float4 c, float4 d, float w0, float w1, float w2, float w3) {
+  return make_float4(w0 * a.x + w1 * b.x + w2 * c.x + w3 * d.x, w0 * a.y + w1 * b.y + w2 * c.y + w3 * d.y,
+                     w0 * a.z + w1 * b.z + w2 * c.z + w3 * d.z, w0 * a.w + w1 * b.w + w2 * c.w + w3 * d.w);
+}
+__device__ __forceinline__ void vfma(float& acc, float w, float v) { acc = fmaf(w, v, acc); }
+__device__ __forceinline__ void vfma(float4& acc, float w, float4 v) {
+  acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y); acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+}
+__device__ __forceinline__ float vzero(float) { return 0.0f; }
+__device__ __forceinline__ float4 vzero(float4) { return make_float4(0.f, 0.f, 0.f, 0.f); }
+
+template <int V>
+__global__ void __launch_bounds__(256) k_up2_fwd(const float* __restrict__ xs, float* __restrict__ ys, size_t n_out, int h, int w, int c) {
+  typedef typename VecT<V>::type T;
+  const T* __restrict__ x = reinterpret_cast<const T*>(xs);
+  T* __restrict__ y = reinterpret_cast<T*>(ys);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const int ow = 2 * w, oh = 2 * h;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += stride) {
@@ -73,10 +95,9 @@ __global__ void k_up2_fwd(const float* __restrict__ x, float* __restrict__ y, si
     int y0, y1, x0, x1; float ly, lx;
     lb_up2_src(oy, h, y0, y1, ly);
     lb_up2_src(ox, w, x0, x1, lx);
-    const float* xb = x + b * h * w * c + ch;
-    const float v00 = xb[((size_t)y0 * w + x0) * c], v01 = xb[((size_t)y0 * w + x1) * c];
-    const float v10 = xb[((size_t)y1 * w + x0) * c], v11 = xb[((size_t)y1 * w + x1) * c];
-    y[i] = (1.0f - ly) * ((1.0f - lx) * v00 + lx * v01) + ly * ((1.0f - lx) * v10 + lx * v11);
+    const T* xb = x + b * h * w * c + ch;
+    y[i] = vmix(xb[((size_t)y0 * w + x0) * c], xb[((size_t)y0 * w + x1) * c], xb[((size_t)y1 * w + x0) * c],
+                xb[((size_t)y1 * w + x1) * c], (1.0f - ly) * (1.0f - lx), (1.0f - ly) * lx, ly * (1.0f - lx), ly * lx);
   }
 }
 // weight with which source index m receives from destination index d along one axis
@@ -85,7 +106,11 @@ __device__ __forceinline__ float lb_up2_weight(int d, int n, int m) {
   lb_up2_src(d, n, i0, i1, lam);
   return (i0 == m ? 1.0f - lam : 0.0f) + (i1 == m ? lam : 0.0f);
 }
-__global__ void k_up2_bwd(const float* __restrict__ g, float* __restrict__ dx, size_t n_in, int h, int w, int c) {
+template <int V>
+__global__ void __launch_bounds__(256) k_up2_bwd(const float* __restrict__ gs, float* __restrict__ dxs, size_t n_in, int h, int w, int c) {
+  typedef typename VecT<V>::type T;
+  const T* __restrict__ g = reinterpret_cast<const T*>(gs);
+  T* __restrict__ dx = reinterpret_cast<T*>(dxs);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const int ow = 2 * w, oh = 2 * h;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_in; i += stride) {
@@ -94,17 +119,15 @@ __global__ void k_up2_bwd(const float* __restrict__ g, float* __restrict__ dx, s
     const int ix = (int)(t % w); t /= w;
     const int iy = (int)(t % h);
     const size_t b = t / h;
-    const float* gb = g + b * oh * ow * c + ch;
-    float acc = 0.0f;
+    const T* gb = g + b * oh * ow * c + ch;
+    T acc = vzero(T());
     for (int dy = max(0, 2 * iy - 2); dy <= min(oh - 1, 2 * iy + 2); ++dy) {
       const float wy = lb_up2_weight(dy, h, iy);
       if (wy == 0.0f) continue;
-      float row = 0.0f;
       for (int dxp = max(0, 2 * ix - 2); dxp <= min(ow - 1, 2 * ix + 2); ++dxp) {
         const float wx = lb_up2_weight(dxp, w, ix);
-        if (wx != 0.0f) row = fmaf(wx, gb[((size_t)dy * ow + dxp) * c], row);
+        if (wx != 0.0f) vfma(acc, wy * wx, gb[((size_t)dy * ow + dxp) * c]);
       }
-      acc = fmaf(wy, row, acc);
     }
     dx[i] = acc;
   }
@@ -112,20 +135,30 @@ __global__ void k_up2_bwd(const float* __restrict__ g, float* __restrict__ dx, s
 extern "C" int lb_upsample2x_fwd(const float* x, float* y, int batch, int h, int w, int c, lb_stream_t s) {
   LB_REQUIRE(x && y && batch > 0 && h > 0 && w > 0 && c > 0);
   const size_t n = (size_t)batch * h * w * c * 4;
-  k_up2_fwd<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(x, y, n, h, w, c);
+  if ((c & 3) == 0 && lb_aligned16(x) && lb_aligned16(y))
+    k_up2_fwd<4><<<lb_grid_1d(n / 4, 256), 256, 0, lb_s(s)>>>(x, y, n / 4, h, w, c / 4);
+  else
+    k_up2_fwd<1><<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(x, y, n, h, w, c);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
 extern "C" int lb_upsample2x_bwd(const float* g, float* dx, int batch, int h, int w, int c, lb_stream_t s) {
   LB_REQUIRE(g && dx && batch > 0 && h > 0 && w > 0 && c > 0);
   const size_t n = (size_t)batch * h * w * c;
-  k_up2_bwd<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(g, dx, n, h, w, c);
+  if ((c & 3) == 0 && lb_aligned16(g) && lb_aligned16(dx))
+    k_up2_bwd<4><<<lb_grid_1d(n / 4, 256), 256, 0, lb_s(s)>>>(g, dx, n / 4, h, w, c / 4);
+  else
+    k_up2_bwd<1><<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(g, dx, n, h, w, c);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
 
 // ---- AvgPool 2x2 / stride 2 (scale.py:40) ----------------------------------------------------
-__global__ void k_avgpool2_fwd(const float* __restrict__ x, float* __restrict__ y, size_t n_out, int h, int w, int c) {
+template <int V>
+__global__ void __launch_bounds__(256) k_avgpool2_fwd(const float* __restrict__ xs, float* __restrict__ ys, size_t n_out, int h, int w, int c) {
+  typedef typename VecT<V>::type T;
+  const T* __restrict__ x = reinterpret_cast<const T*>(xs);
+  T* __restrict__ y = reinterpret_cast<T*>(ys);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const int oh = h / 2, ow = w / 2;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += stride) {
@@ -134,11 +167,15 @@ __global__ void k_avgpool2_fwd(const float* __restrict__ x, float* __restrict__ 
     const int ox = (int)(t % ow); t /= ow;
     const int oy = (int)(t % oh);
     const size_t b = t / oh;
-    const float* p = x + ((b * h + 2 * oy) * w + 2 * ox) * c + ch;
-    y[i] = 0.25f * ((p[0] + p[c]) + (p[(size_t)w * c] + p[(size_t)w * c + c]));
+    const T* p = x + ((b * h + 2 * oy) * w + 2 * ox) * c + ch;
+    y[i] = vmix(p[0], p[c], p[(size_t)w * c], p[(size_t)w * c + c], 0.25f, 0.25f, 0.25f, 0.25f);
   }
 }
-__global__ void k_avgpool2_bwd(const float* __restrict__ g, float* __restrict__ dx, size_t n_in, int h, int w, int c) {
+template <int V>
+__global__ void __launch_bounds__(256) k_avgpool2_bwd(const float* __restrict__ gs, float* __restrict__ dxs, size_t n_in, int h, int w, int c) {
+  typedef typename VecT<V>::type T;
+  const T* __restrict__ g = reinterpret_cast<const T*>(gs);
+  T* __restrict__ dx = reinterpret_cast<T*>(dxs);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const int oh = h / 2, ow = w / 2;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_in; i += stride) {
@@ -148,20 +185,28 @@ __global__ void k_avgpool2_bwd(const float* __restrict__ g, float* __restrict__ 
     const int iy = (int)(t % h);
     const size_t b = t / h;
     const int oy = iy >> 1, ox = ix >> 1;
-    dx[i] = (oy < oh && ox < ow) ? 0.25f * g[((b * oh + oy) * ow + ox) * c + ch] : 0.0f;
+    T acc = vzero(T());
+    if (oy < oh && ox < ow) vfma(acc, 0.25f, g[((b * oh + oy) * ow + ox) * c + ch]);
+    dx[i] = acc;
   }
 }
 extern "C" int lb_avgpool2_fwd(const float* x, float* y, int batch, int h, int w, int c, lb_stream_t s) {
   LB_REQUIRE(x && y && batch > 0 && h > 1 && w > 1 && c > 0);
   const size_t n = (size_t)batch * (h / 2) * (w / 2) * c;
-  k_avgpool2_fwd<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(x, y, n, h, w, c);
+  if ((c & 3) == 0 && lb_aligned16(x) && lb_aligned16(y))
+    k_avgpool2_fwd<4><<<lb_grid_1d(n / 4, 256), 256, 0, lb_s(s)>>>(x, y, n / 4, h, w, c / 4);
+  else
+    k_avgpool2_fwd<1><<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(x, y, n, h, w, c);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
 extern "C" int lb_avgpool2_bwd(const float* g, float* dx, int batch, int h, int w, int c, lb_stream_t s) {
   LB_REQUIRE(g && dx && batch > 0 && h > 1 && w > 1 && c > 0);
   const size_t n = (size_t)batch * h * w * c;
-  k_avgpool2_bwd<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(g, dx, n, h, w, c);
+  if ((c & 3) == 0 && lb_aligned16(g) && lb_aligned16(dx))
+    k_avgpool2_bwd<4><<<lb_grid_1d(n / 4, 256), 256, 0, lb_s(s)>>>(g, dx, n / 4, h, w, c / 4);
+  else
+    k_avgpool2_bwd<1><<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(g, dx, n, h, w, c);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }

@@ -38,7 +38,7 @@ struct WgParams {
 
 __device__ __forceinline__ int floordiv(int a, int b) { int q = a / b; return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q; }
 
-__global__ void __launch_bounds__(192, 1) k_wgrad_tc(const __grid_constant__ WgMaps maps, const WgParams p) {
+__global__ void __launch_bounds__(192, 2) k_wgrad_tc(const __grid_constant__ WgMaps maps, const WgParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[8], bar_empty[8], bar_acc;
   __shared__ uint32_t tmem_slot;
@@ -204,7 +204,9 @@ extern "C" int lb_wgrad_tc(const void* gathered_bf16, const void* dense_bf16, fl
   p.kw = g->kw; p.stride = g->stride; p.pad = g->pad;
   p.dwp = dwp;
   const int stage_bytes = (2 + p.n_boxes) * kBoxBytes;
-  p.stages = stage_bytes <= 32 * 1024 ? 6 : 4;
+  p.stages = (100 * 1024) / stage_bytes;                   // <= ~100 KB: two CTAs per SM
+  if (p.stages < 2) p.stages = 2;
+  if (p.stages > 6) p.stages = 6;
   const int smem_bytes = p.stages * stage_bytes + 1024;
   const int taps = g->kh * g->kw;
   const long long ctas = (long long)p.m_tiles * n_tiles * taps;

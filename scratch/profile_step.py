@@ -24,7 +24,7 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
 tot = collections.defaultdict(lambda:[0,0.0])
 for ev in prof.events():
     if ev.device_type == torch.autograd.DeviceType.CUDA:
-        name = re.sub(r'\(.*','',ev.name)[:70]
+        name = re.sub(r'\(anonymous namespace\)::','',ev.name); name = re.sub(r'\(.*','',name)[:70]
         tot[name][0]+=1; tot[name][1]+=ev.device_time/1e3
 s = sum(v[1] for v in tot.values())
 print(f"B={B} wall {wall:.2f} ms/step; GPU kernel time {s:.2f} ms; launches {sum(v[0] for v in tot.values())}")
