@@ -265,6 +265,7 @@ def run_cuda(args):
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
+        "hbm_peak_gib": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2),
         "step_tflops": value * STEP_GFLOP_PER_IMAGE / 1e3,
         "roofline": roofline,
         "losses": {"d_hinge": float(losses[0][0]), "penalty": float(losses[0][1]), "g_hinge": float(losses[1][0])},

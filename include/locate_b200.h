@@ -92,6 +92,14 @@ int lb_gate_bwd(const float* x, const float* y, const float* gamma, const float*
  * sigma_out[1] = 1/sigma.  work: height + width + 4 floats of scratch. */
 int lb_sn_power_iter(const float* w, int height, int width, float* u, float* v, float* sigma_out,
                      float* work, lb_stream_t stream);
+/* The same iteration for ALL spectral-normed layers of a model in 4 launches.  layers_dev: device array of
+ * n_layers records {const float* w; float* u; float* v; int height, width, t_off, s_off;} (40 bytes each; t_off /
+ * s_off index the float scratch where W^T u and W v of that layer are staged).  items1_dev: int4 {layer, col0,
+ * row0, rows} tiles of 256 columns for pass 1; items3_dev: int2 {layer, row0} groups of 8 rows for pass 2.
+ * sigma_out: n_layers x {sigma, 1/sigma}. */
+int lb_sn_power_iter_batched(const void* layers_dev, int n_layers, const void* items1_dev, int n_items1,
+                             const void* items3_dev, int n_items3, float* scratch, size_t scratch_floats,
+                             float* sigma_out, lb_stream_t stream);
 /* weight-gradient epilogue: with dwn = dL/d(W/sigma) and the LIVE u,v:
  *   grad += dwn/sigma - (sum dwn*W)/sigma^2 * u v^T       (SURVEY.md section 8c identity)
  * dwn has W's layout (packed_taps = 0) or is the tap-major [taps][d0][d1] buffer of lb_wgrad_tc

@@ -42,6 +42,7 @@ _SIGNATURES = {
     "lb_gate_fwd": ([P, P, P, P, c_int, c_int, c_int, c_int, P], c_int),
     "lb_gate_bwd": ([P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P], c_int),
     "lb_sn_power_iter": ([P, c_int, c_int, P, P, P, P, P], c_int),
+    "lb_sn_power_iter_batched": ([P, c_int, P, c_int, P, c_int, P, c_size_t, P, P], c_int),
     "lb_sn_weight_grad": ([P, P, P, P, P, P, c_int, c_int, c_int, P, P], c_int),
     "lb_wgrad_tc_supported": ([POINTER(ConvGeom)], c_int),
     "lb_wgrad_tc": ([P, P, P, POINTER(ConvGeom), P], c_int),

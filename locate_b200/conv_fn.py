@@ -110,7 +110,7 @@ class SNConvFn(torch.autograd.Function):
     the GEMM writes straight into the channel slice of the wider output."""
 
     @staticmethod
-    def forward(ctx, x, w_bar, u, v, bias, spec, cat_input, pre_act):
+    def forward(ctx, x, w_bar, u, v, bias, spec, cat_input, pre_act, pre_sigma):
         x = _as_act(x)
         is_vec = x.dim() == 2
         if is_vec:
@@ -121,7 +121,8 @@ class SNConvFn(torch.autograd.Function):
             raise ValueError(f"expected {spec.cin} input channels, got {cin}")
         if cat_input and pre_act:
             raise ValueError("cat_input and pre_act are exclusive")
-        sigma = power_iterate(w_bar, u.data, v.data, spec)
+        # one power iteration per forward call (done here, or already done for the whole model by sn_batch)
+        sigma = pre_sigma if pre_sigma is not None else power_iterate(w_bar, u.data, v.data, spec)
         oh, ow = spec.out_hw(h, w_)
         if cat_input and (oh, ow) != (h, w_):
             raise ValueError("cat_input needs a size-preserving conv")
@@ -237,8 +238,8 @@ class SNConvFn(torch.autograd.Function):
         if ctx.bias_param is not None and ctx.needs_input_grad[4]:
             dbias, dbias_ret = _grad_sink(ctx.bias_param)
             call("lb_colsum", gout.data_ptr() + off, rows, spec.cout, ctot, ptr(dbias))
-        return dx, dw_ret, None, None, dbias_ret, None, None, None
+        return dx, dw_ret, None, None, dbias_ret, None, None, None, None
 
 
-def sn_conv(x, w_bar, u, v, bias, spec, cat_input=False, pre_act=False):
-    return SNConvFn.apply(x, w_bar, u, v, bias, spec, cat_input, pre_act)
+def sn_conv(x, w_bar, u, v, bias, spec, cat_input=False, pre_act=False, pre_sigma=None):
+    return SNConvFn.apply(x, w_bar, u, v, bias, spec, cat_input, pre_act, pre_sigma)

@@ -120,3 +120,77 @@ extern "C" int lb_sn_weight_grad(const float* dwn, const float* w, const float* 
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
+
+// ---- batched power iteration: every spectral-normed layer of a model in 4 launches ------------------------
+// The per-layer version costs 4 tiny launches per layer per forward (~270 per discriminator pass).  u/v/sigma of a
+// layer depend only on (W, u), so all layers can be iterated up front.  Work is flattened into items so that a
+// 37 M-element weight and a 96-element weight share one grid without load imbalance.
+struct LbSnLayerDev {
+  const float* w; float* u; float* v;
+  int height, width, t_off, s_off;
+};
+// phase 1 item: layer, first column, first row, row count.  t[t_off + j] += sum_rows W[i][j] u[i]
+__global__ void __launch_bounds__(256) k_snb_wt_u(const LbSnLayerDev* __restrict__ layers, const int4* __restrict__ items,
+                                                 float* __restrict__ scratch) {
+  const int4 it = items[blockIdx.x];
+  const LbSnLayerDev L = layers[it.x];
+  const int j = it.y + threadIdx.x;
+  if (j >= L.width) return;
+  const int i1 = min(L.height, it.z + it.w);
+  float acc = 0.0f;
+  for (int i = it.z; i < i1; ++i) acc = fmaf(L.w[(size_t)i * L.width + j], __ldg(L.u + i), acc);
+  atomicAdd(scratch + L.t_off + j, acc);
+}
+// per layer: dst = src/(|src|+eps); phase 2 (v from t) and phase 4 (u from s, sigma)
+__global__ void __launch_bounds__(512) k_snb_normalize(const LbSnLayerDev* __restrict__ layers, const float* __restrict__ scratch,
+                                                      int phase, float* __restrict__ sigma_out) {
+  __shared__ float red[32];
+  __shared__ float s_norm;
+  const LbSnLayerDev L = layers[blockIdx.x];
+  const float* src = scratch + (phase == 2 ? L.t_off : L.s_off);
+  float* dst = phase == 2 ? L.v : L.u;
+  const int n = phase == 2 ? L.width : L.height;
+  float acc = 0.0f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { const float v = src[i]; acc = fmaf(v, v, acc); }
+  acc = lb_block_sum(acc, red);
+  if (threadIdx.x == 0) s_norm = sqrtf(acc);
+  __syncthreads();
+  const float nrm = s_norm;
+  const float inv = 1.0f / (nrm + SN_EPS);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i] * inv;
+  if (phase == 4 && threadIdx.x == 0) {
+    const float sigma = nrm * nrm * inv;
+    sigma_out[2 * blockIdx.x] = sigma;
+    sigma_out[2 * blockIdx.x + 1] = 1.0f / sigma;
+  }
+}
+// phase 3 item: (layer, first row); 8 rows per CTA, one warp per row.  s[s_off + i] = sum_j W[i][j] v[j]
+__global__ void __launch_bounds__(256) k_snb_w_v(const LbSnLayerDev* __restrict__ layers, const int2* __restrict__ items,
+                                                float* __restrict__ scratch) {
+  const int2 it = items[blockIdx.x];
+  const LbSnLayerDev L = layers[it.x];
+  const int row = it.y + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= L.height) return;
+  const float* wr = L.w + (size_t)row * L.width;
+  float acc = 0.0f;
+  for (int j = lane; j < L.width; j += 32) acc = fmaf(wr[j], __ldg(L.v + j), acc);
+  acc = lb_warp_sum(acc);
+  if (lane == 0) scratch[L.s_off + row] = acc;
+}
+extern "C" int lb_sn_power_iter_batched(const void* layers_dev, int n_layers, const void* items1_dev, int n_items1,
+                                        const void* items3_dev, int n_items3, float* scratch, size_t scratch_floats,
+                                        float* sigma_out, lb_stream_t s) {
+  LB_REQUIRE(layers_dev && items1_dev && items3_dev && scratch && sigma_out && n_layers > 0 && n_items1 > 0 && n_items3 > 0);
+  cudaError_t e = cudaMemsetAsync(scratch, 0, scratch_floats * sizeof(float), lb_s(s));
+  if (e != cudaSuccess) return (int)e;
+  const LbSnLayerDev* layers = reinterpret_cast<const LbSnLayerDev*>(layers_dev);
+  k_snb_wt_u<<<n_items1, 256, 0, lb_s(s)>>>(layers, reinterpret_cast<const int4*>(items1_dev), scratch);
+  LB_LAUNCH_CHECK();
+  k_snb_normalize<<<n_layers, 512, 0, lb_s(s)>>>(layers, scratch, 2, sigma_out);
+  LB_LAUNCH_CHECK();
+  k_snb_w_v<<<n_items3, 256, 0, lb_s(s)>>>(layers, reinterpret_cast<const int2*>(items3_dev), scratch);
+  LB_LAUNCH_CHECK();
+  k_snb_normalize<<<n_layers, 512, 0, lb_s(s)>>>(layers, scratch, 4, sigma_out);
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}

@@ -93,6 +93,7 @@ class SpectralNorm(nn.Module):
         if name != 'weight':
             raise NotImplementedError("the reference only ever normalises `weight`")
         self.spec = _spec_of(module)
+        self._pre_sigma = None            # set by sn_batch.SpectralBatch.run() when the model iterates all layers at once
         if not self._made_params():
             self._make_params()
 
@@ -123,7 +124,9 @@ class SpectralNorm(nn.Module):
         squeeze = x.dim() == 3                            # Conv1d input [B,F,L]
         if squeeze:
             x = x.unsqueeze(-1)
-        out = ops.sn_conv(x, m.weight_bar, m.weight_u, m.weight_v, getattr(m, "bias", None), self.spec, cat_input, pre_act)
+        pre_sigma, self._pre_sigma = self._pre_sigma, None
+        out = ops.sn_conv(x, m.weight_bar, m.weight_u, m.weight_v, getattr(m, "bias", None), self.spec, cat_input, pre_act,
+                          pre_sigma)
         return out.squeeze(-1) if squeeze else out
 
 

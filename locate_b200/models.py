@@ -33,6 +33,15 @@ class _ArenaModel(nn.Module):
 
     _lb_optimizer = None
 
+    def _iterate_spectral_norms(self):
+        """One power iteration for every spectral-normed layer, batched (sn_batch.py)."""
+        batch = self.__dict__.get("_lb_sn_batch")
+        if batch is None:
+            from .sn_batch import SpectralBatch
+            batch = SpectralBatch(self)
+            self.__dict__["_lb_sn_batch"] = batch
+        batch.run()
+
     def zero_grad(self, set_to_none=True):
         opt = self.__dict__.get("_lb_optimizer")
         if opt is not None:
@@ -62,6 +71,7 @@ class Generator(_ArenaModel):
         return self
 
     def forward(self, function_input):
+        self._iterate_spectral_norms()
         expanded_noise = self.noise.expand(function_input.size(0), -1, -1, -1)
         conv_out = self.input_block(expanded_noise)
         conv_out = self.conv_block(conv_out, function_input)
@@ -85,4 +95,5 @@ class Discriminator(_ArenaModel):
         self.main = nn.Sequential(cat_module, block_block, tail)
 
     def forward(self, function_input):
+        self._iterate_spectral_norms()
         return self.main(function_input)
