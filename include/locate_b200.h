@@ -142,6 +142,16 @@ size_t lb_conv_tc_packed_elems(const lb_conv_geom* g);
 int lb_conv_tc_pack(const float* w, void* packed, const lb_conv_geom* g, lb_stream_t stream);
 int lb_conv_tc_gemm(const void* in_bf16, const void* w_packed, const float* alpha, const float* bias, float* out,
                     const lb_conv_geom* g, lb_stream_t stream);
+/* Persistent variant with a fused epilogue (TMEM double buffering, TMA-stored outputs):
+ *   acc = alpha * GEMM (+ bias);  if aux: acc *= RootTanh'(aux[pixel][n]) (activation.py:18-36, growth 4);
+ *   out32 (fp32, row stride g->ld_out) and/or out16 (bf16, row stride ld_out16; RootTanh applied first when act16)
+ * aux has the geometry of the output (row stride ld_aux, fp32).  Either output may be NULL, not both.
+ * Returns LB_EUNSUPPORTED when the geometry/alignment is outside the kernel (lb_conv_tc_ex_supported tells in
+ * advance: pass ld_out16 = 0 / ld_aux = 0 for "not used"); callers then use lb_conv_tc_gemm + elementwise kernels. */
+int lb_conv_tc_ex_supported(const lb_conv_geom* g, int ld_out16, int ld_aux);
+int lb_conv_tc_gemm_ex(const void* in_bf16, const void* w_packed, const float* alpha, const float* bias, float* out32,
+                       void* out16, int ld_out16, int act16, const float* aux, int ld_aux, const lb_conv_geom* g,
+                       lb_stream_t stream);
 /* weight gradient on the tensor cores: dwp[tap][n][m] += sum_pixels gathered[pixel@tap][m] * dense[pixel][n]
  * (geometry as lb_conv_wgrad; both operands bf16 channels-last; dwp fp32, zeroed by the caller; feed it to
  * lb_sn_weight_grad with packed_taps = kh*kw). */

@@ -52,6 +52,8 @@ _SIGNATURES = {
     "lb_conv_tc_packed_elems": ([POINTER(ConvGeom)], c_size_t),
     "lb_conv_tc_pack": ([P, P, POINTER(ConvGeom), P], c_int),
     "lb_conv_tc_gemm": ([P, P, P, P, P, POINTER(ConvGeom), P], c_int),
+    "lb_conv_tc_ex_supported": ([POINTER(ConvGeom), c_int, c_int], c_int),
+    "lb_conv_tc_gemm_ex": ([P, P, P, P, P, P, c_int, c_int, P, c_int, POINTER(ConvGeom), P], c_int),
     "lb_cast_bf16": ([P, P, c_size_t, P], c_int),
     "lb_cast_bf16_rows": ([P, c_int, P, c_int, c_int64, c_int, c_int, P], c_int),
     "lb_roottanh_fwd_bf16": ([P, P, c_size_t, c_int, P], c_int),

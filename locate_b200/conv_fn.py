@@ -241,5 +241,129 @@ class SNConvFn(torch.autograd.Function):
         return dx, dw_ret, None, None, dbias_ret, None, None, None, None
 
 
+def _ex_ok(g, ld16, ld_aux):
+    return _lib.lib().lb_conv_tc_ex_supported(ctypes.byref(g), ld16, ld_aux) == 1
+
+
+def _sn_wgrad_tc(ctx_w, u, v, sigma, gathered, dense, g_wgrad, spec, fl, by, dev):
+    """dW of one spectral-normed conv on the tensor cores + the sigma correction, accumulated into the grad sink."""
+    dwp = torch.zeros(ctx_w.numel(), dtype=torch.float32, device=dev)
+    _timed_call("wgrad_tc", fl, by / 2, "lb_wgrad_tc", ptr(gathered), ptr(dense), ptr(dwp), g_wgrad)
+    grad_w, dw_ret = _grad_sink(ctx_w)
+    work = torch.empty(2, dtype=torch.float64, device=dev)
+    height, width = spec.sn_shape
+    call("lb_sn_weight_grad", ptr(dwp), ptr(ctx_w), ptr(u.data), ptr(v.data), ptr(sigma), ptr(grad_w), height, width, spec.taps,
+         ptr(work))
+    return dw_ret
+
+
+class ActivatedPairFn(torch.autograd.Function):
+    """ActivatedBaseConv.forward (conv.py:22-24) as ONE autograd node on the persistent tensor-core kernel:
+
+        y1 = conv_1(RootTanh(conv_0(RootTanh(x))))         (both convs spectral-normed, no bias)
+
+    forward : conv_0's epilogue writes y0 (fp32, kept for the activation backward) AND bf16 RootTanh(y0), the operand
+              of conv_1 -- the activation never makes its own pass over memory;
+    backward: conv_1's input-gradient GEMM multiplies by RootTanh'(y0) in its epilogue and emits the bf16 operand of
+              conv_0's two gradient GEMMs; conv_0's input-gradient GEMM multiplies by RootTanh'(x) the same way.
+    `x` may carry `_lb_act16` = bf16 RootTanh(x) left by the kernel that produced it (norm apply)."""
+
+    @staticmethod
+    def forward(ctx, x, w0, u0, v0, w1, u1, v1, spec0, spec1, sigma0, sigma1, geoms):
+        act16 = getattr(x, "_lb_act16", None)
+        x = _as_act(x)
+        b, cin, h, w_ = x.shape
+        oh, ow = spec0.out_hw(h, w_)
+        mid, cout = spec0.cout, spec1.cout
+        (gf0, gd0, gw0), (gf1, gd1, gw1) = geoms
+        if act16 is None:
+            act16 = _bf16_like(x)
+            call("lb_roottanh_fwd_bf16", ptr(x), ptr(act16), x.numel(), CFG.ROOTTANH_GROWTH)
+        y0 = _new_act((b, mid, oh, ow), x)
+        a0 = _bf16_like(y0)
+        fl0, by0 = _conv_work(spec0, b, h, w_, oh, ow)
+        fl1, by1 = _conv_work(spec1, b, oh, ow, oh, ow)
+        _timed_call("conv_tc", fl0, by0 / 2, "lb_conv_tc_gemm_ex", ptr(act16), ptr(_packed_weight(w0, gf0, "fwd")),
+                    sigma0.data_ptr() + 4, None, ptr(y0), ptr(a0), mid, 1, None, 0, gf0)
+        y1 = _new_act((b, cout, oh, ow), x)
+        _timed_call("conv_tc", fl1, by1 / 2, "lb_conv_tc_gemm_ex", ptr(a0), ptr(_packed_weight(w1, gf1, "fwd")),
+                    sigma1.data_ptr() + 4, None, ptr(y1), None, 0, 0, None, 0, gf1)
+        ctx.save_for_backward(x, act16, y0, a0, w0, w1, sigma0, sigma1)
+        ctx.uv = (u0, v0, u1, v1)                # LIVE u/v (see SNConvFn)
+        ctx.meta = (spec0, spec1, geoms, (b, cin, h, w_, oh, ow, mid, cout), (fl0, by0, fl1, by1))
+        return y1
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, act16, y0, a0, w0, w1, sigma0, sigma1 = ctx.saved_tensors
+        u0, v0, u1, v1 = ctx.uv
+        spec0, spec1, geoms, (b, cin, h, w_, oh, ow, mid, cout), (fl0, by0, fl1, by1) = ctx.meta
+        (gf0, gd0, gw0), (gf1, gd1, gw1) = geoms
+        gout = _as_act(gout)
+        dev = gout.device
+        need_dx, need_dw0, need_dw1 = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[4]
+        g1 = _bf16_like(gout)
+        call("lb_cast_bf16", ptr(gout), ptr(g1), gout.numel())
+        dx = dw0 = dw1 = None
+        if need_dw1:
+            ga, de = (g1, a0) if spec1.kind == "convT" else (a0, g1)
+            dw1 = _sn_wgrad_tc(w1, u1, v1, sigma1, ga, de, gw1, spec1, fl1, by1, dev)
+        if need_dx or need_dw0:
+            d0 = _bf16_like(y0)                  # bf16( dL/dy0 ) = bf16( dgrad_1(g1) * RootTanh'(y0) )
+            _timed_call("conv_tc", fl1, by1 / 2, "lb_conv_tc_gemm_ex", ptr(g1), ptr(_packed_weight(w1, gd1, "dgrad")),
+                        sigma1.data_ptr() + 4, None, None, ptr(d0), mid, 0, ptr(y0), mid, gd1)
+            if need_dw0:
+                ga, de = (d0, act16) if spec0.kind == "convT" else (act16, d0)
+                dw0 = _sn_wgrad_tc(w0, u0, v0, sigma0, ga, de, gw0, spec0, fl0, by0, dev)
+            if need_dx:
+                dx = _new_act((b, cin, h, w_), gout)
+                _timed_call("conv_tc", fl0, by0 / 2, "lb_conv_tc_gemm_ex", ptr(d0), ptr(_packed_weight(w0, gd0, "dgrad")),
+                            sigma0.data_ptr() + 4, None, ptr(dx), None, 0, 0, ptr(x), cin, gd0)
+        return (dx, dw0, None, None, dw1) + (None,) * 7
+
+
+def activated_pair(x, sn0, sn1):
+    """conv_1(RootTanh(conv_0(RootTanh(x)))) for two SpectralNorm wrappers (layers.ActivatedBaseConv); returns None when
+    the fused tensor-core path does not cover the layer (odd channel counts, fp32 mode, weight-bound split-K shapes)."""
+    if CFG.PRECISION != "bf16" or x.dim() != 4 or CFG.ROOTTANH_GROWTH != 4:
+        return None
+    spec0, spec1 = sn0.spec, sn1.spec
+    m0, m1 = sn0.module, sn1.module
+    if getattr(m0, "bias", None) is not None or getattr(m1, "bias", None) is not None:
+        return None
+    b, cin, h, w_ = x.shape
+    mid, cout = spec0.cout, spec1.cout
+    if cin % 8 or mid % 8 or cout % 8 or cin != spec0.cin or mid != spec1.cin:
+        return None
+    oh, ow = spec0.out_hw(h, w_)
+    lib = _lib.lib()
+
+    def geoms(spec, ih, iw, ci, co, o_h, o_w):
+        mode = 1 if spec.kind == "convT" else 0
+        t = spec.taps
+        gf = _geom(b, ih, iw, ci, o_h, o_w, co, spec, mode, ci, co, spec.strides_fwd())
+        gd = _geom(b, o_h, o_w, co, ih, iw, ci, spec, 1 - mode, co, ci, spec.strides_dgrad())
+        if spec.kind == "convT":
+            gw = _geom(b, o_h, o_w, co, ih, iw, ci, spec, 0, co, ci, (t, co * t, spec.kw, 1))
+        else:
+            gw = _geom(b, ih, iw, ci, o_h, o_w, co, spec, 0, ci, co, (t, ci * t, spec.kw, 1))
+        return gf, gd, gw
+
+    g0, g1 = geoms(spec0, h, w_, cin, mid, oh, ow), geoms(spec1, oh, ow, mid, cout, oh, ow)
+    ok = (_ex_ok(g0[0], mid, 0) and _ex_ok(g1[0], 0, 0) and _ex_ok(g1[1], mid, mid) and _ex_ok(g0[1], 0, cin)
+          and lib.lb_wgrad_tc_supported(ctypes.byref(g0[2])) == 1 and lib.lb_wgrad_tc_supported(ctypes.byref(g1[2])) == 1)
+    if not ok:
+        return None
+    sig = []
+    for sn in (sn0, sn1):
+        m = sn.module
+        for _ in range(sn.power_iterations - 1):
+            power_iterate(m.weight_bar, m.weight_u.data, m.weight_v.data, sn.spec)
+        pre, sn._pre_sigma = sn._pre_sigma, None
+        sig.append(pre if pre is not None else power_iterate(m.weight_bar, m.weight_u.data, m.weight_v.data, sn.spec))
+    return ActivatedPairFn.apply(x, m0.weight_bar, m0.weight_u, m0.weight_v, m1.weight_bar, m1.weight_u, m1.weight_v,
+                                 spec0, spec1, sig[0], sig[1], (g0, g1))
+
+
 def sn_conv(x, w_bar, u, v, bias, spec, cat_input=False, pre_act=False, pre_sigma=None):
     return SNConvFn.apply(x, w_bar, u, v, bias, spec, cat_input, pre_act, pre_sigma)

@@ -1,0 +1,510 @@
+// Persistent tcgen05 / TMEM / TMA implicit-GEMM for the convolution family with a fused, TMA-stored epilogue.
+//
+//   acc[pixel][n] = alpha * sum_taps sum_k A_tap[pixel][k] * Wp[tap][n][k]  (+ bias[n])
+//   if aux:   acc *= RootTanh'(aux[pixel][n])            (the activation backward that follows a dgrad GEMM)
+//   if out32: out32[pixel][n] = acc                       (fp32)
+//   if out16: out16[pixel][n] = bf16(act16 ? RootTanh(acc) : acc)   (the next GEMM's operand, produced in place)
+//
+// Operand staging and tap handling are those of conv_tc.cu (per-tap dense TMA boxes of parity views, zero fill =
+// padding).  What is different:
+//  * one CTA per SM walks a static list of (pixel tile, channel tile, phase) work items;
+//  * the TMEM accumulator is double buffered: the MMA warp fills stage (t+1)&1 while the epilogue drains t&1,
+//    and the TMA producer runs ahead across tile boundaries, so per-tile fixed latencies overlap with math;
+//  * the epilogue (8 warps: 2 per TMEM lane quarter, alternating 32-column slabs) moves
+//    tcgen05.ld -> registers -> 128B-swizzled shared slab -> cp.async.bulk.tensor store.  Every global write is a
+//    full-line TMA store of a 4-D box of the (possibly parity-strided) output view, clipped by the tensor map at the
+//    tensor edges; `aux` slabs arrive the same way through per-warp mbarriers, double buffered;
+//  * the last K chunk issues only the k16 steps that hold real channels.
+// Warp roles (320 threads): 0 = TMA producer, 1 = TMEM alloc + MMA issuer, 2-9 = epilogue.
+#include <stdlib.h>
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;                      // bf16 elements = 128 bytes = one swizzle row
+constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KB
+constexpr int kMaxViews = 4;
+constexpr int kSlab = 32;                        // fp32 columns per epilogue slab (128 B per row)
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr int kSmemLimit = 227 * 1024 - 1024;      // dynamic; 1 KB left for the static barriers
+
+struct Tc2Maps {
+  CUtensorMap a[kMaxViews];
+  CUtensorMap b;
+  CUtensorMap o32[kMaxViews];
+  CUtensorMap o16[kMaxViews];
+  CUtensorMap aux[kMaxViews];
+};
+
+struct Tc2Params {
+  int batch, out_c, in_c;
+  int sp;                             // destination parity step (stride in mode 1, else 1)
+  int tile_w, tile_h, tile_b;         // box dims, product = 128
+  int tiles_w, tiles_h, tiles_b, n_tiles, total_tiles;
+  int block_n, acc_stride, kchunks, stages;
+  int kh, kw, stride, pad, mode;
+  int rows_per_tap, view_empty;
+  int ebw, ebh, ebb;                  // 32-row sub-box of one epilogue warp
+  int has_o32, has_o16, has_aux;
+  int act16;                          // 1: RootTanh (growth 4) applied to the bf16 output
+  uint32_t tmem_cols;
+  uint32_t epi_base, epi_per_warp, off_o32, off_o16, off_aux;   // bytes; epi_base relative to the 1 KB aligned base
+  const float* alpha; const float* bias;
+};
+
+__device__ __forceinline__ void tap_span(int mode, int s, int pad, int k, int parity, int& t0, int& step, int& cnt) {
+  if (mode == 1) {
+    t0 = (parity + pad) % s;
+    step = s;
+    cnt = t0 < k ? (k - t0 + s - 1) / s : 0;
+  } else {
+    t0 = 0; step = 1; cnt = k;
+  }
+}
+__device__ __forceinline__ int floordiv(int a, int b) { int q = a / b; return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q; }
+
+struct TileCoord { int x0, y0, b0, n0, py, px, phase; };
+__device__ __forceinline__ TileCoord decode_tile(const Tc2Params& p, int tile) {
+  TileCoord c;
+  int t = tile;
+  const int nt = t % p.n_tiles; t /= p.n_tiles;
+  const int tw = t % p.tiles_w; t /= p.tiles_w;
+  const int th = t % p.tiles_h; t /= p.tiles_h;
+  const int tb = t % p.tiles_b; t /= p.tiles_b;
+  c.phase = t;
+  c.x0 = tw * p.tile_w; c.y0 = th * p.tile_h; c.b0 = tb * p.tile_b; c.n0 = nt * p.block_n;
+  c.py = c.phase / p.sp; c.px = c.phase % p.sp;
+  return c;
+}
+
+// ---- fast elementwise math for the epilogue (results are rounded to bf16 or multiplied into an fp32 gradient) ----
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rsqrt_approx(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sqrt_approx(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// RootTanh(x) = (x^2+1)^(1/4) tanh(x)
+__device__ __forceinline__ float roottanh_fast(float x) {
+  const float e = ex2_approx(-2.8853900817779268f * fabsf(x));      // exp(-2|x|)
+  const float th = copysignf((1.0f - e) * rcp_approx(1.0f + e), x);
+  const float q = fmaf(x, x, 1.0f);
+  return sqrt_approx(sqrt_approx(q)) * th;
+}
+// RootTanh'(x) = (2 q sech^2 + x tanh) q^(1/4) / (2q) = (2 q sech^2 + x tanh) * 0.5 q^(-3/4)
+__device__ __forceinline__ float roottanh_grad_fast(float x) {
+  const float e = ex2_approx(-2.8853900817779268f * fabsf(x));
+  const float r = rcp_approx(1.0f + e);
+  const float th = copysignf((1.0f - e) * r, x);
+  const float s2 = 4.0f * e * r * r;
+  const float q = fmaf(x, x, 1.0f);
+  const float rs = rsqrt_approx(q);                                  // q^(-1/2)
+  const float q34 = rs * sqrt_approx(rs);                            // q^(-3/4)
+  return fmaf(2.0f * q, s2, x * th) * 0.5f * q34;
+}
+
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(tc::smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant__ Tc2Maps maps, const Tc2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_full[8], bar_empty[8], bar_tfull[2], bar_tempty[2], bar_aux[kEpiWarps][2];
+  __shared__ uint32_t tmem_slot;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int b_bytes = p.block_n * kBlockK * 2;
+  const int stage_bytes = kABytes + ((b_bytes + 1023) & ~1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { tc::mbar_init(&bar_full[s], 1); tc::mbar_init(&bar_empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { tc::mbar_init(&bar_tfull[a], 1); tc::mbar_init(&bar_tempty[a], kEpiWarps); }
+    for (int w = 0; w < kEpiWarps; ++w) { tc::mbar_init(&bar_aux[w][0], 1); tc::mbar_init(&bar_aux[w][1], 1); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    for (int v = 0; v < kMaxViews; ++v) tc::tma_prefetch_desc(&maps.a[v]);
+    tc::tma_prefetch_desc(&maps.b);
+  }
+  if (warp == 1) tc::tmem_alloc(&tmem_slot, p.tmem_cols);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (tc::elect_one()) {
+      uint32_t git = 0;                                   // ring position, runs on across tiles
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileCoord c = decode_tile(p, tile);
+        int ty0, tys, tyc, tx0, txs, txc;
+        tap_span(p.mode, p.stride, p.pad, p.kh, c.py, ty0, tys, tyc);
+        tap_span(p.mode, p.stride, p.pad, p.kw, c.px, tx0, txs, txc);
+        const int iters = tyc * txc * p.kchunks;
+        for (int it = 0; it < iters; ++it, ++git) {
+          const int kc = it % p.kchunks, tap = it / p.kchunks;
+          const int ty = ty0 + (tap / txc) * tys, tx = tx0 + (tap % txc) * txs;
+          int view = 0, dy, dx;
+          if (p.mode == 0) {
+            const int ay = floordiv(ty - p.pad, p.stride), ax = floordiv(tx - p.pad, p.stride);
+            const int qy = (ty - p.pad) - ay * p.stride, qx = (tx - p.pad) - ax * p.stride;
+            view = qy * p.stride + qx;
+            dy = ay; dx = ax;
+          } else {
+            dy = (c.py + p.pad - ty) / p.stride;
+            dx = (c.px + p.pad - tx) / p.stride;
+          }
+          const int cb = ((p.view_empty >> view) & 1) ? p.batch : c.b0;   // empty view: box out of range -> zeros
+          const int wrow = (ty * p.kw + tx) * p.rows_per_tap + c.n0;
+          const int s = git % p.stages;
+          const uint32_t ph = (git / p.stages) & 1u;
+          tc::mbar_wait(&bar_empty[s], ph ^ 1u);
+          uint8_t* sa = smem + s * stage_bytes;
+          tc::mbar_arrive_expect_tx(&bar_full[s], (uint32_t)(kABytes + b_bytes));
+          tc::tma_load_4d(sa, &maps.a[view], &bar_full[s], kc * kBlockK, c.x0 + dx, c.y0 + dy, cb);
+          tc::tma_load_2d(sa + kABytes, &maps.b, &bar_full[s], kc * kBlockK, wrow);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (tc::elect_one()) {
+      const uint32_t idesc = tc::idesc_bf16(kBlockM, p.block_n, 0, 0);
+      const int k16_last = (p.in_c - (p.kchunks - 1) * kBlockK + 15) / 16;
+      uint32_t git = 0;
+      int lt = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+        const TileCoord c = decode_tile(p, tile);
+        int ty0, tys, tyc, tx0, txs, txc;
+        tap_span(p.mode, p.stride, p.pad, p.kh, c.py, ty0, tys, tyc);
+        tap_span(p.mode, p.stride, p.pad, p.kw, c.px, tx0, txs, txc);
+        const int iters = tyc * txc * p.kchunks;
+        const int acc = lt & 1;
+        tc::mbar_wait(&bar_tempty[acc], (((uint32_t)lt >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
+        tc::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.acc_stride);
+        for (int it = 0; it < iters; ++it, ++git) {
+          const int s = git % p.stages;
+          const uint32_t ph = (git / p.stages) & 1u;
+          tc::mbar_wait(&bar_full[s], ph);
+          tc::tc_fence_after();
+          const uint32_t sa = tc::smem_u32(smem + s * stage_bytes);
+          const uint32_t sb = sa + kABytes;
+          const int nk = (it % p.kchunks == p.kchunks - 1) ? k16_last : kBlockK / 16;
+          for (int k = 0; k < nk; ++k) {
+            const uint64_t ad = tc::smem_desc_sw128(sa + k * 32, 16, 1024);
+            const uint64_t bd = tc::smem_desc_sw128(sb + k * 32, 16, 1024);
+            tc::umma_bf16(tmem_d, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+          }
+          tc::umma_commit(&bar_empty[s]);
+        }
+        tc::umma_commit(&bar_tfull[acc]);
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..9) =====================
+    const int ew = warp - 2;
+    const int q = warp & 3;                       // TMEM lane quarter this warp may read
+    const int half = ew >> 2;                     // slabs of parity `half`
+    const int r0 = q * 32;                        // first tile row of this warp
+    const int w_off = r0 % p.tile_w, h_off = (r0 / p.tile_w) % p.tile_h, b_off = r0 / (p.tile_w * p.tile_h);
+    uint8_t* ebase = smem + p.epi_base + (uint32_t)ew * p.epi_per_warp;
+    uint8_t* s_o32 = ebase + p.off_o32;
+    uint8_t* s_o16 = ebase + p.off_o16;
+    uint8_t* s_aux = ebase + p.off_aux;           // 2 x 4 KB
+    const float alpha = p.alpha ? __ldg(p.alpha) : 1.0f;
+    const int sw = lane & 7;                      // 128B swizzle: 16-byte chunk j of row r lives at chunk j ^ (r & 7)
+    const int sw64 = (lane >> 1) & 3;             // 64B swizzle: chunk j of row r lives at chunk j ^ ((r >> 1) & 3)
+
+    // aux prefetch runs one job ahead of the consumer
+    int a_tile = blockIdx.x, a_slab = half;
+    uint32_t a_issued = 0, a_done = 0;
+    auto aux_advance = [&]() {                    // skip to the next (tile, slab) this warp owns
+      while (a_tile < p.total_tiles) {
+        const int n0 = (a_tile % p.n_tiles) * p.block_n;
+        const int nsl = (min(p.block_n, p.out_c - n0) + kSlab - 1) / kSlab;
+        if (a_slab < nsl) return;
+        a_tile += gridDim.x; a_slab = half;
+      }
+    };
+    auto aux_issue = [&]() {
+      aux_advance();
+      if (a_tile >= p.total_tiles) return;
+      if (lane == 0) {
+        const TileCoord c = decode_tile(p, a_tile);
+        const uint32_t buf = a_issued & 1u;
+        tc::mbar_arrive_expect_tx(&bar_aux[ew][buf], 32 * kSlab * 4);
+        tc::tma_load_4d(s_aux + buf * 4096, &maps.aux[c.phase], &bar_aux[ew][buf], c.n0 + a_slab * kSlab, c.x0 + w_off,
+                        c.y0 + h_off, c.b0 + b_off);
+      }
+      ++a_issued;
+      a_slab += 2;
+    };
+    if (p.has_aux) aux_issue();
+
+    int lt = 0;
+    bool stores_pending = false;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+      const TileCoord c = decode_tile(p, tile);
+      const int acc = lt & 1;
+      const int nsl = (min(p.block_n, p.out_c - c.n0) + kSlab - 1) / kSlab;
+      tc::mbar_wait(&bar_tfull[acc], ((uint32_t)lt >> 1) & 1u);
+      tc::tc_fence_after();
+      for (int slab = half; slab < nsl; slab += 2) {
+        if (p.has_aux) aux_issue();               // next job's aux while this one is processed
+        float v[32];
+        __syncwarp();
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride + slab * kSlab), v);
+        const int n = c.n0 + slab * kSlab;
+        if (p.bias) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], alpha, (n + i < p.out_c) ? __ldg(p.bias + n + i) : 0.0f);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] *= alpha;
+        }
+        if (p.has_aux) {
+          const uint32_t buf = a_done & 1u;
+          tc::mbar_wait(&bar_aux[ew][buf], (a_done >> 1) & 1u);
+          const uint8_t* row = s_aux + buf * 4096 + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 x4 = *reinterpret_cast<const float4*>(row + ((j ^ sw) << 4));
+            v[4 * j + 0] *= roottanh_grad_fast(x4.x);
+            v[4 * j + 1] *= roottanh_grad_fast(x4.y);
+            v[4 * j + 2] *= roottanh_grad_fast(x4.z);
+            v[4 * j + 3] *= roottanh_grad_fast(x4.w);
+          }
+          ++a_done;
+          __syncwarp();                           // every lane has read the buffer before it is refilled
+        }
+        // staging buffers are single: the previous slab's stores must have read them
+        if (stores_pending) {
+          if (lane == 0) bulk_wait_read0();
+          __syncwarp();
+        }
+        if (p.has_o32) {
+          uint8_t* row = s_o32 + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(row + ((j ^ sw) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        if (p.has_o16) {
+          uint8_t* row = s_o16 + lane * 64;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float t[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t[i] = p.act16 ? roottanh_fast(v[8 * j + i]) : v[8 * j + i];
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(t[0], t[1]), h1 = __floats2bfloat162_rn(t[2], t[3]);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(t[4], t[5]), h3 = __floats2bfloat162_rn(t[6], t[7]);
+            uint4 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+            pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+            *reinterpret_cast<uint4*>(row + ((j ^ sw64) << 4)) = pk;
+          }
+        }
+        tc::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          if (p.has_o32) tma_store_4d(&maps.o32[c.phase], s_o32, n, c.x0 + w_off, c.y0 + h_off, c.b0 + b_off);
+          if (p.has_o16) tma_store_4d(&maps.o16[c.phase], s_o16, n, c.x0 + w_off, c.y0 + h_off, c.b0 + b_off);
+          bulk_commit();
+        }
+        stores_pending = true;
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&bar_tempty[acc]);
+    }
+    if (lane == 0) bulk_wait0();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+int pow2_ceil(int v) { int r = 1; while (r < v) r <<= 1; return r; }
+
+}  // namespace
+
+// Does the persistent kernel cover this geometry and these operands?  (Otherwise lb_conv_tc_gemm stays on k_conv_tc.)
+static bool tc2_ok(const lb_conv_geom* g, const void* out32, const void* out16, int ld16, const void* aux, int ld_aux) {
+  if (g->stride != 1 && g->stride != 2) return false;
+  if (g->ld_in % 8 || g->in_c < 1 || g->out_c < 1 || g->kh * g->kw > 1024) return false;
+  if (g->mode == 1 && (g->kh < g->stride || g->kw < g->stride)) return false;          // a phase without taps
+  if (out32 && ((g->ld_out & 3) || (reinterpret_cast<uintptr_t>(out32) & 15))) return false;
+  if (out16 && ((ld16 & 7) || (reinterpret_cast<uintptr_t>(out16) & 15))) return false;
+  if (aux && ((ld_aux & 3) || (reinterpret_cast<uintptr_t>(aux) & 15))) return false;
+  if (!out32 && !out16) return false;
+  // weight-bound layers whose output tiling cannot fill the GPU stay on k_conv_tc's split-K path
+  const int sp = g->mode == 1 ? g->stride : 1;
+  const int dst_w = (g->out_w + sp - 1) / sp, dst_h = (g->out_h + sp - 1) / sp;
+  const int tw = pow2_ceil(dst_w) < kBlockM ? pow2_ceil(dst_w) : kBlockM;
+  const int th = pow2_ceil(dst_h) < kBlockM / tw ? pow2_ceil(dst_h) : kBlockM / tw;
+  const int tb = kBlockM / (tw * th);
+  const long long m_tiles = (long long)((dst_w + tw - 1) / tw) * ((dst_h + th - 1) / th) * ((g->batch + tb - 1) / tb) * sp * sp;
+  const int taps_eff = g->mode == 1 ? ((g->kh + sp - 1) / sp) * ((g->kw + sp - 1) / sp) : g->kh * g->kw;
+  const int iters_est = taps_eff * ((g->in_c + kBlockK - 1) / kBlockK);
+  if (m_tiles * ((g->out_c + 127) / 128) * 2 <= LB_SMS && iters_est >= 8) return false;
+  return true;
+}
+
+extern "C" int lb_conv_tc_gemm_ex(const void* in_bf16, const void* w_packed, const float* alpha, const float* bias, float* out32,
+                                  void* out16, int ld_out16, int act16, const float* aux, int ld_aux, const lb_conv_geom* g,
+                                  lb_stream_t s) {
+  LB_REQUIRE(in_bf16 && w_packed && g);
+  if (!tc2_ok(g, out32, out16, ld_out16, aux, ld_aux)) return LB_EUNSUPPORTED;
+  if (reinterpret_cast<uintptr_t>(in_bf16) & 15 || reinterpret_cast<uintptr_t>(w_packed) & 15) return LB_EALIGN;
+  Tc2Maps maps;
+  Tc2Params p;
+  p.mode = g->mode; p.stride = g->stride; p.pad = g->pad; p.kh = g->kh; p.kw = g->kw;
+  p.sp = g->mode == 1 ? g->stride : 1;
+  p.batch = g->batch; p.out_c = g->out_c; p.in_c = g->in_c;
+  const int dst_w = (g->out_w + p.sp - 1) / p.sp, dst_h = (g->out_h + p.sp - 1) / p.sp;
+  p.tile_w = pow2_ceil(dst_w) < kBlockM ? pow2_ceil(dst_w) : kBlockM;
+  int rest = kBlockM / p.tile_w;
+  p.tile_h = pow2_ceil(dst_h) < rest ? pow2_ceil(dst_h) : rest;
+  p.tile_b = rest / p.tile_h;
+  p.tiles_w = (dst_w + p.tile_w - 1) / p.tile_w;
+  p.tiles_h = (dst_h + p.tile_h - 1) / p.tile_h;
+  p.tiles_b = (g->batch + p.tile_b - 1) / p.tile_b;
+  p.ebw = p.tile_w < 32 ? p.tile_w : 32;
+  p.ebh = p.tile_h < 32 / p.ebw ? p.tile_h : 32 / p.ebw;
+  p.ebb = 32 / (p.ebw * p.ebh);
+  p.kchunks = (g->in_c + kBlockK - 1) / kBlockK;
+  p.rows_per_tap = g->out_c;
+  p.alpha = alpha; p.bias = bias;
+  p.has_o32 = out32 ? 1 : 0; p.has_o16 = out16 ? 1 : 0; p.has_aux = aux ? 1 : 0; p.act16 = act16 ? 1 : 0;
+
+  // epilogue staging per warp: fp32 slab 4 KB, bf16 slab 2 KB, aux 2 x 4 KB (all 1 KB aligned for the swizzle)
+  uint32_t off = 0;
+  p.off_o32 = off; if (out32) off += 4096;
+  p.off_o16 = off; if (out16) off += 2048;
+  p.off_aux = off; if (aux) off += 8192;
+  p.epi_per_warp = (off + 1023) & ~1023u;
+  const int epi_bytes = (int)p.epi_per_warp * kEpiWarps;
+
+  // channel tile: as wide as TMEM double buffering allows (<= 256) while leaving >= 3 ring stages
+  int nt = (g->out_c + 255) / 256, bn = 0, stage_bytes = 0, stages = 0;
+  for (;; ++nt) {
+    bn = ((g->out_c + nt - 1) / nt + 15) / 16 * 16;
+    stage_bytes = kABytes + ((bn * kBlockK * 2 + 1023) & ~1023);
+    stages = (kSmemLimit - 1024 - epi_bytes) / stage_bytes;
+    if (stages >= 3 || bn <= 64) break;
+  }
+  if (stages < 2) return LB_EUNSUPPORTED;
+  if (stages > 8) stages = 8;
+  p.block_n = bn; p.n_tiles = (g->out_c + bn - 1) / bn; p.stages = stages;
+  p.acc_stride = (bn + 31) / 32 * 32;
+  p.tmem_cols = (uint32_t)pow2_ceil(2 * p.acc_stride < 32 ? 32 : 2 * p.acc_stride);
+  p.epi_base = (uint32_t)(stages * stage_bytes);
+  p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_b * p.n_tiles * p.sp * p.sp;
+
+  // source views: mode 0 with stride 2 -> 4 parity views; otherwise one dense view
+  const int nv = (g->mode == 0) ? g->stride * g->stride : 1;
+  const int vs = (g->mode == 0) ? g->stride : 1;
+  p.view_empty = 0;
+  const char* base = reinterpret_cast<const char*>(in_bf16);
+  for (int v = 0; v < kMaxViews; ++v) {
+    const int vv = v < nv ? v : 0;
+    const int qy = vv / vs, qx = vv % vs;
+    int vw = (g->in_w - qx + vs - 1) / vs, vh = (g->in_h - qy + vs - 1) / vs;
+    if (vw <= 0 || vh <= 0) { if (v < nv) p.view_empty |= 1 << v; vw = vw > 0 ? vw : 1; vh = vh > 0 ? vh : 1; }
+    const uint64_t dims[4] = {(uint64_t)g->in_c, (uint64_t)vw, (uint64_t)vh, (uint64_t)g->batch};
+    const uint64_t strides[3] = {(uint64_t)vs * g->ld_in * 2, (uint64_t)vs * g->in_w * g->ld_in * 2,
+                                 (uint64_t)g->in_h * g->in_w * g->ld_in * 2};
+    const uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)p.tile_w, (uint32_t)p.tile_h, (uint32_t)p.tile_b};
+    const char* vbase = ((p.view_empty >> v) & 1) ? base : base + ((size_t)qy * g->in_w + qx) * g->ld_in * 2;
+    int rc = tc::make_map(&maps.a[v], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, vbase, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  {
+    const int kpad = (g->in_c + 7) / 8 * 8;
+    const uint64_t dims[2] = {(uint64_t)g->in_c, (uint64_t)g->kh * g->kw * g->out_c};
+    const uint64_t strides[1] = {(uint64_t)kpad * 2};
+    const uint32_t box[2] = {(uint32_t)kBlockK, (uint32_t)bn};
+    int rc = tc::make_map(&maps.b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w_packed, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  // destination views (one per output phase): 32-row x 32-column boxes
+  for (int v = 0; v < kMaxViews; ++v) {
+    const int vv = v < p.sp * p.sp ? v : 0;
+    const int py = vv / p.sp, px = vv % p.sp;
+    int vw = (g->out_w - px + p.sp - 1) / p.sp, vh = (g->out_h - py + p.sp - 1) / p.sp;
+    const bool empty = vw <= 0 || vh <= 0;      // no tile ever stores there (tiles are clipped), keep the map valid
+    if (vw < 1) vw = 1;
+    if (vh < 1) vh = 1;
+    const uint64_t dims[4] = {(uint64_t)g->out_c, (uint64_t)vw, (uint64_t)vh, (uint64_t)g->batch};
+    const uint32_t box[4] = {(uint32_t)kSlab, (uint32_t)p.ebw, (uint32_t)p.ebh, (uint32_t)p.ebb};
+    const size_t pix = empty ? 0 : (size_t)py * g->out_w + px;
+    if (out32) {
+      const uint64_t st[3] = {(uint64_t)p.sp * g->ld_out * 4, (uint64_t)p.sp * g->out_w * g->ld_out * 4,
+                              (uint64_t)g->out_h * g->out_w * g->ld_out * 4};
+      int rc = tc::make_map(&maps.o32[v], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, reinterpret_cast<char*>(out32) + pix * g->ld_out * 4, 4,
+                            dims, st, box, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc) return rc;
+    }
+    if (out16) {
+      const uint64_t st[3] = {(uint64_t)p.sp * ld_out16 * 2, (uint64_t)p.sp * g->out_w * ld_out16 * 2,
+                              (uint64_t)g->out_h * g->out_w * ld_out16 * 2};
+      int rc = tc::make_map(&maps.o16[v], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, reinterpret_cast<char*>(out16) + pix * ld_out16 * 2, 4,
+                            dims, st, box, CU_TENSOR_MAP_SWIZZLE_64B);
+      if (rc) return rc;
+    }
+    if (aux) {
+      const uint64_t st[3] = {(uint64_t)p.sp * ld_aux * 4, (uint64_t)p.sp * g->out_w * ld_aux * 4,
+                              (uint64_t)g->out_h * g->out_w * ld_aux * 4};
+      int rc = tc::make_map(&maps.aux[v], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                            const_cast<char*>(reinterpret_cast<const char*>(aux)) + pix * ld_aux * 4, 4, dims, st, box,
+                            CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc) return rc;
+    }
+  }
+  const int smem_bytes = stages * stage_bytes + epi_bytes + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_conv_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  const int grid = p.total_tiles < LB_SMS ? p.total_tiles : LB_SMS;
+  k_conv_tc2<<<grid, kThreads, smem_bytes, lb_s(s)>>>(maps, p);
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
+
+extern "C" int lb_conv_tc_ex_supported(const lb_conv_geom* g, int ld_out16, int ld_aux) {
+  if (!g) return 0;
+  // alignment of the pointers themselves is checked at call time; any 16-byte aligned base passes here
+  return tc2_ok(g, reinterpret_cast<const void*>(16), ld_out16 ? reinterpret_cast<const void*>(16) : nullptr, ld_out16,
+                ld_aux ? reinterpret_cast<const void*>(16) : nullptr, ld_aux) ? 1 : 0;
+}

@@ -321,6 +321,9 @@ class ActivatedBaseConv(nn.Module):
                                         in_channels=mid))
 
     def forward(self, function_input):
+        fused = ops.activated_pair(function_input, self.conv_0, self.conv_1)
+        if fused is not None:
+            return fused
         return self.conv_1(self.conv_0(function_input, pre_act=True), pre_act=True)
 
 

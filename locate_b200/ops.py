@@ -455,4 +455,4 @@ def gate(x, y, gamma, strict_reference=True):
 
 
 # the convolution family lives in conv_fn.py (imports helpers from this module, hence the late import)
-from .conv_fn import ConvSpec, SNConvFn, invalidate_packs, power_iterate, sn_conv  # noqa: E402,F401
+from .conv_fn import ConvSpec, SNConvFn, activated_pair, invalidate_packs, power_iterate, sn_conv  # noqa: E402,F401

@@ -176,7 +176,7 @@ def test_cuda_graph_replay_matches_eager():
     cfg = O.OracleConfig(IMAGE_SIZE=32, BASE_FEATURE_FACTOR=4)
     real, aug, z = (t.to(DEV) for t in O.synthetic_batch(cfg, 4))
     outs = {}
-    for mode in ("eager", "graph"):
+    for mode in ("eager", "eager2", "graph"):
         torch.manual_seed(999)
         gen, g_opt = L.get_model(L.Generator(), L.CFG.GLR, DEV)
         dis, d_opt = L.get_model(L.Discriminator(), L.CFG.DLR, DEV)
@@ -192,9 +192,14 @@ def test_cuda_graph_replay_matches_eager():
         outs[mode] = (d_out.clone().cpu(), g_out.clone().cpu(),
                       torch.cat([p.detach().reshape(-1) for p in dis.parameters()]).cpu(),
                       [a["sched"].cpu() for a in d_opt._arenas])
-    e, g = outs["eager"], outs["graph"]
+    e, e2, g = outs["eager"], outs["eager2"], outs["graph"]
     assert torch.equal(e[3][0], g[3][0]), "device-side Nadam step counters differ"
     assert float(e[3][0][0]) == 4.0
     assert torch.allclose(e[0], g[0], rtol=2e-2, atol=1e-3), (e[0], g[0])
     assert torch.allclose(e[1], g[1], rtol=2e-2, atol=1e-3), (e[1], g[1])
-    assert ((e[2] - g[2]).abs() > 5e-3).float().mean().item() < 1e-2
+    # Nadam's normalised update turns the run-to-run noise of atomically accumulated weight gradients into +-lr moves of
+    # near-zero-gradient parameters, so the yard-stick is the difference between two EAGER runs of the same program
+    def moved(a, b):
+        return ((a - b).abs() > 5e-3).float().mean().item()
+    noise, diff = moved(e[2], e2[2]), moved(e[2], g[2])
+    assert diff <= max(1e-2, 3.0 * noise), f"graph vs eager {diff:.4f}, eager vs eager {noise:.4f}"

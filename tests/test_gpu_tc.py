@@ -141,3 +141,87 @@ def test_tc_wgrad_matches_simt(name):
     call("lb_sn_weight_grad", ptr(dwp), ptr(wbar), ptr(u), ptr(v), ptr(sigma), ptr(gb), d0, d1 * t, t, ptr(work))
     torch.cuda.synchronize()
     assert (ga - gb).abs().max().item() <= 3e-4 * ga.abs().max().item() + 1e-5
+
+
+# ---- persistent kernel with the fused epilogue (lb_conv_tc_gemm_ex) against lb_conv_tc_gemm + torch elementwise ----
+def _roottanh(x):
+    return (x * x + 1) ** 0.25 * torch.tanh(x)
+
+
+def _roottanh_grad(x):
+    q = x * x + 1
+    th = torch.tanh(x)
+    return (2 * q * (1 - th * th) + x * th) * q ** 0.25 / (2 * q)
+
+
+EX_CASES = dict(CASES)
+EX_CASES.update({
+    "convT4_c192": ("convT", 5, 16, 16, 192, 192, 4, 2, 1, "fwd"),       # block_n = 192, many tiles per CTA
+    "convT4_many": ("convT", 40, 32, 32, 96, 96, 4, 2, 1, "fwd"),        # > 148 tiles: persistent loop + TMEM ping-pong
+    "1x1_many": ("conv", 24, 64, 64, 96, 48, 1, 1, 0, "fwd"),
+    "1x1_c384": ("conv", 9, 16, 16, 384, 384, 1, 1, 0, "fwd"),           # two channel tiles
+    "3x3_edge": ("conv", 3, 20, 12, 48, 40, 3, 1, 1, "fwd"),             # tiles overhang every dimension
+    "linear": ("conv", 37, 1, 1, 256, 1536, 1, 1, 0, "fwd"),
+})
+EX_MODES = ["o32", "o16", "o16act", "both_aux", "o16_aux"]
+
+
+@pytest.mark.parametrize("mode", EX_MODES)
+@pytest.mark.parametrize("name", sorted(EX_CASES))
+def test_tc_ex_matches_v1(name, mode):
+    kind, b, h, w, cin, cout, k, s, p, direction = EX_CASES[name]
+    gen = torch.Generator().manual_seed(hash(name) % 1000)
+    t = k * k
+    if kind == "conv":
+        wt = torch.randn((cout, cin, k, k), generator=gen)
+        oh, ow = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
+        fwd, dgr, mode_f, mode_d = (t, cin * t, k, 1), (cin * t, t, k, 1), 0, 1
+    else:
+        wt = torch.randn((cin, cout, k, k), generator=gen)
+        oh, ow = (h - 1) * s - 2 * p + k, (w - 1) * s - 2 * p + k
+        fwd, dgr, mode_f, mode_d = (cout * t, t, k, 1), (t, cout * t, k, 1), 1, 0
+    wt = (wt / (cin * t) ** 0.5).bfloat16().float().to(DEV)
+    pad_out = 8
+    if direction == "fwd":
+        src = torch.randn((b, h, w, cin), generator=gen).bfloat16().to(DEV)
+        g = geom(b, h, w, cin, oh, ow, cout, k, k, s, p, mode_f, cin, cout + pad_out, fwd)
+        out_shape = (b, oh, ow, cout + pad_out)
+    else:
+        src = torch.randn((b, oh, ow, cout), generator=gen).bfloat16().to(DEV)
+        g = geom(b, oh, ow, cout, h, w, cin, k, k, s, p, mode_d, cout, cin + pad_out, dgr)
+        out_shape = (b, h, w, cin + pad_out)
+    n = g.out_c
+    alpha = torch.tensor([1.7], device=DEV)
+    bias = torch.randn(n, generator=gen).to(DEV)
+    ref = torch.full(out_shape, -7.0, device=DEV)
+    packed = torch.empty(_lib.lib().lb_conv_tc_packed_elems(ctypes.byref(g)), dtype=torch.bfloat16, device=DEV)
+    call("lb_conv_tc_pack", ptr(wt), ptr(packed), ctypes.byref(g))
+    call("lb_conv_tc_gemm", ptr(src), ptr(packed), ptr(alpha), ptr(bias), ptr(ref), ctypes.byref(g))
+    ref = ref[..., :n]
+
+    want32 = mode in ("o32", "both_aux")
+    want16 = mode != "o32"
+    use_aux = mode.endswith("aux")
+    ld16 = (n + 7) // 8 * 8 + 8
+    ld_aux = (n + 3) // 4 * 4 + 4
+    got32 = torch.full(out_shape, -7.0, device=DEV) if want32 else None
+    got16 = torch.full(out_shape[:3] + (ld16,), -7.0, device=DEV, dtype=torch.bfloat16) if want16 else None
+    aux = None
+    if use_aux:
+        aux = torch.full(out_shape[:3] + (ld_aux,), float("nan"), device=DEV)
+        aux[..., :n] = 2.0 * torch.randn(out_shape[:3] + (n,), generator=gen).to(DEV)
+    assert _lib.lib().lb_conv_tc_ex_supported(ctypes.byref(g), ld16 if want16 else 0, ld_aux if use_aux else 0) == 1
+    call("lb_conv_tc_gemm_ex", ptr(src), ptr(packed), ptr(alpha), ptr(bias), ptr(got32), ptr(got16), ld16 if want16 else 0,
+         1 if mode == "o16act" else 0, ptr(aux), ld_aux if use_aux else 0, ctypes.byref(g))
+    torch.cuda.synchronize()
+    exp = ref * _roottanh_grad(aux[..., :n]) if use_aux else ref
+    scale = exp.abs().max().item()
+    if want32:
+        assert torch.all(got32[..., n:] == -7.0), "fp32 store outside its channel slice"
+        err = (got32[..., :n] - exp).abs().max().item()
+        assert err <= 2e-4 * scale + 1e-5, f"{name}/{mode}: fp32 max err {err:.3e} vs scale {scale:.3e}"
+    if want16:
+        assert torch.all(got16[..., n:].float() == -7.0), "bf16 store outside its channel slice"
+        exp16 = _roottanh(exp) if mode == "o16act" else exp
+        err = (got16[..., :n].float() - exp16).abs().max().item()
+        assert err <= 6e-3 * exp16.abs().max().item() + 1e-5, f"{name}/{mode}: bf16 max err {err:.3e}"
