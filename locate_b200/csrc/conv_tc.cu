@@ -102,38 +102,40 @@ __global__ void __launch_bounds__(192, 4) k_conv_tc(const __grid_constant__ TcMa
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (tc::elect_one()) {
+      // (tap, k-chunk) and the ring position advance incrementally: a lone producer thread cannot afford integer
+      // divisions per stage (each costs more than the MMAs it feeds)
+      const int sh = p.stride == 2 ? 1 : 0;
+      int kc = it_begin % p.kchunks, tap = it_begin / p.kchunks;
+      int iy = txc > 0 ? tap / txc : 0, ix = txc > 0 ? tap % txc : 0;
+      int s = 0; uint32_t ph = 0;
       for (int it = 0; it < iters; ++it) {
-        const int flat = it_begin + it;
-        const int kc = flat % p.kchunks, tap = flat / p.kchunks;
-        const int ty = ty0 + (tap / txc) * tys, tx = tx0 + (tap % txc) * txs;
+        const int ty = ty0 + iy * tys, tx = tx0 + ix * txs;
         int view = 0, dy, dx;
         if (p.mode == 0) {
-          const int ay = floordiv(ty - p.pad, p.stride), ax = floordiv(tx - p.pad, p.stride);
-          const int qy = (ty - p.pad) - ay * p.stride, qx = (tx - p.pad) - ax * p.stride;
-          view = qy * p.stride + qx;
-          dy = ay; dx = ax;
+          const int oy = ty - p.pad, ox = tx - p.pad;
+          dy = oy >> sh; dx = ox >> sh;                       // arithmetic shift = floor division (stride 1 or 2)
+          view = ((oy & (p.stride - 1)) << sh) + (ox & (p.stride - 1));
         } else {
-          dy = (py + p.pad - ty) / p.stride;
-          dx = (px + p.pad - tx) / p.stride;
+          dy = (py + p.pad - ty) >> sh;
+          dx = (px + p.pad - tx) >> sh;
         }
         const int cb = ((p.view_empty >> view) & 1) ? p.batch : b0;     // empty view: force the box out of range -> zeros
         const int wrow = (ty * p.kw + tx) * p.rows_per_tap + n0;
-        const int s = it % p.stages;
-        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
         tc::mbar_wait(&bar_empty[s], ph ^ 1u);
         uint8_t* sa = smem + s * stage_bytes;
         tc::mbar_arrive_expect_tx(&bar_full[s], (uint32_t)stage_bytes);
         tc::tma_load_4d(sa, &maps.a[view], &bar_full[s], kc * kBlockK, x0 + dx, y0 + dy, cb);
         tc::tma_load_2d(sa + kABytes, &maps.b, &bar_full[s], kc * kBlockK, wrow);
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
+        if (++kc == p.kchunks) { kc = 0; if (++ix == txc) { ix = 0; ++iy; } }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (tc::elect_one()) {
       const uint32_t idesc = tc::idesc_bf16(kBlockM, p.block_n, 0, 0);
+      int s = 0; uint32_t ph = 0;
       for (int it = 0; it < iters; ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
         tc::mbar_wait(&bar_full[s], ph);
         tc::tc_fence_after();
         const uint32_t sa = tc::smem_u32(smem + s * stage_bytes);
@@ -145,6 +147,7 @@ __global__ void __launch_bounds__(192, 4) k_conv_tc(const __grid_constant__ TcMa
           tc::umma_bf16(tmem_base, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
         }
         tc::umma_commit(&bar_empty[s]);          // stage reusable once these MMAs have read it
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
       if (iters > 0) tc::umma_commit(&bar_acc);   // accumulator complete
     }

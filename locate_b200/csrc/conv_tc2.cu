@@ -31,6 +31,19 @@ constexpr int kEpiWarps = 8;
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kSmemLimit = 227 * 1024 - 1024;      // dynamic; 1 KB left for the static barriers
 
+// n / d for n < 2^31 with a precomputed multiplier (Granlund-Montgomery): q = (umulhi(n, mul) + n) >> shr
+struct FastDiv { uint32_t mul, shr, d; };
+FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f; f.d = d; f.shr = 0;
+  while ((1u << f.shr) < d) ++f.shr;
+  f.mul = (uint32_t)((((uint64_t)1 << 32) * (((uint64_t)1 << f.shr) - d)) / d + 1);
+  return f;
+}
+__device__ __forceinline__ void fast_divmod(const FastDiv& f, int n, int& q, int& r) {
+  q = (int)((__umulhi((uint32_t)n, f.mul) + (uint32_t)n) >> f.shr);
+  r = n - q * (int)f.d;
+}
+
 struct Tc2Maps {
   CUtensorMap a[kMaxViews];
   CUtensorMap b;
@@ -40,8 +53,10 @@ struct Tc2Maps {
 };
 
 struct Tc2Params {
-  int batch, out_c, in_c;
+  int batch, out_c, in_c, in_h, in_w;
   int sp;                             // destination parity step (stride in mode 1, else 1)
+  int sh;                             // log2(stride)
+  FastDiv d_nt, d_tw, d_th, d_tb;     // divisors n_tiles, tiles_w, tiles_h, tiles_b
   int tile_w, tile_h, tile_b;         // box dims, product = 128
   int tiles_w, tiles_h, tiles_b, n_tiles, total_tiles;
   int block_n, acc_stride, kchunks, stages;
@@ -55,29 +70,49 @@ struct Tc2Params {
   const float* alpha; const float* bias;
 };
 
-__device__ __forceinline__ void tap_span(int mode, int s, int pad, int k, int parity, int& t0, int& step, int& cnt) {
-  if (mode == 1) {
-    t0 = (parity + pad) % s;
-    step = s;
-    cnt = t0 < k ? (k - t0 + s - 1) / s : 0;
-  } else {
-    t0 = 0; step = 1; cnt = k;
-  }
-}
-__device__ __forceinline__ int floordiv(int a, int b) { int q = a / b; return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q; }
-
 struct TileCoord { int x0, y0, b0, n0, py, px, phase; };
 __device__ __forceinline__ TileCoord decode_tile(const Tc2Params& p, int tile) {
   TileCoord c;
-  int t = tile;
-  const int nt = t % p.n_tiles; t /= p.n_tiles;
-  const int tw = t % p.tiles_w; t /= p.tiles_w;
-  const int th = t % p.tiles_h; t /= p.tiles_h;
-  const int tb = t % p.tiles_b; t /= p.tiles_b;
+  int t = tile, nt, tw, th, tb;
+  fast_divmod(p.d_nt, t, t, nt);
+  fast_divmod(p.d_tw, t, t, tw);
+  fast_divmod(p.d_th, t, t, th);
+  fast_divmod(p.d_tb, t, t, tb);
   c.phase = t;
   c.x0 = tw * p.tile_w; c.y0 = th * p.tile_h; c.b0 = tb * p.tile_b; c.n0 = nt * p.block_n;
-  c.py = c.phase / p.sp; c.px = c.phase % p.sp;
+  c.py = c.phase >> p.sh; c.px = c.phase & (p.sp - 1);
   return c;
+}
+
+// The taps one tile visits along one axis, and for each tap where its source box sits.  stride is 1 or 2, so every
+// division is a shift.  mode 1: taps t0, t0+s, .. (t = (parity + pad) mod s); box shift d = (parity + pad - t) / s in
+// the single dense view.  mode 0: every tap; (a, q) = divmod(t - pad, s): box shift a in parity view q.
+struct AxisTaps { int t0, step, cnt; };
+__device__ __forceinline__ AxisTaps axis_taps(const Tc2Params& p, int k, int parity) {
+  AxisTaps a;
+  if (p.mode == 1) {
+    a.t0 = (parity + p.pad) & (p.stride - 1);
+    a.step = p.stride;
+    a.cnt = a.t0 < k ? (k - a.t0 + p.stride - 1) >> p.sh : 0;
+  } else {
+    a.t0 = 0; a.step = 1; a.cnt = k;
+  }
+  return a;
+}
+// shift d, parity q and liveness of tap t on one axis: the box [o0 + d, o0 + d + tile) must meet the view [0, extent)
+__device__ __forceinline__ bool tap_axis(const Tc2Params& p, int t, int parity, int o0, int tile, int in_extent, int& d, int& q) {
+  int extent;
+  if (p.mode == 0) {
+    const int off = t - p.pad;
+    d = off >> p.sh;                     // arithmetic shift = floor division
+    q = off & (p.stride - 1);
+    extent = (in_extent - q + p.stride - 1) >> p.sh;
+  } else {
+    d = (parity + p.pad - t) >> p.sh;    // exact by construction of t
+    q = 0;
+    extent = in_extent;
+  }
+  return o0 + d < extent && o0 + d + tile > 0;
 }
 
 // ---- fast elementwise math for the epilogue (results are rounded to bf16 or multiplied into an fp32 gradient) ----
@@ -159,35 +194,34 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (tc::elect_one()) {
-      uint32_t git = 0;                                   // ring position, runs on across tiles
+      int st = 0; uint32_t ph = 0;                        // ring position, runs on across tiles
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const TileCoord c = decode_tile(p, tile);
-        int ty0, tys, tyc, tx0, txs, txc;
-        tap_span(p.mode, p.stride, p.pad, p.kh, c.py, ty0, tys, tyc);
-        tap_span(p.mode, p.stride, p.pad, p.kw, c.px, tx0, txs, txc);
-        const int iters = tyc * txc * p.kchunks;
-        for (int it = 0; it < iters; ++it, ++git) {
-          const int kc = it % p.kchunks, tap = it / p.kchunks;
-          const int ty = ty0 + (tap / txc) * tys, tx = tx0 + (tap % txc) * txs;
-          int view = 0, dy, dx;
-          if (p.mode == 0) {
-            const int ay = floordiv(ty - p.pad, p.stride), ax = floordiv(tx - p.pad, p.stride);
-            const int qy = (ty - p.pad) - ay * p.stride, qx = (tx - p.pad) - ax * p.stride;
-            view = qy * p.stride + qx;
-            dy = ay; dx = ax;
-          } else {
-            dy = (c.py + p.pad - ty) / p.stride;
-            dx = (c.px + p.pad - tx) / p.stride;
+        const AxisTaps ay = axis_taps(p, p.kh, c.py), ax = axis_taps(p, p.kw, c.px);
+        bool issued = false;
+        for (int iy = 0; iy < ay.cnt; ++iy) {
+          const int ty = ay.t0 + iy * ay.step;
+          int dy, qy;
+          const bool live_y = tap_axis(p, ty, c.py, c.y0, p.tile_h, p.in_h, dy, qy);
+          for (int ix = 0; ix < ax.cnt; ++ix) {
+            const int tx = ax.t0 + ix * ax.step;
+            int dx, qx;
+            const bool live = tap_axis(p, tx, c.px, c.x0, p.tile_w, p.in_w, dx, qx) && live_y;
+            const bool last = iy == ay.cnt - 1 && ix == ax.cnt - 1;
+            if (!live && !(last && !issued)) continue;        // a tap whose box is all padding adds nothing
+            issued = true;
+            const int view = (qy << p.sh) + qx;
+            const int cb = ((p.view_empty >> view) & 1) ? p.batch : c.b0;   // empty view: box out of range -> zeros
+            const int wrow = (ty * p.kw + tx) * p.rows_per_tap + c.n0;
+            for (int kc = 0; kc < p.kchunks; ++kc) {
+              tc::mbar_wait(&bar_empty[st], ph ^ 1u);
+              uint8_t* sa = smem + st * stage_bytes;
+              tc::mbar_arrive_expect_tx(&bar_full[st], (uint32_t)(kABytes + b_bytes));
+              tc::tma_load_4d(sa, &maps.a[view], &bar_full[st], kc * kBlockK, c.x0 + dx, c.y0 + dy, cb);
+              tc::tma_load_2d(sa + kABytes, &maps.b, &bar_full[st], kc * kBlockK, wrow);
+              if (++st == p.stages) { st = 0; ph ^= 1u; }
+            }
           }
-          const int cb = ((p.view_empty >> view) & 1) ? p.batch : c.b0;   // empty view: box out of range -> zeros
-          const int wrow = (ty * p.kw + tx) * p.rows_per_tap + c.n0;
-          const int s = git % p.stages;
-          const uint32_t ph = (git / p.stages) & 1u;
-          tc::mbar_wait(&bar_empty[s], ph ^ 1u);
-          uint8_t* sa = smem + s * stage_bytes;
-          tc::mbar_arrive_expect_tx(&bar_full[s], (uint32_t)(kABytes + b_bytes));
-          tc::tma_load_4d(sa, &maps.a[view], &bar_full[s], kc * kBlockK, c.x0 + dx, c.y0 + dy, cb);
-          tc::tma_load_2d(sa + kABytes, &maps.b, &bar_full[s], kc * kBlockK, wrow);
         }
       }
     }
@@ -196,32 +230,40 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
     if (tc::elect_one()) {
       const uint32_t idesc = tc::idesc_bf16(kBlockM, p.block_n, 0, 0);
       const int k16_last = (p.in_c - (p.kchunks - 1) * kBlockK + 15) / 16;
-      uint32_t git = 0;
+      int st = 0; uint32_t ph = 0;
       int lt = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
         const TileCoord c = decode_tile(p, tile);
-        int ty0, tys, tyc, tx0, txs, txc;
-        tap_span(p.mode, p.stride, p.pad, p.kh, c.py, ty0, tys, tyc);
-        tap_span(p.mode, p.stride, p.pad, p.kw, c.px, tx0, txs, txc);
-        const int iters = tyc * txc * p.kchunks;
+        const AxisTaps ay = axis_taps(p, p.kh, c.py), ax = axis_taps(p, p.kw, c.px);
         const int acc = lt & 1;
         tc::mbar_wait(&bar_tempty[acc], (((uint32_t)lt >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
         tc::tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.acc_stride);
-        for (int it = 0; it < iters; ++it, ++git) {
-          const int s = git % p.stages;
-          const uint32_t ph = (git / p.stages) & 1u;
-          tc::mbar_wait(&bar_full[s], ph);
-          tc::tc_fence_after();
-          const uint32_t sa = tc::smem_u32(smem + s * stage_bytes);
-          const uint32_t sb = sa + kABytes;
-          const int nk = (it % p.kchunks == p.kchunks - 1) ? k16_last : kBlockK / 16;
-          for (int k = 0; k < nk; ++k) {
-            const uint64_t ad = tc::smem_desc_sw128(sa + k * 32, 16, 1024);
-            const uint64_t bd = tc::smem_desc_sw128(sb + k * 32, 16, 1024);
-            tc::umma_bf16(tmem_d, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
+        bool issued = false;
+        for (int iy = 0; iy < ay.cnt; ++iy) {
+          int dy, qy;
+          const bool live_y = tap_axis(p, ay.t0 + iy * ay.step, c.py, c.y0, p.tile_h, p.in_h, dy, qy);
+          for (int ix = 0; ix < ax.cnt; ++ix) {
+            int dx, qx;
+            const bool live = tap_axis(p, ax.t0 + ix * ax.step, c.px, c.x0, p.tile_w, p.in_w, dx, qx) && live_y;
+            const bool last = iy == ay.cnt - 1 && ix == ax.cnt - 1;
+            if (!live && !(last && !issued)) continue;
+            for (int kc = 0; kc < p.kchunks; ++kc) {
+              tc::mbar_wait(&bar_full[st], ph);
+              tc::tc_fence_after();
+              const uint32_t sa = tc::smem_u32(smem + st * stage_bytes);
+              const uint32_t sb = sa + kABytes;
+              const int nk = (kc == p.kchunks - 1) ? k16_last : kBlockK / 16;
+              for (int k = 0; k < nk; ++k) {
+                const uint64_t ad = tc::smem_desc_sw128(sa + k * 32, 16, 1024);
+                const uint64_t bd = tc::smem_desc_sw128(sb + k * 32, 16, 1024);
+                tc::umma_bf16(tmem_d, ad, bd, idesc, (issued || k != 0) ? 1u : 0u);
+              }
+              issued = true;
+              tc::umma_commit(&bar_empty[st]);
+              if (++st == p.stages) { st = 0; ph ^= 1u; }
+            }
           }
-          tc::umma_commit(&bar_empty[s]);
         }
         tc::umma_commit(&bar_tfull[acc]);
       }
@@ -246,7 +288,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
     uint32_t a_issued = 0, a_done = 0;
     auto aux_advance = [&]() {                    // skip to the next (tile, slab) this warp owns
       while (a_tile < p.total_tiles) {
-        const int n0 = (a_tile % p.n_tiles) * p.block_n;
+        int tq, nt;
+        fast_divmod(p.d_nt, a_tile, tq, nt);
+        const int n0 = nt * p.block_n;
         const int nsl = (min(p.block_n, p.out_c - n0) + kSlab - 1) / kSlab;
         if (a_slab < nsl) return;
         a_tile += gridDim.x; a_slab = half;
@@ -388,7 +432,8 @@ extern "C" int lb_conv_tc_gemm_ex(const void* in_bf16, const void* w_packed, con
   Tc2Params p;
   p.mode = g->mode; p.stride = g->stride; p.pad = g->pad; p.kh = g->kh; p.kw = g->kw;
   p.sp = g->mode == 1 ? g->stride : 1;
-  p.batch = g->batch; p.out_c = g->out_c; p.in_c = g->in_c;
+  p.batch = g->batch; p.out_c = g->out_c; p.in_c = g->in_c; p.in_h = g->in_h; p.in_w = g->in_w;
+  p.sh = g->stride == 2 ? 1 : 0;
   const int dst_w = (g->out_w + p.sp - 1) / p.sp, dst_h = (g->out_h + p.sp - 1) / p.sp;
   p.tile_w = pow2_ceil(dst_w) < kBlockM ? pow2_ceil(dst_w) : kBlockM;
   int rest = kBlockM / p.tile_w;
@@ -428,6 +473,7 @@ extern "C" int lb_conv_tc_gemm_ex(const void* in_bf16, const void* w_packed, con
   p.tmem_cols = (uint32_t)pow2_ceil(2 * p.acc_stride < 32 ? 32 : 2 * p.acc_stride);
   p.epi_base = (uint32_t)(stages * stage_bytes);
   p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_b * p.n_tiles * p.sp * p.sp;
+  p.d_nt = make_fastdiv(p.n_tiles); p.d_tw = make_fastdiv(p.tiles_w); p.d_th = make_fastdiv(p.tiles_h); p.d_tb = make_fastdiv(p.tiles_b);
 
   // source views: mode 0 with stride 2 -> 4 parity views; otherwise one dense view
   const int nv = (g->mode == 0) ? g->stride * g->stride : 1;

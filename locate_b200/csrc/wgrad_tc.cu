@@ -76,13 +76,11 @@ __global__ void __launch_bounds__(192, 2) k_wgrad_tc(const __grid_constant__ WgM
 
   if (warp == 0) {
     if (tc::elect_one()) {
+      // pixel-tile coordinates and the ring position advance incrementally (no divisions in the producer loop)
+      int tw = t_begin % p.tiles_w, th = (t_begin / p.tiles_w) % p.tiles_h, tb = t_begin / (p.tiles_w * p.tiles_h);
+      int s = 0; uint32_t ph = 0;
       for (int it = 0; it < iters; ++it) {
-        int t = t_begin + it;
-        const int tw = t % p.tiles_w; t /= p.tiles_w;
-        const int th = t % p.tiles_h; t /= p.tiles_h;
-        const int x0 = tw * p.tile_w, y0 = th * p.tile_h, b0 = t * p.tile_b;
-        const int s = it % p.stages;
-        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+        const int x0 = tw * p.tile_w, y0 = th * p.tile_h, b0 = tb * p.tile_b;
         tc::mbar_wait(&bar_empty[s], ph ^ 1u);
         uint8_t* sa = smem + s * stage_bytes;
         tc::mbar_arrive_expect_tx(&bar_full[s], (uint32_t)stage_bytes);
@@ -91,14 +89,15 @@ __global__ void __launch_bounds__(192, 2) k_wgrad_tc(const __grid_constant__ WgM
         tc::tma_load_4d(sa + kBoxBytes, &maps.g[view], &bar_full[s], m0 + kBox, x0 + ax, y0 + ay, gb);
         for (int j = 0; j < p.n_boxes; ++j)
           tc::tma_load_4d(sa + a_bytes + j * kBoxBytes, &maps.d, &bar_full[s], n0 + j * kBox, x0, y0, b0);
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
+        if (++tw == p.tiles_w) { tw = 0; if (++th == p.tiles_h) { th = 0; ++tb; } }
       }
     }
   } else if (warp == 1) {
     if (tc::elect_one()) {
       const uint32_t idesc = tc::idesc_bf16(kM, p.block_n, 1, 1);
+      int s = 0; uint32_t ph = 0;
       for (int it = 0; it < iters; ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
         tc::mbar_wait(&bar_full[s], ph);
         tc::tc_fence_after();
         const uint32_t sa = tc::smem_u32(smem + s * stage_bytes);
@@ -111,6 +110,7 @@ __global__ void __launch_bounds__(192, 2) k_wgrad_tc(const __grid_constant__ WgM
           tc::umma_bf16(tmem_base, ad, bd, idesc, (it | k) != 0 ? 1u : 0u);
         }
         tc::umma_commit(&bar_empty[s]);
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
       if (iters > 0) tc::umma_commit(&bar_acc);
     }

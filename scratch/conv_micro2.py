@@ -57,12 +57,22 @@ for name in names:
     g = geom(b, h, h, cin, oh, oh, cout, k, k, s, p, mode, cin, cout, strides)
     packed = torch.empty(_lib.lib().lb_conv_tc_packed_elems(ctypes.byref(g)), dtype=torch.bfloat16, device=DEV)
     call("lb_conv_tc_pack", ptr(wt), ptr(packed), g)
+    if _lib.lib().lb_conv_tc_ex_supported(ctypes.byref(g), cout, cout) != 1:
+        print(name, "not covered by the persistent kernel"); continue
     ms1 = timeit(lambda: call("lb_conv_tc_gemm", ptr(x), ptr(packed), None, None, ptr(out), g))
     ms2 = timeit(lambda: call("lb_conv_tc_gemm_ex", ptr(x), ptr(packed), None, None, ptr(out), None, 0, 0, None, 0, g))
     ms3 = timeit(lambda: call("lb_conv_tc_gemm_ex", ptr(x), ptr(packed), None, None, ptr(out), ptr(out16), cout, 1, None, 0, g))
     ms4 = timeit(lambda: call("lb_conv_tc_gemm_ex", ptr(x), ptr(packed), None, None, None, ptr(out16), cout, 0, ptr(aux), cout, g))
     ms5 = timeit(lambda: call("lb_conv_tc_gemm_ex", ptr(x), ptr(packed), None, None, None, ptr(out16), cout, 0, None, 0, g))
+    # weight gradient of the same layer
+    dy16 = torch.randn((b, oh, oh, cout), device=DEV).bfloat16()
+    if c["kind"] == "conv":
+        gw = geom(b, h, h, cin, oh, oh, cout, k, k, s, p, 0, cin, cout, (t, cin * t, k, 1)); ga, de = x, dy16
+    else:
+        gw = geom(b, oh, oh, cout, h, h, cin, k, k, s, p, 0, cout, cin, (t, cout * t, k, 1)); ga, de = dy16, x
+    dwp = torch.zeros(t * cin * cout, device=DEV)
+    msw = timeit(lambda: call("lb_wgrad_tc", ptr(ga), ptr(de), ptr(dwp), gw))
     io32 = (x.numel() * 2 + out.numel() * 4) / 1e9
     tf = lambda ms: flops / ms / 1e9
     print(f"{name:13s} v1 {ms1*1e3:8.1f}us {tf(ms1):7.1f}TF | ex32 {ms2*1e3:8.1f}us {tf(ms2):7.1f}TF {io32/ms2*1e3:6.0f}GB/s | "
-          f"ex32+16act {ms3*1e3:8.1f}us | ex16+aux {ms4*1e3:8.1f}us | ex16 {ms5*1e3:8.1f}us {tf(ms5):7.1f}TF", flush=True)
+          f"ex32+16act {ms3*1e3:8.1f}us | ex16+aux {ms4*1e3:8.1f}us | ex16 {ms5*1e3:8.1f}us {tf(ms5):7.1f}TF | wgrad {msw*1e3:8.1f}us {tf(msw):7.1f}TF", flush=True)

@@ -210,7 +210,8 @@ def test_tc_ex_matches_v1(name, mode):
     if use_aux:
         aux = torch.full(out_shape[:3] + (ld_aux,), float("nan"), device=DEV)
         aux[..., :n] = 2.0 * torch.randn(out_shape[:3] + (n,), generator=gen).to(DEV)
-    assert _lib.lib().lb_conv_tc_ex_supported(ctypes.byref(g), ld16 if want16 else 0, ld_aux if use_aux else 0) == 1
+    if _lib.lib().lb_conv_tc_ex_supported(ctypes.byref(g), ld16 if want16 else 0, ld_aux if use_aux else 0) != 1:
+        pytest.skip("weight-bound shape: stays on the split-K path of k_conv_tc")
     call("lb_conv_tc_gemm_ex", ptr(src), ptr(packed), ptr(alpha), ptr(bias), ptr(got32), ptr(got16), ld16 if want16 else 0,
          1 if mode == "o16act" else 0, ptr(aux), ld_aux if use_aux else 0, ctypes.byref(g))
     torch.cuda.synchronize()
