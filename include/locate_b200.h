@@ -132,6 +132,17 @@ int lb_conv_gemm(const float* in, const float* w, const float* alpha, const floa
  * channel, w_sn the dense channel.  dw must be zeroed by the caller (atomic accumulation). */
 int lb_conv_wgrad(const float* gathered, const float* dense, float* dw, const lb_conv_geom* g,
                   lb_stream_t stream);
+/* Direct fp32 kernels for layers with a tiny channel count on one side (the discriminator stem 3->3 / 3->32 / 3->29 and
+ * the generator's final 48->3, conv.py:14-20): the weight sits in shared memory, every activation is touched once, and
+ * the neighbouring RootTanh is fused: growth_in > 0 applies RootTanh to the input on load (conv.py:23-24); growth_out > 0
+ * multiplies the result by RootTanh'(xpre[pixel][n]) (activation.py:18-36) -- the input-gradient direction.  Geometry and
+ * weight addressing are those of lb_conv_gemm / lb_conv_wgrad; growth_gathered applies RootTanh to the gathered operand. */
+int lb_conv_small_supported(const lb_conv_geom* g);
+int lb_conv_small(const float* in, const float* w, const float* alpha, const float* bias, float* out, const lb_conv_geom* g,
+                  int growth_in, const float* xpre, int ld_xpre, int growth_out, lb_stream_t stream);
+int lb_conv_small_wgrad_supported(const lb_conv_geom* g);
+int lb_conv_small_wgrad(const float* gathered, const float* dense, float* dw, const lb_conv_geom* g, int growth_gathered,
+                        lb_stream_t stream);
 /* ---- the same GEMM on the 5th-gen tensor cores (tcgen05.mma, TMEM accumulator, TMA tiles), bf16 operands,
  * fp32 accumulate/output.  `in` is the bf16 channels-last activation, `w_packed` the weight packed by
  * lb_conv_tc_pack as [tap][n][k] bf16 (lb_conv_tc_packed_elems elements).  lb_conv_tc_supported says

@@ -5,6 +5,7 @@ constructors (Generator(), Discriminator(), Block...) read when they are CALLED.
 """
 import dataclasses
 import math
+import os
 
 
 @dataclasses.dataclass
@@ -36,6 +37,7 @@ class Config:
     # "bf16": conv/linear GEMMs on the tcgen05 tensor cores (bf16 operands, fp32 accumulate) wherever the
     # geometry allows; "fp32": every GEMM on the fp32 SIMT kernel (bit-for-bit the reference's precision class)
     PRECISION: str = "bf16"
+    SMALL_KERNELS: bool = os.environ.get("LB_SMALL_KERNELS", "1") != "0"         # direct fp32 kernels for layers with <= 4 channels on one side (lb_conv_small*)
 
     @property
     def LAYERS(self):

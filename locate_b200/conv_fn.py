@@ -145,7 +145,10 @@ class SNConvFn(torch.autograd.Function):
         # tensor-core operands are bf16 rows padded to 16 bytes (TMA stride rule); channel counts are arbitrary
         cin_p, cout_p = (cin + 7) // 8 * 8, (spec.cout + 7) // 8 * 8
         tc = False
-        if CFG.PRECISION == "bf16":
+        g32 = geoms(cin, spec.cout)
+        # tiny channel count on one side (D stem, G's last 1x1): direct fp32 kernels, activation fused
+        small = CFG.SMALL_KERNELS and lib.lb_conv_small_supported(ctypes.byref(g32[0])) == 1
+        if CFG.PRECISION == "bf16" and not small:
             g_fwd, g_dgrad, g_wgrad = geoms(cin_p, cout_p)
             tc = (lib.lb_conv_tc_supported(ctypes.byref(g_fwd)) == 1 and lib.lb_conv_tc_supported(ctypes.byref(g_dgrad)) == 1
                   and lib.lb_wgrad_tc_supported(ctypes.byref(g_wgrad)) == 1)
@@ -167,6 +170,10 @@ class SNConvFn(torch.autograd.Function):
             pk = _packed_weight(w_bar, g_fwd, "fwd")
             _timed_call("conv_tc", fl, by / 2, "lb_conv_tc_gemm", ptr(a), ptr(pk), sigma.data_ptr() + 4, ptr(bias),
                         out.data_ptr() + off, g_fwd)
+        elif small:
+            a = x                                 # RootTanh is applied on load; nothing is materialised
+            _timed_call("conv_small", fl, by, "lb_conv_small", ptr(x), ptr(w_bar), sigma.data_ptr() + 4, ptr(bias),
+                        out.data_ptr() + off, g_fwd, CFG.ROOTTANH_GROWTH if pre_act else 0, None, 0, 0)
         else:
             if pre_act:
                 a = torch.empty_like(x)
@@ -181,6 +188,7 @@ class SNConvFn(torch.autograd.Function):
         ctx.u, ctx.v = u, v                      # LIVE u/v: the reference's backward reads them at backward time
         ctx.bias_param, ctx.w_param = bias, w_bar
         ctx.meta = (spec, cat_input, pre_act, tc, (b, h, w_, cin, oh, ow, ctot), g_dgrad, g_wgrad, (fl, by))
+        ctx.raw_a = bool(small and pre_act)      # `a` is the pre-activation: backward applies RootTanh where it needs it
         return out
 
     @staticmethod
@@ -192,6 +200,7 @@ class SNConvFn(torch.autograd.Function):
         rows = b * oh * ow
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         dx = dw_ret = dbias_ret = None
+        dact_done = False
         t = spec.taps
         height, width = spec.sn_shape
         if tc:
@@ -213,25 +222,42 @@ class SNConvFn(torch.autograd.Function):
                 call("lb_sn_weight_grad", ptr(dwp), ptr(w_bar), ptr(ctx.u.data), ptr(ctx.v.data), ptr(sigma), ptr(grad_w),
                      height, width, t, ptr(work))
         else:
+            lib = _lib.lib()
+            growth = CFG.ROOTTANH_GROWTH
             gy_ptr = gout.data_ptr() + off        # gradient of the conv output slice, row stride ctot
             g_dgrad.ld_in = ctot
             if need_dx:
                 dx = torch.empty_like(a)
-                _timed_call("conv_gemm", fl, by, "lb_conv_gemm", gy_ptr, ptr(w_bar), sigma.data_ptr() + 4, None, ptr(dx), g_dgrad)
+                if CFG.SMALL_KERNELS and lib.lb_conv_small_supported(ctypes.byref(g_dgrad)) == 1:
+                    _timed_call("conv_small", fl, by, "lb_conv_small", gy_ptr, ptr(w_bar), sigma.data_ptr() + 4, None, ptr(dx),
+                                g_dgrad, 0, ptr(x) if pre_act else None, cin, growth if pre_act else 0)
+                    dact_done = True
+                else:
+                    _timed_call("conv_gemm", fl, by, "lb_conv_gemm", gy_ptr, ptr(w_bar), sigma.data_ptr() + 4, None, ptr(dx), g_dgrad)
             if need_dw:
                 dwn = torch.zeros_like(w_bar, memory_format=torch.contiguous_format)
                 if spec.kind == "convT":
                     g_wgrad.ld_in = ctot
-                    _timed_call("conv_wgrad", fl, by, "lb_conv_wgrad", gy_ptr, ptr(a), ptr(dwn), g_wgrad)
                 else:
                     g_wgrad.ld_out = ctot
-                    _timed_call("conv_wgrad", fl, by, "lb_conv_wgrad", ptr(a), gy_ptr, ptr(dwn), g_wgrad)
+                small_w = CFG.SMALL_KERNELS and lib.lb_conv_small_wgrad_supported(ctypes.byref(g_wgrad)) == 1
+                fuse_act = ctx.raw_a and small_w and spec.kind != "convT"     # RootTanh on the gathered operand's load
+                if ctx.raw_a and not fuse_act:
+                    act = torch.empty_like(a)
+                    call("lb_roottanh_fwd", ptr(a), ptr(act), a.numel(), growth)
+                    a = act
+                ga_ptr, de_ptr = (gy_ptr, ptr(a)) if spec.kind == "convT" else (ptr(a), gy_ptr)
+                if small_w:
+                    _timed_call("conv_small_wgrad", fl, by, "lb_conv_small_wgrad", ga_ptr, de_ptr, ptr(dwn), g_wgrad,
+                                growth if fuse_act else 0)
+                else:
+                    _timed_call("conv_wgrad", fl, by, "lb_conv_wgrad", ga_ptr, de_ptr, ptr(dwn), g_wgrad)
                 grad_w, dw_ret = _grad_sink(ctx.w_param)
                 work = torch.empty(2, dtype=torch.float64, device=gout.device)
                 call("lb_sn_weight_grad", ptr(dwn), ptr(w_bar), ptr(ctx.u.data), ptr(ctx.v.data), ptr(sigma), ptr(grad_w),
                      height, width, 0, ptr(work))
         if need_dx:
-            if pre_act:
+            if pre_act and not dact_done:
                 call("lb_roottanh_bwd", ptr(x), ptr(dx), ptr(dx), dx.numel(), CFG.ROOTTANH_GROWTH)   # in place
             if cat_input:
                 call("lb_copy_rows", ptr(gout), ctot, ptr(dx), cin, b * h * w_, cin, 1)

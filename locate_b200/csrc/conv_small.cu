@@ -20,6 +20,7 @@ struct SmallP {
   int growth_out;     // > 0: result multiplied by RootTanh'(xpre[p][n])
   int ngroups;        // ceil(out_c / 4)
   long long pixels;   // batch*out_h*out_w
+  LbFastDiv d_grp, d_w, d_h;
 };
 
 // one thread = one output pixel x 4 consecutive output channels
@@ -32,15 +33,14 @@ __global__ void __launch_bounds__(256) k_conv_small(const SmallP p) {
   }
   __syncthreads();
   const float alpha = p.alpha ? __ldg(p.alpha) : 1.0f;
-  const long long total = p.pixels * p.ngroups;
-  const long long stride = (long long)gridDim.x * blockDim.x;
+  const int total = (int)(p.pixels * p.ngroups);          // < 2^31 (checked by the host)
+  const int stride = gridDim.x * blockDim.x;
   const bool vec_in = (p.in_c & 3) == 0 && (p.ld_in & 3) == 0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int grp = (int)(i % p.ngroups);
-    long long t = i / p.ngroups;
-    const int ox = (int)(t % p.out_w); t /= p.out_w;
-    const int oy = (int)(t % p.out_h);
-    const int b = (int)(t / p.out_h);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int t, grp, ox, oy, b;
+    lb_fast_divmod(p.d_grp, i, t, grp);
+    lb_fast_divmod(p.d_w, t, t, ox);
+    lb_fast_divmod(p.d_h, t, b, oy);
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     for (int ty = 0; ty < p.kh; ++ty) {
       int iy;
@@ -115,6 +115,8 @@ extern "C" int lb_conv_small(const float* in, const float* w, const float* alpha
   p.growth_in = growth_in; p.growth_out = growth_out;
   p.ngroups = (g->out_c + 3) / 4;
   p.pixels = (long long)g->batch * g->out_h * g->out_w;
+  if (p.pixels * p.ngroups >= (1ll << 31) - (1ll << 24)) return LB_EUNSUPPORTED;
+  p.d_grp = lb_make_fastdiv(p.ngroups); p.d_w = lb_make_fastdiv(g->out_w); p.d_h = lb_make_fastdiv(g->out_h);
   const size_t smem = (size_t)g->kh * g->kw * g->in_c * p.ngroups * 4 * sizeof(float);
   k_conv_small<<<lb_grid_1d((size_t)p.pixels * p.ngroups, 256, 16), 256, smem, lb_s(s)>>>(p);
   LB_LAUNCH_CHECK();
@@ -132,7 +134,8 @@ struct SmallWgP {
 };
 #define WG_TILE 64
 __global__ void __launch_bounds__(256) k_conv_small_wgrad(const SmallWgP p) {
-  __shared__ float sd[WG_TILE][33];        // dense rows of the tile (d_c <= 32 per pass handled by caller limit)
+  __shared__ float sd[WG_TILE][33];        // dense rows of the tile (d_c <= 32)
+  __shared__ int s_iy[WG_TILE], s_ix[WG_TILE], s_b[WG_TILE];   // gather origin of every dense pixel of the tile
   const int e = threadIdx.x;
   const bool live = e < p.n_elems;
   int kd = 0, kg = 0, ty = 0, tx = 0;
@@ -148,6 +151,14 @@ __global__ void __launch_bounds__(256) k_conv_small_wgrad(const SmallWgP p) {
   for (long long base = p0; base < p1; base += WG_TILE) {
     const int cnt = (int)min((long long)WG_TILE, p1 - base);
     __syncthreads();
+    if (threadIdx.x < cnt) {
+      const long long pix = base + threadIdx.x;
+      const int ox = (int)(pix % p.d_w);
+      const int oy = (int)((pix / p.d_w) % p.d_h);
+      s_b[threadIdx.x] = (int)(pix / ((long long)p.d_w * p.d_h));
+      s_iy[threadIdx.x] = oy * p.stride - p.pad;
+      s_ix[threadIdx.x] = ox * p.stride - p.pad;
+    }
     for (int i = threadIdx.x; i < cnt * p.d_c; i += blockDim.x) {
       const int r = i / p.d_c, c = i % p.d_c;
       sd[r][c] = __ldg(p.dense + (size_t)(base + r) * p.ld_d + c);
@@ -155,13 +166,9 @@ __global__ void __launch_bounds__(256) k_conv_small_wgrad(const SmallWgP p) {
     __syncthreads();
     if (live) {
       for (int r = 0; r < cnt; ++r) {
-        const long long pix = base + r;
-        const int ox = (int)(pix % p.d_w);
-        const int oy = (int)((pix / p.d_w) % p.d_h);
-        const int b = (int)(pix / ((long long)p.d_w * p.d_h));
-        const int iy = oy * p.stride - p.pad + ty, ix = ox * p.stride - p.pad + tx;
+        const int iy = s_iy[r] + ty, ix = s_ix[r] + tx;
         if (iy < 0 || iy >= p.g_h || ix < 0 || ix >= p.g_w) continue;
-        float gv = __ldg(p.gath + ((size_t)(b * p.g_h + iy) * p.g_w + ix) * p.ld_g + kg);
+        float gv = __ldg(p.gath + ((size_t)(s_b[r] * p.g_h + iy) * p.g_w + ix) * p.ld_g + kg);
         if (p.growth_g == 4) gv = lb_roottanh(gv); else if (p.growth_g > 0) gv = lb_roottanh_g(gv, 1.0f / p.growth_g);
         acc = fmaf(gv, sd[r][kd], acc);
       }

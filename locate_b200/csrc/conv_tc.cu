@@ -275,10 +275,58 @@ extern "C" int lb_conv_tc_pack(const float* w, void* packed, const lb_conv_geom*
   return LB_OK;
 }
 
+extern "C" int lb_conv_tc_gemm_ex(const void* in_bf16, const void* w_packed, const float* alpha, const float* bias, float* out32,
+                                  void* out16, int ld_out16, int act16, const float* aux, int ld_aux, const lb_conv_geom* g,
+                                  lb_stream_t s);
+extern "C" int lb_conv_tc_ex_supported(const lb_conv_geom* g, int ld_out16, int ld_aux);
+
+// Live taps of the first tile along one axis (host replica of the kernels' tap walk): a tap whose source box lies
+// entirely in the padding contributes nothing, and the persistent kernel skips it.
+static int live_taps_axis(const lb_conv_geom* g, int k, int tile, int in_extent) {
+  int live = 0;
+  const int s = g->stride;
+  for (int t = 0; t < k; ++t) {
+    int d, extent;
+    if (g->mode == 0) {
+      const int off = t - g->pad;
+      d = off >= 0 ? off / s : -((-off + s - 1) / s);
+      const int q = off - d * s;
+      extent = (in_extent - q + s - 1) / s;
+    } else {
+      if (((t - g->pad) % s + s) % s != 0) continue;   // tap of another output phase (phase 0 is representative)
+      d = (g->pad - t) / s;
+      extent = in_extent;
+    }
+    if (d < extent && d + tile > 0) ++live;
+  }
+  return live;
+}
+
+// Which kernel runs a plain (fp32 out) GEMM: the persistent one wins for few-tap tiles (1x1, the 4 live taps of a 4x4/s2
+// phase: the pipeline never drains between tiles) and whenever it can skip dead taps (full-extent feature-attention
+// kernels, 5x5 kernels on 2x2 maps); many-tap small-channel tiles keep k_conv_tc, whose 3-4 co-resident CTAs per SM
+// hide more TMA latency, and weight-bound shapes keep its split-K.
+static bool prefer_persistent(const lb_conv_geom* g) {
+  const int sp = g->mode == 1 ? g->stride : 1;
+  const int dst_w = (g->out_w + sp - 1) / sp, dst_h = (g->out_h + sp - 1) / sp;
+  const int tw = pow2_ceil(dst_w) < kBlockM ? pow2_ceil(dst_w) : kBlockM;
+  const int th = pow2_ceil(dst_h) < kBlockM / tw ? pow2_ceil(dst_h) : kBlockM / tw;
+  const int taps_eff = g->mode == 1 ? ((g->kh + sp - 1) / sp) * ((g->kw + sp - 1) / sp) : g->kh * g->kw;
+  if (taps_eff <= 4) return true;
+  const int ly = live_taps_axis(g, g->kh, th, g->in_h), lx = live_taps_axis(g, g->kw, tw, g->in_w);
+  const int live = ly * lx;
+  return live * 2 <= taps_eff;
+}
+
 extern "C" int lb_conv_tc_gemm(const void* in_bf16, const void* w_packed, const float* alpha, const float* bias, float* out,
                                const lb_conv_geom* g, lb_stream_t s) {
   LB_REQUIRE(in_bf16 && w_packed && out && g);
   if (!tc_geom_ok(g)) return LB_EUNSUPPORTED;
+  if (!getenv("LB_TC_V1_ONLY") && prefer_persistent(g) && lb_conv_tc_ex_supported(g, 0, 0) == 1 && !(g->ld_out & 3) &&
+      !(reinterpret_cast<uintptr_t>(out) & 15)) {
+    const int rc = lb_conv_tc_gemm_ex(in_bf16, w_packed, alpha, bias, out, nullptr, 0, 0, nullptr, 0, g, s);
+    if (rc != LB_EUNSUPPORTED) return rc;
+  }
   if (reinterpret_cast<uintptr_t>(in_bf16) & 15 || reinterpret_cast<uintptr_t>(w_packed) & 15) return LB_EALIGN;
   TcMaps maps;
   TcParams p;

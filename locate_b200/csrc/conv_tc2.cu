@@ -31,19 +31,6 @@ constexpr int kEpiWarps = 8;
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kSmemLimit = 227 * 1024 - 1024;      // dynamic; 1 KB left for the static barriers
 
-// n / d for n < 2^31 with a precomputed multiplier (Granlund-Montgomery): q = (umulhi(n, mul) + n) >> shr
-struct FastDiv { uint32_t mul, shr, d; };
-FastDiv make_fastdiv(uint32_t d) {
-  FastDiv f; f.d = d; f.shr = 0;
-  while ((1u << f.shr) < d) ++f.shr;
-  f.mul = (uint32_t)((((uint64_t)1 << 32) * (((uint64_t)1 << f.shr) - d)) / d + 1);
-  return f;
-}
-__device__ __forceinline__ void fast_divmod(const FastDiv& f, int n, int& q, int& r) {
-  q = (int)((__umulhi((uint32_t)n, f.mul) + (uint32_t)n) >> f.shr);
-  r = n - q * (int)f.d;
-}
-
 struct Tc2Maps {
   CUtensorMap a[kMaxViews];
   CUtensorMap b;
@@ -56,7 +43,7 @@ struct Tc2Params {
   int batch, out_c, in_c, in_h, in_w;
   int sp;                             // destination parity step (stride in mode 1, else 1)
   int sh;                             // log2(stride)
-  FastDiv d_nt, d_tw, d_th, d_tb;     // divisors n_tiles, tiles_w, tiles_h, tiles_b
+  LbFastDiv d_nt, d_tw, d_th, d_tb;     // divisors n_tiles, tiles_w, tiles_h, tiles_b
   int tile_w, tile_h, tile_b;         // box dims, product = 128
   int tiles_w, tiles_h, tiles_b, n_tiles, total_tiles;
   int block_n, acc_stride, kchunks, stages;
@@ -74,10 +61,10 @@ struct TileCoord { int x0, y0, b0, n0, py, px, phase; };
 __device__ __forceinline__ TileCoord decode_tile(const Tc2Params& p, int tile) {
   TileCoord c;
   int t = tile, nt, tw, th, tb;
-  fast_divmod(p.d_nt, t, t, nt);
-  fast_divmod(p.d_tw, t, t, tw);
-  fast_divmod(p.d_th, t, t, th);
-  fast_divmod(p.d_tb, t, t, tb);
+  lb_fast_divmod(p.d_nt, t, t, nt);
+  lb_fast_divmod(p.d_tw, t, t, tw);
+  lb_fast_divmod(p.d_th, t, t, th);
+  lb_fast_divmod(p.d_tb, t, t, tb);
   c.phase = t;
   c.x0 = tw * p.tile_w; c.y0 = th * p.tile_h; c.b0 = tb * p.tile_b; c.n0 = nt * p.block_n;
   c.py = c.phase >> p.sh; c.px = c.phase & (p.sp - 1);
@@ -289,7 +276,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
     auto aux_advance = [&]() {                    // skip to the next (tile, slab) this warp owns
       while (a_tile < p.total_tiles) {
         int tq, nt;
-        fast_divmod(p.d_nt, a_tile, tq, nt);
+        lb_fast_divmod(p.d_nt, a_tile, tq, nt);
         const int n0 = nt * p.block_n;
         const int nsl = (min(p.block_n, p.out_c - n0) + kSlab - 1) / kSlab;
         if (a_slab < nsl) return;
@@ -461,7 +448,8 @@ extern "C" int lb_conv_tc_gemm_ex(const void* in_bf16, const void* w_packed, con
   // channel tile: as wide as TMEM double buffering allows (<= 256) while leaving >= 3 ring stages
   int nt = (g->out_c + 255) / 256, bn = 0, stage_bytes = 0, stages = 0;
   for (;; ++nt) {
-    bn = ((g->out_c + nt - 1) / nt + 15) / 16 * 16;
+    // several channel tiles: a multiple of the 32-column slab, so no tile's last store reaches into its neighbour
+    bn = nt > 1 ? ((g->out_c + nt - 1) / nt + 31) / 32 * 32 : (g->out_c + 15) / 16 * 16;
     stage_bytes = kABytes + ((bn * kBlockK * 2 + 1023) & ~1023);
     stages = (kSmemLimit - 1024 - epi_bytes) / stage_bytes;
     if (stages >= 3 || bn <= 64) break;
@@ -473,7 +461,7 @@ extern "C" int lb_conv_tc_gemm_ex(const void* in_bf16, const void* w_packed, con
   p.tmem_cols = (uint32_t)pow2_ceil(2 * p.acc_stride < 32 ? 32 : 2 * p.acc_stride);
   p.epi_base = (uint32_t)(stages * stage_bytes);
   p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_b * p.n_tiles * p.sp * p.sp;
-  p.d_nt = make_fastdiv(p.n_tiles); p.d_tw = make_fastdiv(p.tiles_w); p.d_th = make_fastdiv(p.tiles_h); p.d_tb = make_fastdiv(p.tiles_b);
+  p.d_nt = lb_make_fastdiv(p.n_tiles); p.d_tw = lb_make_fastdiv(p.tiles_w); p.d_th = lb_make_fastdiv(p.tiles_h); p.d_tb = lb_make_fastdiv(p.tiles_b);
 
   // source views: mode 0 with stride 2 -> 4 parity views; otherwise one dense view
   const int nv = (g->mode == 0) ? g->stride * g->stride : 1;

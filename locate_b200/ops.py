@@ -57,9 +57,9 @@ def _timed_call(family, flops, nbytes, name, *args):
     e0.record()
     call(name, *args)
     e1.record()
-    g = args[-1]
+    g = next((a for a in args if hasattr(a, "in_c")), None)
     label = (f"{g.kh}x{g.kw}s{g.stride}m{g.mode} {g.in_c}->{g.out_c} in{g.in_h}x{g.in_w} out{g.out_h}x{g.out_w} b{g.batch}"
-             if hasattr(g, "in_c") else "")
+             if g is not None else "")
     _TIMER.records.append((family, flops, nbytes, e0, e1, label))
 
 

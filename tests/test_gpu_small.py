@@ -1,0 +1,134 @@
+"""Direct fp32 kernels for tiny-channel layers (lb_conv_small / lb_conv_small_wgrad) against the fp32 SIMT gather-GEMM
+(lb_conv_gemm / lb_conv_wgrad) with the fused RootTanh / RootTanh' applied by torch on the reference side."""
+import ctypes
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from locate_b200 import _lib                     # noqa: E402
+from locate_b200._lib import ConvGeom, call, ptr  # noqa: E402
+
+DEV = "cuda:0"
+
+
+def geom(b, ih, iw, ic, oh, ow, oc, kh, kw, s, p, mode, ld_in, ld_out, strides):
+    g = ConvGeom()
+    g.batch, g.in_h, g.in_w, g.in_c, g.out_h, g.out_w, g.out_c = b, ih, iw, ic, oh, ow, oc
+    g.kh, g.kw, g.stride, g.pad, g.mode, g.ld_in, g.ld_out = kh, kw, s, p, mode, ld_in, ld_out
+    g.w_sk, g.w_sn, g.w_sty, g.w_stx = strides
+    return g
+
+
+def roottanh(x):
+    return (x * x + 1) ** 0.25 * torch.tanh(x)
+
+
+def roottanh_grad(x):
+    q = x * x + 1
+    th = torch.tanh(x)
+    return (2 * q * (1 - th * th) + x * th) * q ** 0.25 / (2 * q)
+
+
+CASES = {
+    # name: (kind, b, h, w, cin, cout, k, s, p, direction)
+    "stem_1x1_3_29": ("conv", 3, 16, 16, 3, 29, 1, 1, 0, "fwd"),
+    "stem_5x5s2": ("conv", 3, 16, 16, 3, 3, 5, 2, 2, "fwd"),
+    "stem_5x5s2_odd": ("conv", 2, 13, 11, 3, 3, 5, 2, 2, "fwd"),
+    "stem_1x1_3_32": ("conv", 3, 8, 8, 3, 32, 1, 1, 0, "fwd"),
+    "last_1x1_48_3": ("conv", 3, 16, 16, 48, 3, 1, 1, 0, "fwd"),
+    "stem_5x5s2_dgrad": ("conv", 3, 16, 16, 3, 3, 5, 2, 2, "dgrad"),
+    "stem_1x1_3_32_dgrad": ("conv", 3, 8, 8, 3, 32, 1, 1, 0, "dgrad"),
+    "last_1x1_48_3_dgrad": ("conv", 3, 16, 16, 48, 3, 1, 1, 0, "dgrad"),
+    "convT_4x4s2_3": ("convT", 2, 8, 8, 3, 3, 4, 2, 1, "fwd"),
+    "convT_4x4s2_3_dgrad": ("convT", 2, 8, 8, 3, 3, 4, 2, 1, "dgrad"),
+}
+
+
+@pytest.mark.parametrize("fuse", ["plain", "act_in", "dact_out"])
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_small_matches_simt(name, fuse):
+    kind, b, h, w, cin, cout, k, s, p, direction = CASES[name]
+    gen = torch.Generator().manual_seed(hash(name) % 1000)
+    t = k * k
+    if kind == "conv":
+        wt = torch.randn((cout, cin, k, k), generator=gen)
+        oh, ow = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
+        fwd, dgr, mode_f, mode_d = (t, cin * t, k, 1), (cin * t, t, k, 1), 0, 1
+    else:
+        wt = torch.randn((cin, cout, k, k), generator=gen)
+        oh, ow = (h - 1) * s - 2 * p + k, (w - 1) * s - 2 * p + k
+        fwd, dgr, mode_f, mode_d = (cout * t, t, k, 1), (t, cout * t, k, 1), 1, 0
+    wt = wt.to(DEV)
+    pad_out = 5                              # write into a channel slice of a wider tensor
+    if direction == "fwd":
+        src = torch.randn((b, h, w, cin), generator=gen).to(DEV)
+        g = geom(b, h, w, cin, oh, ow, cout, k, k, s, p, mode_f, cin, cout + pad_out, fwd)
+        out_shape = (b, oh, ow, cout + pad_out)
+    else:
+        src = torch.randn((b, oh, ow, cout), generator=gen).to(DEV)
+        g = geom(b, oh, ow, cout, h, w, cin, k, k, s, p, mode_d, cout, cin + pad_out, dgr)
+        out_shape = (b, h, w, cin + pad_out)
+    n = g.out_c
+    assert _lib.lib().lb_conv_small_supported(ctypes.byref(g)) == 1
+    alpha = torch.tensor([0.37], device=DEV)
+    bias = torch.randn(n, generator=gen).to(DEV)
+    ref = torch.full(out_shape, -7.0, device=DEV)
+    got = torch.full(out_shape, -7.0, device=DEV)
+    src_ref = roottanh(src) if fuse == "act_in" else src
+    call("lb_conv_gemm", ptr(src_ref.contiguous()), ptr(wt), ptr(alpha), ptr(bias), ptr(ref), ctypes.byref(g))
+    xpre = None
+    if fuse == "dact_out":
+        xpre = 2.0 * torch.randn(out_shape[:3] + (n,), generator=gen).to(DEV)
+        ref[..., :n] *= roottanh_grad(xpre)
+    call("lb_conv_small", ptr(src), ptr(wt), ptr(alpha), ptr(bias), ptr(got), ctypes.byref(g), 4 if fuse == "act_in" else 0,
+         ptr(xpre), n, 4 if fuse == "dact_out" else 0)
+    torch.cuda.synchronize()
+    assert torch.equal(got[..., n:], ref[..., n:]), "wrote outside its channel slice"
+    err = (got - ref).abs().max().item()
+    scale = ref[..., :n].abs().max().item()
+    assert err <= 1e-4 * scale + 1e-5, f"{name}/{fuse}: max err {err:.3e} vs scale {scale:.3e}"
+
+
+WG_CASES = {
+    # name: (kind, b, h, w, cin, cout, k, s, p)   h,w = layer INPUT size
+    "wg_stem_1x1_3_29": ("conv", 3, 16, 16, 3, 29, 1, 1, 0),
+    "wg_stem_5x5s2": ("conv", 3, 16, 16, 3, 3, 5, 2, 2),
+    "wg_stem_5x5s2_odd": ("conv", 2, 13, 11, 3, 3, 5, 2, 2),
+    "wg_stem_1x1_3_32": ("conv", 5, 8, 8, 3, 32, 1, 1, 0),
+    "wg_last_1x1_48_3": ("conv", 3, 16, 16, 48, 3, 1, 1, 0),
+    "wg_convT_4x4s2_3": ("convT", 2, 8, 8, 3, 3, 4, 2, 1),
+}
+
+
+@pytest.mark.parametrize("act", [0, 4])
+@pytest.mark.parametrize("name", sorted(WG_CASES))
+def test_small_wgrad_matches_simt(name, act):
+    kind, b, h, w, cin, cout, k, s, p = WG_CASES[name]
+    gen = torch.Generator().manual_seed(hash(name) % 1000)
+    t = k * k
+    if kind == "conv":
+        oh, ow = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
+        x = torch.randn((b, h, w, cin), generator=gen).to(DEV)
+        dy = torch.randn((b, oh, ow, cout), generator=gen).to(DEV)
+        gathered, dense = x, dy
+        g = geom(b, h, w, cin, oh, ow, cout, k, k, s, p, 0, cin, cout, (t, cin * t, k, 1))
+        shape = (cout, cin, k, k)
+    else:
+        oh, ow = (h - 1) * s - 2 * p + k, (w - 1) * s - 2 * p + k
+        x = torch.randn((b, h, w, cin), generator=gen).to(DEV)
+        dy = torch.randn((b, oh, ow, cout), generator=gen).to(DEV)
+        gathered, dense = dy, x
+        g = geom(b, oh, ow, cout, h, w, cin, k, k, s, p, 0, cout, cin, (t, cout * t, k, 1))
+        shape = (cin, cout, k, k)
+    assert _lib.lib().lb_conv_small_wgrad_supported(ctypes.byref(g)) == 1
+    ref = torch.zeros(shape, device=DEV)
+    got = torch.zeros(shape, device=DEV)
+    gath_ref = (roottanh(gathered) if act else gathered).contiguous()
+    call("lb_conv_wgrad", ptr(gath_ref), ptr(dense), ptr(ref), ctypes.byref(g))
+    call("lb_conv_small_wgrad", ptr(gathered), ptr(dense), ptr(got), ctypes.byref(g), act)
+    torch.cuda.synchronize()
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= 2e-4 * scale + 1e-5, f"{name}: max err {err:.3e} vs scale {scale:.3e}"

@@ -162,6 +162,9 @@ EX_CASES.update({
     "1x1_c384": ("conv", 9, 16, 16, 384, 384, 1, 1, 0, "fwd"),           # two channel tiles
     "3x3_edge": ("conv", 3, 20, 12, 48, 40, 3, 1, 1, "fwd"),             # tiles overhang every dimension
     "linear": ("conv", 37, 1, 1, 256, 1536, 1, 1, 0, "fwd"),
+    "1x1_c352": ("conv", 4, 2, 2, 32, 352, 1, 1, 0, "fwd"),              # channel tile not a multiple of the 32-column slab
+    "1x1_c416": ("convT", 4, 1, 1, 192, 416, 1, 1, 0, "fwd"),
+    "featattn_dgrad": ("conv", 6, 16, 16, 64, 16, 16, 1, 0, "dgrad"),     # full-extent kernel: 2 live taps of 16 per tile
 })
 EX_MODES = ["o32", "o16", "o16act", "both_aux", "o16_aux"]
 
