@@ -61,6 +61,11 @@ int lb_norm_finalize(const double* sums, double n_total, float* stats, lb_stream
 /* y = (x-mean)*gain/std + bias ; gain is [C] (gain_batch_stride = 0) or [B][C] (stride = C). */
 int lb_norm_apply(const float* x, const float* stats, const float* gain, int gain_batch_stride,
                   const float* bias, float* y, int batch, int pixels, int channels, lb_stream_t stream);
+/* same, also emitting the bf16 operand of the GEMM that consumes the result: y16 = bf16(act16 ? RootTanh(y) : y)
+ * (conv.py:23-24 applies RootTanh first; attention.py:44 and :26 do not).  y may be NULL when only the GEMM reads the
+ * result.  Needs channels % 4 == 0 and 16-byte aligned pointers (LB_EALIGN otherwise: use lb_norm_apply + lb_cast_bf16). */
+int lb_norm_apply_ex(const float* x, const float* stats, const float* gain, int gain_batch_stride, const float* bias,
+                     float* y, void* y16, int act16, int batch, int pixels, int channels, lb_stream_t stream);
 /* backward, 3 steps (inplace_norm.py:17-27 composed with d std/dx):
  *  1. lb_norm_bwd_reduce: p1[b][c] += sum_hw g, p2[b][c] += sum_hw (x-mean)*g      (caller zeroes p1,p2)
  *  2. lb_norm_bwd_finalize: dgain (+=, [C] or [B][C]), dbias (+=, [C]), s[2] = {sum gain*p1, sum gain*p2}

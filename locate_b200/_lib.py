@@ -36,6 +36,7 @@ _SIGNATURES = {
     "lb_norm_stats": ([P, c_size_t, P, P], c_int),
     "lb_norm_finalize": ([P, c_double, P, P], c_int),
     "lb_norm_apply": ([P, P, P, c_int, P, P, c_int, c_int, c_int, P], c_int),
+    "lb_norm_apply_ex": ([P, P, P, c_int, P, P, P, c_int, c_int, c_int, c_int, P], c_int),
     "lb_norm_bwd_reduce": ([P, P, P, P, P, c_int, c_int, c_int, P], c_int),
     "lb_norm_bwd_finalize": ([P, P, P, c_int, P, c_int, c_int, P, P, P, P], c_int),
     "lb_norm_bwd_apply": ([P, P, P, P, c_int, P, P, c_int, c_int, c_int, P], c_int),

@@ -111,7 +111,12 @@ class SNConvFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w_bar, u, v, bias, spec, cat_input, pre_act, pre_sigma):
-        x = _as_act(x)
+        ready16 = getattr(x, "_lb_act16" if pre_act else "_lb_plain16", None)
+        if getattr(x, "_lb_unwritten", False):
+            if ready16 is None or pre_act or cat_input or CFG.PRECISION != "bf16" or x.shape[1] % 8:
+                raise RuntimeError("norm output was emitted as a bf16 operand only, but this conv needs its fp32 values")
+        else:
+            x = _as_act(x)
         is_vec = x.dim() == 2
         if is_vec:
             b, h, w_, cin = x.shape[0], 1, 1, x.shape[1]
@@ -153,12 +158,16 @@ class SNConvFn(torch.autograd.Function):
             tc = (lib.lb_conv_tc_supported(ctypes.byref(g_fwd)) == 1 and lib.lb_conv_tc_supported(ctypes.byref(g_dgrad)) == 1
                   and lib.lb_wgrad_tc_supported(ctypes.byref(g_wgrad)) == 1)
         if not tc:
+            if getattr(x, "_lb_unwritten", False):
+                raise RuntimeError("norm output exists only as a bf16 operand, but this conv is not on the tensor-core path")
             g_fwd, g_dgrad, g_wgrad = geoms(cin, spec.cout)
         fl, by = _conv_work(spec, b, h, w_, oh, ow)
         n = x.numel()
         if tc:
             growth = CFG.ROOTTANH_GROWTH if pre_act else 0
-            if cin_p == cin:
+            if cin_p == cin and ready16 is not None:
+                a = ready16
+            elif cin_p == cin:
                 a = _bf16_like(x)
                 if pre_act:
                     call("lb_roottanh_fwd_bf16", ptr(x), ptr(a), n, growth)
@@ -295,16 +304,20 @@ class ActivatedPairFn(torch.autograd.Function):
     `x` may carry `_lb_act16` = bf16 RootTanh(x) left by the kernel that produced it (norm apply)."""
 
     @staticmethod
-    def forward(ctx, x, w0, u0, v0, w1, u1, v1, spec0, spec1, sigma0, sigma1, geoms):
-        act16 = getattr(x, "_lb_act16", None)
-        x = _as_act(x)
+    def forward(ctx, x, w0, u0, v0, w1, u1, v1, spec0, spec1, sigma0, sigma1, geoms, pre_act0):
+        act16 = getattr(x, "_lb_act16" if pre_act0 else "_lb_plain16", None)
+        if act16 is None:
+            x = _as_act(x)
         b, cin, h, w_ = x.shape
         oh, ow = spec0.out_hw(h, w_)
         mid, cout = spec0.cout, spec1.cout
         (gf0, gd0, gw0), (gf1, gd1, gw1) = geoms
         if act16 is None:
             act16 = _bf16_like(x)
-            call("lb_roottanh_fwd_bf16", ptr(x), ptr(act16), x.numel(), CFG.ROOTTANH_GROWTH)
+            if pre_act0:
+                call("lb_roottanh_fwd_bf16", ptr(x), ptr(act16), x.numel(), CFG.ROOTTANH_GROWTH)
+            else:
+                call("lb_cast_bf16", ptr(x), ptr(act16), x.numel())
         y0 = _new_act((b, mid, oh, ow), x)
         a0 = _bf16_like(y0)
         fl0, by0 = _conv_work(spec0, b, h, w_, oh, ow)
@@ -314,16 +327,16 @@ class ActivatedPairFn(torch.autograd.Function):
         y1 = _new_act((b, cout, oh, ow), x)
         _timed_call("conv_tc", fl1, by1 / 2, "lb_conv_tc_gemm_ex", ptr(a0), ptr(_packed_weight(w1, gf1, "fwd")),
                     sigma1.data_ptr() + 4, None, ptr(y1), None, 0, 0, None, 0, gf1)
-        ctx.save_for_backward(x, act16, y0, a0, w0, w1, sigma0, sigma1)
+        ctx.save_for_backward(x if pre_act0 else None, act16, y0, a0, w0, w1, sigma0, sigma1)
         ctx.uv = (u0, v0, u1, v1)                # LIVE u/v (see SNConvFn)
-        ctx.meta = (spec0, spec1, geoms, (b, cin, h, w_, oh, ow, mid, cout), (fl0, by0, fl1, by1))
+        ctx.meta = (spec0, spec1, geoms, (b, cin, h, w_, oh, ow, mid, cout), (fl0, by0, fl1, by1), pre_act0)
         return y1
 
     @staticmethod
     def backward(ctx, gout):
         x, act16, y0, a0, w0, w1, sigma0, sigma1 = ctx.saved_tensors
         u0, v0, u1, v1 = ctx.uv
-        spec0, spec1, geoms, (b, cin, h, w_, oh, ow, mid, cout), (fl0, by0, fl1, by1) = ctx.meta
+        spec0, spec1, geoms, (b, cin, h, w_, oh, ow, mid, cout), (fl0, by0, fl1, by1), pre_act0 = ctx.meta
         (gf0, gd0, gw0), (gf1, gd1, gw1) = geoms
         gout = _as_act(gout)
         dev = gout.device
@@ -344,11 +357,11 @@ class ActivatedPairFn(torch.autograd.Function):
             if need_dx:
                 dx = _new_act((b, cin, h, w_), gout)
                 _timed_call("conv_tc", fl0, by0 / 2, "lb_conv_tc_gemm_ex", ptr(d0), ptr(_packed_weight(w0, gd0, "dgrad")),
-                            sigma0.data_ptr() + 4, None, ptr(dx), None, 0, 0, ptr(x), cin, gd0)
-        return (dx, dw0, None, None, dw1) + (None,) * 7
+                            sigma0.data_ptr() + 4, None, ptr(dx), None, 0, 0, ptr(x) if pre_act0 else None, cin if pre_act0 else 0, gd0)
+        return (dx, dw0, None, None, dw1) + (None,) * 8
 
 
-def activated_pair(x, sn0, sn1):
+def activated_pair(x, sn0, sn1, pre_act0=True):
     """conv_1(RootTanh(conv_0(RootTanh(x)))) for two SpectralNorm wrappers (layers.ActivatedBaseConv); returns None when
     the fused tensor-core path does not cover the layer (odd channel counts, fp32 mode, weight-bound split-K shapes)."""
     if CFG.PRECISION != "bf16" or x.dim() != 4 or CFG.ROOTTANH_GROWTH != 4:
@@ -376,7 +389,7 @@ def activated_pair(x, sn0, sn1):
         return gf, gd, gw
 
     g0, g1 = geoms(spec0, h, w_, cin, mid, oh, ow), geoms(spec1, oh, ow, mid, cout, oh, ow)
-    ok = (_ex_ok(g0[0], mid, 0) and _ex_ok(g1[0], 0, 0) and _ex_ok(g1[1], mid, mid) and _ex_ok(g0[1], 0, cin)
+    ok = (_ex_ok(g0[0], mid, 0) and _ex_ok(g1[0], 0, 0) and _ex_ok(g1[1], mid, mid) and _ex_ok(g0[1], 0, cin if pre_act0 else 0)
           and lib.lb_wgrad_tc_supported(ctypes.byref(g0[2])) == 1 and lib.lb_wgrad_tc_supported(ctypes.byref(g1[2])) == 1)
     if not ok:
         return None
@@ -388,7 +401,7 @@ def activated_pair(x, sn0, sn1):
         pre, sn._pre_sigma = sn._pre_sigma, None
         sig.append(pre if pre is not None else power_iterate(m.weight_bar, m.weight_u.data, m.weight_v.data, sn.spec))
     return ActivatedPairFn.apply(x, m0.weight_bar, m0.weight_u, m0.weight_v, m1.weight_bar, m1.weight_u, m1.weight_v,
-                                 spec0, spec1, sig[0], sig[1], (g0, g1))
+                                 spec0, spec1, sig[0], sig[1], (g0, g1), pre_act0)
 
 
 def sn_conv(x, w_bar, u, v, bias, spec, cat_input=False, pre_act=False, pre_sigma=None):

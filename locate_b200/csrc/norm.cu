@@ -2,6 +2,7 @@
 // std over all B*C*H*W elements, then per-channel (or per-sample-per-channel) gain and per-channel bias.
 // HBM-bound.  Statistics are accumulated in double so N ~ 1e8 elements survive; the (sum, sumsq) pair
 // and the two backward scalars are exposed so data parallel can all-reduce them between phases.
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 __global__ void __launch_bounds__(256) k_norm_stats(const float* __restrict__ x, size_t n, double* __restrict__ sums, int vec) {
@@ -74,6 +75,34 @@ __global__ void __launch_bounds__(256) k_norm_apply4(const float* __restrict__ x
     lb_st4(y + 4 * i, r);
   }
 }
+// same, also (or only) emitting the bf16 GEMM operand of the consumer: y16 = bf16(RootTanh?(y)).  y may be NULL when
+// nothing reads the fp32 result (a conv follows directly and its backward needs only the bf16 operand).
+template <bool kAct>
+__global__ void __launch_bounds__(256) k_norm_apply4_ex(const float* __restrict__ x, const float* __restrict__ stats,
+                                                       const float* __restrict__ gain, int gain_bs, const float* __restrict__ bias,
+                                                       float* __restrict__ y, __nv_bfloat16* __restrict__ y16, size_t n4, int pc4, int c4) {
+  const float mean = __ldg(stats), rstd = __ldg(stats + 2);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const size_t b = i / (size_t)pc4;
+    const int c = (int)(i % (size_t)c4) * 4;
+    const float4 v = lb_ld4(x + 4 * i);
+    const float4 gn = lb_ld4(gain + b * gain_bs + c);
+    const float4 bs = lb_ld4(bias + c);
+    float4 r;
+    r.x = fmaf((v.x - mean) * rstd, gn.x, bs.x);
+    r.y = fmaf((v.y - mean) * rstd, gn.y, bs.y);
+    r.z = fmaf((v.z - mean) * rstd, gn.z, bs.z);
+    r.w = fmaf((v.w - mean) * rstd, gn.w, bs.w);
+    if (y) lb_st4(y + 4 * i, r);
+    if (kAct) { r.x = lb_roottanh(r.x); r.y = lb_roottanh(r.y); r.z = lb_roottanh(r.z); r.w = lb_roottanh(r.w); }
+    __nv_bfloat162 lo = __floats2bfloat162_rn(r.x, r.y), hi = __floats2bfloat162_rn(r.z, r.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&lo);
+    pk.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(y16 + 4 * i) = pk;
+  }
+}
 __global__ void __launch_bounds__(256) k_norm_apply1(const float* __restrict__ x, const float* __restrict__ stats,
                                                     const float* __restrict__ gain, int gain_bs, const float* __restrict__ bias,
                                                     float* __restrict__ y, size_t n, int pc, int channels) {
@@ -97,6 +126,25 @@ extern "C" int lb_norm_apply(const float* x, const float* stats, const float* ga
   } else {
     k_norm_apply1<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(x, stats, gain, gain_batch_stride, bias, y, n, pixels * channels, channels);
   }
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
+
+extern "C" int lb_norm_apply_ex(const float* x, const float* stats, const float* gain, int gain_batch_stride, const float* bias,
+                                float* y, void* y16, int act16, int batch, int pixels, int channels, lb_stream_t s) {
+  LB_REQUIRE(x && stats && gain && bias && y16 && batch > 0 && pixels > 0 && channels > 0);
+  LB_REQUIRE(gain_batch_stride == 0 || gain_batch_stride == channels);
+  const size_t n = (size_t)batch * pixels * channels;
+  if ((channels & 3) || !lb_aligned16(x) || (y && !lb_aligned16(y)) || !lb_aligned16(gain) || !lb_aligned16(bias) ||
+      (reinterpret_cast<uintptr_t>(y16) & 7))
+    return LB_EALIGN;
+  __nv_bfloat16* o16 = reinterpret_cast<__nv_bfloat16*>(y16);
+  if (act16)
+    k_norm_apply4_ex<true><<<lb_grid_1d(n / 4, 256), 256, 0, lb_s(s)>>>(x, stats, gain, gain_batch_stride, bias, y, o16, n / 4,
+                                                                       pixels * channels / 4, channels / 4);
+  else
+    k_norm_apply4_ex<false><<<lb_grid_1d(n / 4, 256), 256, 0, lb_s(s)>>>(x, stats, gain, gain_batch_stride, bias, y, o16, n / 4,
+                                                                        pixels * channels / 4, channels / 4);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }

@@ -40,8 +40,27 @@ class InPlaceNorm(nn.Module):
         self.weight = nn.Parameter(torch.ones((1, features, *[1] * dim)))
         self.bias = nn.Parameter(torch.zeros((1, features, *[1] * dim)))
 
-    def forward(self, function_input, scale=None):
-        return ops.whole_norm(function_input, self.weight if scale is None else scale, self.bias)
+    def forward(self, function_input, scale=None, emit=None):
+        return ops.whole_norm(function_input, self.weight if scale is None else scale, self.bias, emit)
+
+
+def _emit_mode(module):
+    """Which bf16 GEMM operand the norm kernel should leave for the module that follows it: "act" when the module starts
+    with RootTanh -> conv (conv.py:22-24), "plain" when a spectral-normed conv reads the norm output directly
+    (attention.py:26,44) and nothing else does, None otherwise."""
+    if isinstance(module, ActivatedBaseConv):
+        return "act"
+    if isinstance(module, DeepResidualConv):
+        return _emit_mode(module.layers[0]) if len(module.layers) == 1 else _emit_mode_first(module.layers[0])
+    if isinstance(module, SelfAttention):
+        return "plain"
+    if isinstance(module, nn.Sequential) and len(module) > 0 and isinstance(module[0], SpectralNorm):
+        return "plain"
+    return None
+
+
+def _emit_mode_first(layer):
+    return "act" if isinstance(layer, ActivatedBaseConv) else None
 
 
 class Norm(nn.Module):
@@ -51,7 +70,7 @@ class Norm(nn.Module):
         self.module = module
 
     def forward(self, function_input, scale=None):
-        return self.module(self.i_norm(function_input, scale))
+        return self.module(self.i_norm(function_input, scale, emit=_emit_mode(self.module)))
 
 
 # ---- spectral norm (libs/spectral_norm.py:12-59) -----------------------------------------------
@@ -174,7 +193,7 @@ class ResModule(nn.Module):
             args.append(scale)
         res = self.residual_module(function_input)
         if self._broadcast_tail():
-            h = self.layer_module.i_norm(*args)
+            h = self.layer_module.i_norm(*args, emit=_emit_mode(self.layer_module.module))
             for layer in list(self.layer_module.module)[:-1]:
                 h = layer(h)
             layer_out = h                                  # [B,F,1,1] gate
@@ -304,7 +323,11 @@ class SelfAttention(nn.Module):
         x = function_input
         if len(size) != 2:                                  # generic [B,F,*]: one pixel axis
             x = function_input.reshape(batch, features, -1, 1)
-        out = self.nlin_1(self.conv_1(self.nlin_0(self.conv_0(x))))   # Conv1d(k=1) == per-pixel GEMM
+        fused = ops.activated_pair(x, self.conv_0, self.conv_1, pre_act0=False) if len(size) == 2 else None
+        if fused is not None:                             # conv_1(RootTanh(conv_0(x))) as one node (attention.py:48-52)
+            out = self.nlin_1(fused)
+        else:
+            out = self.nlin_1(self.conv_1(self.nlin_0(self.conv_0(x))))   # Conv1d(k=1) == per-pixel GEMM
         return out if len(size) == 2 else out.reshape(batch, features, *size)
 
 

@@ -74,6 +74,8 @@ def _conv_work(spec, b, h, w_, oh, ow):
 
 def _as_act(t):
     """fp32, CUDA, channels-last (4-D) or contiguous (other ranks)."""
+    if getattr(t, "_lb_unwritten", False):
+        raise RuntimeError("this tensor's fp32 values were never written (only its bf16 GEMM operand exists)")
     if t.dtype != torch.float32:
         t = t.float()
     if t.dim() == 4:
@@ -211,7 +213,10 @@ class WholeNormFn(torch.autograd.Function):
     gain: [1,C,1,1] parameter or [B,C,1,1] style tensor; bias: [1,C,1,1]."""
 
     @staticmethod
-    def forward(ctx, x, gain, bias):
+    def forward(ctx, x, gain, bias, emit=None):
+        """emit: None | "act" | "plain" -- also produce the bf16 operand of the conv that consumes the result
+        (RootTanh applied first for "act"), attached to the output as `_lb_act16` / `_lb_plain16`.  With "plain" nothing
+        but that conv reads the result, so the fp32 tensor is allocated but NOT written (`_lb_unwritten`)."""
         x = _as_act(x)
         b, p, c = _bpc(x)
         per_sample = gain.shape[0] != 1          # [B,C,1,1] style gain (B == 1 degenerates to the shared form)
@@ -224,7 +229,19 @@ class WholeNormFn(torch.autograd.Function):
         stats = torch.empty(4, dtype=torch.float32, device=x.device)
         call("lb_norm_finalize", ptr(sums), n_total, ptr(stats))
         y = torch.empty_like(x)
-        call("lb_norm_apply", ptr(x), ptr(stats), ptr(gain_c), c if per_sample else 0, ptr(bias), ptr(y), b, p, c)
+        from .config import CFG
+        if emit is not None and CFG.PRECISION == "bf16" and c % 8 == 0 and x.dim() == 4:
+            y16 = torch.empty_strided(x.shape, x.stride(), dtype=torch.bfloat16, device=x.device)
+            lazy = emit == "plain" and c >= 32     # wide enough that the consumer is always a tensor-core GEMM
+            call("lb_norm_apply_ex", ptr(x), ptr(stats), ptr(gain_c), c if per_sample else 0, ptr(bias), None if lazy else ptr(y),
+                 ptr(y16), 1 if emit == "act" else 0, b, p, c)
+            if emit == "act":
+                y._lb_act16 = y16
+            else:
+                y._lb_plain16 = y16
+                y._lb_unwritten = True
+        else:
+            call("lb_norm_apply", ptr(x), ptr(stats), ptr(gain_c), c if per_sample else 0, ptr(bias), ptr(y), b, p, c)
         ctx.save_for_backward(x, gain_c, stats)
         ctx.per_sample = per_sample
         ctx.gain_param, ctx.bias_param = gain, bias
@@ -257,7 +274,7 @@ class WholeNormFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             call("lb_norm_bwd_apply", ptr(x), ptr(g), ptr(stats), ptr(gain), c if ctx.per_sample else 0, ptr(sc), ptr(dx), b, p, c)
-        return dx, dgain_ret, dbias_ret
+        return dx, dgain_ret, dbias_ret, None
 
 
 # ------------------------------------------------------------------------------------------
@@ -446,8 +463,8 @@ def roottanh(x, growth=4):
     return RootTanhFn.apply(x, growth)
 
 
-def whole_norm(x, gain, bias):
-    return WholeNormFn.apply(x, gain, bias)
+def whole_norm(x, gain, bias, emit=None):
+    return WholeNormFn.apply(x, gain, bias, emit)
 
 
 def gate(x, y, gamma, strict_reference=True):
