@@ -282,13 +282,13 @@ def run_cuda(args):
 
 
 def main():
-    os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+    os.environ.pop("NCCL_DEBUG", None)         # NCCL prints its version banner on stdout at any debug level: rank 0 prints exactly one JSON line
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--batch", type=int, default=32, help="per-GPU batch")
+    ap.add_argument("--batch", type=int, default=384, help="per-GPU batch (weak scaling: fixed per GPU)")
     ap.add_argument("--ref-batch", type=int, default=4, help="batch of the CPU reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")

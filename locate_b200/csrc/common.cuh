@@ -80,25 +80,31 @@ __device__ __forceinline__ float4 lb_ld4(const float* p) {
 __device__ __forceinline__ void lb_st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
 // ---- RootTanh scalar math (libs/activation.py:9-36), fp32 ---------------------------------
-// tanh and sech^2 from one exp(-2|x|): exact limits, no cosh overflow (the reference's
-// 1/cosh^2 -> 0 for |x| > 44 is reproduced because e underflows to 0 there).
+// tanh and sech^2 from one exp(-2|x|): exact limits, no cosh overflow (the reference's 1/cosh^2 -> 0 for |x| > 44 is
+// reproduced because e underflows to 0 there).  Cost matters: several kernels evaluate this per element next to a
+// handful of bytes of traffic, so it is ~20 instructions (2-3 MUFU) with a few-ulp error instead of libm's tanhf +
+// IEEE sqrt/divide (~70): |x| < 0.25 takes the odd Taylor polynomial (1 - e would cancel), the rest (1-e)/(1+e).
+__device__ __forceinline__ float lb_sqrt_fast(float x) { float y; asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lb_rcp_fast(float x) { float y; asm("rcp.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ void lb_tanh_sech2(float x, float& th, float& sech2) {
   const float e = __expf(-2.0f * fabsf(x));
-  const float r = __frcp_rn(1.0f + e);
-  th = tanhf(x);                       // (1-e)/(1+e) cancels for small |x|; tanhf is 2 ulp
+  const float r = lb_rcp_fast(1.0f + e);
+  const float x2 = x * x;
+  const float poly = x * fmaf(x2, fmaf(x2, fmaf(x2, fmaf(x2, 62.0f / 2835.0f, -17.0f / 315.0f), 2.0f / 15.0f), -1.0f / 3.0f), 1.0f);
+  th = fabsf(x) < 0.25f ? poly : copysignf((1.0f - e) * r, x);
   sech2 = 4.0f * e * r * r;            // no cancellation for large |x| (1 - th^2 would)
 }
 __device__ __forceinline__ float lb_roottanh(float x) {   // growth == 4
   float th, s2;
   lb_tanh_sech2(x, th, s2);
-  return sqrtf(sqrtf(fmaf(x, x, 1.0f))) * th;
+  return lb_sqrt_fast(lb_sqrt_fast(fmaf(x, x, 1.0f))) * th;
 }
-__device__ __forceinline__ float lb_roottanh_grad(float x) {   // growth == 4: q^(3/4) = q / q^(1/4)
+__device__ __forceinline__ float lb_roottanh_grad(float x) {   // growth == 4: (2 q sech^2 + x tanh) q^(1/4) / (2 q)
   float th, s2;
   lb_tanh_sech2(x, th, s2);
   const float q = fmaf(x, x, 1.0f);
-  const float r4 = sqrtf(sqrtf(q));
-  return (2.0f * q * s2 + x * th) * r4 / (2.0f * q);
+  const float r4 = lb_sqrt_fast(lb_sqrt_fast(q));
+  return fmaf(2.0f * q, s2, x * th) * r4 * (0.5f * lb_rcp_fast(q));
 }
 __device__ __forceinline__ float lb_roottanh_g(float x, float inv_growth) {
   float th, s2;

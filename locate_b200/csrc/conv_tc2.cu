@@ -102,6 +102,26 @@ __device__ __forceinline__ bool tap_axis(const Tc2Params& p, int t, int parity, 
   return o0 + d < extent && o0 + d + tile > 0;
 }
 
+// Index range [lo, hi) of axis_taps() entries that can be live for a tile at o0 (a superset: tap_axis() still decides).
+// Scanning every tap costs the lone producer / MMA threads ~25 instructions per tap; a full-extent 64x1 kernel has two
+// live taps out of 64 per tile.
+__device__ __forceinline__ void axis_range(const Tc2Params& p, const AxisTaps& a, int parity, int o0, int tile, int in_extent,
+                                           int& lo, int& hi) {
+  if (p.mode == 1) {                     // d_i = D0 - i
+    const int D0 = (parity + p.pad - a.t0) >> p.sh;
+    lo = o0 + D0 - in_extent + 1;
+    hi = o0 + D0 + tile;
+  } else if (p.stride == 1) {            // d_t = t - pad
+    lo = p.pad - o0 - tile + 1;
+    hi = in_extent + p.pad - o0;
+  } else {                               // d_t = floor((t - pad) / 2), view extent <= ceil(in_extent / 2)
+    lo = p.pad + 2 * (1 - o0 - tile);
+    hi = p.pad + 2 * (((in_extent + 1) >> 1) - o0);
+  }
+  lo = max(lo, 0);
+  hi = min(hi, a.cnt);
+}
+
 // ---- fast elementwise math for the epilogue (results are rounded to bf16 or multiplied into an fp32 gradient) ----
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -185,30 +205,41 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const TileCoord c = decode_tile(p, tile);
         const AxisTaps ay = axis_taps(p, p.kh, c.py), ax = axis_taps(p, p.kw, c.px);
+        int ylo, yhi, xlo, xhi;
+        axis_range(p, ay, c.py, c.y0, p.tile_h, p.in_h, ylo, yhi);
+        axis_range(p, ax, c.px, c.x0, p.tile_w, p.in_w, xlo, xhi);
         bool issued = false;
-        for (int iy = 0; iy < ay.cnt; ++iy) {
+        auto load_tap = [&](int ty, int tx, int dy, int qy, int dx, int qx) {
+          const int view = (qy << p.sh) + qx;
+          const int cb = ((p.view_empty >> view) & 1) ? p.batch : c.b0;   // empty view: box out of range -> zeros
+          const int wrow = (ty * p.kw + tx) * p.rows_per_tap + c.n0;
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            tc::mbar_wait(&bar_empty[st], ph ^ 1u);
+            uint8_t* sa = smem + st * stage_bytes;
+            tc::mbar_arrive_expect_tx(&bar_full[st], (uint32_t)(kABytes + b_bytes));
+            tc::tma_load_4d(sa, &maps.a[view], &bar_full[st], kc * kBlockK, c.x0 + dx, c.y0 + dy, cb);
+            tc::tma_load_2d(sa + kABytes, &maps.b, &bar_full[st], kc * kBlockK, wrow);
+            if (++st == p.stages) { st = 0; ph ^= 1u; }
+          }
+        };
+        for (int iy = ylo; iy < yhi; ++iy) {
           const int ty = ay.t0 + iy * ay.step;
           int dy, qy;
-          const bool live_y = tap_axis(p, ty, c.py, c.y0, p.tile_h, p.in_h, dy, qy);
-          for (int ix = 0; ix < ax.cnt; ++ix) {
+          if (!tap_axis(p, ty, c.py, c.y0, p.tile_h, p.in_h, dy, qy)) continue;
+          for (int ix = xlo; ix < xhi; ++ix) {
             const int tx = ax.t0 + ix * ax.step;
             int dx, qx;
-            const bool live = tap_axis(p, tx, c.px, c.x0, p.tile_w, p.in_w, dx, qx) && live_y;
-            const bool last = iy == ay.cnt - 1 && ix == ax.cnt - 1;
-            if (!live && !(last && !issued)) continue;        // a tap whose box is all padding adds nothing
+            if (!tap_axis(p, tx, c.px, c.x0, p.tile_w, p.in_w, dx, qx)) continue;   // a tap whose box is all padding adds nothing
             issued = true;
-            const int view = (qy << p.sh) + qx;
-            const int cb = ((p.view_empty >> view) & 1) ? p.batch : c.b0;   // empty view: box out of range -> zeros
-            const int wrow = (ty * p.kw + tx) * p.rows_per_tap + c.n0;
-            for (int kc = 0; kc < p.kchunks; ++kc) {
-              tc::mbar_wait(&bar_empty[st], ph ^ 1u);
-              uint8_t* sa = smem + st * stage_bytes;
-              tc::mbar_arrive_expect_tx(&bar_full[st], (uint32_t)(kABytes + b_bytes));
-              tc::tma_load_4d(sa, &maps.a[view], &bar_full[st], kc * kBlockK, c.x0 + dx, c.y0 + dy, cb);
-              tc::tma_load_2d(sa + kABytes, &maps.b, &bar_full[st], kc * kBlockK, wrow);
-              if (++st == p.stages) { st = 0; ph ^= 1u; }
-            }
+            load_tap(ty, tx, dy, qy, dx, qx);
           }
+        }
+        if (!issued) {                                        // every tap is padding: one of them still defines the zeros
+          const int ty = ay.t0 + (ay.cnt - 1) * ay.step, tx = ax.t0 + (ax.cnt - 1) * ax.step;
+          int dy, qy, dx, qx;
+          tap_axis(p, ty, c.py, c.y0, p.tile_h, p.in_h, dy, qy);
+          tap_axis(p, tx, c.px, c.x0, p.tile_w, p.in_w, dx, qx);
+          load_tap(ty, tx, dy, qy, dx, qx);
         }
       }
     }
@@ -226,32 +257,37 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
         tc::mbar_wait(&bar_tempty[acc], (((uint32_t)lt >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
         tc::tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.acc_stride);
+        int ylo, yhi, xlo, xhi;
+        axis_range(p, ay, c.py, c.y0, p.tile_h, p.in_h, ylo, yhi);
+        axis_range(p, ax, c.px, c.x0, p.tile_w, p.in_w, xlo, xhi);
         bool issued = false;
-        for (int iy = 0; iy < ay.cnt; ++iy) {
-          int dy, qy;
-          const bool live_y = tap_axis(p, ay.t0 + iy * ay.step, c.py, c.y0, p.tile_h, p.in_h, dy, qy);
-          for (int ix = 0; ix < ax.cnt; ++ix) {
-            int dx, qx;
-            const bool live = tap_axis(p, ax.t0 + ix * ax.step, c.px, c.x0, p.tile_w, p.in_w, dx, qx) && live_y;
-            const bool last = iy == ay.cnt - 1 && ix == ax.cnt - 1;
-            if (!live && !(last && !issued)) continue;
-            for (int kc = 0; kc < p.kchunks; ++kc) {
-              tc::mbar_wait(&bar_full[st], ph);
-              tc::tc_fence_after();
-              const uint32_t sa = tc::smem_u32(smem + st * stage_bytes);
-              const uint32_t sb = sa + kABytes;
-              const int nk = (kc == p.kchunks - 1) ? k16_last : kBlockK / 16;
-              for (int k = 0; k < nk; ++k) {
-                const uint64_t ad = tc::smem_desc_sw128(sa + k * 32, 16, 1024);
-                const uint64_t bd = tc::smem_desc_sw128(sb + k * 32, 16, 1024);
-                tc::umma_bf16(tmem_d, ad, bd, idesc, (issued || k != 0) ? 1u : 0u);
-              }
-              issued = true;
-              tc::umma_commit(&bar_empty[st]);
-              if (++st == p.stages) { st = 0; ph ^= 1u; }
+        auto mma_tap = [&]() {
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            tc::mbar_wait(&bar_full[st], ph);
+            tc::tc_fence_after();
+            const uint32_t sa = tc::smem_u32(smem + st * stage_bytes);
+            const uint32_t sb = sa + kABytes;
+            const int nk = (kc == p.kchunks - 1) ? k16_last : kBlockK / 16;
+            for (int k = 0; k < nk; ++k) {
+              const uint64_t ad = tc::smem_desc_sw128(sa + k * 32, 16, 1024);
+              const uint64_t bd = tc::smem_desc_sw128(sb + k * 32, 16, 1024);
+              tc::umma_bf16(tmem_d, ad, bd, idesc, (issued || k != 0) ? 1u : 0u);
             }
+            issued = true;
+            tc::umma_commit(&bar_empty[st]);
+            if (++st == p.stages) { st = 0; ph ^= 1u; }
+          }
+        };
+        for (int iy = ylo; iy < yhi; ++iy) {
+          int dy, qy;
+          if (!tap_axis(p, ay.t0 + iy * ay.step, c.py, c.y0, p.tile_h, p.in_h, dy, qy)) continue;
+          for (int ix = xlo; ix < xhi; ++ix) {
+            int dx, qx;
+            if (!tap_axis(p, ax.t0 + ix * ax.step, c.px, c.x0, p.tile_w, p.in_w, dx, qx)) continue;
+            mma_tap();
           }
         }
+        if (!issued) mma_tap();
         tc::umma_commit(&bar_tfull[acc]);
       }
     }

@@ -83,11 +83,16 @@ __global__ void __launch_bounds__(192, 2) k_wgrad_tc(const __grid_constant__ WgM
         const int x0 = tw * p.tile_w, y0 = th * p.tile_h, b0 = tb * p.tile_b;
         tc::mbar_wait(&bar_empty[s], ph ^ 1u);
         uint8_t* sa = smem + s * stage_bytes;
-        tc::mbar_arrive_expect_tx(&bar_full[s], (uint32_t)stage_bytes);
+        // a 64-channel box beyond the operand's channels would be pure zero fill: its accumulator rows / columns are
+        // never stored, so it is not loaded at all (the MMA reads stale shared memory there, rows stay independent)
+        const bool m_hi = m0 + kBox < p.g_c;
+        int n_live = (p.d_c - n0 + kBox - 1) / kBox;
+        if (n_live > p.n_boxes) n_live = p.n_boxes;
+        tc::mbar_arrive_expect_tx(&bar_full[s], (uint32_t)((1 + (m_hi ? 1 : 0) + n_live) * kBoxBytes));
         const int gb = empty_view ? p.batch : b0;
         tc::tma_load_4d(sa, &maps.g[view], &bar_full[s], m0, x0 + ax, y0 + ay, gb);
-        tc::tma_load_4d(sa + kBoxBytes, &maps.g[view], &bar_full[s], m0 + kBox, x0 + ax, y0 + ay, gb);
-        for (int j = 0; j < p.n_boxes; ++j)
+        if (m_hi) tc::tma_load_4d(sa + kBoxBytes, &maps.g[view], &bar_full[s], m0 + kBox, x0 + ax, y0 + ay, gb);
+        for (int j = 0; j < n_live; ++j)
           tc::tma_load_4d(sa + a_bytes + j * kBoxBytes, &maps.d, &bar_full[s], n0 + j * kBox, x0, y0, b0);
         if (++s == p.stages) { s = 0; ph ^= 1u; }
         if (++tw == p.tiles_w) { tw = 0; if (++th == p.tiles_h) { th = 0; ++tb; } }
