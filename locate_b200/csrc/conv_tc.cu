@@ -252,25 +252,31 @@ extern "C" size_t lb_conv_tc_packed_elems(const lb_conv_geom* g) {
   return (size_t)g->kh * g->kw * g->out_c * kpad;
 }
 
-__global__ void k_pack_weight(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int taps_w, int n_rows, int k, int kpad,
-                              long long w_sk, long long w_sn, long long w_sty, long long w_stx, size_t total) {
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int kk = (int)(i % kpad);
-    const size_t r = i / kpad;
-    const int n = (int)(r % n_rows);
-    const int tap = (int)(r / n_rows);
-    const int ty = tap / taps_w, tx = tap % taps_w;
-    const float v = kk < k ? w[kk * w_sk + n * w_sn + ty * w_sty + tx * w_stx] : 0.0f;
-    out[i] = __float2bfloat16(v);
+// One thread = one (n, k) pair: its taps are contiguous in the master layout (64-100 bytes read in one go), and for each
+// tap consecutive threads write consecutive k of one packed row.
+__global__ void __launch_bounds__(256) k_pack_weight(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int taps_h, int taps_w,
+                                                    int n_rows, int k, int kpad, long long w_sk, long long w_sn, long long w_sty,
+                                                    long long w_stx, int items, LbFastDiv d_kpad) {
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < items; i += stride) {
+    int n, kk;
+    lb_fast_divmod(d_kpad, i, n, kk);
+    const float* src = w + kk * w_sk + n * w_sn;
+    __nv_bfloat16* dst = out + (size_t)n * kpad + kk;
+    const size_t tap_stride = (size_t)n_rows * kpad;
+    for (int ty = 0; ty < taps_h; ++ty)
+      for (int tx = 0; tx < taps_w; ++tx)
+        dst[(size_t)(ty * taps_w + tx) * tap_stride] = __float2bfloat16(kk < k ? __ldg(src + ty * w_sty + tx * w_stx) : 0.0f);
   }
 }
 extern "C" int lb_conv_tc_pack(const float* w, void* packed, const lb_conv_geom* g, lb_stream_t s) {
   LB_REQUIRE(w && packed && g);
   const int kpad = (g->in_c + 7) / 8 * 8;
-  const size_t total = lb_conv_tc_packed_elems(g);
-  k_pack_weight<<<lb_grid_1d(total, 256), 256, 0, lb_s(s)>>>(w, reinterpret_cast<__nv_bfloat16*>(packed), g->kw, g->out_c, g->in_c,
-                                                            kpad, g->w_sk, g->w_sn, g->w_sty, g->w_stx, total);
+  const long long items = (long long)g->out_c * kpad;
+  LB_REQUIRE(items < (1ll << 31) - (1ll << 24));
+  k_pack_weight<<<lb_grid_1d((size_t)items, 256), 256, 0, lb_s(s)>>>(w, reinterpret_cast<__nv_bfloat16*>(packed), g->kh, g->kw, g->out_c,
+                                                                    g->in_c, kpad, g->w_sk, g->w_sn, g->w_sty, g->w_stx, (int)items,
+                                                                    lb_make_fastdiv(kpad));
   LB_LAUNCH_CHECK();
   return LB_OK;
 }

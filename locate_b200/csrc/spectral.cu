@@ -77,34 +77,44 @@ extern "C" int lb_sn_power_iter(const float* w, int height, int width, float* u,
 // ---- weight gradient epilogue --------------------------------------------------------------
 // dwn is either in the master layout (packed_taps = 0) or tap-major packed [taps][d0][d1] as written by
 // lb_wgrad_tc (master [d0][d1][taps]); the master index k maps to the packed offset below.
-__device__ __forceinline__ size_t dwn_offset(size_t k, int width, int height, int taps) {
-  if (taps == 0) return k;
-  const size_t i = k / width;
-  const int j = (int)(k % width);
-  const int d1 = width / taps;
-  return ((size_t)(j % taps) * height + i) * d1 + j / taps;
+// Index decoding uses multiply-shift division by (width, taps): a 64-bit divide per element made these two kernels
+// instruction-bound (they only stream W-sized arrays).
+struct SnIdx { LbFastDiv d_width, d_taps; int width, height, taps, d1; };
+__device__ __forceinline__ void sn_decode(const SnIdx& x, int k, int& i, int& j, size_t& off) {
+  lb_fast_divmod(x.d_width, k, i, j);
+  if (x.taps == 0) { off = (size_t)k; return; }
+  int j1, tap;
+  lb_fast_divmod(x.d_taps, j, j1, tap);
+  off = ((size_t)tap * x.height + i) * x.d1 + j1;
 }
-__global__ void __launch_bounds__(256) k_sn_dot(const float* __restrict__ a, const float* __restrict__ b, size_t n, int width, int height,
-                                               int taps, double* __restrict__ out) {
+__global__ void __launch_bounds__(256) k_sn_dot(const float* __restrict__ a, const float* __restrict__ b, int n, const SnIdx x,
+                                               double* __restrict__ out) {
   __shared__ double scratch[32];
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const int stride = gridDim.x * blockDim.x;
+  float part = 0.0f;
   double acc = 0.0;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-    acc += (double)(a[dwn_offset(i, width, height, taps)] * b[i]);
+  int cnt = 0;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+    int i, j; size_t off;
+    sn_decode(x, k, i, j, off);
+    part = fmaf(a[off], b[k], part);
+    if (++cnt == 16) { acc += (double)part; part = 0.0f; cnt = 0; }     // short fp32 runs, fp64 across them
+  }
+  acc += (double)part;
   acc = lb_block_sum(acc, scratch);
   if (threadIdx.x == 0) atomicAdd(out, acc);
 }
 // grad[i][j] += dwn[i][j]/sigma - dot/sigma^2 * u[i] v[j]
 __global__ void __launch_bounds__(256) k_sn_wgrad(const float* __restrict__ dwn, const float* __restrict__ u, const float* __restrict__ v,
                                                  const float* __restrict__ sigma, const double* __restrict__ dot,
-                                                 float* __restrict__ grad, size_t n, int width, int height, int taps) {
+                                                 float* __restrict__ grad, int n, const SnIdx x) {
   const float inv = __ldg(sigma + 1);
   const float coef = (float)(dot[0] * (double)inv * (double)inv);
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
-    const size_t i = k / width;
-    const int j = (int)(k % width);
-    grad[k] += fmaf(dwn[dwn_offset(k, width, height, taps)], inv, -coef * __ldg(u + i) * __ldg(v + j));
+  const int stride = gridDim.x * blockDim.x;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+    int i, j; size_t off;
+    sn_decode(x, k, i, j, off);
+    grad[k] += fmaf(dwn[off], inv, -coef * __ldg(u + i) * __ldg(v + j));
   }
 }
 extern "C" int lb_sn_weight_grad(const float* dwn, const float* w, const float* u, const float* v, const float* sigma,
@@ -112,11 +122,15 @@ extern "C" int lb_sn_weight_grad(const float* dwn, const float* w, const float* 
   LB_REQUIRE(dwn && w && u && v && sigma && grad && work && height > 0 && width > 0 && packed_taps >= 0);
   LB_REQUIRE(packed_taps == 0 || width % packed_taps == 0);
   const size_t n = (size_t)height * width;
+  LB_REQUIRE(n < ((size_t)1 << 31) - ((size_t)1 << 24));
   cudaError_t e = cudaMemsetAsync(work, 0, sizeof(double) * 2, lb_s(s));
   if (e != cudaSuccess) return (int)e;
-  k_sn_dot<<<lb_grid_1d(n, 256, 2), 256, 0, lb_s(s)>>>(dwn, w, n, width, height, packed_taps, work);
+  SnIdx x;
+  x.width = width; x.height = height; x.taps = packed_taps; x.d1 = packed_taps ? width / packed_taps : width;
+  x.d_width = lb_make_fastdiv(width); x.d_taps = lb_make_fastdiv(packed_taps ? packed_taps : 1);
+  k_sn_dot<<<lb_grid_1d(n, 256, 2), 256, 0, lb_s(s)>>>(dwn, w, (int)n, x, work);
   LB_LAUNCH_CHECK();
-  k_sn_wgrad<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(dwn, u, v, sigma, work, grad, n, width, height, packed_taps);
+  k_sn_wgrad<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(dwn, u, v, sigma, work, grad, (int)n, x);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }

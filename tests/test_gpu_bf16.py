@@ -72,15 +72,18 @@ def test_tc_path_is_taken():
     assert "conv_tc" in fams and "wgrad_tc" in fams and "conv_gemm" not in fams, fams
 
 
-def test_step_bf16_vs_oracle_default_width():
-    L.configure(IMAGE_SIZE=32)
-    cfg = O.OracleConfig(IMAGE_SIZE=32)
+@pytest.mark.parametrize("size,batch", [(32, 8), (64, 3), (128, 2)])
+def test_step_bf16_vs_oracle_default_width(size, batch):
+    """One full G+D step (both backward passes, penalty) at the reference's default widths: 32x32 (BASELINE config 0),
+    64x64 (config 1) and the headline 128x128 (config 2) against the fp64 oracle on the same weights and inputs."""
+    L.configure(IMAGE_SIZE=size)
+    cfg = O.OracleConfig(IMAGE_SIZE=size)
     torch.manual_seed(999)
     gen, g_opt = L.get_model(L.Generator(), L.CFG.GLR, DEV)
     dis, d_opt = L.get_model(L.Discriminator(), L.CFG.DLR, DEV)
     gs = O.load_state({k: v.cpu().double() for k, v in gen.state_dict().items()})
     ds = O.load_state({k: v.cpu().double() for k, v in dis.state_dict().items()})
-    real, aug, z = O.synthetic_batch(cfg, 8, dtype=torch.float64)
+    real, aug, z = O.synthetic_batch(cfg, batch, dtype=torch.float64)
     grads = {}
 
     class Spy(O.Nadam):
@@ -103,9 +106,13 @@ def test_step_bf16_vs_oracle_default_width():
         a = torch.cat([mine[tag][k].double().cpu().reshape(-1) for k in keys])
         b = torch.cat([grads[tag][k].reshape(-1) for k in keys])
         total = ((a - b).norm() / b.norm()).item()
-        assert total < 1.5e-2, f"{tag}: relative gradient-norm error {total:.3e}"
+        # yard-stick: the UNMODIFIED reference under torch.autocast(bfloat16) against itself in fp64 on the same sizes
+        # (tests/golden/autocast_yardstick.py -> autocast_yardstick.txt): D/G 1.16e-2/1.12e-2 at 32, 2.03e-2/2.68e-2 at 64,
+        # 2.34e-2/2.76e-2 at 128.  This path must not be worse than the reference's own bf16 mode.
+        limit = {32: 1.5e-2, 64: 2.0e-2, 128: 2.3e-2}[size]
+        assert total < limit, f"{tag}: relative gradient-norm error {total:.3e} (limit {limit})"
         worst = max((rel_l2(mine[tag][k], grads[tag][k]), k) for k in keys if grads[tag][k].norm() > 1e-6 * b.norm())
-        assert worst[0] < 5e-2, worst
+        assert worst[0] < (5e-2 if size == 32 else 8e-2), worst
 
 
 @pytest.mark.parametrize("args,shape", [
@@ -203,3 +210,40 @@ def test_cuda_graph_replay_matches_eager():
         return ((a - b).abs() > 5e-3).float().mean().item()
     noise, diff = moved(e[2], e2[2]), moved(e[2], g[2])
     assert diff <= max(1e-2, 3.0 * noise), f"graph vs eager {diff:.4f}, eager vs eager {noise:.4f}"
+
+
+# ---- BASELINE config 4: isolated self-attention fwd/bwd sweep over HW x channels -------------------------------
+@pytest.mark.parametrize("hw,feat,batch", [(16, 64, 4), (32, 128, 3), (64, 256, 2), (16, 512, 3), (128, 64, 1), (64, 96, 2)])
+@pytest.mark.parametrize("wrapped", [False, True])
+def test_self_attention_sweep_vs_oracle(hw, feat, batch, wrapped):
+    """SelfAttention(F) (attention.py:40-54), bare and as the reference uses it, ResModule(identity, Norm(F, SelfAttention(F)))
+    (block.py:42-43): output, input gradient and weight gradients against the fp64 oracle."""
+    torch.manual_seed(5)
+    sa = layers.SelfAttention(feat)
+    m = layers.ResModule(layers.identity, layers.Norm(feat, sa)) if wrapped else sa
+    if wrapped:
+        with torch.no_grad():
+            m.layer_module.i_norm.weight.uniform_(0.5, 1.5)
+            m.layer_module.i_norm.bias.uniform_(-0.2, 0.2)
+    st = O.load_state({k: v.double().clone() for k, v in m.state_dict().items()})
+    gen = torch.Generator().manual_seed(6)
+    x = torch.randn((batch, feat, hw, hw), generator=gen)
+    xo = x.double().requires_grad_(True)
+    if wrapped:
+        h = O.whole_tensor_norm(xo, st["layer_module.i_norm.weight"], st["layer_module.i_norm.bias"])
+        h = O.self_attention(st, "layer_module.module.", h, 4)
+        yo = O.gate(xo, h, st["gamma"], True)
+    else:
+        yo = O.self_attention(st, "", xo, 4)
+    g = torch.randn(yo.shape, generator=gen)
+    yo.backward(g.double())
+    m = m.to(DEV)
+    xd = x.to(DEV).requires_grad_(True)
+    yd = m(xd)
+    yd.backward(g.to(DEV))
+    torch.cuda.synchronize()
+    assert rel_l2(yd, yo) < 1e-2
+    assert rel_l2(xd.grad, xo.grad) < 2e-2
+    for k, p in m.named_parameters():
+        if p.requires_grad and st[k].grad is not None and st[k].grad.norm() > 0:
+            assert rel_l2(p.grad, st[k].grad) < 3e-2, k
