@@ -144,7 +144,9 @@ int lb_conv_wgrad(const float* gathered, const float* dense, float* dw, const lb
  * weight addressing are those of lb_conv_gemm / lb_conv_wgrad; growth_gathered applies RootTanh to the gathered operand. */
 int lb_conv_small_supported(const lb_conv_geom* g);
 int lb_conv_small(const float* in, const float* w, const float* alpha, const float* bias, float* out, const lb_conv_geom* g,
-                  int growth_in, const float* xpre, int ld_xpre, int growth_out, lb_stream_t stream);
+                  int growth_in, const float* xpre, int ld_xpre, int growth_out, int cat_input, lb_stream_t stream);
+/* cat_input != 0 (1x1 stride-1 layers, no fused activation): `out` is the START of rows [in_c copied | out_c conv] with
+ * row stride g->ld_out -- CatModule's concat (merge.py:10-16) written in the same pass. */
 int lb_conv_small_wgrad_supported(const lb_conv_geom* g);
 int lb_conv_small_wgrad(const float* gathered, const float* dense, float* dw, const lb_conv_geom* g, int growth_gathered,
                         lb_stream_t stream);

@@ -50,7 +50,7 @@ _SIGNATURES = {
     "lb_conv_gemm": ([P, P, P, P, P, POINTER(ConvGeom), P], c_int),
     "lb_conv_wgrad": ([P, P, P, POINTER(ConvGeom), P], c_int),
     "lb_conv_small_supported": ([POINTER(ConvGeom)], c_int),
-    "lb_conv_small": ([P, P, P, P, P, POINTER(ConvGeom), c_int, P, c_int, c_int, P], c_int),
+    "lb_conv_small": ([P, P, P, P, P, POINTER(ConvGeom), c_int, P, c_int, c_int, c_int, P], c_int),
     "lb_conv_small_wgrad_supported": ([POINTER(ConvGeom)], c_int),
     "lb_conv_small_wgrad": ([P, P, P, POINTER(ConvGeom), c_int, P], c_int),
     "lb_conv_tc_supported": ([POINTER(ConvGeom)], c_int),

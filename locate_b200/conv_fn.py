@@ -149,7 +149,7 @@ class SNConvFn(torch.autograd.Function):
 
         # tensor-core operands are bf16 rows padded to 16 bytes (TMA stride rule); channel counts are arbitrary
         cin_p, cout_p = (cin + 7) // 8 * 8, (spec.cout + 7) // 8 * 8
-        tc = False
+        tc = fused_cat = False
         g32 = geoms(cin, spec.cout)
         # tiny channel count on one side (D stem, G's last 1x1): direct fp32 kernels, activation fused
         small = CFG.SMALL_KERNELS and lib.lb_conv_small_supported(ctypes.byref(g32[0])) == 1
@@ -180,9 +180,17 @@ class SNConvFn(torch.autograd.Function):
             _timed_call("conv_tc", fl, by / 2, "lb_conv_tc_gemm", ptr(a), ptr(pk), sigma.data_ptr() + 4, ptr(bias),
                         out.data_ptr() + off, g_fwd)
         elif small:
-            a = x                                 # RootTanh is applied on load; nothing is materialised
-            _timed_call("conv_small", fl, by, "lb_conv_small", ptr(x), ptr(w_bar), sigma.data_ptr() + 4, ptr(bias),
-                        out.data_ptr() + off, g_fwd, CFG.ROOTTANH_GROWTH if pre_act else 0, None, 0, 0)
+            pointwise = spec.taps == 1 and spec.stride == 1 and spec.pad == 0
+            small_growth = CFG.ROOTTANH_GROWTH if pre_act else 0
+            if pre_act and not pointwise:         # every input pixel feeds up to 25 taps: activate it once, not per tap
+                a = torch.empty_like(x)
+                call("lb_roottanh_fwd", ptr(x), ptr(a), n, CFG.ROOTTANH_GROWTH)
+                small_growth = 0
+            else:
+                a = x                             # RootTanh is applied on load; nothing is materialised
+            fused_cat = bool(cat_input and spec.taps == 1 and spec.stride == 1 and spec.pad == 0)
+            _timed_call("conv_small", fl, by, "lb_conv_small", ptr(a), ptr(w_bar), sigma.data_ptr() + 4, ptr(bias),
+                        out.data_ptr() + (0 if fused_cat else off), g_fwd, small_growth, None, 0, 0, 1 if fused_cat else 0)
         else:
             if pre_act:
                 a = torch.empty_like(x)
@@ -191,13 +199,13 @@ class SNConvFn(torch.autograd.Function):
                 a = x
             _timed_call("conv_gemm", fl, by, "lb_conv_gemm", ptr(a), ptr(w_bar), sigma.data_ptr() + 4, ptr(bias),
                         out.data_ptr() + off, g_fwd)
-        if cat_input:
+        if cat_input and not fused_cat:
             call("lb_copy_rows", ptr(x), cin, ptr(out), ctot, b * h * w_, cin, 0)
         ctx.save_for_backward(x if pre_act else None, a, w_bar, sigma)
         ctx.u, ctx.v = u, v                      # LIVE u/v: the reference's backward reads them at backward time
         ctx.bias_param, ctx.w_param = bias, w_bar
         ctx.meta = (spec, cat_input, pre_act, tc, (b, h, w_, cin, oh, ow, ctot), g_dgrad, g_wgrad, (fl, by))
-        ctx.raw_a = bool(small and pre_act)      # `a` is the pre-activation: backward applies RootTanh where it needs it
+        ctx.raw_a = bool(small and pre_act and a is x)   # `a` is the pre-activation: backward applies RootTanh where it needs it
         return out
 
     @staticmethod
@@ -239,7 +247,7 @@ class SNConvFn(torch.autograd.Function):
                 dx = torch.empty_like(a)
                 if CFG.SMALL_KERNELS and lib.lb_conv_small_supported(ctypes.byref(g_dgrad)) == 1:
                     _timed_call("conv_small", fl, by, "lb_conv_small", gy_ptr, ptr(w_bar), sigma.data_ptr() + 4, None, ptr(dx),
-                                g_dgrad, 0, ptr(x) if pre_act else None, cin, growth if pre_act else 0)
+                                g_dgrad, 0, ptr(x) if pre_act else None, cin, growth if pre_act else 0, 0)
                     dact_done = True
                 else:
                     _timed_call("conv_gemm", fl, by, "lb_conv_gemm", gy_ptr, ptr(w_bar), sigma.data_ptr() + 4, None, ptr(dx), g_dgrad)

@@ -37,12 +37,18 @@ static inline LbFastDiv lb_make_fastdiv(uint32_t d) {
   f.mul = (uint32_t)((((uint64_t)1 << 32) * (((uint64_t)1 << f.shr) - d)) / d + 1);
   return f;
 }
+__device__ __forceinline__ LbFastDiv lb_dev_fastdiv(uint32_t d) {    // same constants, computed once per loop on the device
+  LbFastDiv f; f.d = d;
+  f.shr = d > 1 ? 32 - __clz(d - 1) : 0;
+  f.mul = (uint32_t)(((((unsigned long long)1 << f.shr) - d) << 32) / d + 1);
+  return f;
+}
 __device__ __forceinline__ void lb_fast_divmod(const LbFastDiv& f, int n, int& q, int& r) {
   q = (int)((__umulhi((uint32_t)n, f.mul) + (uint32_t)n) >> f.shr);
   r = n - q * (int)f.d;
 }
 
-static inline bool lb_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+__host__ __device__ static inline bool lb_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 template <typename T>
 __device__ __forceinline__ T lb_warp_sum(T v) {

@@ -30,14 +30,14 @@ for name, h, cin, cout, k, s, p, extra, gin, dact in FWD:
     x = torch.randn((b, h, h, cin), device=DEV)
     out = torch.empty((b, oh, oh, cout + extra), device=DEV)
     g = geom(b, h, h, cin, oh, oh, cout, k, k, s, p, 0, cin, cout + extra, (t, cin * t, k, 1))
-    ms = timeit(lambda: call("lb_conv_small", ptr(x), ptr(wt), None, None, out.data_ptr() + 4 * extra, g, gin, None, 0, 0))
+    ms = timeit(lambda: call("lb_conv_small", ptr(x), ptr(wt), None, None, out.data_ptr() + 4 * extra, g, gin, None, 0, 0, 0))
     gb = (x.numel() + b * oh * oh * cout) * 4 / 1e9
     print(f"fwd   {name:16s} {ms*1e3:8.1f} us  {gb/ms*1e3:7.0f} GB/s", flush=True)
     # input gradient (mode 1) with RootTanh' of the input fused
     dy = torch.randn((b, oh, oh, cout), device=DEV)
     dx = torch.empty((b, h, h, cin), device=DEV)
     gd = geom(b, oh, oh, cout, h, h, cin, k, k, s, p, 1, cout, cin, (cin * t, t, k, 1))
-    ms = timeit(lambda: call("lb_conv_small", ptr(dy), ptr(wt), None, None, ptr(dx), gd, 0, ptr(x), cin, 4))
+    ms = timeit(lambda: call("lb_conv_small", ptr(dy), ptr(wt), None, None, ptr(dx), gd, 0, ptr(x), cin, 4, 0))
     gb = (2 * x.numel() + dy.numel()) * 4 / 1e9
     print(f"dgrad {name:16s} {ms*1e3:8.1f} us  {gb/ms*1e3:7.0f} GB/s", flush=True)
     gw = geom(b, h, h, cin, oh, oh, cout, k, k, s, p, 0, cin, cout, (t, cin * t, k, 1))

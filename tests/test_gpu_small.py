@@ -83,7 +83,7 @@ def test_small_matches_simt(name, fuse):
         xpre = 2.0 * torch.randn(out_shape[:3] + (n,), generator=gen).to(DEV)
         ref[..., :n] *= roottanh_grad(xpre)
     call("lb_conv_small", ptr(src), ptr(wt), ptr(alpha), ptr(bias), ptr(got), ctypes.byref(g), 4 if fuse == "act_in" else 0,
-         ptr(xpre), n, 4 if fuse == "dact_out" else 0)
+         ptr(xpre), n, 4 if fuse == "dact_out" else 0, 0)
     torch.cuda.synchronize()
     assert torch.equal(got[..., n:], ref[..., n:]), "wrote outside its channel slice"
     err = (got - ref).abs().max().item()
@@ -132,3 +132,24 @@ def test_small_wgrad_matches_simt(name, act):
     err = (got - ref).abs().max().item()
     scale = ref.abs().max().item()
     assert err <= 2e-4 * scale + 1e-5, f"{name}: max err {err:.3e} vs scale {scale:.3e}"
+
+
+@pytest.mark.parametrize("b,h,w,cin,cout", [(3, 16, 16, 3, 29), (5, 9, 7, 3, 29), (2, 16, 16, 4, 12)])
+def test_small_fused_cat(b, h, w, cin, cout):
+    """CatModule(identity, conv 1x1) (merge.py:10-16, scale.py:31-34): rows [x | conv(x)] written in one pass."""
+    gen = torch.Generator().manual_seed(11)
+    wt = torch.randn((cout, cin, 1, 1), generator=gen).to(DEV)
+    x = torch.randn((b, h, w, cin), generator=gen).to(DEV)
+    bias = torch.randn(cout, generator=gen).to(DEV)
+    alpha = torch.tensor([0.6], device=DEV)
+    ctot = cin + cout
+    g = geom(b, h, w, cin, h, w, cout, 1, 1, 1, 0, 0, cin, ctot, (1, cin, 1, 1))
+    ref = torch.full((b, h, w, ctot), -7.0, device=DEV)
+    got = torch.full((b, h, w, ctot), -7.0, device=DEV)
+    call("lb_conv_gemm", ptr(x), ptr(wt), ptr(alpha), ptr(bias), ref.data_ptr() + 4 * cin, ctypes.byref(g))
+    ref[..., :cin] = x
+    call("lb_conv_small", ptr(x), ptr(wt), ptr(alpha), ptr(bias), ptr(got), ctypes.byref(g), 0, None, 0, 0, 1)
+    torch.cuda.synchronize()
+    assert torch.equal(got[..., :cin], x)
+    err = (got - ref).abs().max().item()
+    assert err <= 1e-4 * ref.abs().max().item() + 1e-5
