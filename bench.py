@@ -236,19 +236,35 @@ def run_cuda(args):
     if fam:
         k = ksum[fam]
         per_launch_ms = k["ms"] / k["launches"]
-        achieved = k["flops"] / (k["ms"] * 1e-3) / 1e12
+        tflops = k["flops"] / (k["ms"] * 1e-3) / 1e12
+        gbs = k["bytes"] / (k["ms"] * 1e-3) / 1e9
+        # a kernel family that mixes tensor-bound (C >= 192 transposed convs) and HBM-bound launches
+        # (1x1 / C <= 96) is judged against whichever roof it sits closer to; both views are reported.
+        frac_tc, frac_hbm = tflops / peaks["tflops"], gbs / peaks["hbm_gbs"]
+        tensor_bound = frac_tc >= frac_hbm
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as fh:
                 traffic = json.load(fh).get(fam)
-        roofline = {"kernel": {"conv_gemm": "k_conv_gemm (fp32 SIMT fwd+dgrad gather-GEMM)", "conv_wgrad": "k_conv_wgrad (fp32 SIMT)",
-                               "conv_tc": "k_conv_tc (tcgen05 implicit GEMM fwd+dgrad)", "wgrad_tc": "k_wgrad_tc (tcgen05 wgrad)"}.get(fam, fam),
-                    "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                    "frac": achieved / peaks["tflops"], "traffic": traffic, "peak_source": peaks["source"],
+        names = {"conv_gemm": "k_conv_gemm (fp32 SIMT fwd+dgrad gather-GEMM)", "conv_wgrad": "k_conv_wgrad (fp32 SIMT)",
+                 "conv_tc": "k_conv_tc2 + k_conv_tc (tcgen05 implicit GEMM fwd+dgrad, persistent / split-K)",
+                 "wgrad_tc": "k_wgrad_tc (tcgen05 wgrad)", "conv_small": "k_conv_small (direct fp32, tiny channel counts)",
+                 "conv_small_wgrad": "k_conv_small_wgrad"}
+        roofline = {"kernel": names.get(fam, fam),
+                    "bound": "tensor" if tensor_bound else "hbm",
+                    "achieved": tflops if tensor_bound else gbs,
+                    "peak": peaks["tflops"] if tensor_bound else peaks["hbm_gbs"],
+                    "unit": "TFLOP/s" if tensor_bound else "GB/s",
+                    "frac": frac_tc if tensor_bound else frac_hbm,
+                    "traffic": traffic, "peak_source": peaks["source"],
+                    "tensor_view": {"achieved": tflops, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": frac_tc},
+                    "hbm_view": {"achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": frac_hbm,
+                                 "algorithmic_bytes_per_step": k["bytes"] / args.steps},
                     "launches_per_step": k["launches"] / args.steps, "avg_launch_ms": per_launch_ms,
                     "share_of_step": k["ms"] / (ms_total if world == 1 else e0.elapsed_time(e1)),
                     "families": {n: {"ms_per_step": v["ms"] / args.steps, "tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12,
+                                     "gbs": v["bytes"] / (v["ms"] * 1e-3) / 1e9,
                                      "launches_per_step": v["launches"] / args.steps} for n, v in ksum.items()}}
     line = {
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

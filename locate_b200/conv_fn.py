@@ -152,7 +152,8 @@ class SNConvFn(torch.autograd.Function):
         tc = fused_cat = False
         g32 = geoms(cin, spec.cout)
         # tiny channel count on one side (D stem, G's last 1x1): direct fp32 kernels, activation fused
-        small = CFG.SMALL_KERNELS and lib.lb_conv_small_supported(ctypes.byref(g32[0])) == 1
+        # (a wide -> 3 layer such as G's last 1x1 is TMA-friendly on its input side and measured faster on the tensor cores)
+        small = CFG.SMALL_KERNELS and cin <= 4 and lib.lb_conv_small_supported(ctypes.byref(g32[0])) == 1
         if CFG.PRECISION == "bf16" and not small:
             g_fwd, g_dgrad, g_wgrad = geoms(cin_p, cout_p)
             tc = (lib.lb_conv_tc_supported(ctypes.byref(g_fwd)) == 1 and lib.lb_conv_tc_supported(ctypes.byref(g_dgrad)) == 1
@@ -177,7 +178,7 @@ class SNConvFn(torch.autograd.Function):
                 a = torch.empty((n // cin, cin_p), dtype=torch.bfloat16, device=x.device)
                 call("lb_cast_bf16_rows", ptr(x), cin, ptr(a), cin_p, n // cin, cin, growth)
             pk = _packed_weight(w_bar, g_fwd, "fwd")
-            _timed_call("conv_tc", fl, by / 2, "lb_conv_tc_gemm", ptr(a), ptr(pk), sigma.data_ptr() + 4, ptr(bias),
+            _timed_call("conv_tc", fl, _tc_bytes(g_fwd), "lb_conv_tc_gemm", ptr(a), ptr(pk), sigma.data_ptr() + 4, ptr(bias),
                         out.data_ptr() + off, g_fwd)
         elif small:
             pointwise = spec.taps == 1 and spec.stride == 1 and spec.pad == 0
@@ -188,7 +189,7 @@ class SNConvFn(torch.autograd.Function):
                 small_growth = 0
             else:
                 a = x                             # RootTanh is applied on load; nothing is materialised
-            fused_cat = bool(cat_input and spec.taps == 1 and spec.stride == 1 and spec.pad == 0)
+            fused_cat = bool(cat_input and pointwise and cin <= 8)     # the D stem's [x | conv(x)] row in one pass
             _timed_call("conv_small", fl, by, "lb_conv_small", ptr(a), ptr(w_bar), sigma.data_ptr() + 4, ptr(bias),
                         out.data_ptr() + (0 if fused_cat else off), g_fwd, small_growth, None, 0, 0, 1 if fused_cat else 0)
         else:
@@ -227,7 +228,7 @@ class SNConvFn(torch.autograd.Function):
             if need_dx:
                 dx = _new_act((b, cin) if gout.dim() == 2 else (b, cin, h, w_), gout)
                 pk = _packed_weight(w_bar, g_dgrad, "dgrad")
-                _timed_call("conv_tc", fl, by / 2, "lb_conv_tc_gemm", ptr(gy), ptr(pk), sigma.data_ptr() + 4, None, ptr(dx), g_dgrad)
+                _timed_call("conv_tc", fl, _tc_bytes(g_dgrad), "lb_conv_tc_gemm", ptr(gy), ptr(pk), sigma.data_ptr() + 4, None, ptr(dx), g_dgrad)
             if need_dw:
                 dwp = torch.zeros(w_bar.numel(), dtype=torch.float32, device=gout.device)
                 if spec.kind == "convT":
@@ -245,7 +246,7 @@ class SNConvFn(torch.autograd.Function):
             g_dgrad.ld_in = ctot
             if need_dx:
                 dx = torch.empty_like(a)
-                if CFG.SMALL_KERNELS and lib.lb_conv_small_supported(ctypes.byref(g_dgrad)) == 1:
+                if CFG.SMALL_KERNELS and cin <= 4 and lib.lb_conv_small_supported(ctypes.byref(g_dgrad)) == 1:
                     _timed_call("conv_small", fl, by, "lb_conv_small", gy_ptr, ptr(w_bar), sigma.data_ptr() + 4, None, ptr(dx),
                                 g_dgrad, 0, ptr(x) if pre_act else None, cin, growth if pre_act else 0, 0)
                     dact_done = True
@@ -257,7 +258,7 @@ class SNConvFn(torch.autograd.Function):
                     g_wgrad.ld_in = ctot
                 else:
                     g_wgrad.ld_out = ctot
-                small_w = CFG.SMALL_KERNELS and lib.lb_conv_small_wgrad_supported(ctypes.byref(g_wgrad)) == 1
+                small_w = CFG.SMALL_KERNELS and cin <= 4 and lib.lb_conv_small_wgrad_supported(ctypes.byref(g_wgrad)) == 1
                 fuse_act = ctx.raw_a and small_w and spec.kind != "convT"     # RootTanh on the gathered operand's load
                 if ctx.raw_a and not fuse_act:
                     act = torch.empty_like(a)
@@ -282,6 +283,15 @@ class SNConvFn(torch.autograd.Function):
             dbias, dbias_ret = _grad_sink(ctx.bias_param)
             call("lb_colsum", gout.data_ptr() + off, rows, spec.cout, ctot, ptr(dbias))
         return dx, dw_ret, None, None, dbias_ret, None, None, None, None
+
+
+def _tc_bytes(g, out32=True, out16=False, aux=False):
+    """Algorithmic bytes of one tensor-core GEMM launch: bf16 input + bf16 packed weight + the outputs it writes
+    (fp32 and/or bf16) + the fp32 pre-activation it reads for a fused RootTanh'."""
+    rows_in = g.batch * g.in_h * g.in_w
+    rows_out = g.batch * g.out_h * g.out_w
+    return (2.0 * rows_in * g.in_c + 2.0 * g.kh * g.kw * g.in_c * g.out_c
+            + rows_out * g.out_c * ((4.0 if out32 else 0.0) + (2.0 if out16 else 0.0) + (4.0 if aux else 0.0)))
 
 
 def _ex_ok(g, ld16, ld_aux):
@@ -330,11 +340,13 @@ class ActivatedPairFn(torch.autograd.Function):
         a0 = _bf16_like(y0)
         fl0, by0 = _conv_work(spec0, b, h, w_, oh, ow)
         fl1, by1 = _conv_work(spec1, b, oh, ow, oh, ow)
-        _timed_call("conv_tc", fl0, by0 / 2, "lb_conv_tc_gemm_ex", ptr(act16), ptr(_packed_weight(w0, gf0, "fwd")),
+        _timed_call("conv_tc", fl0, _tc_bytes(gf0, True, True), "lb_conv_tc_gemm_ex", ptr(act16), ptr(_packed_weight(w0, gf0, "fwd")),
                     sigma0.data_ptr() + 4, None, ptr(y0), ptr(a0), mid, 1, None, 0, gf0)
         y1 = _new_act((b, cout, oh, ow), x)
-        _timed_call("conv_tc", fl1, by1 / 2, "lb_conv_tc_gemm_ex", ptr(a0), ptr(_packed_weight(w1, gf1, "fwd")),
-                    sigma1.data_ptr() + 4, None, ptr(y1), None, 0, 0, None, 0, gf1)
+        # lb_conv_tc_gemm picks the persistent kernel itself and keeps direct stores for rows that TMA cannot address
+        # (cout = 3: G's last layer)
+        _timed_call("conv_tc", fl1, _tc_bytes(gf1), "lb_conv_tc_gemm", ptr(a0), ptr(_packed_weight(w1, gf1, "fwd")),
+                    sigma1.data_ptr() + 4, None, ptr(y1), gf1)
         ctx.save_for_backward(x if pre_act0 else None, act16, y0, a0, w0, w1, sigma0, sigma1)
         ctx.uv = (u0, v0, u1, v1)                # LIVE u/v (see SNConvFn)
         ctx.meta = (spec0, spec1, geoms, (b, cin, h, w_, oh, ow, mid, cout), (fl0, by0, fl1, by1), pre_act0)
@@ -349,22 +361,27 @@ class ActivatedPairFn(torch.autograd.Function):
         gout = _as_act(gout)
         dev = gout.device
         need_dx, need_dw0, need_dw1 = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[4]
-        g1 = _bf16_like(gout)
-        call("lb_cast_bf16", ptr(gout), ptr(g1), gout.numel())
+        cout_p = (cout + 7) // 8 * 8               # bf16 rows are padded to 16 bytes for TMA
+        if cout_p == cout:
+            g1 = _bf16_like(gout)
+            call("lb_cast_bf16", ptr(gout), ptr(g1), gout.numel())
+        else:
+            g1 = torch.empty((b * oh * ow, cout_p), dtype=torch.bfloat16, device=dev)
+            call("lb_cast_bf16_rows", ptr(gout), cout, ptr(g1), cout_p, b * oh * ow, cout, 0)
         dx = dw0 = dw1 = None
         if need_dw1:
             ga, de = (g1, a0) if spec1.kind == "convT" else (a0, g1)
             dw1 = _sn_wgrad_tc(w1, u1, v1, sigma1, ga, de, gw1, spec1, fl1, by1, dev)
         if need_dx or need_dw0:
             d0 = _bf16_like(y0)                  # bf16( dL/dy0 ) = bf16( dgrad_1(g1) * RootTanh'(y0) )
-            _timed_call("conv_tc", fl1, by1 / 2, "lb_conv_tc_gemm_ex", ptr(g1), ptr(_packed_weight(w1, gd1, "dgrad")),
+            _timed_call("conv_tc", fl1, _tc_bytes(gd1, False, True, True), "lb_conv_tc_gemm_ex", ptr(g1), ptr(_packed_weight(w1, gd1, "dgrad")),
                         sigma1.data_ptr() + 4, None, None, ptr(d0), mid, 0, ptr(y0), mid, gd1)
             if need_dw0:
                 ga, de = (d0, act16) if spec0.kind == "convT" else (act16, d0)
                 dw0 = _sn_wgrad_tc(w0, u0, v0, sigma0, ga, de, gw0, spec0, fl0, by0, dev)
             if need_dx:
                 dx = _new_act((b, cin, h, w_), gout)
-                _timed_call("conv_tc", fl0, by0 / 2, "lb_conv_tc_gemm_ex", ptr(d0), ptr(_packed_weight(w0, gd0, "dgrad")),
+                _timed_call("conv_tc", fl0, _tc_bytes(gd0, True, False, pre_act0), "lb_conv_tc_gemm_ex", ptr(d0), ptr(_packed_weight(w0, gd0, "dgrad")),
                             sigma0.data_ptr() + 4, None, ptr(dx), None, 0, 0, ptr(x) if pre_act0 else None, cin if pre_act0 else 0, gd0)
         return (dx, dw0, None, None, dw1) + (None,) * 8
 
@@ -380,24 +397,27 @@ def activated_pair(x, sn0, sn1, pre_act0=True):
         return None
     b, cin, h, w_ = x.shape
     mid, cout = spec0.cout, spec1.cout
-    if cin % 8 or mid % 8 or cout % 8 or cin != spec0.cin or mid != spec1.cin:
+    if cin % 8 or mid % 8 or cin != spec0.cin or mid != spec1.cin:
         return None
+    cout_p = (cout + 7) // 8 * 8
     oh, ow = spec0.out_hw(h, w_)
     lib = _lib.lib()
 
-    def geoms(spec, ih, iw, ci, co, o_h, o_w):
+    def geoms(spec, ih, iw, ci, co, o_h, o_w, ld_co):
+        """ld_co: row stride of the bf16 gradient w.r.t. this conv's output (co padded to 8)."""
         mode = 1 if spec.kind == "convT" else 0
         t = spec.taps
         gf = _geom(b, ih, iw, ci, o_h, o_w, co, spec, mode, ci, co, spec.strides_fwd())
-        gd = _geom(b, o_h, o_w, co, ih, iw, ci, spec, 1 - mode, co, ci, spec.strides_dgrad())
+        gd = _geom(b, o_h, o_w, co, ih, iw, ci, spec, 1 - mode, ld_co, ci, spec.strides_dgrad())
         if spec.kind == "convT":
-            gw = _geom(b, o_h, o_w, co, ih, iw, ci, spec, 0, co, ci, (t, co * t, spec.kw, 1))
+            gw = _geom(b, o_h, o_w, co, ih, iw, ci, spec, 0, ld_co, ci, (t, co * t, spec.kw, 1))
         else:
-            gw = _geom(b, ih, iw, ci, o_h, o_w, co, spec, 0, ci, co, (t, ci * t, spec.kw, 1))
+            gw = _geom(b, ih, iw, ci, o_h, o_w, co, spec, 0, ci, ld_co, (t, ci * t, spec.kw, 1))
         return gf, gd, gw
 
-    g0, g1 = geoms(spec0, h, w_, cin, mid, oh, ow), geoms(spec1, oh, ow, mid, cout, oh, ow)
-    ok = (_ex_ok(g0[0], mid, 0) and _ex_ok(g1[0], 0, 0) and _ex_ok(g1[1], mid, mid) and _ex_ok(g0[1], 0, cin if pre_act0 else 0)
+    g0, g1 = geoms(spec0, h, w_, cin, mid, oh, ow, mid), geoms(spec1, oh, ow, mid, cout, oh, ow, cout_p)
+    ok = (_ex_ok(g0[0], mid, 0) and lib.lb_conv_tc_supported(ctypes.byref(g1[0])) == 1 and _ex_ok(g1[1], mid, mid)
+          and _ex_ok(g0[1], 0, cin if pre_act0 else 0)
           and lib.lb_wgrad_tc_supported(ctypes.byref(g0[2])) == 1 and lib.lb_wgrad_tc_supported(ctypes.byref(g1[2])) == 1)
     if not ok:
         return None
