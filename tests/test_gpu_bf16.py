@@ -72,12 +72,13 @@ def test_tc_path_is_taken():
     assert "conv_tc" in fams and "wgrad_tc" in fams and "conv_gemm" not in fams, fams
 
 
-@pytest.mark.parametrize("size,batch", [(32, 8), (64, 3), (128, 2)])
-def test_step_bf16_vs_oracle_default_width(size, batch):
+@pytest.mark.parametrize("size,batch,depth", [(32, 8, 1), (64, 3, 1), (128, 2, 1), (256, 1, 3)])
+def test_step_bf16_vs_oracle_default_width(size, batch, depth):
     """One full G+D step (both backward passes, penalty) at the reference's default widths: 32x32 (BASELINE config 0),
-    64x64 (config 1) and the headline 128x128 (config 2) against the fp64 oracle on the same weights and inputs."""
-    L.configure(IMAGE_SIZE=size)
-    cfg = O.OracleConfig(IMAGE_SIZE=size)
+    64x64 (config 1), the headline 128x128 (config 2) and 256x256 with DEPTH=3 bottleneck stacks (config 3: HW = 65 536
+    softmax rows) against the fp64 oracle on the same weights and inputs."""
+    L.configure(IMAGE_SIZE=size, DEPTH=depth)
+    cfg = O.OracleConfig(IMAGE_SIZE=size, DEPTH=depth)
     torch.manual_seed(999)
     gen, g_opt = L.get_model(L.Generator(), L.CFG.GLR, DEV)
     dis, d_opt = L.get_model(L.Discriminator(), L.CFG.DLR, DEV)
@@ -109,11 +110,15 @@ def test_step_bf16_vs_oracle_default_width(size, batch):
         # yard-stick: the UNMODIFIED reference under torch.autocast(bfloat16) against itself in fp64 on the same sizes
         # (tests/golden/autocast_yardstick.py -> autocast_yardstick.txt): D/G 1.16e-2/1.12e-2 at 32, 2.03e-2/2.68e-2 at 64,
         # 2.34e-2/2.76e-2 at 128.  This path must not be worse than the reference's own bf16 mode.
-        limit = {32: 1.5e-2, 64: 2.0e-2, 128: 2.3e-2}[size]
+        limit = {32: 1.5e-2, 64: 2.0e-2, 128: 2.3e-2, 256: 3.0e-2}[size]      # 256 / DEPTH=3: no yard-stick run (CPU hours); 128's + 30 %
         assert total < limit, f"{tag}: relative gradient-norm error {total:.3e} (limit {limit})"
-        worst = max((rel_l2(mine[tag][k], grads[tag][k]), k) for k in keys if grads[tag][k].norm() > 1e-6 * b.norm())
-        # single tensors; a scalar gate gain's gradient is one cancelling sum over millions of products, so it alone gets
-        # a wider band at the larger sizes
+        # single tensors.  A scalar gate gain's gradient is ONE cancelling sum (sum x^2 g): at 128 it gets a wider band, and
+        # at 256 (batch 1, gains deep in D see a 1x1 map of one sample) it is judged through the concatenated norm only.
+        def checked(k):
+            if grads[tag][k].norm() <= 1e-6 * b.norm():
+                return False
+            return not (size == 256 and grads[tag][k].numel() == 1)
+        worst = max((rel_l2(mine[tag][k], grads[tag][k]), k) for k in keys if checked(k))
         assert worst[0] < (5e-2 if size == 32 else 8e-2) or (worst[1].endswith("gamma") and worst[0] < 0.15), worst
 
 
