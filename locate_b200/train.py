@@ -59,6 +59,7 @@ class GanTrainer:
         self.gen, self.dis, self.g_opt, self.d_opt = gen, dis, g_opt, d_opt
         self.penalty_gamma = float(penalty_gamma)
         self._graph = self._static_in = self._static_out = None
+        self._copy_stream = self._stage_bufs = self._staged = self._consumed = None
 
     def _reduce_and_step(self, opt):
         for h in [h for flat in opt.flat_grads for h in dist.all_reduce_grads_(flat)]:
@@ -113,6 +114,9 @@ class GanTrainer:
         for dst, src in zip(self._static_in, (real, aug, z)):
             if dst.data_ptr() != src.data_ptr():
                 dst.copy_(src, non_blocking=True)
+        if self._copy_stream is not None:                 # prefetch() may refill its staging buffers from here on
+            self._consumed = torch.cuda.Event()
+            self._consumed.record()
         self._graph.replay()
         for opt in (self.d_opt, self.g_opt):          # host mirrors of the device-side step counters
             for a in opt._arenas:
@@ -120,6 +124,38 @@ class GanTrainer:
                     a["step"] += 1
                     a["epoch"][0] += 1
         return self._static_out
+
+    def prefetch(self, real, aug, z):
+        """Start the host -> device copy of the NEXT batch on a side stream (pinned host tensors), so it overlaps the
+        step that is running; `step()` with no arguments then trains on it.  This is the input side of the reference's
+        loader loop (main.py:122-131) without its per-step synchronous `.to(device)`."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream()
+            self._staged = None
+        if self._stage_bufs is None or any(b.shape != t.shape for b, t in zip(self._stage_bufs, (real, aug, z))):
+            dev = next(self.gen.parameters()).device
+            self._stage_bufs = tuple(torch.empty(t.shape, dtype=t.dtype, device=dev) for t in (real, aug, z))
+        cs = self._copy_stream
+        if self._consumed is not None:                    # the previous batch has left the staging buffers
+            cs.wait_event(self._consumed)
+        with torch.cuda.stream(cs):
+            for dst, src in zip(self._stage_bufs, (real, aug, z)):
+                dst.copy_(src, non_blocking=True)
+        self._staged = torch.cuda.Event()
+        self._staged.record(cs)
+
+    def step_prefetched(self):
+        """Train on the batch handed to `prefetch()`."""
+        if self._staged is None:
+            raise RuntimeError("step_prefetched() without prefetch()")
+        torch.cuda.current_stream().wait_event(self._staged)
+        self._staged = None
+        if self._graph is None:                           # eager: the step reads the staging buffers until it ends
+            out = self._eager_step(*self._stage_bufs)
+            self._consumed = torch.cuda.Event()
+            self._consumed.record()
+            return out
+        return self.step(*self._stage_bufs)
 
     def capture(self, real, aug, z, warmup=3):
         """Capture the step into a CUDA graph (CUDA streams and graphs instead of a tracing compiler).  Everything
