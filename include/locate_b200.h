@@ -88,6 +88,10 @@ int lb_norm_bwd_apply(const float* x, const float* g, const float* stats, const 
  *                or sum x*y*g otherwise.  gamma is a device scalar. */
 int lb_gate_fwd(const float* x, const float* y, const float* gamma, float* out, int batch, int pixels,
                 int channels, int y_bcast, lb_stream_t stream);
+/* same, also accumulating sums[2] (fp64, zeroed by the caller) += (sum out, sum out^2): the statistics of the whole-tensor
+ * norm that consumes every gate output (block.py:46-51), without re-reading it.  channels % 4 == 0, aligned pointers. */
+int lb_gate_fwd_stats(const float* x, const float* y, const float* gamma, float* out, double* sums, int batch, int pixels,
+                      int channels, int y_bcast, lb_stream_t stream);
 int lb_gate_bwd(const float* x, const float* y, const float* gamma, const float* g, float* dx, float* dy,
                 float* dgamma, int batch, int pixels, int channels, int y_bcast, int strict_reference,
                 lb_stream_t stream);

@@ -41,6 +41,7 @@ _SIGNATURES = {
     "lb_norm_bwd_finalize": ([P, P, P, c_int, P, c_int, c_int, P, P, P, P], c_int),
     "lb_norm_bwd_apply": ([P, P, P, P, c_int, P, P, c_int, c_int, c_int, P], c_int),
     "lb_gate_fwd": ([P, P, P, P, c_int, c_int, c_int, c_int, P], c_int),
+    "lb_gate_fwd_stats": ([P, P, P, P, P, c_int, c_int, c_int, c_int, P], c_int),
     "lb_gate_bwd": ([P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P], c_int),
     "lb_sn_power_iter": ([P, c_int, c_int, P, P, P, P, P], c_int),
     "lb_sn_power_iter_batched": ([P, c_int, P, c_int, P, c_int, P, c_size_t, P, P], c_int),

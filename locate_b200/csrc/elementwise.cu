@@ -160,6 +160,53 @@ extern "C" int lb_gate_fwd(const float* x, const float* y, const float* gamma, f
   return LB_OK;
 }
 
+// Same gate, also accumulating (sum, sum of squares) of the OUTPUT in fp64: every gate output feeds a whole-tensor norm
+// (block.py:46-51), whose statistics pass would otherwise re-read the tensor just written.
+__global__ void __launch_bounds__(256) k_gate_fwd_stats(const float* __restrict__ x, const float* __restrict__ y,
+                                                       const float* __restrict__ gamma, float* __restrict__ out, int n4,
+                                                       LbFastDiv d_pc4, LbFastDiv d_c4, int channels, int y_bcast,
+                                                       double* __restrict__ sums) {
+  __shared__ double scratch[32];
+  const float gm = __ldg(gamma);
+  const int stride = gridDim.x * blockDim.x;
+  double s1 = 0.0, s2 = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 a = lb_ld4(x + 4 * (size_t)i);
+    float4 b;
+    if (y_bcast) {
+      int bi, rem, q, c4;
+      lb_fast_divmod(d_pc4, i, bi, rem);
+      lb_fast_divmod(d_c4, rem, q, c4);
+      b = lb_ld4(y + (size_t)bi * channels + 4 * c4);
+    } else {
+      b = lb_ld4(y + 4 * (size_t)i);
+    }
+    float4 r;
+    r.x = fmaf(gm, b.x, 1.0f) * a.x; r.y = fmaf(gm, b.y, 1.0f) * a.y;
+    r.z = fmaf(gm, b.z, 1.0f) * a.z; r.w = fmaf(gm, b.w, 1.0f) * a.w;
+    lb_st4(out + 4 * (size_t)i, r);
+    s1 += (double)((r.x + r.y) + (r.z + r.w));
+    s2 += (double)(fmaf(r.x, r.x, r.y * r.y) + fmaf(r.z, r.z, r.w * r.w));
+  }
+  s1 = lb_block_sum(s1, scratch);
+  s2 = lb_block_sum(s2, scratch);
+  if (threadIdx.x == 0) { atomicAdd(sums, s1); atomicAdd(sums + 1, s2); }
+}
+// sums[2] (fp64, zeroed by the caller) += (sum out, sum out^2).  Needs channels % 4 == 0 and 16-byte aligned pointers
+// (LB_EALIGN otherwise: use lb_gate_fwd + lb_norm_stats).
+extern "C" int lb_gate_fwd_stats(const float* x, const float* y, const float* gamma, float* out, double* sums, int batch,
+                                 int pixels, int channels, int y_bcast, lb_stream_t s) {
+  LB_REQUIRE(x && y && gamma && out && sums && batch > 0 && pixels > 0 && channels > 0);
+  const size_t n = (size_t)batch * pixels * channels;
+  if ((channels & 3) || n / 4 >= ((size_t)1 << 31) - ((size_t)1 << 24) || !lb_aligned16(x) || !lb_aligned16(y) || !lb_aligned16(out))
+    return LB_EALIGN;
+  k_gate_fwd_stats<<<lb_grid_1d(n / 4, 256, 4), 256, 0, lb_s(s)>>>(x, y, gamma, out, (int)(n / 4),
+                                                                  lb_make_fastdiv((uint32_t)((size_t)pixels * channels / 4)),
+                                                                  lb_make_fastdiv(channels / 4), channels, y_bcast, sums);
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
+
 // backward: CTA handles batch b = blockIdx.y, pixel chunk blockIdx.x; thread (cl, pl).
 __global__ void k_gate_bwd(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ gamma,
                            const float* __restrict__ g, float* __restrict__ dx, float* __restrict__ dy,

@@ -187,7 +187,7 @@ extern "C" int lb_norm_bwd_reduce(const float* x, const float* g, const float* s
 // partials are read coalesced and in parallel (a single CTA looping over the batch is latency-bound).
 __global__ void __launch_bounds__(256) k_norm_bwd_finalize(const float* __restrict__ p1, const float* __restrict__ p2,
                                                           const float* __restrict__ gain, int gain_bs,
-                                                          const float* __restrict__ stats, int batch, int channels,
+                                                          const float* __restrict__ stats, int batch, int channels, int bchunk,
                                                           float* __restrict__ dgain, float* __restrict__ dbias,
                                                           double* __restrict__ sout) {
   __shared__ double scratch[32];
@@ -195,10 +195,11 @@ __global__ void __launch_bounds__(256) k_norm_bwd_finalize(const float* __restri
   const float rstd = stats[2];
   const int cl = threadIdx.x & 31, bl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
+  const int b0 = blockIdx.y * bchunk, b1 = min(batch, b0 + bchunk);
   double s1 = 0.0, s2 = 0.0;
   float db = 0.0f, dg_shared = 0.0f;
   if (c < channels) {
-    for (int b = bl; b < batch; b += 8) {
+    for (int b = b0 + bl; b < b1; b += 8) {
       const float a1 = p1[(size_t)b * channels + c], a2 = p2[(size_t)b * channels + c];
       const float gn = gain[(size_t)b * gain_bs + c];
       s1 += (double)gn * a1;
@@ -214,8 +215,8 @@ __global__ void __launch_bounds__(256) k_norm_bwd_finalize(const float* __restri
     float tb = 0.0f, tg = 0.0f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) { tb += s_db[i][cl]; tg += s_dg[i][cl]; }
-    if (dbias) dbias[c] += tb;
-    if (!gain_bs && dgain) dgain[c] += tg * rstd;
+    if (dbias) atomicAdd(dbias + c, tb);                     // batch chunks of one channel land on the same element
+    if (!gain_bs && dgain) atomicAdd(dgain + c, tg * rstd);
   }
   s1 = lb_block_sum(s1, scratch);
   s2 = lb_block_sum(s2, scratch);
@@ -228,8 +229,14 @@ extern "C" int lb_norm_bwd_finalize(const float* p1, const float* p2, const floa
   LB_REQUIRE(gain_batch_stride == 0 || (gain_batch_stride == channels && dgain));
   cudaError_t e = cudaMemsetAsync(sout, 0, 2 * sizeof(double), lb_s(s));
   if (e != cudaSuccess) return (int)e;
-  k_norm_bwd_finalize<<<(channels + 31) / 32, 256, 0, lb_s(s)>>>(p1, p2, gain, gain_batch_stride, stats, batch, channels, dgain,
-                                                               dbias, sout);
+  const int cblocks = (channels + 31) / 32;
+  int bchunks = (LB_SMS + cblocks - 1) / cblocks;            // ~one wave of CTAs
+  if (bchunks > (batch + 7) / 8) bchunks = (batch + 7) / 8;
+  if (bchunks < 1) bchunks = 1;
+  const int bchunk = (batch + bchunks - 1) / bchunks;
+  bchunks = (batch + bchunk - 1) / bchunk;
+  k_norm_bwd_finalize<<<dim3(cblocks, bchunks), 256, 0, lb_s(s)>>>(p1, p2, gain, gain_batch_stride, stats, batch, channels, bchunk,
+                                                                   dgain, dbias, sout);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
@@ -252,11 +259,44 @@ __global__ void __launch_bounds__(256) k_norm_bwd_apply(const float* __restrict_
     dx[i] = fmaf(gn * rstd, g[i], -k0) - k1 * (x[i] - mean);
   }
 }
+// one thread = 4 consecutive channels; index decode by multiply-shift (a 64-bit divide per element made the scalar
+// version instruction-bound at half the HBM rate)
+__global__ void __launch_bounds__(256) k_norm_bwd_apply4(const float* __restrict__ x, const float* __restrict__ g,
+                                                        const float* __restrict__ stats, const float* __restrict__ gain,
+                                                        int gain_bs, const double* __restrict__ sc, float* __restrict__ dx,
+                                                        int n4, LbFastDiv d_pc4, LbFastDiv d_c4) {
+  const float mean = __ldg(stats), rstd = __ldg(stats + 2);
+  const double nn = (double)__ldg(stats + 3);
+  const double r = (double)rstd;
+  const float k0 = (float)(sc[0] * r / nn);
+  const float k1 = (float)(sc[1] * r * r * r / (nn - 1.0));
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    int b, rem, q, c4;
+    lb_fast_divmod(d_pc4, i, b, rem);
+    lb_fast_divmod(d_c4, rem, q, c4);
+    const float4 gn = lb_ld4(gain + (size_t)b * gain_bs + 4 * c4);
+    const float4 gv = lb_ld4(g + 4 * (size_t)i), xv = lb_ld4(x + 4 * (size_t)i);
+    float4 o;
+    o.x = fmaf(gn.x * rstd, gv.x, -k0) - k1 * (xv.x - mean);
+    o.y = fmaf(gn.y * rstd, gv.y, -k0) - k1 * (xv.y - mean);
+    o.z = fmaf(gn.z * rstd, gv.z, -k0) - k1 * (xv.z - mean);
+    o.w = fmaf(gn.w * rstd, gv.w, -k0) - k1 * (xv.w - mean);
+    lb_st4(dx + 4 * (size_t)i, o);
+  }
+}
 extern "C" int lb_norm_bwd_apply(const float* x, const float* g, const float* stats, const float* gain, int gain_batch_stride,
                                  const double* sc, float* dx, int batch, int pixels, int channels, lb_stream_t s) {
   LB_REQUIRE(x && g && stats && gain && sc && dx && batch > 0 && pixels > 0 && channels > 0);
   const size_t n = (size_t)batch * pixels * channels;
-  k_norm_bwd_apply<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(x, g, stats, gain, gain_batch_stride, sc, dx, n, pixels * channels, channels);
+  if (!(channels & 3) && n / 4 < ((size_t)1 << 31) - ((size_t)1 << 24) && lb_aligned16(x) && lb_aligned16(g) && lb_aligned16(dx) &&
+      lb_aligned16(gain)) {
+    k_norm_bwd_apply4<<<lb_grid_1d(n / 4, 256), 256, 0, lb_s(s)>>>(x, g, stats, gain, gain_batch_stride, sc, dx, (int)(n / 4),
+                                                                  lb_make_fastdiv((uint32_t)((size_t)pixels * channels / 4)),
+                                                                  lb_make_fastdiv(channels / 4));
+  } else {
+    k_norm_bwd_apply<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(x, g, stats, gain, gain_batch_stride, sc, dx, n, pixels * channels, channels);
+  }
   LB_LAUNCH_CHECK();
   return LB_OK;
 }

@@ -223,8 +223,12 @@ class WholeNormFn(torch.autograd.Function):
         if gain.numel() != (b if per_sample else 1) * c or bias.numel() != c:
             raise ValueError(f"norm: gain {tuple(gain.shape)} / bias {tuple(bias.shape)} do not fit {tuple(x.shape)}")
         gain_c = gain.contiguous()
-        sums = torch.zeros(2, dtype=torch.float64, device=x.device)
-        call("lb_norm_stats", ptr(x), x.numel(), ptr(sums))
+        ready = getattr(x, "_lb_sums", None)
+        if ready is not None:
+            sums = ready.clone()                  # the producer (gate kernel) already reduced them; clone: all-reduced in place
+        else:
+            sums = torch.zeros(2, dtype=torch.float64, device=x.device)
+            call("lb_norm_stats", ptr(x), x.numel(), ptr(sums))
         n_total = float(x.numel()) * dist.all_reduce_sum_(sums)
         stats = torch.empty(4, dtype=torch.float32, device=x.device)
         call("lb_norm_finalize", ptr(sums), n_total, ptr(stats))
@@ -295,7 +299,13 @@ class GateFn(torch.autograd.Function):
         else:
             y = _match(y, x)
         out = torch.empty_like(x)
-        call("lb_gate_fwd", ptr(x), ptr(y), ptr(gamma), ptr(out), b, p, c, int(bcast))
+        if x.dim() == 4 and c % 4 == 0 and x.numel() < (1 << 32):
+            # every gate output is normalised next (block.py:46-51): leave its (sum, sum^2) for WholeNormFn
+            sums = torch.zeros(2, dtype=torch.float64, device=x.device)
+            call("lb_gate_fwd_stats", ptr(x), ptr(y), ptr(gamma), ptr(out), ptr(sums), b, p, c, int(bcast))
+            out._lb_sums = sums
+        else:
+            call("lb_gate_fwd", ptr(x), ptr(y), ptr(gamma), ptr(out), b, p, c, int(bcast))
         ctx.save_for_backward(x, y, gamma)
         ctx.bcast, ctx.strict, ctx.gamma_param = bcast, strict_reference, gamma
         return out
