@@ -7,7 +7,39 @@
 // The reference views the NCHW-CONTIGUOUS memory of x as [B, Cout, H, W, r] and averages the last
 // axis: out[b,o,h,w] = mean_k flat_b[o*r*HW + (h*W+w)*r + k].  flat index f <-> (channel f / HW,
 // pixel f % HW), which we evaluate against the channels-last storage.
-__global__ void k_featpool_fwd(const float* __restrict__ x, float* __restrict__ y, size_t n_out, int hw, int c_in, int c_out, int r) {
+// With m = HW / r (r divides HW on the reference's path): the r averaged elements of out[b,o,p] are channel
+// ci = o*r + p / m at the consecutive pixels (p % m)*r + k, and dx[b,p,c] = g[b, (c % r)*m + p / r, c / r] / r.
+// All index decoding is 32-bit multiply-shift division (the 64-bit divides of the first version made these gathers
+// instruction-bound at a quarter of the HBM rate).
+struct FeatPoolIdx { LbFastDiv d_c, d_hw, d_m, d_r; int hw, c_in, c_out, r, m; };
+__global__ void __launch_bounds__(256) k_featpool_fwd(const float* __restrict__ x, float* __restrict__ y, int n_out, const FeatPoolIdx q) {
+  const int stride = gridDim.x * blockDim.x;
+  const float inv = 1.0f / q.r;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += stride) {
+    int bp, o, b, p, pj, pm;
+    lb_fast_divmod(q.d_c, i, bp, o);              // d_c = c_out
+    lb_fast_divmod(q.d_hw, bp, b, p);
+    lb_fast_divmod(q.d_m, p, pj, pm);
+    const float* src = x + ((size_t)b * q.hw + (size_t)pm * q.r) * q.c_in + o * q.r + pj;
+    float acc = 0.0f;
+    for (int k = 0; k < q.r; ++k) acc += __ldg(src + (size_t)k * q.c_in);
+    y[i] = acc * inv;
+  }
+}
+__global__ void __launch_bounds__(256) k_featpool_bwd(const float* __restrict__ g, float* __restrict__ dx, int n_in, const FeatPoolIdx q) {
+  const int stride = gridDim.x * blockDim.x;
+  const float inv = 1.0f / q.r;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_in; i += stride) {
+    int bp, c, b, p, o, cr, pq, pr;
+    lb_fast_divmod(q.d_c, i, bp, c);              // d_c = c_in
+    lb_fast_divmod(q.d_hw, bp, b, p);
+    lb_fast_divmod(q.d_r, c, o, cr);
+    lb_fast_divmod(q.d_r, p, pq, pr);
+    dx[i] = __ldg(g + ((size_t)b * q.hw + (size_t)cr * q.m + pq) * q.c_out + o) * inv;
+  }
+}
+// generic fallbacks (r does not divide HW, or more than 2^31 items): 64-bit index arithmetic, any shape
+__global__ void k_featpool_fwd_generic(const float* __restrict__ x, float* __restrict__ y, size_t n_out, int hw, int c_in, int c_out, int r) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const float inv = 1.0f / r;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += stride) {
@@ -24,7 +56,7 @@ __global__ void k_featpool_fwd(const float* __restrict__ x, float* __restrict__ 
     y[i] = acc * inv;
   }
 }
-__global__ void k_featpool_bwd(const float* __restrict__ g, float* __restrict__ dx, size_t n_in, int hw, int c_in, int c_out, int r) {
+__global__ void k_featpool_bwd_generic(const float* __restrict__ g, float* __restrict__ dx, size_t n_in, int hw, int c_in, int c_out, int r) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const float inv = 1.0f / r;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_in; i += stride) {
@@ -38,17 +70,33 @@ __global__ void k_featpool_bwd(const float* __restrict__ g, float* __restrict__ 
     dx[i] = g[(b * hw + q) * c_out + o] * inv;
   }
 }
+static int featpool_idx(FeatPoolIdx* q, int batch, int h, int w, int c_in, int c_out, int c_fast, size_t n) {
+  const int hw = h * w, r = c_in / c_out;
+  if (hw % r != 0 || n >= ((size_t)1 << 31) - ((size_t)1 << 24)) return LB_EUNSUPPORTED;
+  q->hw = hw; q->c_in = c_in; q->c_out = c_out; q->r = r; q->m = hw / r;
+  q->d_c = lb_make_fastdiv(c_fast); q->d_hw = lb_make_fastdiv(hw); q->d_m = lb_make_fastdiv(q->m); q->d_r = lb_make_fastdiv(r);
+  (void)batch;
+  return LB_OK;
+}
 extern "C" int lb_featpool_fwd(const float* x, float* y, int batch, int h, int w, int c_in, int c_out, lb_stream_t s) {
   LB_REQUIRE(x && y && batch > 0 && h > 0 && w > 0 && c_out > 0 && c_in % c_out == 0);
   const size_t n = (size_t)batch * h * w * c_out;
-  k_featpool_fwd<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(x, y, n, h * w, c_in, c_out, c_in / c_out);
+  FeatPoolIdx q;
+  if (featpool_idx(&q, batch, h, w, c_in, c_out, c_out, n) == LB_OK)
+    k_featpool_fwd<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(x, y, (int)n, q);
+  else
+    k_featpool_fwd_generic<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(x, y, n, h * w, c_in, c_out, c_in / c_out);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
 extern "C" int lb_featpool_bwd(const float* g, float* dx, int batch, int h, int w, int c_in, int c_out, lb_stream_t s) {
   LB_REQUIRE(g && dx && batch > 0 && h > 0 && w > 0 && c_out > 0 && c_in % c_out == 0);
   const size_t n = (size_t)batch * h * w * c_in;
-  k_featpool_bwd<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(g, dx, n, h * w, c_in, c_out, c_in / c_out);
+  FeatPoolIdx q;
+  if (featpool_idx(&q, batch, h, w, c_in, c_out, c_in, n) == LB_OK)
+    k_featpool_bwd<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(g, dx, (int)n, q);
+  else
+    k_featpool_bwd_generic<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(g, dx, n, h * w, c_in, c_out, c_in / c_out);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
@@ -61,6 +109,19 @@ __device__ __forceinline__ void lb_up2_src(int d, int n, int& i0, int& i1, float
   i1 = min(i0 + 1, n - 1);
   lam = src - i0;
 }
+// item index -> (channel group, x, y, batch) by 32-bit multiply-shift division
+struct PixIdx { LbFastDiv d_c, d_w, d_h; };
+__device__ __forceinline__ void pix_decode(const PixIdx& q, int i, int& ch, int& x, int& y, int& b) {
+  int t;
+  lb_fast_divmod(q.d_c, i, t, ch);
+  lb_fast_divmod(q.d_w, t, t, x);
+  lb_fast_divmod(q.d_h, t, b, y);
+}
+static inline PixIdx make_pix_idx(int c, int w, int h) {
+  PixIdx q; q.d_c = lb_make_fastdiv(c); q.d_w = lb_make_fastdiv(w); q.d_h = lb_make_fastdiv(h);
+  return q;
+}
+#define LB_REQUIRE_INT_ITEMS(n) LB_REQUIRE((n) < ((size_t)1 << 31) - ((size_t)1 << 24))
 // V = 4: one thread = 4 consecutive channels (128-bit accesses, 4x fewer index computations); V = 1: any layout
 template <int V> struct VecT;
 template <> struct VecT<1> { typedef float type; };
@@ -80,22 +141,19 @@ __device__ __forceinline__ float vzero(float) { return 0.0f; }
 __device__ __forceinline__ float4 vzero(float4) { return make_float4(0.f, 0.f, 0.f, 0.f); }
 
 template <int V>
-__global__ void __launch_bounds__(256) k_up2_fwd(const float* __restrict__ xs, float* __restrict__ ys, size_t n_out, int h, int w, int c) {
+__global__ void __launch_bounds__(256) k_up2_fwd(const float* __restrict__ xs, float* __restrict__ ys, int n_out, int h, int w, int c,
+                                                 const PixIdx q) {
   typedef typename VecT<V>::type T;
   const T* __restrict__ x = reinterpret_cast<const T*>(xs);
   T* __restrict__ y = reinterpret_cast<T*>(ys);
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  const int ow = 2 * w, oh = 2 * h;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += stride) {
-    const int ch = (int)(i % c);
-    size_t t = i / c;
-    const int ox = (int)(t % ow); t /= ow;
-    const int oy = (int)(t % oh);
-    const size_t b = t / oh;
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += stride) {
+    int ch, ox, oy, b;
+    pix_decode(q, i, ch, ox, oy, b);              // q over (c, 2w, 2h)
     int y0, y1, x0, x1; float ly, lx;
     lb_up2_src(oy, h, y0, y1, ly);
     lb_up2_src(ox, w, x0, x1, lx);
-    const T* xb = x + b * h * w * c + ch;
+    const T* xb = x + (size_t)b * h * w * c + ch;
     y[i] = vmix(xb[((size_t)y0 * w + x0) * c], xb[((size_t)y0 * w + x1) * c], xb[((size_t)y1 * w + x0) * c],
                 xb[((size_t)y1 * w + x1) * c], (1.0f - ly) * (1.0f - lx), (1.0f - ly) * lx, ly * (1.0f - lx), ly * lx);
   }
@@ -106,28 +164,34 @@ __device__ __forceinline__ float lb_up2_weight(int d, int n, int m) {
   lb_up2_src(d, n, i0, i1, lam);
   return (i0 == m ? 1.0f - lam : 0.0f) + (i1 == m ? lam : 0.0f);
 }
+// 1-D transposed taps of the x2 bilinear kernel: source m receives from destinations 2m-1 .. 2m+2
 template <int V>
-__global__ void __launch_bounds__(256) k_up2_bwd(const float* __restrict__ gs, float* __restrict__ dxs, size_t n_in, int h, int w, int c) {
+__global__ void __launch_bounds__(256) k_up2_bwd(const float* __restrict__ gs, float* __restrict__ dxs, int n_in, int h, int w, int c,
+                                                 const PixIdx q) {
   typedef typename VecT<V>::type T;
   const T* __restrict__ g = reinterpret_cast<const T*>(gs);
   T* __restrict__ dx = reinterpret_cast<T*>(dxs);
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const int stride = gridDim.x * blockDim.x;
   const int ow = 2 * w, oh = 2 * h;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_in; i += stride) {
-    const int ch = (int)(i % c);
-    size_t t = i / c;
-    const int ix = (int)(t % w); t /= w;
-    const int iy = (int)(t % h);
-    const size_t b = t / h;
-    const T* gb = g + b * oh * ow * c + ch;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_in; i += stride) {
+    int ch, ix, iy, b;
+    pix_decode(q, i, ch, ix, iy, b);              // q over (c, w, h)
+    float wy[4], wx[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int dy = 2 * iy - 1 + t, dxp = 2 * ix - 1 + t;
+      wy[t] = (dy >= 0 && dy < oh) ? lb_up2_weight(dy, h, iy) : 0.0f;
+      wx[t] = (dxp >= 0 && dxp < ow) ? lb_up2_weight(dxp, w, ix) : 0.0f;
+    }
+    const T* gb = g + (size_t)b * oh * ow * c + ch;
     T acc = vzero(T());
-    for (int dy = max(0, 2 * iy - 2); dy <= min(oh - 1, 2 * iy + 2); ++dy) {
-      const float wy = lb_up2_weight(dy, h, iy);
-      if (wy == 0.0f) continue;
-      for (int dxp = max(0, 2 * ix - 2); dxp <= min(ow - 1, 2 * ix + 2); ++dxp) {
-        const float wx = lb_up2_weight(dxp, w, ix);
-        if (wx != 0.0f) vfma(acc, wy * wx, gb[((size_t)dy * ow + dxp) * c]);
-      }
+#pragma unroll
+    for (int ty = 0; ty < 4; ++ty) {
+      if (wy[ty] == 0.0f) continue;
+      const T* row = gb + (size_t)(2 * iy - 1 + ty) * ow * c;
+#pragma unroll
+      for (int tx = 0; tx < 4; ++tx)
+        if (wx[tx] != 0.0f) vfma(acc, wy[ty] * wx[tx], row[(size_t)(2 * ix - 1 + tx) * c]);
     }
     dx[i] = acc;
   }
@@ -135,78 +199,77 @@ __global__ void __launch_bounds__(256) k_up2_bwd(const float* __restrict__ gs, f
 extern "C" int lb_upsample2x_fwd(const float* x, float* y, int batch, int h, int w, int c, lb_stream_t s) {
   LB_REQUIRE(x && y && batch > 0 && h > 0 && w > 0 && c > 0);
   const size_t n = (size_t)batch * h * w * c * 4;
+  LB_REQUIRE_INT_ITEMS(n);
   if ((c & 3) == 0 && lb_aligned16(x) && lb_aligned16(y))
-    k_up2_fwd<4><<<lb_grid_1d(n / 4, 256), 256, 0, lb_s(s)>>>(x, y, n / 4, h, w, c / 4);
+    k_up2_fwd<4><<<lb_grid_1d(n / 4, 256), 256, 0, lb_s(s)>>>(x, y, (int)(n / 4), h, w, c / 4, make_pix_idx(c / 4, 2 * w, 2 * h));
   else
-    k_up2_fwd<1><<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(x, y, n, h, w, c);
+    k_up2_fwd<1><<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(x, y, (int)n, h, w, c, make_pix_idx(c, 2 * w, 2 * h));
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
 extern "C" int lb_upsample2x_bwd(const float* g, float* dx, int batch, int h, int w, int c, lb_stream_t s) {
   LB_REQUIRE(g && dx && batch > 0 && h > 0 && w > 0 && c > 0);
   const size_t n = (size_t)batch * h * w * c;
+  LB_REQUIRE_INT_ITEMS(n);
   if ((c & 3) == 0 && lb_aligned16(g) && lb_aligned16(dx))
-    k_up2_bwd<4><<<lb_grid_1d(n / 4, 256), 256, 0, lb_s(s)>>>(g, dx, n / 4, h, w, c / 4);
+    k_up2_bwd<4><<<lb_grid_1d(n / 4, 256), 256, 0, lb_s(s)>>>(g, dx, (int)(n / 4), h, w, c / 4, make_pix_idx(c / 4, w, h));
   else
-    k_up2_bwd<1><<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(g, dx, n, h, w, c);
+    k_up2_bwd<1><<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(g, dx, (int)n, h, w, c, make_pix_idx(c, w, h));
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
 
 // ---- AvgPool 2x2 / stride 2 (scale.py:40) ----------------------------------------------------
 template <int V>
-__global__ void __launch_bounds__(256) k_avgpool2_fwd(const float* __restrict__ xs, float* __restrict__ ys, size_t n_out, int h, int w, int c) {
+__global__ void __launch_bounds__(256) k_avgpool2_fwd(const float* __restrict__ xs, float* __restrict__ ys, int n_out, int h, int w, int c,
+                                                      const PixIdx q) {
   typedef typename VecT<V>::type T;
   const T* __restrict__ x = reinterpret_cast<const T*>(xs);
   T* __restrict__ y = reinterpret_cast<T*>(ys);
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  const int oh = h / 2, ow = w / 2;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += stride) {
-    const int ch = (int)(i % c);
-    size_t t = i / c;
-    const int ox = (int)(t % ow); t /= ow;
-    const int oy = (int)(t % oh);
-    const size_t b = t / oh;
-    const T* p = x + ((b * h + 2 * oy) * w + 2 * ox) * c + ch;
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += stride) {
+    int ch, ox, oy, b;
+    pix_decode(q, i, ch, ox, oy, b);              // q over (c, w/2, h/2)
+    const T* p = x + (((size_t)b * h + 2 * oy) * w + 2 * ox) * c + ch;
     y[i] = vmix(p[0], p[c], p[(size_t)w * c], p[(size_t)w * c + c], 0.25f, 0.25f, 0.25f, 0.25f);
   }
 }
 template <int V>
-__global__ void __launch_bounds__(256) k_avgpool2_bwd(const float* __restrict__ gs, float* __restrict__ dxs, size_t n_in, int h, int w, int c) {
+__global__ void __launch_bounds__(256) k_avgpool2_bwd(const float* __restrict__ gs, float* __restrict__ dxs, int n_in, int h, int w, int c,
+                                                      const PixIdx q) {
   typedef typename VecT<V>::type T;
   const T* __restrict__ g = reinterpret_cast<const T*>(gs);
   T* __restrict__ dx = reinterpret_cast<T*>(dxs);
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const int stride = gridDim.x * blockDim.x;
   const int oh = h / 2, ow = w / 2;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_in; i += stride) {
-    const int ch = (int)(i % c);
-    size_t t = i / c;
-    const int ix = (int)(t % w); t /= w;
-    const int iy = (int)(t % h);
-    const size_t b = t / h;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_in; i += stride) {
+    int ch, ix, iy, b;
+    pix_decode(q, i, ch, ix, iy, b);              // q over (c, w, h)
     const int oy = iy >> 1, ox = ix >> 1;
     T acc = vzero(T());
-    if (oy < oh && ox < ow) vfma(acc, 0.25f, g[((b * oh + oy) * ow + ox) * c + ch]);
+    if (oy < oh && ox < ow) vfma(acc, 0.25f, g[(((size_t)b * oh + oy) * ow + ox) * c + ch]);
     dx[i] = acc;
   }
 }
 extern "C" int lb_avgpool2_fwd(const float* x, float* y, int batch, int h, int w, int c, lb_stream_t s) {
   LB_REQUIRE(x && y && batch > 0 && h > 1 && w > 1 && c > 0);
   const size_t n = (size_t)batch * (h / 2) * (w / 2) * c;
+  LB_REQUIRE_INT_ITEMS(n);
   if ((c & 3) == 0 && lb_aligned16(x) && lb_aligned16(y))
-    k_avgpool2_fwd<4><<<lb_grid_1d(n / 4, 256), 256, 0, lb_s(s)>>>(x, y, n / 4, h, w, c / 4);
+    k_avgpool2_fwd<4><<<lb_grid_1d(n / 4, 256), 256, 0, lb_s(s)>>>(x, y, (int)(n / 4), h, w, c / 4, make_pix_idx(c / 4, w / 2, h / 2));
   else
-    k_avgpool2_fwd<1><<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(x, y, n, h, w, c);
+    k_avgpool2_fwd<1><<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(x, y, (int)n, h, w, c, make_pix_idx(c, w / 2, h / 2));
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
 extern "C" int lb_avgpool2_bwd(const float* g, float* dx, int batch, int h, int w, int c, lb_stream_t s) {
   LB_REQUIRE(g && dx && batch > 0 && h > 1 && w > 1 && c > 0);
   const size_t n = (size_t)batch * h * w * c;
+  LB_REQUIRE_INT_ITEMS(n);
   if ((c & 3) == 0 && lb_aligned16(g) && lb_aligned16(dx))
-    k_avgpool2_bwd<4><<<lb_grid_1d(n / 4, 256), 256, 0, lb_s(s)>>>(g, dx, n / 4, h, w, c / 4);
+    k_avgpool2_bwd<4><<<lb_grid_1d(n / 4, 256), 256, 0, lb_s(s)>>>(g, dx, (int)(n / 4), h, w, c / 4, make_pix_idx(c / 4, w, h));
   else
-    k_avgpool2_bwd<1><<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(g, dx, n, h, w, c);
+    k_avgpool2_bwd<1><<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(g, dx, (int)n, h, w, c, make_pix_idx(c, w, h));
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
