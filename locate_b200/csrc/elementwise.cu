@@ -223,6 +223,7 @@ __global__ void k_gate_bwd(const float* __restrict__ x, const float* __restrict_
   for (int c = (threadIdx.x < tc * tp ? cl : channels); c < channels; c += tc) {
     float acc_dy = 0.0f;
     const float yb = y_bcast ? __ldg(y + (size_t)b * channels + c) : 0.0f;
+#pragma unroll 4
     for (int p = p0 + pl; p < p1; p += tp) {
       const size_t i = base + (size_t)p * channels + c;
       const float xv = x[i], gv = g[i];
@@ -325,11 +326,31 @@ __global__ void k_copy_rows(const float* __restrict__ src, int ld_src, float* __
     *d = accumulate ? *d + v : v;
   }
 }
+// 16-byte version (cols, both leading dimensions and both pointers multiples of 4 floats), 32-bit multiply-shift decode
+__global__ void __launch_bounds__(256) k_copy_rows4(const float* __restrict__ src, int ld_src, float* __restrict__ dst, int ld_dst,
+                                                   int n4, LbFastDiv d_c4, int accumulate) {
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    int r, c4;
+    lb_fast_divmod(d_c4, i, r, c4);
+    float4 v = lb_ld4(src + (size_t)r * ld_src + 4 * c4);
+    float* d = dst + (size_t)r * ld_dst + 4 * c4;
+    if (accumulate) {
+      const float4 o = *reinterpret_cast<const float4*>(d);
+      v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+    }
+    lb_st4(d, v);
+  }
+}
 extern "C" int lb_copy_rows(const float* src, int ld_src, float* dst, int ld_dst, int64_t rows, int cols, int accumulate,
                             lb_stream_t s) {
   LB_REQUIRE(src && dst && rows >= 0 && cols > 0 && ld_src >= cols && ld_dst >= cols);
   if (rows == 0) return LB_OK;
-  k_copy_rows<<<lb_grid_1d((size_t)rows * cols, 256), 256, 0, lb_s(s)>>>(src, ld_src, dst, ld_dst, (size_t)rows, cols, accumulate);
+  const size_t n = (size_t)rows * cols;
+  if (!(cols & 3) && !(ld_src & 3) && !(ld_dst & 3) && lb_aligned16(src) && lb_aligned16(dst) && n / 4 < ((size_t)1 << 31) - ((size_t)1 << 24))
+    k_copy_rows4<<<lb_grid_1d(n / 4, 256), 256, 0, lb_s(s)>>>(src, ld_src, dst, ld_dst, (int)(n / 4), lb_make_fastdiv(cols / 4), accumulate);
+  else
+    k_copy_rows<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(src, ld_src, dst, ld_dst, (size_t)rows, cols, accumulate);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }

@@ -160,6 +160,7 @@ __global__ void k_norm_bwd_reduce(const float* __restrict__ x, const float* __re
   const size_t base = (size_t)b * pixels * channels;
   for (int c = cl; c < channels; c += tc) {
     float a1 = 0.0f, a2 = 0.0f;
+#pragma unroll 4
     for (int p = q0 + pl; p < q1; p += tp) {
       const size_t i = base + (size_t)p * channels + c;
       const float gv = g[i];

@@ -12,18 +12,20 @@
 // All index decoding is 32-bit multiply-shift division (the 64-bit divides of the first version made these gathers
 // instruction-bound at a quarter of the HBM rate).
 struct FeatPoolIdx { LbFastDiv d_c, d_hw, d_m, d_r; int hw, c_in, c_out, r, m; };
+// forward: one thread = one INPUT channel ci of one pixel group pm (reads: consecutive threads on consecutive channels of
+// r consecutive pixels, full lines); it produces out[b, (ci % r)*m + pm, ci / r].  d_c = c_in here.
 __global__ void __launch_bounds__(256) k_featpool_fwd(const float* __restrict__ x, float* __restrict__ y, int n_out, const FeatPoolIdx q) {
   const int stride = gridDim.x * blockDim.x;
   const float inv = 1.0f / q.r;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += stride) {
-    int bp, o, b, p, pj, pm;
-    lb_fast_divmod(q.d_c, i, bp, o);              // d_c = c_out
-    lb_fast_divmod(q.d_hw, bp, b, p);
-    lb_fast_divmod(q.d_m, p, pj, pm);
-    const float* src = x + ((size_t)b * q.hw + (size_t)pm * q.r) * q.c_in + o * q.r + pj;
+    int t, ci, b, pm, o, pj;
+    lb_fast_divmod(q.d_c, i, t, ci);
+    lb_fast_divmod(q.d_m, t, b, pm);
+    lb_fast_divmod(q.d_r, ci, o, pj);
+    const float* src = x + ((size_t)b * q.hw + (size_t)pm * q.r) * q.c_in + ci;
     float acc = 0.0f;
     for (int k = 0; k < q.r; ++k) acc += __ldg(src + (size_t)k * q.c_in);
-    y[i] = acc * inv;
+    y[((size_t)b * q.hw + (size_t)pj * q.m + pm) * q.c_out + o] = acc * inv;
   }
 }
 __global__ void __launch_bounds__(256) k_featpool_bwd(const float* __restrict__ g, float* __restrict__ dx, int n_in, const FeatPoolIdx q) {
@@ -82,7 +84,7 @@ extern "C" int lb_featpool_fwd(const float* x, float* y, int batch, int h, int w
   LB_REQUIRE(x && y && batch > 0 && h > 0 && w > 0 && c_out > 0 && c_in % c_out == 0);
   const size_t n = (size_t)batch * h * w * c_out;
   FeatPoolIdx q;
-  if (featpool_idx(&q, batch, h, w, c_in, c_out, c_out, n) == LB_OK)
+  if (featpool_idx(&q, batch, h, w, c_in, c_out, c_in, n) == LB_OK)
     k_featpool_fwd<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(x, y, (int)n, q);
   else
     k_featpool_fwd_generic<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(x, y, n, h * w, c_in, c_out, c_in / c_out);
