@@ -241,10 +241,43 @@ __global__ void k_gate_bwd(const float* __restrict__ x, const float* __restrict_
   }
 }
 
+// full-shape gate (y has the shape of x): everything is elementwise except d-gamma, so the kernel streams float4s and
+// reduces one scalar per CTA
+__global__ void __launch_bounds__(256) k_gate_bwd4(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ gamma,
+                                                  const float* __restrict__ g, float* __restrict__ dx, float* __restrict__ dy,
+                                                  float* __restrict__ dgamma, size_t n4, int strict) {
+  __shared__ float scratch[32];
+  const float gm = __ldg(gamma);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  float acc = 0.0f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 xv = lb_ld4(x + 4 * i), yv = lb_ld4(y + 4 * i), gv = lb_ld4(g + 4 * i);
+    float4 a, b;
+    a.x = fmaf(gm, yv.x, 1.0f) * gv.x; a.y = fmaf(gm, yv.y, 1.0f) * gv.y;
+    a.z = fmaf(gm, yv.z, 1.0f) * gv.z; a.w = fmaf(gm, yv.w, 1.0f) * gv.w;
+    const float4 xg = make_float4(xv.x * gv.x, xv.y * gv.y, xv.z * gv.z, xv.w * gv.w);
+    b.x = xg.x * gm; b.y = xg.y * gm; b.z = xg.z * gm; b.w = xg.w * gm;
+    lb_st4(dx + 4 * i, a);
+    lb_st4(dy + 4 * i, b);
+    const float4 m = strict ? xv : yv;
+    acc += fmaf(xg.x, m.x, xg.y * m.y) + fmaf(xg.z, m.z, xg.w * m.w);
+  }
+  if (dgamma) {
+    const float tot = lb_block_sum(acc, scratch);
+    if (threadIdx.x == 0) atomicAdd(dgamma, tot);
+  }
+}
+
 extern "C" int lb_gate_bwd(const float* x, const float* y, const float* gamma, const float* g, float* dx, float* dy,
                            float* dgamma, int batch, int pixels, int channels, int y_bcast, int strict_reference,
                            lb_stream_t s) {
   LB_REQUIRE(x && y && gamma && g && dx && dy && batch > 0 && pixels > 0 && channels > 0);
+  const size_t n = (size_t)batch * pixels * channels;
+  if (!y_bcast && !(n & 3) && lb_aligned16(x) && lb_aligned16(y) && lb_aligned16(g) && lb_aligned16(dx) && lb_aligned16(dy)) {
+    k_gate_bwd4<<<lb_grid_1d(n / 4, 256, 4), 256, 0, lb_s(s)>>>(x, y, gamma, g, dx, dy, dgamma, n / 4, strict_reference);
+    LB_LAUNCH_CHECK();
+    return LB_OK;
+  }
   const LbColShape sh = lb_col_shape(channels);
   // chunk: aim for ~4 waves of CTAs, at least tp pixels each
   int chunks = (LB_SMS * 4 + batch - 1) / batch;
