@@ -305,7 +305,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--batch", type=int, default=384, help="per-GPU batch (weak scaling: fixed per GPU)")
+    ap.add_argument("--batch", type=int, default=512, help="per-GPU batch (weak scaling: fixed per GPU); ~34 GB of HBM at 512")
     ap.add_argument("--ref-batch", type=int, default=4, help="batch of the CPU reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")

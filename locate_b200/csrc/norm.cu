@@ -58,14 +58,16 @@ extern "C" int lb_norm_finalize(const double* sums, double n_total, float* stats
 // y = (x - mean) * gain[b?,c] * rstd + bias[c]; one thread = 4 consecutive channels of one pixel
 __global__ void __launch_bounds__(256) k_norm_apply4(const float* __restrict__ x, const float* __restrict__ stats,
                                                     const float* __restrict__ gain, int gain_bs, const float* __restrict__ bias,
-                                                    float* __restrict__ y, size_t n4, int pc4, int c4) {
+                                                    float* __restrict__ y, size_t n4, LbFastDiv d_pc4, LbFastDiv d_c4) {
   const float mean = __ldg(stats), rstd = __ldg(stats + 2);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    const size_t b = i / (size_t)pc4;
-    const int c = (int)(i % (size_t)c4) * 4;
+    int b, rem, q, c;
+    lb_fast_divmod(d_pc4, (int)i, b, rem);      // n4 < 2^31 (checked by the host)
+    lb_fast_divmod(d_c4, rem, q, c);
+    c *= 4;
     const float4 v = lb_ld4(x + 4 * i);
-    const float4 gn = lb_ld4(gain + b * gain_bs + c);
+    const float4 gn = lb_ld4(gain + (size_t)b * gain_bs + c);
     const float4 bs = lb_ld4(bias + c);
     float4 r;
     r.x = fmaf((v.x - mean) * rstd, gn.x, bs.x);
@@ -80,14 +82,17 @@ __global__ void __launch_bounds__(256) k_norm_apply4(const float* __restrict__ x
 template <bool kAct>
 __global__ void __launch_bounds__(256) k_norm_apply4_ex(const float* __restrict__ x, const float* __restrict__ stats,
                                                        const float* __restrict__ gain, int gain_bs, const float* __restrict__ bias,
-                                                       float* __restrict__ y, __nv_bfloat16* __restrict__ y16, size_t n4, int pc4, int c4) {
+                                                       float* __restrict__ y, __nv_bfloat16* __restrict__ y16, size_t n4, LbFastDiv d_pc4,
+                                                       LbFastDiv d_c4) {
   const float mean = __ldg(stats), rstd = __ldg(stats + 2);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    const size_t b = i / (size_t)pc4;
-    const int c = (int)(i % (size_t)c4) * 4;
+    int b, rem, q, c;
+    lb_fast_divmod(d_pc4, (int)i, b, rem);      // n4 < 2^31 (checked by the host)
+    lb_fast_divmod(d_c4, rem, q, c);
+    c *= 4;
     const float4 v = lb_ld4(x + 4 * i);
-    const float4 gn = lb_ld4(gain + b * gain_bs + c);
+    const float4 gn = lb_ld4(gain + (size_t)b * gain_bs + c);
     const float4 bs = lb_ld4(bias + c);
     float4 r;
     r.x = fmaf((v.x - mean) * rstd, gn.x, bs.x);
@@ -120,9 +125,11 @@ extern "C" int lb_norm_apply(const float* x, const float* stats, const float* ga
   LB_REQUIRE(x && stats && gain && bias && y && batch > 0 && pixels > 0 && channels > 0);
   LB_REQUIRE(gain_batch_stride == 0 || gain_batch_stride == channels);
   const size_t n = (size_t)batch * pixels * channels;
-  if ((channels & 3) == 0 && lb_aligned16(x) && lb_aligned16(y) && lb_aligned16(gain) && lb_aligned16(bias)) {
+  if ((channels & 3) == 0 && n / 4 < ((size_t)1 << 31) - ((size_t)1 << 24) && lb_aligned16(x) && lb_aligned16(y) && lb_aligned16(gain) &&
+      lb_aligned16(bias)) {
     k_norm_apply4<<<lb_grid_1d(n / 4, 256), 256, 0, lb_s(s)>>>(x, stats, gain, gain_batch_stride, bias, y, n / 4,
-                                                              pixels * channels / 4, channels / 4);
+                                                              lb_make_fastdiv((uint32_t)((size_t)pixels * channels / 4)),
+                                                              lb_make_fastdiv(channels / 4));
   } else {
     k_norm_apply1<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(x, stats, gain, gain_batch_stride, bias, y, n, pixels * channels, channels);
   }
@@ -135,16 +142,18 @@ extern "C" int lb_norm_apply_ex(const float* x, const float* stats, const float*
   LB_REQUIRE(x && stats && gain && bias && y16 && batch > 0 && pixels > 0 && channels > 0);
   LB_REQUIRE(gain_batch_stride == 0 || gain_batch_stride == channels);
   const size_t n = (size_t)batch * pixels * channels;
-  if ((channels & 3) || !lb_aligned16(x) || (y && !lb_aligned16(y)) || !lb_aligned16(gain) || !lb_aligned16(bias) ||
-      (reinterpret_cast<uintptr_t>(y16) & 7))
+  if ((channels & 3) || n / 4 >= ((size_t)1 << 31) - ((size_t)1 << 24) || !lb_aligned16(x) || (y && !lb_aligned16(y)) ||
+      !lb_aligned16(gain) || !lb_aligned16(bias) || (reinterpret_cast<uintptr_t>(y16) & 7))
     return LB_EALIGN;
   __nv_bfloat16* o16 = reinterpret_cast<__nv_bfloat16*>(y16);
   if (act16)
     k_norm_apply4_ex<true><<<lb_grid_1d(n / 4, 256), 256, 0, lb_s(s)>>>(x, stats, gain, gain_batch_stride, bias, y, o16, n / 4,
-                                                                       pixels * channels / 4, channels / 4);
+                                                                       lb_make_fastdiv((uint32_t)((size_t)pixels * channels / 4)),
+                                                                       lb_make_fastdiv(channels / 4));
   else
     k_norm_apply4_ex<false><<<lb_grid_1d(n / 4, 256), 256, 0, lb_s(s)>>>(x, stats, gain, gain_batch_stride, bias, y, o16, n / 4,
-                                                                        pixels * channels / 4, channels / 4);
+                                                                        lb_make_fastdiv((uint32_t)((size_t)pixels * channels / 4)),
+                                                                        lb_make_fastdiv(channels / 4));
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
