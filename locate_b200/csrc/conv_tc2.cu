@@ -53,6 +53,9 @@ struct Tc2Params {
   int has_o32, has_o16, has_aux;
   int act16;                          // 1: RootTanh (growth 4) applied to the bf16 output
   uint32_t tmem_cols;
+  uint32_t tab_base; int max_tp;      // per-phase tap table in shared memory: max_tp entries per phase
+  int resident;                       // 1: the weights of one output phase stay in shared memory (res_base), stages carry A only
+  uint32_t res_base, b_tile_bytes;
   uint32_t epi_base, epi_per_warp, off_o32, off_o16, off_aux;   // bytes; epi_base relative to the 1 KB aligned base
   const float* alpha; const float* bias;
 };
@@ -86,23 +89,7 @@ __device__ __forceinline__ AxisTaps axis_taps(const Tc2Params& p, int k, int par
   }
   return a;
 }
-// shift d, parity q and liveness of tap t on one axis: the box [o0 + d, o0 + d + tile) must meet the view [0, extent)
-__device__ __forceinline__ bool tap_axis(const Tc2Params& p, int t, int parity, int o0, int tile, int in_extent, int& d, int& q) {
-  int extent;
-  if (p.mode == 0) {
-    const int off = t - p.pad;
-    d = off >> p.sh;                     // arithmetic shift = floor division
-    q = off & (p.stride - 1);
-    extent = (in_extent - q + p.stride - 1) >> p.sh;
-  } else {
-    d = (parity + p.pad - t) >> p.sh;    // exact by construction of t
-    q = 0;
-    extent = in_extent;
-  }
-  return o0 + d < extent && o0 + d + tile > 0;
-}
-
-// Index range [lo, hi) of axis_taps() entries that can be live for a tile at o0 (a superset: tap_axis() still decides).
+// Index range [lo, hi) of axis_taps() entries that can be live for a tile at o0 (a superset: tap_live() still decides).
 // Scanning every tap costs the lone producer / MMA threads ~25 instructions per tap; a full-extent 64x1 kernel has two
 // live taps out of 64 per tile.
 __device__ __forceinline__ void axis_range(const Tc2Params& p, const AxisTaps& a, int parity, int o0, int tile, int in_extent,
@@ -172,20 +159,56 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Per-phase tap table (built once per CTA): the lone producer / MMA threads were spending ~500 dependent scalar
+// instructions per tile re-deriving each tap's shift, view and weight row (ncu: both warps busy, barely ever waiting),
+// which capped the small-channel layers at ~3 us per tile.  Entry e of phase ph: tapv = {dy, dx, view, weight row of the
+// tap}, tape = {view extent y, x} for the liveness test.
+constexpr int kMaxTapsPhase = 64;
+__device__ __forceinline__ void build_tap_table(const Tc2Params& p, int4* tapv, int2* tape) {
+  const int phases = p.sp * p.sp;
+  for (int idx = threadIdx.x; idx < phases * p.max_tp; idx += blockDim.x) {
+    const int ph = idx / p.max_tp, l = idx - ph * p.max_tp;
+    const int py = ph >> p.sh, px = ph & (p.sp - 1);
+    const AxisTaps ay = axis_taps(p, p.kh, py), ax = axis_taps(p, p.kw, px);
+    if (l >= ay.cnt * ax.cnt) continue;
+    const int iy = l / ax.cnt, ix = l - iy * ax.cnt;
+    const int ty = ay.t0 + iy * ay.step, tx = ax.t0 + ix * ax.step;
+    int dy, qy, dx, qx, eh, ew;
+    if (p.mode == 0) {
+      const int oy = ty - p.pad, ox = tx - p.pad;
+      dy = oy >> p.sh; qy = oy & (p.stride - 1); eh = (p.in_h - qy + p.stride - 1) >> p.sh;
+      dx = ox >> p.sh; qx = ox & (p.stride - 1); ew = (p.in_w - qx + p.stride - 1) >> p.sh;
+    } else {
+      dy = (py + p.pad - ty) >> p.sh; qy = 0; eh = p.in_h;
+      dx = (px + p.pad - tx) >> p.sh; qx = 0; ew = p.in_w;
+    }
+    tapv[idx] = make_int4(dy, dx, (qy << p.sh) + qx, (ty * p.kw + tx) * p.rows_per_tap);
+    tape[idx] = make_int2(eh, ew);
+  }
+}
+__device__ __forceinline__ bool tap_live(const Tc2Params& p, const TileCoord& c, const int4& v, const int2& e) {
+  return c.y0 + v.x < e.x && c.y0 + v.x + p.tile_h > 0 && c.x0 + v.y < e.y && c.x0 + v.y + p.tile_w > 0;
+}
+
 __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant__ Tc2Maps maps, const Tc2Params p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[8], bar_empty[8], bar_tfull[2], bar_tempty[2], bar_aux[kEpiWarps][2];
+  __shared__ __align__(8) uint64_t bar_bfull, bar_bfree;          // resident weights: loaded / no longer read
   __shared__ uint32_t tmem_slot;
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int b_bytes = p.block_n * kBlockK * 2;
-  const int stage_bytes = kABytes + ((b_bytes + 1023) & ~1023);
+  const int stage_bytes = p.resident ? kABytes : kABytes + ((b_bytes + 1023) & ~1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int4* tapv = reinterpret_cast<int4*>(smem + p.tab_base);
+  int2* tape = reinterpret_cast<int2*>(smem + p.tab_base + 4 * kMaxTapsPhase * sizeof(int4));
+  build_tap_table(p, tapv, tape);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { tc::mbar_init(&bar_full[s], 1); tc::mbar_init(&bar_empty[s], 1); }
     for (int a = 0; a < 2; ++a) { tc::mbar_init(&bar_tfull[a], 1); tc::mbar_init(&bar_tempty[a], kEpiWarps); }
     for (int w = 0; w < kEpiWarps; ++w) { tc::mbar_init(&bar_aux[w][0], 1); tc::mbar_init(&bar_aux[w][1], 1); }
+    tc::mbar_init(&bar_bfull, 1); tc::mbar_init(&bar_bfree, 1);
     tc::fence_barrier_init();
   }
   if (warp == 0 && lane == 0) {
@@ -202,45 +225,51 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
     // ===================== TMA producer =====================
     if (tc::elect_one()) {
       int st = 0; uint32_t ph = 0;                        // ring position, runs on across tiles
+      int res_phase = -1; uint32_t epochs = 0;            // resident weights: phase they belong to, sets loaded so far
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const TileCoord c = decode_tile(p, tile);
         const AxisTaps ay = axis_taps(p, p.kh, c.py), ax = axis_taps(p, p.kw, c.px);
+        if (p.resident && c.phase != res_phase) {
+          // every tap x channel chunk of this phase, once; the previous set must have been read by its last MMA
+          if (epochs > 0) tc::mbar_wait(&bar_bfree, (epochs - 1) & 1u);
+          tc::mbar_arrive_expect_tx(&bar_bfull, (uint32_t)(ay.cnt * ax.cnt * p.kchunks * b_bytes));
+          for (int iy = 0; iy < ay.cnt; ++iy)
+            for (int ix = 0; ix < ax.cnt; ++ix) {
+              const int wrow = ((ay.t0 + iy * ay.step) * p.kw + ax.t0 + ix * ax.step) * p.rows_per_tap + c.n0;
+              for (int kc = 0; kc < p.kchunks; ++kc)
+                tc::tma_load_2d(smem + p.res_base + (uint32_t)((iy * ax.cnt + ix) * p.kchunks + kc) * p.b_tile_bytes, &maps.b,
+                                &bar_bfull, kc * kBlockK, wrow);
+            }
+          res_phase = c.phase;
+          ++epochs;
+        }
         int ylo, yhi, xlo, xhi;
         axis_range(p, ay, c.py, c.y0, p.tile_h, p.in_h, ylo, yhi);
         axis_range(p, ax, c.px, c.x0, p.tile_w, p.in_w, xlo, xhi);
+        const int tbase = c.phase * p.max_tp;
         bool issued = false;
-        auto load_tap = [&](int ty, int tx, int dy, int qy, int dx, int qx) {
-          const int view = (qy << p.sh) + qx;
-          const int cb = ((p.view_empty >> view) & 1) ? p.batch : c.b0;   // empty view: box out of range -> zeros
-          const int wrow = (ty * p.kw + tx) * p.rows_per_tap + c.n0;
+        auto load_tap = [&](const int4& v) {
+          const int cb = ((p.view_empty >> v.z) & 1) ? p.batch : c.b0;   // empty view: box out of range -> zeros
+          const int wrow = v.w + c.n0;
           for (int kc = 0; kc < p.kchunks; ++kc) {
             tc::mbar_wait(&bar_empty[st], ph ^ 1u);
             uint8_t* sa = smem + st * stage_bytes;
-            tc::mbar_arrive_expect_tx(&bar_full[st], (uint32_t)(kABytes + b_bytes));
-            tc::tma_load_4d(sa, &maps.a[view], &bar_full[st], kc * kBlockK, c.x0 + dx, c.y0 + dy, cb);
-            tc::tma_load_2d(sa + kABytes, &maps.b, &bar_full[st], kc * kBlockK, wrow);
+            tc::mbar_arrive_expect_tx(&bar_full[st], (uint32_t)(p.resident ? kABytes : kABytes + b_bytes));
+            tc::tma_load_4d(sa, &maps.a[v.z], &bar_full[st], kc * kBlockK, c.x0 + v.y, c.y0 + v.x, cb);
+            if (!p.resident) tc::tma_load_2d(sa + kABytes, &maps.b, &bar_full[st], kc * kBlockK, wrow);
             if (++st == p.stages) { st = 0; ph ^= 1u; }
           }
         };
         for (int iy = ylo; iy < yhi; ++iy) {
-          const int ty = ay.t0 + iy * ay.step;
-          int dy, qy;
-          if (!tap_axis(p, ty, c.py, c.y0, p.tile_h, p.in_h, dy, qy)) continue;
           for (int ix = xlo; ix < xhi; ++ix) {
-            const int tx = ax.t0 + ix * ax.step;
-            int dx, qx;
-            if (!tap_axis(p, tx, c.px, c.x0, p.tile_w, p.in_w, dx, qx)) continue;   // a tap whose box is all padding adds nothing
+            const int e = tbase + iy * ax.cnt + ix;
+            const int4 v = tapv[e];
+            if (!tap_live(p, c, v, tape[e])) continue;       // a tap whose box is all padding adds nothing
             issued = true;
-            load_tap(ty, tx, dy, qy, dx, qx);
+            load_tap(v);
           }
         }
-        if (!issued) {                                        // every tap is padding: one of them still defines the zeros
-          const int ty = ay.t0 + (ay.cnt - 1) * ay.step, tx = ax.t0 + (ax.cnt - 1) * ax.step;
-          int dy, qy, dx, qx;
-          tap_axis(p, ty, c.py, c.y0, p.tile_h, p.in_h, dy, qy);
-          tap_axis(p, tx, c.px, c.x0, p.tile_w, p.in_w, dx, qx);
-          load_tap(ty, tx, dy, qy, dx, qx);
-        }
+        if (!issued) load_tap(tapv[tbase + ay.cnt * ax.cnt - 1]);   // every tap is padding: one of them still defines the zeros
       }
     }
   } else if (warp == 1) {
@@ -250,9 +279,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
       const int k16_last = (p.in_c - (p.kchunks - 1) * kBlockK + 15) / 16;
       int st = 0; uint32_t ph = 0;
       int lt = 0;
+      int res_phase = -1; uint32_t epochs = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
         const TileCoord c = decode_tile(p, tile);
         const AxisTaps ay = axis_taps(p, p.kh, c.py), ax = axis_taps(p, p.kw, c.px);
+        if (p.resident && c.phase != res_phase) {
+          tc::mbar_wait(&bar_bfull, epochs & 1u);
+          tc::tc_fence_after();
+          res_phase = c.phase;
+          ++epochs;
+        }
         const int acc = lt & 1;
         tc::mbar_wait(&bar_tempty[acc], (((uint32_t)lt >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
         tc::tc_fence_after();
@@ -261,12 +297,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
         axis_range(p, ay, c.py, c.y0, p.tile_h, p.in_h, ylo, yhi);
         axis_range(p, ax, c.px, c.x0, p.tile_w, p.in_w, xlo, xhi);
         bool issued = false;
-        auto mma_tap = [&]() {
+        auto mma_tap = [&](int tap_idx) {
           for (int kc = 0; kc < p.kchunks; ++kc) {
             tc::mbar_wait(&bar_full[st], ph);
             tc::tc_fence_after();
             const uint32_t sa = tc::smem_u32(smem + st * stage_bytes);
-            const uint32_t sb = sa + kABytes;
+            const uint32_t sb = p.resident ? tc::smem_u32(smem + p.res_base) + (uint32_t)(tap_idx * p.kchunks + kc) * p.b_tile_bytes
+                                           : sa + kABytes;
             const int nk = (kc == p.kchunks - 1) ? k16_last : kBlockK / 16;
             for (int k = 0; k < nk; ++k) {
               const uint64_t ad = tc::smem_desc_sw128(sa + k * 32, 16, 1024);
@@ -278,17 +315,20 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
             if (++st == p.stages) { st = 0; ph ^= 1u; }
           }
         };
+        const int tbase = c.phase * p.max_tp;
         for (int iy = ylo; iy < yhi; ++iy) {
-          int dy, qy;
-          if (!tap_axis(p, ay.t0 + iy * ay.step, c.py, c.y0, p.tile_h, p.in_h, dy, qy)) continue;
           for (int ix = xlo; ix < xhi; ++ix) {
-            int dx, qx;
-            if (!tap_axis(p, ax.t0 + ix * ax.step, c.px, c.x0, p.tile_w, p.in_w, dx, qx)) continue;
-            mma_tap();
+            const int e = iy * ax.cnt + ix;
+            if (!tap_live(p, c, tapv[tbase + e], tape[tbase + e])) continue;
+            mma_tap(e);
           }
         }
-        if (!issued) mma_tap();
+        if (!issued) mma_tap(ay.cnt * ax.cnt - 1);
         tc::umma_commit(&bar_tfull[acc]);
+        if (p.resident) {                                   // last tile of this weight set: the producer may overwrite it
+          const int next = tile + gridDim.x;
+          if (next >= p.total_tiles || decode_tile(p, next).phase != c.phase) tc::umma_commit(&bar_bfree);
+        }
       }
     }
   } else {
@@ -428,6 +468,10 @@ static bool tc2_ok(const lb_conv_geom* g, const void* out32, const void* out16, 
   if (g->stride != 1 && g->stride != 2) return false;
   if (g->ld_in % 8 || g->in_c < 1 || g->out_c < 1 || g->kh * g->kw > 1024) return false;
   if (g->mode == 1 && (g->kh < g->stride || g->kw < g->stride)) return false;          // a phase without taps
+  {
+    const int sp_ = g->mode == 1 ? g->stride : 1;
+    if ((g->mode == 1 ? ((g->kh + sp_ - 1) / sp_) * ((g->kw + sp_ - 1) / sp_) : g->kh * g->kw) > 64) return false;   // tap table size
+  }
   if (out32 && ((g->ld_out & 3) || (reinterpret_cast<uintptr_t>(out32) & 15))) return false;
   if (out16 && ((ld16 & 7) || (reinterpret_cast<uintptr_t>(out16) & 15))) return false;
   if (aux && ((ld_aux & 3) || (reinterpret_cast<uintptr_t>(aux) & 15))) return false;
@@ -479,7 +523,10 @@ extern "C" int lb_conv_tc_gemm_ex(const void* in_bf16, const void* w_packed, con
   p.off_o16 = off; if (out16) off += 2048;
   p.off_aux = off; if (aux) off += 8192;
   p.epi_per_warp = (off + 1023) & ~1023u;
-  const int epi_bytes = (int)p.epi_per_warp * kEpiWarps;
+  const int tab_bytes = 4 * kMaxTapsPhase * (int)(sizeof(int4) + sizeof(int2));      // 6 KB
+  const int epi_bytes = (int)p.epi_per_warp * kEpiWarps + tab_bytes;
+  p.max_tp = g->mode == 1 ? ((g->kh + p.sp - 1) / p.sp) * ((g->kw + p.sp - 1) / p.sp) : g->kh * g->kw;
+  if (p.max_tp > kMaxTapsPhase) return LB_EUNSUPPORTED;
 
   // channel tile: as wide as TMEM double buffering allows (<= 256) while leaving >= 3 ring stages
   int nt = (g->out_c + 255) / 256, bn = 0, stage_bytes = 0, stages = 0;
@@ -492,10 +539,29 @@ extern "C" int lb_conv_tc_gemm_ex(const void* in_bf16, const void* w_packed, con
   }
   if (stages < 2) return LB_EUNSUPPORTED;
   if (stages > 8) stages = 8;
+  // Optional (LB_TC2_RESIDENT=1): all taps x chunks of one output phase's weights (<= ~100 KB) are loaded once per phase
+  // and stay resident, so ring stages carry A only.  Measured on B200 (profiles/README.md): no gain -- the small-channel
+  // layers are bound by the rate at which the TMA unit processes the 128 strided rows of each A box (~380 ns per box),
+  // not by the bytes of the weight tile -- so it stays off by default.
+  p.resident = 0; p.res_base = 0;
+  p.b_tile_bytes = (uint32_t)((bn * kBlockK * 2 + 1023) & ~1023);
+  {
+    const int taps_phase = g->mode == 1 ? ((g->kh + p.sp - 1) / p.sp) * ((g->kw + p.sp - 1) / p.sp) : g->kh * g->kw;
+    const long long res_bytes = (long long)taps_phase * p.kchunks * p.b_tile_bytes;
+    const int a_stages = (int)((kSmemLimit - 1024 - epi_bytes - res_bytes) / kABytes);
+    if (nt == 1 && res_bytes <= 100 * 1024 && a_stages >= 4 && getenv("LB_TC2_RESIDENT")) {
+      p.resident = 1;
+      stage_bytes = kABytes;
+      stages = a_stages;
+      if (stages > 8) stages = 8;
+      p.res_base = (uint32_t)(stages * stage_bytes);
+    }
+  }
+  if (const char* env = getenv("LB_TC2_STAGES")) { const int v = atoi(env); if (v >= 2 && v < stages) { stages = v; if (p.resident) p.res_base = (uint32_t)(stages * stage_bytes); } }
   p.block_n = bn; p.n_tiles = (g->out_c + bn - 1) / bn; p.stages = stages;
   p.acc_stride = (bn + 31) / 32 * 32;
   p.tmem_cols = (uint32_t)pow2_ceil(2 * p.acc_stride < 32 ? 32 : 2 * p.acc_stride);
-  p.epi_base = (uint32_t)(stages * stage_bytes);
+  p.epi_base = (uint32_t)(stages * stage_bytes) + (p.resident ? (uint32_t)(((g->mode == 1 ? ((g->kh + p.sp - 1) / p.sp) * ((g->kw + p.sp - 1) / p.sp) : g->kh * g->kw)) * p.kchunks) * p.b_tile_bytes : 0u);
   p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_b * p.n_tiles * p.sp * p.sp;
   p.d_nt = lb_make_fastdiv(p.n_tiles); p.d_tw = lb_make_fastdiv(p.tiles_w); p.d_th = lb_make_fastdiv(p.tiles_h); p.d_tb = lb_make_fastdiv(p.tiles_b);
 
@@ -559,7 +625,8 @@ extern "C" int lb_conv_tc_gemm_ex(const void* in_bf16, const void* w_packed, con
       if (rc) return rc;
     }
   }
-  const int smem_bytes = stages * stage_bytes + epi_bytes + 1024;
+  p.tab_base = p.epi_base + p.epi_per_warp * kEpiWarps;
+  const int smem_bytes = (int)p.epi_base + epi_bytes + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(k_conv_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
