@@ -229,3 +229,11 @@ def test_tc_ex_matches_v1(name, mode):
         exp16 = _roottanh(exp) if mode == "o16act" else exp
         err = (got16[..., :n].float() - exp16).abs().max().item()
         assert err <= 6e-3 * exp16.abs().max().item() + 1e-5, f"{name}/{mode}: bf16 max err {err:.3e}"
+
+
+@pytest.mark.parametrize("name", ["convT4", "convT4_many", "3x3_48", "1x1_many", "5x5s2_c32", "convT4_c192"])
+def test_tc_ex_resident_weights(name, monkeypatch):
+    """LB_TC2_RESIDENT=1: the weights of one output phase stay in shared memory (opt-in variant of the persistent kernel)."""
+    monkeypatch.setenv("LB_TC2_RESIDENT", "1")
+    test_tc_ex_matches_v1(name, "both_aux")
+    test_tc_ex_matches_v1(name, "o16act")
