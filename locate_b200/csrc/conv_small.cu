@@ -1,21 +1,22 @@
-// Direct fp32 kernels for the layers whose channel counts are too small for a 128x64 tensor-core tile to make
-// sense: the discriminator stem (5x5/s2 3->3, 1x1 3->32, 1x1 3->29) and the generator's final 1x1 48->3, in all
-// three directions.  They are HBM-bound on the wide side of the layer (AI <= 16 flop/B), so the job is to touch
-// every activation once, with full-line accesses, the tiny weight held in shared memory and the neighbouring
-// elementwise ops fused: RootTanh on the input (forward), multiplication by RootTanh'(x) on the output (input gradient).
+// Direct fp32 kernels for the layers with a tiny channel count on one side -- the discriminator stem (5x5/s2 3->3,
+// 1x1 3->32, 1x1 3->29 + concat) in all three directions.  A 128x64 tensor-core tile makes no sense for K = 3, and the
+// layers are HBM-bound on their wide side (AI <= 16 flop/B), so the job is to touch every activation once with the
+// neighbouring elementwise ops fused: RootTanh on the input (forward), RootTanh'(x) on the output (input gradient), the
+// CatModule copy.
 //
 //   lb_conv_small:       out[p][n] = alpha * sum_{tap,k} act(in[p@tap][k]) * W(tap,k,n) (+bias[n])   [* act'(xpre[p][n])]
 //   lb_conv_small_wgrad: dw(tap,kg,kd) += sum_p act(gathered[p@tap][kg]) * dense[p][kd]
 // Geometry and weight addressing are those of lb_conv_gemm / lb_conv_wgrad (include/locate_b200.h).
 //
-// Both kernels walk tiles of consecutive pixels and move every activation between global and shared memory with
-// consecutive threads on consecutive addresses (a channels-last row of 3 or 29 floats per thread would waste 3/4 of
-// every 32-byte sector request); the arithmetic then reads shared memory only.
+// Every kernel is "one thread = one pixel, everything in registers": the narrow side (<= 4 channels) is a handful of
+// scalars, the wide side (<= 64) lives in up to 64 accumulators, the tiny weight sits in shared memory (alpha folded in)
+// and is read as warp-wide broadcasts.  There is no shared-memory staging of activations and no barrier after the weight
+// load: earlier tile-staged versions of these kernels spent their time in block barriers and index arithmetic
+// (0.6-2.3 TB/s, profiles/r1_small_micro_b192.txt).
 #include "common.cuh"
 
-#define SMALL_MAX_W 4096      // floats of weight held in shared memory (taps*K*N_pad)
-#define SMALL_TP 128          // pixels per tile (forward / input gradient)
 #define SMALL_THREADS 256
+#define SMALL_MAX_W 4096      // floats of weight held in shared memory
 
 struct SmallP {
   const float* in; const float* w; const float* alpha; const float* bias; const float* xpre; float* out;
@@ -24,13 +25,10 @@ struct SmallP {
   long long w_sk, w_sn, w_sty, w_stx;
   int growth_in;      // > 0: RootTanh(growth) applied to every input element on load
   int growth_out;     // > 0: result multiplied by RootTanh'(xpre[p][n])
-  int ngroups;        // ceil(out_c / 4)
-  int stage_in;       // 1x1 stride 1: the input tile is staged (activated once) in shared memory
   int cat;            // rows of `out` are [in (in_c, copied) | conv (out_c)]  (CatModule, merge.py:10-16)
-  int out_pitch;      // floats per staged output row: out_c (+ in_c when cat)
-  int tiles;
-  long long pixels;   // batch*out_h*out_w
-  LbFastDiv d_grp, d_w, d_h, d_ic, d_oc, d_pitch, d_pitch4;
+  int pointwise;      // 1x1, stride 1, pad 0: input pixel == output pixel
+  int pixels;         // batch*out_h*out_w (< 2^31, checked by the host)
+  LbFastDiv d_w, d_h;
 };
 
 __device__ __forceinline__ float small_act(float v, int growth) {
@@ -39,179 +37,191 @@ __device__ __forceinline__ float small_act(float v, int growth) {
 __device__ __forceinline__ float small_dact(float v, int growth) {
   return growth == 4 ? lb_roottanh_grad(v) : lb_roottanh_grad_g(v, 1.0f / growth);
 }
-
-// Tile copies between global rows (`cols` floats every `ld`) and shared rows (`cols` floats every `pitch`, starting at
-// column `col0` of the shared row).  Every thread keeps several independent accesses in flight: with one load per thread
-// per round trip these kernels sat at ~1 TB/s waiting on the long scoreboard (ncu, profiles/r1_small_kernels.txt).
-__device__ __forceinline__ bool tile_is_flat(const float* g, int ld, int pitch, int col0, int rows, int cols) {
-  return ld == cols && pitch == cols && col0 == 0 && !((rows * cols) & 3) && lb_aligned16(g);
-}
-template <typename F>
-__device__ __forceinline__ void tile_load(float* sdst, int pitch, int col0, const float* gsrc, int ld, int rows, int cols,
-                                          const LbFastDiv& dc, F f) {
-  if (tile_is_flat(gsrc, ld, pitch, col0, rows, cols)) {          // one contiguous block on both sides
-    const int n4 = (rows * cols) >> 2;
-    for (int base = threadIdx.x; base < n4; base += 4 * SMALL_THREADS) {
-      float4 v[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (base + j * SMALL_THREADS < n4) v[j] = lb_ld4(gsrc + 4 * (size_t)(base + j * SMALL_THREADS));
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (base + j * SMALL_THREADS < n4) {
-          float4 r = v[j];
-          r.x = f(r.x); r.y = f(r.y); r.z = f(r.z); r.w = f(r.w);
-          *reinterpret_cast<float4*>(sdst + 4 * (size_t)(base + j * SMALL_THREADS)) = r;
-        }
-    }
-    return;
+// source pixel of tap t along one axis (stride 1 or 2): false if the tap does not reach a source pixel
+__device__ __forceinline__ bool small_src(int mode, int stride, int sh, int pad, int o, int t, int extent, int& i) {
+  if (mode == 0) {
+    i = o * stride - pad + t;
+  } else {
+    const int v = o + pad - t;
+    if (v < 0 || (v & (stride - 1))) return false;
+    i = v >> sh;
   }
-  const int n = rows * cols;
-  for (int base = threadIdx.x; base < n; base += 4 * SMALL_THREADS) {
-    float v[4];
-    int r[4], c[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int e = base + j * SMALL_THREADS;
-      if (e < n) { lb_fast_divmod(dc, e, r[j], c[j]); v[j] = __ldg(gsrc + (size_t)r[j] * ld + c[j]); }
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (base + j * SMALL_THREADS < n) sdst[r[j] * pitch + col0 + c[j]] = f(v[j]);
-  }
-}
-__device__ __forceinline__ void tile_store(float* gdst, int ld, const float* ssrc, int rows, int cols, const LbFastDiv& dc,
-                                           const LbFastDiv& dc4) {   // shared pitch == cols
-  if (ld == cols && !((rows * cols) & 3) && lb_aligned16(gdst)) {
-    const int n4 = (rows * cols) >> 2;
-    for (int e = threadIdx.x; e < n4; e += SMALL_THREADS)
-      lb_st4(gdst + 4 * (size_t)e, *reinterpret_cast<const float4*>(ssrc + 4 * (size_t)e));
-    return;
-  }
-  if (!(cols & 3) && !(ld & 3) && lb_aligned16(gdst)) {
-    const int n4 = rows * (cols >> 2);
-    for (int e = threadIdx.x; e < n4; e += SMALL_THREADS) {
-      int r, c;
-      lb_fast_divmod(dc4, e, r, c);
-      lb_st4(gdst + (size_t)r * ld + 4 * c, *reinterpret_cast<const float4*>(ssrc + 4 * (size_t)e));
-    }
-    return;
-  }
-  const int n = rows * cols;
-  for (int e = threadIdx.x; e < n; e += SMALL_THREADS) {
-    int r, c;
-    lb_fast_divmod(dc, e, r, c);
-    gdst[(size_t)r * ld + c] = ssrc[e];
-  }
+  return i >= 0 && i < extent;
 }
 
-
-__global__ void __launch_bounds__(SMALL_THREADS, 4) k_conv_small(const SmallP p) {
+// ---- narrow INPUT (in_c <= 4): forward of the stem layers, input gradient of a wide -> 3 layer -------------------
+// NCH x 16 output columns per thread.  Shared weight wsm[tap][k][16*NCH] holds alpha * W (and, for a concat, identity
+// columns that copy the input), bsm the bias per column.
+template <int NCH>
+__global__ void __launch_bounds__(SMALL_THREADS) k_small_narrow_in(const SmallP p) {
+  constexpr int NC = 16 * NCH;
   extern __shared__ float4 sm4[];
-  float* sm = reinterpret_cast<float*>(sm4);
-  const int taps = p.kh * p.kw, npad = p.ngroups * 4;
-  float* ws = sm;                                           // [tap][k][npad]
-  float* s_out = ws + taps * p.in_c * npad;                 // [SMALL_TP][out_pitch]  (first holds xpre, then the result)
-  float* s_in = s_out + ((SMALL_TP * p.out_pitch + 3) & ~3);  // [SMALL_TP][in_c] (stage_in only)
-  for (int i = threadIdx.x; i < taps * p.in_c * npad; i += blockDim.x) {
-    const int n = i % npad, k = (i / npad) % p.in_c, tap = i / (npad * p.in_c);
-    ws[i] = n < p.out_c ? __ldg(p.w + k * p.w_sk + n * p.w_sn + (tap / p.kw) * p.w_sty + (tap % p.kw) * p.w_stx) : 0.0f;
-  }
+  float* wsm = reinterpret_cast<float*>(sm4);
+  const int taps = p.kh * p.kw;
+  float* bsm = wsm + taps * p.in_c * NC;
+  const int c0 = p.cat ? p.in_c : 0;                 // first conv column
+  const int cols = c0 + p.out_c;
   const float alpha = p.alpha ? __ldg(p.alpha) : 1.0f;
-  const int oc0 = p.cat ? p.in_c : 0;                       // first conv column of a staged output row
-  const int gi = p.growth_in, go = p.growth_out;
+  for (int i = threadIdx.x; i < taps * p.in_c * NC; i += blockDim.x) {
+    const int n = i % NC, k = (i / NC) % p.in_c, tap = i / (NC * p.in_c);
+    float v = 0.0f;
+    if (n < c0) v = (n == k) ? 1.0f : 0.0f;          // concat: column n copies input channel n (1x1 layers only)
+    else if (n < cols) v = alpha * __ldg(p.w + k * p.w_sk + (n - c0) * p.w_sn + (tap / p.kw) * p.w_sty + (tap % p.kw) * p.w_stx);
+    wsm[i] = v;
+  }
+  for (int n = threadIdx.x; n < NC; n += blockDim.x) bsm[n] = (p.bias && n >= c0 && n < cols) ? __ldg(p.bias + n - c0) : 0.0f;
+  __syncthreads();
   const int sh = p.stride == 2 ? 1 : 0;
-  auto act_in = [gi](float v) { return small_act(v, gi); };
-  auto ident = [](float v) { return v; };
-
-  for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
-    const long long pix0 = (long long)tile * SMALL_TP;
-    const int cnt = (int)min((long long)SMALL_TP, p.pixels - pix0);
-    __syncthreads();                                        // previous tile's copy-out has left s_out / s_in
-    // ---- stage: activated input rows (1x1), the copied input columns of a concat, RootTanh pre-activations
-    if (p.stage_in) tile_load(s_in, p.in_c, 0, p.in + pix0 * p.ld_in, p.ld_in, cnt, p.in_c, p.d_ic, act_in);
-    if (p.cat) tile_load(s_out, p.out_pitch, 0, p.in + pix0 * p.ld_in, p.ld_in, cnt, p.in_c, p.d_ic, ident);
-    if (go > 0) tile_load(s_out, p.out_pitch, oc0, p.xpre + pix0 * p.ld_xpre, p.ld_xpre, cnt, p.out_c, p.d_oc, ident);
-    __syncthreads();
-    // ---- compute: one item = one pixel x 4 consecutive output channels
-    for (int it = threadIdx.x; it < cnt * p.ngroups; it += blockDim.x) {
-      int pl, grp;
-      lb_fast_divmod(p.d_grp, it, pl, grp);
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-      if (p.stage_in) {
-        const float* a = s_in + pl * p.in_c;
-        const float* wt = ws + grp * 4;
-        for (int k = 0; k < p.in_c; ++k) {
-          const float av = a[k];
-          const float4 w4 = *reinterpret_cast<const float4*>(wt + (size_t)k * npad);
-          acc[0] = fmaf(av, w4.x, acc[0]); acc[1] = fmaf(av, w4.y, acc[1]);
-          acc[2] = fmaf(av, w4.z, acc[2]); acc[3] = fmaf(av, w4.w, acc[3]);
-        }
-      } else {
-        int t, ox, oy, b;
-        lb_fast_divmod(p.d_w, (int)(pix0 + pl), t, ox);     // pixels < 2^31 (checked by the host)
-        lb_fast_divmod(p.d_h, t, b, oy);
-        for (int ty = 0; ty < p.kh; ++ty) {
-          int iy;
-          if (p.mode == 0) iy = oy * p.stride - p.pad + ty;
-          else { const int v = oy + p.pad - ty; if (v < 0 || (v & (p.stride - 1))) continue; iy = v >> sh; }   // stride 1 | 2
-          if (iy < 0 || iy >= p.in_h) continue;
-          for (int tx = 0; tx < p.kw; ++tx) {
-            int ix;
-            if (p.mode == 0) ix = ox * p.stride - p.pad + tx;
-            else { const int v = ox + p.pad - tx; if (v < 0 || (v & (p.stride - 1))) continue; ix = v >> sh; }
-            if (ix < 0 || ix >= p.in_w) continue;
-            const float* src = p.in + ((size_t)(b * p.in_h + iy) * p.in_w + ix) * p.ld_in;
-            const float* wt = ws + (size_t)(ty * p.kw + tx) * p.in_c * npad + grp * 4;
-            for (int k = 0; k < p.in_c; ++k) {
-              const float av = small_act(__ldg(src + k), gi);
-              const float4 w4 = *reinterpret_cast<const float4*>(wt + (size_t)k * npad);
-              acc[0] = fmaf(av, w4.x, acc[0]); acc[1] = fmaf(av, w4.y, acc[1]);
-              acc[2] = fmaf(av, w4.z, acc[2]); acc[3] = fmaf(av, w4.w, acc[3]);
-            }
+  const int gi = p.growth_in, go = p.growth_out;
+  const bool vec_out = !(p.ld_out & 3) && lb_aligned16(p.out);
+  const int stride_t = gridDim.x * blockDim.x;
+  for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < p.pixels; pix += stride_t) {
+    float acc[NC];
+#pragma unroll
+    for (int n = 0; n < NC; ++n) acc[n] = bsm[n];
+    auto tap_fma = [&](const float* src, const float* wt) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k < p.in_c) {
+          const float a = small_act(__ldg(src + k), gi);
+          const float4* w4 = reinterpret_cast<const float4*>(wt + k * NC);
+#pragma unroll
+          for (int j = 0; j < NC / 4; ++j) {
+            const float4 wv = w4[j];
+            acc[4 * j + 0] = fmaf(a, wv.x, acc[4 * j + 0]); acc[4 * j + 1] = fmaf(a, wv.y, acc[4 * j + 1]);
+            acc[4 * j + 2] = fmaf(a, wv.z, acc[4 * j + 2]); acc[4 * j + 3] = fmaf(a, wv.w, acc[4 * j + 3]);
           }
         }
       }
-      float* o = s_out + pl * p.out_pitch + oc0 + grp * 4;
-      const int nv = min(4, p.out_c - grp * 4);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (j < nv) {
-          float r = acc[j] * alpha;
-          if (p.bias) r += __ldg(p.bias + grp * 4 + j);
-          if (go > 0) r *= small_dact(o[j], go);
-          o[j] = r;
+    };
+    if (p.pointwise) {
+      tap_fma(p.in + (size_t)pix * p.ld_in, wsm);
+    } else {
+      int t, ox, oy, b;
+      lb_fast_divmod(p.d_w, pix, t, ox);
+      lb_fast_divmod(p.d_h, t, b, oy);
+      for (int ty = 0; ty < p.kh; ++ty) {
+        int iy;
+        if (!small_src(p.mode, p.stride, sh, p.pad, oy, ty, p.in_h, iy)) continue;
+        for (int tx = 0; tx < p.kw; ++tx) {
+          int ix;
+          if (!small_src(p.mode, p.stride, sh, p.pad, ox, tx, p.in_w, ix)) continue;
+          tap_fma(p.in + ((size_t)(b * p.in_h + iy) * p.in_w + ix) * p.ld_in, wsm + (ty * p.kw + tx) * p.in_c * NC);
         }
       }
     }
-    __syncthreads();
-    // ---- copy out: full staged rows, consecutive threads on consecutive addresses
-    tile_store(p.out + pix0 * p.ld_out, p.ld_out, s_out, cnt, p.out_pitch, p.d_pitch, p.d_pitch4);
+    if (go > 0) {
+      const float* xr = p.xpre + (size_t)pix * p.ld_xpre;
+#pragma unroll
+      for (int n = 0; n < NC; ++n)
+        if (n < p.out_c) acc[n] *= small_dact(__ldg(xr + n), go);       // no concat on this path (checked by the host)
+    }
+    float* dst = p.out + (size_t)pix * p.ld_out;
+    if (vec_out) {
+#pragma unroll
+      for (int j = 0; j < NC / 4; ++j) {
+        if (4 * j + 3 < cols) lb_st4(dst + 4 * j, make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]));
+        else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) if (4 * j + i < cols) dst[4 * j + i] = acc[4 * j + i];
+        }
+      }
+    } else {
+#pragma unroll
+      for (int n = 0; n < NC; ++n) if (n < cols) dst[n] = acc[n];
+    }
   }
 }
 
-static size_t small_smem_bytes(const lb_conv_geom* g, int cat) {
-  const int ngroups = (g->out_c + 3) / 4;
-  const bool stage = g->kh == 1 && g->kw == 1 && g->stride == 1 && g->pad == 0;
-  const size_t out_floats = ((size_t)SMALL_TP * (g->out_c + (cat ? g->in_c : 0)) + 3) & ~(size_t)3;
-  return ((size_t)g->kh * g->kw * g->in_c * ngroups * 4 + out_floats + (stage ? (size_t)SMALL_TP * g->in_c : 0)) * sizeof(float);
+// ---- narrow OUTPUT (out_c <= 4): input gradient of the stem layers, forward of a wide -> 3 layer --------------------
+// wsm[tap][k] = alpha * W(tap, k, 0..3) as one float4
+__global__ void __launch_bounds__(SMALL_THREADS) k_small_narrow_out(const SmallP p) {
+  extern __shared__ float4 sm4[];
+  const int taps = p.kh * p.kw;
+  const float alpha = p.alpha ? __ldg(p.alpha) : 1.0f;
+  for (int i = threadIdx.x; i < taps * p.in_c; i += blockDim.x) {
+    const int k = i % p.in_c, tap = i / p.in_c;
+    float v[4];
+#pragma unroll
+    for (int n = 0; n < 4; ++n)
+      v[n] = n < p.out_c ? alpha * __ldg(p.w + k * p.w_sk + n * p.w_sn + (tap / p.kw) * p.w_sty + (tap % p.kw) * p.w_stx) : 0.0f;
+    sm4[i] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  __syncthreads();
+  const int sh = p.stride == 2 ? 1 : 0;
+  const int gi = p.growth_in, go = p.growth_out;
+  const bool vec_in = !(p.in_c & 3) && !(p.ld_in & 3) && lb_aligned16(p.in);
+  float b4[4];
+#pragma unroll
+  for (int n = 0; n < 4; ++n) b4[n] = (p.bias && n < p.out_c) ? __ldg(p.bias + n) : 0.0f;
+  const int stride_t = gridDim.x * blockDim.x;
+  for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < p.pixels; pix += stride_t) {
+    float a0 = b4[0], a1 = b4[1], a2 = b4[2], a3 = b4[3];
+    auto tap_fma = [&](const float* src, const float4* wt) {
+      if (vec_in) {
+        for (int k = 0; k < p.in_c; k += 4) {
+          const float4 x4 = lb_ld4(src + k);
+          const float xs[4] = {small_act(x4.x, gi), small_act(x4.y, gi), small_act(x4.z, gi), small_act(x4.w, gi)};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 wv = wt[k + i];
+            a0 = fmaf(xs[i], wv.x, a0); a1 = fmaf(xs[i], wv.y, a1); a2 = fmaf(xs[i], wv.z, a2); a3 = fmaf(xs[i], wv.w, a3);
+          }
+        }
+      } else {
+#pragma unroll 4
+        for (int k = 0; k < p.in_c; ++k) {
+          const float xv = small_act(__ldg(src + k), gi);
+          const float4 wv = wt[k];
+          a0 = fmaf(xv, wv.x, a0); a1 = fmaf(xv, wv.y, a1); a2 = fmaf(xv, wv.z, a2); a3 = fmaf(xv, wv.w, a3);
+        }
+      }
+    };
+    if (p.pointwise) {
+      tap_fma(p.in + (size_t)pix * p.ld_in, sm4);
+    } else {
+      int t, ox, oy, b;
+      lb_fast_divmod(p.d_w, pix, t, ox);
+      lb_fast_divmod(p.d_h, t, b, oy);
+      for (int ty = 0; ty < p.kh; ++ty) {
+        int iy;
+        if (!small_src(p.mode, p.stride, sh, p.pad, oy, ty, p.in_h, iy)) continue;
+        for (int tx = 0; tx < p.kw; ++tx) {
+          int ix;
+          if (!small_src(p.mode, p.stride, sh, p.pad, ox, tx, p.in_w, ix)) continue;
+          tap_fma(p.in + ((size_t)(b * p.in_h + iy) * p.in_w + ix) * p.ld_in, sm4 + (ty * p.kw + tx) * p.in_c);
+        }
+      }
+    }
+    float r[4] = {a0, a1, a2, a3};
+    float* dst = p.out + (size_t)pix * p.ld_out;
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      if (n < p.out_c) {
+        if (go > 0) r[n] *= small_dact(__ldg(p.xpre + (size_t)pix * p.ld_xpre + n), go);
+        dst[n] = r[n];
+      }
+    }
+  }
 }
+
+static bool small_pointwise(const lb_conv_geom* g) { return g->kh == 1 && g->kw == 1 && g->stride == 1 && g->pad == 0; }
 
 extern "C" int lb_conv_small_supported(const lb_conv_geom* g) {
   if (!g) return 0;
   if (g->stride != 1 && g->stride != 2) return 0;
-  const long long wf = (long long)g->kh * g->kw * g->in_c * ((g->out_c + 3) / 4 * 4);
-  // one side of the layer is tiny and the whole weight fits in shared memory (a 1024 -> 1 head on a 1x1 map is a dot
-  // product per sample: that stays a GEMM)
-  if (wf > SMALL_MAX_W || g->in_c > 64 || g->out_c > 64) return 0;
-  if (!(g->in_c <= 4 || g->out_c <= 4 || g->in_c * g->out_c <= 128)) return 0;
+  if (g->in_c < 1 || g->out_c < 1 || g->in_c > 64 || g->out_c > 64) return 0;
+  if (g->in_c > 4 && g->out_c > 4) return 0;                   // one side must be tiny
   const long long pixels = (long long)g->batch * g->out_h * g->out_w;
   if (pixels >= (1ll << 31) - (1ll << 24)) return 0;
-  return small_smem_bytes(g, 0) <= 48 * 1024 ? 1 : 0;
+  const long long taps = (long long)g->kh * g->kw;
+  // (a 1024 -> 1 head on a 1x1 map is a dot product per sample and stays a GEMM: in_c > 64)
+  if (g->in_c <= 4) return taps * g->in_c * 64 + 64 <= 3 * SMALL_MAX_W ? 1 : 0;
+  return taps * g->in_c * 4 <= 3 * SMALL_MAX_W ? 1 : 0;
 }
 
 // cat_input != 0: `out` points at the START of rows of in_c + out_c floats (row stride g->ld_out); the kernel writes the
-// input copy and the conv result of a CatModule in one pass (1x1 stride-1 layers only, no fused activations).
+// input copy and the conv result of a CatModule in one pass (1x1 stride-1 layers with in_c <= 4, no fused activations).
 extern "C" int lb_conv_small(const float* in, const float* w, const float* alpha, const float* bias, float* out,
                              const lb_conv_geom* g, int growth_in, const float* xpre, int ld_xpre, int growth_out,
                              int cat_input, lb_stream_t s) {
@@ -225,117 +235,149 @@ extern "C" int lb_conv_small(const float* in, const float* w, const float* alpha
   p.ld_in = g->ld_in; p.ld_out = g->ld_out; p.ld_xpre = ld_xpre;
   p.w_sk = g->w_sk; p.w_sn = g->w_sn; p.w_sty = g->w_sty; p.w_stx = g->w_stx;
   p.growth_in = growth_in; p.growth_out = growth_out;
-  p.ngroups = (g->out_c + 3) / 4;
-  p.pixels = (long long)g->batch * g->out_h * g->out_w;
-  p.tiles = (int)((p.pixels + SMALL_TP - 1) / SMALL_TP);
-  p.stage_in = (g->kh == 1 && g->kw == 1 && g->stride == 1 && g->pad == 0) ? 1 : 0;
+  p.pointwise = small_pointwise(g) ? 1 : 0;
   p.cat = cat_input ? 1 : 0;
-  if (p.cat) LB_REQUIRE(p.stage_in && growth_in == 0 && growth_out == 0 && g->ld_out >= g->in_c + g->out_c);
-  if (small_smem_bytes(g, p.cat) > 48 * 1024) return LB_EUNSUPPORTED;
-  p.out_pitch = g->out_c + (p.cat ? g->in_c : 0);
-  p.d_grp = lb_make_fastdiv(p.ngroups); p.d_w = lb_make_fastdiv(g->out_w); p.d_h = lb_make_fastdiv(g->out_h);
-  p.d_ic = lb_make_fastdiv(g->in_c); p.d_oc = lb_make_fastdiv(g->out_c);
-  p.d_pitch = lb_make_fastdiv(p.out_pitch); p.d_pitch4 = lb_make_fastdiv(p.out_pitch >= 4 ? p.out_pitch / 4 : 1);
-  const int grid = p.tiles < LB_SMS * 8 ? p.tiles : LB_SMS * 8;
-  k_conv_small<<<grid, SMALL_THREADS, small_smem_bytes(g, p.cat), lb_s(s)>>>(p);
+  p.pixels = (int)((long long)g->batch * g->out_h * g->out_w);
+  p.d_w = lb_make_fastdiv(g->out_w); p.d_h = lb_make_fastdiv(g->out_h);
+  const int taps = g->kh * g->kw;
+  const int grid = lb_grid_1d((size_t)p.pixels, SMALL_THREADS, 8);
+  if (g->in_c <= 4) {
+    if (p.cat) LB_REQUIRE(p.pointwise && growth_in == 0 && growth_out == 0 && g->ld_out >= g->in_c + g->out_c);
+    const int cols = g->out_c + (p.cat ? g->in_c : 0);
+    if (cols > 64) return LB_EUNSUPPORTED;
+    const int nch = (cols + 15) / 16;
+    const size_t smem = ((size_t)taps * g->in_c * 16 * nch + 16 * nch) * sizeof(float);
+    switch (nch) {
+      case 1: k_small_narrow_in<1><<<grid, SMALL_THREADS, smem, lb_s(s)>>>(p); break;
+      case 2: k_small_narrow_in<2><<<grid, SMALL_THREADS, smem, lb_s(s)>>>(p); break;
+      case 3: k_small_narrow_in<3><<<grid, SMALL_THREADS, smem, lb_s(s)>>>(p); break;
+      default: k_small_narrow_in<4><<<grid, SMALL_THREADS, smem, lb_s(s)>>>(p); break;
+    }
+  } else {
+    if (p.cat) return LB_EUNSUPPORTED;
+    const size_t smem = (size_t)taps * g->in_c * sizeof(float4);
+    k_small_narrow_out<<<grid, SMALL_THREADS, smem, lb_s(s)>>>(p);
+  }
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
 
 // ---- weight gradient: tiny output, reduction over every pixel ------------------------------------------------
-// A CTA walks tiles of WG_TP dense pixels.  Per tile the dense rows and the im2col rows of the gathered operand
-// (taps x g_c values per pixel, activated on the way in) are staged in shared memory with coalesced loads; thread e
-// then owns one weight element (tap, kg, kd) and accumulates over the tile's pixels from shared memory only.
+// One thread = one dense pixel, 16 x 4 accumulators in registers: "narrow" is the side with <= 4 channels, "wide" a
+// 16-wide chunk of the other side (blockIdx.y).  acc[w][n] += wide[w] * narrow[n]; at the end a recursive-halving warp
+// reduction, a shared-memory reduction across the CTA's warps and 64 global atomics per CTA.
+//   kNarrowDense = false: 1x1 layers with g_c <= 4: narrow = gathered pixel (g_c), wide = dense channels [16*chunk, +16)
+//   kNarrowDense = true : d_c <= 4: narrow = dense pixel, wide = im2col entries [16*chunk, +16) of (tap, kg) (tap-major)
 struct SmallWgP {
   const float* gath; const float* dense; float* dw;
   int g_h, g_w, g_c, d_h, d_w, d_c, kh, kw, stride, pad, ld_g, ld_d;
   long long w_sk, w_sn, w_sty, w_stx;
-  long long pixels; int tiles, n_elems, rows, growth_g;
-  LbFastDiv f_rows, f_dc, f_gc, f_kw, f_w, f_h;
+  int pixels, rows, growth_g;
+  LbFastDiv f_gc, f_kw, f_w, f_h;
 };
-#define WG_TP 64
-#define WG_MAX_ROWS 80
-__global__ void __launch_bounds__(256, 4) k_conv_small_wgrad(const SmallWgP p) {
-  __shared__ __align__(16) float sd[WG_TP * 32];                // dense rows, pitch d_c (<= 32)
-  __shared__ __align__(16) float sg[WG_TP * WG_MAX_ROWS];       // im2col rows of the gathered operand, pitch rows (<= 80)
-  __shared__ int s_iy[WG_TP], s_ix[WG_TP], s_b[WG_TP];
-  const int e = threadIdx.x;
-  const bool live = e < p.n_elems;
-  int kd = 0, row = 0;
-  if (live) lb_fast_divmod(p.f_dc, e, row, kd);      // e = row * d_c + kd, row = (ty*kw + tx)*g_c + kg
-  const bool pointwise = p.kh == 1 && p.kw == 1 && p.stride == 1 && p.pad == 0;   // gathered pixel == dense pixel
+template <bool kNarrowDense>
+__global__ void __launch_bounds__(SMALL_THREADS) k_small_wgrad(const SmallWgP p) {
+  __shared__ float s_red[64];
+  if (threadIdx.x < 64) s_red[threadIdx.x] = 0.0f;
+  __syncthreads();
+  const int w0 = blockIdx.y * 16;                    // first wide index of this chunk
   const int gg = p.growth_g;
-  auto act_g = [gg](float v) { return small_act(v, gg); };
-  auto ident = [](float v) { return v; };
-  float acc = 0.0f;
-  for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
-    const long long base = (long long)tile * WG_TP;
-    const int cnt = (int)min((long long)WG_TP, p.pixels - base);
-    __syncthreads();
-    tile_load(sd, p.d_c, 0, p.dense + base * p.ld_d, p.ld_d, cnt, p.d_c, p.f_dc, ident);
-    if (pointwise) {
-      tile_load(sg, p.rows, 0, p.gath + base * p.ld_g, p.ld_g, cnt, p.g_c, p.f_gc, act_g);
-    } else {
-      if (threadIdx.x < cnt) {
-        int t, ox, oy, b;
-        lb_fast_divmod(p.f_w, (int)(base + threadIdx.x), t, ox);
-        lb_fast_divmod(p.f_h, t, b, oy);
-        s_b[threadIdx.x] = b;
-        s_iy[threadIdx.x] = oy * p.stride - p.pad;
-        s_ix[threadIdx.x] = ox * p.stride - p.pad;
-      }
-      __syncthreads();
-      const int n = cnt * p.rows;
-      for (int i0 = threadIdx.x; i0 < n; i0 += 2 * 256) {
-        float v[2];
+  float acc[16][4];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {                // 2 independent gathers in flight per thread
-          const int i = i0 + j * 256;
-          v[j] = 0.0f;
-          if (i < n) {
-            int r, rw, tap, kg, ty, tx;
-            lb_fast_divmod(p.f_rows, i, r, rw);
-            lb_fast_divmod(p.f_gc, rw, tap, kg);
-            lb_fast_divmod(p.f_kw, tap, ty, tx);
-            const int iy = s_iy[r] + ty, ix = s_ix[r] + tx;
-            if (iy >= 0 && iy < p.g_h && ix >= 0 && ix < p.g_w)
-              v[j] = __ldg(p.gath + ((size_t)(s_b[r] * p.g_h + iy) * p.g_w + ix) * p.ld_g + kg);
-          }
-        }
+  for (int i = 0; i < 16; ++i)
 #pragma unroll
-        for (int j = 0; j < 2; ++j)
-          if (i0 + j * 256 < n) sg[i0 + j * 256] = small_act(v[j], gg);     // act(0) = 0: padding stays zero
-      }
-    }
-    __syncthreads();
-    if (live) {
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-      const float* gp = sg + row;
-      const float* dp = sd + kd;
-      int r = 0;
-      for (; r + 4 <= cnt; r += 4) {
-        a0 = fmaf(gp[(r + 0) * p.rows], dp[(r + 0) * p.d_c], a0);
-        a1 = fmaf(gp[(r + 1) * p.rows], dp[(r + 1) * p.d_c], a1);
-        a2 = fmaf(gp[(r + 2) * p.rows], dp[(r + 2) * p.d_c], a2);
-        a3 = fmaf(gp[(r + 3) * p.rows], dp[(r + 3) * p.d_c], a3);
-      }
-      for (; r < cnt; ++r) a0 = fmaf(gp[r * p.rows], dp[r * p.d_c], a0);
-      acc += (a0 + a1) + (a2 + a3);
+    for (int n = 0; n < 4; ++n) acc[i][n] = 0.0f;
+  // wide-entry decode for the im2col form is per chunk, not per pixel: entry w = (tap, kg), tap = (ty, tx)
+  int e_ty[16], e_tx[16], e_kg[16];
+  if (kNarrowDense) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      int tap, kg, ty, tx;
+      lb_fast_divmod(p.f_gc, min(w0 + i, p.rows - 1), tap, kg);
+      lb_fast_divmod(p.f_kw, tap, ty, tx);
+      e_ty[i] = ty; e_tx[i] = tx; e_kg[i] = kg;
     }
   }
-  if (live) {
-    int tap, kg, ty, tx;
-    lb_fast_divmod(p.f_gc, row, tap, kg);
-    lb_fast_divmod(p.f_kw, tap, ty, tx);
-    atomicAdd(p.dw + kg * p.w_sk + kd * p.w_sn + ty * p.w_sty + tx * p.w_stx, acc);
+  const int stride_t = gridDim.x * blockDim.x;
+  for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < p.pixels; pix += stride_t) {
+    float nv[4], wv[16];
+    if (!kNarrowDense) {
+      const float* gs = p.gath + (size_t)pix * p.ld_g;
+      const float* ds = p.dense + (size_t)pix * p.ld_d + w0;
+#pragma unroll
+      for (int n = 0; n < 4; ++n) nv[n] = n < p.g_c ? small_act(__ldg(gs + n), gg) : 0.0f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) wv[i] = w0 + i < p.d_c ? __ldg(ds + i) : 0.0f;
+    } else {
+      const float* ds = p.dense + (size_t)pix * p.ld_d;
+#pragma unroll
+      for (int n = 0; n < 4; ++n) nv[n] = n < p.d_c ? __ldg(ds + n) : 0.0f;
+      int t, ox, oy, b;
+      lb_fast_divmod(p.f_w, pix, t, ox);
+      lb_fast_divmod(p.f_h, t, b, oy);
+      const int iy0 = oy * p.stride - p.pad, ix0 = ox * p.stride - p.pad;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int iy = iy0 + e_ty[i], ix = ix0 + e_tx[i];
+        float v = 0.0f;
+        if (w0 + i < p.rows && iy >= 0 && iy < p.g_h && ix >= 0 && ix < p.g_w)
+          v = small_act(__ldg(p.gath + ((size_t)(b * p.g_h + iy) * p.g_w + ix) * p.ld_g + e_kg[i]), gg);   // act(0) = 0
+        wv[i] = v;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+#pragma unroll
+      for (int n = 0; n < 4; ++n) acc[i][n] = fmaf(wv[i], nv[n], acc[i][n]);
+  }
+  // Warp reduction of the 64 per-thread sums by recursive halving: at step s a lane keeps half of its values and trades
+  // the other half with lane ^ (16 >> s), so 32+16+8+4+2 = 62 shuffles (not 64 x 5) leave lane L with the warp totals of
+  // entries 2L and 2L+1.
+  const int lane = threadIdx.x & 31;
+  float v[64];
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+#pragma unroll
+    for (int n = 0; n < 4; ++n) v[i * 4 + n] = acc[i][n];
+#pragma unroll
+  for (int half = 32, bit = 16; half >= 2; half >>= 1, bit >>= 1) {
+    const bool upper = (lane & bit) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = upper ? v[i] : v[i + half];
+      const float keep = upper ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+    }
+  }
+  if (v[0] != 0.0f) atomicAdd(&s_red[2 * lane], v[0]);
+  if (v[1] != 0.0f) atomicAdd(&s_red[2 * lane + 1], v[1]);
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int i = threadIdx.x >> 2, n = threadIdx.x & 3;
+    const int wi = w0 + i;
+    const float v = s_red[threadIdx.x];
+    if (v != 0.0f) {
+      if (!kNarrowDense) {                             // wide = dense channel kd, narrow = gathered channel kg (one tap)
+        if (wi < p.d_c && n < p.g_c) atomicAdd(p.dw + n * p.w_sk + wi * p.w_sn, v);
+      } else if (wi < p.rows && n < p.d_c) {           // wide = (tap, kg), narrow = dense channel kd
+        int tap, kg, ty, tx;
+        lb_fast_divmod(p.f_gc, wi, tap, kg);
+        lb_fast_divmod(p.f_kw, tap, ty, tx);
+        atomicAdd(p.dw + kg * p.w_sk + n * p.w_sn + ty * p.w_sty + tx * p.w_stx, v);
+      }
+    }
   }
 }
 
 extern "C" int lb_conv_small_wgrad_supported(const lb_conv_geom* g) {
   if (!g || g->mode != 0) return 0;
-  const long long rows = (long long)g->kh * g->kw * g->in_c;
+  if (g->stride != 1 && g->stride != 2) return 0;
   const long long pixels = (long long)g->batch * g->out_h * g->out_w;
-  return (rows * g->out_c <= 256 && rows <= WG_MAX_ROWS && g->out_c <= 32 && pixels < (1ll << 31) - (1ll << 24)) ? 1 : 0;
+  if (pixels >= (1ll << 31) - (1ll << 24)) return 0;
+  const bool pointwise = small_pointwise(g);
+  if (pointwise && g->in_c <= 4 && g->out_c <= 1024) return 1;
+  if (g->out_c <= 4 && (long long)g->kh * g->kw * g->in_c <= 1024) return 1;
+  return 0;
 }
 // geom as lb_conv_wgrad: in_* = gathered operand, out_* = dense operand; dw in the master layout (+=, caller zeroes);
 // growth_gathered > 0 applies RootTanh to the gathered operand on load (the layer's pre-activation)
@@ -348,15 +390,18 @@ extern "C" int lb_conv_small_wgrad(const float* gathered, const float* dense, fl
   p.g_h = g->in_h; p.g_w = g->in_w; p.g_c = g->in_c; p.d_h = g->out_h; p.d_w = g->out_w; p.d_c = g->out_c;
   p.kh = g->kh; p.kw = g->kw; p.stride = g->stride; p.pad = g->pad; p.ld_g = g->ld_in; p.ld_d = g->ld_out;
   p.w_sk = g->w_sk; p.w_sn = g->w_sn; p.w_sty = g->w_sty; p.w_stx = g->w_stx;
-  p.pixels = (long long)g->batch * g->out_h * g->out_w;
+  p.pixels = (int)((long long)g->batch * g->out_h * g->out_w);
   p.rows = g->kh * g->kw * g->in_c;
-  p.n_elems = p.rows * g->out_c;
   p.growth_g = growth_gathered;
-  p.tiles = (int)((p.pixels + WG_TP - 1) / WG_TP);
-  p.f_rows = lb_make_fastdiv(p.rows); p.f_dc = lb_make_fastdiv(g->out_c); p.f_gc = lb_make_fastdiv(g->in_c);
-  p.f_kw = lb_make_fastdiv(g->kw); p.f_w = lb_make_fastdiv(g->out_w); p.f_h = lb_make_fastdiv(g->out_h);
-  const int grid = p.tiles < LB_SMS * 6 ? p.tiles : LB_SMS * 6;
-  k_conv_small_wgrad<<<grid, 256, 0, lb_s(s)>>>(p);
+  p.f_gc = lb_make_fastdiv(g->in_c); p.f_kw = lb_make_fastdiv(g->kw);
+  p.f_w = lb_make_fastdiv(g->out_w); p.f_h = lb_make_fastdiv(g->out_h);
+  const bool narrow_gathered = small_pointwise(g) && g->in_c <= 4;
+  const int chunks = narrow_gathered ? (g->out_c + 15) / 16 : (p.rows + 15) / 16;
+  int gx = lb_grid_1d((size_t)p.pixels, SMALL_THREADS, chunks >= 4 ? 1 : 2);   // many pixels per thread: the final reduction is a fixed cost
+  if (chunks > 65535) return LB_EUNSUPPORTED;
+  dim3 grid(gx, chunks);
+  if (narrow_gathered) k_small_wgrad<false><<<grid, SMALL_THREADS, 0, lb_s(s)>>>(p);
+  else k_small_wgrad<true><<<grid, SMALL_THREADS, 0, lb_s(s)>>>(p);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
