@@ -273,6 +273,7 @@ struct SmallWgP {
   int g_h, g_w, g_c, d_h, d_w, d_c, kh, kw, stride, pad, ld_g, ld_d;
   long long w_sk, w_sn, w_sty, w_stx;
   int pixels, rows, growth_g;
+  int d_shift, d_vec;   // dense rows start d_shift floats before `dense` on a 16-byte boundary; d_vec: float4 loads usable
   LbFastDiv f_gc, f_kw, f_w, f_h;
 };
 template <bool kNarrowDense>
@@ -302,12 +303,22 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_small_wgrad(const SmallWgP p)
   for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < p.pixels; pix += stride_t) {
     float nv[4], wv[16];
     if (!kNarrowDense) {
+      // wide index = column of the 16-byte aligned dense row (a concat slice starts d_shift floats into it); columns
+      // outside [d_shift, d_shift + d_c) are dropped when the sums are written
       const float* gs = p.gath + (size_t)pix * p.ld_g;
-      const float* ds = p.dense + (size_t)pix * p.ld_d + w0;
+      const float* ds = p.dense - p.d_shift + (size_t)pix * p.ld_d + w0;
 #pragma unroll
       for (int n = 0; n < 4; ++n) nv[n] = n < p.g_c ? small_act(__ldg(gs + n), gg) : 0.0f;
+      if (p.d_vec) {                                   // a thread reads its own row: 16-byte loads touch each sector twice,
+#pragma unroll                                         // 4-byte loads eight times (the L1 tag rate was the limiter)
+        for (int j = 0; j < 4; ++j) {
+          const float4 d4 = w0 + 4 * j < p.ld_d ? lb_ld4(ds + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          wv[4 * j] = d4.x; wv[4 * j + 1] = d4.y; wv[4 * j + 2] = d4.z; wv[4 * j + 3] = d4.w;
+        }
+      } else {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) wv[i] = w0 + i < p.d_c ? __ldg(ds + i) : 0.0f;
+        for (int i = 0; i < 16; ++i) wv[i] = w0 + i < p.d_shift + p.d_c ? __ldg(ds + i) : 0.0f;
+      }
     } else {
       const float* ds = p.dense + (size_t)pix * p.ld_d;
 #pragma unroll
@@ -357,8 +368,9 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_small_wgrad(const SmallWgP p)
     const int wi = w0 + i;
     const float v = s_red[threadIdx.x];
     if (v != 0.0f) {
-      if (!kNarrowDense) {                             // wide = dense channel kd, narrow = gathered channel kg (one tap)
-        if (wi < p.d_c && n < p.g_c) atomicAdd(p.dw + n * p.w_sk + wi * p.w_sn, v);
+      if (!kNarrowDense) {                             // wide = dense row column, narrow = gathered channel kg (one tap)
+        const int kd = wi - p.d_shift;
+        if (kd >= 0 && kd < p.d_c && n < p.g_c) atomicAdd(p.dw + n * p.w_sk + kd * p.w_sn, v);
       } else if (wi < p.rows && n < p.d_c) {           // wide = (tap, kg), narrow = dense channel kd
         int tap, kg, ty, tx;
         lb_fast_divmod(p.f_gc, wi, tap, kg);
@@ -396,7 +408,13 @@ extern "C" int lb_conv_small_wgrad(const float* gathered, const float* dense, fl
   p.f_gc = lb_make_fastdiv(g->in_c); p.f_kw = lb_make_fastdiv(g->kw);
   p.f_w = lb_make_fastdiv(g->out_w); p.f_h = lb_make_fastdiv(g->out_h);
   const bool narrow_gathered = small_pointwise(g) && g->in_c <= 4;
-  const int chunks = narrow_gathered ? (g->out_c + 15) / 16 : (p.rows + 15) / 16;
+  p.d_shift = 0; p.d_vec = 0;
+  if (narrow_gathered && !(g->ld_out & 3)) {           // dense rows are 16-byte aligned up to a fixed offset of the base
+    p.d_shift = (int)((reinterpret_cast<uintptr_t>(dense) & 15) / 4);
+    p.d_vec = (reinterpret_cast<uintptr_t>(dense) & 3) == 0 && p.d_shift + g->out_c <= g->ld_out ? 1 : 0;
+    if (!p.d_vec) p.d_shift = 0;
+  }
+  const int chunks = narrow_gathered ? (p.d_shift + g->out_c + 15) / 16 : (p.rows + 15) / 16;
   int gx = lb_grid_1d((size_t)p.pixels, SMALL_THREADS, chunks >= 4 ? 1 : 2);   // many pixels per thread: the final reduction is a fixed cost
   if (chunks > 65535) return LB_EUNSUPPORTED;
   dim3 grid(gx, chunks);

@@ -153,3 +153,21 @@ def test_small_fused_cat(b, h, w, cin, cout):
     assert torch.equal(got[..., :cin], x)
     err = (got - ref).abs().max().item()
     assert err <= 1e-4 * ref.abs().max().item() + 1e-5
+
+
+def test_small_wgrad_concat_slice():
+    """Weight gradient of the D stem's concat conv: the dense operand is the channel slice [3:32] of a 32-wide gradient
+    (rows 16-byte aligned, slice start not) -- the aligned-row float4 path with a column shift."""
+    gen = torch.Generator().manual_seed(21)
+    b, h, w, cin, cout = 5, 16, 16, 3, 29
+    x = torch.randn((b, h, w, cin), generator=gen).to(DEV)
+    gfull = torch.randn((b, h, w, cin + cout), generator=gen).to(DEV)
+    g = geom(b, h, w, cin, h, w, cout, 1, 1, 1, 0, 0, cin, cin + cout, (1, cin, 1, 1))
+    ref = torch.zeros((cout, cin, 1, 1), device=DEV)
+    got = torch.zeros((cout, cin, 1, 1), device=DEV)
+    dense_ptr = gfull.data_ptr() + 4 * cin
+    call("lb_conv_wgrad", ptr(x), dense_ptr, ptr(ref), ctypes.byref(g))
+    call("lb_conv_small_wgrad", ptr(x), dense_ptr, ptr(got), ctypes.byref(g), 0)
+    torch.cuda.synchronize()
+    err = (got - ref).abs().max().item()
+    assert err <= 2e-4 * ref.abs().max().item() + 1e-5
