@@ -28,6 +28,23 @@ __global__ void __launch_bounds__(256) k_featpool_fwd(const float* __restrict__ 
     y[((size_t)b * q.hw + (size_t)pj * q.m + pm) * q.c_out + o] = acc * inv;
   }
 }
+// r == 2 (every use on the reference's path: C -> C/2) with 4 input channels per thread: two 16-byte loads, two 8-byte
+// stores (channels ci..ci+3 are outputs (o, o+1) of pixel groups pj = 0 and pj = 1).  d_c = c_in / 4 here.
+__global__ void __launch_bounds__(256) k_featpool_fwd_r2v4(const float* __restrict__ x, float* __restrict__ y, int n_items, const FeatPoolIdx q) {
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += stride) {
+    int t, c4, b, pm;
+    lb_fast_divmod(q.d_c, i, t, c4);
+    lb_fast_divmod(q.d_m, t, b, pm);
+    const float* src = x + ((size_t)b * q.hw + (size_t)pm * 2) * q.c_in + 4 * c4;
+    const float4 a = lb_ld4(src), c = lb_ld4(src + q.c_in);
+    const int o = 2 * c4;                                   // ci = 4*c4 + {0,1,2,3} -> (o, pj) = (2*c4, 0), (2*c4, 1), (2*c4+1, 0), (2*c4+1, 1)
+    float* r0 = y + ((size_t)b * q.hw + pm) * q.c_out + o;              // pj = 0
+    float* r1 = y + ((size_t)b * q.hw + q.m + pm) * q.c_out + o;        // pj = 1
+    *reinterpret_cast<float2*>(r0) = make_float2(0.5f * (a.x + c.x), 0.5f * (a.z + c.z));
+    *reinterpret_cast<float2*>(r1) = make_float2(0.5f * (a.y + c.y), 0.5f * (a.w + c.w));
+  }
+}
 __global__ void __launch_bounds__(256) k_featpool_bwd(const float* __restrict__ g, float* __restrict__ dx, int n_in, const FeatPoolIdx q) {
   const int stride = gridDim.x * blockDim.x;
   const float inv = 1.0f / q.r;
@@ -84,8 +101,14 @@ extern "C" int lb_featpool_fwd(const float* x, float* y, int batch, int h, int w
   LB_REQUIRE(x && y && batch > 0 && h > 0 && w > 0 && c_out > 0 && c_in % c_out == 0);
   const size_t n = (size_t)batch * h * w * c_out;
   FeatPoolIdx q;
-  if (featpool_idx(&q, batch, h, w, c_in, c_out, c_in, n) == LB_OK)
-    k_featpool_fwd<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(x, y, (int)n, q);
+  if (featpool_idx(&q, batch, h, w, c_in, c_out, c_in, n) == LB_OK) {
+    if (q.r == 2 && !(c_in & 3) && lb_aligned16(x) && !(reinterpret_cast<uintptr_t>(y) & 7)) {
+      q.d_c = lb_make_fastdiv(c_in / 4);
+      k_featpool_fwd_r2v4<<<lb_grid_1d(n / 4, 256), 256, 0, lb_s(s)>>>(x, y, (int)(n / 4), q);     // n = B*m*c_in outputs, 4 per item
+    } else {
+      k_featpool_fwd<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(x, y, (int)n, q);
+    }
+  }
   else
     k_featpool_fwd_generic<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(x, y, n, h * w, c_in, c_out, c_in / c_out);
   LB_LAUNCH_CHECK();
