@@ -411,9 +411,36 @@ static int transpose_batched(const float* x, float* y, int batch, int rows, int 
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
+// Few channels (RGB images at the model boundary): a 32x32 tile transpose would run 3 of its 32 rows.  One thread = one
+// pixel: the C plane reads / writes are coalesced across threads, the C interleaved values are one short contiguous run.
+template <bool kToNhwc>
+__global__ void __launch_bounds__(256) k_layout_small_c(const float* __restrict__ x, float* __restrict__ y, int c, int hw, size_t pixels,
+                                                       LbFastDiv d_hw) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < pixels; i += stride) {
+    int b, p;
+    lb_fast_divmod(d_hw, (int)i, b, p);                 // pixels < 2^31 (checked by the host)
+    const size_t plane0 = (size_t)b * c * hw + p;       // NCHW offset of (b, 0, p)
+    const size_t inter0 = i * c;                        // NHWC offset of (b, p, 0)
+    for (int k = 0; k < c; ++k) {
+      if (kToNhwc) y[inter0 + k] = __ldg(x + plane0 + (size_t)k * hw);
+      else y[plane0 + (size_t)k * hw] = __ldg(x + inter0 + k);
+    }
+  }
+}
+static int layout_small_c(const float* x, float* y, int batch, int c, int hw, bool to_nhwc, lb_stream_t s) {
+  const size_t pixels = (size_t)batch * hw;
+  LB_REQUIRE(x && y && batch > 0 && c > 0 && hw > 0 && pixels < ((size_t)1 << 31) - ((size_t)1 << 24));
+  if (to_nhwc) k_layout_small_c<true><<<lb_grid_1d(pixels, 256), 256, 0, lb_s(s)>>>(x, y, c, hw, pixels, lb_make_fastdiv(hw));
+  else k_layout_small_c<false><<<lb_grid_1d(pixels, 256), 256, 0, lb_s(s)>>>(x, y, c, hw, pixels, lb_make_fastdiv(hw));
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
 extern "C" int lb_nchw_to_nhwc(const float* x, float* y, int batch, int c, int hw, lb_stream_t s) {
+  if (c <= 8 && (size_t)batch * hw < ((size_t)1 << 31) - ((size_t)1 << 24)) return layout_small_c(x, y, batch, c, hw, true, s);
   return transpose_batched(x, y, batch, c, hw, s);
 }
 extern "C" int lb_nhwc_to_nchw(const float* x, float* y, int batch, int c, int hw, lb_stream_t s) {
+  if (c <= 8 && (size_t)batch * hw < ((size_t)1 << 31) - ((size_t)1 << 24)) return layout_small_c(x, y, batch, c, hw, false, s);
   return transpose_batched(x, y, batch, hw, c, s);
 }

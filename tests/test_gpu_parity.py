@@ -342,3 +342,14 @@ def test_step_vs_oracle_default_width():
     for k, p in gen.named_parameters():
         if p.requires_grad and gs[k].grad is not None:
             close(p.grad, gs[k].grad, rtol=5e-3, atol_frac=1e-3, what="G grad " + k)
+
+
+@pytest.mark.parametrize("b,c,h,w", [(3, 3, 16, 12), (2, 1, 8, 8), (2, 40, 9, 7), (5, 8, 4, 4)])
+def test_layout_round_trip(b, c, h, w):
+    """NCHW <-> channels-last at the model boundary (few-channel and tiled-transpose kernels)."""
+    x = torch.randn((b, c, h, w), generator=torch.Generator().manual_seed(3)).to(DEV)
+    cl = ops._to_channels_last(x)
+    assert cl.shape == x.shape and torch.equal(cl, x)                      # same logical tensor
+    assert torch.equal(cl.permute(0, 2, 3, 1).contiguous(), x.permute(0, 2, 3, 1).contiguous())
+    back = ops.to_nchw(cl)
+    assert back.is_contiguous() and torch.equal(back, x)
