@@ -66,7 +66,8 @@ class GanTrainer:
             h.wait()
         opt.step()
 
-    def d_step(self, real, aug, z):
+    def d_step(self, real, aug, z, update=True):
+        """main.py:142-156 (+ :158-159 when `update`): D forward on real / generated / augmented, loss, backward."""
         dev = real.device
         with torch.no_grad():
             fake = self.gen(z)
@@ -83,10 +84,12 @@ class GanTrainer:
         call("lb_d_loss", ptr(d_true), ptr(d_fake), ptr(d_aug), ptr(sums), n, n_global, self.penalty_gamma, ptr(out),
              ptr(grads[0]), ptr(grads[1]), ptr(grads[2]))
         torch.autograd.backward([d_true, d_fake, d_aug], [grads[0], grads[1], grads[2]])
-        self._reduce_and_step(self.d_opt)
+        if update:
+            self._reduce_and_step(self.d_opt)
         return out            # [hinge part (local share of the global mean), penalty, 0]
 
-    def g_step(self, z):
+    def g_step(self, z, update=True):
+        """main.py:160-171: generator forward through the frozen discriminator, loss, backward (+ Nadam when `update`)."""
         dev = z.device
         self.dis.requires_grad_(False)
         self.gen.zero_grad()
@@ -96,9 +99,32 @@ class GanTrainer:
         grad = torch.empty(n, dtype=torch.float32, device=dev)
         call("lb_g_loss", ptr(d_fake), n, float(n * dist.world_size()), ptr(out), ptr(grad))
         torch.autograd.backward([d_fake], [grad])
-        self._reduce_and_step(self.g_opt)
+        if update:
+            self._reduce_and_step(self.g_opt)
         self.dis.requires_grad_(True)
         return out
+
+    def run_reference_schedule(self, batches, miniter=1, minibatches=1, diters=1, noise_fn=None):
+        """The reference's loop body (main.py:137-172) over an iterable of (real, aug) batches, with ITS schedule:
+        the discriminator gradient is recomputed (zero_grad + backward) on every batch but Nadam steps only when
+        i % miniter == 0 (i counts from 1), and on every `diters`-th such step the generator runs `minibatches`
+        zero_grad + backward passes on the SAME noise before one Nadam step -- so, exactly as in the reference, only
+        the last of those gradients is applied (each pass still advances every spectral-norm u/v by one iteration).  Yields (i, d_out, g_out or None) per batch.
+        `bench.py` / `step()` measure the miniter = minibatches = diters = 1 case."""
+        g_out = None
+        for i, (real, aug) in enumerate(batches, 1):
+            z = noise_fn(real.shape[0]) if noise_fn is not None else torch.randn(
+                (real.shape[0], CFG.INPUT_VECTOR_Z), device=real.device)
+            d_out = self.d_step(real, aug, z, update=False)
+            stepped = None
+            if i % miniter == 0:
+                self._reduce_and_step(self.d_opt)
+                if (i // miniter) % diters == 0:
+                    for _ in range(minibatches):
+                        g_out = self.g_step(z, update=False)
+                    self._reduce_and_step(self.g_opt)
+                    stepped = g_out
+            yield i, d_out, stepped
 
     def _eager_step(self, real, aug, z):
         d_out = self.d_step(real, aug, z)

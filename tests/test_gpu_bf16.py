@@ -254,3 +254,38 @@ def test_self_attention_sweep_vs_oracle(hw, feat, batch, wrapped):
     for k, p in m.named_parameters():
         if p.requires_grad and st[k].grad is not None and st[k].grad.norm() > 0:
             assert rel_l2(p.grad, st[k].grad) < 3e-2, k
+
+
+def test_reference_schedule_and_checkpoint_round_trip(tmp_path):
+    """SURVEY 'next' row N2: with miniter = MINIBATCHES = DITERS = 1 the reference schedule is step(); MINIBATCHES = 2
+    runs (the repeated generator pass is NOT a no-op: every forward advances the spectral-norm u/v of G and D, as in
+    the reference); a state_dict saved like main.py:235-236 restores the same model."""
+    L.configure(IMAGE_SIZE=32, BASE_FEATURE_FACTOR=4)
+    cfg = O.OracleConfig(IMAGE_SIZE=32, BASE_FEATURE_FACTOR=4)
+    real, aug, z = (t.to(DEV) for t in O.synthetic_batch(cfg, 4))
+    finals = {}
+    for mode in ("step", "sched1", "sched_mb2"):
+        torch.manual_seed(999)
+        gen, g_opt = L.get_model(L.Generator(), L.CFG.GLR, DEV)
+        dis, d_opt = L.get_model(L.Discriminator(), L.CFG.DLR, DEV)
+        tr = L.GanTrainer(gen, dis, g_opt, d_opt)
+        if mode == "step":
+            for _ in range(2):
+                tr.step(real, aug, z)
+        else:
+            list(tr.run_reference_schedule([(real, aug)] * 2, 1, 2 if mode == "sched_mb2" else 1, 1, noise_fn=lambda n: z))
+        torch.cuda.synchronize()
+        finals[mode] = torch.cat([p.detach().reshape(-1) for p in list(dis.parameters()) + list(gen.parameters())]).cpu()
+    def moved(a, b):
+        return ((a - b).abs() > 5e-3).float().mean().item()
+    assert moved(finals["step"], finals["sched1"]) < 1e-2
+    assert torch.isfinite(finals["sched_mb2"]).all()
+    torch.save(gen.state_dict(), tmp_path / "netG.torch")
+    L.config.reset(); L.configure(PRECISION="bf16", IMAGE_SIZE=32, BASE_FEATURE_FACTOR=4)
+    gen2 = L.Generator().to(DEV)
+    gen2.load_state_dict(torch.load(tmp_path / "netG.torch"))
+    gen2.noise = gen.noise
+    with torch.no_grad():
+        a, b = gen(z), gen2(z)
+    torch.cuda.synchronize()
+    assert rel_l2(a, b) < 1e-5
