@@ -53,10 +53,14 @@ int lb_hinge_fwd(const float* x, float* y, size_t n, lb_stream_t stream);
 int lb_hinge_bwd(const float* x, const float* g, float* dx, size_t n, lb_stream_t stream);
 
 /* ---- whole-tensor norm ("InPlaceNorm")                                libs/inplace_norm.py:7-45
- * stats pipeline: lb_norm_stats accumulates (sum, sum of squares) of x into sums[2] (double,
- * caller zeroes it; in data parallel the caller all-reduces sums across ranks), then
- * lb_norm_finalize turns (sums, n_total) into stats[4] = {mean, std(unbiased), 1/std, n_total}. */
-int lb_norm_stats(const float* x, size_t n, double* sums, lb_stream_t stream);
+ * stats pipeline: lb_norm_stats writes (sum, sum of squares) of x to sums[2] (double; in data parallel the
+ * caller all-reduces sums across ranks), then lb_norm_finalize turns (sums, n_total) into
+ * stats[4] = {mean, std(unbiased), 1/std, n_total}.
+ * The reduction uses no floating-point atomics (per-CTA partials added in index order by the last CTA), so the
+ * statistics -- and with them the whole forward pass -- are bit-reproducible like the reference's.  `work`:
+ * lb_stat_work_doubles() doubles, zero-filled ONCE when allocated (the kernels leave it zeroed); one per stream. */
+size_t lb_stat_work_doubles(void);
+int lb_norm_stats(const float* x, size_t n, double* sums, double* work, lb_stream_t stream);
 int lb_norm_finalize(const double* sums, double n_total, float* stats, lb_stream_t stream);
 /* y = (x-mean)*gain/std + bias ; gain is [C] (gain_batch_stride = 0) or [B][C] (stride = C). */
 int lb_norm_apply(const float* x, const float* stats, const float* gain, int gain_batch_stride,
@@ -88,34 +92,51 @@ int lb_norm_bwd_apply(const float* x, const float* g, const float* stats, const 
  *                or sum x*y*g otherwise.  gamma is a device scalar. */
 int lb_gate_fwd(const float* x, const float* y, const float* gamma, float* out, int batch, int pixels,
                 int channels, int y_bcast, lb_stream_t stream);
-/* same, also accumulating sums[2] (fp64, zeroed by the caller) += (sum out, sum out^2): the statistics of the whole-tensor
- * norm that consumes every gate output (block.py:46-51), without re-reading it.  channels % 4 == 0, aligned pointers. */
-int lb_gate_fwd_stats(const float* x, const float* y, const float* gamma, float* out, double* sums, int batch, int pixels,
-                      int channels, int y_bcast, lb_stream_t stream);
+/* same, also writing sums[2] (fp64) = (sum out, sum out^2): the statistics of the whole-tensor norm that consumes every
+ * gate output (block.py:46-51), without re-reading it (work: as lb_norm_stats).  channels % 4 == 0, aligned pointers. */
+int lb_gate_fwd_stats(const float* x, const float* y, const float* gamma, float* out, double* sums, double* work, int batch,
+                      int pixels, int channels, int y_bcast, lb_stream_t stream);
 int lb_gate_bwd(const float* x, const float* y, const float* gamma, const float* g, float* dx, float* dy,
                 float* dgamma, int batch, int pixels, int channels, int y_bcast, int strict_reference,
                 lb_stream_t stream);
 
 /* ---- spectral norm power iteration, one per forward                   libs/spectral_norm.py:21-32
  * W is the row-major [height][width] view of weight_bar.  u,v updated in place; sigma_out[0] = sigma,
- * sigma_out[1] = 1/sigma.  work: height + width + 4 floats of scratch. */
+ * sigma_out[1] = 1/sigma.  work: lb_sn_power_iter_work_floats(height, width) floats of scratch (per-row-split partial
+ * sums of W^T u, added in a fixed order: the iteration is bit-reproducible like the reference's torch.mv). */
+size_t lb_sn_power_iter_work_floats(int height, int width);
 int lb_sn_power_iter(const float* w, int height, int width, float* u, float* v, float* sigma_out,
                      float* work, lb_stream_t stream);
 /* The same iteration for ALL spectral-normed layers of a model in 4 launches.  layers_dev: device array of
- * n_layers records {const float* w; float* u; float* v; int height, width, t_off, s_off;} (40 bytes each; t_off /
- * s_off index the float scratch where W^T u and W v of that layer are staged).  items1_dev: int4 {layer, col0,
- * row0, rows} tiles of 256 columns for pass 1; items3_dev: int2 {layer, row0} groups of 8 rows for pass 2.
- * sigma_out: n_layers x {sigma, 1/sigma}. */
+ * n_layers records {const float* w; float* u; float* v; float* dv; int height, width, t_off, s_off, nsplit,
+ * rows_per_split;} (56 bytes each; t_off indexes the float `scratch` where the nsplit x width partial sums of W^T u of
+ * that layer are staged -- one row per block of rows_per_split rows, added in a fixed order -- and s_off indexes
+ * `s_out`, which receives s = W v of every layer, the pre-normalisation u, kept by the caller for the backward of
+ * trainable u; dv: see lb_sn_uv_grad_batched, may be NULL).  items1_dev: int4 {layer, col0, row0, rows} tiles of 256
+ * columns for pass 1 (row0 a multiple of rows_per_split); items3_dev: int2 {layer, row0} groups of 8 rows for pass 2.
+ * sigma_out: n_layers x {sigma, 1/sigma}.  No floating-point atomics: two runs from the same (W, u) give bit-identical
+ * u, v, sigma. */
 int lb_sn_power_iter_batched(const void* layers_dev, int n_layers, const void* items1_dev, int n_items1,
-                             const void* items3_dev, int n_items3, float* scratch, size_t scratch_floats,
+                             const void* items3_dev, int n_items3, float* scratch, float* s_out,
                              float* sigma_out, lb_stream_t stream);
 /* weight-gradient epilogue: with dwn = dL/d(W/sigma) and the LIVE u,v:
  *   grad += dwn/sigma - (sum dwn*W)/sigma^2 * u v^T       (SURVEY.md section 8c identity)
  * dwn has W's layout (packed_taps = 0) or is the tap-major [taps][d0][d1] buffer of lb_wgrad_tc
- * (packed_taps = kh*kw).  work: 2 doubles of scratch (zeroed by the call). */
+ * (packed_taps = kh*kw).  dot_out: 2 doubles (receives sum dwn*W); stat_work: as lb_norm_stats (ordered grid sum).
+ * Trainable u / v -- the reference's training loop calls dis.requires_grad_(True) (main.py:172), which also switches
+ * on the discriminator's weight_u / weight_v (requires_grad=False Parameters, spectral_norm.py:45-46); from the second
+ * discriminator step on sigma = u.(W v) (spectral_norm.py:31) hands them gradients and Nadam moves them.  Pass
+ * s_fwd (= W v of the forward pass this backward belongs to, from lb_sn_power_iter_batched's s_out), du and cacc (all
+ * three or none): du += c * s_fwd, cacc[0] += c with c = dL/dsigma = -(sum dwn*W)/sigma^2; lb_sn_uv_grad_batched then
+ * turns the accumulated c into dv. */
 int lb_sn_weight_grad(const float* dwn, const float* w, const float* u, const float* v,
                       const float* sigma, float* grad, int height, int width, int packed_taps,
-                      double* work, lb_stream_t stream);
+                      double* dot_out, double* stat_work, const float* s_fwd, float* du, float* cacc,
+                      lb_stream_t stream);
+/* dv += cacc[layer] * W^T u (live u) for every layer record with dv != NULL, then cacc[layer] = 0: the gradient of the
+ * trainable weight_v (see lb_sn_weight_grad); run once after the backward passes of a step, before the optimizer. */
+int lb_sn_uv_grad_batched(const void* layers_dev, int n_layers, const void* items1_dev, int n_items1, float* scratch,
+                          float* cacc, lb_stream_t stream);
 
 /* ---- convolution family as a gather-GEMM                              libs/conv.py:11-24, libs/attention.py:9-54,
  *                                                                       libs/scale.py:25-34, libs/linear.py:10
@@ -164,6 +185,14 @@ size_t lb_conv_tc_packed_elems(const lb_conv_geom* g);
 int lb_conv_tc_pack(const float* w, void* packed, const lb_conv_geom* g, lb_stream_t stream);
 int lb_conv_tc_gemm(const void* in_bf16, const void* w_packed, const float* alpha, const float* bias, float* out,
                     const lb_conv_geom* g, lb_stream_t stream);
+/* Same with a caller-provided workspace of lb_conv_tc_workspace_bytes(g) bytes (0 for most shapes): weight-bound layers
+ * whose output tiling cannot fill the GPU (5x5 1024->1024 on a 2x2 map, style linears at small batch) split the
+ * reduction over taps x channel chunks; every split writes its own partial tile there and a second kernel adds the
+ * splits in index order -- no floating-point atomics, so the forward pass is bit-reproducible.  Without a workspace
+ * (lb_conv_tc_gemm) such layers run unsplit. */
+size_t lb_conv_tc_workspace_bytes(const lb_conv_geom* g);
+int lb_conv_tc_gemm_ws(const void* in_bf16, const void* w_packed, const float* alpha, const float* bias, float* out,
+                       const lb_conv_geom* g, void* work, size_t work_bytes, lb_stream_t stream);
 /* Persistent variant with a fused epilogue (TMEM double buffering, TMA-stored outputs):
  *   acc = alpha * GEMM (+ bias);  if aux: acc *= RootTanh'(aux[pixel][n]) (activation.py:18-36, growth 4);
  *   out32 (fp32, row stride g->ld_out) and/or out16 (bf16, row stride ld_out16; RootTanh applied first when act16)

@@ -33,7 +33,8 @@ _SIGNATURES = {
     "lb_tanh_bwd": ([P, P, P, c_size_t, P], c_int),
     "lb_hinge_fwd": ([P, P, c_size_t, P], c_int),
     "lb_hinge_bwd": ([P, P, P, c_size_t, P], c_int),
-    "lb_norm_stats": ([P, c_size_t, P, P], c_int),
+    "lb_stat_work_doubles": ([], c_size_t),
+    "lb_norm_stats": ([P, c_size_t, P, P, P], c_int),
     "lb_norm_finalize": ([P, c_double, P, P], c_int),
     "lb_norm_apply": ([P, P, P, c_int, P, P, c_int, c_int, c_int, P], c_int),
     "lb_norm_apply_ex": ([P, P, P, c_int, P, P, P, c_int, c_int, c_int, c_int, P], c_int),
@@ -41,11 +42,13 @@ _SIGNATURES = {
     "lb_norm_bwd_finalize": ([P, P, P, c_int, P, c_int, c_int, P, P, P, P], c_int),
     "lb_norm_bwd_apply": ([P, P, P, P, c_int, P, P, c_int, c_int, c_int, P], c_int),
     "lb_gate_fwd": ([P, P, P, P, c_int, c_int, c_int, c_int, P], c_int),
-    "lb_gate_fwd_stats": ([P, P, P, P, P, c_int, c_int, c_int, c_int, P], c_int),
+    "lb_gate_fwd_stats": ([P, P, P, P, P, P, c_int, c_int, c_int, c_int, P], c_int),
     "lb_gate_bwd": ([P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P], c_int),
+    "lb_sn_power_iter_work_floats": ([c_int, c_int], c_size_t),
     "lb_sn_power_iter": ([P, c_int, c_int, P, P, P, P, P], c_int),
-    "lb_sn_power_iter_batched": ([P, c_int, P, c_int, P, c_int, P, c_size_t, P, P], c_int),
-    "lb_sn_weight_grad": ([P, P, P, P, P, P, c_int, c_int, c_int, P, P], c_int),
+    "lb_sn_power_iter_batched": ([P, c_int, P, c_int, P, c_int, P, P, P, P], c_int),
+    "lb_sn_weight_grad": ([P, P, P, P, P, P, c_int, c_int, c_int, P, P, P, P, P, P], c_int),
+    "lb_sn_uv_grad_batched": ([P, c_int, P, c_int, P, P, P], c_int),
     "lb_wgrad_tc_supported": ([POINTER(ConvGeom)], c_int),
     "lb_wgrad_tc": ([P, P, P, POINTER(ConvGeom), P], c_int),
     "lb_conv_gemm": ([P, P, P, P, P, POINTER(ConvGeom), P], c_int),
@@ -58,6 +61,8 @@ _SIGNATURES = {
     "lb_conv_tc_packed_elems": ([POINTER(ConvGeom)], c_size_t),
     "lb_conv_tc_pack": ([P, P, POINTER(ConvGeom), P], c_int),
     "lb_conv_tc_gemm": ([P, P, P, P, P, POINTER(ConvGeom), P], c_int),
+    "lb_conv_tc_workspace_bytes": ([POINTER(ConvGeom)], c_size_t),
+    "lb_conv_tc_gemm_ws": ([P, P, P, P, P, POINTER(ConvGeom), P, c_size_t, P], c_int),
     "lb_conv_tc_ex_supported": ([POINTER(ConvGeom), c_int, c_int], c_int),
     "lb_conv_tc_gemm_ex": ([P, P, P, P, P, P, c_int, c_int, P, c_int, POINTER(ConvGeom), P], c_int),
     "lb_cast_bf16": ([P, P, c_size_t, P], c_int),

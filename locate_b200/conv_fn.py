@@ -75,7 +75,7 @@ def power_iterate(w_bar, u, v, spec):
     """One in-place power iteration (spectral_norm.py:21-32); returns the [sigma, 1/sigma] buffer."""
     height, width = spec.sn_shape
     sigma = torch.empty(2, dtype=torch.float32, device=w_bar.device)
-    work = torch.empty(height + width + 4, dtype=torch.float32, device=w_bar.device)
+    work = torch.empty(_lib.lib().lb_sn_power_iter_work_floats(height, width), dtype=torch.float32, device=w_bar.device)
     call("lb_sn_power_iter", ptr(w_bar), height, width, ptr(u), ptr(v), ptr(sigma), ptr(work))
     return sigma
 
@@ -99,6 +99,42 @@ def _packed_weight(w_bar, g, tag):
         call("lb_conv_tc_pack", ptr(w_bar), ptr(pk), g)
         cache[1][tag] = pk
     return pk
+
+
+def _uv_extra(pre_sigma, u):
+    """(s_fwd, du, cacc) for lb_sn_weight_grad when this layer's u / v are trainable -- the reference's loop switches
+    them on for the discriminator (main.py:172), see oracle._LiveSigma -- else three NULLs."""
+    uv = getattr(pre_sigma, "_lb_uv", None)
+    if uv is None or not CFG.STRICT_REFERENCE or not u.requires_grad:
+        return None
+    du = getattr(u, "_lb_grad", None)
+    if du is None:
+        return None
+    return uv[0], du, uv[1], uv[2]
+
+
+def _sn_weight_grad(dwn, w_bar, u, v, sigma, spec, packed_taps, extra, dev):
+    """grad(W_bar) += dwn/sigma - (sum dwn*W)/sigma^2 u v^T into the gradient sink; returns what autograd gets."""
+    from .ops import _stat_work
+    grad_w, dw_ret = _grad_sink(w_bar)
+    dot = torch.empty(2, dtype=torch.float64, device=dev)
+    height, width = spec.sn_shape
+    s_fwd = du = cacc = None
+    if extra is not None:
+        s_fwd, du, cacc, batch = extra
+        if u.grad is None:
+            u.grad, v.grad = u._lb_grad, v._lb_grad
+        batch.uv_pending = True
+    call("lb_sn_weight_grad", ptr(dwn), ptr(w_bar), ptr(u.data), ptr(v.data), ptr(sigma), ptr(grad_w), height, width, packed_taps,
+         ptr(dot), ptr(_stat_work(dev)), ptr(s_fwd), ptr(du), ptr(cacc))
+    return dw_ret
+
+
+def _tc_gemm(fl, nbytes, a, pk, alpha_ptr, bias, out_ptr, g, dev):
+    """lb_conv_tc_gemm_ws with the split-K workspace the geometry asks for (weight-bound layers; 0 bytes otherwise)."""
+    need = _lib.lib().lb_conv_tc_workspace_bytes(ctypes.byref(g))
+    work = torch.empty(need // 4, dtype=torch.float32, device=dev) if need else None
+    _timed_call("conv_tc", fl, nbytes, "lb_conv_tc_gemm_ws", ptr(a), ptr(pk), alpha_ptr, ptr(bias), out_ptr, g, ptr(work), need)
 
 
 class SNConvFn(torch.autograd.Function):
@@ -178,8 +214,7 @@ class SNConvFn(torch.autograd.Function):
                 a = torch.empty((n // cin, cin_p), dtype=torch.bfloat16, device=x.device)
                 call("lb_cast_bf16_rows", ptr(x), cin, ptr(a), cin_p, n // cin, cin, growth)
             pk = _packed_weight(w_bar, g_fwd, "fwd")
-            _timed_call("conv_tc", fl, _tc_bytes(g_fwd), "lb_conv_tc_gemm", ptr(a), ptr(pk), sigma.data_ptr() + 4, ptr(bias),
-                        out.data_ptr() + off, g_fwd)
+            _tc_gemm(fl, _tc_bytes(g_fwd), a, pk, sigma.data_ptr() + 4, bias, out.data_ptr() + off, g_fwd, x.device)
         elif small:
             pointwise = spec.taps == 1 and spec.stride == 1 and spec.pad == 0
             small_growth = CFG.ROOTTANH_GROWTH if pre_act else 0
@@ -204,6 +239,7 @@ class SNConvFn(torch.autograd.Function):
             call("lb_copy_rows", ptr(x), cin, ptr(out), ctot, b * h * w_, cin, 0)
         ctx.save_for_backward(x if pre_act else None, a, w_bar, sigma)
         ctx.u, ctx.v = u, v                      # LIVE u/v: the reference's backward reads them at backward time
+        ctx.uv_extra = _uv_extra(pre_sigma, u)
         ctx.bias_param, ctx.w_param = bias, w_bar
         ctx.meta = (spec, cat_input, pre_act, tc, (b, h, w_, cin, oh, ow, ctot), g_dgrad, g_wgrad, (fl, by))
         ctx.raw_a = bool(small and pre_act and a is x)   # `a` is the pre-activation: backward applies RootTanh where it needs it
@@ -228,17 +264,14 @@ class SNConvFn(torch.autograd.Function):
             if need_dx:
                 dx = _new_act((b, cin) if gout.dim() == 2 else (b, cin, h, w_), gout)
                 pk = _packed_weight(w_bar, g_dgrad, "dgrad")
-                _timed_call("conv_tc", fl, _tc_bytes(g_dgrad), "lb_conv_tc_gemm", ptr(gy), ptr(pk), sigma.data_ptr() + 4, None, ptr(dx), g_dgrad)
+                _tc_gemm(fl, _tc_bytes(g_dgrad), gy, pk, sigma.data_ptr() + 4, None, ptr(dx), g_dgrad, gout.device)
             if need_dw:
                 dwp = torch.zeros(w_bar.numel(), dtype=torch.float32, device=gout.device)
                 if spec.kind == "convT":
-                    _timed_call("wgrad_tc", fl, by / 2, "lb_wgrad_tc", ptr(gy), ptr(a), ptr(dwp), g_wgrad)
+                    _timed_call("wgrad_tc", fl, _wgrad_bytes(g_wgrad), "lb_wgrad_tc", ptr(gy), ptr(a), ptr(dwp), g_wgrad)
                 else:
-                    _timed_call("wgrad_tc", fl, by / 2, "lb_wgrad_tc", ptr(a), ptr(gy), ptr(dwp), g_wgrad)
-                grad_w, dw_ret = _grad_sink(ctx.w_param)
-                work = torch.empty(2, dtype=torch.float64, device=gout.device)
-                call("lb_sn_weight_grad", ptr(dwp), ptr(w_bar), ptr(ctx.u.data), ptr(ctx.v.data), ptr(sigma), ptr(grad_w),
-                     height, width, t, ptr(work))
+                    _timed_call("wgrad_tc", fl, _wgrad_bytes(g_wgrad), "lb_wgrad_tc", ptr(a), ptr(gy), ptr(dwp), g_wgrad)
+                dw_ret = _sn_weight_grad(dwp, ctx.w_param, ctx.u, ctx.v, sigma, spec, t, ctx.uv_extra, gout.device)
         else:
             lib = _lib.lib()
             growth = CFG.ROOTTANH_GROWTH
@@ -270,10 +303,7 @@ class SNConvFn(torch.autograd.Function):
                                 growth if fuse_act else 0)
                 else:
                     _timed_call("conv_wgrad", fl, by, "lb_conv_wgrad", ga_ptr, de_ptr, ptr(dwn), g_wgrad)
-                grad_w, dw_ret = _grad_sink(ctx.w_param)
-                work = torch.empty(2, dtype=torch.float64, device=gout.device)
-                call("lb_sn_weight_grad", ptr(dwn), ptr(w_bar), ptr(ctx.u.data), ptr(ctx.v.data), ptr(sigma), ptr(grad_w),
-                     height, width, 0, ptr(work))
+                dw_ret = _sn_weight_grad(dwn, ctx.w_param, ctx.u, ctx.v, sigma, spec, 0, ctx.uv_extra, gout.device)
         if need_dx:
             if pre_act and not dact_done:
                 call("lb_roottanh_bwd", ptr(x), ptr(dx), ptr(dx), dx.numel(), CFG.ROOTTANH_GROWTH)   # in place
@@ -285,29 +315,29 @@ class SNConvFn(torch.autograd.Function):
         return dx, dw_ret, None, None, dbias_ret, None, None, None, None
 
 
-def _tc_bytes(g, out32=True, out16=False, aux=False):
-    """Algorithmic bytes of one tensor-core GEMM launch: bf16 input + bf16 packed weight + the outputs it writes
-    (fp32 and/or bf16) + the fp32 pre-activation it reads for a fused RootTanh'."""
+def _tc_bytes(g, *_unused):
+    """ALGORITHMIC bytes of one tensor-core GEMM launch: bf16 activations in + out and the bf16
+    weight -- whatever extra copies (fp32 outputs, pre-activations for a fused RootTanh') the launch really moves."""
     rows_in = g.batch * g.in_h * g.in_w
     rows_out = g.batch * g.out_h * g.out_w
-    return (2.0 * rows_in * g.in_c + 2.0 * g.kh * g.kw * g.in_c * g.out_c
-            + rows_out * g.out_c * ((4.0 if out32 else 0.0) + (2.0 if out16 else 0.0) + (4.0 if aux else 0.0)))
+    return 2.0 * rows_in * g.in_c + 2.0 * g.kh * g.kw * g.in_c * g.out_c + 2.0 * rows_out * g.out_c
+
+
+def _wgrad_bytes(g):
+    """ALGORITHMIC bytes of one weight-gradient launch: both bf16 operands once + the fp32 gradient."""
+    return (2.0 * g.batch * g.in_h * g.in_w * g.in_c + 2.0 * g.batch * g.out_h * g.out_w * g.out_c
+            + 4.0 * g.kh * g.kw * g.in_c * g.out_c)
 
 
 def _ex_ok(g, ld16, ld_aux):
     return _lib.lib().lb_conv_tc_ex_supported(ctypes.byref(g), ld16, ld_aux) == 1
 
 
-def _sn_wgrad_tc(ctx_w, u, v, sigma, gathered, dense, g_wgrad, spec, fl, by, dev):
+def _sn_wgrad_tc(ctx_w, u, v, sigma, gathered, dense, g_wgrad, spec, fl, by, dev, extra=None):
     """dW of one spectral-normed conv on the tensor cores + the sigma correction, accumulated into the grad sink."""
     dwp = torch.zeros(ctx_w.numel(), dtype=torch.float32, device=dev)
-    _timed_call("wgrad_tc", fl, by / 2, "lb_wgrad_tc", ptr(gathered), ptr(dense), ptr(dwp), g_wgrad)
-    grad_w, dw_ret = _grad_sink(ctx_w)
-    work = torch.empty(2, dtype=torch.float64, device=dev)
-    height, width = spec.sn_shape
-    call("lb_sn_weight_grad", ptr(dwp), ptr(ctx_w), ptr(u.data), ptr(v.data), ptr(sigma), ptr(grad_w), height, width, spec.taps,
-         ptr(work))
-    return dw_ret
+    _timed_call("wgrad_tc", fl, _wgrad_bytes(g_wgrad), "lb_wgrad_tc", ptr(gathered), ptr(dense), ptr(dwp), g_wgrad)
+    return _sn_weight_grad(dwp, ctx_w, u, v, sigma, spec, spec.taps, extra, dev)
 
 
 class ActivatedPairFn(torch.autograd.Function):
@@ -345,10 +375,10 @@ class ActivatedPairFn(torch.autograd.Function):
         y1 = _new_act((b, cout, oh, ow), x)
         # lb_conv_tc_gemm picks the persistent kernel itself and keeps direct stores for rows that TMA cannot address
         # (cout = 3: G's last layer)
-        _timed_call("conv_tc", fl1, _tc_bytes(gf1), "lb_conv_tc_gemm", ptr(a0), ptr(_packed_weight(w1, gf1, "fwd")),
-                    sigma1.data_ptr() + 4, None, ptr(y1), gf1)
+        _tc_gemm(fl1, _tc_bytes(gf1), a0, _packed_weight(w1, gf1, "fwd"), sigma1.data_ptr() + 4, None, ptr(y1), gf1, x.device)
         ctx.save_for_backward(x if pre_act0 else None, act16, y0, a0, w0, w1, sigma0, sigma1)
         ctx.uv = (u0, v0, u1, v1)                # LIVE u/v (see SNConvFn)
+        ctx.uv_extra = (_uv_extra(sigma0, u0), _uv_extra(sigma1, u1))
         ctx.meta = (spec0, spec1, geoms, (b, cin, h, w_, oh, ow, mid, cout), (fl0, by0, fl1, by1), pre_act0)
         return y1
 
@@ -371,14 +401,14 @@ class ActivatedPairFn(torch.autograd.Function):
         dx = dw0 = dw1 = None
         if need_dw1:
             ga, de = (g1, a0) if spec1.kind == "convT" else (a0, g1)
-            dw1 = _sn_wgrad_tc(w1, u1, v1, sigma1, ga, de, gw1, spec1, fl1, by1, dev)
+            dw1 = _sn_wgrad_tc(w1, u1, v1, sigma1, ga, de, gw1, spec1, fl1, by1, dev, ctx.uv_extra[1])
         if need_dx or need_dw0:
             d0 = _bf16_like(y0)                  # bf16( dL/dy0 ) = bf16( dgrad_1(g1) * RootTanh'(y0) )
             _timed_call("conv_tc", fl1, _tc_bytes(gd1, False, True, True), "lb_conv_tc_gemm_ex", ptr(g1), ptr(_packed_weight(w1, gd1, "dgrad")),
                         sigma1.data_ptr() + 4, None, None, ptr(d0), mid, 0, ptr(y0), mid, gd1)
             if need_dw0:
                 ga, de = (d0, act16) if spec0.kind == "convT" else (act16, d0)
-                dw0 = _sn_wgrad_tc(w0, u0, v0, sigma0, ga, de, gw0, spec0, fl0, by0, dev)
+                dw0 = _sn_wgrad_tc(w0, u0, v0, sigma0, ga, de, gw0, spec0, fl0, by0, dev, ctx.uv_extra[0])
             if need_dx:
                 dx = _new_act((b, cin, h, w_), gout)
                 _timed_call("conv_tc", fl0, _tc_bytes(gd0, True, False, pre_act0), "lb_conv_tc_gemm_ex", ptr(d0), ptr(_packed_weight(w0, gd0, "dgrad")),

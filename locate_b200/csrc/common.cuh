@@ -79,6 +79,39 @@ __device__ __forceinline__ T lb_block_sum(T v, T* scratch) {
   return v;
 }
 
+// Grid-wide (s1, s2) reduction WITHOUT floating-point atomics, so the result is bit-reproducible run to run: every CTA
+// stores its pair, the last CTA to arrive (integer ticket) adds all pairs in index order with a fixed tree.
+//   work[0]: ticket (low 32 bits; 0 on entry, left 0 on exit), work[1 + 2*cta], work[2 + 2*cta]: the pairs.
+// `s1`, `s2` are the CTA totals held by thread 0; out[2] receives the grid totals.  Call from all threads of the CTA.
+#define LB_STAT_WORK_DOUBLES 2048      // 1 + 2 * (largest statistics grid = LB_SMS * 4), rounded up
+__device__ __forceinline__ void lb_grid_sum2_ordered(double s1, double s2, double* __restrict__ work, double* __restrict__ out,
+                                                     double* scratch) {
+  __shared__ int s_last;
+  if (threadIdx.x == 0) {
+    work[1 + 2 * blockIdx.x] = s1;
+    work[2 + 2 * blockIdx.x] = s2;
+    __threadfence();
+    const unsigned int ticket = atomicAdd(reinterpret_cast<unsigned int*>(work), 1u);
+    s_last = ticket == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    double a = 0.0, b = 0.0;
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
+      a += __ldcg(work + 1 + 2 * i);
+      b += __ldcg(work + 2 + 2 * i);
+    }
+    a = lb_block_sum(a, scratch);
+    b = lb_block_sum(b, scratch);
+    if (threadIdx.x == 0) {
+      out[0] = a;
+      out[1] = b;
+      *reinterpret_cast<unsigned int*>(work) = 0u;
+    }
+  }
+}
+
 // 128-bit streaming accessors (each activation is touched once per kernel: keep it out of L1)
 __device__ __forceinline__ float4 lb_ld4(const float* p) {
   return __ldg(reinterpret_cast<const float4*>(p));

@@ -42,6 +42,8 @@ struct TcParams {
   int rows_per_tap;                   // rows of Wp per tap (= out_c)
   int view_empty;                     // bit v set: parity view v has no pixels
   const float* alpha; const float* bias; float* out;
+  float* part;                        // split-K partial sums [splits][rows][out_c] (raw accumulators), NULL when splits == 1
+  long long part_rows;
 };
 
 __device__ __forceinline__ void tap_span(int mode, int s, int pad, int k, int parity, int& t0, int& step, int& cnt) {
@@ -77,7 +79,8 @@ __global__ void __launch_bounds__(192, 4) k_conv_tc(const __grid_constant__ TcMa
   int ty0, tys, tyc, tx0, txs, txc;
   tap_span(p.mode, p.stride, p.pad, p.kh, py, ty0, tys, tyc);
   tap_span(p.mode, p.stride, p.pad, p.kw, px, tx0, txs, txc);
-  // split-K: this CTA reduces the flat (tap, k-chunk) range [it_begin, it_end) and adds its partial sum atomically
+  // split-K: this CTA reduces the flat (tap, k-chunk) range [it_begin, it_end) into its own partial buffer; k_splitk_reduce
+  // adds the splits in a fixed order (no floating-point atomics: the forward pass is bit-reproducible)
   const int iters_all = tyc * txc * p.kchunks;
   const int per_split = (iters_all + p.splits - 1) / p.splits;
   const int it_begin = min(iters_all, split * per_split);
@@ -177,15 +180,15 @@ __global__ void __launch_bounds__(192, 4) k_conv_tc(const __grid_constant__ TcMa
       }
       const int n = n0 + c0;
       if (valid && n < p.out_c) {
-        const bool add_bias = p.bias && split == 0;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = v[i] * alpha + ((add_bias && n + i < p.out_c) ? __ldg(p.bias + n + i) : 0.0f);
         if (p.splits > 1) {
-          if (iters > 0 || add_bias) {
+          float* pr = p.part + ((size_t)split * p.part_rows + ((size_t)(b * p.out_h + oy) * p.out_w + ox)) * p.out_c + n;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) if (n + i < p.out_c) atomicAdd(dst + n + i, v[i]);
-          }
-        } else if (vec && n + 15 < p.out_c) {
+          for (int i = 0; i < 16; ++i) if (n + i < p.out_c) pr[i] = v[i];
+          continue;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = v[i] * alpha + ((p.bias && n + i < p.out_c) ? __ldg(p.bias + n + i) : 0.0f);
+        if (vec && n + 15 < p.out_c) {
 #pragma unroll
           for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst + n + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
         } else {
@@ -285,6 +288,8 @@ extern "C" int lb_conv_tc_gemm_ex(const void* in_bf16, const void* w_packed, con
                                   void* out16, int ld_out16, int act16, const float* aux, int ld_aux, const lb_conv_geom* g,
                                   lb_stream_t s);
 extern "C" int lb_conv_tc_ex_supported(const lb_conv_geom* g, int ld_out16, int ld_aux);
+extern "C" int lb_conv_tc_gemm_ws(const void* in_bf16, const void* w_packed, const float* alpha, const float* bias, float* out,
+                                  const lb_conv_geom* g, void* work, size_t work_bytes, lb_stream_t s);
 
 // Live taps of the first tile along one axis (host replica of the kernels' tap walk): a tap whose source box lies
 // entirely in the padding contributes nothing, and the persistent kernel skips it.
@@ -324,11 +329,62 @@ static bool prefer_persistent(const lb_conv_geom* g) {
   return live * 2 <= taps_eff;
 }
 
+// out[row][n] = alpha * (part[0][row][n] + part[1][row][n] + ...) + bias[n], splits added in index order
+__global__ void __launch_bounds__(256) k_splitk_reduce(const float* __restrict__ part, int splits, size_t rows, int out_c, int ld_out,
+                                                      const float* __restrict__ alpha, const float* __restrict__ bias,
+                                                      float* __restrict__ out) {
+  const float a = alpha ? __ldg(alpha) : 1.0f;
+  const size_t n = rows * (size_t)out_c;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const size_t r = i / out_c;
+    const int c = (int)(i - r * out_c);
+    float acc = part[i];
+    for (int sp = 1; sp < splits; ++sp) acc += part[(size_t)sp * n + i];
+    out[r * ld_out + c] = fmaf(acc, a, bias ? __ldg(bias + c) : 0.0f);
+  }
+}
+
+// split-K factor of the non-persistent kernel for weight-bound layers whose output tiling cannot fill the GPU
+// (e.g. 5x5 1024->1024 at 2x2); 1 = no split
+static int tc_splits(const lb_conv_geom* g) {
+  const int sp = g->mode == 1 ? g->stride : 1;
+  const int dst_w = (g->out_w + sp - 1) / sp, dst_h = (g->out_h + sp - 1) / sp;
+  const int tw = pow2_ceil(dst_w) < kBlockM ? pow2_ceil(dst_w) : kBlockM;
+  const int rest = kBlockM / tw;
+  const int th = pow2_ceil(dst_h) < rest ? pow2_ceil(dst_h) : rest;
+  const int tb = rest / th;
+  int bn = (g->out_c + 15) / 16 * 16;
+  if (bn > 128) bn = 128;
+  const int n_tiles = (g->out_c + bn - 1) / bn;
+  const long long ctas = (long long)((dst_w + tw - 1) / tw) * ((dst_h + th - 1) / th) * ((g->batch + tb - 1) / tb) * n_tiles * sp * sp;
+  const int taps_eff = g->mode == 1 ? ((g->kh + sp - 1) / sp) * ((g->kw + sp - 1) / sp) : g->kh * g->kw;
+  const int iters_est = taps_eff * ((g->in_c + kBlockK - 1) / kBlockK);
+  if (ctas * 2 <= LB_SMS && iters_est >= 8) {
+    long long want = (LB_SMS * 2 + ctas - 1) / ctas;
+    if (want > iters_est / 4) want = iters_est / 4;
+    if (want > 64) want = 64;
+    if (want > 1) return (int)want;
+  }
+  return 1;
+}
+extern "C" size_t lb_conv_tc_workspace_bytes(const lb_conv_geom* g) {
+  if (!tc_geom_ok(g)) return 0;
+  const int splits = tc_splits(g);
+  return splits > 1 ? (size_t)splits * g->batch * g->out_h * g->out_w * g->out_c * sizeof(float) : 0;
+}
+
 extern "C" int lb_conv_tc_gemm(const void* in_bf16, const void* w_packed, const float* alpha, const float* bias, float* out,
                                const lb_conv_geom* g, lb_stream_t s) {
+  return lb_conv_tc_gemm_ws(in_bf16, w_packed, alpha, bias, out, g, nullptr, 0, s);
+}
+
+extern "C" int lb_conv_tc_gemm_ws(const void* in_bf16, const void* w_packed, const float* alpha, const float* bias, float* out,
+                                  const lb_conv_geom* g, void* work, size_t work_bytes, lb_stream_t s) {
   LB_REQUIRE(in_bf16 && w_packed && out && g);
   if (!tc_geom_ok(g)) return LB_EUNSUPPORTED;
-  if (!getenv("LB_TC_V1_ONLY") && prefer_persistent(g) && lb_conv_tc_ex_supported(g, 0, 0) == 1 && !(g->ld_out & 3) &&
+  static const bool v1_only = getenv("LB_TC_V1_ONLY") != nullptr;      // debugging switches are read once, not per launch
+  if (!v1_only && prefer_persistent(g) && lb_conv_tc_ex_supported(g, 0, 0) == 1 && !(g->ld_out & 3) &&
       !(reinterpret_cast<uintptr_t>(out) & 15)) {
     const int rc = lb_conv_tc_gemm_ex(in_bf16, w_packed, alpha, bias, out, nullptr, 0, 0, nullptr, 0, g, s);
     if (rc != LB_EUNSUPPORTED) return rc;
@@ -392,8 +448,8 @@ extern "C" int lb_conv_tc_gemm(const void* in_bf16, const void* w_packed, const 
     int st = budget / stage_bytes;
     if (st < 2) st = 2;
     if (st > 6) st = 6;
-    const char* env = getenv("LB_TC_STAGES");
-    p.stages = env ? atoi(env) : st;
+    static const int env_stages = getenv("LB_TC_STAGES") ? atoi(getenv("LB_TC_STAGES")) : 0;
+    p.stages = env_stages ? env_stages : st;
   }
   const int smem_bytes = p.stages * stage_bytes + 1024;
   static bool attr_set = false;
@@ -402,25 +458,22 @@ extern "C" int lb_conv_tc_gemm(const void* in_bf16, const void* w_packed, const 
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  // split-K for weight-bound layers whose output tiling cannot fill the GPU (e.g. 5x5 1024->1024 at 2x2)
+  // split-K (tc_splits) needs the caller's workspace for the per-split partial sums; without one the layer runs unsplit
   const int n_tiles = (g->out_c + bn - 1) / bn;
-  const long long ctas = (long long)p.tiles_w * p.tiles_h * tiles_b * n_tiles * p.sp * p.sp;
-  p.splits = 1;
-  if (ctas * 2 <= LB_SMS && iters_est >= 8) {
-    long long want = (LB_SMS * 2 + ctas - 1) / ctas;
-    if (want > iters_est / 4) want = iters_est / 4;
-    if (want > 64) want = 64;
-    if (want > 1) p.splits = (int)want;
-  }
-  if (p.splits > 1) {
-    cudaError_t e = cudaMemset2DAsync(out, (size_t)g->ld_out * 4, 0, (size_t)g->out_c * 4,
-                                      (size_t)g->batch * g->out_h * g->out_w, lb_s(s));
-    if (e != cudaSuccess) return (int)e;
-  }
+  const size_t rows = (size_t)g->batch * g->out_h * g->out_w;
+  p.splits = tc_splits(g);
+  if (p.splits > 1 && (!work || work_bytes < (size_t)p.splits * rows * g->out_c * sizeof(float) || (reinterpret_cast<uintptr_t>(work) & 3)))
+    p.splits = 1;
+  p.part = p.splits > 1 ? reinterpret_cast<float*>(work) : nullptr;
+  p.part_rows = (long long)rows;
   dim3 grid(p.tiles_w * p.tiles_h * tiles_b, n_tiles, p.sp * p.sp * p.splits);
   LB_REQUIRE(grid.y <= 65535 && grid.z <= 65535);
   k_conv_tc<<<grid, 192, smem_bytes, lb_s(s)>>>(maps, p);
   LB_LAUNCH_CHECK();
+  if (p.splits > 1) {
+    k_splitk_reduce<<<lb_grid_1d(rows * g->out_c, 256), 256, 0, lb_s(s)>>>(p.part, p.splits, rows, g->out_c, g->ld_out, alpha, bias, out);
+    LB_LAUNCH_CHECK();
+  }
   return LB_OK;
 }
 

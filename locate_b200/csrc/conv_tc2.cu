@@ -549,7 +549,8 @@ extern "C" int lb_conv_tc_gemm_ex(const void* in_bf16, const void* w_packed, con
     const int taps_phase = g->mode == 1 ? ((g->kh + p.sp - 1) / p.sp) * ((g->kw + p.sp - 1) / p.sp) : g->kh * g->kw;
     const long long res_bytes = (long long)taps_phase * p.kchunks * p.b_tile_bytes;
     const int a_stages = (int)((kSmemLimit - 1024 - epi_bytes - res_bytes) / kABytes);
-    if (nt == 1 && res_bytes <= 100 * 1024 && a_stages >= 4 && getenv("LB_TC2_RESIDENT")) {
+    static const bool env_resident = getenv("LB_TC2_RESIDENT") != nullptr;   // debugging switches are read once, not per launch
+    if (nt == 1 && res_bytes <= 100 * 1024 && a_stages >= 4 && env_resident) {
       p.resident = 1;
       stage_bytes = kABytes;
       stages = a_stages;
@@ -557,7 +558,10 @@ extern "C" int lb_conv_tc_gemm_ex(const void* in_bf16, const void* w_packed, con
       p.res_base = (uint32_t)(stages * stage_bytes);
     }
   }
-  if (const char* env = getenv("LB_TC2_STAGES")) { const int v = atoi(env); if (v >= 2 && v < stages) { stages = v; if (p.resident) p.res_base = (uint32_t)(stages * stage_bytes); } }
+  {
+    static const int env_stages = getenv("LB_TC2_STAGES") ? atoi(getenv("LB_TC2_STAGES")) : 0;
+    if (env_stages >= 2 && env_stages < stages) { stages = env_stages; if (p.resident) p.res_base = (uint32_t)(stages * stage_bytes); }
+  }
   p.block_n = bn; p.n_tiles = (g->out_c + bn - 1) / bn; p.stages = stages;
   p.acc_stride = (bn + 31) / 32 * 32;
   p.tmem_cols = (uint32_t)pow2_ceil(2 * p.acc_stride < 32 ? 32 : 2 * p.acc_stride);

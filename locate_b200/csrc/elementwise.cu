@@ -165,7 +165,7 @@ extern "C" int lb_gate_fwd(const float* x, const float* y, const float* gamma, f
 __global__ void __launch_bounds__(256) k_gate_fwd_stats(const float* __restrict__ x, const float* __restrict__ y,
                                                        const float* __restrict__ gamma, float* __restrict__ out, int n4,
                                                        LbFastDiv d_pc4, LbFastDiv d_c4, int channels, int y_bcast,
-                                                       double* __restrict__ sums) {
+                                                       double* __restrict__ sums, double* __restrict__ work) {
   __shared__ double scratch[32];
   const float gm = __ldg(gamma);
   const int stride = gridDim.x * blockDim.x;
@@ -190,19 +190,19 @@ __global__ void __launch_bounds__(256) k_gate_fwd_stats(const float* __restrict_
   }
   s1 = lb_block_sum(s1, scratch);
   s2 = lb_block_sum(s2, scratch);
-  if (threadIdx.x == 0) { atomicAdd(sums, s1); atomicAdd(sums + 1, s2); }
+  lb_grid_sum2_ordered(s1, s2, work, sums, scratch);
 }
-// sums[2] (fp64, zeroed by the caller) += (sum out, sum out^2).  Needs channels % 4 == 0 and 16-byte aligned pointers
-// (LB_EALIGN otherwise: use lb_gate_fwd + lb_norm_stats).
-extern "C" int lb_gate_fwd_stats(const float* x, const float* y, const float* gamma, float* out, double* sums, int batch,
-                                 int pixels, int channels, int y_bcast, lb_stream_t s) {
-  LB_REQUIRE(x && y && gamma && out && sums && batch > 0 && pixels > 0 && channels > 0);
+// sums[2] (fp64) = (sum out, sum out^2), reduced in a fixed order (work: see lb_norm_stats).  Needs channels % 4 == 0 and
+// 16-byte aligned pointers (LB_EALIGN otherwise: use lb_gate_fwd + lb_norm_stats).
+extern "C" int lb_gate_fwd_stats(const float* x, const float* y, const float* gamma, float* out, double* sums, double* work,
+                                 int batch, int pixels, int channels, int y_bcast, lb_stream_t s) {
+  LB_REQUIRE(x && y && gamma && out && sums && work && batch > 0 && pixels > 0 && channels > 0);
   const size_t n = (size_t)batch * pixels * channels;
   if ((channels & 3) || n / 4 >= ((size_t)1 << 31) - ((size_t)1 << 24) || !lb_aligned16(x) || !lb_aligned16(y) || !lb_aligned16(out))
     return LB_EALIGN;
   k_gate_fwd_stats<<<lb_grid_1d(n / 4, 256, 4), 256, 0, lb_s(s)>>>(x, y, gamma, out, (int)(n / 4),
                                                                   lb_make_fastdiv((uint32_t)((size_t)pixels * channels / 4)),
-                                                                  lb_make_fastdiv(channels / 4), channels, y_bcast, sums);
+                                                                  lb_make_fastdiv(channels / 4), channels, y_bcast, sums, work);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }

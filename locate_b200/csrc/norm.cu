@@ -5,7 +5,8 @@
 #include <cuda_bf16.h>
 #include "common.cuh"
 
-__global__ void __launch_bounds__(256) k_norm_stats(const float* __restrict__ x, size_t n, double* __restrict__ sums, int vec) {
+__global__ void __launch_bounds__(256) k_norm_stats(const float* __restrict__ x, size_t n, double* __restrict__ sums,
+                                                   double* __restrict__ work, int vec) {
   __shared__ double scratch[32];
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   double s1 = 0.0, s2 = 0.0;
@@ -28,12 +29,14 @@ __global__ void __launch_bounds__(256) k_norm_stats(const float* __restrict__ x,
   }
   s1 = lb_block_sum(s1, scratch);
   s2 = lb_block_sum(s2, scratch);
-  if (threadIdx.x == 0) { atomicAdd(sums, s1); atomicAdd(sums + 1, s2); }
+  lb_grid_sum2_ordered(s1, s2, work, sums, scratch);
 }
 
-extern "C" int lb_norm_stats(const float* x, size_t n, double* sums, lb_stream_t s) {
-  LB_REQUIRE(x && sums && n > 0);
-  k_norm_stats<<<lb_grid_1d((n + 3) / 4, 256, 4), 256, 0, lb_s(s)>>>(x, n, sums, lb_aligned16(x) ? 1 : 0);
+extern "C" size_t lb_stat_work_doubles(void) { return LB_STAT_WORK_DOUBLES; }
+
+extern "C" int lb_norm_stats(const float* x, size_t n, double* sums, double* work, lb_stream_t s) {
+  LB_REQUIRE(x && sums && work && n > 0);
+  k_norm_stats<<<lb_grid_1d((n + 3) / 4, 256, 4), 256, 0, lb_s(s)>>>(x, n, sums, work, lb_aligned16(x) ? 1 : 0);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }

@@ -7,24 +7,31 @@
 
 #define SN_EPS 1e-12f
 
-// t[j] += sum_{i in row split} W[i][j] * u[i];   grid = (col tiles of 256, row splits)
-__global__ void __launch_bounds__(256) k_sn_wt_u(const float* __restrict__ w, const float* __restrict__ u, float* __restrict__ t,
+// Deterministic by construction (the reference's torch.mv is): every row split writes its own partial column sums and
+// the normalise kernel adds the splits in a fixed order -- no floating-point atomics anywhere in the iteration.
+// tpart[split][j] = sum_{i in row split} W[i][j] * u[i];   grid = (col tiles of 256, row splits)
+__global__ void __launch_bounds__(256) k_sn_wt_u(const float* __restrict__ w, const float* __restrict__ u, float* __restrict__ tpart,
                                                 int height, int width, int rows_per_split) {
   const int j = blockIdx.x * 256 + threadIdx.x;
   if (j >= width) return;
   const int i0 = blockIdx.y * rows_per_split, i1 = min(height, i0 + rows_per_split);
   float acc = 0.0f;
   for (int i = i0; i < i1; ++i) acc = fmaf(w[(size_t)i * width + j], __ldg(u + i), acc);
-  atomicAdd(t + j, acc);
+  tpart[(size_t)blockIdx.y * width + j] = acc;
 }
 
-// dst = src / (|src| + eps); also writes |src| to norm_out if non-null.  One CTA.
-__global__ void __launch_bounds__(1024) k_sn_normalize(const float* __restrict__ src, float* __restrict__ dst, int n,
+// src[i] <- sum of its `nsplit` partials (stride n, fixed order); dst = src / (|src| + eps); also writes sigma if non-null.  One CTA.
+__global__ void __launch_bounds__(1024) k_sn_normalize(float* __restrict__ src, float* __restrict__ dst, int n, int nsplit,
                                                       float* __restrict__ sigma_out) {
   __shared__ float scratch[32];
   __shared__ float s_norm;
   float acc = 0.0f;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) { const float v = src[i]; acc = fmaf(v, v, acc); }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float v = src[i];
+    for (int sp = 1; sp < nsplit; ++sp) v += src[(size_t)sp * n + i];
+    src[i] = v;
+    acc = fmaf(v, v, acc);
+  }
   acc = lb_block_sum(acc, scratch);
   if (threadIdx.x == 0) s_norm = sqrtf(acc);
   __syncthreads();
@@ -50,26 +57,36 @@ __global__ void __launch_bounds__(256) k_sn_w_v(const float* __restrict__ w, con
   if (lane == 0) sv[row] = acc;
 }
 
+static void sn_splits(int height, int width, int& splits, int& rps) {
+  const int col_tiles = (width + 255) / 256;
+  splits = (LB_SMS * 2 + col_tiles - 1) / col_tiles;
+  if (splits > 16) splits = 16;              // bounds the partial buffer; 16 x col_tiles CTAs still cover the GPU for any wide W
+  if (splits > height) splits = height;
+  if (splits < 1) splits = 1;
+  rps = (height + splits - 1) / splits;
+  splits = (height + rps - 1) / rps;
+}
+extern "C" size_t lb_sn_power_iter_work_floats(int height, int width) {
+  if (height <= 0 || width <= 0) return 0;
+  int splits, rps;
+  sn_splits(height, width, splits, rps);
+  return (size_t)splits * width + height;
+}
 extern "C" int lb_sn_power_iter(const float* w, int height, int width, float* u, float* v, float* sigma_out, float* work,
                                 lb_stream_t s) {
   LB_REQUIRE(w && u && v && sigma_out && work && height > 0 && width > 0);
-  float* t = work;            // [width]
-  float* sv = work + width;   // [height]
-  cudaError_t e = cudaMemsetAsync(t, 0, sizeof(float) * width, lb_s(s));
-  if (e != cudaSuccess) return (int)e;
+  int splits, rps;
+  sn_splits(height, width, splits, rps);
+  float* t = work;                              // [splits][width]
+  float* sv = work + (size_t)splits * width;    // [height]
   const int col_tiles = (width + 255) / 256;
-  int splits = (LB_SMS * 2 + col_tiles - 1) / col_tiles;
-  if (splits > height) splits = height;
-  if (splits < 1) splits = 1;
-  const int rps = (height + splits - 1) / splits;
-  splits = (height + rps - 1) / rps;
   k_sn_wt_u<<<dim3(col_tiles, splits), 256, 0, lb_s(s)>>>(w, u, t, height, width, rps);
   LB_LAUNCH_CHECK();
-  k_sn_normalize<<<1, 1024, 0, lb_s(s)>>>(t, v, width, nullptr);
+  k_sn_normalize<<<1, 1024, 0, lb_s(s)>>>(t, v, width, splits, nullptr);
   LB_LAUNCH_CHECK();
   k_sn_w_v<<<(height + 7) / 8, 256, 0, lb_s(s)>>>(w, v, sv, height, width);
   LB_LAUNCH_CHECK();
-  k_sn_normalize<<<1, 1024, 0, lb_s(s)>>>(sv, u, height, sigma_out);
+  k_sn_normalize<<<1, 1024, 0, lb_s(s)>>>(sv, u, height, 1, sigma_out);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
@@ -88,7 +105,7 @@ __device__ __forceinline__ void sn_decode(const SnIdx& x, int k, int& i, int& j,
   off = ((size_t)tap * x.height + i) * x.d1 + j1;
 }
 __global__ void __launch_bounds__(256) k_sn_dot(const float* __restrict__ a, const float* __restrict__ b, int n, const SnIdx x,
-                                               double* __restrict__ out) {
+                                               double* __restrict__ out, double* __restrict__ stat_work) {
   __shared__ double scratch[32];
   const int stride = gridDim.x * blockDim.x;
   float part = 0.0f;
@@ -102,12 +119,14 @@ __global__ void __launch_bounds__(256) k_sn_dot(const float* __restrict__ a, con
   }
   acc += (double)part;
   acc = lb_block_sum(acc, scratch);
-  if (threadIdx.x == 0) atomicAdd(out, acc);
+  lb_grid_sum2_ordered(acc, 0.0, stat_work, out, scratch);             // fixed-order grid sum: reproducible gradients
 }
-// grad[i][j] += dwn[i][j]/sigma - dot/sigma^2 * u[i] v[j]
+// grad[i][j] += dwn[i][j]/sigma - dot/sigma^2 * u[i] v[j].  When the layer's u / v are trainable (see lb_sn_weight_grad):
+// du[i] += c * s_fwd[i] and cacc += c with c = dL/dsigma = -dot/sigma^2.
 __global__ void __launch_bounds__(256) k_sn_wgrad(const float* __restrict__ dwn, const float* __restrict__ u, const float* __restrict__ v,
                                                  const float* __restrict__ sigma, const double* __restrict__ dot,
-                                                 float* __restrict__ grad, int n, const SnIdx x) {
+                                                 float* __restrict__ grad, int n, const SnIdx x, const float* __restrict__ s_fwd,
+                                                 float* __restrict__ du, float* __restrict__ cacc) {
   const float inv = __ldg(sigma + 1);
   const float coef = (float)(dot[0] * (double)inv * (double)inv);
   const int stride = gridDim.x * blockDim.x;
@@ -115,22 +134,24 @@ __global__ void __launch_bounds__(256) k_sn_wgrad(const float* __restrict__ dwn,
     int i, j; size_t off;
     sn_decode(x, k, i, j, off);
     grad[k] += fmaf(dwn[off], inv, -coef * __ldg(u + i) * __ldg(v + j));
+    if (du && k < x.height) du[k] = fmaf(-coef, __ldg(s_fwd + k), du[k]);
+    if (cacc && k == 0) cacc[0] -= coef;
   }
 }
 extern "C" int lb_sn_weight_grad(const float* dwn, const float* w, const float* u, const float* v, const float* sigma,
-                                 float* grad, int height, int width, int packed_taps, double* work, lb_stream_t s) {
-  LB_REQUIRE(dwn && w && u && v && sigma && grad && work && height > 0 && width > 0 && packed_taps >= 0);
+                                 float* grad, int height, int width, int packed_taps, double* dot_out, double* stat_work,
+                                 const float* s_fwd, float* du, float* cacc, lb_stream_t s) {
+  LB_REQUIRE(dwn && w && u && v && sigma && grad && dot_out && stat_work && height > 0 && width > 0 && packed_taps >= 0);
   LB_REQUIRE(packed_taps == 0 || width % packed_taps == 0);
+  LB_REQUIRE((s_fwd && du && cacc) || (!s_fwd && !du && !cacc));
   const size_t n = (size_t)height * width;
   LB_REQUIRE(n < ((size_t)1 << 31) - ((size_t)1 << 24));
-  cudaError_t e = cudaMemsetAsync(work, 0, sizeof(double) * 2, lb_s(s));
-  if (e != cudaSuccess) return (int)e;
   SnIdx x;
   x.width = width; x.height = height; x.taps = packed_taps; x.d1 = packed_taps ? width / packed_taps : width;
   x.d_width = lb_make_fastdiv(width); x.d_taps = lb_make_fastdiv(packed_taps ? packed_taps : 1);
-  k_sn_dot<<<lb_grid_1d(n, 256, 2), 256, 0, lb_s(s)>>>(dwn, w, (int)n, x, work);
+  k_sn_dot<<<lb_grid_1d(n, 256, 2), 256, 0, lb_s(s)>>>(dwn, w, (int)n, x, dot_out, stat_work);
   LB_LAUNCH_CHECK();
-  k_sn_wgrad<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(dwn, u, v, sigma, work, grad, (int)n, x);
+  k_sn_wgrad<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(dwn, u, v, sigma, dot_out, grad, (int)n, x, s_fwd, du, cacc);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
@@ -140,10 +161,11 @@ extern "C" int lb_sn_weight_grad(const float* dwn, const float* w, const float* 
 // layer depend only on (W, u), so all layers can be iterated up front.  Work is flattened into items so that a
 // 37 M-element weight and a 96-element weight share one grid without load imbalance.
 struct LbSnLayerDev {
-  const float* w; float* u; float* v;
-  int height, width, t_off, s_off;
+  const float* w; float* u; float* v; float* dv;
+  int height, width, t_off, s_off, nsplit, rows_per_split;
 };
-// phase 1 item: layer, first column, first row, row count.  t[t_off + j] += sum_rows W[i][j] u[i]
+// phase 1 item: layer, first column, first row, row count.  Row split r0 / rows_per_split of the layer writes its own
+// partial tpart[split][j] = sum_rows W[i][j] u[i] (plain stores: deterministic, nothing to zero first)
 __global__ void __launch_bounds__(256) k_snb_wt_u(const LbSnLayerDev* __restrict__ layers, const int4* __restrict__ items,
                                                  float* __restrict__ scratch) {
   const int4 it = items[blockIdx.x];
@@ -153,19 +175,25 @@ __global__ void __launch_bounds__(256) k_snb_wt_u(const LbSnLayerDev* __restrict
   const int i1 = min(L.height, it.z + it.w);
   float acc = 0.0f;
   for (int i = it.z; i < i1; ++i) acc = fmaf(L.w[(size_t)i * L.width + j], __ldg(L.u + i), acc);
-  atomicAdd(scratch + L.t_off + j, acc);
+  scratch[(size_t)L.t_off + (size_t)(it.z / L.rows_per_split) * L.width + j] = acc;
 }
 // per layer: dst = src/(|src|+eps); phase 2 (v from t) and phase 4 (u from s, sigma)
-__global__ void __launch_bounds__(512) k_snb_normalize(const LbSnLayerDev* __restrict__ layers, const float* __restrict__ scratch,
-                                                      int phase, float* __restrict__ sigma_out) {
+__global__ void __launch_bounds__(512) k_snb_normalize(const LbSnLayerDev* __restrict__ layers, float* __restrict__ scratch,
+                                                      float* __restrict__ s_out, int phase, float* __restrict__ sigma_out) {
   __shared__ float red[32];
   __shared__ float s_norm;
   const LbSnLayerDev L = layers[blockIdx.x];
-  const float* src = scratch + (phase == 2 ? L.t_off : L.s_off);
+  float* src = phase == 2 ? scratch + L.t_off : s_out + L.s_off;
   float* dst = phase == 2 ? L.v : L.u;
   const int n = phase == 2 ? L.width : L.height;
+  const int nsplit = phase == 2 ? L.nsplit : 1;
   float acc = 0.0f;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) { const float v = src[i]; acc = fmaf(v, v, acc); }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float v = src[i];
+    for (int sp = 1; sp < nsplit; ++sp) v += src[(size_t)sp * n + i];     // fixed order over the row splits
+    src[i] = v;
+    acc = fmaf(v, v, acc);
+  }
   acc = lb_block_sum(acc, red);
   if (threadIdx.x == 0) s_norm = sqrtf(acc);
   __syncthreads();
@@ -178,7 +206,7 @@ __global__ void __launch_bounds__(512) k_snb_normalize(const LbSnLayerDev* __res
     sigma_out[2 * blockIdx.x + 1] = 1.0f / sigma;
   }
 }
-// phase 3 item: (layer, first row); 8 rows per CTA, one warp per row.  s[s_off + i] = sum_j W[i][j] v[j]
+// phase 3 item: (layer, first row); 8 rows per CTA, one warp per row.  s_out[s_off + i] = sum_j W[i][j] v[j]
 __global__ void __launch_bounds__(256) k_snb_w_v(const LbSnLayerDev* __restrict__ layers, const int2* __restrict__ items,
                                                 float* __restrict__ scratch) {
   const int2 it = items[blockIdx.x];
@@ -189,22 +217,50 @@ __global__ void __launch_bounds__(256) k_snb_w_v(const LbSnLayerDev* __restrict_
   float acc = 0.0f;
   for (int j = lane; j < L.width; j += 32) acc = fmaf(wr[j], __ldg(L.v + j), acc);
   acc = lb_warp_sum(acc);
-  if (lane == 0) scratch[L.s_off + row] = acc;
+  if (lane == 0) scratch[L.s_off + row] = acc;        // `scratch` is s_out here
 }
 extern "C" int lb_sn_power_iter_batched(const void* layers_dev, int n_layers, const void* items1_dev, int n_items1,
-                                        const void* items3_dev, int n_items3, float* scratch, size_t scratch_floats,
+                                        const void* items3_dev, int n_items3, float* scratch, float* s_out,
                                         float* sigma_out, lb_stream_t s) {
-  LB_REQUIRE(layers_dev && items1_dev && items3_dev && scratch && sigma_out && n_layers > 0 && n_items1 > 0 && n_items3 > 0);
-  cudaError_t e = cudaMemsetAsync(scratch, 0, scratch_floats * sizeof(float), lb_s(s));
-  if (e != cudaSuccess) return (int)e;
+  LB_REQUIRE(layers_dev && items1_dev && items3_dev && scratch && s_out && sigma_out && n_layers > 0 && n_items1 > 0 && n_items3 > 0);
+  // every partial slot is written before it is read: no zero fill
   const LbSnLayerDev* layers = reinterpret_cast<const LbSnLayerDev*>(layers_dev);
   k_snb_wt_u<<<n_items1, 256, 0, lb_s(s)>>>(layers, reinterpret_cast<const int4*>(items1_dev), scratch);
   LB_LAUNCH_CHECK();
-  k_snb_normalize<<<n_layers, 512, 0, lb_s(s)>>>(layers, scratch, 2, sigma_out);
+  k_snb_normalize<<<n_layers, 512, 0, lb_s(s)>>>(layers, scratch, s_out, 2, sigma_out);
   LB_LAUNCH_CHECK();
-  k_snb_w_v<<<n_items3, 256, 0, lb_s(s)>>>(layers, reinterpret_cast<const int2*>(items3_dev), scratch);
+  k_snb_w_v<<<n_items3, 256, 0, lb_s(s)>>>(layers, reinterpret_cast<const int2*>(items3_dev), s_out);
   LB_LAUNCH_CHECK();
-  k_snb_normalize<<<n_layers, 512, 0, lb_s(s)>>>(layers, scratch, 4, sigma_out);
+  k_snb_normalize<<<n_layers, 512, 0, lb_s(s)>>>(layers, scratch, s_out, 4, sigma_out);
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
+
+// Trainable u / v (the reference's main.py:172 quirk: `dis.requires_grad_(True)` also switches on the discriminator's
+// weight_u / weight_v, whose sigma = u.(W v) then hands them gradients):  dv += C * W^T u with the LIVE u, where
+// C = sum over the backward passes of dL/dsigma (accumulated in cacc by lb_sn_weight_grad; reset here).  One extra pass
+// over the weights per optimizer step, reusing the pass-1 kernel of the power iteration.
+__global__ void __launch_bounds__(512) k_snb_dv(const LbSnLayerDev* __restrict__ layers, const float* __restrict__ scratch,
+                                               float* __restrict__ cacc) {
+  const LbSnLayerDev L = layers[blockIdx.x];
+  const float c = cacc[blockIdx.x];
+  __syncthreads();
+  if (threadIdx.x == 0) cacc[blockIdx.x] = 0.0f;
+  if (!L.dv || c == 0.0f) return;
+  const float* src = scratch + L.t_off;
+  for (int j = threadIdx.x; j < L.width; j += blockDim.x) {
+    float t = src[j];
+    for (int sp = 1; sp < L.nsplit; ++sp) t += src[(size_t)sp * L.width + j];
+    L.dv[j] = fmaf(c, t, L.dv[j]);
+  }
+}
+extern "C" int lb_sn_uv_grad_batched(const void* layers_dev, int n_layers, const void* items1_dev, int n_items1, float* scratch,
+                                     float* cacc, lb_stream_t s) {
+  LB_REQUIRE(layers_dev && items1_dev && scratch && cacc && n_layers > 0 && n_items1 > 0);
+  const LbSnLayerDev* layers = reinterpret_cast<const LbSnLayerDev*>(layers_dev);
+  k_snb_wt_u<<<n_items1, 256, 0, lb_s(s)>>>(layers, reinterpret_cast<const int4*>(items1_dev), scratch);
+  LB_LAUNCH_CHECK();
+  k_snb_dv<<<n_layers, 512, 0, lb_s(s)>>>(layers, scratch, cacc);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }

@@ -42,6 +42,12 @@ class _ArenaModel(nn.Module):
             self.__dict__["_lb_sn_batch"] = batch
         batch.run()
 
+    def _finish_uv_grads(self):
+        """Gradients of trainable spectral-norm weight_v's (the reference's main.py:172 quirk, sn_batch.py)."""
+        batch = self.__dict__.get("_lb_sn_batch")
+        if batch is not None:
+            batch.finish_uv_grads()
+
     def zero_grad(self, set_to_none=True):
         opt = self.__dict__.get("_lb_optimizer")
         if opt is not None:

@@ -118,11 +118,26 @@ def _bpc(t):
     return t.shape[0], 1, t.shape[1]
 
 
+_STAT_WORK = {}
+
+
+def _stat_work(device):
+    """Scratch of the ordered grid reductions (lb_norm_stats / lb_gate_fwd_stats): zero-filled once, the kernels leave it
+    zeroed.  One per device: every kernel of this library runs on torch's current stream, in order."""
+    key = (device.type, device.index)
+    w = _STAT_WORK.get(key)
+    if w is None:
+        w = torch.zeros(_lib.lib().lb_stat_work_doubles(), dtype=torch.float64, device=device)
+        _STAT_WORK[key] = w
+    return w
+
+
 def _grad_sink(param):
     """(buffer the kernels accumulate into, value to hand back to autograd)."""
     arena = getattr(param, "_lb_grad", None)
     if arena is not None:
-        if param.grad is None:
+        if param.grad is None:                      # a plain nn.Module.zero_grad(set_to_none=True) dropped it: start from zero
+            call("lb_fill", ptr(arena), arena.numel(), 0.0)
             param.grad = arena
         return arena, None
     fresh = torch.zeros_like(param, memory_format=torch.contiguous_format)
@@ -227,8 +242,8 @@ class WholeNormFn(torch.autograd.Function):
         if ready is not None:
             sums = ready.clone()                  # the producer (gate kernel) already reduced them; clone: all-reduced in place
         else:
-            sums = torch.zeros(2, dtype=torch.float64, device=x.device)
-            call("lb_norm_stats", ptr(x), x.numel(), ptr(sums))
+            sums = torch.empty(2, dtype=torch.float64, device=x.device)
+            call("lb_norm_stats", ptr(x), x.numel(), ptr(sums), ptr(_stat_work(x.device)))
         n_total = float(x.numel()) * dist.all_reduce_sum_(sums)
         stats = torch.empty(4, dtype=torch.float32, device=x.device)
         call("lb_norm_finalize", ptr(sums), n_total, ptr(stats))
@@ -301,8 +316,8 @@ class GateFn(torch.autograd.Function):
         out = torch.empty_like(x)
         if x.dim() == 4 and c % 4 == 0 and x.numel() < (1 << 32):
             # every gate output is normalised next (block.py:46-51): leave its (sum, sum^2) for WholeNormFn
-            sums = torch.zeros(2, dtype=torch.float64, device=x.device)
-            call("lb_gate_fwd_stats", ptr(x), ptr(y), ptr(gamma), ptr(out), ptr(sums), b, p, c, int(bcast))
+            sums = torch.empty(2, dtype=torch.float64, device=x.device)
+            call("lb_gate_fwd_stats", ptr(x), ptr(y), ptr(gamma), ptr(out), ptr(sums), ptr(_stat_work(x.device)), b, p, c, int(bcast))
             out._lb_sums = sums
         else:
             call("lb_gate_fwd", ptr(x), ptr(y), ptr(gamma), ptr(out), b, p, c, int(bcast))

@@ -48,6 +48,7 @@ def get_model(model, learning_rate, device):
     opt = Nadam(model.parameters(), lr=learning_rate, betas=(CFG.BETA_1, CFG.BETA_2))
     if hasattr(model, "zero_grad") and hasattr(type(model), "_lb_optimizer"):
         model.__dict__["_lb_optimizer"] = opt
+        opt._lb_model = model
     return model, opt
 
 
@@ -62,6 +63,9 @@ class GanTrainer:
         self._copy_stream = self._stage_bufs = self._staged = self._consumed = None
 
     def _reduce_and_step(self, opt):
+        model = getattr(opt, "_lb_model", None)
+        if model is not None:
+            model._finish_uv_grads()       # complete the gradients of trainable spectral-norm v's BEFORE they are reduced
         for h in [h for flat in opt.flat_grads for h in dist.all_reduce_grads_(flat)]:
             h.wait()
         opt.step()
@@ -137,6 +141,9 @@ class GanTrainer:
         the captured static buffers and the graph is replayed."""
         if self._graph is None:
             return self._eager_step(real, aug, z)
+        if tuple(tuple(t.shape) for t in (real, aug, z)) != self._graph_shapes:
+            raise ValueError(f"the captured graph is frozen to input shapes {self._graph_shapes}; "
+                             "call release_graph() / capture() again for another batch shape")
         for dst, src in zip(self._static_in, (real, aug, z)):
             if dst.data_ptr() != src.data_ptr():
                 dst.copy_(src, non_blocking=True)
@@ -145,10 +152,9 @@ class GanTrainer:
             self._consumed.record()
         self._graph.replay()
         for opt in (self.d_opt, self.g_opt):          # host mirrors of the device-side step counters
-            for a in opt._arenas:
-                if a is not None:
-                    a["step"] += 1
-                    a["epoch"][0] += 1
+            for a in opt.live_arenas():
+                a["step"] += 1
+                a["epoch"][0] += 1
         return self._static_out
 
     def prefetch(self, real, aug, z):
@@ -158,10 +164,14 @@ class GanTrainer:
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream()
             self._staged = None
+        cs = self._copy_stream
         if self._stage_bufs is None or any(b.shape != t.shape for b, t in zip(self._stage_bufs, (real, aug, z))):
             dev = next(self.gen.parameters()).device
             self._stage_bufs = tuple(torch.empty(t.shape, dtype=t.dtype, device=dev) for t in (real, aug, z))
-        cs = self._copy_stream
+            # the caching allocator may hand back blocks that kernels still queued on the compute stream read:
+            # order the first copy after everything enqueued so far
+            cs.wait_stream(torch.cuda.current_stream())
+            self._consumed = None
         if self._consumed is not None:                    # the previous batch has left the staging buffers
             cs.wait_event(self._consumed)
         with torch.cuda.stream(cs):
@@ -190,7 +200,9 @@ class GanTrainer:
         steps first (lazy initialisation, allocator warm-up), which train the model like any other step."""
         from .conv_fn import invalidate_packs
         shapes = tuple(tuple(t.shape) for t in (real, aug, z))
-        self._static_in = tuple(torch.empty_like(t).copy_(t) for t in (real, aug, z))
+        dev = next(self.gen.parameters()).device          # static inputs live on the model's device even for (pinned) host batches
+        self._static_in = tuple(torch.empty(t.shape, dtype=t.dtype, device=dev).copy_(t) for t in (real, aug, z))
+        warmup = max(int(warmup), 1)                      # the first step switches D's u / v on (main.py:172): capture the steady state
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):

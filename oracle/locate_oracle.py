@@ -195,16 +195,25 @@ class _LiveSigma(torch.autograd.Function):
     several times before one backward (the three discriminator passes of a D step,
     main.py:149-156), every pass's d(sigma)/dW = u v^T term is evaluated with the LATEST u, v.
     Verified against the reference's gradients in tests/golden/step_*.pt.
+
+    u and v themselves are requires_grad=False Parameters (spectral_norm.py:45-46) -- until the training loop's
+    `dis.requires_grad_(True)` (main.py:172) switches them on for the discriminator.  From then on autograd hands them
+    d(sigma)/du = W v (the mv OUTPUT saved at forward time, i.e. with that pass's v) and d(sigma)/dv = W^T u (u read
+    at backward time) and Nadam moves them (tests/golden/steps3_*.pt).
     """
 
     @staticmethod
     def forward(ctx, mat, u, v):
         ctx.u, ctx.v = u, v          # live references, deliberately not save_for_backward
-        return torch.dot(u, mat.mv(v))
+        ctx.mat = mat.detach()
+        ctx.wv = ctx.mat.mv(v.detach())     # torch.dot saved this tensor: fixed at forward time
+        return torch.dot(u.detach(), ctx.wv)
 
     @staticmethod
     def backward(ctx, g):
-        return g * torch.outer(ctx.u.detach(), ctx.v.detach()), None, None
+        du = g * ctx.wv if ctx.needs_input_grad[1] else None
+        dv = g * ctx.mat.t().mv(ctx.u.detach()) if ctx.needs_input_grad[2] else None
+        return g * torch.outer(ctx.u.detach(), ctx.v.detach()), du, dv
 
 
 def power_iterate(state: State, prefix: str, eps: float = 1e-12) -> torch.Tensor:
@@ -456,7 +465,9 @@ def train_step(g_state: State, d_state: State, const_noise, real, aug, z, cfg: O
     (d_err + pen).backward()
     if d_opt is not None:
         d_opt.step(d_state)
-    trainable = {k: p.requires_grad for k, p in d_state.items()}
+    # main.py:160,172: dis.requires_grad_(False) ... dis.requires_grad_(True) -- the second call also switches on the
+    # discriminator's weight_u / weight_v (see _LiveSigma); the non-strict mode keeps them frozen
+    trainable = {k: (True if strict_reference else p.requires_grad) for k, p in d_state.items()}
     for p in d_state.values():
         p.requires_grad_(False)
     _zero_grads(g_state)

@@ -228,8 +228,49 @@ def full_model(tag, batch, **overrides):
     save(f"{tag}.pt", rec)
 
 
+def multi_step(tag, batch, steps, **overrides):
+    """`steps` consecutive training steps of the reference (main.py:142-172, miniter = MINIBATCHES = DITERS = 1) on the
+    same batch.  Pins what a single step cannot: `dis.requires_grad_(True)` at main.py:172 also switches on the
+    discriminator's weight_u / weight_v (requires_grad=False Parameters, spectral_norm.py:45-46), so from the SECOND
+    discriminator step on they receive gradients through sigma = u.(W v) and Nadam -- whose parameter list holds them
+    since construction (utils.py:149) -- moves them, each with its own step counter / momentum schedule."""
+    libs = ref_loader.load_ref(**overrides)
+    cfg = sys.modules["libs.config"]
+    with ref_loader.quiet():
+        torch.manual_seed(999)
+        gen, g_opt = libs.get_model(libs.Generator(), cfg.GLR, cfg.DEVICE)
+        dis, d_opt = libs.get_model(libs.Discriminator(), cfg.DLR, cfg.DEVICE)
+    s, zdim = cfg.IMAGE_SIZE, cfg.INPUT_VECTOR_Z
+    real = randn(batch, 3, s, s, seed=0).clamp(-1, 1)
+    aug = (real + 0.05 * randn(batch, 3, s, s, seed=1)).clamp(-1, 1)
+    z = randn(batch, zdim, seed=2)
+    rec = dict(overrides=overrides, batch=batch, steps=steps, real=real, aug=aug, z=z, const_noise=gen.noise.clone(),
+               g_state=sd(gen), d_state=sd(dis), losses=[], d_uv_grads=[], d_state_per_step=[], g_state_per_step=[])
+    for _ in range(steps):
+        generated = gen(z).detach()
+        dis.zero_grad()
+        d_true = dis(real).view(-1)
+        d_gen = -dis(generated).view(-1)
+        d_error = (libs.hinge(d_true) + libs.hinge(d_gen)).mean()
+        pen = libs.penalty(d_true, aug, dis, cfg.DEVICE)
+        (d_error + pen).backward()
+        rec["d_uv_grads"].append({k: g for k, g in grads(dis).items() if k.endswith(("_u", "_v"))})
+        d_opt.step()
+        dis.requires_grad_(False)
+        gen.zero_grad()
+        g_error = libs.hinge(dis(gen(z)).view(-1)).mean()
+        g_error.backward()
+        g_opt.step()
+        dis.requires_grad_(True)
+        rec["losses"].append((d_error.item(), pen.item(), g_error.item()))
+        rec["d_state_per_step"].append(sd(dis))
+        rec["g_state_per_step"].append(sd(gen))
+    save(f"{tag}.pt", rec)
+
+
 if __name__ == "__main__":
     libs = ref_loader.load_ref()
     save("primitives.pt", primitives(libs))
     full_model("step_s32_w2_b3", 3, IMAGE_SIZE=32, BASE_FEATURE_FACTOR=2)
     full_model("step_s16_w2_depth3_b2", 2, IMAGE_SIZE=16, BASE_FEATURE_FACTOR=2, DEPTH=3)
+    multi_step("steps3_s16_w2_b2", 2, 3, IMAGE_SIZE=16, BASE_FEATURE_FACTOR=2)

@@ -102,6 +102,9 @@ def test_step_bf16_vs_oracle_default_width(size, batch, depth):
     d_out, g_out = L.GanTrainer(gen, dis, g_opt, d_opt).step(real.float().to(DEV), aug.float().to(DEV), z.float().to(DEV))
     assert abs(d_out[0].item() - o_d.item()) < 2e-2 * abs(o_d.item())
     assert abs(g_out[0].item() - o_g.item()) < 2e-2 * abs(o_g.item())
+    # the penalty 100 (mean D(real) - mean D(aug))^2 is the square of a DIFFERENCE of two nearly equal means: its
+    # relative error is twice that of the difference, which the bf16 GEMMs perturb at ~1e-2 of the logits' spread
+    assert abs(d_out[1].item() - o_pen.item()) < 0.15 * abs(o_pen.item()) + 2e-6, (d_out[1].item(), o_pen.item())
     for tag in ("d", "g"):
         keys = sorted(grads[tag])
         a = torch.cat([mine[tag][k].double().cpu().reshape(-1) for k in keys])
@@ -120,6 +123,45 @@ def test_step_bf16_vs_oracle_default_width(size, batch, depth):
             return not (size == 256 and grads[tag][k].numel() == 1)
         worst = max((rel_l2(mine[tag][k], grads[tag][k]), k) for k in keys if checked(k))
         assert worst[0] < (5e-2 if size == 32 else 8e-2) or (worst[1].endswith("gamma") and worst[0] < 0.15), worst
+
+
+def test_step_bf16_vs_oracle_128_batch32():
+    """The headline resolution at a batch where the tile counts, batch tiling and split-K choices differ from the
+    batch-2 case above (bench.py runs batch 512 and gates itself against the fp32 kernels at that size): losses and
+    the concatenated gradients against the fp32 CPU oracle."""
+    size, batch = 128, 32
+    L.configure(IMAGE_SIZE=size)
+    cfg = O.OracleConfig(IMAGE_SIZE=size)
+    torch.manual_seed(999)
+    gen, g_opt = L.get_model(L.Generator(), L.CFG.GLR, DEV)
+    dis, d_opt = L.get_model(L.Discriminator(), L.CFG.DLR, DEV)
+    gs = O.load_state({k: v.cpu() for k, v in gen.state_dict().items()})
+    ds = O.load_state({k: v.cpu() for k, v in dis.state_dict().items()})
+    real, aug, z = O.synthetic_batch(cfg, batch)
+    grads = {}
+
+    class Spy(O.Nadam):
+        def __init__(self, tag):
+            self.tag = tag
+
+        def step(self, state):
+            grads[self.tag] = {k: p.grad.clone() for k, p in state.items() if p.grad is not None}
+    o_d, o_pen, o_g = O.train_step(gs, ds, gen.noise.cpu(), real, aug, z, cfg, Spy("g"), Spy("d"))
+    mine = {}
+    for tag, opt, model in (("d", d_opt, dis), ("g", g_opt, gen)):
+        def spy(closure=None, tag=tag, model=model):
+            mine[tag] = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.requires_grad}
+        opt.step = spy
+    d_out, g_out = L.GanTrainer(gen, dis, g_opt, d_opt).step(real.to(DEV), aug.to(DEV), z.to(DEV))
+    assert abs(d_out[0].item() - o_d.item()) < 2e-2 * abs(o_d.item())
+    assert abs(g_out[0].item() - o_g.item()) < 2e-2 * abs(o_g.item())
+    assert abs(d_out[1].item() - o_pen.item()) < 0.15 * abs(o_pen.item()) + 2e-6, (d_out[1].item(), o_pen.item())
+    for tag in ("d", "g"):
+        keys = sorted(grads[tag])
+        a = torch.cat([mine[tag][k].double().cpu().reshape(-1) for k in keys])
+        b = torch.cat([grads[tag][k].double().reshape(-1) for k in keys])
+        total = ((a - b).norm() / b.norm()).item()
+        assert total < 2.3e-2, f"{tag}: relative gradient-norm error {total:.3e}"
 
 
 @pytest.mark.parametrize("args,shape", [
@@ -205,7 +247,7 @@ def test_cuda_graph_replay_matches_eager():
         torch.cuda.synchronize()
         outs[mode] = (d_out.clone().cpu(), g_out.clone().cpu(),
                       torch.cat([p.detach().reshape(-1) for p in dis.parameters()]).cpu(),
-                      [a["sched"].cpu() for a in d_opt._arenas])
+                      [a["sched"].cpu() for a in d_opt.live_arenas()])
     e, e2, g = outs["eager"], outs["eager2"], outs["graph"]
     assert torch.equal(e[3][0], g[3][0]), "device-side Nadam step counters differ"
     assert float(e[3][0][0]) == 4.0
@@ -288,4 +330,6 @@ def test_reference_schedule_and_checkpoint_round_trip(tmp_path):
     with torch.no_grad():
         a, b = gen(z), gen2(z)
     torch.cuda.synchronize()
-    assert rel_l2(a, b) < 1e-5
+    # same checkpoint, same input -> same images, bit for bit (the forward pass has no floating-point atomics;
+    # tests/test_gpu_parity.py::test_forward_is_bit_reproducible)
+    assert torch.equal(a, b), rel_l2(a, b)

@@ -323,6 +323,77 @@ def test_full_training_step_golden(golden, name):
         close(dsd[k], v, rtol=2e-3, atol_frac=2e-3, what="D final " + k)
 
 
+def test_three_training_steps_golden(golden):
+    """Three consecutive steps against the REAL reference (tests/golden/steps3_*.pt): from the second discriminator step
+    on the reference trains D's weight_u / weight_v (main.py:172 switches them on, sigma = u.(W v) at
+    spectral_norm.py:31 hands them gradients, Nadam holds them since utils.py:149) -- losses, the u / v gradients and
+    the u / v themselves after every step must follow."""
+    r = golden("steps3_s16_w2_b2.pt")
+    gen, dis, g_opt, d_opt = _build(r)
+    trainer = L.GanTrainer(gen, dis, g_opt, d_opt)
+    real, aug, z = dev(r["real"]), dev(r["aug"]), dev(r["z"])
+    uv = {}
+    orig = d_opt.step
+
+    def spy(closure=None):
+        dis._finish_uv_grads()
+        uv.clear()
+        uv.update({k: p.grad.detach().clone() for k, p in dis.named_parameters()
+                   if k.endswith(("_u", "_v")) and p.requires_grad and p.grad is not None})
+        return orig()
+    d_opt.step = spy
+    for step in range(r["steps"]):
+        d_out, g_out = trainer.step(real, aug, z)
+        want = r["losses"][step]
+        assert abs(d_out[0].item() - want[0]) < 1e-3 * abs(want[0]), (step, d_out[0].item(), want)
+        assert abs(d_out[1].item() - want[1]) < 2e-2 * abs(want[1]) + 1e-7, (step, d_out[1].item(), want)
+        assert abs(g_out[0].item() - want[2]) < 2e-3 * abs(want[2]), (step, g_out[0].item(), want)
+        assert set(uv) == set(r["d_uv_grads"][step]), (step, sorted(uv))
+        for k, g in r["d_uv_grads"][step].items():
+            close(uv[k], g, rtol=1e-2, atol_frac=1e-2, what=f"step {step} grad {k}")
+        dsd = dis.state_dict()
+        for k, v in r["d_state_per_step"][step].items():
+            if k.endswith(("_u", "_v")):
+                close(dsd[k], v, rtol=1e-2, atol_frac=1e-2, what=f"step {step} {k}")
+    assert len(r["d_uv_grads"][1]) > 0
+
+
+def test_forward_is_bit_reproducible(golden):
+    """The reference is deterministic (plain torch.mv / conv on CPU): the same state must give the same images, logits
+    and u / v, run after run and model instance after model instance (parameters re-homed in the optimizer arena or
+    freshly allocated).  No floating-point atomics on the forward path: spectral-norm partial sums, split-K partial
+    tiles and the norm statistics are all reduced in a fixed order."""
+    r = golden("step_s32_w2_b3.pt")
+    z, real = dev(r["z"]), dev(r["real"])
+    outs = []
+    for trial in range(3):
+        L.config.reset()
+        L.configure(PRECISION="bf16", **r["overrides"])   # the product (tensor-core) path, split-K layers included
+        gen, dis = L.Generator().to(DEV), L.Discriminator().to(DEV)
+        if trial == 1:                                   # parameters as views of the flat Nadam arena
+            L.Nadam(gen.parameters(), lr=1e-3)
+            L.Nadam(dis.parameters(), lr=1e-3)
+        gen.load_state_dict(r["g_state"])
+        dis.load_state_dict(r["d_state"])
+        gen.noise = dev(r["const_noise"])
+        with torch.no_grad():
+            img = gen(z)
+            logit = dis(real)
+            img2 = gen(z)                                # second call: u / v have advanced, as in the reference
+        torch.cuda.synchronize()
+        outs.append((img.clone(), logit.clone(), img2.clone(),
+                     {k: v.clone() for k, v in gen.state_dict().items() if k.endswith(("_u", "_v"))},
+                     {k: v.clone() for k, v in dis.state_dict().items() if k.endswith(("_u", "_v"))}))
+    for other in outs[1:]:
+        assert torch.equal(outs[0][0], other[0]), "G(z) differs between runs"
+        assert torch.equal(outs[0][1], other[1]), "D(x) differs between runs"
+        assert torch.equal(outs[0][2], other[2]), "second G(z) differs between runs"
+        for a, b in ((outs[0][3], other[3]), (outs[0][4], other[4])):
+            for k in a:
+                assert torch.equal(a[k], b[k]), k
+    assert not torch.equal(outs[0][0], outs[0][2])       # every forward runs a power iteration (spectral_norm.py:57-59)
+
+
 def test_step_vs_oracle_default_width():
     """32x32 with the reference's default channel widths, batch 4, vs the CPU oracle."""
     L.configure(IMAGE_SIZE=32)

@@ -137,8 +137,11 @@ def test_tc_wgrad_matches_simt(name):
     sigma = torch.tensor([2.0, 0.5], device=DEV)
     ga, gb = torch.zeros(shape, device=DEV), torch.zeros(shape, device=DEV)
     work = torch.empty(2, dtype=torch.float64, device=DEV)
-    call("lb_sn_weight_grad", ptr(ref), ptr(wbar), ptr(u), ptr(v), ptr(sigma), ptr(ga), d0, d1 * t, 0, ptr(work))
-    call("lb_sn_weight_grad", ptr(dwp), ptr(wbar), ptr(u), ptr(v), ptr(sigma), ptr(gb), d0, d1 * t, t, ptr(work))
+    stat_work = torch.zeros(_lib.lib().lb_stat_work_doubles(), dtype=torch.float64, device=DEV)
+    call("lb_sn_weight_grad", ptr(ref), ptr(wbar), ptr(u), ptr(v), ptr(sigma), ptr(ga), d0, d1 * t, 0, ptr(work), ptr(stat_work),
+         None, None, None)
+    call("lb_sn_weight_grad", ptr(dwp), ptr(wbar), ptr(u), ptr(v), ptr(sigma), ptr(gb), d0, d1 * t, t, ptr(work), ptr(stat_work),
+         None, None, None)
     torch.cuda.synchronize()
     assert (ga - gb).abs().max().item() <= 3e-4 * ga.abs().max().item() + 1e-5
 
