@@ -279,15 +279,19 @@ def attention_bench(res, batch, peaks, reps=5):
     for net, feat, size in attention_shapes(res):
         torch.manual_seed(11)
         m = layers.ResModule(layers.identity, layers.Norm(feat, layers.SelfAttention(feat))).to("cuda")
-        x = torch.randn((batch, feat, size, size), device="cuda").contiguous(memory_format=torch.channels_last).requires_grad_(True)
-        g = torch.randn((batch, feat, size, size), device="cuda").contiguous(memory_format=torch.channels_last)
+        from locate_b200 import ops
+        st_dtype = ops.store_dtype((batch, feat, size, size))          # activations arrive in the model's storage type
+        x32 = torch.randn((batch, feat, size, size), device="cuda").contiguous(memory_format=torch.channels_last)
+        g32 = torch.randn((batch, feat, size, size), device="cuda").contiguous(memory_format=torch.channels_last)
+        x = x32.to(st_dtype).requires_grad_(True)
+        g = g32.to(st_dtype)
 
         def mine():
             x.grad = None
             m(x).backward(g)
         st = O.load_state({k: v.detach().clone() for k, v in m.state_dict().items()})
-        xe = x.detach().contiguous().requires_grad_(True)
-        ge = g.contiguous()
+        xe = x32.contiguous().requires_grad_(True)
+        ge = g32.contiguous()
 
         def eager(autocast=False):
             xe.grad = None
@@ -320,7 +324,7 @@ def attention_bench(res, batch, peaks, reps=5):
                      "frac_of_cap": tf / peaks["tflops"] / cap,
                      "torch_eager_fp32_ms": ms_eager, "torch_eager_bf16_autocast_ms": ms_autocast,
                      "speedup_vs_eager_fp32": ms_eager / ms, "speedup_vs_eager_bf16": ms_autocast / ms})
-        del m, x, g, xe, ge, st
+        del m, x, g, xe, ge, st, x32, g32
         torch.cuda.empty_cache()
     return rows
 

@@ -27,6 +27,10 @@ extern "C" {
 
 typedef struct CUstream_st* lb_stream_t; /* == cudaStream_t */
 
+/* storage type of activations and their gradients (the `dtype` argument of the elementwise / reduction entry points):
+ * arithmetic is fp32 either way; bf16 storage is the tensor-core configuration (half the HBM bytes of every pass). */
+enum { LB_F32 = 0, LB_BF16 = 1 };
+
 enum {
   LB_OK = 0,
   LB_EINVAL = -1,   /* bad size / null pointer / unsupported combination */
@@ -42,11 +46,13 @@ void lb_reset_launch_count(void);
 
 /* ---- RootTanh activation: y = (x^2+1)^(1/growth) * tanh(x)          libs/activation.py:9-16
  *      bwd: dx = g * (2(x^2+1) sech^2 x + x tanh x) / (2 (x^2+1)^((growth-1)/growth))  :20-36 */
-int lb_roottanh_fwd(const float* x, float* y, size_t n, int growth, lb_stream_t stream);
-int lb_roottanh_bwd(const float* x, const float* g, float* dx, size_t n, int growth, lb_stream_t stream);
+int lb_roottanh_fwd(const void* x, void* y, size_t n, int growth, int dtype, lb_stream_t stream);
+int lb_roottanh_bwd(const void* x, const void* g, void* dx, size_t n, int growth, int dtype, lb_stream_t stream);
 /* tanh on the generator output                                          libs/models.py:66 */
-int lb_tanh_fwd(const float* x, float* y, size_t n, lb_stream_t stream);
-int lb_tanh_bwd(const float* y, const float* g, float* dx, size_t n, lb_stream_t stream);
+int lb_tanh_fwd(const void* x, void* y, size_t n, int dtype, lb_stream_t stream);
+int lb_tanh_bwd(const void* y, const void* g, void* dx, size_t n, int dtype, lb_stream_t stream);
+/* y = a + b (the sum autograd forms when a tensor feeds two branches, e.g. block.py:44-46 skip path + gated branch) */
+int lb_add(const void* a, const void* b, void* y, size_t n, int dtype, lb_stream_t stream);
 
 /* hinge(t) = max(1 - t, 0) elementwise                                   libs/utils.py:133-134 */
 int lb_hinge_fwd(const float* x, float* y, size_t n, lb_stream_t stream);
@@ -60,44 +66,47 @@ int lb_hinge_bwd(const float* x, const float* g, float* dx, size_t n, lb_stream_
  * statistics -- and with them the whole forward pass -- are bit-reproducible like the reference's.  `work`:
  * lb_stat_work_doubles() doubles, zero-filled ONCE when allocated (the kernels leave it zeroed); one per stream. */
 size_t lb_stat_work_doubles(void);
-int lb_norm_stats(const float* x, size_t n, double* sums, double* work, lb_stream_t stream);
+int lb_norm_stats(const void* x, size_t n, double* sums, double* work, int dtype, lb_stream_t stream);
 int lb_norm_finalize(const double* sums, double n_total, float* stats, lb_stream_t stream);
-/* y = (x-mean)*gain/std + bias ; gain is [C] (gain_batch_stride = 0) or [B][C] (stride = C). */
-int lb_norm_apply(const float* x, const float* stats, const float* gain, int gain_batch_stride,
-                  const float* bias, float* y, int batch, int pixels, int channels, lb_stream_t stream);
-/* same, also emitting the bf16 operand of the GEMM that consumes the result: y16 = bf16(act16 ? RootTanh(y) : y)
- * (conv.py:23-24 applies RootTanh first; attention.py:44 and :26 do not).  y may be NULL when only the GEMM reads the
- * result.  Needs channels % 4 == 0 and 16-byte aligned pointers (LB_EALIGN otherwise: use lb_norm_apply + lb_cast_bf16). */
-int lb_norm_apply_ex(const float* x, const float* stats, const float* gain, int gain_batch_stride, const float* bias,
-                     float* y, void* y16, int act16, int batch, int pixels, int channels, lb_stream_t stream);
+/* y = (x-mean)*gain/std + bias ; gain is [C] (gain_batch_stride = 0) or [B][C] (stride = C); x, y in storage `dtype`,
+ * statistics / gain / bias always fp32. */
+int lb_norm_apply(const void* x, const float* stats, const float* gain, int gain_batch_stride,
+                  const float* bias, void* y, int batch, int pixels, int channels, int dtype, lb_stream_t stream);
+/* same, also emitting act = RootTanh(y), the operand of the convolution that consumes the result (conv.py:23-24), in
+ * the same pass; y may be NULL when nothing else reads it.  Needs channels % 4 == 0 and aligned pointers (LB_EALIGN
+ * otherwise: use lb_norm_apply + lb_roottanh_fwd). */
+int lb_norm_apply_ex(const void* x, const float* stats, const float* gain, int gain_batch_stride, const float* bias,
+                     void* y, void* act, int batch, int pixels, int channels, int dtype, lb_stream_t stream);
 /* backward, 3 steps (inplace_norm.py:17-27 composed with d std/dx):
  *  1. lb_norm_bwd_reduce: p1[b][c] += sum_hw g, p2[b][c] += sum_hw (x-mean)*g      (caller zeroes p1,p2)
  *  2. lb_norm_bwd_finalize: dgain (+=, [C] or [B][C]), dbias (+=, [C]), s[2] = {sum gain*p1, sum gain*p2}
  *     (double; in data parallel the caller all-reduces s)
- *  3. lb_norm_bwd_apply: dx = gain*g/std - s0/(std*N) - s1*(x-mean)/((N-1)*std^3)                   */
-int lb_norm_bwd_reduce(const float* x, const float* g, const float* stats, float* p1, float* p2,
-                       int batch, int pixels, int channels, lb_stream_t stream);
+ *  3. lb_norm_bwd_apply: dx = gain*g/std - s0/(std*N) - s1*(x-mean)/((N-1)*std^3) (+ add, optional: the gradient
+ *     reaching x through another branch, summed in the same pass)                                     */
+int lb_norm_bwd_reduce(const void* x, const void* g, const float* stats, float* p1, float* p2,
+                       int batch, int pixels, int channels, int dtype, lb_stream_t stream);
 int lb_norm_bwd_finalize(const float* p1, const float* p2, const float* gain, int gain_batch_stride,
                          const float* stats, int batch, int channels, float* dgain, float* dbias,
                          double* s, lb_stream_t stream);
-int lb_norm_bwd_apply(const float* x, const float* g, const float* stats, const float* gain,
-                      int gain_batch_stride, const double* s, float* dx, int batch, int pixels,
-                      int channels, lb_stream_t stream);
+int lb_norm_bwd_apply(const void* x, const void* g, const float* stats, const float* gain,
+                      int gain_batch_stride, const double* s, const void* add, void* dx, int batch, int pixels,
+                      int channels, int dtype, lb_stream_t stream);
 
 /* ---- gated residual: out = (gamma*y + 1)*x                            libs/merge.py:19-39
  * y is a full tensor (y_bcast = 0) or a per-(b,c) gate [B][C] broadcast over pixels (y_bcast = 1;
- * the Expand of feature attention, libs/util_modules.py:6-12, never materialised).
- * bwd: dx = (gamma*y+1)*g ; dy = gamma*x*g (summed over pixels when y_bcast; caller zeroes dy then);
- *      dgamma += sum x*x*g when strict_reference (the reference's formula, merge.py:33-38)
+ * the Expand of feature attention, libs/util_modules.py:6-12, never materialised).  x, y, out, g, dx, dy share one
+ * storage type (`dtype`).
+ * bwd: dx = (gamma*y+1)*g ; dy = gamma*x*g, or -- y_bcast -- dy_bcast[b][c] += gamma * sum_pixels x*g (fp32, zeroed by the
+ *      caller); dgamma += sum x*x*g when strict_reference (the reference's formula, merge.py:33-38)
  *                or sum x*y*g otherwise.  gamma is a device scalar. */
-int lb_gate_fwd(const float* x, const float* y, const float* gamma, float* out, int batch, int pixels,
-                int channels, int y_bcast, lb_stream_t stream);
+int lb_gate_fwd(const void* x, const void* y, const float* gamma, void* out, int batch, int pixels,
+                int channels, int y_bcast, int dtype, lb_stream_t stream);
 /* same, also writing sums[2] (fp64) = (sum out, sum out^2): the statistics of the whole-tensor norm that consumes every
  * gate output (block.py:46-51), without re-reading it (work: as lb_norm_stats).  channels % 4 == 0, aligned pointers. */
-int lb_gate_fwd_stats(const float* x, const float* y, const float* gamma, float* out, double* sums, double* work, int batch,
-                      int pixels, int channels, int y_bcast, lb_stream_t stream);
-int lb_gate_bwd(const float* x, const float* y, const float* gamma, const float* g, float* dx, float* dy,
-                float* dgamma, int batch, int pixels, int channels, int y_bcast, int strict_reference,
+int lb_gate_fwd_stats(const void* x, const void* y, const float* gamma, void* out, double* sums, double* work, int batch,
+                      int pixels, int channels, int y_bcast, int dtype, lb_stream_t stream);
+int lb_gate_bwd(const void* x, const void* y, const float* gamma, const void* g, void* dx, void* dy, float* dy_bcast,
+                float* dgamma, int batch, int pixels, int channels, int y_bcast, int strict_reference, int dtype,
                 lb_stream_t stream);
 
 /* ---- spectral norm power iteration, one per forward                   libs/spectral_norm.py:21-32
@@ -168,13 +177,15 @@ int lb_conv_wgrad(const float* gathered, const float* dense, float* dw, const lb
  * multiplies the result by RootTanh'(xpre[pixel][n]) (activation.py:18-36) -- the input-gradient direction.  Geometry and
  * weight addressing are those of lb_conv_gemm / lb_conv_wgrad; growth_gathered applies RootTanh to the gathered operand. */
 int lb_conv_small_supported(const lb_conv_geom* g);
-int lb_conv_small(const float* in, const float* w, const float* alpha, const float* bias, float* out, const lb_conv_geom* g,
-                  int growth_in, const float* xpre, int ld_xpre, int growth_out, int cat_input, lb_stream_t stream);
+int lb_conv_small(const void* in, const float* w, const float* alpha, const float* bias, void* out, const lb_conv_geom* g,
+                  int growth_in, const void* xpre, int ld_xpre, int growth_out, int cat_input, int wide_dtype, lb_stream_t stream);
+/* The side with <= 4 channels is always fp32; wide_dtype is the storage of the other side (out / xpre when in_c <= 4,
+ * else in; for the weight gradient: dense when it is a 1x1 layer with in_c <= 4, else gathered). */
 /* cat_input != 0 (1x1 stride-1 layers, no fused activation): `out` is the START of rows [in_c copied | out_c conv] with
  * row stride g->ld_out -- CatModule's concat (merge.py:10-16) written in the same pass. */
 int lb_conv_small_wgrad_supported(const lb_conv_geom* g);
-int lb_conv_small_wgrad(const float* gathered, const float* dense, float* dw, const lb_conv_geom* g, int growth_gathered,
-                        lb_stream_t stream);
+int lb_conv_small_wgrad(const void* gathered, const void* dense, float* dw, const lb_conv_geom* g, int growth_gathered,
+                        int wide_dtype, lb_stream_t stream);
 /* ---- the same GEMM on the 5th-gen tensor cores (tcgen05.mma, TMEM accumulator, TMA tiles), bf16 operands,
  * fp32 accumulate/output.  `in` is the bf16 channels-last activation, `w_packed` the weight packed by
  * lb_conv_tc_pack as [tap][n][k] bf16 (lb_conv_tc_packed_elems elements).  lb_conv_tc_supported says
@@ -191,18 +202,21 @@ int lb_conv_tc_gemm(const void* in_bf16, const void* w_packed, const float* alph
  * splits in index order -- no floating-point atomics, so the forward pass is bit-reproducible.  Without a workspace
  * (lb_conv_tc_gemm) such layers run unsplit. */
 size_t lb_conv_tc_workspace_bytes(const lb_conv_geom* g);
-int lb_conv_tc_gemm_ws(const void* in_bf16, const void* w_packed, const float* alpha, const float* bias, float* out,
-                       const lb_conv_geom* g, void* work, size_t work_bytes, lb_stream_t stream);
+/* out_dtype: LB_F32 or LB_BF16 rows of `out` (bf16 = the activation storage of the tensor-core configuration) */
+int lb_conv_tc_gemm_ws(const void* in_bf16, const void* w_packed, const float* alpha, const float* bias, void* out,
+                       const lb_conv_geom* g, void* work, size_t work_bytes, int out_dtype, lb_stream_t stream);
 /* Persistent variant with a fused epilogue (TMEM double buffering, TMA-stored outputs):
- *   acc = alpha * GEMM (+ bias);  if aux: acc *= RootTanh'(aux[pixel][n]) (activation.py:18-36, growth 4);
- *   out32 (fp32, row stride g->ld_out) and/or out16 (bf16, row stride ld_out16; RootTanh applied first when act16)
- * aux has the geometry of the output (row stride ld_aux, fp32).  Either output may be NULL, not both.
- * Returns LB_EUNSUPPORTED when the geometry/alignment is outside the kernel (lb_conv_tc_ex_supported tells in
- * advance: pass ld_out16 = 0 / ld_aux = 0 for "not used"); callers then use lb_conv_tc_gemm + elementwise kernels. */
-int lb_conv_tc_ex_supported(const lb_conv_geom* g, int ld_out16, int ld_aux);
+ *   acc = alpha * GEMM (+ bias);  if aux: acc *= RootTanh'(aux[pixel][n]) (activation.py:18-36, growth 4; aux has the
+ *   geometry of the output, row stride ld_aux, storage aux_dtype);
+ *   out32 (fp32, row stride g->ld_out), out16 (bf16 of acc) and / or out16a (bf16 of RootTanh(acc), the operand of the
+ *   convolution that follows, conv.py:23-24), both bf16 outputs with row stride ld_out16.  Any subset, not none.
+ * Returns LB_EUNSUPPORTED when the geometry / alignment is outside the kernel (lb_conv_tc_ex_supported tells in
+ * advance: out32_used 0/1, ld_out16 = 0 / ld_aux = 0 for "not used"); callers then use lb_conv_tc_gemm_ws + elementwise
+ * kernels. */
+int lb_conv_tc_ex_supported(const lb_conv_geom* g, int out32_used, int ld_out16, int ld_aux, int aux_dtype);
 int lb_conv_tc_gemm_ex(const void* in_bf16, const void* w_packed, const float* alpha, const float* bias, float* out32,
-                       void* out16, int ld_out16, int act16, const float* aux, int ld_aux, const lb_conv_geom* g,
-                       lb_stream_t stream);
+                       void* out16, void* out16a, int ld_out16, const void* aux, int ld_aux, int aux_dtype,
+                       const lb_conv_geom* g, lb_stream_t stream);
 /* weight gradient on the tensor cores: dwp[tap][n][m] += sum_pixels gathered[pixel@tap][m] * dense[pixel][n]
  * (geometry as lb_conv_wgrad; both operands bf16 channels-last; dwp fp32, zeroed by the caller; feed it to
  * lb_sn_weight_grad with packed_taps = kh*kw). */
@@ -215,34 +229,39 @@ int lb_cast_bf16_rows(const float* src, int ld_src, void* dst, int ld_dst, int64
                       lb_stream_t stream);
 int lb_roottanh_fwd_bf16(const float* x, void* y, size_t n, int growth, lb_stream_t stream);
 
-/* column sum: out[c] += sum_rows x[row*ld + c]  (bias gradients) */
-int lb_colsum(const float* x, int64_t rows, int cols, int ld, float* out, lb_stream_t stream);
+/* column sum: out[c] += sum_rows x[row*ld + c]  (bias gradients); x in storage `dtype`, out fp32 */
+int lb_colsum(const void* x, int64_t rows, int cols, int ld, float* out, int dtype, lb_stream_t stream);
 
 /* ---- softmax                                                          libs/attention.py:35,47 */
-/* over pixels for every (b,c) of a channels-last [B][P][C] tensor (SelfAttention, dim=-1 of [B,F,HW]) */
-int lb_softmax_pixels_fwd(const float* x, float* y, int batch, int pixels, int channels, lb_stream_t stream);
-int lb_softmax_pixels_bwd(const float* y, const float* g, float* dx, int batch, int pixels, int channels,
-                          lb_stream_t stream);
+/* over pixels for every (b,c) of a channels-last [B][P][C] tensor (SelfAttention, dim=-1 of [B,F,HW]); storage `dtype`.
+ * Long rows at small batch (HW = 65 536 at 256x256) are split over CTAs through `work`
+ * (lb_softmax_pixels_work_floats floats; 0 = not needed; NULL = run unsplit): per-split (max, sum exp) partials combined
+ * in a fixed order. */
+size_t lb_softmax_pixels_work_floats(int batch, int pixels, int channels);
+int lb_softmax_pixels_fwd(const void* x, void* y, int batch, int pixels, int channels, float* work, size_t work_floats,
+                          int dtype, lb_stream_t stream);
+int lb_softmax_pixels_bwd(const void* y, const void* g, void* dx, int batch, int pixels, int channels, float* work,
+                          size_t work_floats, int dtype, lb_stream_t stream);
 /* over the contiguous last axis of [rows][cols] (feature attention, Softmax(dim=1) on [B,F,1,1]) */
-int lb_softmax_rows_fwd(const float* x, float* y, int rows, int cols, lb_stream_t stream);
-int lb_softmax_rows_bwd(const float* y, const float* g, float* dx, int rows, int cols, lb_stream_t stream);
+int lb_softmax_rows_fwd(const void* x, void* y, int rows, int cols, int dtype, lb_stream_t stream);
+int lb_softmax_rows_bwd(const void* y, const void* g, void* dx, int rows, int cols, int dtype, lb_stream_t stream);
 
 /* ---- skip path resampling                                             libs/scale.py:7-45, libs/merge.py:4-16 */
-/* FeaturePooling: flat NCHW-memory regrouping mean (scale.py:12-16) evaluated on channels-last data */
-int lb_featpool_fwd(const float* x, float* y, int batch, int h, int w, int c_in, int c_out, lb_stream_t stream);
-int lb_featpool_bwd(const float* g, float* dx, int batch, int h, int w, int c_in, int c_out, lb_stream_t stream);
+/* FeaturePooling: flat NCHW-memory regrouping mean (scale.py:12-16) evaluated on channels-last data; storage `dtype` */
+int lb_featpool_fwd(const void* x, void* y, int batch, int h, int w, int c_in, int c_out, int dtype, lb_stream_t stream);
+int lb_featpool_bwd(const void* g, void* dx, int batch, int h, int w, int c_in, int c_out, int dtype, lb_stream_t stream);
 /* bilinear x2, align_corners = False (scale.py:37-38) */
-int lb_upsample2x_fwd(const float* x, float* y, int batch, int h, int w, int c, lb_stream_t stream);
-int lb_upsample2x_bwd(const float* g, float* dx, int batch, int h, int w, int c, lb_stream_t stream);
+int lb_upsample2x_fwd(const void* x, void* y, int batch, int h, int w, int c, int dtype, lb_stream_t stream);
+int lb_upsample2x_bwd(const void* g, void* dx, int batch, int h, int w, int c, int dtype, lb_stream_t stream);
 /* AvgPool 2x2 stride 2 (scale.py:40); h,w are the INPUT sizes (even) */
-int lb_avgpool2_fwd(const float* x, float* y, int batch, int h, int w, int c, lb_stream_t stream);
-int lb_avgpool2_bwd(const float* g, float* dx, int batch, int h, int w, int c, lb_stream_t stream);
+int lb_avgpool2_fwd(const void* x, void* y, int batch, int h, int w, int c, int dtype, lb_stream_t stream);
+int lb_avgpool2_bwd(const void* g, void* dx, int batch, int h, int w, int c, int dtype, lb_stream_t stream);
 /* strided row copy dst[row*ld_dst + c] (=|+=) src[row*ld_src + c]: channel concat / slice (merge.py:15) */
-int lb_copy_rows(const float* src, int ld_src, float* dst, int ld_dst, int64_t rows, int cols, int accumulate,
-                 lb_stream_t stream);
-/* layout change at the model boundary: NCHW <-> channels-last */
-int lb_nchw_to_nhwc(const float* x, float* y, int batch, int c, int hw, lb_stream_t stream);
-int lb_nhwc_to_nchw(const float* x, float* y, int batch, int c, int hw, lb_stream_t stream);
+int lb_copy_rows(const void* src, int ld_src, void* dst, int ld_dst, int64_t rows, int cols, int accumulate, int src_dtype,
+                 int dst_dtype, lb_stream_t stream);
+/* layout change at the model boundary: fp32 NCHW (what the reference's callers hold) <-> channels-last in storage `dtype` */
+int lb_nchw_to_nhwc(const float* x, void* y, int batch, int c, int hw, int out_dtype, lb_stream_t stream);
+int lb_nhwc_to_nchw(const void* x, float* y, int batch, int c, int hw, int in_dtype, lb_stream_t stream);
 
 /* ---- losses                                                           libs/utils.py:133-134, libs/grad_penalty.py:1-2, main.py:149-156,616-621
  * D step: loss = mean(hinge(d_true) + hinge(-d_fake)) + gamma*(mean(d_true) - mean(d_aug))^2.

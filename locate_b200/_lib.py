@@ -27,23 +27,24 @@ _SIGNATURES = {
     "lb_sm_arch": ([], c_int),
     "lb_last_launch_count": ([], c_int),
     "lb_reset_launch_count": ([], None),
-    "lb_roottanh_fwd": ([P, P, c_size_t, c_int, P], c_int),
-    "lb_roottanh_bwd": ([P, P, P, c_size_t, c_int, P], c_int),
-    "lb_tanh_fwd": ([P, P, c_size_t, P], c_int),
-    "lb_tanh_bwd": ([P, P, P, c_size_t, P], c_int),
+    "lb_roottanh_fwd": ([P, P, c_size_t, c_int, c_int, P], c_int),
+    "lb_roottanh_bwd": ([P, P, P, c_size_t, c_int, c_int, P], c_int),
+    "lb_tanh_fwd": ([P, P, c_size_t, c_int, P], c_int),
+    "lb_tanh_bwd": ([P, P, P, c_size_t, c_int, P], c_int),
+    "lb_add": ([P, P, P, c_size_t, c_int, P], c_int),
     "lb_hinge_fwd": ([P, P, c_size_t, P], c_int),
     "lb_hinge_bwd": ([P, P, P, c_size_t, P], c_int),
     "lb_stat_work_doubles": ([], c_size_t),
-    "lb_norm_stats": ([P, c_size_t, P, P, P], c_int),
+    "lb_norm_stats": ([P, c_size_t, P, P, c_int, P], c_int),
     "lb_norm_finalize": ([P, c_double, P, P], c_int),
-    "lb_norm_apply": ([P, P, P, c_int, P, P, c_int, c_int, c_int, P], c_int),
+    "lb_norm_apply": ([P, P, P, c_int, P, P, c_int, c_int, c_int, c_int, P], c_int),
     "lb_norm_apply_ex": ([P, P, P, c_int, P, P, P, c_int, c_int, c_int, c_int, P], c_int),
-    "lb_norm_bwd_reduce": ([P, P, P, P, P, c_int, c_int, c_int, P], c_int),
+    "lb_norm_bwd_reduce": ([P, P, P, P, P, c_int, c_int, c_int, c_int, P], c_int),
     "lb_norm_bwd_finalize": ([P, P, P, c_int, P, c_int, c_int, P, P, P, P], c_int),
-    "lb_norm_bwd_apply": ([P, P, P, P, c_int, P, P, c_int, c_int, c_int, P], c_int),
-    "lb_gate_fwd": ([P, P, P, P, c_int, c_int, c_int, c_int, P], c_int),
-    "lb_gate_fwd_stats": ([P, P, P, P, P, P, c_int, c_int, c_int, c_int, P], c_int),
-    "lb_gate_bwd": ([P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P], c_int),
+    "lb_norm_bwd_apply": ([P, P, P, P, c_int, P, P, P, c_int, c_int, c_int, c_int, P], c_int),
+    "lb_gate_fwd": ([P, P, P, P, c_int, c_int, c_int, c_int, c_int, P], c_int),
+    "lb_gate_fwd_stats": ([P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P], c_int),
+    "lb_gate_bwd": ([P, P, P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, P], c_int),
     "lb_sn_power_iter_work_floats": ([c_int, c_int], c_size_t),
     "lb_sn_power_iter": ([P, c_int, c_int, P, P, P, P, P], c_int),
     "lb_sn_power_iter_batched": ([P, c_int, P, c_int, P, c_int, P, P, P, P], c_int),
@@ -54,34 +55,35 @@ _SIGNATURES = {
     "lb_conv_gemm": ([P, P, P, P, P, POINTER(ConvGeom), P], c_int),
     "lb_conv_wgrad": ([P, P, P, POINTER(ConvGeom), P], c_int),
     "lb_conv_small_supported": ([POINTER(ConvGeom)], c_int),
-    "lb_conv_small": ([P, P, P, P, P, POINTER(ConvGeom), c_int, P, c_int, c_int, c_int, P], c_int),
+    "lb_conv_small": ([P, P, P, P, P, POINTER(ConvGeom), c_int, P, c_int, c_int, c_int, c_int, P], c_int),
     "lb_conv_small_wgrad_supported": ([POINTER(ConvGeom)], c_int),
-    "lb_conv_small_wgrad": ([P, P, P, POINTER(ConvGeom), c_int, P], c_int),
+    "lb_conv_small_wgrad": ([P, P, P, POINTER(ConvGeom), c_int, c_int, P], c_int),
     "lb_conv_tc_supported": ([POINTER(ConvGeom)], c_int),
     "lb_conv_tc_packed_elems": ([POINTER(ConvGeom)], c_size_t),
     "lb_conv_tc_pack": ([P, P, POINTER(ConvGeom), P], c_int),
     "lb_conv_tc_gemm": ([P, P, P, P, P, POINTER(ConvGeom), P], c_int),
     "lb_conv_tc_workspace_bytes": ([POINTER(ConvGeom)], c_size_t),
-    "lb_conv_tc_gemm_ws": ([P, P, P, P, P, POINTER(ConvGeom), P, c_size_t, P], c_int),
-    "lb_conv_tc_ex_supported": ([POINTER(ConvGeom), c_int, c_int], c_int),
-    "lb_conv_tc_gemm_ex": ([P, P, P, P, P, P, c_int, c_int, P, c_int, POINTER(ConvGeom), P], c_int),
+    "lb_conv_tc_gemm_ws": ([P, P, P, P, P, POINTER(ConvGeom), P, c_size_t, c_int, P], c_int),
+    "lb_conv_tc_ex_supported": ([POINTER(ConvGeom), c_int, c_int, c_int, c_int], c_int),
+    "lb_conv_tc_gemm_ex": ([P, P, P, P, P, P, P, c_int, P, c_int, c_int, POINTER(ConvGeom), P], c_int),
     "lb_cast_bf16": ([P, P, c_size_t, P], c_int),
     "lb_cast_bf16_rows": ([P, c_int, P, c_int, c_int64, c_int, c_int, P], c_int),
     "lb_roottanh_fwd_bf16": ([P, P, c_size_t, c_int, P], c_int),
-    "lb_colsum": ([P, c_int64, c_int, c_int, P, P], c_int),
-    "lb_softmax_pixels_fwd": ([P, P, c_int, c_int, c_int, P], c_int),
-    "lb_softmax_pixels_bwd": ([P, P, P, c_int, c_int, c_int, P], c_int),
-    "lb_softmax_rows_fwd": ([P, P, c_int, c_int, P], c_int),
-    "lb_softmax_rows_bwd": ([P, P, P, c_int, c_int, P], c_int),
-    "lb_featpool_fwd": ([P, P, c_int, c_int, c_int, c_int, c_int, P], c_int),
-    "lb_featpool_bwd": ([P, P, c_int, c_int, c_int, c_int, c_int, P], c_int),
-    "lb_upsample2x_fwd": ([P, P, c_int, c_int, c_int, c_int, P], c_int),
-    "lb_upsample2x_bwd": ([P, P, c_int, c_int, c_int, c_int, P], c_int),
-    "lb_avgpool2_fwd": ([P, P, c_int, c_int, c_int, c_int, P], c_int),
-    "lb_avgpool2_bwd": ([P, P, c_int, c_int, c_int, c_int, P], c_int),
-    "lb_copy_rows": ([P, c_int, P, c_int, c_int64, c_int, c_int, P], c_int),
-    "lb_nchw_to_nhwc": ([P, P, c_int, c_int, c_int, P], c_int),
-    "lb_nhwc_to_nchw": ([P, P, c_int, c_int, c_int, P], c_int),
+    "lb_colsum": ([P, c_int64, c_int, c_int, P, c_int, P], c_int),
+    "lb_softmax_pixels_work_floats": ([c_int, c_int, c_int], c_size_t),
+    "lb_softmax_pixels_fwd": ([P, P, c_int, c_int, c_int, P, c_size_t, c_int, P], c_int),
+    "lb_softmax_pixels_bwd": ([P, P, P, c_int, c_int, c_int, P, c_size_t, c_int, P], c_int),
+    "lb_softmax_rows_fwd": ([P, P, c_int, c_int, c_int, P], c_int),
+    "lb_softmax_rows_bwd": ([P, P, P, c_int, c_int, c_int, P], c_int),
+    "lb_featpool_fwd": ([P, P, c_int, c_int, c_int, c_int, c_int, c_int, P], c_int),
+    "lb_featpool_bwd": ([P, P, c_int, c_int, c_int, c_int, c_int, c_int, P], c_int),
+    "lb_upsample2x_fwd": ([P, P, c_int, c_int, c_int, c_int, c_int, P], c_int),
+    "lb_upsample2x_bwd": ([P, P, c_int, c_int, c_int, c_int, c_int, P], c_int),
+    "lb_avgpool2_fwd": ([P, P, c_int, c_int, c_int, c_int, c_int, P], c_int),
+    "lb_avgpool2_bwd": ([P, P, c_int, c_int, c_int, c_int, c_int, P], c_int),
+    "lb_copy_rows": ([P, c_int, P, c_int, c_int64, c_int, c_int, c_int, c_int, P], c_int),
+    "lb_nchw_to_nhwc": ([P, P, c_int, c_int, c_int, c_int, P], c_int),
+    "lb_nhwc_to_nchw": ([P, P, c_int, c_int, c_int, c_int, P], c_int),
     "lb_loss_sums": ([P, P, c_int, P, P], c_int),
     "lb_d_loss": ([P, P, P, P, c_int, c_double, c_float, P, P, P, P, P], c_int),
     "lb_g_loss": ([P, c_int, c_double, P, P, P], c_int),

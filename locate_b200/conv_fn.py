@@ -1,10 +1,11 @@
 """The spectral-normed convolution family as one autograd Function (fwd, dgrad, wgrad + the power iteration).
 
 Two kernel paths, chosen per layer:
-  * CFG.PRECISION == "bf16" and the geometry is covered by the tensor-core kernels (channels % 8, stride 1|2,
-    <= 32 taps): tcgen05 implicit GEMM (lb_conv_tc_gemm / lb_wgrad_tc), bf16 operands, fp32 accumulate + output.
-    Operands are produced in bf16 by the kernel that computes them (RootTanh fused with the cast).
-  * otherwise: the fp32 SIMT gather-GEMM (lb_conv_gemm / lb_conv_wgrad).
+  * CFG.PRECISION == "bf16" and the geometry is covered by the tensor-core kernels (stride 1|2, <= 64 taps per phase):
+    tcgen05 implicit GEMM (lb_conv_tc_gemm_ws / lb_conv_tc_gemm_ex / lb_wgrad_tc), bf16 operands, fp32 accumulate.
+    Wide activations ([B,C,H,W], C % 8 == 0) are STORED as bf16 (ops.store_dtype), so a GEMM reads its operand where the
+    producer left it and writes the next one from its epilogue: no cast passes, RootTanh / RootTanh' fused.
+  * otherwise: the fp32 SIMT gather-GEMM (lb_conv_gemm / lb_conv_wgrad), everything fp32.
 `pre_act` fuses the RootTanh that precedes every conv of ActivatedBaseConv (conv.py:22-24) into this Function.
 """
 import ctypes
@@ -14,7 +15,7 @@ import torch
 from . import _lib
 from ._lib import ConvGeom, call, ptr
 from .config import CFG
-from .ops import _as_act, _conv_work, _grad_sink, _new_act, _timed_call
+from .ops import BF16, F32, _as_act, _conv_work, _dt, _esz, _grad_sink, _match, _new_act, _timed_call, store_dtype
 
 # weight packs are reused while the weights are unchanged (3 discriminator passes per D step);
 # optim.Nadam.step / load_state_dict bump the epoch, torch's version counter covers in-place torch ops.
@@ -80,10 +81,6 @@ def power_iterate(w_bar, u, v, spec):
     return sigma
 
 
-def _bf16_like(t):
-    return torch.empty_strided(t.shape, t.stride(), dtype=torch.bfloat16, device=t.device)
-
-
 def _packed_weight(w_bar, g, tag):
     """bf16 [tap][n][k] copy of the master weight for geometry g (cached per weight version)."""
     epoch = getattr(w_bar, "_lb_epoch", _PACK_EPOCH)       # per-optimizer counter when the weight lives in a Nadam arena
@@ -130,11 +127,40 @@ def _sn_weight_grad(dwn, w_bar, u, v, sigma, spec, packed_taps, extra, dev):
     return dw_ret
 
 
-def _tc_gemm(fl, nbytes, a, pk, alpha_ptr, bias, out_ptr, g, dev):
-    """lb_conv_tc_gemm_ws with the split-K workspace the geometry asks for (weight-bound layers; 0 bytes otherwise)."""
+def _tc_gemm(fl, nbytes, a_ptr, pk, alpha_ptr, bias, out_ptr, g, dev, out_dtype=F32):
+    """lb_conv_tc_gemm_ws with the split-K workspace the geometry asks for (weight-bound layers; 0 bytes otherwise).
+    a_ptr / out_ptr are raw device addresses (operands are often channel slices of wider rows)."""
     need = _lib.lib().lb_conv_tc_workspace_bytes(ctypes.byref(g))
     work = torch.empty(need // 4, dtype=torch.float32, device=dev) if need else None
-    _timed_call("conv_tc", fl, nbytes, "lb_conv_tc_gemm_ws", ptr(a), ptr(pk), alpha_ptr, ptr(bias), out_ptr, g, ptr(work), need)
+    _timed_call("conv_tc", fl, nbytes, "lb_conv_tc_gemm_ws", a_ptr, ptr(pk), alpha_ptr, ptr(bias), out_ptr, g, ptr(work), need,
+                out_dtype)
+
+
+class _Like:
+    """shape / stride / dtype of a tensor that is gone (what ops._match needs to lay a gradient out)."""
+
+    def __init__(self, shape, stride, dtype):
+        self.shape, self._stride, self.dtype = torch.Size(shape), tuple(stride), dtype
+
+    def stride(self):
+        return self._stride
+
+
+def _bf16_rows(t, cols, cols_p, growth=0, offset=0, ld=None):
+    """bf16 [rows, cols_p] copy (rows padded to 16 bytes for TMA) of `cols` columns of the fp32 rows of `t` starting at
+    column `offset` -- operands whose channel count is not a multiple of 8 (RGB images, logits, vectors of the style
+    chain), optionally through RootTanh."""
+    ld = ld if ld is not None else t.shape[1]
+    rows = t.numel() // ld
+    if t.dtype == torch.bfloat16:                 # an unaligned channel slice of bf16 rows (no activation on this path)
+        if growth:
+            raise ValueError("RootTanh on a bf16 slice copy")
+        out = torch.zeros((rows, cols_p), dtype=torch.bfloat16, device=t.device)
+        call("lb_copy_rows", t.data_ptr() + 2 * offset, ld, ptr(out), cols_p, rows, cols, 0, BF16, BF16)
+        return out
+    out = torch.empty((rows, cols_p), dtype=torch.bfloat16, device=t.device)
+    call("lb_cast_bf16_rows", t.data_ptr() + 4 * offset, ld, ptr(out), cols_p, rows, cols, growth)
+    return out
 
 
 class SNConvFn(torch.autograd.Function):
@@ -147,12 +173,8 @@ class SNConvFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w_bar, u, v, bias, spec, cat_input, pre_act, pre_sigma):
-        ready16 = getattr(x, "_lb_act16" if pre_act else "_lb_plain16", None)
-        if getattr(x, "_lb_unwritten", False):
-            if ready16 is None or pre_act or cat_input or CFG.PRECISION != "bf16" or x.shape[1] % 8:
-                raise RuntimeError("norm output was emitted as a bf16 operand only, but this conv needs its fp32 values")
-        else:
-            x = _as_act(x)
+        ready_act = getattr(x, "_lb_act16", None) if pre_act else None
+        x = _as_act(x)
         is_vec = x.dim() == 2
         if is_vec:
             b, h, w_, cin = x.shape[0], 1, 1, x.shape[1]
@@ -169,10 +191,12 @@ class SNConvFn(torch.autograd.Function):
             raise ValueError("cat_input needs a size-preserving conv")
         ctot = spec.cout + (cin if cat_input else 0)
         out = _new_act((b, ctot) if is_vec else (b, ctot, oh, ow), x)
-        off = cin * 4 if cat_input else 0
+        esz_o = _esz(out)
+        off = cin if cat_input else 0                 # first column of the conv result inside the output rows
         t = spec.taps
         mode = 1 if spec.kind == "convT" else 0
         lib = _lib.lib()
+        x16, out16 = x.dtype == torch.bfloat16, out.dtype == torch.bfloat16
 
         def geoms(ld_x, ld_dy):
             gf = _geom(b, h, w_, cin, oh, ow, spec.cout, spec, mode, ld_x, ctot, spec.strides_fwd())
@@ -183,65 +207,73 @@ class SNConvFn(torch.autograd.Function):
                 gw = _geom(b, h, w_, cin, oh, ow, spec.cout, spec, 0, ld_x, ld_dy, (t, cin * t, spec.kw, 1))
             return gf, gd, gw
 
-        # tensor-core operands are bf16 rows padded to 16 bytes (TMA stride rule); channel counts are arbitrary
+        # tensor-core operands are bf16 rows of >= 16 bytes (TMA stride rule): a wide bf16 activation is its own operand,
+        # anything else is copied into rows padded to 8 channels
         cin_p, cout_p = (cin + 7) // 8 * 8, (spec.cout + 7) // 8 * 8
+        # the gradient of a bf16 output is its own operand too when the conv's slice of the rows is 16-byte aligned
+        gy_direct = out16 and off % 8 == 0 and spec.cout % 8 == 0
+        ld_x = cin if x16 else cin_p
+        ld_gy = ctot if gy_direct else cout_p
         tc = fused_cat = False
         g32 = geoms(cin, spec.cout)
-        # tiny channel count on one side (D stem, G's last 1x1): direct fp32 kernels, activation fused
+        # tiny channel count on one side (D stem, G's last 1x1): direct kernels, activation fused
         # (a wide -> 3 layer such as G's last 1x1 is TMA-friendly on its input side and measured faster on the tensor cores)
-        small = CFG.SMALL_KERNELS and cin <= 4 and lib.lb_conv_small_supported(ctypes.byref(g32[0])) == 1
+        small = CFG.SMALL_KERNELS and cin <= 4 and not x16 and lib.lb_conv_small_supported(ctypes.byref(g32[0])) == 1
         if CFG.PRECISION == "bf16" and not small:
-            g_fwd, g_dgrad, g_wgrad = geoms(cin_p, cout_p)
+            g_fwd, g_dgrad, g_wgrad = geoms(ld_x, ld_gy)
             tc = (lib.lb_conv_tc_supported(ctypes.byref(g_fwd)) == 1 and lib.lb_conv_tc_supported(ctypes.byref(g_dgrad)) == 1
                   and lib.lb_wgrad_tc_supported(ctypes.byref(g_wgrad)) == 1)
         if not tc:
-            if getattr(x, "_lb_unwritten", False):
-                raise RuntimeError("norm output exists only as a bf16 operand, but this conv is not on the tensor-core path")
+            if (x16 or out16) and not small:
+                raise RuntimeError("bf16-stored activations reached a layer the tensor-core kernels do not cover")
             g_fwd, g_dgrad, g_wgrad = geoms(cin, spec.cout)
         fl, by = _conv_work(spec, b, h, w_, oh, ow)
         n = x.numel()
         if tc:
             growth = CFG.ROOTTANH_GROWTH if pre_act else 0
-            if cin_p == cin and ready16 is not None:
-                a = ready16
-            elif cin_p == cin:
-                a = _bf16_like(x)
-                if pre_act:
-                    call("lb_roottanh_fwd_bf16", ptr(x), ptr(a), n, growth)
+            if x16:
+                if not pre_act:
+                    a = x
+                elif ready_act is not None:
+                    a = ready_act
                 else:
-                    call("lb_cast_bf16", ptr(x), ptr(a), n)
+                    a = torch.empty_like(x)
+                    call("lb_roottanh_fwd", ptr(x), ptr(a), n, growth, BF16)
             else:
-                a = torch.empty((n // cin, cin_p), dtype=torch.bfloat16, device=x.device)
-                call("lb_cast_bf16_rows", ptr(x), cin, ptr(a), cin_p, n // cin, cin, growth)
+                a = _bf16_rows(x, cin, cin_p, growth)
             pk = _packed_weight(w_bar, g_fwd, "fwd")
-            _tc_gemm(fl, _tc_bytes(g_fwd), a, pk, sigma.data_ptr() + 4, bias, out.data_ptr() + off, g_fwd, x.device)
+            _tc_gemm(fl, _tc_bytes(g_fwd), ptr(a), pk, sigma.data_ptr() + 4, bias, out.data_ptr() + off * esz_o, g_fwd, x.device,
+                     BF16 if out16 else F32)
         elif small:
             pointwise = spec.taps == 1 and spec.stride == 1 and spec.pad == 0
             small_growth = CFG.ROOTTANH_GROWTH if pre_act else 0
             if pre_act and not pointwise:         # every input pixel feeds up to 25 taps: activate it once, not per tap
                 a = torch.empty_like(x)
-                call("lb_roottanh_fwd", ptr(x), ptr(a), n, CFG.ROOTTANH_GROWTH)
+                call("lb_roottanh_fwd", ptr(x), ptr(a), n, CFG.ROOTTANH_GROWTH, F32)
                 small_growth = 0
             else:
                 a = x                             # RootTanh is applied on load; nothing is materialised
             fused_cat = bool(cat_input and pointwise and cin <= 8)     # the D stem's [x | conv(x)] row in one pass
             _timed_call("conv_small", fl, by, "lb_conv_small", ptr(a), ptr(w_bar), sigma.data_ptr() + 4, ptr(bias),
-                        out.data_ptr() + (0 if fused_cat else off), g_fwd, small_growth, None, 0, 0, 1 if fused_cat else 0)
+                        out.data_ptr() + (0 if fused_cat else off * esz_o), g_fwd, small_growth, None, 0, 0, 1 if fused_cat else 0,
+                        _dt(out))
         else:
             if pre_act:
                 a = torch.empty_like(x)
-                call("lb_roottanh_fwd", ptr(x), ptr(a), n, CFG.ROOTTANH_GROWTH)
+                call("lb_roottanh_fwd", ptr(x), ptr(a), n, CFG.ROOTTANH_GROWTH, F32)
             else:
                 a = x
             _timed_call("conv_gemm", fl, by, "lb_conv_gemm", ptr(a), ptr(w_bar), sigma.data_ptr() + 4, ptr(bias),
-                        out.data_ptr() + off, g_fwd)
+                        out.data_ptr() + off * 4, g_fwd)
         if cat_input and not fused_cat:
-            call("lb_copy_rows", ptr(x), cin, ptr(out), ctot, b * h * w_, cin, 0)
+            call("lb_copy_rows", ptr(x), cin, ptr(out), ctot, b * h * w_, cin, 0, _dt(x), _dt(out))
         ctx.save_for_backward(x if pre_act else None, a, w_bar, sigma)
         ctx.u, ctx.v = u, v                      # LIVE u/v: the reference's backward reads them at backward time
         ctx.uv_extra = _uv_extra(pre_sigma, u)
         ctx.bias_param, ctx.w_param = bias, w_bar
         ctx.meta = (spec, cat_input, pre_act, tc, (b, h, w_, cin, oh, ow, ctot), g_dgrad, g_wgrad, (fl, by))
+        ctx.dtypes = (x.dtype, out.dtype, tuple(x.shape), gy_direct, ld_gy)
+        ctx.out_like = (tuple(out.shape), tuple(out.stride()))
         ctx.raw_a = bool(small and pre_act and a is x)   # `a` is the pre-activation: backward applies RootTanh where it needs it
         return out
 
@@ -249,39 +281,56 @@ class SNConvFn(torch.autograd.Function):
     def backward(ctx, gout):
         x, a, w_bar, sigma = ctx.saved_tensors
         spec, cat_input, pre_act, tc, (b, h, w_, cin, oh, ow, ctot), g_dgrad, g_wgrad, (fl, by) = ctx.meta
-        gout = _as_act(gout)
-        off = cin * 4 if cat_input else 0
+        x_dtype, out_dtype, x_shape, gy_direct, ld_gy = ctx.dtypes
+        out_shape, out_stride = ctx.out_like
+        gout = _match(gout, _Like(out_shape, out_stride, out_dtype))
+        esz_g = _esz(gout)
+        off = cin if cat_input else 0
         rows = b * oh * ow
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         dx = dw_ret = dbias_ret = None
         dact_done = False
         t = spec.taps
-        height, width = spec.sn_shape
+        dev = gout.device
+        x16 = x_dtype == torch.bfloat16
+        lib = _lib.lib()
         if tc:
-            cout_p = (spec.cout + 7) // 8 * 8
-            gy = torch.empty((rows, cout_p), dtype=torch.bfloat16, device=gout.device)
-            call("lb_cast_bf16_rows", gout.data_ptr() + off, ctot, ptr(gy), cout_p, rows, spec.cout, 0)
+            if gy_direct:
+                gy_ptr = gout.data_ptr() + off * 2     # the conv's slice of the bf16 gradient rows, row stride ctot
+                gy_keep = gout
+            else:
+                gy_keep = _bf16_rows(gout, spec.cout, ld_gy, 0, off, ctot)
+                gy_ptr = gy_keep.data_ptr()
             if need_dx:
-                dx = _new_act((b, cin) if gout.dim() == 2 else (b, cin, h, w_), gout)
+                dx = _new_act(x_shape, gout, x_dtype)
                 pk = _packed_weight(w_bar, g_dgrad, "dgrad")
-                _tc_gemm(fl, _tc_bytes(g_dgrad), gy, pk, sigma.data_ptr() + 4, None, ptr(dx), g_dgrad, gout.device)
+                if x16:
+                    aux_ok = pre_act and lib.lb_conv_tc_ex_supported(ctypes.byref(g_dgrad), 0, cin, cin, BF16) == 1
+                    if aux_ok:      # dx = dgrad(gy) * RootTanh'(x) in the GEMM epilogue
+                        _timed_call("conv_tc", fl, _tc_bytes(g_dgrad), "lb_conv_tc_gemm_ex", gy_ptr, ptr(pk), sigma.data_ptr() + 4, None,
+                                    None, ptr(dx), None, cin, ptr(x), cin, BF16, g_dgrad)
+                        dact_done = True
+                    else:
+                        _tc_gemm(fl, _tc_bytes(g_dgrad), gy_ptr, pk, sigma.data_ptr() + 4, None, ptr(dx), g_dgrad, dev, BF16)
+                else:               # narrow / vector input: fp32 rows of cin
+                    _tc_gemm(fl, _tc_bytes(g_dgrad), gy_ptr, pk, sigma.data_ptr() + 4, None, ptr(dx), g_dgrad, dev, F32)
             if need_dw:
-                dwp = torch.zeros(w_bar.numel(), dtype=torch.float32, device=gout.device)
+                dwp = torch.zeros(w_bar.numel(), dtype=torch.float32, device=dev)
                 if spec.kind == "convT":
-                    _timed_call("wgrad_tc", fl, _wgrad_bytes(g_wgrad), "lb_wgrad_tc", ptr(gy), ptr(a), ptr(dwp), g_wgrad)
+                    _timed_call("wgrad_tc", fl, _wgrad_bytes(g_wgrad), "lb_wgrad_tc", gy_ptr, ptr(a), ptr(dwp), g_wgrad)
                 else:
-                    _timed_call("wgrad_tc", fl, _wgrad_bytes(g_wgrad), "lb_wgrad_tc", ptr(a), ptr(gy), ptr(dwp), g_wgrad)
-                dw_ret = _sn_weight_grad(dwp, ctx.w_param, ctx.u, ctx.v, sigma, spec, t, ctx.uv_extra, gout.device)
+                    _timed_call("wgrad_tc", fl, _wgrad_bytes(g_wgrad), "lb_wgrad_tc", ptr(a), gy_ptr, ptr(dwp), g_wgrad)
+                dw_ret = _sn_weight_grad(dwp, ctx.w_param, ctx.u, ctx.v, sigma, spec, t, ctx.uv_extra, dev)
         else:
-            lib = _lib.lib()
             growth = CFG.ROOTTANH_GROWTH
-            gy_ptr = gout.data_ptr() + off        # gradient of the conv output slice, row stride ctot
+            gy_ptr = gout.data_ptr() + off * esz_g    # gradient of the conv output slice, row stride ctot
             g_dgrad.ld_in = ctot
+            small_in = CFG.SMALL_KERNELS and cin <= 4 and not x16
             if need_dx:
                 dx = torch.empty_like(a)
-                if CFG.SMALL_KERNELS and cin <= 4 and lib.lb_conv_small_supported(ctypes.byref(g_dgrad)) == 1:
+                if small_in and lib.lb_conv_small_supported(ctypes.byref(g_dgrad)) == 1:
                     _timed_call("conv_small", fl, by, "lb_conv_small", gy_ptr, ptr(w_bar), sigma.data_ptr() + 4, None, ptr(dx),
-                                g_dgrad, 0, ptr(x) if pre_act else None, cin, growth if pre_act else 0, 0)
+                                g_dgrad, 0, ptr(x) if pre_act else None, cin, growth if pre_act else 0, 0, _dt(gout))
                     dact_done = True
                 else:
                     _timed_call("conv_gemm", fl, by, "lb_conv_gemm", gy_ptr, ptr(w_bar), sigma.data_ptr() + 4, None, ptr(dx), g_dgrad)
@@ -291,27 +340,31 @@ class SNConvFn(torch.autograd.Function):
                     g_wgrad.ld_in = ctot
                 else:
                     g_wgrad.ld_out = ctot
-                small_w = CFG.SMALL_KERNELS and cin <= 4 and lib.lb_conv_small_wgrad_supported(ctypes.byref(g_wgrad)) == 1
+                small_w = small_in and lib.lb_conv_small_wgrad_supported(ctypes.byref(g_wgrad)) == 1
                 fuse_act = ctx.raw_a and small_w and spec.kind != "convT"     # RootTanh on the gathered operand's load
                 if ctx.raw_a and not fuse_act:
                     act = torch.empty_like(a)
-                    call("lb_roottanh_fwd", ptr(a), ptr(act), a.numel(), growth)
+                    call("lb_roottanh_fwd", ptr(a), ptr(act), a.numel(), growth, F32)
                     a = act
                 ga_ptr, de_ptr = (gy_ptr, ptr(a)) if spec.kind == "convT" else (ptr(a), gy_ptr)
                 if small_w:
+                    # the wide operand (lb_conv_small_wgrad): dense for a 1x1 layer with <= 4 gathered channels, else gathered
+                    ga_dt, de_dt = (_dt(gout), _dt(a)) if spec.kind == "convT" else (_dt(a), _dt(gout))
+                    pointwise = spec.taps == 1 and spec.stride == 1 and spec.pad == 0
+                    wide = de_dt if (pointwise and g_wgrad.in_c <= 4) else ga_dt
                     _timed_call("conv_small_wgrad", fl, by, "lb_conv_small_wgrad", ga_ptr, de_ptr, ptr(dwn), g_wgrad,
-                                growth if fuse_act else 0)
+                                growth if fuse_act else 0, wide)
                 else:
                     _timed_call("conv_wgrad", fl, by, "lb_conv_wgrad", ga_ptr, de_ptr, ptr(dwn), g_wgrad)
-                dw_ret = _sn_weight_grad(dwn, ctx.w_param, ctx.u, ctx.v, sigma, spec, 0, ctx.uv_extra, gout.device)
+                dw_ret = _sn_weight_grad(dwn, ctx.w_param, ctx.u, ctx.v, sigma, spec, 0, ctx.uv_extra, dev)
         if need_dx:
             if pre_act and not dact_done:
-                call("lb_roottanh_bwd", ptr(x), ptr(dx), ptr(dx), dx.numel(), CFG.ROOTTANH_GROWTH)   # in place
+                call("lb_roottanh_bwd", ptr(x), ptr(dx), ptr(dx), dx.numel(), CFG.ROOTTANH_GROWTH, _dt(dx))   # in place
             if cat_input:
-                call("lb_copy_rows", ptr(gout), ctot, ptr(dx), cin, b * h * w_, cin, 1)
+                call("lb_copy_rows", ptr(gout), ctot, ptr(dx), cin, b * h * w_, cin, 1, _dt(gout), _dt(dx))
         if ctx.bias_param is not None and ctx.needs_input_grad[4]:
             dbias, dbias_ret = _grad_sink(ctx.bias_param)
-            call("lb_colsum", gout.data_ptr() + off, rows, spec.cout, ctot, ptr(dbias))
+            call("lb_colsum", gout.data_ptr() + off * esz_g, rows, spec.cout, ctot, ptr(dbias), _dt(gout))
         return dx, dw_ret, None, None, dbias_ret, None, None, None, None
 
 
@@ -329,57 +382,60 @@ def _wgrad_bytes(g):
             + 4.0 * g.kh * g.kw * g.in_c * g.out_c)
 
 
-def _ex_ok(g, ld16, ld_aux):
-    return _lib.lib().lb_conv_tc_ex_supported(ctypes.byref(g), ld16, ld_aux) == 1
+def _ex_ok(g, out32, ld16, ld_aux, aux_dtype=F32):
+    return _lib.lib().lb_conv_tc_ex_supported(ctypes.byref(g), int(out32), ld16, ld_aux, aux_dtype) == 1
 
 
-def _sn_wgrad_tc(ctx_w, u, v, sigma, gathered, dense, g_wgrad, spec, fl, by, dev, extra=None):
+def _sn_wgrad_tc(ctx_w, u, v, sigma, gathered_ptr, dense_ptr, g_wgrad, spec, fl, by, dev, extra=None):
     """dW of one spectral-normed conv on the tensor cores + the sigma correction, accumulated into the grad sink."""
     dwp = torch.zeros(ctx_w.numel(), dtype=torch.float32, device=dev)
-    _timed_call("wgrad_tc", fl, _wgrad_bytes(g_wgrad), "lb_wgrad_tc", ptr(gathered), ptr(dense), ptr(dwp), g_wgrad)
+    _timed_call("wgrad_tc", fl, _wgrad_bytes(g_wgrad), "lb_wgrad_tc", gathered_ptr, dense_ptr, ptr(dwp), g_wgrad)
     return _sn_weight_grad(dwp, ctx_w, u, v, sigma, spec, spec.taps, extra, dev)
 
 
 class ActivatedPairFn(torch.autograd.Function):
-    """ActivatedBaseConv.forward (conv.py:22-24) as ONE autograd node on the persistent tensor-core kernel:
+    """ActivatedBaseConv.forward (conv.py:22-24) as ONE autograd node on the persistent tensor-core kernel, every
+    activation stored as bf16:
 
         y1 = conv_1(RootTanh(conv_0(RootTanh(x))))         (both convs spectral-normed, no bias)
 
-    forward : conv_0's epilogue writes y0 (fp32, kept for the activation backward) AND bf16 RootTanh(y0), the operand
-              of conv_1 -- the activation never makes its own pass over memory;
-    backward: conv_1's input-gradient GEMM multiplies by RootTanh'(y0) in its epilogue and emits the bf16 operand of
-              conv_0's two gradient GEMMs; conv_0's input-gradient GEMM multiplies by RootTanh'(x) the same way.
-    `x` may carry `_lb_act16` = bf16 RootTanh(x) left by the kernel that produced it (norm apply)."""
+    forward : conv_0's epilogue writes y0 (bf16, kept for the activation backward) AND RootTanh(y0), the operand of
+              conv_1 -- the activation never makes its own pass over memory; conv_1 writes y1 as bf16 (or fp32 rows when
+              it has fewer than 8 channels: the generator's RGB output);
+    backward: the incoming bf16 gradient is conv_1's operand as it stands; conv_1's input-gradient GEMM multiplies by
+              RootTanh'(y0) in its epilogue and emits the bf16 operand of conv_0's two gradient GEMMs; conv_0's
+              input-gradient GEMM multiplies by RootTanh'(x) the same way and writes dx as bf16.
+    `x` (bf16) may carry `_lb_act16` = RootTanh(x) left by the kernel that produced it (norm apply)."""
 
     @staticmethod
     def forward(ctx, x, w0, u0, v0, w1, u1, v1, spec0, spec1, sigma0, sigma1, geoms, pre_act0):
-        act16 = getattr(x, "_lb_act16" if pre_act0 else "_lb_plain16", None)
-        if act16 is None:
-            x = _as_act(x)
+        act16 = getattr(x, "_lb_act16", None) if pre_act0 else None
+        x = _as_act(x)                               # bf16 (cin % 8 == 0, checked by activated_pair)
         b, cin, h, w_ = x.shape
         oh, ow = spec0.out_hw(h, w_)
         mid, cout = spec0.cout, spec1.cout
         (gf0, gd0, gw0), (gf1, gd1, gw1) = geoms
-        if act16 is None:
-            act16 = _bf16_like(x)
-            if pre_act0:
-                call("lb_roottanh_fwd_bf16", ptr(x), ptr(act16), x.numel(), CFG.ROOTTANH_GROWTH)
-            else:
-                call("lb_cast_bf16", ptr(x), ptr(act16), x.numel())
-        y0 = _new_act((b, mid, oh, ow), x)
-        a0 = _bf16_like(y0)
+        if not pre_act0:
+            act16 = x
+        elif act16 is None:
+            act16 = torch.empty_like(x)
+            call("lb_roottanh_fwd", ptr(x), ptr(act16), x.numel(), CFG.ROOTTANH_GROWTH, BF16)
+        y0 = _new_act((b, mid, oh, ow), x, torch.bfloat16)
+        a0 = torch.empty_like(y0)
         fl0, by0 = _conv_work(spec0, b, h, w_, oh, ow)
         fl1, by1 = _conv_work(spec1, b, oh, ow, oh, ow)
-        _timed_call("conv_tc", fl0, _tc_bytes(gf0, True, True), "lb_conv_tc_gemm_ex", ptr(act16), ptr(_packed_weight(w0, gf0, "fwd")),
-                    sigma0.data_ptr() + 4, None, ptr(y0), ptr(a0), mid, 1, None, 0, gf0)
+        _timed_call("conv_tc", fl0, _tc_bytes(gf0), "lb_conv_tc_gemm_ex", ptr(act16), ptr(_packed_weight(w0, gf0, "fwd")),
+                    sigma0.data_ptr() + 4, None, None, ptr(y0), ptr(a0), mid, None, 0, F32, gf0)
         y1 = _new_act((b, cout, oh, ow), x)
-        # lb_conv_tc_gemm picks the persistent kernel itself and keeps direct stores for rows that TMA cannot address
-        # (cout = 3: G's last layer)
-        _tc_gemm(fl1, _tc_bytes(gf1), a0, _packed_weight(w1, gf1, "fwd"), sigma1.data_ptr() + 4, None, ptr(y1), gf1, x.device)
+        # lb_conv_tc_gemm_ws picks the persistent kernel itself and keeps direct stores for rows that TMA cannot address
+        # (cout = 3: G's last layer, fp32 rows)
+        _tc_gemm(fl1, _tc_bytes(gf1), ptr(a0), _packed_weight(w1, gf1, "fwd"), sigma1.data_ptr() + 4, None, ptr(y1), gf1, x.device,
+                 _dt(y1))
         ctx.save_for_backward(x if pre_act0 else None, act16, y0, a0, w0, w1, sigma0, sigma1)
         ctx.uv = (u0, v0, u1, v1)                # LIVE u/v (see SNConvFn)
         ctx.uv_extra = (_uv_extra(sigma0, u0), _uv_extra(sigma1, u1))
         ctx.meta = (spec0, spec1, geoms, (b, cin, h, w_, oh, ow, mid, cout), (fl0, by0, fl1, by1), pre_act0)
+        ctx.out_like = _Like(y1.shape, y1.stride(), y1.dtype)
         return y1
 
     @staticmethod
@@ -388,31 +444,27 @@ class ActivatedPairFn(torch.autograd.Function):
         u0, v0, u1, v1 = ctx.uv
         spec0, spec1, geoms, (b, cin, h, w_, oh, ow, mid, cout), (fl0, by0, fl1, by1), pre_act0 = ctx.meta
         (gf0, gd0, gw0), (gf1, gd1, gw1) = geoms
-        gout = _as_act(gout)
+        gout = _match(gout, ctx.out_like)
         dev = gout.device
         need_dx, need_dw0, need_dw1 = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[4]
-        cout_p = (cout + 7) // 8 * 8               # bf16 rows are padded to 16 bytes for TMA
-        if cout_p == cout:
-            g1 = _bf16_like(gout)
-            call("lb_cast_bf16", ptr(gout), ptr(g1), gout.numel())
-        else:
-            g1 = torch.empty((b * oh * ow, cout_p), dtype=torch.bfloat16, device=dev)
-            call("lb_cast_bf16_rows", ptr(gout), cout, ptr(g1), cout_p, b * oh * ow, cout, 0)
+        cout_p = (cout + 7) // 8 * 8               # bf16 rows of >= 16 bytes for TMA
+        g1 = gout if gout.dtype == torch.bfloat16 else _bf16_rows(gout, cout, cout_p, 0, 0, cout)
         dx = dw0 = dw1 = None
         if need_dw1:
             ga, de = (g1, a0) if spec1.kind == "convT" else (a0, g1)
-            dw1 = _sn_wgrad_tc(w1, u1, v1, sigma1, ga, de, gw1, spec1, fl1, by1, dev, ctx.uv_extra[1])
+            dw1 = _sn_wgrad_tc(w1, u1, v1, sigma1, ptr(ga), ptr(de), gw1, spec1, fl1, by1, dev, ctx.uv_extra[1])
         if need_dx or need_dw0:
-            d0 = _bf16_like(y0)                  # bf16( dL/dy0 ) = bf16( dgrad_1(g1) * RootTanh'(y0) )
-            _timed_call("conv_tc", fl1, _tc_bytes(gd1, False, True, True), "lb_conv_tc_gemm_ex", ptr(g1), ptr(_packed_weight(w1, gd1, "dgrad")),
-                        sigma1.data_ptr() + 4, None, None, ptr(d0), mid, 0, ptr(y0), mid, gd1)
+            d0 = torch.empty_like(y0)            # bf16( dL/dy0 ) = bf16( dgrad_1(g1) * RootTanh'(y0) )
+            _timed_call("conv_tc", fl1, _tc_bytes(gd1), "lb_conv_tc_gemm_ex", ptr(g1), ptr(_packed_weight(w1, gd1, "dgrad")),
+                        sigma1.data_ptr() + 4, None, None, ptr(d0), None, mid, ptr(y0), mid, BF16, gd1)
             if need_dw0:
                 ga, de = (d0, act16) if spec0.kind == "convT" else (act16, d0)
-                dw0 = _sn_wgrad_tc(w0, u0, v0, sigma0, ga, de, gw0, spec0, fl0, by0, dev, ctx.uv_extra[0])
+                dw0 = _sn_wgrad_tc(w0, u0, v0, sigma0, ptr(ga), ptr(de), gw0, spec0, fl0, by0, dev, ctx.uv_extra[0])
             if need_dx:
-                dx = _new_act((b, cin, h, w_), gout)
-                _timed_call("conv_tc", fl0, _tc_bytes(gd0, True, False, pre_act0), "lb_conv_tc_gemm_ex", ptr(d0), ptr(_packed_weight(w0, gd0, "dgrad")),
-                            sigma0.data_ptr() + 4, None, ptr(dx), None, 0, 0, ptr(x) if pre_act0 else None, cin if pre_act0 else 0, gd0)
+                dx = _new_act((b, cin, h, w_), gout, torch.bfloat16)
+                _timed_call("conv_tc", fl0, _tc_bytes(gd0), "lb_conv_tc_gemm_ex", ptr(d0), ptr(_packed_weight(w0, gd0, "dgrad")),
+                            sigma0.data_ptr() + 4, None, None, ptr(dx), None, cin, ptr(x) if pre_act0 else None,
+                            cin if pre_act0 else 0, BF16, gd0)
         return (dx, dw0, None, None, dw1) + (None,) * 8
 
 
@@ -446,8 +498,8 @@ def activated_pair(x, sn0, sn1, pre_act0=True):
         return gf, gd, gw
 
     g0, g1 = geoms(spec0, h, w_, cin, mid, oh, ow, mid), geoms(spec1, oh, ow, mid, cout, oh, ow, cout_p)
-    ok = (_ex_ok(g0[0], mid, 0) and lib.lb_conv_tc_supported(ctypes.byref(g1[0])) == 1 and _ex_ok(g1[1], mid, mid)
-          and _ex_ok(g0[1], 0, cin if pre_act0 else 0)
+    ok = (_ex_ok(g0[0], False, mid, 0) and lib.lb_conv_tc_supported(ctypes.byref(g1[0])) == 1 and _ex_ok(g1[1], False, mid, mid, BF16)
+          and _ex_ok(g0[1], False, cin, cin if pre_act0 else 0, BF16)
           and lib.lb_wgrad_tc_supported(ctypes.byref(g0[2])) == 1 and lib.lb_wgrad_tc_supported(ctypes.byref(g1[2])) == 1)
     if not ok:
         return None

@@ -1,5 +1,6 @@
 // Shared device helpers for the locate_b200 kernels (sm_100a).
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <math.h>
@@ -112,11 +113,44 @@ __device__ __forceinline__ void lb_grid_sum2_ordered(double s1, double s2, doubl
   }
 }
 
-// 128-bit streaming accessors (each activation is touched once per kernel: keep it out of L1)
+// ---- storage types ----------------------------------------------------------------------------------------------
+// Activations and their gradients are stored as fp32 (LB_F32: the reference's precision class) or bf16 (LB_BF16: the
+// tensor-core configuration, half the HBM traffic of every elementwise pass); arithmetic is fp32 either way.  Kernels
+// are templated on the storage type T and read / write through these overloads: 4 consecutive elements per access.
+typedef __nv_bfloat16 lb_bf16;
 __device__ __forceinline__ float4 lb_ld4(const float* p) {
   return __ldg(reinterpret_cast<const float4*>(p));
 }
 __device__ __forceinline__ void lb_st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 lb_ld4(const lb_bf16* p) {
+  const uint2 r = __ldg(reinterpret_cast<const uint2*>(p));
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void lb_st4(lb_bf16* p, float4 v) {
+  const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+  uint2 r;
+  r.x = *reinterpret_cast<const uint32_t*>(&lo);
+  r.y = *reinterpret_cast<const uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = r;
+}
+__device__ __forceinline__ float lb_ld1(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float lb_ld1(const lb_bf16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void lb_st1(float* p, float v) { *p = v; }
+__device__ __forceinline__ void lb_st1(lb_bf16* p, float v) { *p = __float2bfloat16(v); }
+// is a 4-element access at p aligned?
+template <typename T>
+__host__ __device__ static inline bool lb_vec4_ok(const T* p) { return (reinterpret_cast<uintptr_t>(p) & (4 * sizeof(T) - 1)) == 0; }
+// LB_DISPATCH(dtype, T, statement using T): instantiate for the storage type named by the C-ABI `dtype` argument
+#define LB_DISPATCH(dtype, T, ...)                                          \
+  do {                                                                      \
+    if ((dtype) == LB_F32) { typedef float T; __VA_ARGS__; }                \
+    else if ((dtype) == LB_BF16) { typedef lb_bf16 T; __VA_ARGS__; }        \
+    else return LB_EINVAL;                                                  \
+  } while (0)
+template <typename T> static inline const T* lb_cp(const void* p) { return reinterpret_cast<const T*>(p); }
+template <typename T> static inline T* lb_p(void* p) { return reinterpret_cast<T*>(p); }
 
 // ---- RootTanh scalar math (libs/activation.py:9-36), fp32 ---------------------------------
 // tanh and sech^2 from one exp(-2|x|): exact limits, no cosh overflow (the reference's 1/cosh^2 -> 0 for |x| > 44 is

@@ -18,8 +18,10 @@
 #define SMALL_THREADS 256
 #define SMALL_MAX_W 4096      // floats of weight held in shared memory
 
+// `in` / `out` / `xpre` are untyped here: the NARROW side (<= 4 channels) is always fp32, the wide side has the storage
+// type the kernel is instantiated for (fp32 or bf16).
 struct SmallP {
-  const float* in; const float* w; const float* alpha; const float* bias; const float* xpre; float* out;
+  const void* in; const float* w; const float* alpha; const float* bias; const void* xpre; void* out;
   int batch, in_h, in_w, in_c, out_h, out_w, out_c;
   int kh, kw, stride, pad, mode, ld_in, ld_out, ld_xpre;
   long long w_sk, w_sn, w_sty, w_stx;
@@ -52,8 +54,11 @@ __device__ __forceinline__ bool small_src(int mode, int stride, int sh, int pad,
 // ---- narrow INPUT (in_c <= 4): forward of the stem layers, input gradient of a wide -> 3 layer -------------------
 // NCH x 16 output columns per thread.  Shared weight wsm[tap][k][16*NCH] holds alpha * W (and, for a concat, identity
 // columns that copy the input), bsm the bias per column.
-template <int NCH>
+template <int NCH, typename TO>
 __global__ void __launch_bounds__(SMALL_THREADS) k_small_narrow_in(const SmallP p) {
+  const float* p_in = reinterpret_cast<const float*>(p.in);
+  TO* p_out = reinterpret_cast<TO*>(p.out);
+  const TO* p_xpre = reinterpret_cast<const TO*>(p.xpre);
   constexpr int NC = 16 * NCH;
   extern __shared__ float4 sm4[];
   float* wsm = reinterpret_cast<float*>(sm4);
@@ -73,7 +78,7 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_small_narrow_in(const SmallP 
   __syncthreads();
   const int sh = p.stride == 2 ? 1 : 0;
   const int gi = p.growth_in, go = p.growth_out;
-  const bool vec_out = !(p.ld_out & 3) && lb_aligned16(p.out);
+  const bool vec_out = !(p.ld_out & 3) && lb_vec4_ok(p_out);
   const int stride_t = gridDim.x * blockDim.x;
   for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < p.pixels; pix += stride_t) {
     float acc[NC];
@@ -95,7 +100,7 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_small_narrow_in(const SmallP 
       }
     };
     if (p.pointwise) {
-      tap_fma(p.in + (size_t)pix * p.ld_in, wsm);
+      tap_fma(p_in + (size_t)pix * p.ld_in, wsm);
     } else {
       int t, ox, oy, b;
       lb_fast_divmod(p.d_w, pix, t, ox);
@@ -106,37 +111,41 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_small_narrow_in(const SmallP 
         for (int tx = 0; tx < p.kw; ++tx) {
           int ix;
           if (!small_src(p.mode, p.stride, sh, p.pad, ox, tx, p.in_w, ix)) continue;
-          tap_fma(p.in + ((size_t)(b * p.in_h + iy) * p.in_w + ix) * p.ld_in, wsm + (ty * p.kw + tx) * p.in_c * NC);
+          tap_fma(p_in + ((size_t)(b * p.in_h + iy) * p.in_w + ix) * p.ld_in, wsm + (ty * p.kw + tx) * p.in_c * NC);
         }
       }
     }
     if (go > 0) {
-      const float* xr = p.xpre + (size_t)pix * p.ld_xpre;
+      const TO* xr = p_xpre + (size_t)pix * p.ld_xpre;
 #pragma unroll
       for (int n = 0; n < NC; ++n)
-        if (n < p.out_c) acc[n] *= small_dact(__ldg(xr + n), go);       // no concat on this path (checked by the host)
+        if (n < p.out_c) acc[n] *= small_dact(lb_ld1(xr + n), go);      // no concat on this path (checked by the host)
     }
-    float* dst = p.out + (size_t)pix * p.ld_out;
+    TO* dst = p_out + (size_t)pix * p.ld_out;
     if (vec_out) {
 #pragma unroll
       for (int j = 0; j < NC / 4; ++j) {
         if (4 * j + 3 < cols) lb_st4(dst + 4 * j, make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]));
         else {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) if (4 * j + i < cols) dst[4 * j + i] = acc[4 * j + i];
+          for (int i = 0; i < 4; ++i) if (4 * j + i < cols) lb_st1(dst + 4 * j + i, acc[4 * j + i]);
         }
       }
     } else {
 #pragma unroll
-      for (int n = 0; n < NC; ++n) if (n < cols) dst[n] = acc[n];
+      for (int n = 0; n < NC; ++n) if (n < cols) lb_st1(dst + n, acc[n]);
     }
   }
 }
 
 // ---- narrow OUTPUT (out_c <= 4): input gradient of the stem layers, forward of a wide -> 3 layer --------------------
 // wsm[tap][k] = alpha * W(tap, k, 0..3) as one float4
+template <typename TI>
 __global__ void __launch_bounds__(SMALL_THREADS) k_small_narrow_out(const SmallP p) {
   extern __shared__ float4 sm4[];
+  const TI* p_in = reinterpret_cast<const TI*>(p.in);
+  float* p_out = reinterpret_cast<float*>(p.out);
+  const float* p_xpre = reinterpret_cast<const float*>(p.xpre);
   const int taps = p.kh * p.kw;
   const float alpha = p.alpha ? __ldg(p.alpha) : 1.0f;
   for (int i = threadIdx.x; i < taps * p.in_c; i += blockDim.x) {
@@ -150,14 +159,14 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_small_narrow_out(const SmallP
   __syncthreads();
   const int sh = p.stride == 2 ? 1 : 0;
   const int gi = p.growth_in, go = p.growth_out;
-  const bool vec_in = !(p.in_c & 3) && !(p.ld_in & 3) && lb_aligned16(p.in);
+  const bool vec_in = !(p.in_c & 3) && !(p.ld_in & 3) && lb_vec4_ok(p_in);
   float b4[4];
 #pragma unroll
   for (int n = 0; n < 4; ++n) b4[n] = (p.bias && n < p.out_c) ? __ldg(p.bias + n) : 0.0f;
   const int stride_t = gridDim.x * blockDim.x;
   for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < p.pixels; pix += stride_t) {
     float a0 = b4[0], a1 = b4[1], a2 = b4[2], a3 = b4[3];
-    auto tap_fma = [&](const float* src, const float4* wt) {
+    auto tap_fma = [&](const TI* src, const float4* wt) {
       if (vec_in) {
         for (int k = 0; k < p.in_c; k += 4) {
           const float4 x4 = lb_ld4(src + k);
@@ -171,14 +180,14 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_small_narrow_out(const SmallP
       } else {
 #pragma unroll 4
         for (int k = 0; k < p.in_c; ++k) {
-          const float xv = small_act(__ldg(src + k), gi);
+          const float xv = small_act(lb_ld1(src + k), gi);
           const float4 wv = wt[k];
           a0 = fmaf(xv, wv.x, a0); a1 = fmaf(xv, wv.y, a1); a2 = fmaf(xv, wv.z, a2); a3 = fmaf(xv, wv.w, a3);
         }
       }
     };
     if (p.pointwise) {
-      tap_fma(p.in + (size_t)pix * p.ld_in, sm4);
+      tap_fma(p_in + (size_t)pix * p.ld_in, sm4);
     } else {
       int t, ox, oy, b;
       lb_fast_divmod(p.d_w, pix, t, ox);
@@ -189,16 +198,16 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_small_narrow_out(const SmallP
         for (int tx = 0; tx < p.kw; ++tx) {
           int ix;
           if (!small_src(p.mode, p.stride, sh, p.pad, ox, tx, p.in_w, ix)) continue;
-          tap_fma(p.in + ((size_t)(b * p.in_h + iy) * p.in_w + ix) * p.ld_in, sm4 + (ty * p.kw + tx) * p.in_c);
+          tap_fma(p_in + ((size_t)(b * p.in_h + iy) * p.in_w + ix) * p.ld_in, sm4 + (ty * p.kw + tx) * p.in_c);
         }
       }
     }
     float r[4] = {a0, a1, a2, a3};
-    float* dst = p.out + (size_t)pix * p.ld_out;
+    float* dst = p_out + (size_t)pix * p.ld_out;
 #pragma unroll
     for (int n = 0; n < 4; ++n) {
       if (n < p.out_c) {
-        if (go > 0) r[n] *= small_dact(__ldg(p.xpre + (size_t)pix * p.ld_xpre + n), go);
+        if (go > 0) r[n] *= small_dact(__ldg(p_xpre + (size_t)pix * p.ld_xpre + n), go);
         dst[n] = r[n];
       }
     }
@@ -222,10 +231,13 @@ extern "C" int lb_conv_small_supported(const lb_conv_geom* g) {
 
 // cat_input != 0: `out` points at the START of rows of in_c + out_c floats (row stride g->ld_out); the kernel writes the
 // input copy and the conv result of a CatModule in one pass (1x1 stride-1 layers with in_c <= 4, no fused activations).
-extern "C" int lb_conv_small(const float* in, const float* w, const float* alpha, const float* bias, float* out,
-                             const lb_conv_geom* g, int growth_in, const float* xpre, int ld_xpre, int growth_out,
-                             int cat_input, lb_stream_t s) {
+// wide_dtype: storage of the WIDE side (out and xpre when in_c <= 4, else in); the narrow side is fp32.  A layer with
+// both sides narrow (3 -> 3) is all fp32: pass LB_F32.
+extern "C" int lb_conv_small(const void* in, const float* w, const float* alpha, const float* bias, void* out,
+                             const lb_conv_geom* g, int growth_in, const void* xpre, int ld_xpre, int growth_out,
+                             int cat_input, int wide_dtype, lb_stream_t s) {
   LB_REQUIRE(in && w && out && g && growth_in >= 0 && growth_out >= 0 && (growth_out == 0 || xpre));
+  LB_REQUIRE(wide_dtype == LB_F32 || wide_dtype == LB_BF16);
   if (!lb_conv_small_supported(g)) return LB_EUNSUPPORTED;
   SmallP p;
   p.in = in; p.w = w; p.alpha = alpha; p.bias = bias; p.xpre = xpre; p.out = out;
@@ -247,16 +259,18 @@ extern "C" int lb_conv_small(const float* in, const float* w, const float* alpha
     if (cols > 64) return LB_EUNSUPPORTED;
     const int nch = (cols + 15) / 16;
     const size_t smem = ((size_t)taps * g->in_c * 16 * nch + 16 * nch) * sizeof(float);
-    switch (nch) {
-      case 1: k_small_narrow_in<1><<<grid, SMALL_THREADS, smem, lb_s(s)>>>(p); break;
-      case 2: k_small_narrow_in<2><<<grid, SMALL_THREADS, smem, lb_s(s)>>>(p); break;
-      case 3: k_small_narrow_in<3><<<grid, SMALL_THREADS, smem, lb_s(s)>>>(p); break;
-      default: k_small_narrow_in<4><<<grid, SMALL_THREADS, smem, lb_s(s)>>>(p); break;
-    }
+    LB_DISPATCH(wide_dtype, T, {
+      switch (nch) {
+        case 1: k_small_narrow_in<1, T><<<grid, SMALL_THREADS, smem, lb_s(s)>>>(p); break;
+        case 2: k_small_narrow_in<2, T><<<grid, SMALL_THREADS, smem, lb_s(s)>>>(p); break;
+        case 3: k_small_narrow_in<3, T><<<grid, SMALL_THREADS, smem, lb_s(s)>>>(p); break;
+        default: k_small_narrow_in<4, T><<<grid, SMALL_THREADS, smem, lb_s(s)>>>(p); break;
+      }
+    });
   } else {
     if (p.cat) return LB_EUNSUPPORTED;
     const size_t smem = (size_t)taps * g->in_c * sizeof(float4);
-    k_small_narrow_out<<<grid, SMALL_THREADS, smem, lb_s(s)>>>(p);
+    LB_DISPATCH(wide_dtype, T, k_small_narrow_out<T><<<grid, SMALL_THREADS, smem, lb_s(s)>>>(p));
   }
   LB_LAUNCH_CHECK();
   return LB_OK;
@@ -269,14 +283,14 @@ extern "C" int lb_conv_small(const float* in, const float* w, const float* alpha
 //   kNarrowDense = false: 1x1 layers with g_c <= 4: narrow = gathered pixel (g_c), wide = dense channels [16*chunk, +16)
 //   kNarrowDense = true : d_c <= 4: narrow = dense pixel, wide = im2col entries [16*chunk, +16) of (tap, kg) (tap-major)
 struct SmallWgP {
-  const float* gath; const float* dense; float* dw;
+  const void* gath; const void* dense; float* dw;      // the narrow operand is fp32, the wide one has storage TW
   int g_h, g_w, g_c, d_h, d_w, d_c, kh, kw, stride, pad, ld_g, ld_d;
   long long w_sk, w_sn, w_sty, w_stx;
   int pixels, rows, growth_g;
-  int d_shift, d_vec;   // dense rows start d_shift floats before `dense` on a 16-byte boundary; d_vec: float4 loads usable
+  int d_shift, d_vec;   // dense rows start d_shift elements before `dense` on a 4-element boundary; d_vec: 4-element loads usable
   LbFastDiv f_gc, f_kw, f_w, f_h;
 };
-template <bool kNarrowDense>
+template <bool kNarrowDense, typename TW>
 __global__ void __launch_bounds__(SMALL_THREADS) k_small_wgrad(const SmallWgP p) {
   __shared__ float s_red[64];
   if (threadIdx.x < 64) s_red[threadIdx.x] = 0.0f;
@@ -305,8 +319,8 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_small_wgrad(const SmallWgP p)
     if (!kNarrowDense) {
       // wide index = column of the 16-byte aligned dense row (a concat slice starts d_shift floats into it); columns
       // outside [d_shift, d_shift + d_c) are dropped when the sums are written
-      const float* gs = p.gath + (size_t)pix * p.ld_g;
-      const float* ds = p.dense - p.d_shift + (size_t)pix * p.ld_d + w0;
+      const float* gs = reinterpret_cast<const float*>(p.gath) + (size_t)pix * p.ld_g;
+      const TW* ds = reinterpret_cast<const TW*>(p.dense) - p.d_shift + (size_t)pix * p.ld_d + w0;
 #pragma unroll
       for (int n = 0; n < 4; ++n) nv[n] = n < p.g_c ? small_act(__ldg(gs + n), gg) : 0.0f;
       if (p.d_vec) {                                   // a thread reads its own row: 16-byte loads touch each sector twice,
@@ -317,10 +331,10 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_small_wgrad(const SmallWgP p)
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) wv[i] = w0 + i < p.d_shift + p.d_c ? __ldg(ds + i) : 0.0f;
+        for (int i = 0; i < 16; ++i) wv[i] = w0 + i < p.d_shift + p.d_c ? lb_ld1(ds + i) : 0.0f;
       }
     } else {
-      const float* ds = p.dense + (size_t)pix * p.ld_d;
+      const float* ds = reinterpret_cast<const float*>(p.dense) + (size_t)pix * p.ld_d;
 #pragma unroll
       for (int n = 0; n < 4; ++n) nv[n] = n < p.d_c ? __ldg(ds + n) : 0.0f;
       int t, ox, oy, b;
@@ -332,7 +346,7 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_small_wgrad(const SmallWgP p)
         const int iy = iy0 + e_ty[i], ix = ix0 + e_tx[i];
         float v = 0.0f;
         if (w0 + i < p.rows && iy >= 0 && iy < p.g_h && ix >= 0 && ix < p.g_w)
-          v = small_act(__ldg(p.gath + ((size_t)(b * p.g_h + iy) * p.g_w + ix) * p.ld_g + e_kg[i]), gg);   // act(0) = 0
+          v = small_act(lb_ld1(reinterpret_cast<const TW*>(p.gath) + ((size_t)(b * p.g_h + iy) * p.g_w + ix) * p.ld_g + e_kg[i]), gg);   // act(0) = 0
         wv[i] = v;
       }
     }
@@ -393,9 +407,11 @@ extern "C" int lb_conv_small_wgrad_supported(const lb_conv_geom* g) {
 }
 // geom as lb_conv_wgrad: in_* = gathered operand, out_* = dense operand; dw in the master layout (+=, caller zeroes);
 // growth_gathered > 0 applies RootTanh to the gathered operand on load (the layer's pre-activation)
-extern "C" int lb_conv_small_wgrad(const float* gathered, const float* dense, float* dw, const lb_conv_geom* g, int growth_gathered,
-                                   lb_stream_t s) {
+// wide_dtype: storage of the wide operand (dense for 1x1 layers with in_c <= 4, else gathered); the narrow one is fp32
+extern "C" int lb_conv_small_wgrad(const void* gathered, const void* dense, float* dw, const lb_conv_geom* g, int growth_gathered,
+                                   int wide_dtype, lb_stream_t s) {
   LB_REQUIRE(gathered && dense && dw && g && growth_gathered >= 0);
+  LB_REQUIRE(wide_dtype == LB_F32 || wide_dtype == LB_BF16);
   if (!lb_conv_small_wgrad_supported(g)) return LB_EUNSUPPORTED;
   SmallWgP p;
   p.gath = gathered; p.dense = dense; p.dw = dw;
@@ -409,17 +425,20 @@ extern "C" int lb_conv_small_wgrad(const float* gathered, const float* dense, fl
   p.f_w = lb_make_fastdiv(g->out_w); p.f_h = lb_make_fastdiv(g->out_h);
   const bool narrow_gathered = small_pointwise(g) && g->in_c <= 4;
   p.d_shift = 0; p.d_vec = 0;
-  if (narrow_gathered && !(g->ld_out & 3)) {           // dense rows are 16-byte aligned up to a fixed offset of the base
-    p.d_shift = (int)((reinterpret_cast<uintptr_t>(dense) & 15) / 4);
-    p.d_vec = (reinterpret_cast<uintptr_t>(dense) & 3) == 0 && p.d_shift + g->out_c <= g->ld_out ? 1 : 0;
+  if (narrow_gathered && !(g->ld_out & 3)) {           // dense rows are aligned for 4-element loads up to a fixed offset of the base
+    const uintptr_t esz = wide_dtype == LB_BF16 ? 2 : 4;
+    p.d_shift = (int)((reinterpret_cast<uintptr_t>(dense) & (4 * esz - 1)) / esz);
+    p.d_vec = (reinterpret_cast<uintptr_t>(dense) & (esz - 1)) == 0 && p.d_shift + g->out_c <= g->ld_out ? 1 : 0;
     if (!p.d_vec) p.d_shift = 0;
   }
   const int chunks = narrow_gathered ? (p.d_shift + g->out_c + 15) / 16 : (p.rows + 15) / 16;
   int gx = lb_grid_1d((size_t)p.pixels, SMALL_THREADS, chunks >= 4 ? 1 : 2);   // many pixels per thread: the final reduction is a fixed cost
   if (chunks > 65535) return LB_EUNSUPPORTED;
   dim3 grid(gx, chunks);
-  if (narrow_gathered) k_small_wgrad<false><<<grid, SMALL_THREADS, 0, lb_s(s)>>>(p);
-  else k_small_wgrad<true><<<grid, SMALL_THREADS, 0, lb_s(s)>>>(p);
+  LB_DISPATCH(wide_dtype, T, {
+    if (narrow_gathered) k_small_wgrad<false, T><<<grid, SMALL_THREADS, 0, lb_s(s)>>>(p);
+    else k_small_wgrad<true, T><<<grid, SMALL_THREADS, 0, lb_s(s)>>>(p);
+  });
   LB_LAUNCH_CHECK();
   return LB_OK;
 }

@@ -41,7 +41,8 @@ struct TcParams {
   int kh, kw, stride, pad, mode;
   int rows_per_tap;                   // rows of Wp per tap (= out_c)
   int view_empty;                     // bit v set: parity view v has no pixels
-  const float* alpha; const float* bias; float* out;
+  const float* alpha; const float* bias; void* out;
+  int out_bf16;                       // `out` rows are bf16 (activation storage of the tensor-core configuration) instead of fp32
   float* part;                        // split-K partial sums [splits][rows][out_c] (raw accumulators), NULL when splits == 1
   long long part_rows;
 };
@@ -162,9 +163,12 @@ __global__ void __launch_bounds__(192, 4) k_conv_tc(const __grid_constant__ TcMa
     const int x = x0 + wl, y = y0 + hl, b = b0 + bl;
     const int oy = y * p.sp + py, ox = x * p.sp + px;
     const bool valid = x < p.dst_w && y < p.dst_h && b < p.batch && oy < p.out_h && ox < p.out_w;
-    float* dst = p.out + ((size_t)(b * p.out_h + oy) * p.out_w + ox) * p.ld_out;
+    const size_t row_off = ((size_t)(b * p.out_h + oy) * p.out_w + ox) * p.ld_out;
+    float* dst = reinterpret_cast<float*>(p.out) + row_off;
+    __nv_bfloat16* dst16 = reinterpret_cast<__nv_bfloat16*>(p.out) + row_off;
     const float alpha = p.alpha ? __ldg(p.alpha) : 1.0f;
-    const bool vec = (p.ld_out & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+    const bool vec = p.out_bf16 ? ((p.ld_out & 7) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0)
+                                : ((p.ld_out & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
     if (iters > 0) {
       tc::mbar_wait(&bar_acc, 0);
       tc::tc_fence_after();
@@ -188,7 +192,22 @@ __global__ void __launch_bounds__(192, 4) k_conv_tc(const __grid_constant__ TcMa
         }
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = v[i] * alpha + ((p.bias && n + i < p.out_c) ? __ldg(p.bias + n + i) : 0.0f);
-        if (vec && n + 15 < p.out_c) {
+        if (p.out_bf16) {
+          if (vec && n + 15 < p.out_c) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 8) {
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(v[i], v[i + 1]), h1 = __floats2bfloat162_rn(v[i + 2], v[i + 3]);
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(v[i + 4], v[i + 5]), h3 = __floats2bfloat162_rn(v[i + 6], v[i + 7]);
+              uint4 pk;
+              pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+              pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+              *reinterpret_cast<uint4*>(dst16 + n + i) = pk;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) if (n + i < p.out_c) dst16[n + i] = __float2bfloat16(v[i]);
+          }
+        } else if (vec && n + 15 < p.out_c) {
 #pragma unroll
           for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst + n + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
         } else {
@@ -285,11 +304,11 @@ extern "C" int lb_conv_tc_pack(const float* w, void* packed, const lb_conv_geom*
 }
 
 extern "C" int lb_conv_tc_gemm_ex(const void* in_bf16, const void* w_packed, const float* alpha, const float* bias, float* out32,
-                                  void* out16, int ld_out16, int act16, const float* aux, int ld_aux, const lb_conv_geom* g,
-                                  lb_stream_t s);
-extern "C" int lb_conv_tc_ex_supported(const lb_conv_geom* g, int ld_out16, int ld_aux);
-extern "C" int lb_conv_tc_gemm_ws(const void* in_bf16, const void* w_packed, const float* alpha, const float* bias, float* out,
-                                  const lb_conv_geom* g, void* work, size_t work_bytes, lb_stream_t s);
+                                  void* out16, void* out16a, int ld_out16, const void* aux, int ld_aux, int aux_dtype,
+                                  const lb_conv_geom* g, lb_stream_t s);
+extern "C" int lb_conv_tc_ex_supported(const lb_conv_geom* g, int out32_used, int ld_out16, int ld_aux, int aux_dtype);
+extern "C" int lb_conv_tc_gemm_ws(const void* in_bf16, const void* w_packed, const float* alpha, const float* bias, void* out,
+                                  const lb_conv_geom* g, void* work, size_t work_bytes, int out_dtype, lb_stream_t s);
 
 // Live taps of the first tile along one axis (host replica of the kernels' tap walk): a tap whose source box lies
 // entirely in the padding contributes nothing, and the persistent kernel skips it.
@@ -330,9 +349,10 @@ static bool prefer_persistent(const lb_conv_geom* g) {
 }
 
 // out[row][n] = alpha * (part[0][row][n] + part[1][row][n] + ...) + bias[n], splits added in index order
+template <typename T>
 __global__ void __launch_bounds__(256) k_splitk_reduce(const float* __restrict__ part, int splits, size_t rows, int out_c, int ld_out,
                                                       const float* __restrict__ alpha, const float* __restrict__ bias,
-                                                      float* __restrict__ out) {
+                                                      T* __restrict__ out) {
   const float a = alpha ? __ldg(alpha) : 1.0f;
   const size_t n = rows * (size_t)out_c;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -341,7 +361,7 @@ __global__ void __launch_bounds__(256) k_splitk_reduce(const float* __restrict__
     const int c = (int)(i - r * out_c);
     float acc = part[i];
     for (int sp = 1; sp < splits; ++sp) acc += part[(size_t)sp * n + i];
-    out[r * ld_out + c] = fmaf(acc, a, bias ? __ldg(bias + c) : 0.0f);
+    lb_st1(out + r * ld_out + c, fmaf(acc, a, bias ? __ldg(bias + c) : 0.0f));
   }
 }
 
@@ -376,17 +396,20 @@ extern "C" size_t lb_conv_tc_workspace_bytes(const lb_conv_geom* g) {
 
 extern "C" int lb_conv_tc_gemm(const void* in_bf16, const void* w_packed, const float* alpha, const float* bias, float* out,
                                const lb_conv_geom* g, lb_stream_t s) {
-  return lb_conv_tc_gemm_ws(in_bf16, w_packed, alpha, bias, out, g, nullptr, 0, s);
+  return lb_conv_tc_gemm_ws(in_bf16, w_packed, alpha, bias, out, g, nullptr, 0, LB_F32, s);
 }
 
-extern "C" int lb_conv_tc_gemm_ws(const void* in_bf16, const void* w_packed, const float* alpha, const float* bias, float* out,
-                                  const lb_conv_geom* g, void* work, size_t work_bytes, lb_stream_t s) {
+extern "C" int lb_conv_tc_gemm_ws(const void* in_bf16, const void* w_packed, const float* alpha, const float* bias, void* out,
+                                  const lb_conv_geom* g, void* work, size_t work_bytes, int out_dtype, lb_stream_t s) {
   LB_REQUIRE(in_bf16 && w_packed && out && g);
+  LB_REQUIRE(out_dtype == LB_F32 || out_dtype == LB_BF16);
   if (!tc_geom_ok(g)) return LB_EUNSUPPORTED;
   static const bool v1_only = getenv("LB_TC_V1_ONLY") != nullptr;      // debugging switches are read once, not per launch
-  if (!v1_only && prefer_persistent(g) && lb_conv_tc_ex_supported(g, 0, 0) == 1 && !(g->ld_out & 3) &&
+  const bool o16 = out_dtype == LB_BF16;
+  if (!v1_only && prefer_persistent(g) && lb_conv_tc_ex_supported(g, o16 ? 0 : 1, o16 ? g->ld_out : 0, 0, LB_F32) == 1 &&
       !(reinterpret_cast<uintptr_t>(out) & 15)) {
-    const int rc = lb_conv_tc_gemm_ex(in_bf16, w_packed, alpha, bias, out, nullptr, 0, 0, nullptr, 0, g, s);
+    const int rc = lb_conv_tc_gemm_ex(in_bf16, w_packed, alpha, bias, o16 ? nullptr : reinterpret_cast<float*>(out), o16 ? out : nullptr,
+                                      nullptr, o16 ? g->ld_out : 0, nullptr, 0, LB_F32, g, s);
     if (rc != LB_EUNSUPPORTED) return rc;
   }
   if (reinterpret_cast<uintptr_t>(in_bf16) & 15 || reinterpret_cast<uintptr_t>(w_packed) & 15) return LB_EALIGN;
@@ -409,7 +432,7 @@ extern "C" int lb_conv_tc_gemm_ws(const void* in_bf16, const void* w_packed, con
   p.block_n = bn;
   p.kchunks = (g->in_c + kBlockK - 1) / kBlockK;
   p.rows_per_tap = g->out_c;
-  p.alpha = alpha; p.bias = bias; p.out = out;
+  p.alpha = alpha; p.bias = bias; p.out = out; p.out_bf16 = o16 ? 1 : 0;
   const int stage_bytes = kABytes + bn * kBlockK * 2;
 
   // source views: mode 0 with stride 2 -> 4 parity views; otherwise one dense view
@@ -471,7 +494,8 @@ extern "C" int lb_conv_tc_gemm_ws(const void* in_bf16, const void* w_packed, con
   k_conv_tc<<<grid, 192, smem_bytes, lb_s(s)>>>(maps, p);
   LB_LAUNCH_CHECK();
   if (p.splits > 1) {
-    k_splitk_reduce<<<lb_grid_1d(rows * g->out_c, 256), 256, 0, lb_s(s)>>>(p.part, p.splits, rows, g->out_c, g->ld_out, alpha, bias, out);
+    LB_DISPATCH(out_dtype, T, k_splitk_reduce<<<lb_grid_1d(rows * g->out_c, 256), 256, 0, lb_s(s)>>>(p.part, p.splits, rows, g->out_c,
+                                                                                                    g->ld_out, alpha, bias, lb_p<T>(out)));
     LB_LAUNCH_CHECK();
   }
   return LB_OK;

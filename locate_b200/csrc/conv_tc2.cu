@@ -1,9 +1,12 @@
 // Persistent tcgen05 / TMEM / TMA implicit-GEMM for the convolution family with a fused, TMA-stored epilogue.
 //
 //   acc[pixel][n] = alpha * sum_taps sum_k A_tap[pixel][k] * Wp[tap][n][k]  (+ bias[n])
-//   if aux:   acc *= RootTanh'(aux[pixel][n])            (the activation backward that follows a dgrad GEMM)
-//   if out32: out32[pixel][n] = acc                       (fp32)
-//   if out16: out16[pixel][n] = bf16(act16 ? RootTanh(acc) : acc)   (the next GEMM's operand, produced in place)
+//   if aux:    acc *= RootTanh'(aux[pixel][n])           (the activation backward that follows a dgrad GEMM; aux fp32 or bf16)
+//   if out32:  out32[pixel][n]  = acc                     (fp32)
+//   if out16:  out16[pixel][n]  = bf16(acc)               (bf16 activation storage: pre-activation / gradient)
+//   if out16a: out16a[pixel][n] = bf16(RootTanh(acc'))    (the next GEMM's operand, produced in place; acc' = the value
+//                                                          stored by out16 when both are written, so that the backward's
+//                                                          RootTanh'(out16) belongs to exactly this function value)
 //
 // Operand staging and tap handling are those of conv_tc.cu (per-tap dense TMA boxes of parity views, zero fill =
 // padding).  What is different:
@@ -36,6 +39,7 @@ struct Tc2Maps {
   CUtensorMap b;
   CUtensorMap o32[kMaxViews];
   CUtensorMap o16[kMaxViews];
+  CUtensorMap o16a[kMaxViews];
   CUtensorMap aux[kMaxViews];
 };
 
@@ -50,13 +54,13 @@ struct Tc2Params {
   int kh, kw, stride, pad, mode;
   int rows_per_tap, view_empty;
   int ebw, ebh, ebb;                  // 32-row sub-box of one epilogue warp
-  int has_o32, has_o16, has_aux;
-  int act16;                          // 1: RootTanh (growth 4) applied to the bf16 output
+  int has_o32, has_o16, has_o16a, has_aux;
+  int aux_bf16;                       // aux slabs are bf16 (64-byte rows) instead of fp32 (128-byte rows)
   uint32_t tmem_cols;
   uint32_t tab_base; int max_tp;      // per-phase tap table in shared memory: max_tp entries per phase
   int resident;                       // 1: the weights of one output phase stay in shared memory (res_base), stages carry A only
   uint32_t res_base, b_tile_bytes;
-  uint32_t epi_base, epi_per_warp, off_o32, off_o16, off_aux;   // bytes; epi_base relative to the 1 KB aligned base
+  uint32_t epi_base, epi_per_warp, off_o32, off_o16, off_o16a, off_aux, aux_bytes;   // bytes; epi_base relative to the 1 KB aligned base
   const float* alpha; const float* bias;
 };
 
@@ -341,7 +345,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
     uint8_t* ebase = smem + p.epi_base + (uint32_t)ew * p.epi_per_warp;
     uint8_t* s_o32 = ebase + p.off_o32;
     uint8_t* s_o16 = ebase + p.off_o16;
-    uint8_t* s_aux = ebase + p.off_aux;           // 2 x 4 KB
+    uint8_t* s_o16a = ebase + p.off_o16a;
+    uint8_t* s_aux = ebase + p.off_aux;           // 2 x (4 KB fp32 | 2 KB bf16)
     const float alpha = p.alpha ? __ldg(p.alpha) : 1.0f;
     const int sw = lane & 7;                      // 128B swizzle: 16-byte chunk j of row r lives at chunk j ^ (r & 7)
     const int sw64 = (lane >> 1) & 3;             // 64B swizzle: chunk j of row r lives at chunk j ^ ((r >> 1) & 3)
@@ -365,8 +370,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
       if (lane == 0) {
         const TileCoord c = decode_tile(p, a_tile);
         const uint32_t buf = a_issued & 1u;
-        tc::mbar_arrive_expect_tx(&bar_aux[ew][buf], 32 * kSlab * 4);
-        tc::tma_load_4d(s_aux + buf * 4096, &maps.aux[c.phase], &bar_aux[ew][buf], c.n0 + a_slab * kSlab, c.x0 + w_off,
+        tc::mbar_arrive_expect_tx(&bar_aux[ew][buf], p.aux_bytes);
+        tc::tma_load_4d(s_aux + buf * p.aux_bytes, &maps.aux[c.phase], &bar_aux[ew][buf], c.n0 + a_slab * kSlab, c.x0 + w_off,
                         c.y0 + h_off, c.b0 + b_off);
       }
       ++a_issued;
@@ -398,14 +403,29 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
         if (p.has_aux) {
           const uint32_t buf = a_done & 1u;
           tc::mbar_wait(&bar_aux[ew][buf], (a_done >> 1) & 1u);
-          const uint8_t* row = s_aux + buf * 4096 + lane * 128;
+          if (p.aux_bf16) {
+            const uint8_t* row = s_aux + buf * 2048 + lane * 64;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 x4 = *reinterpret_cast<const float4*>(row + ((j ^ sw) << 4));
-            v[4 * j + 0] *= roottanh_grad_fast(x4.x);
-            v[4 * j + 1] *= roottanh_grad_fast(x4.y);
-            v[4 * j + 2] *= roottanh_grad_fast(x4.z);
-            v[4 * j + 3] *= roottanh_grad_fast(x4.w);
+            for (int j = 0; j < 4; ++j) {
+              const uint4 pk = *reinterpret_cast<const uint4*>(row + ((j ^ sw64) << 4));
+              const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+                v[8 * j + 2 * i] *= roottanh_grad_fast(f.x);
+                v[8 * j + 2 * i + 1] *= roottanh_grad_fast(f.y);
+              }
+            }
+          } else {
+            const uint8_t* row = s_aux + buf * 4096 + lane * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 x4 = *reinterpret_cast<const float4*>(row + ((j ^ sw) << 4));
+              v[4 * j + 0] *= roottanh_grad_fast(x4.x);
+              v[4 * j + 1] *= roottanh_grad_fast(x4.y);
+              v[4 * j + 2] *= roottanh_grad_fast(x4.z);
+              v[4 * j + 3] *= roottanh_grad_fast(x4.w);
+            }
           }
           ++a_done;
           __syncwarp();                           // every lane has read the buffer before it is refilled
@@ -421,19 +441,33 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
           for (int j = 0; j < 8; ++j)
             *reinterpret_cast<float4*>(row + ((j ^ sw) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
-        if (p.has_o16) {
+        if (p.has_o16 || p.has_o16a) {
           uint8_t* row = s_o16 + lane * 64;
+          uint8_t* rowa = s_o16a + lane * 64;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            float t[8];
+            __nv_bfloat162 h[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) t[i] = p.act16 ? roottanh_fast(v[8 * j + i]) : v[8 * j + i];
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(t[0], t[1]), h1 = __floats2bfloat162_rn(t[2], t[3]);
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(t[4], t[5]), h3 = __floats2bfloat162_rn(t[6], t[7]);
-            uint4 pk;
-            pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-            pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-            *reinterpret_cast<uint4*>(row + ((j ^ sw64) << 4)) = pk;
+            for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[8 * j + 2 * i], v[8 * j + 2 * i + 1]);
+            if (p.has_o16) {
+              uint4 pk;
+              pk.x = *reinterpret_cast<uint32_t*>(&h[0]); pk.y = *reinterpret_cast<uint32_t*>(&h[1]);
+              pk.z = *reinterpret_cast<uint32_t*>(&h[2]); pk.w = *reinterpret_cast<uint32_t*>(&h[3]);
+              *reinterpret_cast<uint4*>(row + ((j ^ sw64) << 4)) = pk;
+            }
+            if (p.has_o16a) {
+              __nv_bfloat162 a[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                // with a stored pre-activation the function value belongs to the STORED (rounded) argument
+                const float2 f = p.has_o16 ? __bfloat1622float2(h[i]) : make_float2(v[8 * j + 2 * i], v[8 * j + 2 * i + 1]);
+                a[i] = __floats2bfloat162_rn(roottanh_fast(f.x), roottanh_fast(f.y));
+              }
+              uint4 pk;
+              pk.x = *reinterpret_cast<uint32_t*>(&a[0]); pk.y = *reinterpret_cast<uint32_t*>(&a[1]);
+              pk.z = *reinterpret_cast<uint32_t*>(&a[2]); pk.w = *reinterpret_cast<uint32_t*>(&a[3]);
+              *reinterpret_cast<uint4*>(rowa + ((j ^ sw64) << 4)) = pk;
+            }
           }
         }
         tc::fence_proxy_async();
@@ -441,6 +475,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
         if (lane == 0) {
           if (p.has_o32) tma_store_4d(&maps.o32[c.phase], s_o32, n, c.x0 + w_off, c.y0 + h_off, c.b0 + b_off);
           if (p.has_o16) tma_store_4d(&maps.o16[c.phase], s_o16, n, c.x0 + w_off, c.y0 + h_off, c.b0 + b_off);
+          if (p.has_o16a) tma_store_4d(&maps.o16a[c.phase], s_o16a, n, c.x0 + w_off, c.y0 + h_off, c.b0 + b_off);
           bulk_commit();
         }
         stores_pending = true;
@@ -464,7 +499,8 @@ int pow2_ceil(int v) { int r = 1; while (r < v) r <<= 1; return r; }
 }  // namespace
 
 // Does the persistent kernel cover this geometry and these operands?  (Otherwise lb_conv_tc_gemm stays on k_conv_tc.)
-static bool tc2_ok(const lb_conv_geom* g, const void* out32, const void* out16, int ld16, const void* aux, int ld_aux) {
+static bool tc2_ok(const lb_conv_geom* g, const void* out32, const void* out16, const void* out16a, int ld16, const void* aux, int ld_aux,
+                   int aux_dtype) {
   if (g->stride != 1 && g->stride != 2) return false;
   if (g->ld_in % 8 || g->in_c < 1 || g->out_c < 1 || g->kh * g->kw > 1024) return false;
   if (g->mode == 1 && (g->kh < g->stride || g->kw < g->stride)) return false;          // a phase without taps
@@ -474,8 +510,10 @@ static bool tc2_ok(const lb_conv_geom* g, const void* out32, const void* out16, 
   }
   if (out32 && ((g->ld_out & 3) || (reinterpret_cast<uintptr_t>(out32) & 15))) return false;
   if (out16 && ((ld16 & 7) || (reinterpret_cast<uintptr_t>(out16) & 15))) return false;
-  if (aux && ((ld_aux & 3) || (reinterpret_cast<uintptr_t>(aux) & 15))) return false;
-  if (!out32 && !out16) return false;
+  if (out16a && ((ld16 & 7) || (reinterpret_cast<uintptr_t>(out16a) & 15))) return false;
+  if (aux && ((ld_aux & (aux_dtype == LB_BF16 ? 7 : 3)) || (reinterpret_cast<uintptr_t>(aux) & 15))) return false;
+  if (aux_dtype != LB_F32 && aux_dtype != LB_BF16) return false;
+  if (!out32 && !out16 && !out16a) return false;
   // weight-bound layers whose output tiling cannot fill the GPU stay on k_conv_tc's split-K path
   const int sp = g->mode == 1 ? g->stride : 1;
   const int dst_w = (g->out_w + sp - 1) / sp, dst_h = (g->out_h + sp - 1) / sp;
@@ -490,10 +528,10 @@ static bool tc2_ok(const lb_conv_geom* g, const void* out32, const void* out16, 
 }
 
 extern "C" int lb_conv_tc_gemm_ex(const void* in_bf16, const void* w_packed, const float* alpha, const float* bias, float* out32,
-                                  void* out16, int ld_out16, int act16, const float* aux, int ld_aux, const lb_conv_geom* g,
-                                  lb_stream_t s) {
+                                  void* out16, void* out16a, int ld_out16, const void* aux, int ld_aux, int aux_dtype,
+                                  const lb_conv_geom* g, lb_stream_t s) {
   LB_REQUIRE(in_bf16 && w_packed && g);
-  if (!tc2_ok(g, out32, out16, ld_out16, aux, ld_aux)) return LB_EUNSUPPORTED;
+  if (!tc2_ok(g, out32, out16, out16a, ld_out16, aux, ld_aux, aux_dtype)) return LB_EUNSUPPORTED;
   if (reinterpret_cast<uintptr_t>(in_bf16) & 15 || reinterpret_cast<uintptr_t>(w_packed) & 15) return LB_EALIGN;
   Tc2Maps maps;
   Tc2Params p;
@@ -515,13 +553,16 @@ extern "C" int lb_conv_tc_gemm_ex(const void* in_bf16, const void* w_packed, con
   p.kchunks = (g->in_c + kBlockK - 1) / kBlockK;
   p.rows_per_tap = g->out_c;
   p.alpha = alpha; p.bias = bias;
-  p.has_o32 = out32 ? 1 : 0; p.has_o16 = out16 ? 1 : 0; p.has_aux = aux ? 1 : 0; p.act16 = act16 ? 1 : 0;
+  p.has_o32 = out32 ? 1 : 0; p.has_o16 = out16 ? 1 : 0; p.has_o16a = out16a ? 1 : 0; p.has_aux = aux ? 1 : 0;
+  p.aux_bf16 = aux_dtype == LB_BF16 ? 1 : 0;
+  p.aux_bytes = p.aux_bf16 ? 32 * kSlab * 2 : 32 * kSlab * 4;
 
-  // epilogue staging per warp: fp32 slab 4 KB, bf16 slab 2 KB, aux 2 x 4 KB (all 1 KB aligned for the swizzle)
+  // epilogue staging per warp: fp32 slab 4 KB, bf16 slabs 2 KB each, aux 2 x (4 | 2) KB (all 1 KB aligned for the swizzle)
   uint32_t off = 0;
   p.off_o32 = off; if (out32) off += 4096;
   p.off_o16 = off; if (out16) off += 2048;
-  p.off_aux = off; if (aux) off += 8192;
+  p.off_o16a = off; if (out16a) off += 2048;
+  p.off_aux = off; if (aux) off += 2 * p.aux_bytes;
   p.epi_per_warp = (off + 1023) & ~1023u;
   const int tab_bytes = 4 * kMaxTapsPhase * (int)(sizeof(int4) + sizeof(int2));      // 6 KB
   const int epi_bytes = (int)p.epi_per_warp * kEpiWarps + tab_bytes;
@@ -613,19 +654,27 @@ extern "C" int lb_conv_tc_gemm_ex(const void* in_bf16, const void* w_packed, con
                             dims, st, box, CU_TENSOR_MAP_SWIZZLE_128B);
       if (rc) return rc;
     }
-    if (out16) {
+    if (out16 || out16a) {
       const uint64_t st[3] = {(uint64_t)p.sp * ld_out16 * 2, (uint64_t)p.sp * g->out_w * ld_out16 * 2,
                               (uint64_t)g->out_h * g->out_w * ld_out16 * 2};
-      int rc = tc::make_map(&maps.o16[v], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, reinterpret_cast<char*>(out16) + pix * ld_out16 * 2, 4,
-                            dims, st, box, CU_TENSOR_MAP_SWIZZLE_64B);
-      if (rc) return rc;
+      if (out16) {
+        int rc = tc::make_map(&maps.o16[v], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, reinterpret_cast<char*>(out16) + pix * ld_out16 * 2, 4,
+                              dims, st, box, CU_TENSOR_MAP_SWIZZLE_64B);
+        if (rc) return rc;
+      }
+      if (out16a) {
+        int rc = tc::make_map(&maps.o16a[v], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, reinterpret_cast<char*>(out16a) + pix * ld_out16 * 2, 4,
+                              dims, st, box, CU_TENSOR_MAP_SWIZZLE_64B);
+        if (rc) return rc;
+      }
     }
     if (aux) {
-      const uint64_t st[3] = {(uint64_t)p.sp * ld_aux * 4, (uint64_t)p.sp * g->out_w * ld_aux * 4,
-                              (uint64_t)g->out_h * g->out_w * ld_aux * 4};
-      int rc = tc::make_map(&maps.aux[v], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
-                            const_cast<char*>(reinterpret_cast<const char*>(aux)) + pix * ld_aux * 4, 4, dims, st, box,
-                            CU_TENSOR_MAP_SWIZZLE_128B);
+      const uint64_t es = p.aux_bf16 ? 2 : 4;
+      const uint64_t st[3] = {(uint64_t)p.sp * ld_aux * es, (uint64_t)p.sp * g->out_w * ld_aux * es,
+                              (uint64_t)g->out_h * g->out_w * ld_aux * es};
+      int rc = tc::make_map(&maps.aux[v], p.aux_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (int)es,
+                            const_cast<char*>(reinterpret_cast<const char*>(aux)) + pix * ld_aux * es, 4, dims, st, box,
+                            p.aux_bf16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
       if (rc) return rc;
     }
   }
@@ -643,9 +692,10 @@ extern "C" int lb_conv_tc_gemm_ex(const void* in_bf16, const void* w_packed, con
   return LB_OK;
 }
 
-extern "C" int lb_conv_tc_ex_supported(const lb_conv_geom* g, int ld_out16, int ld_aux) {
+// out32_used: an fp32 output (row stride g->ld_out) is written; ld_out16 / ld_aux: 0 = not used
+extern "C" int lb_conv_tc_ex_supported(const lb_conv_geom* g, int out32_used, int ld_out16, int ld_aux, int aux_dtype) {
   if (!g) return 0;
   // alignment of the pointers themselves is checked at call time; any 16-byte aligned base passes here
-  return tc2_ok(g, reinterpret_cast<const void*>(16), ld_out16 ? reinterpret_cast<const void*>(16) : nullptr, ld_out16,
-                ld_aux ? reinterpret_cast<const void*>(16) : nullptr, ld_aux) ? 1 : 0;
+  const void* ok = reinterpret_cast<const void*>(16);
+  return tc2_ok(g, out32_used ? ok : nullptr, ld_out16 ? ok : nullptr, nullptr, ld_out16, ld_aux ? ok : nullptr, ld_aux, aux_dtype) ? 1 : 0;
 }

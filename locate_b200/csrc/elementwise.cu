@@ -10,10 +10,10 @@ extern "C" int lb_last_launch_count(void) { return g_lb_launches; }
 extern "C" void lb_reset_launch_count(void) { g_lb_launches = 0; }
 
 // ------------------------------------------------------------------------------------------
-// generic unary / binary streaming kernels
+// generic unary / binary streaming kernels (storage type T: fp32 or bf16, fp32 arithmetic)
 // ------------------------------------------------------------------------------------------
-template <typename F>
-__global__ void __launch_bounds__(256) k_unary(const float* __restrict__ x, float* __restrict__ y, size_t n, F f) {
+template <typename T, typename F>
+__global__ void __launch_bounds__(256) k_unary(const T* __restrict__ x, T* __restrict__ y, size_t n, F f) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const size_t n4 = n >> 2;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -21,12 +21,11 @@ __global__ void __launch_bounds__(256) k_unary(const float* __restrict__ x, floa
     v.x = f(v.x); v.y = f(v.y); v.z = f(v.z); v.w = f(v.w);
     lb_st4(y + 4 * i, v);
   }
-  for (size_t i = (n4 << 2) + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] = f(x[i]);
+  for (size_t i = (n4 << 2) + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) lb_st1(y + i, f(lb_ld1(x + i)));
 }
 
-template <typename F>
-__global__ void __launch_bounds__(256) k_binary(const float* __restrict__ a, const float* __restrict__ b,
-                                                float* __restrict__ y, size_t n, F f) {
+template <typename T, typename F>
+__global__ void __launch_bounds__(256) k_binary(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ y, size_t n, F f) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const size_t n4 = n >> 2;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -34,26 +33,27 @@ __global__ void __launch_bounds__(256) k_binary(const float* __restrict__ a, con
     r.x = f(u.x, v.x); r.y = f(u.y, v.y); r.z = f(u.z, v.z); r.w = f(u.w, v.w);
     lb_st4(y + 4 * i, r);
   }
-  for (size_t i = (n4 << 2) + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] = f(a[i], b[i]);
+  for (size_t i = (n4 << 2) + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    lb_st1(y + i, f(lb_ld1(a + i), lb_ld1(b + i)));
 }
 
 // scalar fallbacks for unaligned views
-template <typename F>
-__global__ void k_unary_s(const float* __restrict__ x, float* __restrict__ y, size_t n, F f) {
+template <typename T, typename F>
+__global__ void k_unary_s(const T* __restrict__ x, T* __restrict__ y, size_t n, F f) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] = f(x[i]);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) lb_st1(y + i, f(lb_ld1(x + i)));
 }
-template <typename F>
-__global__ void k_binary_s(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y, size_t n, F f) {
+template <typename T, typename F>
+__global__ void k_binary_s(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ y, size_t n, F f) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] = f(a[i], b[i]);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) lb_st1(y + i, f(lb_ld1(a + i), lb_ld1(b + i)));
 }
 
-template <typename F>
-static int launch_unary(const float* x, float* y, size_t n, F f, lb_stream_t s) {
+template <typename T, typename F>
+static int launch_unary_t(const T* x, T* y, size_t n, F f, lb_stream_t s) {
   LB_REQUIRE(x && y);
   if (n == 0) return LB_OK;
-  if (lb_aligned16(x) && lb_aligned16(y)) {
+  if (lb_vec4_ok(x) && lb_vec4_ok(y)) {
     k_unary<<<lb_grid_1d((n + 3) / 4, 256), 256, 0, lb_s(s)>>>(x, y, n, f);
   } else {
     k_unary_s<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(x, y, n, f);
@@ -61,17 +61,25 @@ static int launch_unary(const float* x, float* y, size_t n, F f, lb_stream_t s) 
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
-template <typename F>
-static int launch_binary(const float* a, const float* b, float* y, size_t n, F f, lb_stream_t s) {
+template <typename T, typename F>
+static int launch_binary_t(const T* a, const T* b, T* y, size_t n, F f, lb_stream_t s) {
   LB_REQUIRE(a && b && y);
   if (n == 0) return LB_OK;
-  if (lb_aligned16(a) && lb_aligned16(b) && lb_aligned16(y)) {
+  if (lb_vec4_ok(a) && lb_vec4_ok(b) && lb_vec4_ok(y)) {
     k_binary<<<lb_grid_1d((n + 3) / 4, 256), 256, 0, lb_s(s)>>>(a, b, y, n, f);
   } else {
     k_binary_s<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(a, b, y, n, f);
   }
   LB_LAUNCH_CHECK();
   return LB_OK;
+}
+template <typename F>
+static int launch_unary(const void* x, void* y, size_t n, F f, int dtype, lb_stream_t s) {
+  LB_DISPATCH(dtype, T, return launch_unary_t(lb_cp<T>(x), lb_p<T>(y), n, f, s));
+}
+template <typename F>
+static int launch_binary(const void* a, const void* b, void* y, size_t n, F f, int dtype, lb_stream_t s) {
+  LB_DISPATCH(dtype, T, return launch_binary_t(lb_cp<T>(a), lb_cp<T>(b), lb_p<T>(y), n, f, s));
 }
 
 struct RootTanh4 { __device__ float operator()(float x) const { return lb_roottanh(x); } };
@@ -83,26 +91,31 @@ struct TanhB { __device__ float operator()(float y, float g) const { return g * 
 struct HingeF { __device__ float operator()(float x) const { return fmaxf(1.0f - x, 0.0f); } };
 struct HingeB { __device__ float operator()(float x, float g) const { return x < 1.0f ? -g : 0.0f; } };
 struct ScaleF { float f; __device__ float operator()(float x) const { return x * f; } };
+struct AddF { __device__ float operator()(float a, float b) const { return a + b; } };
 
-extern "C" int lb_roottanh_fwd(const float* x, float* y, size_t n, int growth, lb_stream_t s) {
+extern "C" int lb_roottanh_fwd(const void* x, void* y, size_t n, int growth, int dtype, lb_stream_t s) {
   LB_REQUIRE(growth >= 1);
-  if (growth == 4) return launch_unary(x, y, n, RootTanh4{}, s);
-  return launch_unary(x, y, n, RootTanhG{1.0f / growth}, s);
+  if (growth == 4) return launch_unary(x, y, n, RootTanh4{}, dtype, s);
+  return launch_unary(x, y, n, RootTanhG{1.0f / growth}, dtype, s);
 }
-extern "C" int lb_roottanh_bwd(const float* x, const float* g, float* dx, size_t n, int growth, lb_stream_t s) {
+extern "C" int lb_roottanh_bwd(const void* x, const void* g, void* dx, size_t n, int growth, int dtype, lb_stream_t s) {
   LB_REQUIRE(growth >= 1);
-  if (growth == 4) return launch_binary(x, g, dx, n, RootTanhBwd4{}, s);
-  return launch_binary(x, g, dx, n, RootTanhBwdG{1.0f / growth}, s);
+  if (growth == 4) return launch_binary(x, g, dx, n, RootTanhBwd4{}, dtype, s);
+  return launch_binary(x, g, dx, n, RootTanhBwdG{1.0f / growth}, dtype, s);
 }
-extern "C" int lb_tanh_fwd(const float* x, float* y, size_t n, lb_stream_t s) { return launch_unary(x, y, n, TanhF{}, s); }
-extern "C" int lb_tanh_bwd(const float* y, const float* g, float* dx, size_t n, lb_stream_t s) {
-  return launch_binary(y, g, dx, n, TanhB{}, s);
+extern "C" int lb_tanh_fwd(const void* x, void* y, size_t n, int dtype, lb_stream_t s) { return launch_unary(x, y, n, TanhF{}, dtype, s); }
+extern "C" int lb_tanh_bwd(const void* y, const void* g, void* dx, size_t n, int dtype, lb_stream_t s) {
+  return launch_binary(y, g, dx, n, TanhB{}, dtype, s);
 }
-extern "C" int lb_hinge_fwd(const float* x, float* y, size_t n, lb_stream_t s) { return launch_unary(x, y, n, HingeF{}, s); }
+extern "C" int lb_hinge_fwd(const float* x, float* y, size_t n, lb_stream_t s) { return launch_unary(x, y, n, HingeF{}, LB_F32, s); }
 extern "C" int lb_hinge_bwd(const float* x, const float* g, float* dx, size_t n, lb_stream_t s) {
-  return launch_binary(x, g, dx, n, HingeB{}, s);
+  return launch_binary(x, g, dx, n, HingeB{}, LB_F32, s);
 }
-extern "C" int lb_scale(float* x, size_t n, float factor, lb_stream_t s) { return launch_unary(x, x, n, ScaleF{factor}, s); }
+extern "C" int lb_scale(float* x, size_t n, float factor, lb_stream_t s) { return launch_unary(x, x, n, ScaleF{factor}, LB_F32, s); }
+// y = a + b: the sum of the gradients that reach a tensor consumed by two branches (skip path + gated branch of a block)
+extern "C" int lb_add(const void* a, const void* b, void* y, size_t n, int dtype, lb_stream_t s) {
+  return launch_binary(a, b, y, n, AddF{}, dtype, s);
+}
 
 __global__ void k_fill(float* __restrict__ x, size_t n, float v) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -118,10 +131,11 @@ extern "C" int lb_fill(float* x, size_t n, float value, lb_stream_t s) {
 
 // ------------------------------------------------------------------------------------------
 // gated residual (libs/merge.py:19-39) on channels-last [B][P][C]
-// thread shape: tc channel lanes x tp pixel lanes; CTA = (batch b, pixel chunk)
+// y: full tensor (storage T) or a per-(b,c) gate [B][C] (storage T) broadcast over pixels
 // ------------------------------------------------------------------------------------------
-__global__ void k_gate_fwd(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ gamma,
-                           float* __restrict__ out, size_t n, int pc, int channels, int y_bcast) {
+template <typename T>
+__global__ void k_gate_fwd(const T* __restrict__ x, const T* __restrict__ y, const float* __restrict__ gamma,
+                           T* __restrict__ out, size_t n, int pc, int channels, int y_bcast) {
   const float gm = __ldg(gamma);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   if (!y_bcast) {
@@ -136,22 +150,23 @@ __global__ void k_gate_fwd(const float* __restrict__ x, const float* __restrict_
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
       const size_t b = i / (size_t)pc;
       const int c = (int)(i % (size_t)channels);
-      out[i] = fmaf(gm, __ldg(y + b * channels + c), 1.0f) * x[i];
+      lb_st1(out + i, fmaf(gm, lb_ld1(y + b * channels + c), 1.0f) * lb_ld1(x + i));
     }
   }
 }
-__global__ void k_gate_fwd_s(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ gamma,
-                             float* __restrict__ out, size_t n) {
+template <typename T>
+__global__ void k_gate_fwd_s(const T* __restrict__ x, const T* __restrict__ y, const float* __restrict__ gamma,
+                             T* __restrict__ out, size_t n) {
   const float gm = __ldg(gamma);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = fmaf(gm, y[i], 1.0f) * x[i];
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    lb_st1(out + i, fmaf(gm, lb_ld1(y + i), 1.0f) * lb_ld1(x + i));
 }
 
-extern "C" int lb_gate_fwd(const float* x, const float* y, const float* gamma, float* out, int batch, int pixels,
-                           int channels, int y_bcast, lb_stream_t s) {
-  LB_REQUIRE(x && y && gamma && out && batch > 0 && pixels > 0 && channels > 0);
+template <typename T>
+static int gate_fwd_t(const T* x, const T* y, const float* gamma, T* out, int batch, int pixels, int channels, int y_bcast, lb_stream_t s) {
   const size_t n = (size_t)batch * pixels * channels;
-  if (!y_bcast && !((n & 3) == 0 && lb_aligned16(x) && lb_aligned16(y) && lb_aligned16(out))) {
+  if (!y_bcast && !((n & 3) == 0 && lb_vec4_ok(x) && lb_vec4_ok(y) && lb_vec4_ok(out))) {
     k_gate_fwd_s<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(x, y, gamma, out, n);
   } else {
     k_gate_fwd<<<lb_grid_1d(y_bcast ? n : n / 4, 256), 256, 0, lb_s(s)>>>(x, y, gamma, out, n, pixels * channels, channels, y_bcast);
@@ -159,11 +174,17 @@ extern "C" int lb_gate_fwd(const float* x, const float* y, const float* gamma, f
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
+extern "C" int lb_gate_fwd(const void* x, const void* y, const float* gamma, void* out, int batch, int pixels,
+                           int channels, int y_bcast, int dtype, lb_stream_t s) {
+  LB_REQUIRE(x && y && gamma && out && batch > 0 && pixels > 0 && channels > 0);
+  LB_DISPATCH(dtype, T, return gate_fwd_t(lb_cp<T>(x), lb_cp<T>(y), gamma, lb_p<T>(out), batch, pixels, channels, y_bcast, s));
+}
 
-// Same gate, also accumulating (sum, sum of squares) of the OUTPUT in fp64: every gate output feeds a whole-tensor norm
-// (block.py:46-51), whose statistics pass would otherwise re-read the tensor just written.
-__global__ void __launch_bounds__(256) k_gate_fwd_stats(const float* __restrict__ x, const float* __restrict__ y,
-                                                       const float* __restrict__ gamma, float* __restrict__ out, int n4,
+// Same gate, also accumulating (sum, sum of squares) of the OUTPUT (as stored, i.e. after rounding to T) in fp64: every gate
+// output feeds a whole-tensor norm (block.py:46-51), whose statistics pass would otherwise re-read the tensor just written.
+template <typename T>
+__global__ void __launch_bounds__(256) k_gate_fwd_stats(const T* __restrict__ x, const T* __restrict__ y,
+                                                       const float* __restrict__ gamma, T* __restrict__ out, int n4,
                                                        LbFastDiv d_pc4, LbFastDiv d_c4, int channels, int y_bcast,
                                                        double* __restrict__ sums, double* __restrict__ work) {
   __shared__ double scratch[32];
@@ -185,6 +206,10 @@ __global__ void __launch_bounds__(256) k_gate_fwd_stats(const float* __restrict_
     r.x = fmaf(gm, b.x, 1.0f) * a.x; r.y = fmaf(gm, b.y, 1.0f) * a.y;
     r.z = fmaf(gm, b.z, 1.0f) * a.z; r.w = fmaf(gm, b.w, 1.0f) * a.w;
     lb_st4(out + 4 * (size_t)i, r);
+    if (sizeof(T) == 2) {                       // statistics of what the norm will read back
+      r.x = __bfloat162float(__float2bfloat16(r.x)); r.y = __bfloat162float(__float2bfloat16(r.y));
+      r.z = __bfloat162float(__float2bfloat16(r.z)); r.w = __bfloat162float(__float2bfloat16(r.w));
+    }
     s1 += (double)((r.x + r.y) + (r.z + r.w));
     s2 += (double)(fmaf(r.x, r.x, r.y * r.y) + fmaf(r.z, r.z, r.w * r.w));
   }
@@ -193,23 +218,27 @@ __global__ void __launch_bounds__(256) k_gate_fwd_stats(const float* __restrict_
   lb_grid_sum2_ordered(s1, s2, work, sums, scratch);
 }
 // sums[2] (fp64) = (sum out, sum out^2), reduced in a fixed order (work: see lb_norm_stats).  Needs channels % 4 == 0 and
-// 16-byte aligned pointers (LB_EALIGN otherwise: use lb_gate_fwd + lb_norm_stats).
-extern "C" int lb_gate_fwd_stats(const float* x, const float* y, const float* gamma, float* out, double* sums, double* work,
-                                 int batch, int pixels, int channels, int y_bcast, lb_stream_t s) {
+// aligned pointers (LB_EALIGN otherwise: use lb_gate_fwd + lb_norm_stats).
+extern "C" int lb_gate_fwd_stats(const void* x, const void* y, const float* gamma, void* out, double* sums, double* work,
+                                 int batch, int pixels, int channels, int y_bcast, int dtype, lb_stream_t s) {
   LB_REQUIRE(x && y && gamma && out && sums && work && batch > 0 && pixels > 0 && channels > 0);
   const size_t n = (size_t)batch * pixels * channels;
-  if ((channels & 3) || n / 4 >= ((size_t)1 << 31) - ((size_t)1 << 24) || !lb_aligned16(x) || !lb_aligned16(y) || !lb_aligned16(out))
-    return LB_EALIGN;
-  k_gate_fwd_stats<<<lb_grid_1d(n / 4, 256, 4), 256, 0, lb_s(s)>>>(x, y, gamma, out, (int)(n / 4),
-                                                                  lb_make_fastdiv((uint32_t)((size_t)pixels * channels / 4)),
-                                                                  lb_make_fastdiv(channels / 4), channels, y_bcast, sums, work);
+  if ((channels & 3) || n / 4 >= ((size_t)1 << 31) - ((size_t)1 << 24)) return LB_EALIGN;
+  LB_DISPATCH(dtype, T, {
+    if (!lb_vec4_ok(lb_cp<T>(x)) || !lb_vec4_ok(lb_cp<T>(y)) || !lb_vec4_ok(lb_cp<T>(out))) return LB_EALIGN;
+    k_gate_fwd_stats<<<lb_grid_1d(n / 4, 256, 4), 256, 0, lb_s(s)>>>(lb_cp<T>(x), lb_cp<T>(y), gamma, lb_p<T>(out), (int)(n / 4),
+                                                                    lb_make_fastdiv((uint32_t)((size_t)pixels * channels / 4)),
+                                                                    lb_make_fastdiv(channels / 4), channels, y_bcast, sums, work);
+  });
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
 
-// backward: CTA handles batch b = blockIdx.y, pixel chunk blockIdx.x; thread (cl, pl).
-__global__ void k_gate_bwd(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ gamma,
-                           const float* __restrict__ g, float* __restrict__ dx, float* __restrict__ dy,
+// backward: CTA handles batch b = blockIdx.y, pixel chunk blockIdx.x; thread (cl, pl).  dy of the broadcast gate is fp32
+// [B][C] (atomically accumulated over pixel chunks; the caller zeroes it and converts).
+template <typename T>
+__global__ void k_gate_bwd(const T* __restrict__ x, const T* __restrict__ y, const float* __restrict__ gamma,
+                           const T* __restrict__ g, T* __restrict__ dx, T* __restrict__ dy, float* __restrict__ dy_bcast,
                            float* __restrict__ dgamma, int pixels, int channels, int chunk, int tc, int tp,
                            int y_bcast, int strict) {
   __shared__ float scratch[32];
@@ -222,18 +251,18 @@ __global__ void k_gate_bwd(const float* __restrict__ x, const float* __restrict_
   float acc_gamma = 0.0f;
   for (int c = (threadIdx.x < tc * tp ? cl : channels); c < channels; c += tc) {
     float acc_dy = 0.0f;
-    const float yb = y_bcast ? __ldg(y + (size_t)b * channels + c) : 0.0f;
+    const float yb = y_bcast ? lb_ld1(y + (size_t)b * channels + c) : 0.0f;
 #pragma unroll 4
     for (int p = p0 + pl; p < p1; p += tp) {
       const size_t i = base + (size_t)p * channels + c;
-      const float xv = x[i], gv = g[i];
-      const float yv = y_bcast ? yb : y[i];
+      const float xv = lb_ld1(x + i), gv = lb_ld1(g + i);
+      const float yv = y_bcast ? yb : lb_ld1(y + i);
       const float xg = xv * gv;
-      dx[i] = fmaf(gm, yv, 1.0f) * gv;
-      if (y_bcast) acc_dy += xg; else dy[i] = xg * gm;
+      lb_st1(dx + i, fmaf(gm, yv, 1.0f) * gv);
+      if (y_bcast) acc_dy += xg; else lb_st1(dy + i, xg * gm);
       acc_gamma = fmaf(xg, strict ? xv : yv, acc_gamma);
     }
-    if (y_bcast) atomicAdd(dy + (size_t)b * channels + c, acc_dy * gm);
+    if (y_bcast) atomicAdd(dy_bcast + (size_t)b * channels + c, acc_dy * gm);
   }
   if (dgamma) {
     const float tot = lb_block_sum(acc_gamma, scratch);
@@ -241,10 +270,11 @@ __global__ void k_gate_bwd(const float* __restrict__ x, const float* __restrict_
   }
 }
 
-// full-shape gate (y has the shape of x): everything is elementwise except d-gamma, so the kernel streams float4s and
+// full-shape gate (y has the shape of x): everything is elementwise except d-gamma, so the kernel streams 4-vectors and
 // reduces one scalar per CTA
-__global__ void __launch_bounds__(256) k_gate_bwd4(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ gamma,
-                                                  const float* __restrict__ g, float* __restrict__ dx, float* __restrict__ dy,
+template <typename T>
+__global__ void __launch_bounds__(256) k_gate_bwd4(const T* __restrict__ x, const T* __restrict__ y, const float* __restrict__ gamma,
+                                                  const T* __restrict__ g, T* __restrict__ dx, T* __restrict__ dy,
                                                   float* __restrict__ dgamma, size_t n4, int strict) {
   __shared__ float scratch[32];
   const float gm = __ldg(gamma);
@@ -268,12 +298,11 @@ __global__ void __launch_bounds__(256) k_gate_bwd4(const float* __restrict__ x, 
   }
 }
 
-extern "C" int lb_gate_bwd(const float* x, const float* y, const float* gamma, const float* g, float* dx, float* dy,
-                           float* dgamma, int batch, int pixels, int channels, int y_bcast, int strict_reference,
-                           lb_stream_t s) {
-  LB_REQUIRE(x && y && gamma && g && dx && dy && batch > 0 && pixels > 0 && channels > 0);
+template <typename T>
+static int gate_bwd_t(const T* x, const T* y, const float* gamma, const T* g, T* dx, T* dy, float* dy_bcast, float* dgamma, int batch,
+                      int pixels, int channels, int y_bcast, int strict_reference, lb_stream_t s) {
   const size_t n = (size_t)batch * pixels * channels;
-  if (!y_bcast && !(n & 3) && lb_aligned16(x) && lb_aligned16(y) && lb_aligned16(g) && lb_aligned16(dx) && lb_aligned16(dy)) {
+  if (!y_bcast && !(n & 3) && lb_vec4_ok(x) && lb_vec4_ok(y) && lb_vec4_ok(g) && lb_vec4_ok(dx) && lb_vec4_ok(dy)) {
     k_gate_bwd4<<<lb_grid_1d(n / 4, 256, 4), 256, 0, lb_s(s)>>>(x, y, gamma, g, dx, dy, dgamma, n / 4, strict_reference);
     LB_LAUNCH_CHECK();
     return LB_OK;
@@ -285,10 +314,19 @@ extern "C" int lb_gate_bwd(const float* x, const float* y, const float* gamma, c
   if (chunk < sh.tp) chunk = sh.tp;
   chunks = (pixels + chunk - 1) / chunk;
   dim3 grid(chunks, batch);
-  k_gate_bwd<<<grid, sh.threads, 0, lb_s(s)>>>(x, y, gamma, g, dx, dy, dgamma, pixels, channels, chunk, sh.tc, sh.tp,
+  k_gate_bwd<<<grid, sh.threads, 0, lb_s(s)>>>(x, y, gamma, g, dx, dy, dy_bcast, dgamma, pixels, channels, chunk, sh.tc, sh.tp,
                                                   y_bcast, strict_reference);
   LB_LAUNCH_CHECK();
   return LB_OK;
+}
+// dy: storage T, shape of x (y_bcast = 0);  dy_bcast: fp32 [B][C], zeroed by the caller (y_bcast = 1)
+extern "C" int lb_gate_bwd(const void* x, const void* y, const float* gamma, const void* g, void* dx, void* dy, float* dy_bcast,
+                           float* dgamma, int batch, int pixels, int channels, int y_bcast, int strict_reference, int dtype,
+                           lb_stream_t s) {
+  LB_REQUIRE(x && y && gamma && g && dx && batch > 0 && pixels > 0 && channels > 0);
+  LB_REQUIRE(y_bcast ? dy_bcast != nullptr : dy != nullptr);
+  LB_DISPATCH(dtype, T, return gate_bwd_t(lb_cp<T>(x), lb_cp<T>(y), gamma, lb_cp<T>(g), lb_p<T>(dx), lb_p<T>(dy), dy_bcast, dgamma,
+                                          batch, pixels, channels, y_bcast, strict_reference, s));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -347,63 +385,73 @@ extern "C" int lb_nadam_step(float* param, const float* grad, float* exp_avg, fl
 // ------------------------------------------------------------------------------------------
 // strided row copy (channel concat / slice) and layout changes
 // ------------------------------------------------------------------------------------------
-__global__ void k_copy_rows(const float* __restrict__ src, int ld_src, float* __restrict__ dst, int ld_dst, size_t rows,
+template <typename TI, typename TO>
+__global__ void k_copy_rows(const TI* __restrict__ src, int ld_src, TO* __restrict__ dst, int ld_dst, size_t rows,
                             int cols, int accumulate) {
   const size_t n = rows * (size_t)cols;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const size_t r = i / cols;
     const int c = (int)(i % cols);
-    const float v = src[r * ld_src + c];
-    float* d = dst + r * ld_dst + c;
-    *d = accumulate ? *d + v : v;
+    const float v = lb_ld1(src + r * ld_src + c);
+    TO* d = dst + r * ld_dst + c;
+    lb_st1(d, accumulate ? lb_ld1(d) + v : v);
   }
 }
-// 16-byte version (cols, both leading dimensions and both pointers multiples of 4 floats), 32-bit multiply-shift decode
-__global__ void __launch_bounds__(256) k_copy_rows4(const float* __restrict__ src, int ld_src, float* __restrict__ dst, int ld_dst,
+// 4-element version (cols, both leading dimensions multiples of 4, aligned pointers), 32-bit multiply-shift decode
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) k_copy_rows4(const TI* __restrict__ src, int ld_src, TO* __restrict__ dst, int ld_dst,
                                                    int n4, LbFastDiv d_c4, int accumulate) {
   const int stride = gridDim.x * blockDim.x;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     int r, c4;
     lb_fast_divmod(d_c4, i, r, c4);
     float4 v = lb_ld4(src + (size_t)r * ld_src + 4 * c4);
-    float* d = dst + (size_t)r * ld_dst + 4 * c4;
+    TO* d = dst + (size_t)r * ld_dst + 4 * c4;
     if (accumulate) {
-      const float4 o = *reinterpret_cast<const float4*>(d);
+      const float4 o = lb_ld4(d);
       v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
     }
     lb_st4(d, v);
   }
 }
-extern "C" int lb_copy_rows(const float* src, int ld_src, float* dst, int ld_dst, int64_t rows, int cols, int accumulate,
-                            lb_stream_t s) {
-  LB_REQUIRE(src && dst && rows >= 0 && cols > 0 && ld_src >= cols && ld_dst >= cols);
-  if (rows == 0) return LB_OK;
+template <typename TI, typename TO>
+static int copy_rows_t(const TI* src, int ld_src, TO* dst, int ld_dst, int64_t rows, int cols, int accumulate, lb_stream_t s) {
   const size_t n = (size_t)rows * cols;
-  if (!(cols & 3) && !(ld_src & 3) && !(ld_dst & 3) && lb_aligned16(src) && lb_aligned16(dst) && n / 4 < ((size_t)1 << 31) - ((size_t)1 << 24))
+  if (!(cols & 3) && !(ld_src & 3) && !(ld_dst & 3) && lb_vec4_ok(src) && lb_vec4_ok(dst) && n / 4 < ((size_t)1 << 31) - ((size_t)1 << 24))
     k_copy_rows4<<<lb_grid_1d(n / 4, 256), 256, 0, lb_s(s)>>>(src, ld_src, dst, ld_dst, (int)(n / 4), lb_make_fastdiv(cols / 4), accumulate);
   else
     k_copy_rows<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(src, ld_src, dst, ld_dst, (size_t)rows, cols, accumulate);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
+// src / dst may differ in storage type (a concat of a 3-channel fp32 image into a wide bf16 tensor, and its backward)
+extern "C" int lb_copy_rows(const void* src, int ld_src, void* dst, int ld_dst, int64_t rows, int cols, int accumulate, int src_dtype,
+                            int dst_dtype, lb_stream_t s) {
+  LB_REQUIRE(src && dst && rows >= 0 && cols > 0 && ld_src >= cols && ld_dst >= cols);
+  if (rows == 0) return LB_OK;
+  LB_DISPATCH(src_dtype, TI, LB_DISPATCH(dst_dtype, TO, return copy_rows_t(lb_cp<TI>(src), ld_src, lb_p<TO>(dst), ld_dst, rows, cols,
+                                                                          accumulate, s)));
+}
 
-// [B][C][HW] <-> [B][HW][C] through a 32x33 shared tile (coalesced on both sides)
-__global__ void k_transpose_batched(const float* __restrict__ x, float* __restrict__ y, int rows, int cols) {
+// [B][C][HW] <-> [B][HW][C] through a 32x33 shared tile (coalesced on both sides); TI / TO: storage of source / destination
+template <typename TI, typename TO>
+__global__ void k_transpose_batched(const TI* __restrict__ x, TO* __restrict__ y, int rows, int cols) {
   __shared__ float tile[32][33];
   const size_t base = (size_t)blockIdx.z * rows * cols;
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
     const int r = r0 + j, c = c0 + threadIdx.x;
-    if (r < rows && c < cols) tile[j][threadIdx.x] = x[base + (size_t)r * cols + c];
+    if (r < rows && c < cols) tile[j][threadIdx.x] = lb_ld1(x + base + (size_t)r * cols + c);
   }
   __syncthreads();
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
     const int c = c0 + j, r = r0 + threadIdx.x;
-    if (r < rows && c < cols) y[base + (size_t)c * rows + r] = tile[threadIdx.x][j];
+    if (r < rows && c < cols) lb_st1(y + base + (size_t)c * rows + r, tile[threadIdx.x][j]);
   }
 }
-static int transpose_batched(const float* x, float* y, int batch, int rows, int cols, lb_stream_t s) {
+template <typename TI, typename TO>
+static int transpose_batched(const TI* x, TO* y, int batch, int rows, int cols, lb_stream_t s) {
   LB_REQUIRE(x && y && batch > 0 && rows > 0 && cols > 0 && batch <= 65535);
   dim3 grid((cols + 31) / 32, (rows + 31) / 32, batch);
   LB_REQUIRE(grid.y <= 65535);
@@ -436,11 +484,15 @@ static int layout_small_c(const float* x, float* y, int batch, int c, int hw, bo
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
-extern "C" int lb_nchw_to_nhwc(const float* x, float* y, int batch, int c, int hw, lb_stream_t s) {
-  if (c <= 8 && (size_t)batch * hw < ((size_t)1 << 31) - ((size_t)1 << 24)) return layout_small_c(x, y, batch, c, hw, true, s);
-  return transpose_batched(x, y, batch, c, hw, s);
+// x: fp32 NCHW (what the reference's loaders and callers hand in); y: channels-last with storage `out_dtype`
+extern "C" int lb_nchw_to_nhwc(const float* x, void* y, int batch, int c, int hw, int out_dtype, lb_stream_t s) {
+  if (out_dtype == LB_F32 && c <= 8 && (size_t)batch * hw < ((size_t)1 << 31) - ((size_t)1 << 24))
+    return layout_small_c(x, lb_p<float>(y), batch, c, hw, true, s);
+  LB_DISPATCH(out_dtype, T, return transpose_batched(x, lb_p<T>(y), batch, c, hw, s));
 }
-extern "C" int lb_nhwc_to_nchw(const float* x, float* y, int batch, int c, int hw, lb_stream_t s) {
-  if (c <= 8 && (size_t)batch * hw < ((size_t)1 << 31) - ((size_t)1 << 24)) return layout_small_c(x, y, batch, c, hw, false, s);
-  return transpose_batched(x, y, batch, hw, c, s);
+// x: channels-last with storage `in_dtype`; y: fp32 NCHW
+extern "C" int lb_nhwc_to_nchw(const void* x, float* y, int batch, int c, int hw, int in_dtype, lb_stream_t s) {
+  if (in_dtype == LB_F32 && c <= 8 && (size_t)batch * hw < ((size_t)1 << 31) - ((size_t)1 << 24))
+    return layout_small_c(lb_cp<float>(x), y, batch, c, hw, false, s);
+  LB_DISPATCH(in_dtype, T, return transpose_batched(lb_cp<T>(x), y, batch, hw, c, s));
 }

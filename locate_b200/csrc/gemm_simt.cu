@@ -345,24 +345,25 @@ extern "C" int lb_conv_wgrad(const float* gathered, const float* dense, float* d
 }
 
 // ---- column sums (bias gradients) ---------------------------------------------------------------
-__global__ void k_colsum(const float* __restrict__ x, long long rows, int cols, int ld, float* __restrict__ out, int chunk, int tc, int tp) {
+template <typename T>
+__global__ void k_colsum(const T* __restrict__ x, long long rows, int cols, int ld, float* __restrict__ out, int chunk, int tc, int tp) {
   if (threadIdx.x >= tc * tp) return;
   const int cl = threadIdx.x % tc, pl = threadIdx.x / tc;
   const long long r0 = (long long)blockIdx.x * chunk, r1 = min(rows, r0 + chunk);
   for (int c = cl; c < cols; c += tc) {
     float acc = 0.0f;
-    for (long long r = r0 + pl; r < r1; r += tp) acc += x[r * ld + c];
+    for (long long r = r0 + pl; r < r1; r += tp) acc += lb_ld1(x + r * ld + c);
     atomicAdd(out + c, acc);
   }
 }
-extern "C" int lb_colsum(const float* x, int64_t rows, int cols, int ld, float* out, lb_stream_t s) {
+extern "C" int lb_colsum(const void* x, int64_t rows, int cols, int ld, float* out, int dtype, lb_stream_t s) {
   LB_REQUIRE(x && out && rows > 0 && cols > 0 && ld >= cols);
   const LbColShape sh = lb_col_shape(cols);
   long long chunks = LB_SMS * 4;
   long long chunk = (rows + chunks - 1) / chunks;
   if (chunk < sh.tp) chunk = sh.tp;
   chunks = (rows + chunk - 1) / chunk;
-  k_colsum<<<(unsigned)chunks, sh.threads, 0, lb_s(s)>>>(x, rows, cols, ld, out, (int)chunk, sh.tc, sh.tp);
+  LB_DISPATCH(dtype, T, k_colsum<<<(unsigned)chunks, sh.threads, 0, lb_s(s)>>>(lb_cp<T>(x), rows, cols, ld, out, (int)chunk, sh.tc, sh.tp));
   LB_LAUNCH_CHECK();
   return LB_OK;
 }

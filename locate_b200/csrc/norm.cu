@@ -5,7 +5,8 @@
 #include <cuda_bf16.h>
 #include "common.cuh"
 
-__global__ void __launch_bounds__(256) k_norm_stats(const float* __restrict__ x, size_t n, double* __restrict__ sums,
+template <typename T>
+__global__ void __launch_bounds__(256) k_norm_stats(const T* __restrict__ x, size_t n, double* __restrict__ sums,
                                                    double* __restrict__ work, int vec) {
   __shared__ double scratch[32];
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -18,12 +19,12 @@ __global__ void __launch_bounds__(256) k_norm_stats(const float* __restrict__ x,
       s2 += (double)(fmaf(v.x, v.x, v.y * v.y) + fmaf(v.z, v.z, v.w * v.w));
     }
     for (size_t i = (n4 << 2) + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-      const float v = x[i];
+      const float v = lb_ld1(x + i);
       s1 += v; s2 += (double)v * v;
     }
   } else {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-      const float v = x[i];
+      const float v = lb_ld1(x + i);
       s1 += v; s2 += (double)v * v;
     }
   }
@@ -34,9 +35,10 @@ __global__ void __launch_bounds__(256) k_norm_stats(const float* __restrict__ x,
 
 extern "C" size_t lb_stat_work_doubles(void) { return LB_STAT_WORK_DOUBLES; }
 
-extern "C" int lb_norm_stats(const float* x, size_t n, double* sums, double* work, lb_stream_t s) {
+extern "C" int lb_norm_stats(const void* x, size_t n, double* sums, double* work, int dtype, lb_stream_t s) {
   LB_REQUIRE(x && sums && work && n > 0);
-  k_norm_stats<<<lb_grid_1d((n + 3) / 4, 256, 4), 256, 0, lb_s(s)>>>(x, n, sums, work, lb_aligned16(x) ? 1 : 0);
+  LB_DISPATCH(dtype, T, k_norm_stats<<<lb_grid_1d((n + 3) / 4, 256, 4), 256, 0, lb_s(s)>>>(lb_cp<T>(x), n, sums, work,
+                                                                                          lb_vec4_ok(lb_cp<T>(x)) ? 1 : 0));
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
@@ -58,35 +60,12 @@ extern "C" int lb_norm_finalize(const double* sums, double n_total, float* stats
   return LB_OK;
 }
 
-// y = (x - mean) * gain[b?,c] * rstd + bias[c]; one thread = 4 consecutive channels of one pixel
-__global__ void __launch_bounds__(256) k_norm_apply4(const float* __restrict__ x, const float* __restrict__ stats,
+// y = (x - mean) * gain[b?,c] * rstd + bias[c]; one thread = 4 consecutive channels of one pixel.  Optionally also (or
+// only) act = RootTanh(y): the operand of the convolution that follows (conv.py:23-24), produced in the same pass.
+template <typename T, bool kAct>
+__global__ void __launch_bounds__(256) k_norm_apply4(const T* __restrict__ x, const float* __restrict__ stats,
                                                     const float* __restrict__ gain, int gain_bs, const float* __restrict__ bias,
-                                                    float* __restrict__ y, size_t n4, LbFastDiv d_pc4, LbFastDiv d_c4) {
-  const float mean = __ldg(stats), rstd = __ldg(stats + 2);
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    int b, rem, q, c;
-    lb_fast_divmod(d_pc4, (int)i, b, rem);      // n4 < 2^31 (checked by the host)
-    lb_fast_divmod(d_c4, rem, q, c);
-    c *= 4;
-    const float4 v = lb_ld4(x + 4 * i);
-    const float4 gn = lb_ld4(gain + (size_t)b * gain_bs + c);
-    const float4 bs = lb_ld4(bias + c);
-    float4 r;
-    r.x = fmaf((v.x - mean) * rstd, gn.x, bs.x);
-    r.y = fmaf((v.y - mean) * rstd, gn.y, bs.y);
-    r.z = fmaf((v.z - mean) * rstd, gn.z, bs.z);
-    r.w = fmaf((v.w - mean) * rstd, gn.w, bs.w);
-    lb_st4(y + 4 * i, r);
-  }
-}
-// same, also (or only) emitting the bf16 GEMM operand of the consumer: y16 = bf16(RootTanh?(y)).  y may be NULL when
-// nothing reads the fp32 result (a conv follows directly and its backward needs only the bf16 operand).
-template <bool kAct>
-__global__ void __launch_bounds__(256) k_norm_apply4_ex(const float* __restrict__ x, const float* __restrict__ stats,
-                                                       const float* __restrict__ gain, int gain_bs, const float* __restrict__ bias,
-                                                       float* __restrict__ y, __nv_bfloat16* __restrict__ y16, size_t n4, LbFastDiv d_pc4,
-                                                       LbFastDiv d_c4) {
+                                                    T* __restrict__ y, T* __restrict__ act, size_t n4, LbFastDiv d_pc4, LbFastDiv d_c4) {
   const float mean = __ldg(stats), rstd = __ldg(stats + 2);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -103,66 +82,76 @@ __global__ void __launch_bounds__(256) k_norm_apply4_ex(const float* __restrict_
     r.z = fmaf((v.z - mean) * rstd, gn.z, bs.z);
     r.w = fmaf((v.w - mean) * rstd, gn.w, bs.w);
     if (y) lb_st4(y + 4 * i, r);
-    if (kAct) { r.x = lb_roottanh(r.x); r.y = lb_roottanh(r.y); r.z = lb_roottanh(r.z); r.w = lb_roottanh(r.w); }
-    __nv_bfloat162 lo = __floats2bfloat162_rn(r.x, r.y), hi = __floats2bfloat162_rn(r.z, r.w);
-    uint2 pk;
-    pk.x = *reinterpret_cast<uint32_t*>(&lo);
-    pk.y = *reinterpret_cast<uint32_t*>(&hi);
-    *reinterpret_cast<uint2*>(y16 + 4 * i) = pk;
+    if (kAct) {
+      if (sizeof(T) == 2) {                     // the backward evaluates RootTanh' at the STORED (rounded) pre-activation
+        r.x = __bfloat162float(__float2bfloat16(r.x)); r.y = __bfloat162float(__float2bfloat16(r.y));
+        r.z = __bfloat162float(__float2bfloat16(r.z)); r.w = __bfloat162float(__float2bfloat16(r.w));
+      }
+      r.x = lb_roottanh(r.x); r.y = lb_roottanh(r.y); r.z = lb_roottanh(r.z); r.w = lb_roottanh(r.w);
+      lb_st4(act + 4 * i, r);
+    }
   }
 }
-__global__ void __launch_bounds__(256) k_norm_apply1(const float* __restrict__ x, const float* __restrict__ stats,
+template <typename T>
+__global__ void __launch_bounds__(256) k_norm_apply1(const T* __restrict__ x, const float* __restrict__ stats,
                                                     const float* __restrict__ gain, int gain_bs, const float* __restrict__ bias,
-                                                    float* __restrict__ y, size_t n, int pc, int channels) {
+                                                    T* __restrict__ y, size_t n, int pc, int channels) {
   const float mean = __ldg(stats), rstd = __ldg(stats + 2);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const size_t b = i / (size_t)pc;
     const int c = (int)(i % (size_t)channels);
-    y[i] = fmaf((x[i] - mean) * rstd, __ldg(gain + b * gain_bs + c), __ldg(bias + c));
+    lb_st1(y + i, fmaf((lb_ld1(x + i) - mean) * rstd, __ldg(gain + b * gain_bs + c), __ldg(bias + c)));
   }
 }
 
-extern "C" int lb_norm_apply(const float* x, const float* stats, const float* gain, int gain_batch_stride, const float* bias,
-                             float* y, int batch, int pixels, int channels, lb_stream_t s) {
-  LB_REQUIRE(x && stats && gain && bias && y && batch > 0 && pixels > 0 && channels > 0);
-  LB_REQUIRE(gain_batch_stride == 0 || gain_batch_stride == channels);
+template <typename T>
+static int norm_apply_t(const T* x, const float* stats, const float* gain, int gbs, const float* bias, T* y, int batch, int pixels,
+                        int channels, lb_stream_t s) {
   const size_t n = (size_t)batch * pixels * channels;
-  if ((channels & 3) == 0 && n / 4 < ((size_t)1 << 31) - ((size_t)1 << 24) && lb_aligned16(x) && lb_aligned16(y) && lb_aligned16(gain) &&
+  if ((channels & 3) == 0 && n / 4 < ((size_t)1 << 31) - ((size_t)1 << 24) && lb_vec4_ok(x) && lb_vec4_ok(y) && lb_aligned16(gain) &&
       lb_aligned16(bias)) {
-    k_norm_apply4<<<lb_grid_1d(n / 4, 256), 256, 0, lb_s(s)>>>(x, stats, gain, gain_batch_stride, bias, y, n / 4,
-                                                              lb_make_fastdiv((uint32_t)((size_t)pixels * channels / 4)),
-                                                              lb_make_fastdiv(channels / 4));
-  } else {
-    k_norm_apply1<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(x, stats, gain, gain_batch_stride, bias, y, n, pixels * channels, channels);
-  }
-  LB_LAUNCH_CHECK();
-  return LB_OK;
-}
-
-extern "C" int lb_norm_apply_ex(const float* x, const float* stats, const float* gain, int gain_batch_stride, const float* bias,
-                                float* y, void* y16, int act16, int batch, int pixels, int channels, lb_stream_t s) {
-  LB_REQUIRE(x && stats && gain && bias && y16 && batch > 0 && pixels > 0 && channels > 0);
-  LB_REQUIRE(gain_batch_stride == 0 || gain_batch_stride == channels);
-  const size_t n = (size_t)batch * pixels * channels;
-  if ((channels & 3) || n / 4 >= ((size_t)1 << 31) - ((size_t)1 << 24) || !lb_aligned16(x) || (y && !lb_aligned16(y)) ||
-      !lb_aligned16(gain) || !lb_aligned16(bias) || (reinterpret_cast<uintptr_t>(y16) & 7))
-    return LB_EALIGN;
-  __nv_bfloat16* o16 = reinterpret_cast<__nv_bfloat16*>(y16);
-  if (act16)
-    k_norm_apply4_ex<true><<<lb_grid_1d(n / 4, 256), 256, 0, lb_s(s)>>>(x, stats, gain, gain_batch_stride, bias, y, o16, n / 4,
-                                                                       lb_make_fastdiv((uint32_t)((size_t)pixels * channels / 4)),
-                                                                       lb_make_fastdiv(channels / 4));
-  else
-    k_norm_apply4_ex<false><<<lb_grid_1d(n / 4, 256), 256, 0, lb_s(s)>>>(x, stats, gain, gain_batch_stride, bias, y, o16, n / 4,
+    k_norm_apply4<T, false><<<lb_grid_1d(n / 4, 256), 256, 0, lb_s(s)>>>(x, stats, gain, gbs, bias, y, nullptr, n / 4,
                                                                         lb_make_fastdiv((uint32_t)((size_t)pixels * channels / 4)),
                                                                         lb_make_fastdiv(channels / 4));
+  } else {
+    k_norm_apply1<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(x, stats, gain, gbs, bias, y, n, pixels * channels, channels);
+  }
   LB_LAUNCH_CHECK();
   return LB_OK;
+}
+extern "C" int lb_norm_apply(const void* x, const float* stats, const float* gain, int gain_batch_stride, const float* bias,
+                             void* y, int batch, int pixels, int channels, int dtype, lb_stream_t s) {
+  LB_REQUIRE(x && stats && gain && bias && y && batch > 0 && pixels > 0 && channels > 0);
+  LB_REQUIRE(gain_batch_stride == 0 || gain_batch_stride == channels);
+  LB_DISPATCH(dtype, T, return norm_apply_t(lb_cp<T>(x), stats, gain, gain_batch_stride, bias, lb_p<T>(y), batch, pixels, channels, s));
+}
+
+template <typename T>
+static int norm_apply_ex_t(const T* x, const float* stats, const float* gain, int gbs, const float* bias, T* y, T* act, int batch,
+                           int pixels, int channels, lb_stream_t s) {
+  const size_t n = (size_t)batch * pixels * channels;
+  if ((channels & 3) || n / 4 >= ((size_t)1 << 31) - ((size_t)1 << 24) || !lb_vec4_ok(x) || (y && !lb_vec4_ok(y)) || !lb_vec4_ok(act) ||
+      !lb_aligned16(gain) || !lb_aligned16(bias))
+    return LB_EALIGN;
+  k_norm_apply4<T, true><<<lb_grid_1d(n / 4, 256), 256, 0, lb_s(s)>>>(x, stats, gain, gbs, bias, y, act, n / 4,
+                                                                     lb_make_fastdiv((uint32_t)((size_t)pixels * channels / 4)),
+                                                                     lb_make_fastdiv(channels / 4));
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
+// y (may be NULL) and act = RootTanh(y), both in storage `dtype`
+extern "C" int lb_norm_apply_ex(const void* x, const float* stats, const float* gain, int gain_batch_stride, const float* bias,
+                                void* y, void* act, int batch, int pixels, int channels, int dtype, lb_stream_t s) {
+  LB_REQUIRE(x && stats && gain && bias && act && batch > 0 && pixels > 0 && channels > 0);
+  LB_REQUIRE(gain_batch_stride == 0 || gain_batch_stride == channels);
+  LB_DISPATCH(dtype, T, return norm_apply_ex_t(lb_cp<T>(x), stats, gain, gain_batch_stride, bias, lb_p<T>(y), lb_p<T>(act), batch,
+                                               pixels, channels, s));
 }
 
 // backward phase 1: per-(b,c) column sums over pixels.  CTA = (pixel chunk, b); thread = (channel lane, pixel lane)
-__global__ void k_norm_bwd_reduce(const float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ stats,
+template <typename T>
+__global__ void k_norm_bwd_reduce(const T* __restrict__ x, const T* __restrict__ g, const float* __restrict__ stats,
                                   float* __restrict__ p1, float* __restrict__ p2, int pixels, int channels, int chunk, int tc, int tp) {
   if (threadIdx.x >= tc * tp) return;
   const float mean = __ldg(stats);
@@ -175,23 +164,24 @@ __global__ void k_norm_bwd_reduce(const float* __restrict__ x, const float* __re
 #pragma unroll 4
     for (int p = q0 + pl; p < q1; p += tp) {
       const size_t i = base + (size_t)p * channels + c;
-      const float gv = g[i];
+      const float gv = lb_ld1(g + i);
       a1 += gv;
-      a2 = fmaf(x[i] - mean, gv, a2);
+      a2 = fmaf(lb_ld1(x + i) - mean, gv, a2);
     }
     atomicAdd(p1 + (size_t)b * channels + c, a1);
     atomicAdd(p2 + (size_t)b * channels + c, a2);
   }
 }
-extern "C" int lb_norm_bwd_reduce(const float* x, const float* g, const float* stats, float* p1, float* p2, int batch,
-                                  int pixels, int channels, lb_stream_t s) {
+extern "C" int lb_norm_bwd_reduce(const void* x, const void* g, const float* stats, float* p1, float* p2, int batch,
+                                  int pixels, int channels, int dtype, lb_stream_t s) {
   LB_REQUIRE(x && g && stats && p1 && p2 && batch > 0 && pixels > 0 && channels > 0);
   const LbColShape sh = lb_col_shape(channels);
   int chunks = (LB_SMS * 4 + batch - 1) / batch;
   int chunk = (pixels + chunks - 1) / chunks;
   if (chunk < sh.tp) chunk = sh.tp;
   chunks = (pixels + chunk - 1) / chunk;
-  k_norm_bwd_reduce<<<dim3(chunks, batch), sh.threads, 0, lb_s(s)>>>(x, g, stats, p1, p2, pixels, channels, chunk, sh.tc, sh.tp);
+  LB_DISPATCH(dtype, T, k_norm_bwd_reduce<<<dim3(chunks, batch), sh.threads, 0, lb_s(s)>>>(lb_cp<T>(x), lb_cp<T>(g), stats, p1, p2, pixels,
+                                                                                          channels, chunk, sh.tc, sh.tp));
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
@@ -254,11 +244,13 @@ extern "C" int lb_norm_bwd_finalize(const float* p1, const float* p2, const floa
   return LB_OK;
 }
 
-// backward phase 3: dx = gain*g*rstd - s0*rstd/N - s1*(x-mean)*rstd^3/(N-1)
-__global__ void __launch_bounds__(256) k_norm_bwd_apply(const float* __restrict__ x, const float* __restrict__ g,
+// backward phase 3: dx = gain*g*rstd - s0*rstd/N - s1*(x-mean)*rstd^3/(N-1)  (+ add, the gradient that reaches x through
+// another branch -- the block's skip path -- summed here instead of in a pass of its own)
+template <typename T>
+__global__ void __launch_bounds__(256) k_norm_bwd_apply(const T* __restrict__ x, const T* __restrict__ g,
                                                        const float* __restrict__ stats, const float* __restrict__ gain,
-                                                       int gain_bs, const double* __restrict__ sc, float* __restrict__ dx,
-                                                       size_t n, int pc, int channels) {
+                                                       int gain_bs, const double* __restrict__ sc, const T* __restrict__ add,
+                                                       T* __restrict__ dx, size_t n, int pc, int channels) {
   const float mean = __ldg(stats), rstd = __ldg(stats + 2);
   const double nn = (double)__ldg(stats + 3);
   const double r = (double)rstd;
@@ -269,15 +261,18 @@ __global__ void __launch_bounds__(256) k_norm_bwd_apply(const float* __restrict_
     const size_t b = i / (size_t)pc;
     const int c = (int)(i % (size_t)channels);
     const float gn = __ldg(gain + b * gain_bs + c);
-    dx[i] = fmaf(gn * rstd, g[i], -k0) - k1 * (x[i] - mean);
+    float o = fmaf(gn * rstd, lb_ld1(g + i), -k0) - k1 * (lb_ld1(x + i) - mean);
+    if (add) o += lb_ld1(add + i);
+    lb_st1(dx + i, o);
   }
 }
 // one thread = 4 consecutive channels; index decode by multiply-shift (a 64-bit divide per element made the scalar
 // version instruction-bound at half the HBM rate)
-__global__ void __launch_bounds__(256) k_norm_bwd_apply4(const float* __restrict__ x, const float* __restrict__ g,
+template <typename T>
+__global__ void __launch_bounds__(256) k_norm_bwd_apply4(const T* __restrict__ x, const T* __restrict__ g,
                                                         const float* __restrict__ stats, const float* __restrict__ gain,
-                                                        int gain_bs, const double* __restrict__ sc, float* __restrict__ dx,
-                                                        int n4, LbFastDiv d_pc4, LbFastDiv d_c4) {
+                                                        int gain_bs, const double* __restrict__ sc, const T* __restrict__ add,
+                                                        T* __restrict__ dx, int n4, LbFastDiv d_pc4, LbFastDiv d_c4) {
   const float mean = __ldg(stats), rstd = __ldg(stats + 2);
   const double nn = (double)__ldg(stats + 3);
   const double r = (double)rstd;
@@ -295,21 +290,32 @@ __global__ void __launch_bounds__(256) k_norm_bwd_apply4(const float* __restrict
     o.y = fmaf(gn.y * rstd, gv.y, -k0) - k1 * (xv.y - mean);
     o.z = fmaf(gn.z * rstd, gv.z, -k0) - k1 * (xv.z - mean);
     o.w = fmaf(gn.w * rstd, gv.w, -k0) - k1 * (xv.w - mean);
+    if (add) {
+      const float4 e = lb_ld4(add + 4 * (size_t)i);
+      o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w;
+    }
     lb_st4(dx + 4 * (size_t)i, o);
   }
 }
-extern "C" int lb_norm_bwd_apply(const float* x, const float* g, const float* stats, const float* gain, int gain_batch_stride,
-                                 const double* sc, float* dx, int batch, int pixels, int channels, lb_stream_t s) {
-  LB_REQUIRE(x && g && stats && gain && sc && dx && batch > 0 && pixels > 0 && channels > 0);
+template <typename T>
+static int norm_bwd_apply_t(const T* x, const T* g, const float* stats, const float* gain, int gbs, const double* sc, const T* add, T* dx,
+                            int batch, int pixels, int channels, lb_stream_t s) {
   const size_t n = (size_t)batch * pixels * channels;
-  if (!(channels & 3) && n / 4 < ((size_t)1 << 31) - ((size_t)1 << 24) && lb_aligned16(x) && lb_aligned16(g) && lb_aligned16(dx) &&
-      lb_aligned16(gain)) {
-    k_norm_bwd_apply4<<<lb_grid_1d(n / 4, 256), 256, 0, lb_s(s)>>>(x, g, stats, gain, gain_batch_stride, sc, dx, (int)(n / 4),
+  if (!(channels & 3) && n / 4 < ((size_t)1 << 31) - ((size_t)1 << 24) && lb_vec4_ok(x) && lb_vec4_ok(g) && lb_vec4_ok(dx) &&
+      lb_aligned16(gain) && (!add || lb_vec4_ok(add))) {
+    k_norm_bwd_apply4<<<lb_grid_1d(n / 4, 256), 256, 0, lb_s(s)>>>(x, g, stats, gain, gbs, sc, add, dx, (int)(n / 4),
                                                                   lb_make_fastdiv((uint32_t)((size_t)pixels * channels / 4)),
                                                                   lb_make_fastdiv(channels / 4));
   } else {
-    k_norm_bwd_apply<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(x, g, stats, gain, gain_batch_stride, sc, dx, n, pixels * channels, channels);
+    k_norm_bwd_apply<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(x, g, stats, gain, gbs, sc, add, dx, n, pixels * channels, channels);
   }
   LB_LAUNCH_CHECK();
   return LB_OK;
+}
+extern "C" int lb_norm_bwd_apply(const void* x, const void* g, const float* stats, const float* gain, int gain_batch_stride,
+                                 const double* sc, const void* add, void* dx, int batch, int pixels, int channels, int dtype,
+                                 lb_stream_t s) {
+  LB_REQUIRE(x && g && stats && gain && sc && dx && batch > 0 && pixels > 0 && channels > 0);
+  LB_DISPATCH(dtype, T, return norm_bwd_apply_t(lb_cp<T>(x), lb_cp<T>(g), stats, gain, gain_batch_stride, sc, lb_cp<T>(add), lb_p<T>(dx),
+                                                batch, pixels, channels, s));
 }

@@ -14,7 +14,10 @@
 struct FeatPoolIdx { LbFastDiv d_c, d_hw, d_m, d_r; int hw, c_in, c_out, r, m; };
 // forward: one thread = one INPUT channel ci of one pixel group pm (reads: consecutive threads on consecutive channels of
 // r consecutive pixels, full lines); it produces out[b, (ci % r)*m + pm, ci / r].  d_c = c_in here.
-__global__ void __launch_bounds__(256) k_featpool_fwd(const float* __restrict__ x, float* __restrict__ y, int n_out, const FeatPoolIdx q) {
+__device__ __forceinline__ void lb_st2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+__device__ __forceinline__ void lb_st2(lb_bf16* p, float a, float b) { *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b); }
+template <typename T>
+__global__ void __launch_bounds__(256) k_featpool_fwd(const T* __restrict__ x, T* __restrict__ y, int n_out, const FeatPoolIdx q) {
   const int stride = gridDim.x * blockDim.x;
   const float inv = 1.0f / q.r;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += stride) {
@@ -22,30 +25,30 @@ __global__ void __launch_bounds__(256) k_featpool_fwd(const float* __restrict__ 
     lb_fast_divmod(q.d_c, i, t, ci);
     lb_fast_divmod(q.d_m, t, b, pm);
     lb_fast_divmod(q.d_r, ci, o, pj);
-    const float* src = x + ((size_t)b * q.hw + (size_t)pm * q.r) * q.c_in + ci;
+    const T* src = x + ((size_t)b * q.hw + (size_t)pm * q.r) * q.c_in + ci;
     float acc = 0.0f;
-    for (int k = 0; k < q.r; ++k) acc += __ldg(src + (size_t)k * q.c_in);
-    y[((size_t)b * q.hw + (size_t)pj * q.m + pm) * q.c_out + o] = acc * inv;
+    for (int k = 0; k < q.r; ++k) acc += lb_ld1(src + (size_t)k * q.c_in);
+    lb_st1(y + ((size_t)b * q.hw + (size_t)pj * q.m + pm) * q.c_out + o, acc * inv);
   }
 }
 // r == 2 (every use on the reference's path: C -> C/2) with 4 input channels per thread: two 16-byte loads, two 8-byte
 // stores (channels ci..ci+3 are outputs (o, o+1) of pixel groups pj = 0 and pj = 1).  d_c = c_in / 4 here.
-__global__ void __launch_bounds__(256) k_featpool_fwd_r2v4(const float* __restrict__ x, float* __restrict__ y, int n_items, const FeatPoolIdx q) {
+template <typename T>
+__global__ void __launch_bounds__(256) k_featpool_fwd_r2v4(const T* __restrict__ x, T* __restrict__ y, int n_items, const FeatPoolIdx q) {
   const int stride = gridDim.x * blockDim.x;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += stride) {
     int t, c4, b, pm;
     lb_fast_divmod(q.d_c, i, t, c4);
     lb_fast_divmod(q.d_m, t, b, pm);
-    const float* src = x + ((size_t)b * q.hw + (size_t)pm * 2) * q.c_in + 4 * c4;
+    const T* src = x + ((size_t)b * q.hw + (size_t)pm * 2) * q.c_in + 4 * c4;
     const float4 a = lb_ld4(src), c = lb_ld4(src + q.c_in);
     const int o = 2 * c4;                                   // ci = 4*c4 + {0,1,2,3} -> (o, pj) = (2*c4, 0), (2*c4, 1), (2*c4+1, 0), (2*c4+1, 1)
-    float* r0 = y + ((size_t)b * q.hw + pm) * q.c_out + o;              // pj = 0
-    float* r1 = y + ((size_t)b * q.hw + q.m + pm) * q.c_out + o;        // pj = 1
-    *reinterpret_cast<float2*>(r0) = make_float2(0.5f * (a.x + c.x), 0.5f * (a.z + c.z));
-    *reinterpret_cast<float2*>(r1) = make_float2(0.5f * (a.y + c.y), 0.5f * (a.w + c.w));
+    lb_st2(y + ((size_t)b * q.hw + pm) * q.c_out + o, 0.5f * (a.x + c.x), 0.5f * (a.z + c.z));              // pj = 0
+    lb_st2(y + ((size_t)b * q.hw + q.m + pm) * q.c_out + o, 0.5f * (a.y + c.y), 0.5f * (a.w + c.w));        // pj = 1
   }
 }
-__global__ void __launch_bounds__(256) k_featpool_bwd(const float* __restrict__ g, float* __restrict__ dx, int n_in, const FeatPoolIdx q) {
+template <typename T>
+__global__ void __launch_bounds__(256) k_featpool_bwd(const T* __restrict__ g, T* __restrict__ dx, int n_in, const FeatPoolIdx q) {
   const int stride = gridDim.x * blockDim.x;
   const float inv = 1.0f / q.r;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_in; i += stride) {
@@ -54,11 +57,12 @@ __global__ void __launch_bounds__(256) k_featpool_bwd(const float* __restrict__ 
     lb_fast_divmod(q.d_hw, bp, b, p);
     lb_fast_divmod(q.d_r, c, o, cr);
     lb_fast_divmod(q.d_r, p, pq, pr);
-    dx[i] = __ldg(g + ((size_t)b * q.hw + (size_t)cr * q.m + pq) * q.c_out + o) * inv;
+    lb_st1(dx + i, lb_ld1(g + ((size_t)b * q.hw + (size_t)cr * q.m + pq) * q.c_out + o) * inv);
   }
 }
 // generic fallbacks (r does not divide HW, or more than 2^31 items): 64-bit index arithmetic, any shape
-__global__ void k_featpool_fwd_generic(const float* __restrict__ x, float* __restrict__ y, size_t n_out, int hw, int c_in, int c_out, int r) {
+template <typename T>
+__global__ void k_featpool_fwd_generic(const T* __restrict__ x, T* __restrict__ y, size_t n_out, int hw, int c_in, int c_out, int r) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const float inv = 1.0f / r;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += stride) {
@@ -70,12 +74,13 @@ __global__ void k_featpool_fwd_generic(const float* __restrict__ x, float* __res
     float acc = 0.0f;
     for (int k = 0; k < r; ++k) {
       const size_t f = f0 + k;
-      acc += x[(b * hw + f % hw) * c_in + f / hw];
+      acc += lb_ld1(x + (b * hw + f % hw) * c_in + f / hw);
     }
-    y[i] = acc * inv;
+    lb_st1(y + i, acc * inv);
   }
 }
-__global__ void k_featpool_bwd_generic(const float* __restrict__ g, float* __restrict__ dx, size_t n_in, int hw, int c_in, int c_out, int r) {
+template <typename T>
+__global__ void k_featpool_bwd_generic(const T* __restrict__ g, T* __restrict__ dx, size_t n_in, int hw, int c_in, int c_out, int r) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const float inv = 1.0f / r;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_in; i += stride) {
@@ -86,7 +91,7 @@ __global__ void k_featpool_bwd_generic(const float* __restrict__ g, float* __res
     const size_t f = (size_t)c * hw + p;          // flat NCHW index inside the sample
     const size_t o = f / ((size_t)r * hw);
     const size_t q = (f % ((size_t)r * hw)) / r;  // output pixel
-    dx[i] = g[(b * hw + q) * c_out + o] * inv;
+    lb_st1(dx + i, lb_ld1(g + (b * hw + q) * c_out + o) * inv);
   }
 }
 static int featpool_idx(FeatPoolIdx* q, int batch, int h, int w, int c_in, int c_out, int c_fast, size_t n) {
@@ -97,12 +102,12 @@ static int featpool_idx(FeatPoolIdx* q, int batch, int h, int w, int c_in, int c
   (void)batch;
   return LB_OK;
 }
-extern "C" int lb_featpool_fwd(const float* x, float* y, int batch, int h, int w, int c_in, int c_out, lb_stream_t s) {
-  LB_REQUIRE(x && y && batch > 0 && h > 0 && w > 0 && c_out > 0 && c_in % c_out == 0);
+template <typename T>
+static int featpool_fwd_t(const T* x, T* y, int batch, int h, int w, int c_in, int c_out, lb_stream_t s) {
   const size_t n = (size_t)batch * h * w * c_out;
   FeatPoolIdx q;
   if (featpool_idx(&q, batch, h, w, c_in, c_out, c_in, n) == LB_OK) {
-    if (q.r == 2 && !(c_in & 3) && lb_aligned16(x) && !(reinterpret_cast<uintptr_t>(y) & 7)) {
+    if (q.r == 2 && !(c_in & 3) && lb_vec4_ok(x) && !(reinterpret_cast<uintptr_t>(y) & (2 * sizeof(T) - 1))) {
       q.d_c = lb_make_fastdiv(c_in / 4);
       k_featpool_fwd_r2v4<<<lb_grid_1d(n / 4, 256), 256, 0, lb_s(s)>>>(x, y, (int)(n / 4), q);     // n = B*m*c_in outputs, 4 per item
     } else {
@@ -114,8 +119,8 @@ extern "C" int lb_featpool_fwd(const float* x, float* y, int batch, int h, int w
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
-extern "C" int lb_featpool_bwd(const float* g, float* dx, int batch, int h, int w, int c_in, int c_out, lb_stream_t s) {
-  LB_REQUIRE(g && dx && batch > 0 && h > 0 && w > 0 && c_out > 0 && c_in % c_out == 0);
+template <typename T>
+static int featpool_bwd_t(const T* g, T* dx, int batch, int h, int w, int c_in, int c_out, lb_stream_t s) {
   const size_t n = (size_t)batch * h * w * c_in;
   FeatPoolIdx q;
   if (featpool_idx(&q, batch, h, w, c_in, c_out, c_in, n) == LB_OK)
@@ -124,6 +129,14 @@ extern "C" int lb_featpool_bwd(const float* g, float* dx, int batch, int h, int 
     k_featpool_bwd_generic<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(g, dx, n, h * w, c_in, c_out, c_in / c_out);
   LB_LAUNCH_CHECK();
   return LB_OK;
+}
+extern "C" int lb_featpool_fwd(const void* x, void* y, int batch, int h, int w, int c_in, int c_out, int dtype, lb_stream_t s) {
+  LB_REQUIRE(x && y && batch > 0 && h > 0 && w > 0 && c_out > 0 && c_in % c_out == 0);
+  LB_DISPATCH(dtype, T, return featpool_fwd_t(lb_cp<T>(x), lb_p<T>(y), batch, h, w, c_in, c_out, s));
+}
+extern "C" int lb_featpool_bwd(const void* g, void* dx, int batch, int h, int w, int c_in, int c_out, int dtype, lb_stream_t s) {
+  LB_REQUIRE(g && dx && batch > 0 && h > 0 && w > 0 && c_out > 0 && c_in % c_out == 0);
+  LB_DISPATCH(dtype, T, return featpool_bwd_t(lb_cp<T>(g), lb_p<T>(dx), batch, h, w, c_in, c_out, s));
 }
 
 // ---- bilinear x2, align_corners=False (scale.py:37-38) --------------------------------------
@@ -147,40 +160,41 @@ static inline PixIdx make_pix_idx(int c, int w, int h) {
   return q;
 }
 #define LB_REQUIRE_INT_ITEMS(n) LB_REQUIRE((n) < ((size_t)1 << 31) - ((size_t)1 << 24))
-// V = 4: one thread = 4 consecutive channels (128-bit accesses, 4x fewer index computations); V = 1: any layout
-template <int V> struct VecT;
-template <> struct VecT<1> { typedef float type; };
-template <> struct VecT<4> { typedef float4 type; };
-__device__ __forceinline__ float vmix(float a, float b, float c, float d, float w0, float w1, float w2, float w3) {
-  return w0 * a + w1 * b + w2 * c + w3 * d;
-}
-__device__ __forceinline__ float4 vmix(float4 a, float4 b, float4 c, float4 d, float w0, float w1, float w2, float w3) {
-  return make_float4(w0 * a.x + w1 * b.x + w2 * c.x + w3 * d.x, w0 * a.y + w1 * b.y + w2 * c.y + w3 * d.y,
-                     w0 * a.z + w1 * b.z + w2 * c.z + w3 * d.z, w0 * a.w + w1 * b.w + w2 * c.w + w3 * d.w);
-}
-__device__ __forceinline__ void vfma(float& acc, float w, float v) { acc = fmaf(w, v, acc); }
-__device__ __forceinline__ void vfma(float4& acc, float w, float4 v) {
-  acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y); acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
-}
-__device__ __forceinline__ float vzero(float) { return 0.0f; }
-__device__ __forceinline__ float4 vzero(float4) { return make_float4(0.f, 0.f, 0.f, 0.f); }
+// V = 4: one thread = 4 consecutive channels (one 4-element access, 4x fewer index computations); V = 1: any layout.
+// `c` below is the channel count in ELEMENTS; the item decode runs over channel groups of V.
+template <int V> struct Acc;
+template <> struct Acc<1> {
+  float v;
+  __device__ Acc() : v(0.0f) {}
+  template <typename T> __device__ void fma(float w, const T* p) { v = fmaf(w, lb_ld1(p), v); }
+  template <typename T> __device__ void store(T* p) const { lb_st1(p, v); }
+};
+template <> struct Acc<4> {
+  float4 v;
+  __device__ Acc() : v(make_float4(0.f, 0.f, 0.f, 0.f)) {}
+  template <typename T> __device__ void fma(float w, const T* p) {
+    const float4 a = lb_ld4(p);
+    v.x = fmaf(w, a.x, v.x); v.y = fmaf(w, a.y, v.y); v.z = fmaf(w, a.z, v.z); v.w = fmaf(w, a.w, v.w);
+  }
+  template <typename T> __device__ void store(T* p) const { lb_st4(p, v); }
+};
 
-template <int V>
-__global__ void __launch_bounds__(256) k_up2_fwd(const float* __restrict__ xs, float* __restrict__ ys, int n_out, int h, int w, int c,
-                                                 const PixIdx q) {
-  typedef typename VecT<V>::type T;
-  const T* __restrict__ x = reinterpret_cast<const T*>(xs);
-  T* __restrict__ y = reinterpret_cast<T*>(ys);
+template <typename T, int V>
+__global__ void __launch_bounds__(256) k_up2_fwd(const T* __restrict__ x, T* __restrict__ y, int n_out, int h, int w, int c, const PixIdx q) {
   const int stride = gridDim.x * blockDim.x;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += stride) {
     int ch, ox, oy, b;
-    pix_decode(q, i, ch, ox, oy, b);              // q over (c, 2w, 2h)
+    pix_decode(q, i, ch, ox, oy, b);              // q over (c / V, 2w, 2h)
     int y0, y1, x0, x1; float ly, lx;
     lb_up2_src(oy, h, y0, y1, ly);
     lb_up2_src(ox, w, x0, x1, lx);
-    const T* xb = x + (size_t)b * h * w * c + ch;
-    y[i] = vmix(xb[((size_t)y0 * w + x0) * c], xb[((size_t)y0 * w + x1) * c], xb[((size_t)y1 * w + x0) * c],
-                xb[((size_t)y1 * w + x1) * c], (1.0f - ly) * (1.0f - lx), (1.0f - ly) * lx, ly * (1.0f - lx), ly * lx);
+    const T* xb = x + (size_t)b * h * w * c + ch * V;
+    Acc<V> acc;
+    acc.fma((1.0f - ly) * (1.0f - lx), xb + ((size_t)y0 * w + x0) * c);
+    acc.fma((1.0f - ly) * lx, xb + ((size_t)y0 * w + x1) * c);
+    acc.fma(ly * (1.0f - lx), xb + ((size_t)y1 * w + x0) * c);
+    acc.fma(ly * lx, xb + ((size_t)y1 * w + x1) * c);
+    acc.store(y + (size_t)i * V);
   }
 }
 // weight with which source index m receives from destination index d along one axis
@@ -190,17 +204,13 @@ __device__ __forceinline__ float lb_up2_weight(int d, int n, int m) {
   return (i0 == m ? 1.0f - lam : 0.0f) + (i1 == m ? lam : 0.0f);
 }
 // 1-D transposed taps of the x2 bilinear kernel: source m receives from destinations 2m-1 .. 2m+2
-template <int V>
-__global__ void __launch_bounds__(256) k_up2_bwd(const float* __restrict__ gs, float* __restrict__ dxs, int n_in, int h, int w, int c,
-                                                 const PixIdx q) {
-  typedef typename VecT<V>::type T;
-  const T* __restrict__ g = reinterpret_cast<const T*>(gs);
-  T* __restrict__ dx = reinterpret_cast<T*>(dxs);
+template <typename T, int V>
+__global__ void __launch_bounds__(256) k_up2_bwd(const T* __restrict__ g, T* __restrict__ dx, int n_in, int h, int w, int c, const PixIdx q) {
   const int stride = gridDim.x * blockDim.x;
   const int ow = 2 * w, oh = 2 * h;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_in; i += stride) {
     int ch, ix, iy, b;
-    pix_decode(q, i, ch, ix, iy, b);              // q over (c, w, h)
+    pix_decode(q, i, ch, ix, iy, b);              // q over (c / V, w, h)
     float wy[4], wx[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
@@ -208,93 +218,103 @@ __global__ void __launch_bounds__(256) k_up2_bwd(const float* __restrict__ gs, f
       wy[t] = (dy >= 0 && dy < oh) ? lb_up2_weight(dy, h, iy) : 0.0f;
       wx[t] = (dxp >= 0 && dxp < ow) ? lb_up2_weight(dxp, w, ix) : 0.0f;
     }
-    const T* gb = g + (size_t)b * oh * ow * c + ch;
-    T acc = vzero(T());
+    const T* gb = g + (size_t)b * oh * ow * c + ch * V;
+    Acc<V> acc;
 #pragma unroll
     for (int ty = 0; ty < 4; ++ty) {
       if (wy[ty] == 0.0f) continue;
       const T* row = gb + (size_t)(2 * iy - 1 + ty) * ow * c;
 #pragma unroll
       for (int tx = 0; tx < 4; ++tx)
-        if (wx[tx] != 0.0f) vfma(acc, wy[ty] * wx[tx], row[(size_t)(2 * ix - 1 + tx) * c]);
+        if (wx[tx] != 0.0f) acc.fma(wy[ty] * wx[tx], row + (size_t)(2 * ix - 1 + tx) * c);
     }
-    dx[i] = acc;
+    acc.store(dx + (size_t)i * V);
   }
 }
-extern "C" int lb_upsample2x_fwd(const float* x, float* y, int batch, int h, int w, int c, lb_stream_t s) {
-  LB_REQUIRE(x && y && batch > 0 && h > 0 && w > 0 && c > 0);
+template <typename T>
+static int up2_fwd_t(const T* x, T* y, int batch, int h, int w, int c, lb_stream_t s) {
   const size_t n = (size_t)batch * h * w * c * 4;
   LB_REQUIRE_INT_ITEMS(n);
-  if ((c & 3) == 0 && lb_aligned16(x) && lb_aligned16(y))
-    k_up2_fwd<4><<<lb_grid_1d(n / 4, 256), 256, 0, lb_s(s)>>>(x, y, (int)(n / 4), h, w, c / 4, make_pix_idx(c / 4, 2 * w, 2 * h));
+  if ((c & 3) == 0 && lb_vec4_ok(x) && lb_vec4_ok(y))
+    k_up2_fwd<T, 4><<<lb_grid_1d(n / 4, 256), 256, 0, lb_s(s)>>>(x, y, (int)(n / 4), h, w, c, make_pix_idx(c / 4, 2 * w, 2 * h));
   else
-    k_up2_fwd<1><<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(x, y, (int)n, h, w, c, make_pix_idx(c, 2 * w, 2 * h));
+    k_up2_fwd<T, 1><<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(x, y, (int)n, h, w, c, make_pix_idx(c, 2 * w, 2 * h));
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
-extern "C" int lb_upsample2x_bwd(const float* g, float* dx, int batch, int h, int w, int c, lb_stream_t s) {
-  LB_REQUIRE(g && dx && batch > 0 && h > 0 && w > 0 && c > 0);
+template <typename T>
+static int up2_bwd_t(const T* g, T* dx, int batch, int h, int w, int c, lb_stream_t s) {
   const size_t n = (size_t)batch * h * w * c;
   LB_REQUIRE_INT_ITEMS(n);
-  if ((c & 3) == 0 && lb_aligned16(g) && lb_aligned16(dx))
-    k_up2_bwd<4><<<lb_grid_1d(n / 4, 256), 256, 0, lb_s(s)>>>(g, dx, (int)(n / 4), h, w, c / 4, make_pix_idx(c / 4, w, h));
+  if ((c & 3) == 0 && lb_vec4_ok(g) && lb_vec4_ok(dx))
+    k_up2_bwd<T, 4><<<lb_grid_1d(n / 4, 256), 256, 0, lb_s(s)>>>(g, dx, (int)(n / 4), h, w, c, make_pix_idx(c / 4, w, h));
   else
-    k_up2_bwd<1><<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(g, dx, (int)n, h, w, c, make_pix_idx(c, w, h));
+    k_up2_bwd<T, 1><<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(g, dx, (int)n, h, w, c, make_pix_idx(c, w, h));
   LB_LAUNCH_CHECK();
   return LB_OK;
+}
+extern "C" int lb_upsample2x_fwd(const void* x, void* y, int batch, int h, int w, int c, int dtype, lb_stream_t s) {
+  LB_REQUIRE(x && y && batch > 0 && h > 0 && w > 0 && c > 0);
+  LB_DISPATCH(dtype, T, return up2_fwd_t(lb_cp<T>(x), lb_p<T>(y), batch, h, w, c, s));
+}
+extern "C" int lb_upsample2x_bwd(const void* g, void* dx, int batch, int h, int w, int c, int dtype, lb_stream_t s) {
+  LB_REQUIRE(g && dx && batch > 0 && h > 0 && w > 0 && c > 0);
+  LB_DISPATCH(dtype, T, return up2_bwd_t(lb_cp<T>(g), lb_p<T>(dx), batch, h, w, c, s));
 }
 
 // ---- AvgPool 2x2 / stride 2 (scale.py:40) ----------------------------------------------------
-template <int V>
-__global__ void __launch_bounds__(256) k_avgpool2_fwd(const float* __restrict__ xs, float* __restrict__ ys, int n_out, int h, int w, int c,
-                                                      const PixIdx q) {
-  typedef typename VecT<V>::type T;
-  const T* __restrict__ x = reinterpret_cast<const T*>(xs);
-  T* __restrict__ y = reinterpret_cast<T*>(ys);
+template <typename T, int V>
+__global__ void __launch_bounds__(256) k_avgpool2_fwd(const T* __restrict__ x, T* __restrict__ y, int n_out, int h, int w, int c, const PixIdx q) {
   const int stride = gridDim.x * blockDim.x;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += stride) {
     int ch, ox, oy, b;
-    pix_decode(q, i, ch, ox, oy, b);              // q over (c, w/2, h/2)
-    const T* p = x + (((size_t)b * h + 2 * oy) * w + 2 * ox) * c + ch;
-    y[i] = vmix(p[0], p[c], p[(size_t)w * c], p[(size_t)w * c + c], 0.25f, 0.25f, 0.25f, 0.25f);
+    pix_decode(q, i, ch, ox, oy, b);              // q over (c / V, w/2, h/2)
+    const T* p = x + (((size_t)b * h + 2 * oy) * w + 2 * ox) * c + ch * V;
+    Acc<V> acc;
+    acc.fma(0.25f, p); acc.fma(0.25f, p + c); acc.fma(0.25f, p + (size_t)w * c); acc.fma(0.25f, p + (size_t)w * c + c);
+    acc.store(y + (size_t)i * V);
   }
 }
-template <int V>
-__global__ void __launch_bounds__(256) k_avgpool2_bwd(const float* __restrict__ gs, float* __restrict__ dxs, int n_in, int h, int w, int c,
-                                                      const PixIdx q) {
-  typedef typename VecT<V>::type T;
-  const T* __restrict__ g = reinterpret_cast<const T*>(gs);
-  T* __restrict__ dx = reinterpret_cast<T*>(dxs);
+template <typename T, int V>
+__global__ void __launch_bounds__(256) k_avgpool2_bwd(const T* __restrict__ g, T* __restrict__ dx, int n_in, int h, int w, int c, const PixIdx q) {
   const int stride = gridDim.x * blockDim.x;
   const int oh = h / 2, ow = w / 2;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_in; i += stride) {
     int ch, ix, iy, b;
-    pix_decode(q, i, ch, ix, iy, b);              // q over (c, w, h)
+    pix_decode(q, i, ch, ix, iy, b);              // q over (c / V, w, h)
     const int oy = iy >> 1, ox = ix >> 1;
-    T acc = vzero(T());
-    if (oy < oh && ox < ow) vfma(acc, 0.25f, g[(((size_t)b * oh + oy) * ow + ox) * c + ch]);
-    dx[i] = acc;
+    Acc<V> acc;
+    if (oy < oh && ox < ow) acc.fma(0.25f, g + (((size_t)b * oh + oy) * ow + ox) * c + ch * V);
+    acc.store(dx + (size_t)i * V);
   }
 }
-extern "C" int lb_avgpool2_fwd(const float* x, float* y, int batch, int h, int w, int c, lb_stream_t s) {
-  LB_REQUIRE(x && y && batch > 0 && h > 1 && w > 1 && c > 0);
+template <typename T>
+static int avgpool2_fwd_t(const T* x, T* y, int batch, int h, int w, int c, lb_stream_t s) {
   const size_t n = (size_t)batch * (h / 2) * (w / 2) * c;
   LB_REQUIRE_INT_ITEMS(n);
-  if ((c & 3) == 0 && lb_aligned16(x) && lb_aligned16(y))
-    k_avgpool2_fwd<4><<<lb_grid_1d(n / 4, 256), 256, 0, lb_s(s)>>>(x, y, (int)(n / 4), h, w, c / 4, make_pix_idx(c / 4, w / 2, h / 2));
+  if ((c & 3) == 0 && lb_vec4_ok(x) && lb_vec4_ok(y))
+    k_avgpool2_fwd<T, 4><<<lb_grid_1d(n / 4, 256), 256, 0, lb_s(s)>>>(x, y, (int)(n / 4), h, w, c, make_pix_idx(c / 4, w / 2, h / 2));
   else
-    k_avgpool2_fwd<1><<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(x, y, (int)n, h, w, c, make_pix_idx(c, w / 2, h / 2));
+    k_avgpool2_fwd<T, 1><<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(x, y, (int)n, h, w, c, make_pix_idx(c, w / 2, h / 2));
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
-extern "C" int lb_avgpool2_bwd(const float* g, float* dx, int batch, int h, int w, int c, lb_stream_t s) {
-  LB_REQUIRE(g && dx && batch > 0 && h > 1 && w > 1 && c > 0);
+template <typename T>
+static int avgpool2_bwd_t(const T* g, T* dx, int batch, int h, int w, int c, lb_stream_t s) {
   const size_t n = (size_t)batch * h * w * c;
   LB_REQUIRE_INT_ITEMS(n);
-  if ((c & 3) == 0 && lb_aligned16(g) && lb_aligned16(dx))
-    k_avgpool2_bwd<4><<<lb_grid_1d(n / 4, 256), 256, 0, lb_s(s)>>>(g, dx, (int)(n / 4), h, w, c / 4, make_pix_idx(c / 4, w, h));
+  if ((c & 3) == 0 && lb_vec4_ok(g) && lb_vec4_ok(dx))
+    k_avgpool2_bwd<T, 4><<<lb_grid_1d(n / 4, 256), 256, 0, lb_s(s)>>>(g, dx, (int)(n / 4), h, w, c, make_pix_idx(c / 4, w, h));
   else
-    k_avgpool2_bwd<1><<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(g, dx, (int)n, h, w, c, make_pix_idx(c, w, h));
+    k_avgpool2_bwd<T, 1><<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(g, dx, (int)n, h, w, c, make_pix_idx(c, w, h));
   LB_LAUNCH_CHECK();
   return LB_OK;
+}
+extern "C" int lb_avgpool2_fwd(const void* x, void* y, int batch, int h, int w, int c, int dtype, lb_stream_t s) {
+  LB_REQUIRE(x && y && batch > 0 && h > 1 && w > 1 && c > 0);
+  LB_DISPATCH(dtype, T, return avgpool2_fwd_t(lb_cp<T>(x), lb_p<T>(y), batch, h, w, c, s));
+}
+extern "C" int lb_avgpool2_bwd(const void* g, void* dx, int batch, int h, int w, int c, int dtype, lb_stream_t s) {
+  LB_REQUIRE(g && dx && batch > 0 && h > 1 && w > 1 && c > 0);
+  LB_DISPATCH(dtype, T, return avgpool2_bwd_t(lb_cp<T>(g), lb_p<T>(dx), batch, h, w, c, s));
 }

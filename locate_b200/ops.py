@@ -72,41 +72,89 @@ def _conv_work(spec, b, h, w_, oh, ow):
     return flops, nbytes
 
 
-def _as_act(t):
-    """fp32, CUDA, channels-last (4-D) or contiguous (other ranks)."""
-    if getattr(t, "_lb_unwritten", False):
-        raise RuntimeError("this tensor's fp32 values were never written (only its bf16 GEMM operand exists)")
+F32, BF16 = 0, 1          # include/locate_b200.h: LB_F32 / LB_BF16
+
+
+def _dt(t):
+    """C-ABI storage code of an activation tensor."""
+    if t.dtype == torch.bfloat16:
+        return BF16
     if t.dtype != torch.float32:
+        raise TypeError(f"activations are fp32 or bf16, got {t.dtype}")
+    return F32
+
+
+def store_dtype(shape):
+    """Storage type of an activation of this logical shape: in the tensor-core configuration every [B,C,H,W] map whose
+    channel count TMA can address (C % 8 == 0) lives in HBM as bf16 -- half the bytes of every elementwise pass and
+    directly the GEMM operand; narrow maps (RGB images, logits) and [B,C] vectors (style chain) stay fp32."""
+    from .config import CFG
+    if CFG.PRECISION == "bf16" and len(shape) == 4 and shape[1] % 8 == 0:
+        return torch.bfloat16
+    return torch.float32
+
+
+def _cl_strides(shape):
+    b, c, h, w = shape
+    return (h * w * c, 1, w * c, c)
+
+
+def _cast(t, dtype):
+    """Same layout, other storage type (fp32 -> bf16 through lb_cast_bf16; the reverse only happens at API edges)."""
+    if t.dtype == dtype:
+        return t
+    if dtype == torch.bfloat16 and t.dtype == torch.float32 and t.is_cuda and t.numel() > 0 and (
+            t.is_contiguous() or (t.dim() == 4 and t.is_contiguous(memory_format=_CL))) and t.data_ptr() % 16 == 0:
+        out = torch.empty_strided(t.shape, t.stride(), dtype=torch.bfloat16, device=t.device)
+        call("lb_cast_bf16", ptr(t), ptr(out), t.numel())
+        return out
+    return t.to(dtype)
+
+
+def _as_act(t):
+    """Bring a tensor to the library's activation form: CUDA, storage type per store_dtype(), channels-last (4-D) or
+    contiguous (other ranks).  Anything else is converted once at the boundary."""
+    if t.dtype not in (torch.float32, torch.bfloat16):
         t = t.float()
     if t.dim() == 4:
-        return t if t.is_contiguous(memory_format=_CL) else _to_channels_last(t)
+        want = store_dtype(t.shape)
+        if t.is_contiguous(memory_format=_CL):
+            if t.stride() != _cl_strides(t.shape):          # size-1 dims leave strides ambiguous: same memory, canonical strides
+                t = t.as_strided(t.shape, _cl_strides(t.shape))
+            return _cast(t, want)
+        if t.dtype != torch.float32:
+            return _cast(t.contiguous(memory_format=_CL), want)
+        return _to_channels_last(t, want)
+    if t.dtype != torch.float32:
+        t = t.float()
     return t.contiguous()
 
 
-def _to_channels_last(t):
-    """NCHW-contiguous -> channels-last through lb_nchw_to_nhwc (no torch copy kernel)."""
+def _to_channels_last(t, dtype=torch.float32):
+    """fp32 NCHW-contiguous -> channels-last (fp32 or bf16 storage) through lb_nchw_to_nhwc (no torch copy kernel)."""
     if not t.is_contiguous():
         t = t.contiguous()
     b, c, h, w = t.shape
-    out = torch.empty_strided((b, c, h, w), (h * w * c, 1, w * c, c), dtype=t.dtype, device=t.device)
-    call("lb_nchw_to_nhwc", ptr(t), ptr(out), b, c, h * w)
+    out = torch.empty_strided((b, c, h, w), (h * w * c, 1, w * c, c), dtype=dtype, device=t.device)
+    call("lb_nchw_to_nhwc", ptr(t), ptr(out), b, c, h * w, BF16 if dtype == torch.bfloat16 else F32)
     return out
 
 
 def to_nchw(t):
-    """channels-last -> NCHW-contiguous copy (model boundary, e.g. image dumps)."""
+    """channels-last (either storage type) -> fp32 NCHW-contiguous copy (model boundary, e.g. image dumps)."""
     t = _as_act(t)
     b, c, h, w = t.shape
-    out = torch.empty((b, c, h, w), dtype=t.dtype, device=t.device)
-    call("lb_nhwc_to_nchw", ptr(t), ptr(out), b, c, h * w)
+    out = torch.empty((b, c, h, w), dtype=torch.float32, device=t.device)
+    call("lb_nhwc_to_nchw", ptr(t), ptr(out), b, c, h * w, _dt(t))
     return out
 
 
-def _new_act(shape, like):
+def _new_act(shape, like, dtype=None):
+    if dtype is None:
+        dtype = store_dtype(shape)
     if len(shape) == 4:
-        b, c, h, w = shape
-        return torch.empty_strided((b, c, h, w), (h * w * c, 1, w * c, c), dtype=torch.float32, device=like.device)
-    return torch.empty(shape, dtype=torch.float32, device=like.device)
+        return torch.empty_strided(tuple(shape), _cl_strides(shape), dtype=dtype, device=like.device)
+    return torch.empty(shape, dtype=dtype, device=like.device)
 
 
 def _bpc(t):
@@ -144,6 +192,22 @@ def _grad_sink(param):
     return fresh, fresh
 
 
+def _match(g, ref):
+    """Bring an incoming gradient to the layout and storage type of `ref` (same logical shape)."""
+    if g.shape != ref.shape:
+        g = g.expand(tuple(ref.shape))
+    if g.stride() != tuple(ref.stride()) or g.dtype != ref.dtype:
+        if g.dim() == 4:
+            if not g.is_contiguous(memory_format=_CL):
+                g = _to_channels_last(g.float(), ref.dtype)     # NCHW gradients only arrive at the API boundary
+            g = _cast(g, ref.dtype)
+        else:
+            g = _cast(g.contiguous(), ref.dtype)
+        if g.stride() != tuple(ref.stride()):   # size-1 dims make strides ambiguous; data is identical
+            g = g.as_strided(tuple(ref.shape), tuple(ref.stride()))
+    return g
+
+
 # ------------------------------------------------------------------------------------------
 # activations
 # ------------------------------------------------------------------------------------------
@@ -154,7 +218,7 @@ class RootTanhFn(torch.autograd.Function):
     def forward(ctx, x, growth):
         x = _as_act(x)
         y = torch.empty_like(x)
-        call("lb_roottanh_fwd", ptr(x), ptr(y), x.numel(), growth)
+        call("lb_roottanh_fwd", ptr(x), ptr(y), x.numel(), growth, _dt(x))
         ctx.save_for_backward(x)
         ctx.growth = growth
         return y
@@ -164,7 +228,7 @@ class RootTanhFn(torch.autograd.Function):
         (x,) = ctx.saved_tensors
         g = _match(g, x)
         dx = torch.empty_like(x)
-        call("lb_roottanh_bwd", ptr(x), ptr(g), ptr(dx), x.numel(), ctx.growth)
+        call("lb_roottanh_bwd", ptr(x), ptr(g), ptr(dx), x.numel(), ctx.growth, _dt(x))
         return dx, None
 
 
@@ -175,7 +239,7 @@ class TanhFn(torch.autograd.Function):
     def forward(ctx, x):
         x = _as_act(x)
         y = torch.empty_like(x)
-        call("lb_tanh_fwd", ptr(x), ptr(y), x.numel())
+        call("lb_tanh_fwd", ptr(x), ptr(y), x.numel(), _dt(x))
         ctx.save_for_backward(y)
         return y
 
@@ -184,7 +248,7 @@ class TanhFn(torch.autograd.Function):
         (y,) = ctx.saved_tensors
         g = _match(g, y)
         dx = torch.empty_like(y)
-        call("lb_tanh_bwd", ptr(y), ptr(g), ptr(dx), y.numel())
+        call("lb_tanh_bwd", ptr(y), ptr(g), ptr(dx), y.numel(), _dt(y))
         return dx
 
 
@@ -193,7 +257,7 @@ class HingeFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x):
-        x = x.contiguous()
+        x = x.float().contiguous()
         y = torch.empty_like(x)
         call("lb_hinge_fwd", ptr(x), ptr(y), x.numel())
         ctx.save_for_backward(x)
@@ -202,21 +266,10 @@ class HingeFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         (x,) = ctx.saved_tensors
-        g = g.contiguous()
+        g = g.float().contiguous()
         dx = torch.empty_like(x)
         call("lb_hinge_bwd", ptr(x), ptr(g), ptr(dx), x.numel())
         return dx
-
-
-def _match(g, ref):
-    """Bring an incoming gradient to the layout of `ref` (same logical shape)."""
-    if g.shape != ref.shape:
-        g = g.expand_as(ref)
-    if g.stride() != ref.stride() or g.dtype != torch.float32:
-        g = _as_act(g.float())
-        if g.stride() != ref.stride():          # size-1 dims make strides ambiguous; data is identical
-            g = g.as_strided(ref.shape, ref.stride())
-    return g
 
 
 # ------------------------------------------------------------------------------------------
@@ -229,38 +282,33 @@ class WholeNormFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, gain, bias, emit=None):
-        """emit: None | "act" | "plain" -- also produce the bf16 operand of the conv that consumes the result
-        (RootTanh applied first for "act"), attached to the output as `_lb_act16` / `_lb_plain16`.  With "plain" nothing
-        but that conv reads the result, so the fp32 tensor is allocated but NOT written (`_lb_unwritten`)."""
+        """emit == "act": the module that follows starts with RootTanh -> conv (conv.py:22-24); in the tensor-core
+        configuration the same pass also writes RootTanh(y), that convolution's GEMM operand, attached to the output as
+        `_lb_act16` (the pre-activation y stays: the backward needs RootTanh'(y))."""
         x = _as_act(x)
+        dt = _dt(x)
         b, p, c = _bpc(x)
         per_sample = gain.shape[0] != 1          # [B,C,1,1] style gain (B == 1 degenerates to the shared form)
         if gain.numel() != (b if per_sample else 1) * c or bias.numel() != c:
             raise ValueError(f"norm: gain {tuple(gain.shape)} / bias {tuple(bias.shape)} do not fit {tuple(x.shape)}")
-        gain_c = gain.contiguous()
+        gain_c = gain.float().contiguous()
         ready = getattr(x, "_lb_sums", None)
         if ready is not None:
             sums = ready.clone()                  # the producer (gate kernel) already reduced them; clone: all-reduced in place
         else:
             sums = torch.empty(2, dtype=torch.float64, device=x.device)
-            call("lb_norm_stats", ptr(x), x.numel(), ptr(sums), ptr(_stat_work(x.device)))
+            call("lb_norm_stats", ptr(x), x.numel(), ptr(sums), ptr(_stat_work(x.device)), dt)
         n_total = float(x.numel()) * dist.all_reduce_sum_(sums)
         stats = torch.empty(4, dtype=torch.float32, device=x.device)
         call("lb_norm_finalize", ptr(sums), n_total, ptr(stats))
         y = torch.empty_like(x)
-        from .config import CFG
-        if emit is not None and CFG.PRECISION == "bf16" and c % 8 == 0 and x.dim() == 4:
-            y16 = torch.empty_strided(x.shape, x.stride(), dtype=torch.bfloat16, device=x.device)
-            lazy = emit == "plain" and c >= 32     # wide enough that the consumer is always a tensor-core GEMM
-            call("lb_norm_apply_ex", ptr(x), ptr(stats), ptr(gain_c), c if per_sample else 0, ptr(bias), None if lazy else ptr(y),
-                 ptr(y16), 1 if emit == "act" else 0, b, p, c)
-            if emit == "act":
-                y._lb_act16 = y16
-            else:
-                y._lb_plain16 = y16
-                y._lb_unwritten = True
+        gbs = c if per_sample else 0
+        if emit == "act" and dt == BF16 and c % 4 == 0 and x.dim() == 4:
+            act = torch.empty_like(x)
+            call("lb_norm_apply_ex", ptr(x), ptr(stats), ptr(gain_c), gbs, ptr(bias), ptr(y), ptr(act), b, p, c, dt)
+            y._lb_act16 = act
         else:
-            call("lb_norm_apply", ptr(x), ptr(stats), ptr(gain_c), c if per_sample else 0, ptr(bias), ptr(y), b, p, c)
+            call("lb_norm_apply", ptr(x), ptr(stats), ptr(gain_c), gbs, ptr(bias), ptr(y), b, p, c, dt)
         ctx.save_for_backward(x, gain_c, stats)
         ctx.per_sample = per_sample
         ctx.gain_param, ctx.bias_param = gain, bias
@@ -270,9 +318,10 @@ class WholeNormFn(torch.autograd.Function):
     def backward(ctx, g):
         x, gain, stats = ctx.saved_tensors
         g = _match(g, x)
+        dt = _dt(x)
         b, p, c = _bpc(x)
         part = torch.zeros((2, b, c), dtype=torch.float32, device=x.device)
-        call("lb_norm_bwd_reduce", ptr(x), ptr(g), ptr(stats), ptr(part[0]), ptr(part[1]), b, p, c)
+        call("lb_norm_bwd_reduce", ptr(x), ptr(g), ptr(stats), ptr(part[0]), ptr(part[1]), b, p, c, dt)
         need_gain, need_bias = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         if ctx.per_sample:
             dgain = torch.zeros_like(gain)           # the kernel always writes the per-sample slots
@@ -292,7 +341,8 @@ class WholeNormFn(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
-            call("lb_norm_bwd_apply", ptr(x), ptr(g), ptr(stats), ptr(gain), c if ctx.per_sample else 0, ptr(sc), ptr(dx), b, p, c)
+            call("lb_norm_bwd_apply", ptr(x), ptr(g), ptr(stats), ptr(gain), c if ctx.per_sample else 0, ptr(sc), None, ptr(dx),
+                 b, p, c, dt)
         return dx, dgain_ret, dbias_ret, None
 
 
@@ -305,45 +355,59 @@ class GateFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, y, gamma, strict_reference):
         x = _as_act(x)
+        dt = _dt(x)
         b, p, c = _bpc(x)
         bcast = y.shape != x.shape
+        y_in_dtype = y.dtype
         if bcast:
             if tuple(y.shape[:2]) != (b, c) or y.numel() != b * c:
                 raise ValueError(f"gate: cannot broadcast {tuple(y.shape)} over {tuple(x.shape)}")
-            y = y.contiguous()
+            y = _cast(y.contiguous() if y.dim() != 4 else _as_act(y), x.dtype)
         else:
             y = _match(y, x)
         out = torch.empty_like(x)
         if x.dim() == 4 and c % 4 == 0 and x.numel() < (1 << 32):
             # every gate output is normalised next (block.py:46-51): leave its (sum, sum^2) for WholeNormFn
             sums = torch.empty(2, dtype=torch.float64, device=x.device)
-            call("lb_gate_fwd_stats", ptr(x), ptr(y), ptr(gamma), ptr(out), ptr(sums), ptr(_stat_work(x.device)), b, p, c, int(bcast))
+            call("lb_gate_fwd_stats", ptr(x), ptr(y), ptr(gamma), ptr(out), ptr(sums), ptr(_stat_work(x.device)), b, p, c,
+                 int(bcast), dt)
             out._lb_sums = sums
         else:
-            call("lb_gate_fwd", ptr(x), ptr(y), ptr(gamma), ptr(out), b, p, c, int(bcast))
+            call("lb_gate_fwd", ptr(x), ptr(y), ptr(gamma), ptr(out), b, p, c, int(bcast), dt)
         ctx.save_for_backward(x, y, gamma)
-        ctx.bcast, ctx.strict, ctx.gamma_param = bcast, strict_reference, gamma
+        ctx.bcast, ctx.strict, ctx.gamma_param, ctx.y_dtype = bcast, strict_reference, gamma, y_in_dtype
         return out
 
     @staticmethod
     def backward(ctx, g):
         x, y, gamma = ctx.saved_tensors
         g = _match(g, x)
+        dt = _dt(x)
         b, p, c = _bpc(x)
         dx = torch.empty_like(x)
-        dy = torch.zeros_like(y) if ctx.bcast else torch.empty_like(y)
+        if ctx.bcast:
+            dy, dyb = None, torch.zeros((b, c), dtype=torch.float32, device=x.device)
+        else:
+            dy, dyb = torch.empty_like(y), None
         if ctx.needs_input_grad[2]:
             dgamma, dgamma_ret = _grad_sink(ctx.gamma_param)
         else:
             dgamma, dgamma_ret = None, None
-        call("lb_gate_bwd", ptr(x), ptr(y), ptr(gamma), ptr(g), ptr(dx), ptr(dy), ptr(dgamma), b, p, c, int(ctx.bcast),
-             int(ctx.strict))
+        call("lb_gate_bwd", ptr(x), ptr(y), ptr(gamma), ptr(g), ptr(dx), ptr(dy), ptr(dyb), ptr(dgamma), b, p, c, int(ctx.bcast),
+             int(ctx.strict), dt)
+        if ctx.bcast:
+            dy = _cast(dyb, ctx.y_dtype).view(y.shape)
         return dx, dy, dgamma_ret, None
 
 
 # ------------------------------------------------------------------------------------------
 # softmax
 # ------------------------------------------------------------------------------------------
+def _softmax_work(b, p, c, dev):
+    n = _lib.lib().lb_softmax_pixels_work_floats(b, p, c)
+    return (torch.empty(n, dtype=torch.float32, device=dev), n) if n else (None, 0)
+
+
 class SoftmaxPixelsFn(torch.autograd.Function):
     """Softmax over HW for every (b,c) (attention.py:47 on the [B,F,HW] view)."""
 
@@ -352,7 +416,8 @@ class SoftmaxPixelsFn(torch.autograd.Function):
         x = _as_act(x)
         b, p, c = _bpc(x)
         y = torch.empty_like(x)
-        call("lb_softmax_pixels_fwd", ptr(x), ptr(y), b, p, c)
+        work, n = _softmax_work(b, p, c, x.device)
+        call("lb_softmax_pixels_fwd", ptr(x), ptr(y), b, p, c, ptr(work), n, _dt(x))
         ctx.save_for_backward(y)
         return y
 
@@ -362,7 +427,8 @@ class SoftmaxPixelsFn(torch.autograd.Function):
         g = _match(g, y)
         b, p, c = _bpc(y)
         dx = torch.empty_like(y)
-        call("lb_softmax_pixels_bwd", ptr(y), ptr(g), ptr(dx), b, p, c)
+        work, n = _softmax_work(b, p, c, y.device)
+        call("lb_softmax_pixels_bwd", ptr(y), ptr(g), ptr(dx), b, p, c, ptr(work), n, _dt(y))
         return dx
 
 
@@ -374,7 +440,7 @@ class SoftmaxChannelsFn(torch.autograd.Function):
         x = _as_act(x)
         b, p, c = _bpc(x)
         y = torch.empty_like(x)
-        call("lb_softmax_rows_fwd", ptr(x), ptr(y), b * p, c)
+        call("lb_softmax_rows_fwd", ptr(x), ptr(y), b * p, c, _dt(x))
         ctx.save_for_backward(y)
         return y
 
@@ -384,7 +450,7 @@ class SoftmaxChannelsFn(torch.autograd.Function):
         g = _match(g, y)
         b, p, c = _bpc(y)
         dx = torch.empty_like(y)
-        call("lb_softmax_rows_bwd", ptr(y), ptr(g), ptr(dx), b * p, c)
+        call("lb_softmax_rows_bwd", ptr(y), ptr(g), ptr(dx), b * p, c, _dt(y))
         return dx
 
 
@@ -398,8 +464,8 @@ class FeaturePoolFn(torch.autograd.Function):
     def forward(ctx, x, c_out):
         x = _as_act(x)
         b, c, h, w = x.shape
-        y = _new_act((b, c_out, h, w), x)
-        call("lb_featpool_fwd", ptr(x), ptr(y), b, h, w, c, c_out)
+        y = _new_act((b, c_out, h, w), x, x.dtype)
+        call("lb_featpool_fwd", ptr(x), ptr(y), b, h, w, c, c_out, _dt(x))
         ctx.dims = (b, c, h, w, c_out)
         return y
 
@@ -407,8 +473,8 @@ class FeaturePoolFn(torch.autograd.Function):
     def backward(ctx, g):
         b, c, h, w, c_out = ctx.dims
         g = _as_act(g)
-        dx = _new_act((b, c, h, w), g)
-        call("lb_featpool_bwd", ptr(g), ptr(dx), b, h, w, c, c_out)
+        dx = _new_act((b, c, h, w), g, g.dtype)
+        call("lb_featpool_bwd", ptr(g), ptr(dx), b, h, w, c, c_out, _dt(g))
         return dx, None
 
 
@@ -419,8 +485,8 @@ class Upsample2xFn(torch.autograd.Function):
     def forward(ctx, x):
         x = _as_act(x)
         b, c, h, w = x.shape
-        y = _new_act((b, c, 2 * h, 2 * w), x)
-        call("lb_upsample2x_fwd", ptr(x), ptr(y), b, h, w, c)
+        y = _new_act((b, c, 2 * h, 2 * w), x, x.dtype)
+        call("lb_upsample2x_fwd", ptr(x), ptr(y), b, h, w, c, _dt(x))
         ctx.dims = (b, c, h, w)
         return y
 
@@ -428,8 +494,8 @@ class Upsample2xFn(torch.autograd.Function):
     def backward(ctx, g):
         b, c, h, w = ctx.dims
         g = _as_act(g)
-        dx = _new_act((b, c, h, w), g)
-        call("lb_upsample2x_bwd", ptr(g), ptr(dx), b, h, w, c)
+        dx = _new_act((b, c, h, w), g, g.dtype)
+        call("lb_upsample2x_bwd", ptr(g), ptr(dx), b, h, w, c, _dt(g))
         return dx
 
 
@@ -440,8 +506,8 @@ class AvgPool2Fn(torch.autograd.Function):
     def forward(ctx, x):
         x = _as_act(x)
         b, c, h, w = x.shape
-        y = _new_act((b, c, h // 2, w // 2), x)
-        call("lb_avgpool2_fwd", ptr(x), ptr(y), b, h, w, c)
+        y = _new_act((b, c, h // 2, w // 2), x, x.dtype)
+        call("lb_avgpool2_fwd", ptr(x), ptr(y), b, h, w, c, _dt(x))
         ctx.dims = (b, c, h, w)
         return y
 
@@ -449,9 +515,13 @@ class AvgPool2Fn(torch.autograd.Function):
     def backward(ctx, g):
         b, c, h, w = ctx.dims
         g = _as_act(g)
-        dx = _new_act((b, c, h, w), g)
-        call("lb_avgpool2_bwd", ptr(g), ptr(dx), b, h, w, c)
+        dx = _new_act((b, c, h, w), g, g.dtype)
+        call("lb_avgpool2_bwd", ptr(g), ptr(dx), b, h, w, c, _dt(g))
         return dx
+
+
+def _esz(t):
+    return 2 if t.dtype == torch.bfloat16 else 4
 
 
 class CatFn(torch.autograd.Function):
@@ -464,22 +534,22 @@ class CatFn(torch.autograd.Function):
         ca, cb = a.shape[1], b.shape[1]
         rows = a.numel() // ca
         out = _new_act((a.shape[0], ca + cb, *a.shape[2:]), a)
-        call("lb_copy_rows", ptr(a), ca, ptr(out), ca + cb, rows, ca, 0)
-        call("lb_copy_rows", ptr(b), cb, out.data_ptr() + 4 * ca, ca + cb, rows, cb, 0)
-        ctx.meta = (ca, cb, rows, tuple(a.shape), tuple(b.shape))
+        call("lb_copy_rows", ptr(a), ca, ptr(out), ca + cb, rows, ca, 0, _dt(a), _dt(out))
+        call("lb_copy_rows", ptr(b), cb, out.data_ptr() + _esz(out) * ca, ca + cb, rows, cb, 0, _dt(b), _dt(out))
+        ctx.meta = (ca, cb, rows, tuple(a.shape), tuple(b.shape), a.dtype, b.dtype)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        ca, cb, rows, sa, sb = ctx.meta
+        ca, cb, rows, sa, sb, da_t, db_t = ctx.meta
         g = _as_act(g)
         da = db = None
         if ctx.needs_input_grad[0]:
-            da = _new_act(sa, g)
-            call("lb_copy_rows", ptr(g), ca + cb, ptr(da), ca, rows, ca, 0)
+            da = _new_act(sa, g, da_t)
+            call("lb_copy_rows", ptr(g), ca + cb, ptr(da), ca, rows, ca, 0, _dt(g), _dt(da))
         if ctx.needs_input_grad[1]:
-            db = _new_act(sb, g)
-            call("lb_copy_rows", g.data_ptr() + 4 * ca, ca + cb, ptr(db), cb, rows, cb, 0)
+            db = _new_act(sb, g, db_t)
+            call("lb_copy_rows", g.data_ptr() + _esz(g) * ca, ca + cb, ptr(db), cb, rows, cb, 0, _dt(g), _dt(db))
         return da, db
 
 

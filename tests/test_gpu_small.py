@@ -1,5 +1,7 @@
-"""Direct fp32 kernels for tiny-channel layers (lb_conv_small / lb_conv_small_wgrad) against the fp32 SIMT gather-GEMM
-(lb_conv_gemm / lb_conv_wgrad) with the fused RootTanh / RootTanh' applied by torch on the reference side."""
+"""Direct kernels for tiny-channel layers (lb_conv_small / lb_conv_small_wgrad) against the fp32 SIMT gather-GEMM
+(lb_conv_gemm / lb_conv_wgrad) with the fused RootTanh / RootTanh' applied by torch on the reference side.  The narrow
+side (<= 4 channels) is always fp32; the wide side is stored as fp32 or bf16 (`wide`): the bf16 cases feed both kernels
+the same bf16-rounded operand, so only the output rounding differs."""
 import ctypes
 
 import pytest
@@ -46,9 +48,13 @@ CASES = {
 }
 
 
+F32, BF16 = 0, 1
+
+
+@pytest.mark.parametrize("wide", [F32, BF16])
 @pytest.mark.parametrize("fuse", ["plain", "act_in", "dact_out"])
 @pytest.mark.parametrize("name", sorted(CASES))
-def test_small_matches_simt(name, fuse):
+def test_small_matches_simt(name, fuse, wide):
     kind, b, h, w, cin, cout, k, s, p, direction = CASES[name]
     gen = torch.Generator().manual_seed(hash(name) % 1000)
     t = k * k
@@ -72,23 +78,32 @@ def test_small_matches_simt(name, fuse):
         out_shape = (b, h, w, cin + pad_out)
     n = g.out_c
     assert _lib.lib().lb_conv_small_supported(ctypes.byref(g)) == 1
+    in_wide, out_wide = g.in_c > 4, g.in_c <= 4            # which side carries the `wide` storage type
+    if wide == BF16 and g.in_c <= 4 and g.out_c <= 4:
+        pytest.skip("both sides narrow: an all-fp32 layer")
+    src_k = src.bfloat16() if (wide == BF16 and in_wide) else src
+    src = src_k.float()
     alpha = torch.tensor([0.37], device=DEV)
     bias = torch.randn(n, generator=gen).to(DEV)
     ref = torch.full(out_shape, -7.0, device=DEV)
-    got = torch.full(out_shape, -7.0, device=DEV)
+    got = torch.full(out_shape, -7.0, device=DEV, dtype=torch.bfloat16 if (wide == BF16 and out_wide) else torch.float32)
     src_ref = roottanh(src) if fuse == "act_in" else src
     call("lb_conv_gemm", ptr(src_ref.contiguous()), ptr(wt), ptr(alpha), ptr(bias), ptr(ref), ctypes.byref(g))
     xpre = None
     if fuse == "dact_out":
         xpre = 2.0 * torch.randn(out_shape[:3] + (n,), generator=gen).to(DEV)
-        ref[..., :n] *= roottanh_grad(xpre)
-    call("lb_conv_small", ptr(src), ptr(wt), ptr(alpha), ptr(bias), ptr(got), ctypes.byref(g), 4 if fuse == "act_in" else 0,
-         ptr(xpre), n, 4 if fuse == "dact_out" else 0, 0)
+        if wide == BF16 and out_wide:
+            xpre = xpre.bfloat16()
+        ref[..., :n] *= roottanh_grad(xpre.float())
+    call("lb_conv_small", ptr(src_k), ptr(wt), ptr(alpha), ptr(bias), ptr(got), ctypes.byref(g), 4 if fuse == "act_in" else 0,
+         ptr(xpre), n, 4 if fuse == "dact_out" else 0, 0, wide)
     torch.cuda.synchronize()
+    got = got.float()
     assert torch.equal(got[..., n:], ref[..., n:]), "wrote outside its channel slice"
-    err = (got - ref).abs().max().item()
+    err = (got - ref)[..., :n].abs().max().item()
     scale = ref[..., :n].abs().max().item()
-    assert err <= 1e-4 * scale + 1e-5, f"{name}/{fuse}: max err {err:.3e} vs scale {scale:.3e}"
+    tol = 8e-3 if got.dtype != ref.dtype or (wide == BF16 and out_wide) else 1e-4
+    assert err <= tol * scale + 1e-5, f"{name}/{fuse}: max err {err:.3e} vs scale {scale:.3e}"
 
 
 WG_CASES = {
@@ -102,9 +117,10 @@ WG_CASES = {
 }
 
 
+@pytest.mark.parametrize("wide", [F32, BF16])
 @pytest.mark.parametrize("act", [0, 4])
 @pytest.mark.parametrize("name", sorted(WG_CASES))
-def test_small_wgrad_matches_simt(name, act):
+def test_small_wgrad_matches_simt(name, act, wide):
     kind, b, h, w, cin, cout, k, s, p = WG_CASES[name]
     gen = torch.Generator().manual_seed(hash(name) % 1000)
     t = k * k
@@ -123,11 +139,20 @@ def test_small_wgrad_matches_simt(name, act):
         g = geom(b, oh, ow, cout, h, w, cin, k, k, s, p, 0, cout, cin, (t, cout * t, k, 1))
         shape = (cin, cout, k, k)
     assert _lib.lib().lb_conv_small_wgrad_supported(ctypes.byref(g)) == 1
+    dense_wide = k == 1 and s == 1 and p == 0 and g.in_c <= 4     # else the gathered operand is the wide one
+    gath_k, dense_k = gathered, dense
+    if wide == BF16:
+        if g.in_c <= 4 and g.out_c <= 4:
+            pytest.skip("both operands narrow: all fp32")
+        if dense_wide:
+            dense_k = dense.bfloat16(); dense = dense_k.float()
+        else:
+            gath_k = gathered.bfloat16(); gathered = gath_k.float()
     ref = torch.zeros(shape, device=DEV)
     got = torch.zeros(shape, device=DEV)
     gath_ref = (roottanh(gathered) if act else gathered).contiguous()
     call("lb_conv_wgrad", ptr(gath_ref), ptr(dense), ptr(ref), ctypes.byref(g))
-    call("lb_conv_small_wgrad", ptr(gathered), ptr(dense), ptr(got), ctypes.byref(g), act)
+    call("lb_conv_small_wgrad", ptr(gath_k), ptr(dense_k), ptr(got), ctypes.byref(g), act, wide)
     torch.cuda.synchronize()
     err = (got - ref).abs().max().item()
     scale = ref.abs().max().item()
@@ -148,11 +173,16 @@ def test_small_fused_cat(b, h, w, cin, cout):
     got = torch.full((b, h, w, ctot), -7.0, device=DEV)
     call("lb_conv_gemm", ptr(x), ptr(wt), ptr(alpha), ptr(bias), ref.data_ptr() + 4 * cin, ctypes.byref(g))
     ref[..., :cin] = x
-    call("lb_conv_small", ptr(x), ptr(wt), ptr(alpha), ptr(bias), ptr(got), ctypes.byref(g), 0, None, 0, 0, 1)
+    call("lb_conv_small", ptr(x), ptr(wt), ptr(alpha), ptr(bias), ptr(got), ctypes.byref(g), 0, None, 0, 0, 1, F32)
     torch.cuda.synchronize()
     assert torch.equal(got[..., :cin], x)
     err = (got - ref).abs().max().item()
     assert err <= 1e-4 * ref.abs().max().item() + 1e-5
+    # the same rows stored as bf16 (the tensor-core configuration: the concat output is a wide, bf16 tensor)
+    got16 = torch.full((b, h, w, ctot), -7.0, device=DEV, dtype=torch.bfloat16)
+    call("lb_conv_small", ptr(x), ptr(wt), ptr(alpha), ptr(bias), ptr(got16), ctypes.byref(g), 0, None, 0, 0, 1, BF16)
+    torch.cuda.synchronize()
+    assert (got16.float() - ref).abs().max().item() <= 8e-3 * ref.abs().max().item() + 1e-5
 
 
 def test_small_wgrad_concat_slice():
@@ -167,7 +197,16 @@ def test_small_wgrad_concat_slice():
     got = torch.zeros((cout, cin, 1, 1), device=DEV)
     dense_ptr = gfull.data_ptr() + 4 * cin
     call("lb_conv_wgrad", ptr(x), dense_ptr, ptr(ref), ctypes.byref(g))
-    call("lb_conv_small_wgrad", ptr(x), dense_ptr, ptr(got), ctypes.byref(g), 0)
+    call("lb_conv_small_wgrad", ptr(x), dense_ptr, ptr(got), ctypes.byref(g), 0, F32)
     torch.cuda.synchronize()
     err = (got - ref).abs().max().item()
     assert err <= 2e-4 * ref.abs().max().item() + 1e-5
+    # bf16 gradient rows: the slice starts 6 bytes into 64-byte rows (4-element loads with a 3-element shift)
+    g16 = gfull.bfloat16()
+    ref16 = torch.zeros((cout, cin, 1, 1), device=DEV)
+    got16 = torch.zeros((cout, cin, 1, 1), device=DEV)
+    gf = g16.float()
+    call("lb_conv_wgrad", ptr(x), gf.data_ptr() + 4 * cin, ptr(ref16), ctypes.byref(g))
+    call("lb_conv_small_wgrad", ptr(x), g16.data_ptr() + 2 * cin, ptr(got16), ctypes.byref(g), 0, BF16)
+    torch.cuda.synchronize()
+    assert (got16 - ref16).abs().max().item() <= 2e-4 * ref16.abs().max().item() + 1e-5

@@ -169,7 +169,7 @@ EX_CASES.update({
     "1x1_c416": ("convT", 4, 1, 1, 192, 416, 1, 1, 0, "fwd"),
     "featattn_dgrad": ("conv", 6, 16, 16, 64, 16, 16, 1, 0, "dgrad"),     # full-extent kernel: 2 live taps of 16 per tile
 })
-EX_MODES = ["o32", "o16", "o16act", "both_aux", "o16_aux"]
+EX_MODES = ["o32", "o16", "o16act", "o16both", "both_aux", "o16_aux", "o16_aux16"]
 
 
 @pytest.mark.parametrize("mode", EX_MODES)
@@ -206,22 +206,29 @@ def test_tc_ex_matches_v1(name, mode):
     ref = ref[..., :n]
 
     want32 = mode in ("o32", "both_aux")
-    want16 = mode != "o32"
-    use_aux = mode.endswith("aux")
+    want16 = mode in ("o16", "o16both", "both_aux", "o16_aux", "o16_aux16")       # bf16 of the accumulator
+    want16a = mode in ("o16act", "o16both")                                        # bf16 of RootTanh(accumulator)
+    use_aux = "aux" in mode
+    aux16 = mode.endswith("aux16")
     ld16 = (n + 7) // 8 * 8 + 8
-    ld_aux = (n + 3) // 4 * 4 + 4
+    ld_aux = ((n + 7) // 8 * 8 + 8) if aux16 else ((n + 3) // 4 * 4 + 4)
     got32 = torch.full(out_shape, -7.0, device=DEV) if want32 else None
     got16 = torch.full(out_shape[:3] + (ld16,), -7.0, device=DEV, dtype=torch.bfloat16) if want16 else None
+    got16a = torch.full(out_shape[:3] + (ld16,), -7.0, device=DEV, dtype=torch.bfloat16) if want16a else None
     aux = None
     if use_aux:
         aux = torch.full(out_shape[:3] + (ld_aux,), float("nan"), device=DEV)
         aux[..., :n] = 2.0 * torch.randn(out_shape[:3] + (n,), generator=gen).to(DEV)
-    if _lib.lib().lb_conv_tc_ex_supported(ctypes.byref(g), ld16 if want16 else 0, ld_aux if use_aux else 0) != 1:
+        if aux16:
+            aux = aux.bfloat16()
+    any16 = want16 or want16a
+    if _lib.lib().lb_conv_tc_ex_supported(ctypes.byref(g), int(want32), ld16 if any16 else 0, ld_aux if use_aux else 0,
+                                          1 if aux16 else 0) != 1:
         pytest.skip("weight-bound shape: stays on the split-K path of k_conv_tc")
-    call("lb_conv_tc_gemm_ex", ptr(src), ptr(packed), ptr(alpha), ptr(bias), ptr(got32), ptr(got16), ld16 if want16 else 0,
-         1 if mode == "o16act" else 0, ptr(aux), ld_aux if use_aux else 0, ctypes.byref(g))
+    call("lb_conv_tc_gemm_ex", ptr(src), ptr(packed), ptr(alpha), ptr(bias), ptr(got32), ptr(got16), ptr(got16a),
+         ld16 if any16 else 0, ptr(aux), ld_aux if use_aux else 0, 1 if aux16 else 0, ctypes.byref(g))
     torch.cuda.synchronize()
-    exp = ref * _roottanh_grad(aux[..., :n]) if use_aux else ref
+    exp = ref * _roottanh_grad(aux[..., :n].float()) if use_aux else ref
     scale = exp.abs().max().item()
     if want32:
         assert torch.all(got32[..., n:] == -7.0), "fp32 store outside its channel slice"
@@ -229,14 +236,28 @@ def test_tc_ex_matches_v1(name, mode):
         assert err <= 2e-4 * scale + 1e-5, f"{name}/{mode}: fp32 max err {err:.3e} vs scale {scale:.3e}"
     if want16:
         assert torch.all(got16[..., n:].float() == -7.0), "bf16 store outside its channel slice"
-        exp16 = _roottanh(exp) if mode == "o16act" else exp
-        err = (got16[..., :n].float() - exp16).abs().max().item()
-        assert err <= 6e-3 * exp16.abs().max().item() + 1e-5, f"{name}/{mode}: bf16 max err {err:.3e}"
+        err = (got16[..., :n].float() - exp).abs().max().item()
+        assert err <= 6e-3 * scale + 1e-5, f"{name}/{mode}: bf16 max err {err:.3e}"
+    if want16a:
+        assert torch.all(got16a[..., n:].float() == -7.0), "bf16 (activated) store outside its channel slice"
+        # with a stored pre-activation the function value belongs to the STORED (bf16-rounded) argument
+        arg = got16[..., :n].float() if want16 else exp
+        exp16 = _roottanh(arg)
+        err = (got16a[..., :n].float() - exp16).abs().max().item()
+        assert err <= 6e-3 * exp16.abs().max().item() + 1e-5, f"{name}/{mode}: activated bf16 max err {err:.3e}"
 
 
-@pytest.mark.parametrize("name", ["convT4", "convT4_many", "3x3_48", "1x1_many", "5x5s2_c32", "convT4_c192"])
-def test_tc_ex_resident_weights(name, monkeypatch):
-    """LB_TC2_RESIDENT=1: the weights of one output phase stay in shared memory (opt-in variant of the persistent kernel)."""
-    monkeypatch.setenv("LB_TC2_RESIDENT", "1")
-    test_tc_ex_matches_v1(name, "both_aux")
-    test_tc_ex_matches_v1(name, "o16act")
+def test_tc_ex_resident_weights():
+    """LB_TC2_RESIDENT=1: the weights of one output phase stay in shared memory (opt-in variant of the persistent kernel).
+    The library reads its debugging switches once per process, so the variant runs in a child process."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("LB_TC2_RESIDENT"):
+        pytest.skip("already inside the resident-weights child run")
+    env = dict(os.environ, LB_TC2_RESIDENT="1")
+    sel = "test_tc_ex_matches_v1 and (convT4 or 3x3_48 or 1x1_many or 5x5s2_c32) and (both_aux or o16both)"
+    res = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k", sel,
+                          "-p", "no:cacheprovider"], env=env, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
+    assert " passed" in res.stdout
