@@ -84,7 +84,7 @@ __device__ __forceinline__ T lb_block_sum(T v, T* scratch) {
 // stores its pair, the last CTA to arrive (integer ticket) adds all pairs in index order with a fixed tree.
 //   work[0]: ticket (low 32 bits; 0 on entry, left 0 on exit), work[1 + 2*cta], work[2 + 2*cta]: the pairs.
 // `s1`, `s2` are the CTA totals held by thread 0; out[2] receives the grid totals.  Call from all threads of the CTA.
-#define LB_STAT_WORK_DOUBLES 2048      // 1 + 2 * (largest statistics grid = LB_SMS * 4), rounded up
+#define LB_STAT_WORK_DOUBLES 4096      // 1 + 2 * (largest statistics grid = LB_SMS * 8), rounded up
 __device__ __forceinline__ void lb_grid_sum2_ordered(double s1, double s2, double* __restrict__ work, double* __restrict__ out,
                                                      double* scratch) {
   __shared__ int s_last;
@@ -139,6 +139,52 @@ __device__ __forceinline__ float lb_ld1(const float* p) { return __ldg(p); }
 __device__ __forceinline__ float lb_ld1(const lb_bf16* p) { return __bfloat162float(*p); }
 __device__ __forceinline__ void lb_st1(float* p, float v) { *p = v; }
 __device__ __forceinline__ void lb_st1(lb_bf16* p, float v) { *p = __float2bfloat16(v); }
+// One 16-byte access per thread whatever the storage type: 4 floats or 8 bf16.  (With 8-byte accesses the bf16 kernels
+// had half the bytes in flight of their fp32 versions and ran no faster: latency-bound, not bandwidth-bound.)
+template <typename T> struct LbV;
+template <> struct LbV<float> { static constexpr int N = 4; };
+template <> struct LbV<lb_bf16> { static constexpr int N = 8; };
+__device__ __forceinline__ void lb_ldv(const float* p, float (&v)[4]) {
+  const float4 r = __ldg(reinterpret_cast<const float4*>(p));
+  v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w;
+}
+__device__ __forceinline__ void lb_ldv(const lb_bf16* p, float (&v)[8]) {
+  const uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void lb_stv(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void lb_stv(lb_bf16* p, const float (&v)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    w[i] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+// N consecutive fp32 parameters (per-channel gain / bias) for an N-wide activation vector
+template <int N>
+__device__ __forceinline__ void lb_ldf(const float* p, float (&v)[N]) {
+#pragma unroll
+  for (int i = 0; i < N; i += 4) {
+    const float4 r = __ldg(reinterpret_cast<const float4*>(p + i));
+    v[i] = r.x; v[i + 1] = r.y; v[i + 2] = r.z; v[i + 3] = r.w;
+  }
+}
+// value as it will be read back from storage T (bf16 rounding; identity for fp32)
+template <typename T> __device__ __forceinline__ float lb_round_as(float v);
+template <> __device__ __forceinline__ float lb_round_as<float>(float v) { return v; }
+template <> __device__ __forceinline__ float lb_round_as<lb_bf16>(float v) { return __bfloat162float(__float2bfloat16(v)); }
+template <typename T>
+__host__ __device__ static inline bool lb_vec_ok(const T* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 // is a 4-element access at p aligned?
 template <typename T>
 __host__ __device__ static inline bool lb_vec4_ok(const T* p) { return (reinterpret_cast<uintptr_t>(p) & (4 * sizeof(T) - 1)) == 0; }

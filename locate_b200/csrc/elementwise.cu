@@ -14,26 +14,33 @@ extern "C" void lb_reset_launch_count(void) { g_lb_launches = 0; }
 // ------------------------------------------------------------------------------------------
 template <typename T, typename F>
 __global__ void __launch_bounds__(256) k_unary(const T* __restrict__ x, T* __restrict__ y, size_t n, F f) {
+  constexpr int N = LbV<T>::N;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  const size_t n4 = n >> 2;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    float4 v = lb_ld4(x + 4 * i);
-    v.x = f(v.x); v.y = f(v.y); v.z = f(v.z); v.w = f(v.w);
-    lb_st4(y + 4 * i, v);
+  const size_t nv = n / N;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+    float v[N];
+    lb_ldv(x + N * i, v);
+#pragma unroll
+    for (int k = 0; k < N; ++k) v[k] = f(v[k]);
+    lb_stv(y + N * i, v);
   }
-  for (size_t i = (n4 << 2) + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) lb_st1(y + i, f(lb_ld1(x + i)));
+  for (size_t i = nv * N + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) lb_st1(y + i, f(lb_ld1(x + i)));
 }
 
 template <typename T, typename F>
 __global__ void __launch_bounds__(256) k_binary(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ y, size_t n, F f) {
+  constexpr int N = LbV<T>::N;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  const size_t n4 = n >> 2;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    float4 u = lb_ld4(a + 4 * i), v = lb_ld4(b + 4 * i), r;
-    r.x = f(u.x, v.x); r.y = f(u.y, v.y); r.z = f(u.z, v.z); r.w = f(u.w, v.w);
-    lb_st4(y + 4 * i, r);
+  const size_t nv = n / N;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+    float u[N], v[N];
+    lb_ldv(a + N * i, u);
+    lb_ldv(b + N * i, v);
+#pragma unroll
+    for (int k = 0; k < N; ++k) u[k] = f(u[k], v[k]);
+    lb_stv(y + N * i, u);
   }
-  for (size_t i = (n4 << 2) + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+  for (size_t i = nv * N + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
     lb_st1(y + i, f(lb_ld1(a + i), lb_ld1(b + i)));
 }
 
@@ -53,8 +60,8 @@ template <typename T, typename F>
 static int launch_unary_t(const T* x, T* y, size_t n, F f, lb_stream_t s) {
   LB_REQUIRE(x && y);
   if (n == 0) return LB_OK;
-  if (lb_vec4_ok(x) && lb_vec4_ok(y)) {
-    k_unary<<<lb_grid_1d((n + 3) / 4, 256), 256, 0, lb_s(s)>>>(x, y, n, f);
+  if (lb_vec_ok(x) && lb_vec_ok(y)) {
+    k_unary<<<lb_grid_1d((n + LbV<T>::N - 1) / LbV<T>::N, 256), 256, 0, lb_s(s)>>>(x, y, n, f);
   } else {
     k_unary_s<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(x, y, n, f);
   }
@@ -65,8 +72,8 @@ template <typename T, typename F>
 static int launch_binary_t(const T* a, const T* b, T* y, size_t n, F f, lb_stream_t s) {
   LB_REQUIRE(a && b && y);
   if (n == 0) return LB_OK;
-  if (lb_vec4_ok(a) && lb_vec4_ok(b) && lb_vec4_ok(y)) {
-    k_binary<<<lb_grid_1d((n + 3) / 4, 256), 256, 0, lb_s(s)>>>(a, b, y, n, f);
+  if (lb_vec_ok(a) && lb_vec_ok(b) && lb_vec_ok(y)) {
+    k_binary<<<lb_grid_1d((n + LbV<T>::N - 1) / LbV<T>::N, 256), 256, 0, lb_s(s)>>>(a, b, y, n, f);
   } else {
     k_binary_s<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(a, b, y, n, f);
   }
@@ -184,51 +191,54 @@ extern "C" int lb_gate_fwd(const void* x, const void* y, const float* gamma, voi
 // output feeds a whole-tensor norm (block.py:46-51), whose statistics pass would otherwise re-read the tensor just written.
 template <typename T>
 __global__ void __launch_bounds__(256) k_gate_fwd_stats(const T* __restrict__ x, const T* __restrict__ y,
-                                                       const float* __restrict__ gamma, T* __restrict__ out, int n4,
-                                                       LbFastDiv d_pc4, LbFastDiv d_c4, int channels, int y_bcast,
+                                                       const float* __restrict__ gamma, T* __restrict__ out, int nv,
+                                                       LbFastDiv d_pcv, LbFastDiv d_cv, int channels, int y_bcast,
                                                        double* __restrict__ sums, double* __restrict__ work) {
+  constexpr int N = LbV<T>::N;
   __shared__ double scratch[32];
   const float gm = __ldg(gamma);
   const int stride = gridDim.x * blockDim.x;
   double s1 = 0.0, s2 = 0.0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    const float4 a = lb_ld4(x + 4 * (size_t)i);
-    float4 b;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+    float a[N], b[N];
+    lb_ldv(x + (size_t)N * i, a);
     if (y_bcast) {
-      int bi, rem, q, c4;
-      lb_fast_divmod(d_pc4, i, bi, rem);
-      lb_fast_divmod(d_c4, rem, q, c4);
-      b = lb_ld4(y + (size_t)bi * channels + 4 * c4);
+      int bi, rem, q, cv;
+      lb_fast_divmod(d_pcv, i, bi, rem);
+      lb_fast_divmod(d_cv, rem, q, cv);
+      lb_ldv(y + (size_t)bi * channels + N * cv, b);
     } else {
-      b = lb_ld4(y + 4 * (size_t)i);
+      lb_ldv(y + (size_t)N * i, b);
     }
-    float4 r;
-    r.x = fmaf(gm, b.x, 1.0f) * a.x; r.y = fmaf(gm, b.y, 1.0f) * a.y;
-    r.z = fmaf(gm, b.z, 1.0f) * a.z; r.w = fmaf(gm, b.w, 1.0f) * a.w;
-    lb_st4(out + 4 * (size_t)i, r);
-    if (sizeof(T) == 2) {                       // statistics of what the norm will read back
-      r.x = __bfloat162float(__float2bfloat16(r.x)); r.y = __bfloat162float(__float2bfloat16(r.y));
-      r.z = __bfloat162float(__float2bfloat16(r.z)); r.w = __bfloat162float(__float2bfloat16(r.w));
+    float p1 = 0.0f, p2 = 0.0f;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      a[k] = fmaf(gm, b[k], 1.0f) * a[k];
+      const float r = lb_round_as<T>(a[k]);     // statistics of what the norm will read back
+      p1 += r;
+      p2 = fmaf(r, r, p2);
     }
-    s1 += (double)((r.x + r.y) + (r.z + r.w));
-    s2 += (double)(fmaf(r.x, r.x, r.y * r.y) + fmaf(r.z, r.z, r.w * r.w));
+    lb_stv(out + (size_t)N * i, a);
+    s1 += (double)p1;
+    s2 += (double)p2;
   }
   s1 = lb_block_sum(s1, scratch);
   s2 = lb_block_sum(s2, scratch);
   lb_grid_sum2_ordered(s1, s2, work, sums, scratch);
 }
-// sums[2] (fp64) = (sum out, sum out^2), reduced in a fixed order (work: see lb_norm_stats).  Needs channels % 4 == 0 and
-// aligned pointers (LB_EALIGN otherwise: use lb_gate_fwd + lb_norm_stats).
+// sums[2] (fp64) = (sum out, sum out^2), reduced in a fixed order (work: see lb_norm_stats).  Needs channels % (16 bytes of
+// elements) == 0 and 16-byte aligned pointers (LB_EALIGN otherwise: use lb_gate_fwd + lb_norm_stats).
 extern "C" int lb_gate_fwd_stats(const void* x, const void* y, const float* gamma, void* out, double* sums, double* work,
                                  int batch, int pixels, int channels, int y_bcast, int dtype, lb_stream_t s) {
   LB_REQUIRE(x && y && gamma && out && sums && work && batch > 0 && pixels > 0 && channels > 0);
   const size_t n = (size_t)batch * pixels * channels;
-  if ((channels & 3) || n / 4 >= ((size_t)1 << 31) - ((size_t)1 << 24)) return LB_EALIGN;
   LB_DISPATCH(dtype, T, {
-    if (!lb_vec4_ok(lb_cp<T>(x)) || !lb_vec4_ok(lb_cp<T>(y)) || !lb_vec4_ok(lb_cp<T>(out))) return LB_EALIGN;
-    k_gate_fwd_stats<<<lb_grid_1d(n / 4, 256, 4), 256, 0, lb_s(s)>>>(lb_cp<T>(x), lb_cp<T>(y), gamma, lb_p<T>(out), (int)(n / 4),
-                                                                    lb_make_fastdiv((uint32_t)((size_t)pixels * channels / 4)),
-                                                                    lb_make_fastdiv(channels / 4), channels, y_bcast, sums, work);
+    constexpr int N = LbV<T>::N;
+    if ((channels % N) || n / N >= ((size_t)1 << 31) - ((size_t)1 << 24)) return LB_EALIGN;
+    if (!lb_vec_ok(lb_cp<T>(x)) || !lb_vec_ok(lb_cp<T>(y)) || !lb_vec_ok(lb_cp<T>(out))) return LB_EALIGN;
+    k_gate_fwd_stats<<<lb_grid_1d(n / N, 256, 8), 256, 0, lb_s(s)>>>(lb_cp<T>(x), lb_cp<T>(y), gamma, lb_p<T>(out), (int)(n / N),
+                                                                    lb_make_fastdiv((uint32_t)((size_t)pixels * channels / N)),
+                                                                    lb_make_fastdiv(channels / N), channels, y_bcast, sums, work);
   });
   LB_LAUNCH_CHECK();
   return LB_OK;
@@ -275,22 +285,28 @@ __global__ void k_gate_bwd(const T* __restrict__ x, const T* __restrict__ y, con
 template <typename T>
 __global__ void __launch_bounds__(256) k_gate_bwd4(const T* __restrict__ x, const T* __restrict__ y, const float* __restrict__ gamma,
                                                   const T* __restrict__ g, T* __restrict__ dx, T* __restrict__ dy,
-                                                  float* __restrict__ dgamma, size_t n4, int strict) {
+                                                  float* __restrict__ dgamma, size_t nv, int strict) {
+  constexpr int N = LbV<T>::N;
   __shared__ float scratch[32];
   const float gm = __ldg(gamma);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   float acc = 0.0f;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    const float4 xv = lb_ld4(x + 4 * i), yv = lb_ld4(y + 4 * i), gv = lb_ld4(g + 4 * i);
-    float4 a, b;
-    a.x = fmaf(gm, yv.x, 1.0f) * gv.x; a.y = fmaf(gm, yv.y, 1.0f) * gv.y;
-    a.z = fmaf(gm, yv.z, 1.0f) * gv.z; a.w = fmaf(gm, yv.w, 1.0f) * gv.w;
-    const float4 xg = make_float4(xv.x * gv.x, xv.y * gv.y, xv.z * gv.z, xv.w * gv.w);
-    b.x = xg.x * gm; b.y = xg.y * gm; b.z = xg.z * gm; b.w = xg.w * gm;
-    lb_st4(dx + 4 * i, a);
-    lb_st4(dy + 4 * i, b);
-    const float4 m = strict ? xv : yv;
-    acc += fmaf(xg.x, m.x, xg.y * m.y) + fmaf(xg.z, m.z, xg.w * m.w);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+    float xv[N], yv[N], gv[N];
+    lb_ldv(x + N * i, xv);
+    lb_ldv(y + N * i, yv);
+    lb_ldv(g + N * i, gv);
+    float part = 0.0f;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const float xg = xv[k] * gv[k];
+      part = fmaf(xg, strict ? xv[k] : yv[k], part);
+      yv[k] = fmaf(gm, yv[k], 1.0f) * gv[k];      // dx
+      xv[k] = xg * gm;                           // dy
+    }
+    lb_stv(dx + N * i, yv);
+    lb_stv(dy + N * i, xv);
+    acc += part;
   }
   if (dgamma) {
     const float tot = lb_block_sum(acc, scratch);
@@ -302,8 +318,8 @@ template <typename T>
 static int gate_bwd_t(const T* x, const T* y, const float* gamma, const T* g, T* dx, T* dy, float* dy_bcast, float* dgamma, int batch,
                       int pixels, int channels, int y_bcast, int strict_reference, lb_stream_t s) {
   const size_t n = (size_t)batch * pixels * channels;
-  if (!y_bcast && !(n & 3) && lb_vec4_ok(x) && lb_vec4_ok(y) && lb_vec4_ok(g) && lb_vec4_ok(dx) && lb_vec4_ok(dy)) {
-    k_gate_bwd4<<<lb_grid_1d(n / 4, 256, 4), 256, 0, lb_s(s)>>>(x, y, gamma, g, dx, dy, dgamma, n / 4, strict_reference);
+  if (!y_bcast && !(n % LbV<T>::N) && lb_vec_ok(x) && lb_vec_ok(y) && lb_vec_ok(g) && lb_vec_ok(dx) && lb_vec_ok(dy)) {
+    k_gate_bwd4<<<lb_grid_1d(n / LbV<T>::N, 256, 8), 256, 0, lb_s(s)>>>(x, y, gamma, g, dx, dy, dgamma, n / LbV<T>::N, strict_reference);
     LB_LAUNCH_CHECK();
     return LB_OK;
   }

@@ -12,13 +12,18 @@ __global__ void __launch_bounds__(256) k_norm_stats(const T* __restrict__ x, siz
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   double s1 = 0.0, s2 = 0.0;
   if (vec) {
-    const size_t n4 = n >> 2;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-      const float4 v = lb_ld4(x + 4 * i);
-      s1 += (double)((v.x + v.y) + (v.z + v.w));
-      s2 += (double)(fmaf(v.x, v.x, v.y * v.y) + fmaf(v.z, v.z, v.w * v.w));
+    constexpr int N = LbV<T>::N;
+    const size_t nv = n / N;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+      float v[N];
+      lb_ldv(x + N * i, v);
+      float p1 = 0.0f, p2 = 0.0f;
+#pragma unroll
+      for (int k = 0; k < N; ++k) { p1 += v[k]; p2 = fmaf(v[k], v[k], p2); }
+      s1 += (double)p1;
+      s2 += (double)p2;
     }
-    for (size_t i = (n4 << 2) + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    for (size_t i = nv * N + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
       const float v = lb_ld1(x + i);
       s1 += v; s2 += (double)v * v;
     }
@@ -37,8 +42,8 @@ extern "C" size_t lb_stat_work_doubles(void) { return LB_STAT_WORK_DOUBLES; }
 
 extern "C" int lb_norm_stats(const void* x, size_t n, double* sums, double* work, int dtype, lb_stream_t s) {
   LB_REQUIRE(x && sums && work && n > 0);
-  LB_DISPATCH(dtype, T, k_norm_stats<<<lb_grid_1d((n + 3) / 4, 256, 4), 256, 0, lb_s(s)>>>(lb_cp<T>(x), n, sums, work,
-                                                                                          lb_vec4_ok(lb_cp<T>(x)) ? 1 : 0));
+  LB_DISPATCH(dtype, T, k_norm_stats<<<lb_grid_1d((n + 3) / 4, 256, 8), 256, 0, lb_s(s)>>>(lb_cp<T>(x), n, sums, work,
+                                                                                          lb_vec_ok(lb_cp<T>(x)) ? 1 : 0));
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
@@ -65,30 +70,26 @@ extern "C" int lb_norm_finalize(const double* sums, double n_total, float* stats
 template <typename T, bool kAct>
 __global__ void __launch_bounds__(256) k_norm_apply4(const T* __restrict__ x, const float* __restrict__ stats,
                                                     const float* __restrict__ gain, int gain_bs, const float* __restrict__ bias,
-                                                    T* __restrict__ y, T* __restrict__ act, size_t n4, LbFastDiv d_pc4, LbFastDiv d_c4) {
+                                                    T* __restrict__ y, T* __restrict__ act, size_t nv, LbFastDiv d_pcv, LbFastDiv d_cv) {
+  constexpr int N = LbV<T>::N;
   const float mean = __ldg(stats), rstd = __ldg(stats + 2);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
     int b, rem, q, c;
-    lb_fast_divmod(d_pc4, (int)i, b, rem);      // n4 < 2^31 (checked by the host)
-    lb_fast_divmod(d_c4, rem, q, c);
-    c *= 4;
-    const float4 v = lb_ld4(x + 4 * i);
-    const float4 gn = lb_ld4(gain + (size_t)b * gain_bs + c);
-    const float4 bs = lb_ld4(bias + c);
-    float4 r;
-    r.x = fmaf((v.x - mean) * rstd, gn.x, bs.x);
-    r.y = fmaf((v.y - mean) * rstd, gn.y, bs.y);
-    r.z = fmaf((v.z - mean) * rstd, gn.z, bs.z);
-    r.w = fmaf((v.w - mean) * rstd, gn.w, bs.w);
-    if (y) lb_st4(y + 4 * i, r);
+    lb_fast_divmod(d_pcv, (int)i, b, rem);      // nv < 2^31 (checked by the host)
+    lb_fast_divmod(d_cv, rem, q, c);
+    c *= N;
+    float v[N], gn[N], bs[N];
+    lb_ldv(x + N * i, v);
+    lb_ldf<N>(gain + (size_t)b * gain_bs + c, gn);
+    lb_ldf<N>(bias + c, bs);
+#pragma unroll
+    for (int k = 0; k < N; ++k) v[k] = fmaf((v[k] - mean) * rstd, gn[k], bs[k]);
+    if (y) lb_stv(y + N * i, v);
     if (kAct) {
-      if (sizeof(T) == 2) {                     // the backward evaluates RootTanh' at the STORED (rounded) pre-activation
-        r.x = __bfloat162float(__float2bfloat16(r.x)); r.y = __bfloat162float(__float2bfloat16(r.y));
-        r.z = __bfloat162float(__float2bfloat16(r.z)); r.w = __bfloat162float(__float2bfloat16(r.w));
-      }
-      r.x = lb_roottanh(r.x); r.y = lb_roottanh(r.y); r.z = lb_roottanh(r.z); r.w = lb_roottanh(r.w);
-      lb_st4(act + 4 * i, r);
+#pragma unroll
+      for (int k = 0; k < N; ++k) v[k] = lb_roottanh(lb_round_as<T>(v[k]));   // the backward evaluates RootTanh' at the STORED pre-activation
+      lb_stv(act + N * i, v);
     }
   }
 }
@@ -109,11 +110,12 @@ template <typename T>
 static int norm_apply_t(const T* x, const float* stats, const float* gain, int gbs, const float* bias, T* y, int batch, int pixels,
                         int channels, lb_stream_t s) {
   const size_t n = (size_t)batch * pixels * channels;
-  if ((channels & 3) == 0 && n / 4 < ((size_t)1 << 31) - ((size_t)1 << 24) && lb_vec4_ok(x) && lb_vec4_ok(y) && lb_aligned16(gain) &&
+  constexpr int N = LbV<T>::N;
+  if ((channels % N) == 0 && n / N < ((size_t)1 << 31) - ((size_t)1 << 24) && lb_vec_ok(x) && lb_vec_ok(y) && lb_aligned16(gain) &&
       lb_aligned16(bias)) {
-    k_norm_apply4<T, false><<<lb_grid_1d(n / 4, 256), 256, 0, lb_s(s)>>>(x, stats, gain, gbs, bias, y, nullptr, n / 4,
-                                                                        lb_make_fastdiv((uint32_t)((size_t)pixels * channels / 4)),
-                                                                        lb_make_fastdiv(channels / 4));
+    k_norm_apply4<T, false><<<lb_grid_1d(n / N, 256), 256, 0, lb_s(s)>>>(x, stats, gain, gbs, bias, y, nullptr, n / N,
+                                                                        lb_make_fastdiv((uint32_t)((size_t)pixels * channels / N)),
+                                                                        lb_make_fastdiv(channels / N));
   } else {
     k_norm_apply1<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(x, stats, gain, gbs, bias, y, n, pixels * channels, channels);
   }
@@ -131,12 +133,13 @@ template <typename T>
 static int norm_apply_ex_t(const T* x, const float* stats, const float* gain, int gbs, const float* bias, T* y, T* act, int batch,
                            int pixels, int channels, lb_stream_t s) {
   const size_t n = (size_t)batch * pixels * channels;
-  if ((channels & 3) || n / 4 >= ((size_t)1 << 31) - ((size_t)1 << 24) || !lb_vec4_ok(x) || (y && !lb_vec4_ok(y)) || !lb_vec4_ok(act) ||
+  constexpr int N = LbV<T>::N;
+  if ((channels % N) || n / N >= ((size_t)1 << 31) - ((size_t)1 << 24) || !lb_vec_ok(x) || (y && !lb_vec_ok(y)) || !lb_vec_ok(act) ||
       !lb_aligned16(gain) || !lb_aligned16(bias))
     return LB_EALIGN;
-  k_norm_apply4<T, true><<<lb_grid_1d(n / 4, 256), 256, 0, lb_s(s)>>>(x, stats, gain, gbs, bias, y, act, n / 4,
-                                                                     lb_make_fastdiv((uint32_t)((size_t)pixels * channels / 4)),
-                                                                     lb_make_fastdiv(channels / 4));
+  k_norm_apply4<T, true><<<lb_grid_1d(n / N, 256), 256, 0, lb_s(s)>>>(x, stats, gain, gbs, bias, y, act, n / N,
+                                                                     lb_make_fastdiv((uint32_t)((size_t)pixels * channels / N)),
+                                                                     lb_make_fastdiv(channels / N));
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
@@ -272,40 +275,42 @@ template <typename T>
 __global__ void __launch_bounds__(256) k_norm_bwd_apply4(const T* __restrict__ x, const T* __restrict__ g,
                                                         const float* __restrict__ stats, const float* __restrict__ gain,
                                                         int gain_bs, const double* __restrict__ sc, const T* __restrict__ add,
-                                                        T* __restrict__ dx, int n4, LbFastDiv d_pc4, LbFastDiv d_c4) {
+                                                        T* __restrict__ dx, int nv, LbFastDiv d_pcv, LbFastDiv d_cv) {
+  constexpr int N = LbV<T>::N;
   const float mean = __ldg(stats), rstd = __ldg(stats + 2);
   const double nn = (double)__ldg(stats + 3);
   const double r = (double)rstd;
   const float k0 = (float)(sc[0] * r / nn);
   const float k1 = (float)(sc[1] * r * r * r / (nn - 1.0));
   const int stride = gridDim.x * blockDim.x;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    int b, rem, q, c4;
-    lb_fast_divmod(d_pc4, i, b, rem);
-    lb_fast_divmod(d_c4, rem, q, c4);
-    const float4 gn = lb_ld4(gain + (size_t)b * gain_bs + 4 * c4);
-    const float4 gv = lb_ld4(g + 4 * (size_t)i), xv = lb_ld4(x + 4 * (size_t)i);
-    float4 o;
-    o.x = fmaf(gn.x * rstd, gv.x, -k0) - k1 * (xv.x - mean);
-    o.y = fmaf(gn.y * rstd, gv.y, -k0) - k1 * (xv.y - mean);
-    o.z = fmaf(gn.z * rstd, gv.z, -k0) - k1 * (xv.z - mean);
-    o.w = fmaf(gn.w * rstd, gv.w, -k0) - k1 * (xv.w - mean);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+    int b, rem, q, cv;
+    lb_fast_divmod(d_pcv, i, b, rem);
+    lb_fast_divmod(d_cv, rem, q, cv);
+    float gn[N], gv[N], xv[N];
+    lb_ldf<N>(gain + (size_t)b * gain_bs + N * cv, gn);
+    lb_ldv(g + (size_t)N * i, gv);
+    lb_ldv(x + (size_t)N * i, xv);
+#pragma unroll
+    for (int k = 0; k < N; ++k) gv[k] = fmaf(gn[k] * rstd, gv[k], -k0) - k1 * (xv[k] - mean);
     if (add) {
-      const float4 e = lb_ld4(add + 4 * (size_t)i);
-      o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w;
+      lb_ldv(add + (size_t)N * i, xv);
+#pragma unroll
+      for (int k = 0; k < N; ++k) gv[k] += xv[k];
     }
-    lb_st4(dx + 4 * (size_t)i, o);
+    lb_stv(dx + (size_t)N * i, gv);
   }
 }
 template <typename T>
 static int norm_bwd_apply_t(const T* x, const T* g, const float* stats, const float* gain, int gbs, const double* sc, const T* add, T* dx,
                             int batch, int pixels, int channels, lb_stream_t s) {
   const size_t n = (size_t)batch * pixels * channels;
-  if (!(channels & 3) && n / 4 < ((size_t)1 << 31) - ((size_t)1 << 24) && lb_vec4_ok(x) && lb_vec4_ok(g) && lb_vec4_ok(dx) &&
-      lb_aligned16(gain) && (!add || lb_vec4_ok(add))) {
-    k_norm_bwd_apply4<<<lb_grid_1d(n / 4, 256), 256, 0, lb_s(s)>>>(x, g, stats, gain, gbs, sc, add, dx, (int)(n / 4),
-                                                                  lb_make_fastdiv((uint32_t)((size_t)pixels * channels / 4)),
-                                                                  lb_make_fastdiv(channels / 4));
+  constexpr int N = LbV<T>::N;
+  if (!(channels % N) && n / N < ((size_t)1 << 31) - ((size_t)1 << 24) && lb_vec_ok(x) && lb_vec_ok(g) && lb_vec_ok(dx) &&
+      lb_aligned16(gain) && (!add || lb_vec_ok(add))) {
+    k_norm_bwd_apply4<<<lb_grid_1d(n / N, 256), 256, 0, lb_s(s)>>>(x, g, stats, gain, gbs, sc, add, dx, (int)(n / N),
+                                                                  lb_make_fastdiv((uint32_t)((size_t)pixels * channels / N)),
+                                                                  lb_make_fastdiv(channels / N));
   } else {
     k_norm_bwd_apply<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(x, g, stats, gain, gbs, sc, add, dx, n, pixels * channels, channels);
   }

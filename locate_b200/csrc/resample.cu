@@ -162,21 +162,25 @@ static inline PixIdx make_pix_idx(int c, int w, int h) {
 #define LB_REQUIRE_INT_ITEMS(n) LB_REQUIRE((n) < ((size_t)1 << 31) - ((size_t)1 << 24))
 // V = 4: one thread = 4 consecutive channels (one 4-element access, 4x fewer index computations); V = 1: any layout.
 // `c` below is the channel count in ELEMENTS; the item decode runs over channel groups of V.
-template <int V> struct Acc;
+template <int V> struct Acc {                 // V = LbV<T>::N: one 16-byte access of storage T
+  float v[V];
+  __device__ Acc() {
+#pragma unroll
+    for (int k = 0; k < V; ++k) v[k] = 0.0f;
+  }
+  template <typename T> __device__ void fma(float w, const T* p) {
+    float a[V];
+    lb_ldv(p, a);
+#pragma unroll
+    for (int k = 0; k < V; ++k) v[k] = fmaf(w, a[k], v[k]);
+  }
+  template <typename T> __device__ void store(T* p) const { lb_stv(p, v); }
+};
 template <> struct Acc<1> {
   float v;
   __device__ Acc() : v(0.0f) {}
   template <typename T> __device__ void fma(float w, const T* p) { v = fmaf(w, lb_ld1(p), v); }
   template <typename T> __device__ void store(T* p) const { lb_st1(p, v); }
-};
-template <> struct Acc<4> {
-  float4 v;
-  __device__ Acc() : v(make_float4(0.f, 0.f, 0.f, 0.f)) {}
-  template <typename T> __device__ void fma(float w, const T* p) {
-    const float4 a = lb_ld4(p);
-    v.x = fmaf(w, a.x, v.x); v.y = fmaf(w, a.y, v.y); v.z = fmaf(w, a.z, v.z); v.w = fmaf(w, a.w, v.w);
-  }
-  template <typename T> __device__ void store(T* p) const { lb_st4(p, v); }
 };
 
 template <typename T, int V>
@@ -235,8 +239,9 @@ template <typename T>
 static int up2_fwd_t(const T* x, T* y, int batch, int h, int w, int c, lb_stream_t s) {
   const size_t n = (size_t)batch * h * w * c * 4;
   LB_REQUIRE_INT_ITEMS(n);
-  if ((c & 3) == 0 && lb_vec4_ok(x) && lb_vec4_ok(y))
-    k_up2_fwd<T, 4><<<lb_grid_1d(n / 4, 256), 256, 0, lb_s(s)>>>(x, y, (int)(n / 4), h, w, c, make_pix_idx(c / 4, 2 * w, 2 * h));
+  constexpr int N = LbV<T>::N;
+  if ((c % N) == 0 && lb_vec_ok(x) && lb_vec_ok(y))
+    k_up2_fwd<T, N><<<lb_grid_1d(n / N, 256), 256, 0, lb_s(s)>>>(x, y, (int)(n / N), h, w, c, make_pix_idx(c / N, 2 * w, 2 * h));
   else
     k_up2_fwd<T, 1><<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(x, y, (int)n, h, w, c, make_pix_idx(c, 2 * w, 2 * h));
   LB_LAUNCH_CHECK();
@@ -246,8 +251,9 @@ template <typename T>
 static int up2_bwd_t(const T* g, T* dx, int batch, int h, int w, int c, lb_stream_t s) {
   const size_t n = (size_t)batch * h * w * c;
   LB_REQUIRE_INT_ITEMS(n);
-  if ((c & 3) == 0 && lb_vec4_ok(g) && lb_vec4_ok(dx))
-    k_up2_bwd<T, 4><<<lb_grid_1d(n / 4, 256), 256, 0, lb_s(s)>>>(g, dx, (int)(n / 4), h, w, c, make_pix_idx(c / 4, w, h));
+  constexpr int N = LbV<T>::N;
+  if ((c % N) == 0 && lb_vec_ok(g) && lb_vec_ok(dx))
+    k_up2_bwd<T, N><<<lb_grid_1d(n / N, 256), 256, 0, lb_s(s)>>>(g, dx, (int)(n / N), h, w, c, make_pix_idx(c / N, w, h));
   else
     k_up2_bwd<T, 1><<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(g, dx, (int)n, h, w, c, make_pix_idx(c, w, h));
   LB_LAUNCH_CHECK();
@@ -292,8 +298,9 @@ template <typename T>
 static int avgpool2_fwd_t(const T* x, T* y, int batch, int h, int w, int c, lb_stream_t s) {
   const size_t n = (size_t)batch * (h / 2) * (w / 2) * c;
   LB_REQUIRE_INT_ITEMS(n);
-  if ((c & 3) == 0 && lb_vec4_ok(x) && lb_vec4_ok(y))
-    k_avgpool2_fwd<T, 4><<<lb_grid_1d(n / 4, 256), 256, 0, lb_s(s)>>>(x, y, (int)(n / 4), h, w, c, make_pix_idx(c / 4, w / 2, h / 2));
+  constexpr int N = LbV<T>::N;
+  if ((c % N) == 0 && lb_vec_ok(x) && lb_vec_ok(y))
+    k_avgpool2_fwd<T, N><<<lb_grid_1d(n / N, 256), 256, 0, lb_s(s)>>>(x, y, (int)(n / N), h, w, c, make_pix_idx(c / N, w / 2, h / 2));
   else
     k_avgpool2_fwd<T, 1><<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(x, y, (int)n, h, w, c, make_pix_idx(c, w / 2, h / 2));
   LB_LAUNCH_CHECK();
@@ -303,8 +310,9 @@ template <typename T>
 static int avgpool2_bwd_t(const T* g, T* dx, int batch, int h, int w, int c, lb_stream_t s) {
   const size_t n = (size_t)batch * h * w * c;
   LB_REQUIRE_INT_ITEMS(n);
-  if ((c & 3) == 0 && lb_vec4_ok(g) && lb_vec4_ok(dx))
-    k_avgpool2_bwd<T, 4><<<lb_grid_1d(n / 4, 256), 256, 0, lb_s(s)>>>(g, dx, (int)(n / 4), h, w, c, make_pix_idx(c / 4, w, h));
+  constexpr int N = LbV<T>::N;
+  if ((c % N) == 0 && lb_vec_ok(g) && lb_vec_ok(dx))
+    k_avgpool2_bwd<T, N><<<lb_grid_1d(n / N, 256), 256, 0, lb_s(s)>>>(g, dx, (int)(n / N), h, w, c, make_pix_idx(c / N, w, h));
   else
     k_avgpool2_bwd<T, 1><<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(g, dx, (int)n, h, w, c, make_pix_idx(c, w, h));
   LB_LAUNCH_CHECK();
