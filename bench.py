@@ -502,6 +502,11 @@ def run_cuda(args):
                                      "gbs": v["bytes"] / (v["ms"] * 1e-3) / 1e9,
                                      "launches_per_step": v["launches"] / args.steps} for n, v in ksum.items()},
                     "shapes": shape_rows(klabel, peaks, args.steps)}
+    if args.shapes_file:
+        with open(args.shapes_file, "w") as fh:
+            for r in shape_rows(klabel, peaks, args.steps, top=10 ** 6):
+                fh.write(f"{r['ms_per_step']:8.3f} ms  n={r['launches_per_step']:5.1f}  {r['kernel']:16s} {r['shape']:52s} "
+                         f"{r['bound']:6s} {r['tflops']:7.1f} TF/s {r['gbs']:7.1f} GB/s  frac {r['frac']:.3f}\n")
     gflop = STEP_GFLOP_PER_IMAGE.get(res) if args.depth == 1 else None
     line = {
         "metric": metric_name(res), "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -577,6 +582,7 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="skip the fp32-vs-bf16 correctness gate")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--shapes-file", default=None, help="write every GEMM-class launch shape of a step with its time / roofline here")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

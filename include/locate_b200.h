@@ -53,6 +53,8 @@ int lb_tanh_fwd(const void* x, void* y, size_t n, int dtype, lb_stream_t stream)
 int lb_tanh_bwd(const void* y, const void* g, void* dx, size_t n, int dtype, lb_stream_t stream);
 /* y = a + b (the sum autograd forms when a tensor feeds two branches, e.g. block.py:44-46 skip path + gated branch) */
 int lb_add(const void* a, const void* b, void* y, size_t n, int dtype, lb_stream_t stream);
+/* y = a * b (a gradient times the stored RootTanh' factor, where no GEMM epilogue can apply it) */
+int lb_mul(const void* a, const void* b, void* y, size_t n, int dtype, lb_stream_t stream);
 
 /* hinge(t) = max(1 - t, 0) elementwise                                   libs/utils.py:133-134 */
 int lb_hinge_fwd(const float* x, float* y, size_t n, lb_stream_t stream);
@@ -73,10 +75,11 @@ int lb_norm_finalize(const double* sums, double n_total, float* stats, lb_stream
 int lb_norm_apply(const void* x, const float* stats, const float* gain, int gain_batch_stride,
                   const float* bias, void* y, int batch, int pixels, int channels, int dtype, lb_stream_t stream);
 /* same, also emitting act = RootTanh(y), the operand of the convolution that consumes the result (conv.py:23-24), in
- * the same pass; y may be NULL when nothing else reads it.  Needs channels % 4 == 0 and aligned pointers (LB_EALIGN
- * otherwise: use lb_norm_apply + lb_roottanh_fwd). */
+ * the same pass, and optionally dact = RootTanh'(y) (activation.py:20-36), the factor that convolution's input gradient
+ * is multiplied by (lb_conv_tc_gemm_ex, LB_EX_AUX_IS_FACTOR); y may be NULL when nothing else reads it.  Needs
+ * channels % (16 bytes of elements) == 0 and 16-byte aligned pointers (LB_EALIGN otherwise: lb_norm_apply + lb_roottanh_fwd). */
 int lb_norm_apply_ex(const void* x, const float* stats, const float* gain, int gain_batch_stride, const float* bias,
-                     void* y, void* act, int batch, int pixels, int channels, int dtype, lb_stream_t stream);
+                     void* y, void* act, void* dact, int batch, int pixels, int channels, int dtype, lb_stream_t stream);
 /* backward, 3 steps (inplace_norm.py:17-27 composed with d std/dx):
  *  1. lb_norm_bwd_reduce: p1[b][c] += sum_hw g, p2[b][c] += sum_hw (x-mean)*g      (caller zeroes p1,p2)
  *  2. lb_norm_bwd_finalize: dgain (+=, [C] or [B][C]), dbias (+=, [C]), s[2] = {sum gain*p1, sum gain*p2}
@@ -210,12 +213,16 @@ int lb_conv_tc_gemm_ws(const void* in_bf16, const void* w_packed, const float* a
  *   geometry of the output, row stride ld_aux, storage aux_dtype);
  *   out32 (fp32, row stride g->ld_out), out16 (bf16 of acc) and / or out16a (bf16 of RootTanh(acc), the operand of the
  *   convolution that follows, conv.py:23-24), both bf16 outputs with row stride ld_out16.  Any subset, not none.
+ *   flags: LB_EX_OUT16_IS_DACT -- out16 receives RootTanh'(acc) instead of acc (needs out16 and out16a): the forward
+ *   pass stores the activation's derivative, computed with RootTanh from shared intermediates, and the backward pass
+ *   passes it back as aux with LB_EX_AUX_IS_FACTOR -- acc *= aux[pixel][n], no transcendental in the backward epilogue.
  * Returns LB_EUNSUPPORTED when the geometry / alignment is outside the kernel (lb_conv_tc_ex_supported tells in
  * advance: out32_used 0/1, ld_out16 = 0 / ld_aux = 0 for "not used"); callers then use lb_conv_tc_gemm_ws + elementwise
  * kernels. */
 int lb_conv_tc_ex_supported(const lb_conv_geom* g, int out32_used, int ld_out16, int ld_aux, int aux_dtype);
+enum { LB_EX_AUX_IS_FACTOR = 1, LB_EX_OUT16_IS_DACT = 2 };
 int lb_conv_tc_gemm_ex(const void* in_bf16, const void* w_packed, const float* alpha, const float* bias, float* out32,
-                       void* out16, void* out16a, int ld_out16, const void* aux, int ld_aux, int aux_dtype,
+                       void* out16, void* out16a, int ld_out16, const void* aux, int ld_aux, int aux_dtype, int flags,
                        const lb_conv_geom* g, lb_stream_t stream);
 /* weight gradient on the tensor cores: dwp[tap][n][m] += sum_pixels gathered[pixel@tap][m] * dense[pixel][n]
  * (geometry as lb_conv_wgrad; both operands bf16 channels-last; dwp fp32, zeroed by the caller; feed it to

@@ -32,13 +32,14 @@ _SIGNATURES = {
     "lb_tanh_fwd": ([P, P, c_size_t, c_int, P], c_int),
     "lb_tanh_bwd": ([P, P, P, c_size_t, c_int, P], c_int),
     "lb_add": ([P, P, P, c_size_t, c_int, P], c_int),
+    "lb_mul": ([P, P, P, c_size_t, c_int, P], c_int),
     "lb_hinge_fwd": ([P, P, c_size_t, P], c_int),
     "lb_hinge_bwd": ([P, P, P, c_size_t, P], c_int),
     "lb_stat_work_doubles": ([], c_size_t),
     "lb_norm_stats": ([P, c_size_t, P, P, c_int, P], c_int),
     "lb_norm_finalize": ([P, c_double, P, P], c_int),
     "lb_norm_apply": ([P, P, P, c_int, P, P, c_int, c_int, c_int, c_int, P], c_int),
-    "lb_norm_apply_ex": ([P, P, P, c_int, P, P, P, c_int, c_int, c_int, c_int, P], c_int),
+    "lb_norm_apply_ex": ([P, P, P, c_int, P, P, P, P, c_int, c_int, c_int, c_int, P], c_int),
     "lb_norm_bwd_reduce": ([P, P, P, P, P, c_int, c_int, c_int, c_int, P], c_int),
     "lb_norm_bwd_finalize": ([P, P, P, c_int, P, c_int, c_int, P, P, P, P], c_int),
     "lb_norm_bwd_apply": ([P, P, P, P, c_int, P, P, P, c_int, c_int, c_int, c_int, P], c_int),
@@ -65,7 +66,7 @@ _SIGNATURES = {
     "lb_conv_tc_workspace_bytes": ([POINTER(ConvGeom)], c_size_t),
     "lb_conv_tc_gemm_ws": ([P, P, P, P, P, POINTER(ConvGeom), P, c_size_t, c_int, P], c_int),
     "lb_conv_tc_ex_supported": ([POINTER(ConvGeom), c_int, c_int, c_int, c_int], c_int),
-    "lb_conv_tc_gemm_ex": ([P, P, P, P, P, P, P, c_int, P, c_int, c_int, POINTER(ConvGeom), P], c_int),
+    "lb_conv_tc_gemm_ex": ([P, P, P, P, P, P, P, c_int, P, c_int, c_int, c_int, POINTER(ConvGeom), P], c_int),
     "lb_cast_bf16": ([P, P, c_size_t, P], c_int),
     "lb_cast_bf16_rows": ([P, c_int, P, c_int, c_int64, c_int, c_int, P], c_int),
     "lb_roottanh_fwd_bf16": ([P, P, c_size_t, c_int, P], c_int),

@@ -174,7 +174,14 @@ class SNConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w_bar, u, v, bias, spec, cat_input, pre_act, pre_sigma):
         ready_act = getattr(x, "_lb_act16", None) if pre_act else None
-        x = _as_act(x)
+        ready_dact = getattr(x, "_lb_dact16", None) if pre_act else None
+        if getattr(x, "_lb_unwritten", False):       # a norm output that exists only as RootTanh(y) / RootTanh'(y)
+            if ready_act is None:
+                raise RuntimeError("norm output was emitted for an activated conv, but this conv does not start with RootTanh")
+            x_vals = None
+        else:
+            x = _as_act(x)
+            x_vals = x
         is_vec = x.dim() == 2
         if is_vec:
             b, h, w_, cin = x.shape[0], 1, 1, x.shape[1]
@@ -226,6 +233,8 @@ class SNConvFn(torch.autograd.Function):
         if not tc:
             if (x16 or out16) and not small:
                 raise RuntimeError("bf16-stored activations reached a layer the tensor-core kernels do not cover")
+            if x_vals is None:
+                raise RuntimeError("placeholder norm output reached a layer outside the tensor-core path")
             g_fwd, g_dgrad, g_wgrad = geoms(cin, spec.cout)
         fl, by = _conv_work(spec, b, h, w_, oh, ow)
         n = x.numel()
@@ -267,7 +276,9 @@ class SNConvFn(torch.autograd.Function):
                         out.data_ptr() + off * 4, g_fwd)
         if cat_input and not fused_cat:
             call("lb_copy_rows", ptr(x), cin, ptr(out), ctot, b * h * w_, cin, 0, _dt(x), _dt(out))
-        ctx.save_for_backward(x if pre_act else None, a, w_bar, sigma)
+        # RootTanh'(x) for the backward: the factor itself when the producer left it, else x to evaluate it from
+        ctx.dact_ready = bool(pre_act and ready_dact is not None)
+        ctx.save_for_backward((ready_dact if ctx.dact_ready else x_vals) if pre_act else None, a, w_bar, sigma)
         ctx.u, ctx.v = u, v                      # LIVE u/v: the reference's backward reads them at backward time
         ctx.uv_extra = _uv_extra(pre_sigma, u)
         ctx.bias_param, ctx.w_param = bias, w_bar
@@ -306,9 +317,9 @@ class SNConvFn(torch.autograd.Function):
                 pk = _packed_weight(w_bar, g_dgrad, "dgrad")
                 if x16:
                     aux_ok = pre_act and lib.lb_conv_tc_ex_supported(ctypes.byref(g_dgrad), 0, cin, cin, BF16) == 1
-                    if aux_ok:      # dx = dgrad(gy) * RootTanh'(x) in the GEMM epilogue
+                    if aux_ok:      # dx = dgrad(gy) * RootTanh'(x) in the GEMM epilogue (x holds the factor itself if dact_ready)
                         _timed_call("conv_tc", fl, _tc_bytes(g_dgrad), "lb_conv_tc_gemm_ex", gy_ptr, ptr(pk), sigma.data_ptr() + 4, None,
-                                    None, ptr(dx), None, cin, ptr(x), cin, BF16, g_dgrad)
+                                    None, ptr(dx), None, cin, ptr(x), cin, BF16, EX_AUX_IS_FACTOR if ctx.dact_ready else 0, g_dgrad)
                         dact_done = True
                     else:
                         _tc_gemm(fl, _tc_bytes(g_dgrad), gy_ptr, pk, sigma.data_ptr() + 4, None, ptr(dx), g_dgrad, dev, BF16)
@@ -358,7 +369,9 @@ class SNConvFn(torch.autograd.Function):
                     _timed_call("conv_wgrad", fl, by, "lb_conv_wgrad", ga_ptr, de_ptr, ptr(dwn), g_wgrad)
                 dw_ret = _sn_weight_grad(dwn, ctx.w_param, ctx.u, ctx.v, sigma, spec, 0, ctx.uv_extra, dev)
         if need_dx:
-            if pre_act and not dact_done:
+            if pre_act and not dact_done and ctx.dact_ready:
+                call("lb_mul", ptr(x), ptr(dx), ptr(dx), dx.numel(), _dt(dx))                                  # dx *= RootTanh'(x), in place
+            elif pre_act and not dact_done:
                 call("lb_roottanh_bwd", ptr(x), ptr(dx), ptr(dx), dx.numel(), CFG.ROOTTANH_GROWTH, _dt(dx))   # in place
             if cat_input:
                 call("lb_copy_rows", ptr(gout), ctot, ptr(dx), cin, b * h * w_, cin, 1, _dt(gout), _dt(dx))
@@ -380,6 +393,9 @@ def _wgrad_bytes(g):
     """ALGORITHMIC bytes of one weight-gradient launch: both bf16 operands once + the fp32 gradient."""
     return (2.0 * g.batch * g.in_h * g.in_w * g.in_c + 2.0 * g.batch * g.out_h * g.out_w * g.out_c
             + 4.0 * g.kh * g.kw * g.in_c * g.out_c)
+
+
+EX_AUX_IS_FACTOR, EX_OUT16_IS_DACT = 1, 2      # include/locate_b200.h LB_EX_*
 
 
 def _ex_ok(g, out32, ld16, ld_aux, aux_dtype=F32):
@@ -410,7 +426,13 @@ class ActivatedPairFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w0, u0, v0, w1, u1, v1, spec0, spec1, sigma0, sigma1, geoms, pre_act0):
         act16 = getattr(x, "_lb_act16", None) if pre_act0 else None
-        x = _as_act(x)                               # bf16 (cin % 8 == 0, checked by activated_pair)
+        dact_x = getattr(x, "_lb_dact16", None) if pre_act0 else None
+        need_bwd = any(ctx.needs_input_grad)
+        x_vals = None
+        if not getattr(x, "_lb_unwritten", False):
+            x_vals = x = _as_act(x)                  # bf16 (cin % 8 == 0, checked by activated_pair)
+        elif act16 is None or (need_bwd and dact_x is None):
+            raise RuntimeError("placeholder norm output without its RootTanh / RootTanh' companions")
         b, cin, h, w_ = x.shape
         oh, ow = spec0.out_hw(h, w_)
         mid, cout = spec0.cout, spec1.cout
@@ -420,18 +442,21 @@ class ActivatedPairFn(torch.autograd.Function):
         elif act16 is None:
             act16 = torch.empty_like(x)
             call("lb_roottanh_fwd", ptr(x), ptr(act16), x.numel(), CFG.ROOTTANH_GROWTH, BF16)
-        y0 = _new_act((b, mid, oh, ow), x, torch.bfloat16)
-        a0 = torch.empty_like(y0)
+        a0 = _new_act((b, mid, oh, ow), x, torch.bfloat16)
+        # with a backward pass to come conv_0 also stores RootTanh'(y0) (not y0): conv_1's input gradient multiplies by it
+        dact0 = torch.empty_like(a0) if need_bwd else None
         fl0, by0 = _conv_work(spec0, b, h, w_, oh, ow)
         fl1, by1 = _conv_work(spec1, b, oh, ow, oh, ow)
         _timed_call("conv_tc", fl0, _tc_bytes(gf0), "lb_conv_tc_gemm_ex", ptr(act16), ptr(_packed_weight(w0, gf0, "fwd")),
-                    sigma0.data_ptr() + 4, None, None, ptr(y0), ptr(a0), mid, None, 0, F32, gf0)
+                    sigma0.data_ptr() + 4, None, None, ptr(dact0), ptr(a0), mid, None, 0, F32, EX_OUT16_IS_DACT if need_bwd else 0, gf0)
         y1 = _new_act((b, cout, oh, ow), x)
         # lb_conv_tc_gemm_ws picks the persistent kernel itself and keeps direct stores for rows that TMA cannot address
         # (cout = 3: G's last layer, fp32 rows)
         _tc_gemm(fl1, _tc_bytes(gf1), ptr(a0), _packed_weight(w1, gf1, "fwd"), sigma1.data_ptr() + 4, None, ptr(y1), gf1, x.device,
                  _dt(y1))
-        ctx.save_for_backward(x if pre_act0 else None, act16, y0, a0, w0, w1, sigma0, sigma1)
+        # RootTanh'(x): the factor left by the norm kernel, else x itself (the epilogue then evaluates it)
+        ctx.x_is_factor = bool(pre_act0 and dact_x is not None)
+        ctx.save_for_backward((dact_x if ctx.x_is_factor else x_vals) if pre_act0 else None, act16, dact0, a0, w0, w1, sigma0, sigma1)
         ctx.uv = (u0, v0, u1, v1)                # LIVE u/v (see SNConvFn)
         ctx.uv_extra = (_uv_extra(sigma0, u0), _uv_extra(sigma1, u1))
         ctx.meta = (spec0, spec1, geoms, (b, cin, h, w_, oh, ow, mid, cout), (fl0, by0, fl1, by1), pre_act0)
@@ -440,7 +465,7 @@ class ActivatedPairFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gout):
-        x, act16, y0, a0, w0, w1, sigma0, sigma1 = ctx.saved_tensors
+        x, act16, dact0, a0, w0, w1, sigma0, sigma1 = ctx.saved_tensors
         u0, v0, u1, v1 = ctx.uv
         spec0, spec1, geoms, (b, cin, h, w_, oh, ow, mid, cout), (fl0, by0, fl1, by1), pre_act0 = ctx.meta
         (gf0, gd0, gw0), (gf1, gd1, gw1) = geoms
@@ -454,9 +479,9 @@ class ActivatedPairFn(torch.autograd.Function):
             ga, de = (g1, a0) if spec1.kind == "convT" else (a0, g1)
             dw1 = _sn_wgrad_tc(w1, u1, v1, sigma1, ptr(ga), ptr(de), gw1, spec1, fl1, by1, dev, ctx.uv_extra[1])
         if need_dx or need_dw0:
-            d0 = torch.empty_like(y0)            # bf16( dL/dy0 ) = bf16( dgrad_1(g1) * RootTanh'(y0) )
+            d0 = torch.empty_like(a0)            # bf16( dL/dy0 ) = bf16( dgrad_1(g1) * RootTanh'(y0) ), the factor stored by the forward
             _timed_call("conv_tc", fl1, _tc_bytes(gd1), "lb_conv_tc_gemm_ex", ptr(g1), ptr(_packed_weight(w1, gd1, "dgrad")),
-                        sigma1.data_ptr() + 4, None, None, ptr(d0), None, mid, ptr(y0), mid, BF16, gd1)
+                        sigma1.data_ptr() + 4, None, None, ptr(d0), None, mid, ptr(dact0), mid, BF16, EX_AUX_IS_FACTOR, gd1)
             if need_dw0:
                 ga, de = (d0, act16) if spec0.kind == "convT" else (act16, d0)
                 dw0 = _sn_wgrad_tc(w0, u0, v0, sigma0, ptr(ga), ptr(de), gw0, spec0, fl0, by0, dev, ctx.uv_extra[0])
@@ -464,7 +489,7 @@ class ActivatedPairFn(torch.autograd.Function):
                 dx = _new_act((b, cin, h, w_), gout, torch.bfloat16)
                 _timed_call("conv_tc", fl0, _tc_bytes(gd0), "lb_conv_tc_gemm_ex", ptr(d0), ptr(_packed_weight(w0, gd0, "dgrad")),
                             sigma0.data_ptr() + 4, None, None, ptr(dx), None, cin, ptr(x) if pre_act0 else None,
-                            cin if pre_act0 else 0, BF16, gd0)
+                            cin if pre_act0 else 0, BF16, EX_AUX_IS_FACTOR if ctx.x_is_factor else 0, gd0)
         return (dx, dw0, None, None, dw1) + (None,) * 8
 
 

@@ -225,6 +225,15 @@ __device__ __forceinline__ float lb_roottanh_grad(float x) {   // growth == 4: (
   const float r4 = lb_sqrt_fast(lb_sqrt_fast(q));
   return fmaf(2.0f * q, s2, x * th) * r4 * (0.5f * lb_rcp_fast(q));
 }
+// both at once (growth == 4): shared tanh / sech^2 / powers
+__device__ __forceinline__ void lb_roottanh_both(float x, float& f, float& df) {
+  float th, s2;
+  lb_tanh_sech2(x, th, s2);
+  const float q = fmaf(x, x, 1.0f);
+  const float r4 = lb_sqrt_fast(lb_sqrt_fast(q));
+  f = r4 * th;
+  df = fmaf(2.0f * q, s2, x * th) * r4 * (0.5f * lb_rcp_fast(q));
+}
 __device__ __forceinline__ float lb_roottanh_g(float x, float inv_growth) {
   float th, s2;
   lb_tanh_sech2(x, th, s2);

@@ -304,7 +304,7 @@ extern "C" int lb_conv_tc_pack(const float* w, void* packed, const lb_conv_geom*
 }
 
 extern "C" int lb_conv_tc_gemm_ex(const void* in_bf16, const void* w_packed, const float* alpha, const float* bias, float* out32,
-                                  void* out16, void* out16a, int ld_out16, const void* aux, int ld_aux, int aux_dtype,
+                                  void* out16, void* out16a, int ld_out16, const void* aux, int ld_aux, int aux_dtype, int flags,
                                   const lb_conv_geom* g, lb_stream_t s);
 extern "C" int lb_conv_tc_ex_supported(const lb_conv_geom* g, int out32_used, int ld_out16, int ld_aux, int aux_dtype);
 extern "C" int lb_conv_tc_gemm_ws(const void* in_bf16, const void* w_packed, const float* alpha, const float* bias, void* out,
@@ -409,7 +409,7 @@ extern "C" int lb_conv_tc_gemm_ws(const void* in_bf16, const void* w_packed, con
   if (!v1_only && prefer_persistent(g) && lb_conv_tc_ex_supported(g, o16 ? 0 : 1, o16 ? g->ld_out : 0, 0, LB_F32) == 1 &&
       !(reinterpret_cast<uintptr_t>(out) & 15)) {
     const int rc = lb_conv_tc_gemm_ex(in_bf16, w_packed, alpha, bias, o16 ? nullptr : reinterpret_cast<float*>(out), o16 ? out : nullptr,
-                                      nullptr, o16 ? g->ld_out : 0, nullptr, 0, LB_F32, g, s);
+                                      nullptr, o16 ? g->ld_out : 0, nullptr, 0, LB_F32, 0, g, s);
     if (rc != LB_EUNSUPPORTED) return rc;
   }
   if (reinterpret_cast<uintptr_t>(in_bf16) & 15 || reinterpret_cast<uintptr_t>(w_packed) & 15) return LB_EALIGN;

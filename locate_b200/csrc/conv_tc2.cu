@@ -2,11 +2,16 @@
 //
 //   acc[pixel][n] = alpha * sum_taps sum_k A_tap[pixel][k] * Wp[tap][n][k]  (+ bias[n])
 //   if aux:    acc *= RootTanh'(aux[pixel][n])           (the activation backward that follows a dgrad GEMM; aux fp32 or bf16)
+//              or, LB_EX_AUX_IS_FACTOR: acc *= aux[pixel][n]   (aux already holds RootTanh' -- see below)
 //   if out32:  out32[pixel][n]  = acc                     (fp32)
 //   if out16:  out16[pixel][n]  = bf16(acc)               (bf16 activation storage: pre-activation / gradient)
+//              or, LB_EX_OUT16_IS_DACT: bf16(RootTanh'(acc)): the forward pass stores the activation's DERIVATIVE instead
+//              of its argument, so the backward epilogue multiplies by a loaded factor instead of evaluating it -- the
+//              transcendental work (4 MUFU ops per element, the limiter of the C <= 96 layers' epilogues) is done once,
+//              next to RootTanh itself with which it shares every intermediate
 //   if out16a: out16a[pixel][n] = bf16(RootTanh(acc'))    (the next GEMM's operand, produced in place; acc' = the value
-//                                                          stored by out16 when both are written, so that the backward's
-//                                                          RootTanh'(out16) belongs to exactly this function value)
+//                                                          stored by out16 when a pre-activation is written, so that the
+//                                                          backward's RootTanh'(out16) belongs to exactly this value)
 //
 // Operand staging and tap handling are those of conv_tc.cu (per-tap dense TMA boxes of parity views, zero fill =
 // padding).  What is different:
@@ -56,6 +61,8 @@ struct Tc2Params {
   int ebw, ebh, ebb;                  // 32-row sub-box of one epilogue warp
   int has_o32, has_o16, has_o16a, has_aux;
   int aux_bf16;                       // aux slabs are bf16 (64-byte rows) instead of fp32 (128-byte rows)
+  int aux_factor;                     // aux holds the factor itself (RootTanh' precomputed by the forward pass)
+  int o16_dact;                       // out16 receives RootTanh'(acc) instead of acc
   uint32_t tmem_cols;
   uint32_t tab_base; int max_tp;      // per-phase tap table in shared memory: max_tp entries per phase
   int resident;                       // 1: the weights of one output phase stay in shared memory (res_base), stages carry A only
@@ -124,6 +131,24 @@ __device__ __forceinline__ float roottanh_fast(float x) {
   const float th = copysignf((1.0f - e) * rcp_approx(1.0f + e), x);
   const float q = fmaf(x, x, 1.0f);
   return sqrt_approx(sqrt_approx(q)) * th;
+}
+__device__ __forceinline__ float tanh_approx(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// RootTanh only (no derivative wanted): tanh.approx + two square roots = 3 MUFU ops; relative error ~5e-4, below the bf16
+// rounding of the stored result
+__device__ __forceinline__ float roottanh_only_fast(float x) {
+  return sqrt_approx(sqrt_approx(fmaf(x, x, 1.0f))) * tanh_approx(x);
+}
+// RootTanh and RootTanh' together: every intermediate is shared (4 MUFU ops for both)
+__device__ __forceinline__ void roottanh_both_fast(float x, float& f, float& df) {
+  const float e = ex2_approx(-2.8853900817779268f * fabsf(x));
+  const float r = rcp_approx(1.0f + e);
+  const float th = copysignf((1.0f - e) * r, x);
+  const float s2 = 4.0f * e * r * r;
+  const float q = fmaf(x, x, 1.0f);
+  const float rs = rsqrt_approx(q);                                  // q^(-1/2)
+  const float q34 = rs * sqrt_approx(rs);                            // q^(-3/4)
+  f = q * q34 * th;                                                  // q^(1/4) tanh
+  df = fmaf(2.0f * q, s2, x * th) * 0.5f * q34;
 }
 // RootTanh'(x) = (2 q sech^2 + x tanh) q^(1/4) / (2q) = (2 q sech^2 + x tanh) * 0.5 q^(-3/4)
 __device__ __forceinline__ float roottanh_grad_fast(float x) {
@@ -412,9 +437,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
-                v[8 * j + 2 * i] *= roottanh_grad_fast(f.x);
-                v[8 * j + 2 * i + 1] *= roottanh_grad_fast(f.y);
+                if (p.aux_factor) {
+                  v[8 * j + 2 * i] *= f.x;
+                  v[8 * j + 2 * i + 1] *= f.y;
+                } else {
+                  v[8 * j + 2 * i] *= roottanh_grad_fast(f.x);
+                  v[8 * j + 2 * i + 1] *= roottanh_grad_fast(f.y);
+                }
               }
+            }
+          } else if (p.aux_factor) {
+            const uint8_t* row = s_aux + buf * 4096 + lane * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 x4 = *reinterpret_cast<const float4*>(row + ((j ^ sw) << 4));
+              v[4 * j + 0] *= x4.x; v[4 * j + 1] *= x4.y; v[4 * j + 2] *= x4.z; v[4 * j + 3] *= x4.w;
             }
           } else {
             const uint8_t* row = s_aux + buf * 4096 + lane * 128;
@@ -446,9 +483,29 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
           uint8_t* rowa = s_o16a + lane * 64;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            __nv_bfloat162 h[4];
+            __nv_bfloat162 h[4], a[4];
+            if (p.o16_dact) {                    // RootTanh -> out16a, RootTanh' -> out16, all intermediates shared
 #pragma unroll
-            for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[8 * j + 2 * i], v[8 * j + 2 * i + 1]);
+              for (int i = 0; i < 4; ++i) {
+                float f0, d0, f1, d1;
+                roottanh_both_fast(v[8 * j + 2 * i], f0, d0);
+                roottanh_both_fast(v[8 * j + 2 * i + 1], f1, d1);
+                a[i] = __floats2bfloat162_rn(f0, f1);
+                h[i] = __floats2bfloat162_rn(d0, d1);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[8 * j + 2 * i], v[8 * j + 2 * i + 1]);
+              if (p.has_o16a) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  // with a stored pre-activation the function value belongs to the STORED (rounded) argument
+                  const float2 f = p.has_o16 ? __bfloat1622float2(h[i]) : make_float2(v[8 * j + 2 * i], v[8 * j + 2 * i + 1]);
+                  a[i] = p.has_o16 ? __floats2bfloat162_rn(roottanh_fast(f.x), roottanh_fast(f.y))
+                                   : __floats2bfloat162_rn(roottanh_only_fast(f.x), roottanh_only_fast(f.y));
+                }
+              }
+            }
             if (p.has_o16) {
               uint4 pk;
               pk.x = *reinterpret_cast<uint32_t*>(&h[0]); pk.y = *reinterpret_cast<uint32_t*>(&h[1]);
@@ -456,13 +513,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
               *reinterpret_cast<uint4*>(row + ((j ^ sw64) << 4)) = pk;
             }
             if (p.has_o16a) {
-              __nv_bfloat162 a[4];
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                // with a stored pre-activation the function value belongs to the STORED (rounded) argument
-                const float2 f = p.has_o16 ? __bfloat1622float2(h[i]) : make_float2(v[8 * j + 2 * i], v[8 * j + 2 * i + 1]);
-                a[i] = __floats2bfloat162_rn(roottanh_fast(f.x), roottanh_fast(f.y));
-              }
               uint4 pk;
               pk.x = *reinterpret_cast<uint32_t*>(&a[0]); pk.y = *reinterpret_cast<uint32_t*>(&a[1]);
               pk.z = *reinterpret_cast<uint32_t*>(&a[2]); pk.w = *reinterpret_cast<uint32_t*>(&a[3]);
@@ -528,9 +578,11 @@ static bool tc2_ok(const lb_conv_geom* g, const void* out32, const void* out16, 
 }
 
 extern "C" int lb_conv_tc_gemm_ex(const void* in_bf16, const void* w_packed, const float* alpha, const float* bias, float* out32,
-                                  void* out16, void* out16a, int ld_out16, const void* aux, int ld_aux, int aux_dtype,
+                                  void* out16, void* out16a, int ld_out16, const void* aux, int ld_aux, int aux_dtype, int flags,
                                   const lb_conv_geom* g, lb_stream_t s) {
   LB_REQUIRE(in_bf16 && w_packed && g);
+  LB_REQUIRE(!(flags & ~(LB_EX_AUX_IS_FACTOR | LB_EX_OUT16_IS_DACT)));
+  LB_REQUIRE(!(flags & LB_EX_OUT16_IS_DACT) || (out16 && out16a));
   if (!tc2_ok(g, out32, out16, out16a, ld_out16, aux, ld_aux, aux_dtype)) return LB_EUNSUPPORTED;
   if (reinterpret_cast<uintptr_t>(in_bf16) & 15 || reinterpret_cast<uintptr_t>(w_packed) & 15) return LB_EALIGN;
   Tc2Maps maps;
@@ -555,6 +607,8 @@ extern "C" int lb_conv_tc_gemm_ex(const void* in_bf16, const void* w_packed, con
   p.alpha = alpha; p.bias = bias;
   p.has_o32 = out32 ? 1 : 0; p.has_o16 = out16 ? 1 : 0; p.has_o16a = out16a ? 1 : 0; p.has_aux = aux ? 1 : 0;
   p.aux_bf16 = aux_dtype == LB_BF16 ? 1 : 0;
+  p.aux_factor = (flags & LB_EX_AUX_IS_FACTOR) ? 1 : 0;
+  p.o16_dact = (flags & LB_EX_OUT16_IS_DACT) ? 1 : 0;
   p.aux_bytes = p.aux_bf16 ? 32 * kSlab * 2 : 32 * kSlab * 4;
 
   // epilogue staging per warp: fp32 slab 4 KB, bf16 slabs 2 KB each, aux 2 x (4 | 2) KB (all 1 KB aligned for the swizzle)

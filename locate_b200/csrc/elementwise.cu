@@ -99,6 +99,7 @@ struct HingeF { __device__ float operator()(float x) const { return fmaxf(1.0f -
 struct HingeB { __device__ float operator()(float x, float g) const { return x < 1.0f ? -g : 0.0f; } };
 struct ScaleF { float f; __device__ float operator()(float x) const { return x * f; } };
 struct AddF { __device__ float operator()(float a, float b) const { return a + b; } };
+struct MulF { __device__ float operator()(float a, float b) const { return a * b; } };
 
 extern "C" int lb_roottanh_fwd(const void* x, void* y, size_t n, int growth, int dtype, lb_stream_t s) {
   LB_REQUIRE(growth >= 1);
@@ -122,6 +123,10 @@ extern "C" int lb_scale(float* x, size_t n, float factor, lb_stream_t s) { retur
 // y = a + b: the sum of the gradients that reach a tensor consumed by two branches (skip path + gated branch of a block)
 extern "C" int lb_add(const void* a, const void* b, void* y, size_t n, int dtype, lb_stream_t s) {
   return launch_binary(a, b, y, n, AddF{}, dtype, s);
+}
+// y = a * b: a gradient times a stored activation derivative (RootTanh' kept by the forward pass)
+extern "C" int lb_mul(const void* a, const void* b, void* y, size_t n, int dtype, lb_stream_t s) {
+  return launch_binary(a, b, y, n, MulF{}, dtype, s);
 }
 
 __global__ void k_fill(float* __restrict__ x, size_t n, float v) {

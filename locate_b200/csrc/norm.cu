@@ -70,7 +70,8 @@ extern "C" int lb_norm_finalize(const double* sums, double n_total, float* stats
 template <typename T, bool kAct>
 __global__ void __launch_bounds__(256) k_norm_apply4(const T* __restrict__ x, const float* __restrict__ stats,
                                                     const float* __restrict__ gain, int gain_bs, const float* __restrict__ bias,
-                                                    T* __restrict__ y, T* __restrict__ act, size_t nv, LbFastDiv d_pcv, LbFastDiv d_cv) {
+                                                    T* __restrict__ y, T* __restrict__ act, T* __restrict__ dact, size_t nv,
+                                                    LbFastDiv d_pcv, LbFastDiv d_cv) {
   constexpr int N = LbV<T>::N;
   const float mean = __ldg(stats), rstd = __ldg(stats + 2);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -87,8 +88,14 @@ __global__ void __launch_bounds__(256) k_norm_apply4(const T* __restrict__ x, co
     for (int k = 0; k < N; ++k) v[k] = fmaf((v[k] - mean) * rstd, gn[k], bs[k]);
     if (y) lb_stv(y + N * i, v);
     if (kAct) {
+      if (dact) {                               // RootTanh and its derivative from shared intermediates
 #pragma unroll
-      for (int k = 0; k < N; ++k) v[k] = lb_roottanh(lb_round_as<T>(v[k]));   // the backward evaluates RootTanh' at the STORED pre-activation
+        for (int k = 0; k < N; ++k) lb_roottanh_both(v[k], v[k], gn[k]);
+        lb_stv(dact + N * i, gn);
+      } else {
+#pragma unroll
+        for (int k = 0; k < N; ++k) v[k] = lb_roottanh(v[k]);
+      }
       lb_stv(act + N * i, v);
     }
   }
@@ -113,7 +120,7 @@ static int norm_apply_t(const T* x, const float* stats, const float* gain, int g
   constexpr int N = LbV<T>::N;
   if ((channels % N) == 0 && n / N < ((size_t)1 << 31) - ((size_t)1 << 24) && lb_vec_ok(x) && lb_vec_ok(y) && lb_aligned16(gain) &&
       lb_aligned16(bias)) {
-    k_norm_apply4<T, false><<<lb_grid_1d(n / N, 256), 256, 0, lb_s(s)>>>(x, stats, gain, gbs, bias, y, nullptr, n / N,
+    k_norm_apply4<T, false><<<lb_grid_1d(n / N, 256), 256, 0, lb_s(s)>>>(x, stats, gain, gbs, bias, y, nullptr, nullptr, n / N,
                                                                         lb_make_fastdiv((uint32_t)((size_t)pixels * channels / N)),
                                                                         lb_make_fastdiv(channels / N));
   } else {
@@ -130,26 +137,26 @@ extern "C" int lb_norm_apply(const void* x, const float* stats, const float* gai
 }
 
 template <typename T>
-static int norm_apply_ex_t(const T* x, const float* stats, const float* gain, int gbs, const float* bias, T* y, T* act, int batch,
-                           int pixels, int channels, lb_stream_t s) {
+static int norm_apply_ex_t(const T* x, const float* stats, const float* gain, int gbs, const float* bias, T* y, T* act, T* dact,
+                           int batch, int pixels, int channels, lb_stream_t s) {
   const size_t n = (size_t)batch * pixels * channels;
   constexpr int N = LbV<T>::N;
   if ((channels % N) || n / N >= ((size_t)1 << 31) - ((size_t)1 << 24) || !lb_vec_ok(x) || (y && !lb_vec_ok(y)) || !lb_vec_ok(act) ||
-      !lb_aligned16(gain) || !lb_aligned16(bias))
+      (dact && !lb_vec_ok(dact)) || !lb_aligned16(gain) || !lb_aligned16(bias))
     return LB_EALIGN;
-  k_norm_apply4<T, true><<<lb_grid_1d(n / N, 256), 256, 0, lb_s(s)>>>(x, stats, gain, gbs, bias, y, act, n / N,
+  k_norm_apply4<T, true><<<lb_grid_1d(n / N, 256), 256, 0, lb_s(s)>>>(x, stats, gain, gbs, bias, y, act, dact, n / N,
                                                                      lb_make_fastdiv((uint32_t)((size_t)pixels * channels / N)),
                                                                      lb_make_fastdiv(channels / N));
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
-// y (may be NULL) and act = RootTanh(y), both in storage `dtype`
+// y (may be NULL), act = RootTanh(y) and dact = RootTanh'(y) (may be NULL), all in storage `dtype`
 extern "C" int lb_norm_apply_ex(const void* x, const float* stats, const float* gain, int gain_batch_stride, const float* bias,
-                                void* y, void* act, int batch, int pixels, int channels, int dtype, lb_stream_t s) {
+                                void* y, void* act, void* dact, int batch, int pixels, int channels, int dtype, lb_stream_t s) {
   LB_REQUIRE(x && stats && gain && bias && act && batch > 0 && pixels > 0 && channels > 0);
   LB_REQUIRE(gain_batch_stride == 0 || gain_batch_stride == channels);
-  LB_DISPATCH(dtype, T, return norm_apply_ex_t(lb_cp<T>(x), stats, gain, gain_batch_stride, bias, lb_p<T>(y), lb_p<T>(act), batch,
-                                               pixels, channels, s));
+  LB_DISPATCH(dtype, T, return norm_apply_ex_t(lb_cp<T>(x), stats, gain, gain_batch_stride, bias, lb_p<T>(y), lb_p<T>(act),
+                                               lb_p<T>(dact), batch, pixels, channels, s));
 }
 
 // backward phase 1: per-(b,c) column sums over pixels.  CTA = (pixel chunk, b); thread = (channel lane, pixel lane)

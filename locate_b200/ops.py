@@ -114,6 +114,8 @@ def _cast(t, dtype):
 def _as_act(t):
     """Bring a tensor to the library's activation form: CUDA, storage type per store_dtype(), channels-last (4-D) or
     contiguous (other ranks).  Anything else is converted once at the boundary."""
+    if getattr(t, "_lb_unwritten", False):
+        raise RuntimeError("this norm output exists only as RootTanh(y) / RootTanh'(y) (emit='act'): its values were never written")
     if t.dtype not in (torch.float32, torch.bfloat16):
         t = t.float()
     if t.dim() == 4:
@@ -282,9 +284,10 @@ class WholeNormFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, gain, bias, emit=None):
-        """emit == "act": the module that follows starts with RootTanh -> conv (conv.py:22-24); in the tensor-core
-        configuration the same pass also writes RootTanh(y), that convolution's GEMM operand, attached to the output as
-        `_lb_act16` (the pre-activation y stays: the backward needs RootTanh'(y))."""
+        """emit == "act": the module that follows starts with RootTanh -> conv (conv.py:22-24) and nothing else reads the
+        norm output.  In the tensor-core configuration the pass then writes RootTanh(y), that convolution's GEMM
+        operand (`_lb_act16`), and -- when a backward pass will follow -- RootTanh'(y) (`_lb_dact16`), the factor its
+        input gradient is multiplied by, INSTEAD of y: the returned tensor is a placeholder (`_lb_unwritten`)."""
         x = _as_act(x)
         dt = _dt(x)
         b, p, c = _bpc(x)
@@ -303,10 +306,12 @@ class WholeNormFn(torch.autograd.Function):
         call("lb_norm_finalize", ptr(sums), n_total, ptr(stats))
         y = torch.empty_like(x)
         gbs = c if per_sample else 0
-        if emit == "act" and dt == BF16 and c % 4 == 0 and x.dim() == 4:
+        from .config import CFG
+        if emit == "act" and dt == BF16 and c % 8 == 0 and x.dim() == 4 and CFG.ROOTTANH_GROWTH == 4:
             act = torch.empty_like(x)
-            call("lb_norm_apply_ex", ptr(x), ptr(stats), ptr(gain_c), gbs, ptr(bias), ptr(y), ptr(act), b, p, c, dt)
-            y._lb_act16 = act
+            dact = torch.empty_like(x) if any(ctx.needs_input_grad) else None
+            call("lb_norm_apply_ex", ptr(x), ptr(stats), ptr(gain_c), gbs, ptr(bias), None, ptr(act), ptr(dact), b, p, c, dt)
+            y._lb_act16, y._lb_dact16, y._lb_unwritten = act, dact, True
         else:
             call("lb_norm_apply", ptr(x), ptr(stats), ptr(gain_c), gbs, ptr(bias), ptr(y), b, p, c, dt)
         ctx.save_for_backward(x, gain_c, stats)

@@ -169,7 +169,7 @@ EX_CASES.update({
     "1x1_c416": ("convT", 4, 1, 1, 192, 416, 1, 1, 0, "fwd"),
     "featattn_dgrad": ("conv", 6, 16, 16, 64, 16, 16, 1, 0, "dgrad"),     # full-extent kernel: 2 live taps of 16 per tile
 })
-EX_MODES = ["o32", "o16", "o16act", "o16both", "both_aux", "o16_aux", "o16_aux16"]
+EX_MODES = ["o32", "o16", "o16act", "o16both", "o16dact", "both_aux", "o16_aux", "o16_aux16", "o16_auxfac16"]
 
 
 @pytest.mark.parametrize("mode", EX_MODES)
@@ -206,10 +206,13 @@ def test_tc_ex_matches_v1(name, mode):
     ref = ref[..., :n]
 
     want32 = mode in ("o32", "both_aux")
-    want16 = mode in ("o16", "o16both", "both_aux", "o16_aux", "o16_aux16")       # bf16 of the accumulator
-    want16a = mode in ("o16act", "o16both")                                        # bf16 of RootTanh(accumulator)
+    want16 = mode in ("o16", "o16both", "o16dact", "both_aux", "o16_aux", "o16_aux16", "o16_auxfac16")   # bf16 of the accumulator
+    want16a = mode in ("o16act", "o16both", "o16dact")                             # bf16 of RootTanh(accumulator)
+    dact = mode == "o16dact"                                                       # out16 holds RootTanh'(accumulator) instead
     use_aux = "aux" in mode
-    aux16 = mode.endswith("aux16")
+    aux16 = mode.endswith("16") and use_aux
+    auxfac = "auxfac" in mode                                                      # aux is the factor itself
+    flags = (1 if auxfac else 0) | (2 if dact else 0)
     ld16 = (n + 7) // 8 * 8 + 8
     ld_aux = ((n + 7) // 8 * 8 + 8) if aux16 else ((n + 3) // 4 * 4 + 4)
     got32 = torch.full(out_shape, -7.0, device=DEV) if want32 else None
@@ -226,9 +229,11 @@ def test_tc_ex_matches_v1(name, mode):
                                           1 if aux16 else 0) != 1:
         pytest.skip("weight-bound shape: stays on the split-K path of k_conv_tc")
     call("lb_conv_tc_gemm_ex", ptr(src), ptr(packed), ptr(alpha), ptr(bias), ptr(got32), ptr(got16), ptr(got16a),
-         ld16 if any16 else 0, ptr(aux), ld_aux if use_aux else 0, 1 if aux16 else 0, ctypes.byref(g))
+         ld16 if any16 else 0, ptr(aux), ld_aux if use_aux else 0, 1 if aux16 else 0, flags, ctypes.byref(g))
     torch.cuda.synchronize()
-    exp = ref * _roottanh_grad(aux[..., :n].float()) if use_aux else ref
+    exp = ref
+    if use_aux:
+        exp = ref * (aux[..., :n].float() if auxfac else _roottanh_grad(aux[..., :n].float()))
     scale = exp.abs().max().item()
     if want32:
         assert torch.all(got32[..., n:] == -7.0), "fp32 store outside its channel slice"
@@ -236,12 +241,13 @@ def test_tc_ex_matches_v1(name, mode):
         assert err <= 2e-4 * scale + 1e-5, f"{name}/{mode}: fp32 max err {err:.3e} vs scale {scale:.3e}"
     if want16:
         assert torch.all(got16[..., n:].float() == -7.0), "bf16 store outside its channel slice"
-        err = (got16[..., :n].float() - exp).abs().max().item()
-        assert err <= 6e-3 * scale + 1e-5, f"{name}/{mode}: bf16 max err {err:.3e}"
+        exp16 = _roottanh_grad(exp) if dact else exp
+        err = (got16[..., :n].float() - exp16).abs().max().item()
+        assert err <= 6e-3 * exp16.abs().max().item() + 1e-5, f"{name}/{mode}: bf16 max err {err:.3e}"
     if want16a:
         assert torch.all(got16a[..., n:].float() == -7.0), "bf16 (activated) store outside its channel slice"
         # with a stored pre-activation the function value belongs to the STORED (bf16-rounded) argument
-        arg = got16[..., :n].float() if want16 else exp
+        arg = got16[..., :n].float() if (want16 and not dact) else exp
         exp16 = _roottanh(arg)
         err = (got16a[..., :n].float() - exp16).abs().max().item()
         assert err <= 6e-3 * exp16.abs().max().item() + 1e-5, f"{name}/{mode}: activated bf16 max err {err:.3e}"
