@@ -336,7 +336,9 @@ static int live_taps_axis(const lb_conv_geom* g, int k, int tile, int in_extent)
 // phase: the pipeline never drains between tiles) and whenever it can skip dead taps (full-extent feature-attention
 // kernels, 5x5 kernels on 2x2 maps); many-tap small-channel tiles keep k_conv_tc, whose 3-4 co-resident CTAs per SM
 // hide more TMA latency, and weight-bound shapes keep its split-K.
+extern "C" int lb_tc2_halo_eligible(const lb_conv_geom* g);
 static bool prefer_persistent(const lb_conv_geom* g) {
+  if (lb_tc2_halo_eligible(g)) return true;        // many-tap tiles served from one halo tile: the persistent kernel wins
   const int sp = g->mode == 1 ? g->stride : 1;
   const int dst_w = (g->out_w + sp - 1) / sp, dst_h = (g->out_h + sp - 1) / sp;
   const int tw = pow2_ceil(dst_w) < kBlockM ? pow2_ceil(dst_w) : kBlockM;

@@ -18,12 +18,15 @@
 //  * one CTA per SM walks a static list of (pixel tile, channel tile, phase) work items;
 //  * the TMEM accumulator is double buffered: the MMA warp fills stage (t+1)&1 while the epilogue drains t&1,
 //    and the TMA producer runs ahead across tile boundaries, so per-tile fixed latencies overlap with math;
-//  * the epilogue (8 warps: 2 per TMEM lane quarter, alternating 32-column slabs) moves
+//  * the epilogue (16 warps: 4 per TMEM lane quarter, each taking every 4th 32-column slab; 8 warps when the staging
+//    buffers of 16 would not fit) moves
 //    tcgen05.ld -> registers -> 128B-swizzled shared slab -> cp.async.bulk.tensor store.  Every global write is a
 //    full-line TMA store of a 4-D box of the (possibly parity-strided) output view, clipped by the tensor map at the
 //    tensor edges; `aux` slabs arrive the same way through per-warp mbarriers, double buffered;
 //  * the last K chunk issues only the k16 steps that hold real channels.
-// Warp roles (320 threads): 0 = TMA producer, 1 = TMEM alloc + MMA issuer, 2-9 = epilogue.
+// Warp roles (up to 576 threads): 0 = TMA producer, 1 = TMEM alloc + MMA issuer, 2.. = epilogue.  The epilogue of the
+// C <= 96 layers costs more than their MMAs (RootTanh: ~25 instructions, 4 of them MUFU, per output element against
+// 2*K flops on the tensor core), and with 2 warps per scheduler it ran latency-bound at a third of its issue rate.
 #include <stdlib.h>
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -35,7 +38,7 @@ constexpr int kBlockK = 64;                      // bf16 elements = 128 bytes = 
 constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KB
 constexpr int kMaxViews = 4;
 constexpr int kSlab = 32;                        // fp32 columns per epilogue slab (128 B per row)
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;                    // at most: 4 per TMEM lane quarter; launches use 8 or 16 (Tc2Params::epi_warps)
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kSmemLimit = 227 * 1024 - 1024;      // dynamic; 1 KB left for the static barriers
 
@@ -59,12 +62,19 @@ struct Tc2Params {
   int kh, kw, stride, pad, mode;
   int rows_per_tap, view_empty;
   int ebw, ebh, ebb;                  // 32-row sub-box of one epilogue warp
+  int epi_warps;                      // 8 or 16
   int has_o32, has_o16, has_o16a, has_aux;
   int aux_bf16;                       // aux slabs are bf16 (64-byte rows) instead of fp32 (128-byte rows)
   int aux_factor;                     // aux holds the factor itself (RootTanh' precomputed by the forward pass)
   int o16_dact;                       // out16 receives RootTanh'(acc) instead of acc
   uint32_t tmem_cols;
   uint32_t tab_base; int max_tp;      // per-phase tap table in shared memory: max_tp entries per phase
+  // halo mode: ONE A box per (source view, 64-channel chunk) covers every tap shift of that view; each tap's operand
+  // is the same shared-memory tile addressed through the UMMA descriptor (start row = shift, 8-row groups 16 rows apart).
+  int halo;                           // 0 / 1
+  int a_stages; uint32_t a_stage_bytes, a_base;   // ring of halo tiles (bytes; a_base relative to the 1 KB aligned base)
+  int n_views;
+  uint32_t htab_base;                 // view / tap tables of the halo mode (after the tap table)
   int resident;                       // 1: the weights of one output phase stay in shared memory (res_base), stages carry A only
   uint32_t res_base, b_tile_bytes;
   uint32_t epi_base, epi_per_warp, off_o32, off_o16, off_o16a, off_aux, aux_bytes;   // bytes; epi_base relative to the 1 KB aligned base
@@ -193,6 +203,45 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 // which capped the small-channel layers at ~3 us per tile.  Entry e of phase ph: tapv = {dy, dx, view, weight row of the
 // tap}, tape = {view extent y, x} for the liveness test.
 constexpr int kMaxTapsPhase = 64;
+constexpr int kHaloPitch = 16;                   // pixels per halo-tile row: a multiple of 8, so every 8-row group of every tap
+                                                 // shift starts at the same swizzle phase (descriptor base offset)
+// halo-mode tables (built once per CTA).  hview[phase * 4 + view] = {dxmin, dymin, taps of this view, index of its first tap};
+// htap[phase * 64 + j] = {row offset of the tap's shift inside the halo tile, weight row of the tap}, taps sorted by view.
+__device__ __forceinline__ void build_halo_tables(const Tc2Params& p, const int4* tapv, int4* hview, int2* htap) {
+  const int phases = p.sp * p.sp;
+  if ((int)threadIdx.x >= phases) return;
+  const int ph = threadIdx.x;
+  const int py = ph >> p.sh, px = ph & (p.sp - 1);
+  const AxisTaps ay = axis_taps(p, p.kh, py), ax = axis_taps(p, p.kw, px);
+  const int nt = ay.cnt * ax.cnt;
+  int first = 0;
+  for (int v = 0; v < kMaxViews; ++v) {
+    int dxmin = 1 << 20, dymin = 1 << 20, cnt = 0;
+    for (int l = 0; l < nt; ++l) {
+      const int4 t = tapv[ph * p.max_tp + l];
+      if (t.z != v) continue;
+      dxmin = min(dxmin, t.y); dymin = min(dymin, t.x); ++cnt;
+    }
+    int j = first;
+    for (int l = 0; l < nt; ++l) {
+      const int4 t = tapv[ph * p.max_tp + l];
+      if (t.z != v) continue;
+      htap[ph * kMaxTapsPhase + j] = make_int2((t.x - dymin) * kHaloPitch + (t.y - dxmin), t.w);
+      ++j;
+    }
+    hview[ph * kMaxViews + v] = make_int4(cnt ? dxmin : 0, cnt ? dymin : 0, cnt, first);
+    first = j;
+  }
+}
+// K-major SWIZZLE_128B descriptor whose 8-row groups are `sbo_bytes` apart and whose first row sits `row` rows (of 128
+// bytes) into a 1 KB aligned tile: the start address is not aligned to the 1 KB swizzle pattern, so the descriptor
+// carries the pattern phase of its first row (matrix base offset, bits [49,52) = (start address >> 7) & 7).
+__device__ __forceinline__ uint64_t smem_desc_sw128_row(uint32_t tile_addr, int row, uint32_t k_bytes, uint32_t sbo_bytes, int use_base) {
+  const uint32_t addr = tile_addr + (uint32_t)row * 128u + k_bytes;
+  uint64_t d = tc::smem_desc_sw128(addr, 16, sbo_bytes);
+  if (use_base) d |= (uint64_t)((addr >> 7) & 7u) << 49;
+  return d;
+}
 __device__ __forceinline__ void build_tap_table(const Tc2Params& p, int4* tapv, int2* tape) {
   const int phases = p.sp * p.sp;
   for (int idx = threadIdx.x; idx < phases * p.max_tp; idx += blockDim.x) {
@@ -223,20 +272,28 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bar_full[8], bar_empty[8], bar_tfull[2], bar_tempty[2], bar_aux[kEpiWarps][2];
   __shared__ __align__(8) uint64_t bar_bfull, bar_bfree;          // resident weights: loaded / no longer read
+  __shared__ __align__(8) uint64_t bar_afull[4], bar_aempty[4];   // halo mode: ring of halo tiles
   __shared__ uint32_t tmem_slot;
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int b_bytes = p.block_n * kBlockK * 2;
-  const int stage_bytes = p.resident ? kABytes : kABytes + ((b_bytes + 1023) & ~1023);
+  const int stage_bytes = p.halo ? (int)p.b_tile_bytes : (p.resident ? kABytes : kABytes + ((b_bytes + 1023) & ~1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int4* tapv = reinterpret_cast<int4*>(smem + p.tab_base);
   int2* tape = reinterpret_cast<int2*>(smem + p.tab_base + 4 * kMaxTapsPhase * sizeof(int4));
   build_tap_table(p, tapv, tape);
+  int4* hview = reinterpret_cast<int4*>(smem + p.htab_base);
+  int2* htap = reinterpret_cast<int2*>(smem + p.htab_base + 4 * kMaxViews * sizeof(int4));
+  if (p.halo) {
+    __syncthreads();
+    build_halo_tables(p, tapv, hview, htap);
+  }
 
   if (threadIdx.x == 0) {
+    for (int a = 0; a < 4; ++a) { tc::mbar_init(&bar_afull[a], 1); tc::mbar_init(&bar_aempty[a], 1); }
     for (int s = 0; s < p.stages; ++s) { tc::mbar_init(&bar_full[s], 1); tc::mbar_init(&bar_empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { tc::mbar_init(&bar_tfull[a], 1); tc::mbar_init(&bar_tempty[a], kEpiWarps); }
-    for (int w = 0; w < kEpiWarps; ++w) { tc::mbar_init(&bar_aux[w][0], 1); tc::mbar_init(&bar_aux[w][1], 1); }
+    for (int a = 0; a < 2; ++a) { tc::mbar_init(&bar_tfull[a], 1); tc::mbar_init(&bar_tempty[a], p.epi_warps); }
+    for (int w = 0; w < p.epi_warps; ++w) { tc::mbar_init(&bar_aux[w][0], 1); tc::mbar_init(&bar_aux[w][1], 1); }
     tc::mbar_init(&bar_bfull, 1); tc::mbar_init(&bar_bfree, 1);
     tc::fence_barrier_init();
   }
@@ -255,8 +312,32 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
     if (tc::elect_one()) {
       int st = 0; uint32_t ph = 0;                        // ring position, runs on across tiles
       int res_phase = -1; uint32_t epochs = 0;            // resident weights: phase they belong to, sets loaded so far
+      int ast = 0; uint32_t aph = 0;                      // halo ring position
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const TileCoord c = decode_tile(p, tile);
+        if (p.halo) {
+          // per (view, channel chunk): one halo box, then the weight tile of every tap of that view
+          for (int v = 0; v < p.n_views; ++v) {
+            const int4 hv = hview[c.phase * kMaxViews + v];
+            if (hv.z == 0) continue;
+            const int cb = ((p.view_empty >> v) & 1) ? p.batch : c.b0;
+            for (int kc = 0; kc < p.kchunks; ++kc) {
+              tc::mbar_wait(&bar_aempty[ast], aph ^ 1u);
+              tc::mbar_arrive_expect_tx(&bar_afull[ast], p.a_stage_bytes);
+              tc::tma_load_4d(smem + p.a_base + ast * p.a_stage_bytes, &maps.a[v], &bar_afull[ast], kc * kBlockK, c.x0 + hv.x,
+                              c.y0 + hv.y, cb);
+              if (++ast == p.a_stages) { ast = 0; aph ^= 1u; }
+              for (int j = 0; j < hv.z; ++j) {
+                const int2 ht = htap[c.phase * kMaxTapsPhase + hv.w + j];
+                tc::mbar_wait(&bar_empty[st], ph ^ 1u);
+                tc::mbar_arrive_expect_tx(&bar_full[st], (uint32_t)b_bytes);
+                tc::tma_load_2d(smem + st * stage_bytes, &maps.b, &bar_full[st], kc * kBlockK, ht.y + c.n0);
+                if (++st == p.stages) { st = 0; ph ^= 1u; }
+              }
+            }
+          }
+          continue;
+        }
         const AxisTaps ay = axis_taps(p, p.kh, c.py), ax = axis_taps(p, p.kw, c.px);
         if (p.resident && c.phase != res_phase) {
           // every tap x channel chunk of this phase, once; the previous set must have been read by its last MMA
@@ -309,6 +390,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
       int st = 0; uint32_t ph = 0;
       int lt = 0;
       int res_phase = -1; uint32_t epochs = 0;
+      int ast = 0; uint32_t aph = 0;                      // halo ring position
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
         const TileCoord c = decode_tile(p, tile);
         const AxisTaps ay = axis_taps(p, p.kh, c.py), ax = axis_taps(p, p.kw, c.px);
@@ -322,6 +404,37 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
         tc::mbar_wait(&bar_tempty[acc], (((uint32_t)lt >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
         tc::tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.acc_stride);
+        if (p.halo) {
+          bool first = true;
+          for (int v = 0; v < p.n_views; ++v) {
+            const int4 hv = hview[c.phase * kMaxViews + v];
+            if (hv.z == 0) continue;
+            for (int kc = 0; kc < p.kchunks; ++kc) {
+              tc::mbar_wait(&bar_afull[ast], aph);
+              tc::tc_fence_after();
+              const uint32_t sa = tc::smem_u32(smem + p.a_base + ast * p.a_stage_bytes);
+              const int nk = (kc == p.kchunks - 1) ? k16_last : kBlockK / 16;
+              for (int j = 0; j < hv.z; ++j) {
+                const int2 ht = htap[c.phase * kMaxTapsPhase + hv.w + j];
+                tc::mbar_wait(&bar_full[st], ph);
+                tc::tc_fence_after();
+                const uint32_t sb = tc::smem_u32(smem + st * stage_bytes);
+                for (int k = 0; k < nk; ++k) {
+                  const uint64_t ad = smem_desc_sw128_row(sa, ht.x, (uint32_t)k * 32u, kHaloPitch * 128u, p.halo & 1);
+                  const uint64_t bd = tc::smem_desc_sw128(sb + k * 32, 16, 1024);
+                  tc::umma_bf16(tmem_d, ad, bd, idesc, (first && k == 0) ? 0u : 1u);
+                }
+                first = false;
+                tc::umma_commit(&bar_empty[st]);
+                if (++st == p.stages) { st = 0; ph ^= 1u; }
+              }
+              tc::umma_commit(&bar_aempty[ast]);
+              if (++ast == p.a_stages) { ast = 0; aph ^= 1u; }
+            }
+          }
+          tc::umma_commit(&bar_tfull[acc]);
+          continue;
+        }
         int ylo, yhi, xlo, xhi;
         axis_range(p, ay, c.py, c.y0, p.tile_h, p.in_h, ylo, yhi);
         axis_range(p, ax, c.px, c.x0, p.tile_w, p.in_w, xlo, xhi);
@@ -361,10 +474,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
       }
     }
   } else {
-    // ===================== epilogue (warps 2..9) =====================
+    // ===================== epilogue (warps 2..) =====================
     const int ew = warp - 2;
     const int q = warp & 3;                       // TMEM lane quarter this warp may read
-    const int half = ew >> 2;                     // slabs of parity `half`
+    const int half = ew >> 2;                     // this warp takes slabs half, half + ngrp, ...
+    const int ngrp = p.epi_warps >> 2;
     const int r0 = q * 32;                        // first tile row of this warp
     const int w_off = r0 % p.tile_w, h_off = (r0 / p.tile_w) % p.tile_h, b_off = r0 / (p.tile_w * p.tile_h);
     uint8_t* ebase = smem + p.epi_base + (uint32_t)ew * p.epi_per_warp;
@@ -400,7 +514,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
                         c.y0 + h_off, c.b0 + b_off);
       }
       ++a_issued;
-      a_slab += 2;
+      a_slab += ngrp;
     };
     if (p.has_aux) aux_issue();
 
@@ -412,7 +526,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
       const int nsl = (min(p.block_n, p.out_c - c.n0) + kSlab - 1) / kSlab;
       tc::mbar_wait(&bar_tfull[acc], ((uint32_t)lt >> 1) & 1u);
       tc::tc_fence_after();
-      for (int slab = half; slab < nsl; slab += 2) {
+      for (int slab = half; slab < nsl; slab += ngrp) {
         if (p.has_aux) aux_issue();               // next job's aux while this one is processed
         float v[32];
         __syncwarp();
@@ -548,6 +662,49 @@ int pow2_ceil(int v) { int r = 1; while (r < v) r <<= 1; return r; }
 
 }  // namespace
 
+// Halo mode: can every tap of a source view be served from ONE shared-memory tile of that view?  Returns the largest
+// vertical shift span over (phase, view) pairs, or -1 when the geometry does not qualify (single-tap layers gain nothing;
+// full-extent feature-attention kernels have mostly dead taps, which only the per-tap path skips; small maps need
+// batch-spanning tiles, whose 8-row groups are not equidistant in a halo tile).
+static int halo_span_y(const lb_conv_geom* g) {
+  static const int env_halo = getenv("LB_TC2_HALO") ? atoi(getenv("LB_TC2_HALO")) : 1;
+  if (!env_halo) return -1;
+  const int sp = g->mode == 1 ? g->stride : 1, s = g->stride, sh = s == 2 ? 1 : 0;
+  const int dst_w = (g->out_w + sp - 1) / sp, dst_h = (g->out_h + sp - 1) / sp;
+  if (g->kh > 8 || g->kw > 8 || dst_w < 8 || dst_h < 16) return -1;
+  int span_y = 0, span_x = 0, max_taps = 0;
+  for (int ph = 0; ph < sp * sp; ++ph) {
+    const int py = ph / sp, px = ph % sp;
+    int lo_y[kMaxViews], hi_y[kMaxViews], lo_x[kMaxViews], hi_x[kMaxViews], cnt[kMaxViews] = {0, 0, 0, 0};
+    int taps = 0;
+    for (int ty = 0; ty < g->kh; ++ty)
+      for (int tx = 0; tx < g->kw; ++tx) {
+        int dy, dx, view = 0;
+        if (g->mode == 1) {
+          if (((py + g->pad - ty) & (s - 1)) || ((px + g->pad - tx) & (s - 1))) continue;   // tap of another phase
+          dy = (py + g->pad - ty) >> sh; dx = (px + g->pad - tx) >> sh;
+        } else {
+          const int oy = ty - g->pad, ox = tx - g->pad;
+          dy = oy >> sh; dx = ox >> sh;
+          view = ((oy & (s - 1)) << sh) + (ox & (s - 1));
+        }
+        if (!cnt[view]) { lo_y[view] = hi_y[view] = dy; lo_x[view] = hi_x[view] = dx; }
+        lo_y[view] = dy < lo_y[view] ? dy : lo_y[view]; hi_y[view] = dy > hi_y[view] ? dy : hi_y[view];
+        lo_x[view] = dx < lo_x[view] ? dx : lo_x[view]; hi_x[view] = dx > hi_x[view] ? dx : hi_x[view];
+        ++cnt[view]; ++taps;
+      }
+    for (int v = 0; v < kMaxViews; ++v)
+      if (cnt[v]) {
+        span_y = hi_y[v] - lo_y[v] > span_y ? hi_y[v] - lo_y[v] : span_y;
+        span_x = hi_x[v] - lo_x[v] > span_x ? hi_x[v] - lo_x[v] : span_x;
+      }
+    max_taps = taps > max_taps ? taps : max_taps;
+  }
+  if (max_taps < 2 || span_x > kHaloPitch - 8) return -1;
+  return span_y;
+}
+extern "C" int lb_tc2_halo_eligible(const lb_conv_geom* g) { return g && halo_span_y(g) >= 0 ? 1 : 0; }
+
 // Does the persistent kernel cover this geometry and these operands?  (Otherwise lb_conv_tc_gemm stays on k_conv_tc.)
 static bool tc2_ok(const lb_conv_geom* g, const void* out32, const void* out16, const void* out16a, int ld16, const void* aux, int ld_aux,
                    int aux_dtype) {
@@ -596,6 +753,13 @@ extern "C" int lb_conv_tc_gemm_ex(const void* in_bf16, const void* w_packed, con
   int rest = kBlockM / p.tile_w;
   p.tile_h = pow2_ceil(dst_h) < rest ? pow2_ceil(dst_h) : rest;
   p.tile_b = rest / p.tile_h;
+  int span_y = halo_span_y(g);
+  p.halo = 0;
+  if (span_y >= 0) {                   // 8 x 16 pixel tiles of one image: 8-row groups = rows of the tile, 16 halo rows apart
+    static const int env_halo = getenv("LB_TC2_HALO") ? atoi(getenv("LB_TC2_HALO")) : 1;
+    p.halo = env_halo == 2 ? 2 : 1;    // 2: descriptors without the base-offset field (debugging aid)
+    p.tile_w = 8; p.tile_h = 16; p.tile_b = 1;
+  }
   p.tiles_w = (dst_w + p.tile_w - 1) / p.tile_w;
   p.tiles_h = (dst_h + p.tile_h - 1) / p.tile_h;
   p.tiles_b = (g->batch + p.tile_b - 1) / p.tile_b;
@@ -618,8 +782,10 @@ extern "C" int lb_conv_tc_gemm_ex(const void* in_bf16, const void* w_packed, con
   p.off_o16a = off; if (out16a) off += 2048;
   p.off_aux = off; if (aux) off += 2 * p.aux_bytes;
   p.epi_per_warp = (off + 1023) & ~1023u;
-  const int tab_bytes = 4 * kMaxTapsPhase * (int)(sizeof(int4) + sizeof(int2));      // 6 KB
-  const int epi_bytes = (int)p.epi_per_warp * kEpiWarps + tab_bytes;
+  p.epi_warps = p.epi_per_warp * 16 <= 100 * 1024 ? 16 : 8;
+  const int tap_tab_bytes = 4 * kMaxTapsPhase * (int)(sizeof(int4) + sizeof(int2));  // 6 KB
+  const int tab_bytes = tap_tab_bytes + 4096;                                         // + the halo-mode view / tap tables
+  const int epi_bytes = (int)p.epi_per_warp * p.epi_warps + tab_bytes;
   p.max_tp = g->mode == 1 ? ((g->kh + p.sp - 1) / p.sp) * ((g->kw + p.sp - 1) / p.sp) : g->kh * g->kw;
   if (p.max_tp > kMaxTapsPhase) return LB_EUNSUPPORTED;
 
@@ -657,16 +823,43 @@ extern "C" int lb_conv_tc_gemm_ex(const void* in_bf16, const void* w_packed, con
     static const int env_stages = getenv("LB_TC2_STAGES") ? atoi(getenv("LB_TC2_STAGES")) : 0;
     if (env_stages >= 2 && env_stages < stages) { stages = env_stages; if (p.resident) p.res_base = (uint32_t)(stages * stage_bytes); }
   }
+  p.a_stages = 0; p.a_stage_bytes = 0; p.a_base = 0;
+  if (p.halo) {
+    // B ring (one weight tile per stage) + A ring (one halo tile per stage)
+    p.a_stage_bytes = (uint32_t)(kHaloPitch * (16 + span_y) * 128);
+    const int budget = kSmemLimit - 1024 - epi_bytes;
+    int a_st = 3, b_st = (budget - a_st * (int)p.a_stage_bytes) / (int)p.b_tile_bytes;
+    if (b_st < 4) { a_st = 2; b_st = (budget - a_st * (int)p.a_stage_bytes) / (int)p.b_tile_bytes; }
+    if (b_st < 3 || p.resident) {
+      p.halo = 0;                      // does not fit: back to per-tap boxes with the generic tile shape
+      p.tile_w = pow2_ceil(dst_w) < kBlockM ? pow2_ceil(dst_w) : kBlockM;
+      rest = kBlockM / p.tile_w;
+      p.tile_h = pow2_ceil(dst_h) < rest ? pow2_ceil(dst_h) : rest;
+      p.tile_b = rest / p.tile_h;
+      p.tiles_w = (dst_w + p.tile_w - 1) / p.tile_w;
+      p.tiles_h = (dst_h + p.tile_h - 1) / p.tile_h;
+      p.tiles_b = (g->batch + p.tile_b - 1) / p.tile_b;
+      p.ebw = p.tile_w < 32 ? p.tile_w : 32;
+      p.ebh = p.tile_h < 32 / p.ebw ? p.tile_h : 32 / p.ebw;
+      p.ebb = 32 / (p.ebw * p.ebh);
+    } else {
+      if (b_st > 8) b_st = 8;
+      stages = b_st; stage_bytes = (int)p.b_tile_bytes;
+      p.a_stages = a_st;
+      p.a_base = (uint32_t)(stages * stage_bytes);
+    }
+  }
   p.block_n = bn; p.n_tiles = (g->out_c + bn - 1) / bn; p.stages = stages;
   p.acc_stride = (bn + 31) / 32 * 32;
   p.tmem_cols = (uint32_t)pow2_ceil(2 * p.acc_stride < 32 ? 32 : 2 * p.acc_stride);
-  p.epi_base = (uint32_t)(stages * stage_bytes) + (p.resident ? (uint32_t)(((g->mode == 1 ? ((g->kh + p.sp - 1) / p.sp) * ((g->kw + p.sp - 1) / p.sp) : g->kh * g->kw)) * p.kchunks) * p.b_tile_bytes : 0u);
+  p.epi_base = (uint32_t)(stages * stage_bytes) + (uint32_t)p.a_stages * p.a_stage_bytes + (p.resident ? (uint32_t)(((g->mode == 1 ? ((g->kh + p.sp - 1) / p.sp) * ((g->kw + p.sp - 1) / p.sp) : g->kh * g->kw)) * p.kchunks) * p.b_tile_bytes : 0u);
   p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_b * p.n_tiles * p.sp * p.sp;
   p.d_nt = lb_make_fastdiv(p.n_tiles); p.d_tw = lb_make_fastdiv(p.tiles_w); p.d_th = lb_make_fastdiv(p.tiles_h); p.d_tb = lb_make_fastdiv(p.tiles_b);
 
   // source views: mode 0 with stride 2 -> 4 parity views; otherwise one dense view
   const int nv = (g->mode == 0) ? g->stride * g->stride : 1;
   const int vs = (g->mode == 0) ? g->stride : 1;
+  p.n_views = nv;
   p.view_empty = 0;
   const char* base = reinterpret_cast<const char*>(in_bf16);
   for (int v = 0; v < kMaxViews; ++v) {
@@ -677,7 +870,8 @@ extern "C" int lb_conv_tc_gemm_ex(const void* in_bf16, const void* w_packed, con
     const uint64_t dims[4] = {(uint64_t)g->in_c, (uint64_t)vw, (uint64_t)vh, (uint64_t)g->batch};
     const uint64_t strides[3] = {(uint64_t)vs * g->ld_in * 2, (uint64_t)vs * g->in_w * g->ld_in * 2,
                                  (uint64_t)g->in_h * g->in_w * g->ld_in * 2};
-    const uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)p.tile_w, (uint32_t)p.tile_h, (uint32_t)p.tile_b};
+    uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)p.tile_w, (uint32_t)p.tile_h, (uint32_t)p.tile_b};
+    if (p.halo) { box[1] = kHaloPitch; box[2] = (uint32_t)(16 + span_y); box[3] = 1; }   // one box serves every tap shift of the view
     const char* vbase = ((p.view_empty >> v) & 1) ? base : base + ((size_t)qy * g->in_w + qx) * g->ld_in * 2;
     int rc = tc::make_map(&maps.a[v], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, vbase, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
@@ -732,7 +926,8 @@ extern "C" int lb_conv_tc_gemm_ex(const void* in_bf16, const void* w_packed, con
       if (rc) return rc;
     }
   }
-  p.tab_base = p.epi_base + p.epi_per_warp * kEpiWarps;
+  p.tab_base = p.epi_base + p.epi_per_warp * p.epi_warps;
+  p.htab_base = p.tab_base + (uint32_t)tap_tab_bytes;
   const int smem_bytes = (int)p.epi_base + epi_bytes + 1024;
   static bool attr_set = false;
   if (!attr_set) {
@@ -741,7 +936,7 @@ extern "C" int lb_conv_tc_gemm_ex(const void* in_bf16, const void* w_packed, con
     attr_set = true;
   }
   const int grid = p.total_tiles < LB_SMS ? p.total_tiles : LB_SMS;
-  k_conv_tc2<<<grid, kThreads, smem_bytes, lb_s(s)>>>(maps, p);
+  k_conv_tc2<<<grid, 64 + 32 * p.epi_warps, smem_bytes, lb_s(s)>>>(maps, p);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }

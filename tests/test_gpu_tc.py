@@ -168,6 +168,14 @@ EX_CASES.update({
     "1x1_c352": ("conv", 4, 2, 2, 32, 352, 1, 1, 0, "fwd"),              # channel tile not a multiple of the 32-column slab
     "1x1_c416": ("convT", 4, 1, 1, 192, 416, 1, 1, 0, "fwd"),
     "featattn_dgrad": ("conv", 6, 16, 16, 64, 16, 16, 1, 0, "dgrad"),     # full-extent kernel: 2 live taps of 16 per tile
+    # halo mode (one shared-memory tile per source view serves every tap shift; 8 x 16 pixel tiles)
+    "halo_convT4_64": ("convT", 3, 64, 64, 96, 96, 4, 2, 1, "fwd"),       # 4 output phases x 4 taps, two channel chunks
+    "halo_3x3_c48": ("conv", 2, 64, 48, 48, 48, 3, 1, 1, "fwd"),          # 9 taps of one view, partial channel chunk
+    "halo_3x3_dgrad": ("conv", 2, 40, 24, 48, 48, 3, 1, 1, "dgrad"),      # mode 1 stride 1, tiles overhang both axes
+    "halo_5x5s2_c32": ("conv", 2, 64, 64, 32, 32, 5, 2, 2, "fwd"),        # 4 parity views: 9 / 6 / 6 / 4 taps
+    "halo_5x5s2_dgrad": ("conv", 2, 64, 64, 32, 32, 5, 2, 2, "dgrad"),    # mode 1 stride 2: 4 phases, up to 9 taps each
+    "halo_convT4_dgrad": ("convT", 2, 32, 32, 192, 192, 4, 2, 1, "dgrad"),  # mode 0 stride 2, 4 taps per view, 3 chunks
+    "halo_odd": ("conv", 3, 21, 19, 40, 24, 3, 1, 1, "fwd"),
 })
 EX_MODES = ["o32", "o16", "o16act", "o16both", "o16dact", "both_aux", "o16_aux", "o16_aux16", "o16_auxfac16"]
 
@@ -202,7 +210,9 @@ def test_tc_ex_matches_v1(name, mode):
     ref = torch.full(out_shape, -7.0, device=DEV)
     packed = torch.empty(_lib.lib().lb_conv_tc_packed_elems(ctypes.byref(g)), dtype=torch.bfloat16, device=DEV)
     call("lb_conv_tc_pack", ptr(wt), ptr(packed), ctypes.byref(g))
-    call("lb_conv_tc_gemm", ptr(src), ptr(packed), ptr(alpha), ptr(bias), ptr(ref), ctypes.byref(g))
+    # reference: the fp32 SIMT gather-GEMM on the same bf16-rounded operands (an independent kernel: lb_conv_tc_gemm would
+    # route halo-eligible shapes through the persistent kernel under test)
+    call("lb_conv_gemm", ptr(src.float().contiguous()), ptr(wt), ptr(alpha), ptr(bias), ptr(ref), ctypes.byref(g))
     ref = ref[..., :n]
 
     want32 = mode in ("o32", "both_aux")
