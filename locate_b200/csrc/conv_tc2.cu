@@ -148,15 +148,16 @@ __device__ __forceinline__ float tanh_approx(float x) { float y; asm("tanh.appro
 __device__ __forceinline__ float roottanh_only_fast(float x) {
   return sqrt_approx(sqrt_approx(fmaf(x, x, 1.0f))) * tanh_approx(x);
 }
-// RootTanh and RootTanh' together: every intermediate is shared (4 MUFU ops for both)
+// RootTanh and RootTanh' together from shared intermediates, 3 MUFU ops (tanh, rsqrt, sqrt) -- the MUFU pipe (16 lanes
+// per clock per SM) is what bounds the epilogue of the C <= 96 layers.  sech^2 = 1 - tanh^2 carries the absolute error
+// of tanh.approx (~5e-4) times 2, harmless while the sech^2 term matters (|x| < ~4: relative error of RootTanh' <= 0.9 %,
+// the bf16 rounding of the stored factor is 0.4 %); beyond |x| = 4.5, where it contributes < 0.5 %, the term is dropped.
 __device__ __forceinline__ void roottanh_both_fast(float x, float& f, float& df) {
-  const float e = ex2_approx(-2.8853900817779268f * fabsf(x));
-  const float r = rcp_approx(1.0f + e);
-  const float th = copysignf((1.0f - e) * r, x);
-  const float s2 = 4.0f * e * r * r;
+  const float th = tanh_approx(x);
   const float q = fmaf(x, x, 1.0f);
   const float rs = rsqrt_approx(q);                                  // q^(-1/2)
   const float q34 = rs * sqrt_approx(rs);                            // q^(-3/4)
+  const float s2 = fabsf(x) > 4.5f ? 0.0f : fmaf(-th, th, 1.0f);
   f = q * q34 * th;                                                  // q^(1/4) tanh
   df = fmaf(2.0f * q, s2, x * th) * 0.5f * q34;
 }
@@ -198,6 +199,66 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// ---- lean helpers for the single-thread producer / MMA loops -------------------------------------------------------
+// Those loops ARE the critical path of the small-channel layers (ncu: epilogue warps wait on the accumulator barrier,
+// the tensor pipe is 15 % busy, producer / MMA warps never wait -- they are executing ~100 scalar instructions per MMA).
+// Everything here works on 32-bit shared-window addresses computed once, and on precomputed descriptor halves.
+__device__ __forceinline__ void mbar_wait_a(uint32_t addr, uint32_t parity) {
+  uint32_t done = 0;
+#pragma unroll 1
+  for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, 0x989680;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void mbar_expect_tx_a(uint32_t addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_a(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+               "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_a(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+               "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void umma_commit_a(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ int2 lds_int2(uint32_t addr) {
+  int2 v;
+  asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ int4 lds_int4(uint32_t addr) {
+  int4 v;
+  asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+// descriptor = {hi, lo}: lo = start >> 4 | LBO(16 B) << 16; hi = SBO >> 4 | version 1 << 14 | SWIZZLE_128B << 29
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) { return ((smem_addr >> 4) & 0x3FFFu) | (1u << 16); }
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29); }
+__device__ __forceinline__ void umma_bf16_hl(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // Per-phase tap table (built once per CTA): the lone producer / MMA threads were spending ~500 dependent scalar
 // instructions per tile re-deriving each tap's shift, view and weight row (ncu: both warps busy, barely ever waiting),
 // which capped the small-channel layers at ~3 us per tile.  Entry e of phase ph: tapv = {dy, dx, view, weight row of the
@@ -233,15 +294,14 @@ __device__ __forceinline__ void build_halo_tables(const Tc2Params& p, const int4
     first = j;
   }
 }
-// K-major SWIZZLE_128B descriptor whose 8-row groups are `sbo_bytes` apart and whose first row sits `row` rows (of 128
-// bytes) into a 1 KB aligned tile: the start address is not aligned to the 1 KB swizzle pattern, so the descriptor
-// carries the pattern phase of its first row (matrix base offset, bits [49,52) = (start address >> 7) & 7).
-__device__ __forceinline__ uint64_t smem_desc_sw128_row(uint32_t tile_addr, int row, uint32_t k_bytes, uint32_t sbo_bytes, int use_base) {
-  const uint32_t addr = tile_addr + (uint32_t)row * 128u + k_bytes;
-  uint64_t d = tc::smem_desc_sw128(addr, 16, sbo_bytes);
-  if (use_base) d |= (uint64_t)((addr >> 7) & 7u) << 49;
-  return d;
-}
+// Halo-mode A descriptors: K-major SWIZZLE_128B whose 8-row groups are 16 rows (2 KB) apart and whose first row sits
+// `row` rows (of 128 bytes) into a 1 KB aligned tile.  The start address is then not aligned to the 1 KB swizzle pattern;
+// measured on B200: the tensor core applies the swizzle to the absolute shared-memory address (as TMA did when it wrote
+// the tile), so the descriptor's base-offset field (bits [49,52)) stays 0 -- setting it to (start >> 7) & 7 gives wrong
+// products (tests/test_gpu_tc.py halo_* cases).
+// (Descriptors are assembled from precomputed halves in the MMA loop: desc_lo / desc_hi above.)
+// Per-phase tap table (built once per CTA): entry e of phase ph: tapv = {dy, dx, view, weight row of the tap},
+// tape = {view extent y, x} for the liveness test of the per-tap path.
 __device__ __forceinline__ void build_tap_table(const Tc2Params& p, int4* tapv, int2* tape) {
   const int phases = p.sp * p.sp;
   for (int idx = threadIdx.x; idx < phases * p.max_tp; idx += blockDim.x) {
@@ -306,6 +366,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  // shared-window addresses, computed once (the compiler otherwise re-derives them from generic pointers at every use)
+  const uint32_t smem_a = tc::smem_u32(smem), htab_a = smem_a + p.htab_base;
+  const uint32_t bar_full_a = tc::smem_u32(&bar_full[0]), bar_empty_a = tc::smem_u32(&bar_empty[0]);
+  const uint32_t bar_afull_a = tc::smem_u32(&bar_afull[0]), bar_aempty_a = tc::smem_u32(&bar_aempty[0]);
+  const uint32_t bar_tfull_a = tc::smem_u32(&bar_tfull[0]);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -317,21 +382,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
         const TileCoord c = decode_tile(p, tile);
         if (p.halo) {
           // per (view, channel chunk): one halo box, then the weight tile of every tap of that view
+          const uint32_t hv_a = htab_a + (uint32_t)(c.phase * kMaxViews) * 16u, ht_a = htab_a + 4u * kMaxViews * 16u + (uint32_t)(c.phase * kMaxTapsPhase) * 8u;
           for (int v = 0; v < p.n_views; ++v) {
-            const int4 hv = hview[c.phase * kMaxViews + v];
+            const int4 hv = lds_int4(hv_a + (uint32_t)v * 16u);
             if (hv.z == 0) continue;
             const int cb = ((p.view_empty >> v) & 1) ? p.batch : c.b0;
+            const int cx = c.x0 + hv.x, cy = c.y0 + hv.y;
             for (int kc = 0; kc < p.kchunks; ++kc) {
-              tc::mbar_wait(&bar_aempty[ast], aph ^ 1u);
-              tc::mbar_arrive_expect_tx(&bar_afull[ast], p.a_stage_bytes);
-              tc::tma_load_4d(smem + p.a_base + ast * p.a_stage_bytes, &maps.a[v], &bar_afull[ast], kc * kBlockK, c.x0 + hv.x,
-                              c.y0 + hv.y, cb);
+              mbar_wait_a(bar_aempty_a + 8u * ast, aph ^ 1u);
+              mbar_expect_tx_a(bar_afull_a + 8u * ast, p.a_stage_bytes);
+              tma_load_4d_a(smem_a + p.a_base + ast * p.a_stage_bytes, &maps.a[v], bar_afull_a + 8u * ast, kc * kBlockK, cx, cy, cb);
               if (++ast == p.a_stages) { ast = 0; aph ^= 1u; }
               for (int j = 0; j < hv.z; ++j) {
-                const int2 ht = htap[c.phase * kMaxTapsPhase + hv.w + j];
-                tc::mbar_wait(&bar_empty[st], ph ^ 1u);
-                tc::mbar_arrive_expect_tx(&bar_full[st], (uint32_t)b_bytes);
-                tc::tma_load_2d(smem + st * stage_bytes, &maps.b, &bar_full[st], kc * kBlockK, ht.y + c.n0);
+                const int2 ht = lds_int2(ht_a + (uint32_t)(hv.w + j) * 8u);
+                mbar_wait_a(bar_empty_a + 8u * st, ph ^ 1u);
+                mbar_expect_tx_a(bar_full_a + 8u * st, (uint32_t)b_bytes);
+                tma_load_2d_a(smem_a + st * stage_bytes, &maps.b, bar_full_a + 8u * st, kc * kBlockK, ht.y + c.n0);
                 if (++st == p.stages) { st = 0; ph ^= 1u; }
               }
             }
@@ -361,12 +427,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
         auto load_tap = [&](const int4& v) {
           const int cb = ((p.view_empty >> v.z) & 1) ? p.batch : c.b0;   // empty view: box out of range -> zeros
           const int wrow = v.w + c.n0;
+          const int cx = c.x0 + v.y, cy = c.y0 + v.x;
+          const uint32_t tx_bytes = (uint32_t)(p.resident ? kABytes : kABytes + b_bytes);
           for (int kc = 0; kc < p.kchunks; ++kc) {
-            tc::mbar_wait(&bar_empty[st], ph ^ 1u);
-            uint8_t* sa = smem + st * stage_bytes;
-            tc::mbar_arrive_expect_tx(&bar_full[st], (uint32_t)(p.resident ? kABytes : kABytes + b_bytes));
-            tc::tma_load_4d(sa, &maps.a[v.z], &bar_full[st], kc * kBlockK, c.x0 + v.y, c.y0 + v.x, cb);
-            if (!p.resident) tc::tma_load_2d(sa + kABytes, &maps.b, &bar_full[st], kc * kBlockK, wrow);
+            mbar_wait_a(bar_empty_a + 8u * st, ph ^ 1u);
+            const uint32_t sa = smem_a + st * stage_bytes, bf = bar_full_a + 8u * st;
+            mbar_expect_tx_a(bf, tx_bytes);
+            tma_load_4d_a(sa, &maps.a[v.z], bf, kc * kBlockK, cx, cy, cb);
+            if (!p.resident) tma_load_2d_a(sa + kABytes, &maps.b, bf, kc * kBlockK, wrow);
             if (++st == p.stages) { st = 0; ph ^= 1u; }
           }
         };
@@ -405,34 +473,40 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
         tc::tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.acc_stride);
         if (p.halo) {
-          bool first = true;
+          uint32_t accum = 0;
+          const uint32_t hv_a = htab_a + (uint32_t)(c.phase * kMaxViews) * 16u, ht_a = htab_a + 4u * kMaxViews * 16u + (uint32_t)(c.phase * kMaxTapsPhase) * 8u;
+          const uint32_t a_hi = desc_hi(kHaloPitch * 128u), b_hi = desc_hi(1024u);
           for (int v = 0; v < p.n_views; ++v) {
-            const int4 hv = hview[c.phase * kMaxViews + v];
+            const int4 hv = lds_int4(hv_a + (uint32_t)v * 16u);
             if (hv.z == 0) continue;
             for (int kc = 0; kc < p.kchunks; ++kc) {
-              tc::mbar_wait(&bar_afull[ast], aph);
+              mbar_wait_a(bar_afull_a + 8u * ast, aph);
               tc::tc_fence_after();
-              const uint32_t sa = tc::smem_u32(smem + p.a_base + ast * p.a_stage_bytes);
-              const int nk = (kc == p.kchunks - 1) ? k16_last : kBlockK / 16;
+              const uint32_t a_lo0 = desc_lo(smem_a + p.a_base + ast * p.a_stage_bytes);
+              const bool full_chunk = kc != p.kchunks - 1 || k16_last == kBlockK / 16;
               for (int j = 0; j < hv.z; ++j) {
-                const int2 ht = htap[c.phase * kMaxTapsPhase + hv.w + j];
-                tc::mbar_wait(&bar_full[st], ph);
+                const int2 ht = lds_int2(ht_a + (uint32_t)(hv.w + j) * 8u);
+                mbar_wait_a(bar_full_a + 8u * st, ph);
                 tc::tc_fence_after();
-                const uint32_t sb = tc::smem_u32(smem + st * stage_bytes);
-                for (int k = 0; k < nk; ++k) {
-                  const uint64_t ad = smem_desc_sw128_row(sa, ht.x, (uint32_t)k * 32u, kHaloPitch * 128u, p.halo & 1);
-                  const uint64_t bd = tc::smem_desc_sw128(sb + k * 32, 16, 1024);
-                  tc::umma_bf16(tmem_d, ad, bd, idesc, (first && k == 0) ? 0u : 1u);
+                const uint32_t a_lo = a_lo0 + (uint32_t)ht.x * 8u;                  // + row * 128 B
+                const uint32_t b_lo = desc_lo(smem_a + st * stage_bytes);
+                if (full_chunk) {
+                  umma_bf16_hl(tmem_d, a_hi, a_lo, b_hi, b_lo, idesc, accum);
+                  umma_bf16_hl(tmem_d, a_hi, a_lo + 2u, b_hi, b_lo + 2u, idesc, 1u);
+                  umma_bf16_hl(tmem_d, a_hi, a_lo + 4u, b_hi, b_lo + 4u, idesc, 1u);
+                  umma_bf16_hl(tmem_d, a_hi, a_lo + 6u, b_hi, b_lo + 6u, idesc, 1u);
+                } else {
+                  for (int k = 0; k < k16_last; ++k) umma_bf16_hl(tmem_d, a_hi, a_lo + 2u * k, b_hi, b_lo + 2u * k, idesc, k ? 1u : accum);
                 }
-                first = false;
-                tc::umma_commit(&bar_empty[st]);
+                accum = 1u;
+                umma_commit_a(bar_empty_a + 8u * st);
                 if (++st == p.stages) { st = 0; ph ^= 1u; }
               }
-              tc::umma_commit(&bar_aempty[ast]);
+              umma_commit_a(bar_aempty_a + 8u * ast);
               if (++ast == p.a_stages) { ast = 0; aph ^= 1u; }
             }
           }
-          tc::umma_commit(&bar_tfull[acc]);
+          umma_commit_a(bar_tfull_a + 8u * acc);
           continue;
         }
         int ylo, yhi, xlo, xhi;
@@ -440,20 +514,23 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
         axis_range(p, ax, c.px, c.x0, p.tile_w, p.in_w, xlo, xhi);
         bool issued = false;
         auto mma_tap = [&](int tap_idx) {
+          const uint32_t d_hi = desc_hi(1024u);
           for (int kc = 0; kc < p.kchunks; ++kc) {
-            tc::mbar_wait(&bar_full[st], ph);
+            mbar_wait_a(bar_full_a + 8u * st, ph);
             tc::tc_fence_after();
-            const uint32_t sa = tc::smem_u32(smem + st * stage_bytes);
-            const uint32_t sb = p.resident ? tc::smem_u32(smem + p.res_base) + (uint32_t)(tap_idx * p.kchunks + kc) * p.b_tile_bytes
-                                           : sa + kABytes;
-            const int nk = (kc == p.kchunks - 1) ? k16_last : kBlockK / 16;
-            for (int k = 0; k < nk; ++k) {
-              const uint64_t ad = tc::smem_desc_sw128(sa + k * 32, 16, 1024);
-              const uint64_t bd = tc::smem_desc_sw128(sb + k * 32, 16, 1024);
-              tc::umma_bf16(tmem_d, ad, bd, idesc, (issued || k != 0) ? 1u : 0u);
+            const uint32_t sa = smem_a + st * stage_bytes;
+            const uint32_t sb = p.resident ? smem_a + p.res_base + (uint32_t)(tap_idx * p.kchunks + kc) * p.b_tile_bytes : sa + kABytes;
+            const uint32_t a_lo = desc_lo(sa), b_lo = desc_lo(sb);
+            if (kc != p.kchunks - 1 || k16_last == kBlockK / 16) {
+              umma_bf16_hl(tmem_d, d_hi, a_lo, d_hi, b_lo, idesc, issued ? 1u : 0u);
+              umma_bf16_hl(tmem_d, d_hi, a_lo + 2u, d_hi, b_lo + 2u, idesc, 1u);
+              umma_bf16_hl(tmem_d, d_hi, a_lo + 4u, d_hi, b_lo + 4u, idesc, 1u);
+              umma_bf16_hl(tmem_d, d_hi, a_lo + 6u, d_hi, b_lo + 6u, idesc, 1u);
+            } else {
+              for (int k = 0; k < k16_last; ++k) umma_bf16_hl(tmem_d, d_hi, a_lo + 2u * k, d_hi, b_lo + 2u * k, idesc, (issued || k != 0) ? 1u : 0u);
             }
             issued = true;
-            tc::umma_commit(&bar_empty[st]);
+            umma_commit_a(bar_empty_a + 8u * st);
             if (++st == p.stages) { st = 0; ph ^= 1u; }
           }
         };
@@ -466,7 +543,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
           }
         }
         if (!issued) mma_tap(ay.cnt * ax.cnt - 1);
-        tc::umma_commit(&bar_tfull[acc]);
+        umma_commit_a(bar_tfull_a + 8u * acc);
         if (p.resident) {                                   // last tile of this weight set: the producer may overwrite it
           const int next = tile + gridDim.x;
           if (next >= p.total_tiles || decode_tile(p, next).phase != c.phase) tc::umma_commit(&bar_bfree);
@@ -757,7 +834,7 @@ extern "C" int lb_conv_tc_gemm_ex(const void* in_bf16, const void* w_packed, con
   p.halo = 0;
   if (span_y >= 0) {                   // 8 x 16 pixel tiles of one image: 8-row groups = rows of the tile, 16 halo rows apart
     static const int env_halo = getenv("LB_TC2_HALO") ? atoi(getenv("LB_TC2_HALO")) : 1;
-    p.halo = env_halo == 2 ? 2 : 1;    // 2: descriptors without the base-offset field (debugging aid)
+    p.halo = 1;
     p.tile_w = 8; p.tile_h = 16; p.tile_b = 1;
   }
   p.tiles_w = (dst_w + p.tile_w - 1) / p.tile_w;

@@ -36,6 +36,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done = 0;
+#pragma unroll 1
   for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
     asm volatile(
         "{\n\t.reg .pred P;\n\t"

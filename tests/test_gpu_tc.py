@@ -170,12 +170,12 @@ EX_CASES.update({
     "featattn_dgrad": ("conv", 6, 16, 16, 64, 16, 16, 1, 0, "dgrad"),     # full-extent kernel: 2 live taps of 16 per tile
     # halo mode (one shared-memory tile per source view serves every tap shift; 8 x 16 pixel tiles)
     "halo_convT4_64": ("convT", 3, 64, 64, 96, 96, 4, 2, 1, "fwd"),       # 4 output phases x 4 taps, two channel chunks
-    "halo_3x3_c48": ("conv", 2, 64, 48, 48, 48, 3, 1, 1, "fwd"),          # 9 taps of one view, partial channel chunk
-    "halo_3x3_dgrad": ("conv", 2, 40, 24, 48, 48, 3, 1, 1, "dgrad"),      # mode 1 stride 1, tiles overhang both axes
-    "halo_5x5s2_c32": ("conv", 2, 64, 64, 32, 32, 5, 2, 2, "fwd"),        # 4 parity views: 9 / 6 / 6 / 4 taps
-    "halo_5x5s2_dgrad": ("conv", 2, 64, 64, 32, 32, 5, 2, 2, "dgrad"),    # mode 1 stride 2: 4 phases, up to 9 taps each
-    "halo_convT4_dgrad": ("convT", 2, 32, 32, 192, 192, 4, 2, 1, "dgrad"),  # mode 0 stride 2, 4 taps per view, 3 chunks
-    "halo_odd": ("conv", 3, 21, 19, 40, 24, 3, 1, 1, "fwd"),
+    "halo_3x3_c48": ("conv", 4, 64, 48, 48, 48, 3, 1, 1, "fwd"),          # 9 taps of one view, partial channel chunk
+    "halo_3x3_dgrad": ("conv", 12, 40, 24, 48, 48, 3, 1, 1, "dgrad"),     # mode 1 stride 1, tiles overhang both axes
+    "halo_5x5s2_c32": ("conv", 10, 64, 64, 32, 32, 5, 2, 2, "fwd"),       # 4 parity views: 9 / 6 / 6 / 4 taps
+    "halo_5x5s2_dgrad": ("conv", 3, 64, 64, 32, 32, 5, 2, 2, "dgrad"),    # mode 1 stride 2: 4 phases, up to 9 taps each
+    "halo_convT4_dgrad": ("convT", 40, 16, 16, 192, 192, 4, 2, 1, "dgrad"),  # mode 0 stride 2, 4 taps per view, 3 chunks
+    "halo_odd": ("conv", 26, 21, 19, 40, 24, 3, 1, 1, "fwd"),
 })
 EX_MODES = ["o32", "o16", "o16act", "o16both", "o16dact", "both_aux", "o16_aux", "o16_aux16", "o16_auxfac16"]
 
