@@ -189,6 +189,26 @@ int lb_conv_small(const void* in, const float* w, const float* alpha, const floa
 int lb_conv_small_wgrad_supported(const lb_conv_geom* g);
 int lb_conv_small_wgrad(const void* gathered, const void* dense, float* dw, const lb_conv_geom* g, int growth_gathered,
                         int wide_dtype, lb_stream_t stream);
+/* ---- SEPARABLE = True (config.py:53): the grouped convolutions of that configuration                libs/conv.py:17, libs/attention.py:15-21
+ * Depthwise k x k conv / transposed conv (groups = channels): out[b,oy,ox,c] = alpha * sum_taps in[b,iy,ix,c] * w[c][ty][tx]
+ * with the mode conventions above (forward of one = input gradient of the other, same weights); w is the fp32 master
+ * weight (C,1,kh,kw); in / out channels-last in storage `dtype`.  One multiply-add per byte: HBM-bound direct kernels. */
+int lb_dw_conv(const void* in, const float* w, const float* alpha, void* out, int batch, int in_h, int in_w, int out_h,
+               int out_w, int channels, int kh, int kw, int stride, int pad, int mode, int dtype, lb_stream_t stream);
+/* dw[c][ty][tx] += sum_pixels gathered[pixel@tap][c] * dense[pixel][c] (mode-0 gather around the dense grid: gathered = x,
+ * dense = dy for a conv; gathered = dy, dense = x for a transposed conv). */
+int lb_dw_wgrad(const void* gathered, const void* dense, float* dw, int batch, int g_h, int g_w, int d_h, int d_w,
+                int channels, int kh, int kw, int stride, int pad, int dtype, lb_stream_t stream);
+/* Feature attention's grouped full-extent conv: in [B][P][F] -> out [B][F/r], out[b,o] = alpha * sum_{j<r,p} in[b,p,o*r+j] * w[o][j][p]
+ * (w fp32 (F/r, r, S, S)); its input gradient din[b,p,c] = alpha * g[b,c/r] * w[c][p]; its weight gradient
+ * dw[c][p] += sum_b in[b,p,c] * g[b,c/r] (fixed order over the batch). */
+int lb_gfull_fwd(const void* in, const float* w, const float* alpha, void* out, int batch, int pixels, int features,
+                 int group_in, int dtype, lb_stream_t stream);
+int lb_gfull_dgrad(const void* g, const float* w, const float* alpha, void* din, int batch, int pixels, int features,
+                   int group_in, int dtype, lb_stream_t stream);
+int lb_gfull_wgrad(const void* in, const void* g, float* dw, int batch, int pixels, int features, int group_in, int dtype,
+                   lb_stream_t stream);
+
 /* ---- the same GEMM on the 5th-gen tensor cores (tcgen05.mma, TMEM accumulator, TMA tiles), bf16 operands,
  * fp32 accumulate/output.  `in` is the bf16 channels-last activation, `w_packed` the weight packed by
  * lb_conv_tc_pack as [tap][n][k] bf16 (lb_conv_tc_packed_elems elements).  lb_conv_tc_supported says

@@ -59,6 +59,11 @@ _SIGNATURES = {
     "lb_conv_small": ([P, P, P, P, P, POINTER(ConvGeom), c_int, P, c_int, c_int, c_int, c_int, P], c_int),
     "lb_conv_small_wgrad_supported": ([POINTER(ConvGeom)], c_int),
     "lb_conv_small_wgrad": ([P, P, P, POINTER(ConvGeom), c_int, c_int, P], c_int),
+    "lb_dw_conv": ([P, P, P, P] + [c_int] * 12 + [P], c_int),
+    "lb_dw_wgrad": ([P, P, P] + [c_int] * 11 + [P], c_int),
+    "lb_gfull_fwd": ([P, P, P, P, c_int, c_int, c_int, c_int, c_int, P], c_int),
+    "lb_gfull_dgrad": ([P, P, P, P, c_int, c_int, c_int, c_int, c_int, P], c_int),
+    "lb_gfull_wgrad": ([P, P, P, c_int, c_int, c_int, c_int, c_int, P], c_int),
     "lb_conv_tc_supported": ([POINTER(ConvGeom)], c_int),
     "lb_conv_tc_packed_elems": ([POINTER(ConvGeom)], c_size_t),
     "lb_conv_tc_pack": ([P, P, POINTER(ConvGeom), P], c_int),

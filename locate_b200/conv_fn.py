@@ -15,7 +15,7 @@ import torch
 from . import _lib
 from ._lib import ConvGeom, call, ptr
 from .config import CFG
-from .ops import BF16, F32, _as_act, _conv_work, _dt, _esz, _grad_sink, _match, _new_act, _timed_call, store_dtype
+from .ops import BF16, F32, _as_act, _cast, _conv_work, _dt, _esz, _grad_sink, _match, _new_act, _timed_call, store_dtype
 
 # weight packs are reused while the weights are unchanged (3 discriminator passes per D step);
 # optim.Nadam.step / load_state_dict bump the epoch, torch's version counter covers in-place torch ops.
@@ -32,9 +32,10 @@ class ConvSpec:
     kind: 'conv' (weight [Cout,Cin,kh,kw]), 'convT' (weight [Cin,Cout,kh,kw]), 'linear'
     (weight [out,in]), 'conv1d' (weight [Cout,Cin,1] applied per pixel)."""
 
-    def __init__(self, kind, cin, cout, kh=1, kw=1, stride=1, pad=0):
+    def __init__(self, kind, cin, cout, kh=1, kw=1, stride=1, pad=0, groups=1):
         self.kind, self.cin, self.cout = kind, cin, cout
         self.kh, self.kw, self.stride, self.pad = kh, kw, stride, pad
+        self.groups = groups           # 1, or SEPARABLE's two grouped forms: depthwise (groups = cin = cout) / full-extent
 
     def out_hw(self, h, w):
         if self.kind == "convT":
@@ -48,6 +49,8 @@ class ConvSpec:
     @property
     def sn_shape(self):
         """(height, width) of the matrix view spectral norm iterates on (spectral_norm.py:26)."""
+        if self.groups > 1:            # weight (cout, cin / groups, kh, kw) -- for both Conv and ConvTranspose when cin = cout
+            return self.cout, (self.cin // self.groups) * self.taps
         if self.kind == "convT":
             return self.cin, self.cout * self.taps
         return self.cout, self.cin * self.taps
@@ -502,6 +505,8 @@ def activated_pair(x, sn0, sn1, pre_act0=True):
     m0, m1 = sn0.module, sn1.module
     if getattr(m0, "bias", None) is not None or getattr(m1, "bias", None) is not None:
         return None
+    if spec0.groups > 1 or spec1.groups > 1:          # SEPARABLE: depthwise conv_0 runs on its own direct kernel
+        return None
     b, cin, h, w_ = x.shape
     mid, cout = spec0.cout, spec1.cout
     if cin % 8 or mid % 8 or cin != spec0.cin or mid != spec1.cin:
@@ -539,5 +544,84 @@ def activated_pair(x, sn0, sn1, pre_act0=True):
                                  spec0, spec1, sig[0], sig[1], (g0, g1), pre_act0)
 
 
+class GroupedSNConvFn(torch.autograd.Function):
+    """The grouped spectral-normed convolutions of SEPARABLE = True (config.py:53) on direct HBM-bound kernels:
+    depthwise k x k Conv2d / ConvTranspose2d (conv.py:17, groups = channels) optionally preceded by RootTanh
+    (conv.py:23), and feature attention's full-extent grouped conv (attention.py:15-21, kernel = the whole map)."""
+
+    @staticmethod
+    def forward(ctx, x, w_bar, u, v, spec, pre_act, pre_sigma):
+        x = _as_act(x)
+        b, c, h, w_ = x.shape
+        if c != spec.cin:
+            raise ValueError(f"expected {spec.cin} input channels, got {c}")
+        sigma = pre_sigma if pre_sigma is not None else power_iterate(w_bar, u.data, v.data, spec)
+        dt = _dt(x)
+        a = x
+        if pre_act:
+            a = torch.empty_like(x)
+            call("lb_roottanh_fwd", ptr(x), ptr(a), x.numel(), CFG.ROOTTANH_GROWTH, dt)
+        full = spec.groups != spec.cin                    # full-extent grouped conv: [B,F,S,S] -> [B,F/r,1,1]
+        if full:
+            if (spec.kh, spec.kw) != (h, w_) or spec.stride != 1 or spec.pad != 0 or spec.kind != "conv" or pre_act:
+                raise NotImplementedError("grouped conv other than depthwise / full-extent (attention.py:15-21)")
+            r = spec.cin // spec.groups
+            if spec.cout != spec.groups:
+                raise NotImplementedError("full-extent grouped conv with more than one output per group")
+            out = _new_act((b, spec.cout, 1, 1), x, x.dtype)
+            call("lb_gfull_fwd", ptr(a), ptr(w_bar), sigma.data_ptr() + 4, ptr(out), b, h * w_, c, r, dt)
+            out = _cast(out, store_dtype(out.shape))      # F/r may fall off the bf16 storage rule (C % 8)
+        else:
+            if spec.cout != spec.cin:
+                raise NotImplementedError("depthwise conv with a channel multiplier (FEATURE_MULTIPLIER != 1)")
+            oh, ow = spec.out_hw(h, w_)
+            out = _new_act((b, c, oh, ow), x, x.dtype)
+            call("lb_dw_conv", ptr(a), ptr(w_bar), sigma.data_ptr() + 4, ptr(out), b, h, w_, oh, ow, c, spec.kh, spec.kw, spec.stride,
+                 spec.pad, 1 if spec.kind == "convT" else 0, dt)
+        ctx.save_for_backward(x if pre_act else None, a, w_bar, sigma)
+        ctx.u, ctx.v = u, v
+        ctx.uv_extra = _uv_extra(pre_sigma, u)
+        ctx.w_param = w_bar
+        ctx.meta = (spec, pre_act, full, tuple(x.shape), _Like(out.shape, out.stride(), out.dtype))
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, a, w_bar, sigma = ctx.saved_tensors
+        spec, pre_act, full, (b, c, h, w_), out_like = ctx.meta
+        gout = _match(gout, out_like)
+        if gout.dtype != a.dtype:
+            gout = gout.to(a.dtype)
+        dt = _dt(gout)
+        dev = gout.device
+        dx = dw_ret = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(a)
+            if full:
+                call("lb_gfull_dgrad", ptr(gout), ptr(w_bar), sigma.data_ptr() + 4, ptr(dx), b, h * w_, c, spec.cin // spec.groups, dt)
+            else:
+                oh, ow = out_like.shape[2], out_like.shape[3]
+                call("lb_dw_conv", ptr(gout), ptr(w_bar), sigma.data_ptr() + 4, ptr(dx), b, oh, ow, h, w_, c, spec.kh, spec.kw,
+                     spec.stride, spec.pad, 0 if spec.kind == "convT" else 1, dt)
+            if pre_act:
+                call("lb_roottanh_bwd", ptr(x), ptr(dx), ptr(dx), dx.numel(), CFG.ROOTTANH_GROWTH, dt)
+        if ctx.needs_input_grad[1]:
+            dwn = torch.zeros_like(w_bar, memory_format=torch.contiguous_format)
+            if full:
+                call("lb_gfull_wgrad", ptr(a), ptr(gout), ptr(dwn), b, h * w_, c, spec.cin // spec.groups, dt)
+            elif spec.kind == "convT":    # gathered = dy (the larger map), dense = x
+                oh, ow = out_like.shape[2], out_like.shape[3]
+                call("lb_dw_wgrad", ptr(gout), ptr(a), ptr(dwn), b, oh, ow, h, w_, c, spec.kh, spec.kw, spec.stride, spec.pad, dt)
+            else:
+                oh, ow = out_like.shape[2], out_like.shape[3]
+                call("lb_dw_wgrad", ptr(a), ptr(gout), ptr(dwn), b, h, w_, oh, ow, c, spec.kh, spec.kw, spec.stride, spec.pad, dt)
+            dw_ret = _sn_weight_grad(dwn, ctx.w_param, ctx.u, ctx.v, sigma, spec, 0, ctx.uv_extra, dev)
+        return dx, dw_ret, None, None, None, None, None
+
+
 def sn_conv(x, w_bar, u, v, bias, spec, cat_input=False, pre_act=False, pre_sigma=None):
+    if spec.groups > 1:
+        if bias is not None or cat_input:
+            raise NotImplementedError("grouped convolutions carry no bias / concat on the reference's path")
+        return GroupedSNConvFn.apply(x, w_bar, u, v, spec, pre_act, pre_sigma)
     return SNConvFn.apply(x, w_bar, u, v, bias, spec, cat_input, pre_act, pre_sigma)

@@ -49,7 +49,7 @@ def _emit_mode(module):
     with RootTanh -> conv (conv.py:22-24), "plain" when a spectral-normed conv reads the norm output directly
     (attention.py:26,44) and nothing else does, None otherwise."""
     if isinstance(module, ActivatedBaseConv):
-        return "act"
+        return None if module.conv_0.spec.groups > 1 else "act"     # the depthwise kernel applies RootTanh itself
     if isinstance(module, DeepResidualConv):
         return _emit_mode(module.layers[0]) if len(module.layers) == 1 else _emit_mode_first(module.layers[0])
     if isinstance(module, SelfAttention):
@@ -89,12 +89,19 @@ def _spec_of(module):
     if isinstance(module, (nn.Conv2d, nn.ConvTranspose2d)):
         transposed = isinstance(module, nn.ConvTranspose2d)
         (kh, kw), (sh, sw), (ph, pw) = module.kernel_size, module.stride, _pair(module.padding)
-        if module.groups != 1 or module.dilation != (1, 1) or sh != sw or ph != pw or module.padding_mode != "zeros":
-            raise NotImplementedError("groups/dilation/anisotropic stride or padding are not on the default path "
-                                      "(SEPARABLE=True is SURVEY.md 'next' row N3)")
+        if module.dilation != (1, 1) or sh != sw or ph != pw or module.padding_mode != "zeros":
+            raise NotImplementedError("dilation / anisotropic stride or padding are not on the reference's path")
         if transposed and module.output_padding != (0, 0):
             raise NotImplementedError("output_padding")
-        return ConvSpec("convT" if transposed else "conv", module.in_channels, module.out_channels, kh, kw, sh, ph)
+        g = module.groups
+        if g != 1:
+            # SEPARABLE = True builds exactly two grouped forms: depthwise (conv.py:17) and the full-extent
+            # feature-attention conv with one output per group (attention.py:15-21)
+            depthwise = g == module.in_channels == module.out_channels
+            full = (not transposed) and g == module.out_channels and module.in_channels % g == 0 and (sh, ph) == (1, 0)
+            if not (depthwise or full):
+                raise NotImplementedError(f"grouped convolution groups={g} {module.in_channels}->{module.out_channels}")
+        return ConvSpec("convT" if transposed else "conv", module.in_channels, module.out_channels, kh, kw, sh, ph, g)
     raise NotImplementedError(f"SpectralNorm over {type(module).__name__}")
 
 
@@ -284,17 +291,21 @@ def Scale(in_features, out_features, stride, transpose, dim=2):
 # ---- attention (libs/attention.py:9-54) --------------------------------------------------------
 def feature_attention(in_size, features, dim=2):
     _need_2d(dim)
-    if CFG.SEPARABLE:
-        raise NotImplementedError("SEPARABLE=True (grouped full-extent conv) is SURVEY.md 'next' row N3")
     bfeatures = features // CFG.BOTTLENECK
     layers = []
     input_features = features
-    for i in range(dim):
-        kernel_size = [1] * dim
-        kernel_size[i] = in_size
-        layers.extend([SpectralNorm(nn.Conv2d(input_features, bfeatures, kernel_size=kernel_size, bias=False, groups=1)),
-                       NonLinear()])
-        input_features = bfeatures
+    min_features = min(input_features, bfeatures)
+    if CFG.SEPARABLE and input_features % min_features == 0 and bfeatures % min_features == 0:
+        # one grouped conv spanning the whole map, no activation after it (attention.py:15-21)
+        layers.append(SpectralNorm(nn.Conv2d(input_features, bfeatures, kernel_size=[in_size] * dim, bias=False,
+                                             groups=min_features)))
+    else:
+        for i in range(dim):
+            kernel_size = [1] * dim
+            kernel_size[i] = in_size
+            layers.extend([SpectralNorm(nn.Conv2d(input_features, bfeatures, kernel_size=kernel_size, bias=False, groups=1)),
+                           NonLinear()])
+            input_features = bfeatures
     layers.extend([SpectralNorm(nn.Conv2d(bfeatures, features, kernel_size=1, bias=False)),
                    SoftmaxChannels(),
                    Expand(-1, features, *([in_size] * dim))])
@@ -335,11 +346,9 @@ class SelfAttention(nn.Module):
 class ActivatedBaseConv(nn.Module):
     def __init__(self, in_features, out_features, conv, kernel=5, stride=1, pad=2):
         super().__init__()
-        if CFG.SEPARABLE:
-            raise NotImplementedError("SEPARABLE=True (depthwise conv) is SURVEY.md 'next' row N3")
         mid = in_features * CFG.FEATURE_MULTIPLIER
         self.conv_0 = SpectralNorm(conv(in_channels=in_features, kernel_size=kernel, stride=stride, padding=pad,
-                                        bias=False, out_channels=mid, groups=1))
+                                        bias=False, out_channels=mid, groups=in_features if CFG.SEPARABLE else 1))
         self.conv_1 = SpectralNorm(conv(kernel_size=1, stride=1, padding=0, out_channels=out_features, bias=False,
                                         in_channels=mid))
 

@@ -14,10 +14,12 @@ def quadnorm(number: int):
 
 
 def generator_feature_list():
-    """[Z, f(L-2), ..., f(0)] with f(i) = quadnorm(GEN_FEATURES * FACTOR**(i - (L-1)))  (models.py:16-22,37-52)."""
+    """[in, f(L-2), ..., f(0)] with f(i) = quadnorm(GEN_FEATURES * FACTOR**(i - (L-1)))  (models.py:16-22,37-52); in = Z, or
+    with an input block (START_LAYER >= 1) its output width f(L-1) = quadnorm(GEN_FEATURES) (models.py:44-50)."""
     clayers = CFG.LAYERS - 1
     feats = [quadnorm(int(CFG.GEN_FEATURES * CFG.FACTOR ** (i - clayers))) for i in range(clayers - 1, -1, -1)]
-    return [CFG.INPUT_VECTOR_Z] + feats
+    first = quadnorm(int(CFG.GEN_FEATURES)) if CFG.START_LAYER >= 1 else CFG.INPUT_VECTOR_Z
+    return [first] + feats
 
 
 def discriminator_feature_list():
@@ -59,13 +61,17 @@ class _ArenaModel(nn.Module):
 class Generator(_ArenaModel):
     def __init__(self):
         super().__init__()
-        if CFG.START_LAYER >= 1:
-            raise NotImplementedError("START_LAYER >= 1 is SURVEY.md 'next' row N3")
         if CFG.G_STRIDE != 2:
             raise NotImplementedError("G_STRIDE != 2")
         strides = [2] * (CFG.LAYERS - 1)
         feature_list = generator_feature_list()
-        self.input_block = identity
+        if CFG.START_LAYER >= 1:
+            # models.py:46-48.  NOTE: the reference's own forward then fails -- the style chain's first Linear is built
+            # for `feature_list[0]` inputs (block.py:88-96) but receives the Z-dimensional latent -- and so does this one
+            # (same constructors, same state_dict keys, same shape error); see tests/test_abi_and_host.py.
+            self.input_block = DeepResidualConv(CFG.INPUT_VECTOR_Z, feature_list[0], False, 1, False, 2, CFG.START_LAYER)
+        else:
+            self.input_block = identity
         self.conv_block = BlockBlock(len(strides), 2, feature_list, strides, True, True)
         self.out_conv = DeepResidualConv(self.conv_block.out_features, 3, False, 1, False, 2, 1)
         self.g_in = feature_list[0]

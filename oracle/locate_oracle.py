@@ -45,6 +45,8 @@ class OracleConfig:
     MIN_ATTENTION_SIZE: int = 8
     ATTENTION_EVERY_NTH_LAYER: int = 2
     DEPTH: int = 1
+    SEPARABLE: bool = False            # config.py:53: depthwise k x k convs (conv.py:17), grouped full-extent feature attention
+    START_LAYER: int = 0               # config.py:39: depth of the generator's input block (models.py:46-48)
     ROOTTANH_GROWTH: int = 4
     GLR: float = 5e-4
     DLR: float = 2e-3
@@ -73,10 +75,12 @@ def _quad(n: int) -> int:  # models.py:12-13
 
 
 def generator_features(cfg: OracleConfig) -> List[int]:
-    """[Z, f_0, ..., f_{L-2}]: models.py:16-22,37-52 (START_LAYER = 0 path)."""
+    """[in, f_0, ..., f_{L-2}]: models.py:16-22,37-52; in = Z, or with an input block (START_LAYER >= 1) its output
+    width GFeatures(0, L-1)(L-1) = quadnorm(GEN_FEATURES)."""
     n = cfg.LAYERS - 1
     widths = [_quad(int(cfg.GEN_FEATURES * cfg.FACTOR ** (i - n))) for i in range(n - 1, -1, -1)]
-    return [cfg.INPUT_VECTOR_Z] + widths
+    first = _quad(int(cfg.GEN_FEATURES)) if cfg.START_LAYER >= 1 else cfg.INPUT_VECTOR_Z
+    return [first] + widths
 
 
 def discriminator_features(cfg: OracleConfig) -> List[int]:
@@ -238,14 +242,16 @@ def power_iterate(state: State, prefix: str, eps: float = 1e-12) -> torch.Tensor
 # --------------------------------------------------------------------------------------
 # sub-graphs
 # --------------------------------------------------------------------------------------
-def _conv_pair(state: State, prefix: str, x, transpose: bool, k: int, stride: int, pad: int, growth: int):
-    """ActivatedBaseConv: conv1x1(act(convkxk(act(x)))), both spectral-normed, no bias (conv.py:11-24)."""
+def _conv_pair(state: State, prefix: str, x, transpose: bool, k: int, stride: int, pad: int, growth: int, separable=False):
+    """ActivatedBaseConv: conv1x1(act(convkxk(act(x)))), both spectral-normed, no bias (conv.py:11-24); `separable`:
+    the k x k conv is depthwise, groups = in_features (conv.py:17)."""
     w0 = power_iterate(state, prefix + "conv_0.module.")
     h = roottanh(x, growth)
+    groups = x.shape[1] if separable else 1
     if transpose:
-        h = F.conv_transpose2d(h, w0, None, stride=stride, padding=pad)
+        h = F.conv_transpose2d(h, w0, None, stride=stride, padding=pad, groups=groups)
     else:
-        h = F.conv2d(h, w0, None, stride=stride, padding=pad)
+        h = F.conv2d(h, w0, None, stride=stride, padding=pad, groups=groups)
     w1 = power_iterate(state, prefix + "conv_1.module.")
     h = roottanh(h, growth)
     if transpose:
@@ -283,7 +289,7 @@ def deep_conv(state: State, prefix: str, x, cfg: OracleConfig, cin, cout, transp
         if normalize:
             h = whole_tensor_norm(h, state[inner + "i_norm.weight"], state[inner + "i_norm.bias"])
             inner += "module."
-        h = _conv_pair(state, inner, h, tr, k, s, pad, cfg.ROOTTANH_GROWTH)
+        h = _conv_pair(state, inner, h, tr, k, s, pad, cfg.ROOTTANH_GROWTH, cfg.SEPARABLE)
         x = gate(x, h, state[name + "gamma"], strict_reference) if residual else h
     return x
 
@@ -317,9 +323,16 @@ def skip_path(state: State, prefix: str, x, cin: int, cout: int, stride: int, tr
     return x
 
 
-def feature_attention(state: State, prefix: str, x, size: int, features: int, growth: int):
-    """attention.py:9-37 (SEPARABLE = False): (S x 1) conv -> act -> (1 x S) conv -> act ->
-    1x1 conv -> softmax over channels -> broadcast to [B,F,S,S]."""
+def feature_attention(state: State, prefix: str, x, size: int, features: int, growth: int, separable=False, bottleneck=4):
+    """attention.py:9-37: (S x 1) conv -> act -> (1 x S) conv -> act -> 1x1 conv -> softmax over channels -> broadcast
+    to [B,F,S,S]; `separable` (attention.py:15-21): ONE grouped full-extent S x S conv F -> F/4 (groups = F/4, no
+    activation) instead of the two axis convs."""
+    if separable and features % (features // bottleneck) == 0:
+        w = power_iterate(state, prefix + "0.module.")
+        h = F.conv2d(x, w, groups=features // bottleneck)
+        w = power_iterate(state, prefix + "1.module.")
+        h = torch.softmax(F.conv2d(h, w), dim=1)
+        return h.reshape(h.shape[0], -1, 1, 1).expand(-1, features, size, size)
     w = power_iterate(state, prefix + "0.module.")
     h = roottanh(F.conv2d(x, w), growth)
     w = power_iterate(state, prefix + "2.module.")
@@ -357,7 +370,8 @@ def block(state: State, prefix: str, x, cfg: OracleConfig, out_size: int, cin: i
     out = gate(skip, h, state[prefix + "res_module_i.gamma"], strict_reference)
     if _has_attention(cfg, out_size, number):
         a = normed(out, "res_module_f.", scales[1])
-        a = feature_attention(state, prefix + "res_module_f.layer_module.module.", a, out_size, cout, g)
+        a = feature_attention(state, prefix + "res_module_f.layer_module.module.", a, out_size, cout, g, cfg.SEPARABLE,
+                              cfg.BOTTLENECK)
         out = gate(out, a, state[prefix + "res_module_f.gamma"], strict_reference)
         a = normed(out, "res_module_s.", scales[2])
         a = self_attention(state, prefix + "res_module_s.layer_module.module.", a, g)
@@ -519,11 +533,12 @@ def _deep_conv_entries(state, prefix, cfg, cin, cout, transpose, stride, use_bot
         if normalize:
             _norm_entries(state, inner + "i_norm.", ci, gen, dtype)
             inner += "module."
+        mid = 1 if cfg.SEPARABLE else ci               # depthwise: one filter per channel (conv.py:17)
         if tr:
-            _sn_entries(state, inner + "conv_0.module.", (ci, ci, k, k), False, gen, dtype)
+            _sn_entries(state, inner + "conv_0.module.", (ci, mid, k, k), False, gen, dtype)
             _sn_entries(state, inner + "conv_1.module.", (ci, co, 1, 1), False, gen, dtype)
         else:
-            _sn_entries(state, inner + "conv_0.module.", (ci, ci, k, k), False, gen, dtype)
+            _sn_entries(state, inner + "conv_0.module.", (ci, mid, k, k), False, gen, dtype)
             _sn_entries(state, inner + "conv_1.module.", (co, ci, 1, 1), False, gen, dtype)
 
 
@@ -543,9 +558,13 @@ def _block_entries(state, prefix, cfg, out_size, cin, cout, stride, transpose, n
         state[prefix + "res_module_f.gamma"] = _gamma(gen, 0, dtype)
         _norm_entries(state, prefix + "res_module_f.layer_module.i_norm.", cout, gen, dtype)
         fa = prefix + "res_module_f.layer_module.module."
-        _sn_entries(state, fa + "0.module.", (bf, cout, out_size, 1), False, gen, dtype)
-        _sn_entries(state, fa + "2.module.", (bf, bf, 1, out_size), False, gen, dtype)
-        _sn_entries(state, fa + "4.module.", (cout, bf, 1, 1), False, gen, dtype)
+        if cfg.SEPARABLE and cout % bf == 0:               # attention.py:15-21
+            _sn_entries(state, fa + "0.module.", (bf, cout // bf, out_size, out_size), False, gen, dtype)
+            _sn_entries(state, fa + "1.module.", (cout, bf, 1, 1), False, gen, dtype)
+        else:
+            _sn_entries(state, fa + "0.module.", (bf, cout, out_size, 1), False, gen, dtype)
+            _sn_entries(state, fa + "2.module.", (bf, bf, 1, out_size), False, gen, dtype)
+            _sn_entries(state, fa + "4.module.", (cout, bf, 1, 1), False, gen, dtype)
         state[prefix + "res_module_s.gamma"] = _gamma(gen, 0, dtype)
         _norm_entries(state, prefix + "res_module_s.layer_module.i_norm.", cout, gen, dtype)
         sa = prefix + "res_module_s.layer_module.module."

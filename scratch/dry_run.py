@@ -1,6 +1,6 @@
 """CPU dry run of the Python plumbing: every C-ABI call is replaced by an arity / ctypes-conversion check (no kernel
 runs, tensors hold garbage), so signature drift between include/locate_b200.h, _lib.py and the autograd glue shows up
-without a GPU.  usage: python scratch/dry_run.py [res]"""
+without a GPU.  usage: python scratch/dry_run.py [res] [separable]"""
 import ctypes
 import sys
 
@@ -40,9 +40,10 @@ for mod in (_lib, ops, conv_fn, optim, sn_batch, train):
 optim.Nadam._attach_orig = optim.Nadam._attach
 
 res = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+separable = len(sys.argv) > 2 and sys.argv[2] == "separable"
 for precision in ("bf16", "fp32"):
     L.config.reset()
-    L.configure(IMAGE_SIZE=res, PRECISION=precision, BASE_FEATURE_FACTOR=2 if res <= 32 else 8)
+    L.configure(IMAGE_SIZE=res, PRECISION=precision, BASE_FEATURE_FACTOR=2 if res <= 32 else 8, SEPARABLE=separable)
     torch.manual_seed(0)
     gen, dis = L.Generator(), L.Discriminator()
     g_opt = L.Nadam(gen.parameters(), lr=1e-3)

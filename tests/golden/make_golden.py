@@ -268,9 +268,31 @@ def multi_step(tag, batch, steps, **overrides):
     save(f"{tag}.pt", rec)
 
 
+def start_layer(tag, **overrides):
+    """START_LAYER >= 1 (models.py:44-50): what the reference CONSTRUCTS (state_dict names and shapes) and what its own
+    forward does with it -- it raises: the style chain's first Linear is built for the input block's output width but is
+    fed the Z-dimensional latent (block.py:88-96)."""
+    libs = ref_loader.load_ref(**overrides)
+    with ref_loader.quiet():
+        torch.manual_seed(999)
+        gen = libs.Generator()
+    rec = dict(overrides=overrides, g_shapes={k: tuple(v.shape) for k, v in gen.state_dict().items()})
+    try:
+        gen(randn(2, sys.modules["libs.config"].INPUT_VECTOR_Z, seed=2))
+        rec["forward_error"] = None
+    except RuntimeError as exc:
+        rec["forward_error"] = str(exc)
+    print("START_LAYER forward:", rec["forward_error"])
+    save(f"{tag}.pt", rec)
+
+
 if __name__ == "__main__":
     libs = ref_loader.load_ref()
     save("primitives.pt", primitives(libs))
     full_model("step_s32_w2_b3", 3, IMAGE_SIZE=32, BASE_FEATURE_FACTOR=2)
     full_model("step_s16_w2_depth3_b2", 2, IMAGE_SIZE=16, BASE_FEATURE_FACTOR=2, DEPTH=3)
     multi_step("steps3_s16_w2_b2", 2, 3, IMAGE_SIZE=16, BASE_FEATURE_FACTOR=2)
+    # SEPARABLE = True (config.py:53): depthwise k x k convs (conv.py:17) and the grouped full-extent feature-attention
+    # conv (attention.py:15-21); BASE_FEATURE_FACTOR = 4 so that both attention sizes (8, 16 / 8) keep >= 1 group
+    full_model("step_s16_w4_separable_b2", 2, IMAGE_SIZE=16, BASE_FEATURE_FACTOR=4, SEPARABLE=True)
+    start_layer("start_layer1_s16_w2", IMAGE_SIZE=16, BASE_FEATURE_FACTOR=2, START_LAYER=1)

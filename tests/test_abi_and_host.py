@@ -74,7 +74,7 @@ def test_feature_schedules_match_oracle(size):
         assert models.discriminator_feature_list() == [32, 64, 128, 256, 512, 1024, 1024]
 
 
-@pytest.mark.parametrize("name", ["step_s32_w2_b3.pt", "step_s16_w2_depth3_b2.pt"])
+@pytest.mark.parametrize("name", ["step_s32_w2_b3.pt", "step_s16_w2_depth3_b2.pt", "step_s16_w4_separable_b2.pt"])
 def test_state_dict_keys_and_seeded_init_equal_the_reference(golden, name):
     r = golden(name)
     L.configure(**r["overrides"])
@@ -126,7 +126,18 @@ def test_configure_rejects_unknown_and_derived():
         L.configure(LAYERS=3)
 
 
+def test_start_layer_builds_what_the_reference_builds(golden):
+    """START_LAYER >= 1 (models.py:44-50): same modules, names and shapes as the reference constructs.  (The reference's
+    own forward then raises -- fixture key `forward_error` -- see tests/test_gpu_parity.py for the mirrored behaviour.)"""
+    r = golden("start_layer1_s16_w2.pt")
+    L.configure(**r["overrides"])
+    gen = L.Generator()
+    assert {k: tuple(v.shape) for k, v in gen.state_dict().items()} == r["g_shapes"]
+    assert list(gen.state_dict()) == list(r["g_shapes"])
+    assert r["forward_error"] is not None and "cannot be multiplied" in r["forward_error"]
+
+
 def test_unsupported_flags_fail_loudly():
-    L.configure(SEPARABLE=True, IMAGE_SIZE=32)
+    L.configure(G_STRIDE=4, IMAGE_SIZE=32)
     with pytest.raises(NotImplementedError):
         L.Generator()

@@ -129,6 +129,45 @@ def test_step_bf16_vs_oracle_default_width(size, batch, depth):
         assert worst[0] < (5e-2 if size == 32 else 8e-2) or (worst[1].endswith("gamma") and worst[0] < 0.25), worst
 
 
+@pytest.mark.parametrize("size,batch", [(32, 4), (64, 2)])
+def test_step_bf16_separable_vs_oracle(size, batch):
+    """SEPARABLE = True (config.py:53, SURVEY 'next' row N3) at the default widths in bf16 storage: depthwise k x k convs
+    and the grouped full-extent feature-attention conv run on the direct kernels of csrc/depthwise.cu over bf16
+    activations; losses and concatenated gradients against the fp64 oracle."""
+    L.configure(IMAGE_SIZE=size, SEPARABLE=True)
+    cfg = O.OracleConfig(IMAGE_SIZE=size, SEPARABLE=True)
+    torch.manual_seed(999)
+    gen, g_opt = L.get_model(L.Generator(), L.CFG.GLR, DEV)
+    dis, d_opt = L.get_model(L.Discriminator(), L.CFG.DLR, DEV)
+    gs = O.load_state({k: v.cpu().double() for k, v in gen.state_dict().items()})
+    ds = O.load_state({k: v.cpu().double() for k, v in dis.state_dict().items()})
+    real, aug, z = O.synthetic_batch(cfg, batch, dtype=torch.float64)
+    grads = {}
+
+    class Spy(O.Nadam):
+        def __init__(self, tag):
+            self.tag = tag
+
+        def step(self, state):
+            grads[self.tag] = {k: p.grad.clone() for k, p in state.items() if p.grad is not None}
+    o_d, o_pen, o_g = O.train_step(gs, ds, gen.noise.cpu().double(), real, aug, z, cfg, Spy("g"), Spy("d"))
+    mine = {}
+    for tag, opt, model in (("d", d_opt, dis), ("g", g_opt, gen)):
+        def spy(closure=None, tag=tag, model=model):
+            mine[tag] = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.requires_grad}
+        opt.step = spy
+    d_out, g_out = L.GanTrainer(gen, dis, g_opt, d_opt).step(real.float().to(DEV), aug.float().to(DEV), z.float().to(DEV))
+    assert abs(d_out[0].item() - o_d.item()) < 2e-2 * abs(o_d.item())
+    assert abs(g_out[0].item() - o_g.item()) < 2e-2 * abs(o_g.item())
+    assert abs(d_out[1].item() - o_pen.item()) < 0.15 * abs(o_pen.item()) + 2e-6, (d_out[1].item(), o_pen.item())
+    for tag in ("d", "g"):
+        keys = sorted(grads[tag])
+        a = torch.cat([mine[tag][k].double().cpu().reshape(-1) for k in keys])
+        b = torch.cat([grads[tag][k].reshape(-1) for k in keys])
+        total = ((a - b).norm() / b.norm()).item()
+        assert total < 3.0e-2, f"{tag}: relative gradient-norm error {total:.3e}"
+
+
 def test_step_bf16_vs_oracle_128_batch32():
     """The headline resolution at a batch where the tile counts, batch tiling and split-K choices differ from the
     batch-2 case above (bench.py runs batch 512 and gates itself against the fp32 kernels at that size): losses and

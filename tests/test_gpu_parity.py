@@ -268,7 +268,7 @@ def _build(rec):
     return gen, dis, g_opt, d_opt
 
 
-@pytest.mark.parametrize("name", ["step_s32_w2_b3.pt", "step_s16_w2_depth3_b2.pt"])
+@pytest.mark.parametrize("name", ["step_s32_w2_b3.pt", "step_s16_w2_depth3_b2.pt", "step_s16_w4_separable_b2.pt"])
 def test_full_forward_golden(golden, name):
     r = golden(name)
     gen, dis, _, _ = _build(r)
@@ -282,7 +282,7 @@ def test_full_forward_golden(golden, name):
         close(sd[k], v, what=k)
 
 
-@pytest.mark.parametrize("name", ["step_s32_w2_b3.pt", "step_s16_w2_depth3_b2.pt"])
+@pytest.mark.parametrize("name", ["step_s32_w2_b3.pt", "step_s16_w2_depth3_b2.pt", "step_s16_w4_separable_b2.pt"])
 def test_full_training_step_golden(golden, name):
     r = golden(name)
     gen, dis, g_opt, d_opt = _build(r)
@@ -321,6 +321,18 @@ def test_full_training_step_golden(golden, name):
         assert frac < 2e-3, f"G param {k}: {frac:.2e} of elements moved differently"
     for k, v in r["d_state_final"].items():
         close(dsd[k], v, rtol=2e-3, atol_frac=2e-3, what="D final " + k)
+
+
+def test_start_layer_forward_fails_like_the_reference(golden):
+    """START_LAYER = 1: the reference's forward raises a shape error in the style chain's first Linear (fixture key
+    `forward_error`, generated by running the reference); the drop-in raises at the same layer instead of inventing
+    semantics the reference does not have."""
+    r = golden("start_layer1_s16_w2.pt")
+    assert "cannot be multiplied" in r["forward_error"]
+    L.configure(**r["overrides"])
+    gen, _ = L.get_model(L.Generator(), L.CFG.GLR, DEV)
+    with pytest.raises((ValueError, RuntimeError), match="input channels|shape"):
+        gen(torch.randn(2, L.CFG.INPUT_VECTOR_Z, device=DEV))
 
 
 def test_three_training_steps_golden(golden):
