@@ -244,11 +244,16 @@ enum { LB_EX_AUX_IS_FACTOR = 1, LB_EX_OUT16_IS_DACT = 2 };
 int lb_conv_tc_gemm_ex(const void* in_bf16, const void* w_packed, const float* alpha, const float* bias, float* out32,
                        void* out16, void* out16a, int ld_out16, const void* aux, int ld_aux, int aux_dtype, int flags,
                        const lb_conv_geom* g, lb_stream_t stream);
-/* weight gradient on the tensor cores: dwp[tap][n][m] += sum_pixels gathered[pixel@tap][m] * dense[pixel][n]
- * (geometry as lb_conv_wgrad; both operands bf16 channels-last; dwp fp32, zeroed by the caller; feed it to
- * lb_sn_weight_grad with packed_taps = kh*kw). */
+/* weight gradient on the tensor cores: dwn[n][m][tap] = sum_pixels gathered[pixel@tap][m] * dense[pixel][n]
+ * (geometry as lb_conv_wgrad: in_* = gathered, out_* = dense; both operands bf16 channels-last).  dwn is fp32 in the
+ * master weight's own layout (Conv2d [Cout][Cin][kh][kw] with gathered = x; ConvTranspose2d [Cin][Cout][kh][kw] with
+ * gathered = dy) and is OVERWRITTEN: feed it to lb_sn_weight_grad with packed_taps = 0.  Split-K over the pixel axis is
+ * deterministic: every split stores its own partial in `work` (lb_wgrad_tc_workspace_floats(g) floats, contents
+ * irrelevant on entry) and a second kernel adds the splits in index order -- no floating-point atomics. */
 int lb_wgrad_tc_supported(const lb_conv_geom* g);
-int lb_wgrad_tc(const void* gathered_bf16, const void* dense_bf16, float* dwp, const lb_conv_geom* g, lb_stream_t stream);
+size_t lb_wgrad_tc_workspace_floats(const lb_conv_geom* g);
+int lb_wgrad_tc(const void* gathered_bf16, const void* dense_bf16, float* dwn, const lb_conv_geom* g, float* work,
+                size_t work_floats, lb_stream_t stream);
 /* fp32 -> bf16 producers of GEMM operands: plain cast, and RootTanh fused with the cast (activation.py:9-16) */
 int lb_cast_bf16(const float* x, void* y, size_t n, lb_stream_t stream);
 /* row-strided variant: dst[r*ld_dst + c] = bf16(f(src[r*ld_src + c])); f = identity (growth 0) or RootTanh (growth >= 1) */

@@ -329,12 +329,9 @@ class SNConvFn(torch.autograd.Function):
                 else:               # narrow / vector input: fp32 rows of cin
                     _tc_gemm(fl, _tc_bytes(g_dgrad), gy_ptr, pk, sigma.data_ptr() + 4, None, ptr(dx), g_dgrad, dev, F32)
             if need_dw:
-                dwp = torch.zeros(w_bar.numel(), dtype=torch.float32, device=dev)
-                if spec.kind == "convT":
-                    _timed_call("wgrad_tc", fl, _wgrad_bytes(g_wgrad), "lb_wgrad_tc", gy_ptr, ptr(a), ptr(dwp), g_wgrad)
-                else:
-                    _timed_call("wgrad_tc", fl, _wgrad_bytes(g_wgrad), "lb_wgrad_tc", ptr(a), gy_ptr, ptr(dwp), g_wgrad)
-                dw_ret = _sn_weight_grad(dwp, ctx.w_param, ctx.u, ctx.v, sigma, spec, t, ctx.uv_extra, dev)
+                ga_ptr, de_ptr = (gy_ptr, ptr(a)) if spec.kind == "convT" else (ptr(a), gy_ptr)
+                dwn = _wgrad_tc(ga_ptr, de_ptr, g_wgrad, w_bar.numel(), fl, dev)
+                dw_ret = _sn_weight_grad(dwn, ctx.w_param, ctx.u, ctx.v, sigma, spec, 0, ctx.uv_extra, dev)
         else:
             growth = CFG.ROOTTANH_GROWTH
             gy_ptr = gout.data_ptr() + off * esz_g    # gradient of the conv output slice, row stride ctot
@@ -405,11 +402,26 @@ def _ex_ok(g, out32, ld16, ld_aux, aux_dtype=F32):
     return _lib.lib().lb_conv_tc_ex_supported(ctypes.byref(g), int(out32), ld16, ld_aux, aux_dtype) == 1
 
 
+_WGRAD_WORK = {}
+
+
+def _wgrad_tc(gathered_ptr, dense_ptr, g_wgrad, numel, fl, dev):
+    """Raw dW (fp32, master layout) of one conv on the tensor cores: lb_wgrad_tc with its split-K workspace (one buffer
+    per device, grown to the largest layer; every layer overwrites it, stream order keeps the uses apart)."""
+    need = _lib.lib().lb_wgrad_tc_workspace_floats(ctypes.byref(g_wgrad))
+    work = _WGRAD_WORK.get(dev)
+    if work is None or work.numel() < need:
+        work = _WGRAD_WORK[dev] = torch.empty(max(need, 1 << 22), dtype=torch.float32, device=dev)
+    dwn = torch.empty(numel, dtype=torch.float32, device=dev)
+    _timed_call("wgrad_tc", fl, _wgrad_bytes(g_wgrad), "lb_wgrad_tc", gathered_ptr, dense_ptr, ptr(dwn), g_wgrad, ptr(work),
+                work.numel())
+    return dwn
+
+
 def _sn_wgrad_tc(ctx_w, u, v, sigma, gathered_ptr, dense_ptr, g_wgrad, spec, fl, by, dev, extra=None):
     """dW of one spectral-normed conv on the tensor cores + the sigma correction, accumulated into the grad sink."""
-    dwp = torch.zeros(ctx_w.numel(), dtype=torch.float32, device=dev)
-    _timed_call("wgrad_tc", fl, _wgrad_bytes(g_wgrad), "lb_wgrad_tc", gathered_ptr, dense_ptr, ptr(dwp), g_wgrad)
-    return _sn_weight_grad(dwp, ctx_w, u, v, sigma, spec, spec.taps, extra, dev)
+    dwn = _wgrad_tc(gathered_ptr, dense_ptr, g_wgrad, ctx_w.numel(), fl, dev)
+    return _sn_weight_grad(dwn, ctx_w, u, v, sigma, spec, 0, extra, dev)
 
 
 class ActivatedPairFn(torch.autograd.Function):

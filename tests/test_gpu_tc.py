@@ -97,6 +97,14 @@ WG_CASES = {
     "wg_convT1x1": ("convT", 3, 8, 8, 192, 96, 1, 1, 0),
     "wg_3x3_odd": ("conv", 2, 9, 9, 40, 24, 3, 1, 1),
     "wg_5x5s2_tiny": ("conv", 6, 2, 2, 256, 320, 5, 2, 2),
+    # halo-tile main loop (dense map >= 8 wide, several taps): tap groups per parity view, ragged tiles, both channel boxes
+    "wg_halo_3x3_b5": ("conv", 5, 24, 40, 48, 48, 3, 1, 1),
+    "wg_halo_3x3_wide": ("conv", 2, 16, 16, 160, 272, 3, 1, 1),
+    "wg_halo_5x5s2_odd": ("conv", 3, 21, 19, 40, 72, 5, 2, 2),
+    "wg_halo_5x5s1": ("conv", 2, 12, 12, 16, 32, 5, 1, 2),
+    "wg_halo_convT4_192": ("convT", 3, 16, 16, 192, 192, 4, 2, 1),
+    "wg_halo_convT4_b9": ("convT", 9, 8, 8, 96, 136, 4, 2, 1),
+    "wg_halo_shallow": ("conv", 7, 2, 16, 24, 24, 3, 1, 1),
 }
 
 
@@ -123,13 +131,21 @@ def test_tc_wgrad_matches_simt(name):
     gath_f, dense_f = gathered.float().contiguous(), dense.float().contiguous()      # keep alive across the async launch
     call("lb_conv_wgrad", ptr(gath_f), ptr(dense_f), ptr(ref), ctypes.byref(g))
     assert _lib.lib().lb_wgrad_tc_supported(ctypes.byref(g)) == 1
-    dwp = torch.zeros((t, d0, d1), device=DEV)
-    call("lb_wgrad_tc", ptr(gathered), ptr(dense), ptr(dwp), ctypes.byref(g))
+    need = _lib.lib().lb_wgrad_tc_workspace_floats(ctypes.byref(g))
+    assert need >= ref.numel() and need % ref.numel() == 0
+    got = torch.full(shape, float("nan"), device=DEV)                 # overwritten, no zero-fill contract
+    work = torch.full((need + 16,), float("nan"), device=DEV)
+    call("lb_wgrad_tc", ptr(gathered), ptr(dense), ptr(got), ctypes.byref(g), ptr(work), need)
     torch.cuda.synchronize()
-    got = dwp.permute(1, 2, 0).reshape(shape)
     err = (got - ref).abs().max().item()
     scale = ref.abs().max().item()
     assert err <= 3e-4 * scale + 1e-5, f"{name}: max err {err:.3e} vs scale {scale:.3e}"
+    assert torch.isnan(work[need:]).all()                             # stays inside the workspace it asked for
+    # ordered split-K: bit-identical on a second run
+    again = torch.empty(shape, device=DEV)
+    call("lb_wgrad_tc", ptr(gathered), ptr(dense), ptr(again), ctypes.byref(g), ptr(work), need)
+    assert torch.equal(got, again)
+    dwp = got.reshape(d0, d1, t).permute(2, 0, 1).contiguous()        # the tap-major form lb_sn_weight_grad also accepts
     # the packed read path of the spectral-norm epilogue
     wbar = torch.randn(shape, generator=gen).to(DEV)
     u = torch.randn(d0, generator=gen).to(DEV)
