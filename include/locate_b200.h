@@ -135,6 +135,7 @@ int lb_sn_power_iter_batched(const void* layers_dev, int n_layers, const void* i
  *   grad += dwn/sigma - (sum dwn*W)/sigma^2 * u v^T       (SURVEY.md section 8c identity)
  * dwn has W's layout (packed_taps = 0) or is the tap-major [taps][d0][d1] buffer of lb_wgrad_tc
  * (packed_taps = kh*kw).  dot_out: 2 doubles (receives sum dwn*W); stat_work: as lb_norm_stats (ordered grid sum).
+ * w = NULL (packed_taps = 0 only): dot_out[0] already holds sum dwn*W (lb_wgrad_tc computes it as it writes dwn).
  * Trainable u / v -- the reference's training loop calls dis.requires_grad_(True) (main.py:172), which also switches
  * on the discriminator's weight_u / weight_v (requires_grad=False Parameters, spectral_norm.py:45-46); from the second
  * discriminator step on sigma = u.(W v) (spectral_norm.py:31) hands them gradients and Nadam moves them.  Pass
@@ -177,7 +178,8 @@ int lb_conv_wgrad(const float* gathered, const float* dense, float* dw, const lb
 /* Direct fp32 kernels for layers with a tiny channel count on one side (the discriminator stem 3->3 / 3->32 / 3->29 and
  * the generator's final 48->3, conv.py:14-20): the weight sits in shared memory, every activation is touched once, and
  * the neighbouring RootTanh is fused: growth_in > 0 applies RootTanh to the input on load (conv.py:23-24); growth_out > 0
- * multiplies the result by RootTanh'(xpre[pixel][n]) (activation.py:18-36) -- the input-gradient direction.  Geometry and
+ * multiplies the result by RootTanh'(xpre[pixel][n]) (activation.py:18-36) -- the input-gradient direction; growth_out = -1
+ * multiplies by xpre[pixel][n] itself (the derivative the forward pass stored, LB_EX_OUT16_IS_DACT).  Geometry and
  * weight addressing are those of lb_conv_gemm / lb_conv_wgrad; growth_gathered applies RootTanh to the gathered operand. */
 int lb_conv_small_supported(const lb_conv_geom* g);
 int lb_conv_small(const void* in, const float* w, const float* alpha, const float* bias, void* out, const lb_conv_geom* g,
@@ -252,8 +254,11 @@ int lb_conv_tc_gemm_ex(const void* in_bf16, const void* w_packed, const float* a
  * irrelevant on entry) and a second kernel adds the splits in index order -- no floating-point atomics. */
 int lb_wgrad_tc_supported(const lb_conv_geom* g);
 size_t lb_wgrad_tc_workspace_floats(const lb_conv_geom* g);
+/* w / dot_out / stat_work (all three or none): the reduction pass also leaves dot_out[0] = sum dwn * w (w = the master
+ * weight; fixed-order grid sum through stat_work, lb_stat_work_doubles() zeroed doubles) -- lb_sn_weight_grad called with
+ * w = NULL then takes dot_out as given instead of making its own pass over dwn and w. */
 int lb_wgrad_tc(const void* gathered_bf16, const void* dense_bf16, float* dwn, const lb_conv_geom* g, float* work,
-                size_t work_floats, lb_stream_t stream);
+                size_t work_floats, const float* w, double* dot_out, double* stat_work, lb_stream_t stream);
 /* fp32 -> bf16 producers of GEMM operands: plain cast, and RootTanh fused with the cast (activation.py:9-16) */
 int lb_cast_bf16(const float* x, void* y, size_t n, lb_stream_t stream);
 /* row-strided variant: dst[r*ld_dst + c] = bf16(f(src[r*ld_src + c])); f = identity (growth 0) or RootTanh (growth >= 1) */

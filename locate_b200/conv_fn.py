@@ -15,6 +15,7 @@ import torch
 from . import _lib
 from ._lib import ConvGeom, call, ptr
 from .config import CFG
+from . import dist
 from .ops import BF16, F32, _as_act, _cast, _conv_work, _dt, _esz, _grad_sink, _match, _new_act, _timed_call, store_dtype
 
 # weight packs are reused while the weights are unchanged (3 discriminator passes per D step);
@@ -113,11 +114,14 @@ def _uv_extra(pre_sigma, u):
     return uv[0], du, uv[1], uv[2]
 
 
-def _sn_weight_grad(dwn, w_bar, u, v, sigma, spec, packed_taps, extra, dev):
-    """grad(W_bar) += dwn/sigma - (sum dwn*W)/sigma^2 u v^T into the gradient sink; returns what autograd gets."""
+def _sn_weight_grad(dwn, w_bar, u, v, sigma, spec, packed_taps, extra, dev, dot=None):
+    """grad(W_bar) += dwn/sigma - (sum dwn*W)/sigma^2 u v^T into the gradient sink; returns what autograd gets.
+    `dot`: 2 doubles already holding sum dwn*W (left by lb_wgrad_tc's reduction pass)."""
     from .ops import _stat_work
     grad_w, dw_ret = _grad_sink(w_bar)
-    dot = torch.empty(2, dtype=torch.float64, device=dev)
+    have_dot = dot is not None
+    if not have_dot:
+        dot = torch.empty(2, dtype=torch.float64, device=dev)
     height, width = spec.sn_shape
     s_fwd = du = cacc = None
     if extra is not None:
@@ -125,8 +129,9 @@ def _sn_weight_grad(dwn, w_bar, u, v, sigma, spec, packed_taps, extra, dev):
         if u.grad is None:
             u.grad, v.grad = u._lb_grad, v._lb_grad
         batch.uv_pending = True
-    call("lb_sn_weight_grad", ptr(dwn), ptr(w_bar), ptr(u.data), ptr(v.data), ptr(sigma), ptr(grad_w), height, width, packed_taps,
-         ptr(dot), ptr(_stat_work(dev)), ptr(s_fwd), ptr(du), ptr(cacc))
+    call("lb_sn_weight_grad", ptr(dwn), None if have_dot else ptr(w_bar), ptr(u.data), ptr(v.data), ptr(sigma), ptr(grad_w), height,
+         width, packed_taps, ptr(dot), ptr(_stat_work(dev)), ptr(s_fwd), ptr(du), ptr(cacc))
+    dist.grad_written(w_bar)
     return dw_ret
 
 
@@ -330,8 +335,8 @@ class SNConvFn(torch.autograd.Function):
                     _tc_gemm(fl, _tc_bytes(g_dgrad), gy_ptr, pk, sigma.data_ptr() + 4, None, ptr(dx), g_dgrad, dev, F32)
             if need_dw:
                 ga_ptr, de_ptr = (gy_ptr, ptr(a)) if spec.kind == "convT" else (ptr(a), gy_ptr)
-                dwn = _wgrad_tc(ga_ptr, de_ptr, g_wgrad, w_bar.numel(), fl, dev)
-                dw_ret = _sn_weight_grad(dwn, ctx.w_param, ctx.u, ctx.v, sigma, spec, 0, ctx.uv_extra, dev)
+                dwn, dot = _wgrad_tc(ga_ptr, de_ptr, g_wgrad, w_bar, fl, dev)
+                dw_ret = _sn_weight_grad(dwn, ctx.w_param, ctx.u, ctx.v, sigma, spec, 0, ctx.uv_extra, dev, dot)
         else:
             growth = CFG.ROOTTANH_GROWTH
             gy_ptr = gout.data_ptr() + off * esz_g    # gradient of the conv output slice, row stride ctot
@@ -378,6 +383,7 @@ class SNConvFn(torch.autograd.Function):
         if ctx.bias_param is not None and ctx.needs_input_grad[4]:
             dbias, dbias_ret = _grad_sink(ctx.bias_param)
             call("lb_colsum", gout.data_ptr() + off * esz_g, rows, spec.cout, ctot, ptr(dbias), _dt(gout))
+            dist.grad_written(ctx.bias_param)
         return dx, dw_ret, None, None, dbias_ret, None, None, None, None
 
 
@@ -405,23 +411,26 @@ def _ex_ok(g, out32, ld16, ld_aux, aux_dtype=F32):
 _WGRAD_WORK = {}
 
 
-def _wgrad_tc(gathered_ptr, dense_ptr, g_wgrad, numel, fl, dev):
-    """Raw dW (fp32, master layout) of one conv on the tensor cores: lb_wgrad_tc with its split-K workspace (one buffer
-    per device, grown to the largest layer; every layer overwrites it, stream order keeps the uses apart)."""
+def _wgrad_tc(gathered_ptr, dense_ptr, g_wgrad, w_bar, fl, dev):
+    """Raw dW (fp32, master layout) of one conv on the tensor cores and sum dW * W_bar: lb_wgrad_tc with its split-K
+    workspace (one buffer per device, grown to the largest layer; every layer overwrites it, stream order keeps the
+    uses apart)."""
+    from .ops import _stat_work
     need = _lib.lib().lb_wgrad_tc_workspace_floats(ctypes.byref(g_wgrad))
     work = _WGRAD_WORK.get(dev)
     if work is None or work.numel() < need:
         work = _WGRAD_WORK[dev] = torch.empty(max(need, 1 << 22), dtype=torch.float32, device=dev)
-    dwn = torch.empty(numel, dtype=torch.float32, device=dev)
+    dwn = torch.empty(w_bar.numel(), dtype=torch.float32, device=dev)
+    dot = torch.empty(2, dtype=torch.float64, device=dev)
     _timed_call("wgrad_tc", fl, _wgrad_bytes(g_wgrad), "lb_wgrad_tc", gathered_ptr, dense_ptr, ptr(dwn), g_wgrad, ptr(work),
-                work.numel())
-    return dwn
+                work.numel(), ptr(w_bar), ptr(dot), ptr(_stat_work(dev)))
+    return dwn, dot
 
 
 def _sn_wgrad_tc(ctx_w, u, v, sigma, gathered_ptr, dense_ptr, g_wgrad, spec, fl, by, dev, extra=None):
     """dW of one spectral-normed conv on the tensor cores + the sigma correction, accumulated into the grad sink."""
-    dwn = _wgrad_tc(gathered_ptr, dense_ptr, g_wgrad, ctx_w.numel(), fl, dev)
-    return _sn_weight_grad(dwn, ctx_w, u, v, sigma, spec, 0, extra, dev)
+    dwn, dot = _wgrad_tc(gathered_ptr, dense_ptr, g_wgrad, ctx_w, fl, dev)
+    return _sn_weight_grad(dwn, ctx_w, u, v, sigma, spec, 0, extra, dev, dot)
 
 
 class ActivatedPairFn(torch.autograd.Function):
@@ -495,8 +504,19 @@ class ActivatedPairFn(torch.autograd.Function):
             dw1 = _sn_wgrad_tc(w1, u1, v1, sigma1, ptr(ga), ptr(de), gw1, spec1, fl1, by1, dev, ctx.uv_extra[1])
         if need_dx or need_dw0:
             d0 = torch.empty_like(a0)            # bf16( dL/dy0 ) = bf16( dgrad_1(g1) * RootTanh'(y0) ), the factor stored by the forward
-            _timed_call("conv_tc", fl1, _tc_bytes(gd1), "lb_conv_tc_gemm_ex", ptr(g1), ptr(_packed_weight(w1, gd1, "dgrad")),
-                        sigma1.data_ptr() + 4, None, None, ptr(d0), None, mid, ptr(dact0), mid, BF16, EX_AUX_IS_FACTOR, gd1)
+            gs = None
+            if cout <= 4 and gout.dtype == torch.float32 and CFG.SMALL_KERNELS:
+                # RGB-wide gradient (G's last layer): 3 fp32 values per pixel fan out to `mid` channels on the direct kernel
+                gs = ConvGeom.from_buffer_copy(bytes(gd1))
+                gs.ld_in = cout                         # fp32 rows of the RGB gradient, dense
+                if _lib.lib().lb_conv_small_supported(ctypes.byref(gs)) != 1:
+                    gs = None
+            if gs is not None:
+                _timed_call("conv_small", fl1, _tc_bytes(gd1), "lb_conv_small", ptr(gout), ptr(w1), sigma1.data_ptr() + 4, None, ptr(d0),
+                            gs, 0, ptr(dact0), mid, -1, 0, BF16)
+            else:
+                _timed_call("conv_tc", fl1, _tc_bytes(gd1), "lb_conv_tc_gemm_ex", ptr(g1), ptr(_packed_weight(w1, gd1, "dgrad")),
+                            sigma1.data_ptr() + 4, None, None, ptr(d0), None, mid, ptr(dact0), mid, BF16, EX_AUX_IS_FACTOR, gd1)
             if need_dw0:
                 ga, de = (d0, act16) if spec0.kind == "convT" else (act16, d0)
                 dw0 = _sn_wgrad_tc(w0, u0, v0, sigma0, ptr(ga), ptr(de), gw0, spec0, fl0, by0, dev, ctx.uv_extra[0])

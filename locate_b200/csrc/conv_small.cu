@@ -26,7 +26,7 @@ struct SmallP {
   int kh, kw, stride, pad, mode, ld_in, ld_out, ld_xpre;
   long long w_sk, w_sn, w_sty, w_stx;
   int growth_in;      // > 0: RootTanh(growth) applied to every input element on load
-  int growth_out;     // > 0: result multiplied by RootTanh'(xpre[p][n])
+  int growth_out;     // > 0: result multiplied by RootTanh'(xpre[p][n]); -1: by xpre[p][n] itself (a stored derivative)
   int cat;            // rows of `out` are [in (in_c, copied) | conv (out_c)]  (CatModule, merge.py:10-16)
   int pointwise;      // 1x1, stride 1, pad 0: input pixel == output pixel
   int pixels;         // batch*out_h*out_w (< 2^31, checked by the host)
@@ -37,6 +37,7 @@ __device__ __forceinline__ float small_act(float v, int growth) {
   return growth == 4 ? lb_roottanh(v) : (growth > 0 ? lb_roottanh_g(v, 1.0f / growth) : v);
 }
 __device__ __forceinline__ float small_dact(float v, int growth) {
+  if (growth < 0) return v;                            // xpre already holds RootTanh' (stored by the forward pass)
   return growth == 4 ? lb_roottanh_grad(v) : lb_roottanh_grad_g(v, 1.0f / growth);
 }
 // source pixel of tap t along one axis (stride 1 or 2): false if the tap does not reach a source pixel
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_small_narrow_in(const SmallP 
         }
       }
     }
-    if (go > 0) {
+    if (go != 0) {
       const TO* xr = p_xpre + (size_t)pix * p.ld_xpre;
 #pragma unroll
       for (int n = 0; n < NC; ++n)
@@ -207,7 +208,7 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_small_narrow_out(const SmallP
 #pragma unroll
     for (int n = 0; n < 4; ++n) {
       if (n < p.out_c) {
-        if (go > 0) r[n] *= small_dact(__ldg(p_xpre + (size_t)pix * p.ld_xpre + n), go);
+        if (go != 0) r[n] *= small_dact(__ldg(p_xpre + (size_t)pix * p.ld_xpre + n), go);
         dst[n] = r[n];
       }
     }
@@ -236,7 +237,7 @@ extern "C" int lb_conv_small_supported(const lb_conv_geom* g) {
 extern "C" int lb_conv_small(const void* in, const float* w, const float* alpha, const float* bias, void* out,
                              const lb_conv_geom* g, int growth_in, const void* xpre, int ld_xpre, int growth_out,
                              int cat_input, int wide_dtype, lb_stream_t s) {
-  LB_REQUIRE(in && w && out && g && growth_in >= 0 && growth_out >= 0 && (growth_out == 0 || xpre));
+  LB_REQUIRE(in && w && out && g && growth_in >= 0 && growth_out >= -1 && (growth_out == 0 || xpre));
   LB_REQUIRE(wide_dtype == LB_F32 || wide_dtype == LB_BF16);
   if (!lb_conv_small_supported(g)) return LB_EUNSUPPORTED;
   SmallP p;

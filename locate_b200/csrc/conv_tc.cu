@@ -276,6 +276,7 @@ extern "C" size_t lb_conv_tc_packed_elems(const lb_conv_geom* g) {
 
 // One thread = one (n, k) pair: its taps are contiguous in the master layout (64-100 bytes read in one go), and for each
 // tap consecutive threads write consecutive k of one packed row.
+template <bool kVec4>
 __global__ void __launch_bounds__(256) k_pack_weight(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int taps_h, int taps_w,
                                                     int n_rows, int k, int kpad, long long w_sk, long long w_sn, long long w_sty,
                                                     long long w_stx, int items, LbFastDiv d_kpad) {
@@ -286,9 +287,20 @@ __global__ void __launch_bounds__(256) k_pack_weight(const float* __restrict__ w
     const float* src = w + kk * w_sk + n * w_sn;
     __nv_bfloat16* dst = out + (size_t)n * kpad + kk;
     const size_t tap_stride = (size_t)n_rows * kpad;
-    for (int ty = 0; ty < taps_h; ++ty)
-      for (int tx = 0; tx < taps_w; ++tx)
-        dst[(size_t)(ty * taps_w + tx) * tap_stride] = __float2bfloat16(kk < k ? __ldg(src + ty * w_sty + tx * w_stx) : 0.0f);
+    if (kVec4) {                       // the taps of one (n, k) pair are one contiguous, 16-byte aligned run of the master weight
+      const int taps = taps_h * taps_w;
+      for (int t = 0; t < taps; t += 4) {
+        const float4 v = kk < k ? __ldcs(reinterpret_cast<const float4*>(src + t)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        dst[(size_t)t * tap_stride] = __float2bfloat16(v.x);
+        dst[(size_t)(t + 1) * tap_stride] = __float2bfloat16(v.y);
+        dst[(size_t)(t + 2) * tap_stride] = __float2bfloat16(v.z);
+        dst[(size_t)(t + 3) * tap_stride] = __float2bfloat16(v.w);
+      }
+    } else {
+      for (int ty = 0; ty < taps_h; ++ty)
+        for (int tx = 0; tx < taps_w; ++tx)
+          dst[(size_t)(ty * taps_w + tx) * tap_stride] = __float2bfloat16(kk < k ? __ldg(src + ty * w_sty + tx * w_stx) : 0.0f);
+    }
   }
 }
 extern "C" int lb_conv_tc_pack(const float* w, void* packed, const lb_conv_geom* g, lb_stream_t s) {
@@ -296,9 +308,17 @@ extern "C" int lb_conv_tc_pack(const float* w, void* packed, const lb_conv_geom*
   const int kpad = (g->in_c + 7) / 8 * 8;
   const long long items = (long long)g->out_c * kpad;
   LB_REQUIRE(items < (1ll << 31) - (1ll << 24));
-  k_pack_weight<<<lb_grid_1d((size_t)items, 256), 256, 0, lb_s(s)>>>(w, reinterpret_cast<__nv_bfloat16*>(packed), g->kh, g->kw, g->out_c,
-                                                                    g->in_c, kpad, g->w_sk, g->w_sn, g->w_sty, g->w_stx, (int)items,
-                                                                    lb_make_fastdiv(kpad));
+  const int taps = g->kh * g->kw;
+  const bool vec = taps % 4 == 0 && g->w_stx == 1 && g->w_sty == g->kw && g->w_sk % 4 == 0 && g->w_sn % 4 == 0 &&
+                   (reinterpret_cast<uintptr_t>(w) & 15) == 0;
+  if (vec)
+    k_pack_weight<true><<<lb_grid_1d((size_t)items, 256), 256, 0, lb_s(s)>>>(w, reinterpret_cast<__nv_bfloat16*>(packed), g->kh, g->kw,
+                                                                            g->out_c, g->in_c, kpad, g->w_sk, g->w_sn, g->w_sty,
+                                                                            g->w_stx, (int)items, lb_make_fastdiv(kpad));
+  else
+    k_pack_weight<false><<<lb_grid_1d((size_t)items, 256), 256, 0, lb_s(s)>>>(w, reinterpret_cast<__nv_bfloat16*>(packed), g->kh, g->kw,
+                                                                             g->out_c, g->in_c, kpad, g->w_sk, g->w_sn, g->w_sty,
+                                                                             g->w_stx, (int)items, lb_make_fastdiv(kpad));
   LB_LAUNCH_CHECK();
   return LB_OK;
 }

@@ -138,10 +138,52 @@ __global__ void __launch_bounds__(256) k_sn_wgrad(const float* __restrict__ dwn,
     if (cacc && k == 0) cacc[0] -= coef;
   }
 }
+// contiguous (packed_taps = 0) fast paths: 4 consecutive elements of one matrix row per thread
+__global__ void __launch_bounds__(256) k_sn_dot4(const float4* __restrict__ a, const float4* __restrict__ b, int n4,
+                                                double* __restrict__ out, double* __restrict__ stat_work) {
+  __shared__ double scratch[32];
+  const int stride = gridDim.x * blockDim.x;
+  double acc = 0.0;
+  float part = 0.0f;
+  int cnt = 0;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n4; k += stride) {
+    const float4 x = __ldcs(a + k), y = __ldg(b + k);
+    part = fmaf(x.x, y.x, fmaf(x.y, y.y, fmaf(x.z, y.z, fmaf(x.w, y.w, part))));
+    if (++cnt == 4) { acc += (double)part; part = 0.0f; cnt = 0; }
+  }
+  acc += (double)part;
+  acc = lb_block_sum(acc, scratch);
+  lb_grid_sum2_ordered(acc, 0.0, stat_work, out, scratch);
+}
+__global__ void __launch_bounds__(256) k_sn_wgrad4(const float4* __restrict__ dwn, const float* __restrict__ u, const float* __restrict__ v,
+                                                  const float* __restrict__ sigma, const double* __restrict__ dot,
+                                                  float4* __restrict__ grad, int n4, int height, LbFastDiv d_w4,
+                                                  const float* __restrict__ s_fwd, float* __restrict__ du, float* __restrict__ cacc) {
+  const float inv = __ldg(sigma + 1);
+  const float coef = (float)(dot[0] * (double)inv * (double)inv);
+  const int stride = gridDim.x * blockDim.x;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n4; k += stride) {
+    int i, j4;
+    lb_fast_divmod(d_w4, k, i, j4);
+    const float cu = -coef * __ldg(u + i);
+    const float4 vv = __ldg(reinterpret_cast<const float4*>(v) + j4);
+    const float4 d = __ldcs(dwn + k);
+    float4 g = grad[k];
+    g.x += fmaf(d.x, inv, cu * vv.x);
+    g.y += fmaf(d.y, inv, cu * vv.y);
+    g.z += fmaf(d.z, inv, cu * vv.z);
+    g.w += fmaf(d.w, inv, cu * vv.w);
+    grad[k] = g;
+    if (du && k < height) du[k] = fmaf(-coef, __ldg(s_fwd + k), du[k]);
+    if (cacc && k == 0) cacc[0] -= coef;
+  }
+}
+// w == NULL: dot_out[0] already holds sum dwn * W (lb_wgrad_tc computes it while it writes dwn).
 extern "C" int lb_sn_weight_grad(const float* dwn, const float* w, const float* u, const float* v, const float* sigma,
                                  float* grad, int height, int width, int packed_taps, double* dot_out, double* stat_work,
                                  const float* s_fwd, float* du, float* cacc, lb_stream_t s) {
-  LB_REQUIRE(dwn && w && u && v && sigma && grad && dot_out && stat_work && height > 0 && width > 0 && packed_taps >= 0);
+  LB_REQUIRE(dwn && u && v && sigma && grad && dot_out && stat_work && height > 0 && width > 0 && packed_taps >= 0);
+  LB_REQUIRE(w || packed_taps == 0);
   LB_REQUIRE(packed_taps == 0 || width % packed_taps == 0);
   LB_REQUIRE((s_fwd && du && cacc) || (!s_fwd && !du && !cacc));
   const size_t n = (size_t)height * width;
@@ -149,9 +191,23 @@ extern "C" int lb_sn_weight_grad(const float* dwn, const float* w, const float* 
   SnIdx x;
   x.width = width; x.height = height; x.taps = packed_taps; x.d1 = packed_taps ? width / packed_taps : width;
   x.d_width = lb_make_fastdiv(width); x.d_taps = lb_make_fastdiv(packed_taps ? packed_taps : 1);
-  k_sn_dot<<<lb_grid_1d(n, 256, 2), 256, 0, lb_s(s)>>>(dwn, w, (int)n, x, dot_out, stat_work);
-  LB_LAUNCH_CHECK();
-  k_sn_wgrad<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(dwn, u, v, sigma, dot_out, grad, (int)n, x, s_fwd, du, cacc);
+  const bool vec = packed_taps == 0 && width % 4 == 0 && height <= (int)(n / 4) &&
+                   !((reinterpret_cast<uintptr_t>(dwn) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(v) |
+                      (w ? reinterpret_cast<uintptr_t>(w) : 0)) & 15);
+  if (w) {
+    if (vec)
+      k_sn_dot4<<<lb_grid_1d(n / 4, 256, 4), 256, 0, lb_s(s)>>>(reinterpret_cast<const float4*>(dwn), reinterpret_cast<const float4*>(w),
+                                                                  (int)(n / 4), dot_out, stat_work);
+    else
+      k_sn_dot<<<lb_grid_1d(n, 256, 2), 256, 0, lb_s(s)>>>(dwn, w, (int)n, x, dot_out, stat_work);
+    LB_LAUNCH_CHECK();
+  }
+  if (vec)
+    k_sn_wgrad4<<<lb_grid_1d(n / 4, 256), 256, 0, lb_s(s)>>>(reinterpret_cast<const float4*>(dwn), u, v, sigma, dot_out,
+                                                              reinterpret_cast<float4*>(grad), (int)(n / 4), height,
+                                                              lb_make_fastdiv(width / 4), s_fwd, du, cacc);
+  else
+    k_sn_wgrad<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(dwn, u, v, sigma, dot_out, grad, (int)n, x, s_fwd, du, cacc);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
@@ -170,15 +226,31 @@ __global__ void __launch_bounds__(256) k_snb_wt_u(const LbSnLayerDev* __restrict
                                                  float* __restrict__ scratch) {
   const int4 it = items[blockIdx.x];
   const LbSnLayerDev L = layers[it.x];
-  const int j = it.y + threadIdx.x;
+  const int j = it.y + 4 * threadIdx.x;                    // 4 consecutive columns per thread
   if (j >= L.width) return;
   const int i1 = min(L.height, it.z + it.w);
-  float acc = 0.0f;
-  for (int i = it.z; i < i1; ++i) acc = fmaf(L.w[(size_t)i * L.width + j], __ldg(L.u + i), acc);
-  scratch[(size_t)L.t_off + (size_t)(it.z / L.rows_per_split) * L.width + j] = acc;
+  float* dst = scratch + (size_t)L.t_off + (size_t)(it.z / L.rows_per_split) * L.width + j;
+  if ((L.width & 3) == 0 && (reinterpret_cast<uintptr_t>(L.w) & 15) == 0) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int i = it.z; i < i1; ++i) {
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(L.w + (size_t)i * L.width + j));
+      const float ui = __ldg(L.u + i);
+      acc.x = fmaf(wv.x, ui, acc.x); acc.y = fmaf(wv.y, ui, acc.y); acc.z = fmaf(wv.z, ui, acc.z); acc.w = fmaf(wv.w, ui, acc.w);
+    }
+    dst[0] = acc.x; dst[1] = acc.y; dst[2] = acc.z; dst[3] = acc.w;
+  } else {
+    const int cols = min(4, L.width - j);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int i = it.z; i < i1; ++i) {
+      const float ui = __ldg(L.u + i);
+      for (int e = 0; e < cols; ++e) acc[e] = fmaf(L.w[(size_t)i * L.width + j + e], ui, acc[e]);
+    }
+    for (int e = 0; e < cols; ++e) dst[e] = acc[e];
+  }
 }
 // per layer: dst = src/(|src|+eps); phase 2 (v from t) and phase 4 (u from s, sigma)
-__global__ void __launch_bounds__(512) k_snb_normalize(const LbSnLayerDev* __restrict__ layers, float* __restrict__ scratch,
+__global__ void __launch_bounds__(1024) k_snb_normalize(const LbSnLayerDev* __restrict__ layers, float* __restrict__ scratch,
                                                       float* __restrict__ s_out, int phase, float* __restrict__ sigma_out) {
   __shared__ float red[32];
   __shared__ float s_norm;
@@ -190,7 +262,13 @@ __global__ void __launch_bounds__(512) k_snb_normalize(const LbSnLayerDev* __res
   float acc = 0.0f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     float v = src[i];
-    for (int sp = 1; sp < nsplit; ++sp) v += src[(size_t)sp * n + i];     // fixed order over the row splits
+    int sp = 1;
+    for (; sp + 4 <= nsplit; sp += 4) {                                   // fixed order over the row splits, loads in flight together
+      const float a = src[(size_t)sp * n + i], b = src[(size_t)(sp + 1) * n + i], c = src[(size_t)(sp + 2) * n + i],
+                  d = src[(size_t)(sp + 3) * n + i];
+      v = (((v + a) + b) + c) + d;
+    }
+    for (; sp < nsplit; ++sp) v += src[(size_t)sp * n + i];
     src[i] = v;
     acc = fmaf(v, v, acc);
   }
@@ -215,7 +293,16 @@ __global__ void __launch_bounds__(256) k_snb_w_v(const LbSnLayerDev* __restrict_
   if (row >= L.height) return;
   const float* wr = L.w + (size_t)row * L.width;
   float acc = 0.0f;
-  for (int j = lane; j < L.width; j += 32) acc = fmaf(wr[j], __ldg(L.v + j), acc);
+  if ((L.width & 3) == 0 && ((reinterpret_cast<uintptr_t>(L.w) | reinterpret_cast<uintptr_t>(L.v)) & 15) == 0) {
+#pragma unroll 2
+    for (int j = 4 * lane; j < L.width; j += 128) {
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(wr + j));
+      const float4 vv = __ldg(reinterpret_cast<const float4*>(L.v + j));
+      acc = fmaf(wv.x, vv.x, fmaf(wv.y, vv.y, fmaf(wv.z, vv.z, fmaf(wv.w, vv.w, acc))));
+    }
+  } else {
+    for (int j = lane; j < L.width; j += 32) acc = fmaf(wr[j], __ldg(L.v + j), acc);
+  }
   acc = lb_warp_sum(acc);
   if (lane == 0) scratch[L.s_off + row] = acc;        // `scratch` is s_out here
 }
@@ -227,11 +314,11 @@ extern "C" int lb_sn_power_iter_batched(const void* layers_dev, int n_layers, co
   const LbSnLayerDev* layers = reinterpret_cast<const LbSnLayerDev*>(layers_dev);
   k_snb_wt_u<<<n_items1, 256, 0, lb_s(s)>>>(layers, reinterpret_cast<const int4*>(items1_dev), scratch);
   LB_LAUNCH_CHECK();
-  k_snb_normalize<<<n_layers, 512, 0, lb_s(s)>>>(layers, scratch, s_out, 2, sigma_out);
+  k_snb_normalize<<<n_layers, 1024, 0, lb_s(s)>>>(layers, scratch, s_out, 2, sigma_out);
   LB_LAUNCH_CHECK();
   k_snb_w_v<<<n_items3, 256, 0, lb_s(s)>>>(layers, reinterpret_cast<const int2*>(items3_dev), s_out);
   LB_LAUNCH_CHECK();
-  k_snb_normalize<<<n_layers, 512, 0, lb_s(s)>>>(layers, scratch, s_out, 4, sigma_out);
+  k_snb_normalize<<<n_layers, 1024, 0, lb_s(s)>>>(layers, scratch, s_out, 4, sigma_out);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }

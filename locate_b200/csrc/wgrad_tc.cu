@@ -303,34 +303,53 @@ __global__ void __launch_bounds__(192, 1) k_wgrad_halo(const __grid_constant__ W
   }
 }
 
-// ---- ordered split reduction + transposition to the master layout ---------------------------------------------------
-// part: [splits][taps][d_c][g_c] (m contiguous) -> dwn[(n * g_c + m) * taps + tap].  CTA = (32 m, one n): warps walk the
-// taps (coalesced 128-byte reads per split, summed in split order), shared memory turns the tile, and the store side
-// writes 32 x taps consecutive floats.
-constexpr int kRedTaps = 64;
-__global__ void __launch_bounds__(256) k_wgrad_reduce(const float* __restrict__ part, float* __restrict__ dwn, int splits,
-                                                      size_t split_stride, int taps, int d_c, int g_c) {
-  __shared__ float tile[32][kRedTaps + 1];
-  const int m0 = blockIdx.x * 32, n = blockIdx.y;
+// ---- ordered split reduction + transposition to the master layout (+ the spectral-norm dot product) ------------------
+// part: [splits][taps][d_c][g_c] (m contiguous) -> dwn[(n * g_c + m) * taps + tap].  One WARP per tile (one n, 32 m): it
+// walks the taps (coalesced 128-byte reads per split, summed in split order -- all taps' loads in flight together), turns
+// the tile through its own slice of shared memory and stores 32 x taps consecutive floats.  With `w` (the master weight)
+// the same pass accumulates dot = sum dwn * w, reduced over the grid in fixed order: the spectral-norm correction
+// (lb_sn_weight_grad) then needs no pass of its own over dwn and w.
+constexpr int kRedTaps = 32;
+__global__ void __launch_bounds__(256) k_wgrad_reduce(const float* __restrict__ part, float* __restrict__ dwn, const float* __restrict__ w,
+                                                      int splits, size_t split_stride, int taps, int d_c, int g_c, int m_chunks,
+                                                      int tiles, double* __restrict__ dot_out, double* __restrict__ stat_work) {
+  __shared__ float tile_s[8][32][kRedTaps + 1];
+  __shared__ double scratch[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int mm = min(32, g_c - m0);
-  for (int t0 = 0; t0 < taps; t0 += kRedTaps) {
-    const int tc_ = min(kRedTaps, taps - t0);
-    for (int t = warp; t < tc_; t += 8) {
-      float acc = 0.0f;
+  float (*tile)[kRedTaps + 1] = tile_s[warp];
+  double dacc = 0.0;
+  for (int tl = blockIdx.x * 8 + warp; tl < tiles; tl += gridDim.x * 8) {
+    const int n = tl / m_chunks, m0 = (tl - n * m_chunks) * 32;
+    const int mm = min(32, g_c - m0);
+    float fpart = 0.0f;
+    for (int t0 = 0; t0 < taps; t0 += kRedTaps) {
+      const int tc_ = min(kRedTaps, taps - t0);
       if (lane < mm) {
-        const float* src = part + ((size_t)(t0 + t) * d_c + n) * g_c + m0 + lane;
-        for (int s = 0; s < splits; ++s) acc += __ldg(src + s * split_stride);
+        const float* src = part + ((size_t)t0 * d_c + n) * g_c + m0 + lane;
+        const size_t tap_stride = (size_t)d_c * g_c;
+#pragma unroll 4
+        for (int t = 0; t < tc_; ++t) {
+          float acc = 0.0f;
+          for (int sp = 0; sp < splits; ++sp) acc += __ldcs(src + t * tap_stride + sp * split_stride);
+          tile[lane][t] = acc;
+        }
       }
-      tile[lane][t] = acc;
+      __syncwarp();
+      const size_t base = ((size_t)n * g_c + m0) * taps + t0;
+      for (int j = lane; j < mm * tc_; j += 32) {
+        const int m = j / tc_, t = j - m * tc_;
+        const float v = tile[m][t];
+        const size_t idx = base + (size_t)m * taps + t;
+        dwn[idx] = v;
+        if (w) fpart = fmaf(v, __ldg(w + idx), fpart);
+      }
+      __syncwarp();
     }
-    __syncthreads();
-    float* dst = dwn + ((size_t)n * g_c + m0) * taps + t0;
-    for (int j = threadIdx.x; j < mm * tc_; j += 256) {
-      const int m = j / tc_, t = j - m * tc_;
-      dst[(size_t)m * taps + t] = tile[m][t];
-    }
-    __syncthreads();
+    dacc += (double)fpart;                              // short fp32 runs (<= taps floats per lane), fp64 across tiles
+  }
+  if (w) {
+    dacc = lb_block_sum(dacc, scratch);
+    lb_grid_sum2_ordered(dacc, 0.0, stat_work, dot_out, scratch);
   }
 }
 
@@ -480,9 +499,11 @@ extern "C" size_t lb_wgrad_tc_workspace_floats(const lb_conv_geom* g) {
 
 // geom as lb_conv_wgrad: in_* = gathered operand, out_* = dense operand.  dwn: fp32, the master weight's layout
 // [out_c][in_c][kh][kw] of this geometry's (dense, gathered) channel pair, OVERWRITTEN.
+// w / dot_out / stat_work (all or none): dot_out[0] = sum dwn * w in fixed order (stat_work as lb_norm_stats).
 extern "C" int lb_wgrad_tc(const void* gathered_bf16, const void* dense_bf16, float* dwn, const lb_conv_geom* g, float* work,
-                           size_t work_floats, lb_stream_t s) {
+                           size_t work_floats, const float* w, double* dot_out, double* stat_work, lb_stream_t s) {
   LB_REQUIRE(gathered_bf16 && dense_bf16 && dwn && g && work);
+  LB_REQUIRE((w && dot_out && stat_work) || (!w && !dot_out && !stat_work));
   if (!wg_geom_ok(g)) return LB_EUNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(gathered_bf16) & 15) || (reinterpret_cast<uintptr_t>(dense_bf16) & 15)) return LB_EALIGN;
   WgPlan pl;
@@ -570,9 +591,13 @@ extern "C" int lb_wgrad_tc(const void* gathered_bf16, const void* dense_bf16, fl
     k_wgrad_tc<<<grid, 192, pl.smem_bytes, lb_s(s)>>>(maps, p);
     LB_LAUNCH_CHECK();
   }
-  dim3 rgrid((g->in_c + 31) / 32, g->out_c);
-  LB_REQUIRE(rgrid.y <= 65535);
-  k_wgrad_reduce<<<rgrid, 256, 0, lb_s(s)>>>(work, dwn, pl.splits, numel, pl.taps, g->out_c, g->in_c);
+  const int m_chunks = (g->in_c + 31) / 32;
+  const long long tiles = (long long)m_chunks * g->out_c;
+  LB_REQUIRE(tiles < (1ll << 31));
+  long long rblocks = (tiles + 7) / 8;
+  if (rblocks > LB_SMS * 8) rblocks = LB_SMS * 8;       // <= the statistics workspace's grid bound
+  k_wgrad_reduce<<<(unsigned)rblocks, 256, 0, lb_s(s)>>>(work, dwn, w, pl.splits, numel, pl.taps, g->out_c, g->in_c, m_chunks, (int)tiles,
+                                                         dot_out, stat_work);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }

@@ -342,6 +342,10 @@ class WholeNormFn(torch.autograd.Function):
         sc = torch.empty(2, dtype=torch.float64, device=x.device)
         call("lb_norm_bwd_finalize", ptr(part[0]), ptr(part[1]), ptr(gain), c if ctx.per_sample else 0, ptr(stats), b, c,
              ptr(dgain), ptr(dbias), ptr(sc))
+        if need_gain and not ctx.per_sample:
+            dist.grad_written(ctx.gain_param)
+        if need_bias:
+            dist.grad_written(ctx.bias_param)
         dist.all_reduce_sum_(sc)
         dx = None
         if ctx.needs_input_grad[0]:
@@ -400,6 +404,8 @@ class GateFn(torch.autograd.Function):
             dgamma, dgamma_ret = None, None
         call("lb_gate_bwd", ptr(x), ptr(y), ptr(gamma), ptr(g), ptr(dx), ptr(dy), ptr(dyb), ptr(dgamma), b, p, c, int(ctx.bcast),
              int(ctx.strict), dt)
+        if ctx.needs_input_grad[2]:
+            dist.grad_written(ctx.gamma_param)
         if ctx.bcast:
             dy = _cast(dyb, ctx.y_dtype).view(y.shape)
         return dx, dy, dgamma_ret, None

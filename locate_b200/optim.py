@@ -76,7 +76,7 @@ class Nadam(Optimizer):
                     p._lb_epoch = epoch
                     p.grad = gview
         return dict(param=flat_p, grad=flat_g, exp_avg=torch.zeros_like(flat_p), exp_avg_sq=torch.zeros_like(flat_p),
-                    step=0, n=total, epoch=epoch, late=late, params=train,
+                    step=0, n=total, epoch=epoch, late=late, params=train, offsets=offsets,
                     sched=torch.tensor([0.0, 1.0], dtype=torch.float64, device=dev),   # {t, m_schedule}
                     hyper=torch.zeros(3, dtype=torch.float32, device=dev))
 

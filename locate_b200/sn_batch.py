@@ -13,6 +13,7 @@ import torch
 from ._lib import call, ptr
 
 _ROWS_PER_ITEM1 = 256        # rows x 256 columns per pass-1 work item (64 K elements)
+_COLS_PER_ITEM1 = 1024      # k_snb_wt_u: 256 threads x 4 consecutive columns (one 16-byte load per row)
 
 
 class _LayerRec(ctypes.Structure):
@@ -49,7 +50,7 @@ class SpectralBatch:
             self._s_slices.append((s_off, height))
             off += nsplit * width
             s_off += height
-            for c0 in range(0, width, 256):
+            for c0 in range(0, width, _COLS_PER_ITEM1):
                 for r0 in range(0, height, _ROWS_PER_ITEM1):
                     items1.append((l, c0, r0, min(_ROWS_PER_ITEM1, height - r0)))
             for r0 in range(0, height, 8):

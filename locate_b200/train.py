@@ -62,11 +62,32 @@ class GanTrainer:
         self._graph = self._static_in = self._static_out = None
         self._copy_stream = self._stage_bufs = self._staged = self._consumed = None
 
+    def _overlap_begin(self, opt, tag):
+        """Data parallel: from here on every gradient bucket of `opt`'s main arena is all-reduced as soon as its last
+        contributor of this backward pass has run (dist.GradOverlap), overlapping the exchange with the backward pass."""
+        if not dist.active():
+            return
+        trackers = self.__dict__.setdefault("_overlap", {})
+        tr = trackers.get(id(opt))
+        if tr is None:
+            main = [a for a in opt.live_arenas() if not a["late"]]
+            if len(main) != 1:
+                return
+            a = main[0]
+            tr = trackers[id(opt)] = dist.GradOverlap(a["grad"], a["params"], a["offsets"])
+        tr.begin(tag)
+        dist._TRACKER[0] = tr
+
     def _reduce_and_step(self, opt):
         model = getattr(opt, "_lb_model", None)
         if model is not None:
             model._finish_uv_grads()       # complete the gradients of trainable spectral-norm v's BEFORE they are reduced
-        for h in [h for flat in opt.flat_grads for h in dist.all_reduce_grads_(flat)]:
+        tr, dist._TRACKER[0] = dist._TRACKER[0], None
+        done = None
+        if tr is not None and tr.flat.data_ptr() in [f.data_ptr() for f in opt.flat_grads]:
+            tr.finish()                    # buckets that fired during the backward pass are (being) reduced already
+            done = tr.flat.data_ptr()
+        for h in [h for flat in opt.flat_grads if flat.data_ptr() != done for h in dist.all_reduce_grads_(flat)]:
             h.wait()
         opt.step()
 
@@ -76,6 +97,8 @@ class GanTrainer:
         with torch.no_grad():
             fake = self.gen(z)
         self.dis.zero_grad()
+        if update:
+            self._overlap_begin(self.d_opt, "d_step")
         d_true = self.dis(real).view(-1)
         d_fake = self.dis(fake).view(-1)
         d_aug = self.dis(aug).view(-1)
@@ -97,6 +120,8 @@ class GanTrainer:
         dev = z.device
         self.dis.requires_grad_(False)
         self.gen.zero_grad()
+        if update:
+            self._overlap_begin(self.g_opt, "g_step")
         d_fake = self.dis(self.gen(z)).view(-1)
         n = d_fake.numel()
         out = torch.empty(1, dtype=torch.float32, device=dev)

@@ -57,7 +57,7 @@ for kind, h, cin, cout, k, s, p in SHAPES:
     need = _lib.lib().lb_wgrad_tc_workspace_floats(ctypes.byref(g))
     work = torch.empty(need, device=DEV)
     dwn = torch.empty(t * cin * cout, device=DEV)
-    ms = timeit(lambda: call("lb_wgrad_tc", ptr(ga), ptr(de), ptr(dwn), ctypes.byref(g), ptr(work), need))
+    ms = timeit(lambda: call("lb_wgrad_tc", ptr(ga), ptr(de), ptr(dwn), ctypes.byref(g), ptr(work), need, None, None, None))
     flops = 2.0 * px * t * cin * cout
     byts = (x.numel() + dy.numel()) * 2 + dwn.numel() * 4
     print(f"{kind:5s} {k}x{k}s{s} {cin:4d}->{cout:4d} in{h:3d}  {ms*1e3:8.1f} us  {flops/ms/1e9:7.1f} TF/s  {byts/ms/1e6:7.1f} GB/s  "

@@ -48,6 +48,41 @@ def _worker(rank, world, port, ret):
     for h in dist.all_reduce_grads_(flat, bucket_elems=4):
         h.wait()
     ok = ok and torch.equal(flat, torch.arange(10, dtype=torch.float32) * 3)
+    # overlapped bucketing: buckets fire as soon as every parameter in them has its learned number of contributions
+    params = [torch.zeros(n) for n in (3, 5, 2, 6)]
+    offsets = [0, 4, 12, 16]                                     # arena slots aligned to 4 elements
+    arena = torch.zeros(24)
+    order = [3, 2, 3, 1, 0, 2, 1, 0]                             # "backward": two contributions per parameter, last layer first
+    tr = dist.GradOverlap(arena, params, offsets, bucket_elems=8)
+
+    def backward_pass(scale):
+        arena.zero_()
+        tr.begin("d_step")
+        fired_at = []
+        for i in order:
+            arena[offsets[i]:offsets[i] + params[i].numel()] += scale * (i + 1) * (rank + 1)
+            tr.written(params[i])
+            fired_at.append(tr.fired_early)
+        early = tr.fired_early
+        tr.finish()
+        return early, fired_at
+    e0, _ = backward_pass(1.0)                                   # learning pass: nothing fires early
+    want = torch.zeros(24)
+    for i in range(4):
+        want[offsets[i]:offsets[i] + params[i].numel()] = 2 * (i + 1) * 3
+    ok = ok and e0 == 0 and torch.equal(arena, want)
+    e1, fired_at = backward_pass(2.0)                            # learned: bucket 2 (param 3) fires after its 2nd contribution
+    ok = ok and e1 == 3 and fired_at[2] == 1 and torch.equal(arena, 2 * want)
+    tr.begin("d_step")                                           # a pass that changed shape must not produce a silent wrong sum
+    for i in (3, 3):
+        tr.written(params[i])
+    try:
+        tr.written(params[3])
+        ok = False
+    except RuntimeError:
+        pass
+    tr.tag = None
+    td.barrier()
     # non-parity mode: per-replica norm statistics
     dist.enable(sync_norm=False)
     t = torch.ones(2, dtype=torch.float64)

@@ -52,7 +52,7 @@ F32, BF16 = 0, 1
 
 
 @pytest.mark.parametrize("wide", [F32, BF16])
-@pytest.mark.parametrize("fuse", ["plain", "act_in", "dact_out"])
+@pytest.mark.parametrize("fuse", ["plain", "act_in", "dact_out", "factor_out"])
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_small_matches_simt(name, fuse, wide):
     kind, b, h, w, cin, cout, k, s, p, direction = CASES[name]
@@ -95,8 +95,13 @@ def test_small_matches_simt(name, fuse, wide):
         if wide == BF16 and out_wide:
             xpre = xpre.bfloat16()
         ref[..., :n] *= roottanh_grad(xpre.float())
+    if fuse == "factor_out":                 # xpre holds the derivative itself (stored by the forward pass): growth_out = -1
+        xpre = torch.randn(out_shape[:3] + (n,), generator=gen).to(DEV)
+        if wide == BF16 and out_wide:
+            xpre = xpre.bfloat16()
+        ref[..., :n] *= xpre.float()
     call("lb_conv_small", ptr(src_k), ptr(wt), ptr(alpha), ptr(bias), ptr(got), ctypes.byref(g), 4 if fuse == "act_in" else 0,
-         ptr(xpre), n, 4 if fuse == "dact_out" else 0, 0, wide)
+         ptr(xpre), n, {"dact_out": 4, "factor_out": -1}.get(fuse, 0), 0, wide)
     torch.cuda.synchronize()
     got = got.float()
     assert torch.equal(got[..., n:], ref[..., n:]), "wrote outside its channel slice"

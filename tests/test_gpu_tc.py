@@ -135,19 +135,26 @@ def test_tc_wgrad_matches_simt(name):
     assert need >= ref.numel() and need % ref.numel() == 0
     got = torch.full(shape, float("nan"), device=DEV)                 # overwritten, no zero-fill contract
     work = torch.full((need + 16,), float("nan"), device=DEV)
-    call("lb_wgrad_tc", ptr(gathered), ptr(dense), ptr(got), ctypes.byref(g), ptr(work), need)
+    wbar = torch.randn(shape, generator=gen).to(DEV)
+    dot = torch.zeros(2, dtype=torch.float64, device=DEV)
+    stat_work = torch.zeros(_lib.lib().lb_stat_work_doubles(), dtype=torch.float64, device=DEV)
+    call("lb_wgrad_tc", ptr(gathered), ptr(dense), ptr(got), ctypes.byref(g), ptr(work), need, ptr(wbar), ptr(dot), ptr(stat_work))
     torch.cuda.synchronize()
+    want_dot = (ref.double() * wbar.double()).sum().item()
+    assert abs(dot[0].item() - want_dot) <= 3e-4 * (ref.double() * wbar.double()).abs().sum().item() + 1e-6
     err = (got - ref).abs().max().item()
     scale = ref.abs().max().item()
     assert err <= 3e-4 * scale + 1e-5, f"{name}: max err {err:.3e} vs scale {scale:.3e}"
     assert torch.isnan(work[need:]).all()                             # stays inside the workspace it asked for
     # ordered split-K: bit-identical on a second run
     again = torch.empty(shape, device=DEV)
-    call("lb_wgrad_tc", ptr(gathered), ptr(dense), ptr(again), ctypes.byref(g), ptr(work), need)
+    dot2 = torch.zeros(2, dtype=torch.float64, device=DEV)
+    call("lb_wgrad_tc", ptr(gathered), ptr(dense), ptr(again), ctypes.byref(g), ptr(work), need, ptr(wbar), ptr(dot2), ptr(stat_work))
+    assert torch.equal(got, again) and dot[0].item() == dot2[0].item()
+    call("lb_wgrad_tc", ptr(gathered), ptr(dense), ptr(again), ctypes.byref(g), ptr(work), need, None, None, None)
     assert torch.equal(got, again)
     dwp = got.reshape(d0, d1, t).permute(2, 0, 1).contiguous()        # the tap-major form lb_sn_weight_grad also accepts
-    # the packed read path of the spectral-norm epilogue
-    wbar = torch.randn(shape, generator=gen).to(DEV)
+    # the packed read path of the spectral-norm epilogue, and the "dot already computed" path
     u = torch.randn(d0, generator=gen).to(DEV)
     v = torch.randn(d1 * t, generator=gen).to(DEV)
     sigma = torch.tensor([2.0, 0.5], device=DEV)
@@ -160,6 +167,11 @@ def test_tc_wgrad_matches_simt(name):
          None, None, None)
     torch.cuda.synchronize()
     assert (ga - gb).abs().max().item() <= 3e-4 * ga.abs().max().item() + 1e-5
+    gc = torch.zeros(shape, device=DEV)
+    call("lb_sn_weight_grad", ptr(got), None, ptr(u), ptr(v), ptr(sigma), ptr(gc), d0, d1 * t, 0, ptr(dot), ptr(stat_work),
+         None, None, None)
+    torch.cuda.synchronize()
+    assert (ga - gc).abs().max().item() <= 3e-4 * ga.abs().max().item() + 1e-5
 
 
 # ---- persistent kernel with the fused epilogue (lb_conv_tc_gemm_ex) against lb_conv_tc_gemm + torch elementwise ----
