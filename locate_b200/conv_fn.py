@@ -504,19 +504,8 @@ class ActivatedPairFn(torch.autograd.Function):
             dw1 = _sn_wgrad_tc(w1, u1, v1, sigma1, ptr(ga), ptr(de), gw1, spec1, fl1, by1, dev, ctx.uv_extra[1])
         if need_dx or need_dw0:
             d0 = torch.empty_like(a0)            # bf16( dL/dy0 ) = bf16( dgrad_1(g1) * RootTanh'(y0) ), the factor stored by the forward
-            gs = None
-            if cout <= 4 and gout.dtype == torch.float32 and CFG.SMALL_KERNELS:
-                # RGB-wide gradient (G's last layer): 3 fp32 values per pixel fan out to `mid` channels on the direct kernel
-                gs = ConvGeom.from_buffer_copy(bytes(gd1))
-                gs.ld_in = cout                         # fp32 rows of the RGB gradient, dense
-                if _lib.lib().lb_conv_small_supported(ctypes.byref(gs)) != 1:
-                    gs = None
-            if gs is not None:
-                _timed_call("conv_small", fl1, _tc_bytes(gd1), "lb_conv_small", ptr(gout), ptr(w1), sigma1.data_ptr() + 4, None, ptr(d0),
-                            gs, 0, ptr(dact0), mid, -1, 0, BF16)
-            else:
-                _timed_call("conv_tc", fl1, _tc_bytes(gd1), "lb_conv_tc_gemm_ex", ptr(g1), ptr(_packed_weight(w1, gd1, "dgrad")),
-                            sigma1.data_ptr() + 4, None, None, ptr(d0), None, mid, ptr(dact0), mid, BF16, EX_AUX_IS_FACTOR, gd1)
+            _timed_call("conv_tc", fl1, _tc_bytes(gd1), "lb_conv_tc_gemm_ex", ptr(g1), ptr(_packed_weight(w1, gd1, "dgrad")),
+                        sigma1.data_ptr() + 4, None, None, ptr(d0), None, mid, ptr(dact0), mid, BF16, EX_AUX_IS_FACTOR, gd1)
             if need_dw0:
                 ga, de = (d0, act16) if spec0.kind == "convT" else (act16, d0)
                 dw0 = _sn_wgrad_tc(w0, u0, v0, sigma0, ptr(ga), ptr(de), gw0, spec0, fl0, by0, dev, ctx.uv_extra[0])

@@ -145,6 +145,7 @@ __device__ __forceinline__ float roottanh_fast(float x) {
 __device__ __forceinline__ float tanh_approx(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 // RootTanh only (no derivative wanted): tanh.approx + two square roots = 3 MUFU ops; relative error ~5e-4, below the bf16
 // rounding of the stored result
+__device__ __forceinline__ uint32_t pin_u32(uint32_t v) { asm volatile("" : "+r"(v)); return v; }
 __device__ __forceinline__ float roottanh_only_fast(float x) {
   return sqrt_approx(sqrt_approx(fmaf(x, x, 1.0f))) * tanh_approx(x);
 }
@@ -217,6 +218,9 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t addr, uint32_t parity) {
     if (done) return;
   }
   __trap();
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx_a(uint32_t addr, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
@@ -367,10 +371,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
   tc::tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
   // shared-window addresses, computed once (the compiler otherwise re-derives them from generic pointers at every use)
-  const uint32_t smem_a = tc::smem_u32(smem), htab_a = smem_a + p.htab_base;
-  const uint32_t bar_full_a = tc::smem_u32(&bar_full[0]), bar_empty_a = tc::smem_u32(&bar_empty[0]);
-  const uint32_t bar_afull_a = tc::smem_u32(&bar_afull[0]), bar_aempty_a = tc::smem_u32(&bar_aempty[0]);
-  const uint32_t bar_tfull_a = tc::smem_u32(&bar_tfull[0]);
+  // (pinned: ptxas would rather rematerialise them -- S2UR SR_CgaCtaId + two ULEAs in front of every barrier operation of the
+  // single-thread producer / MMA loops, which are the critical path of the small-channel layers)
+  const uint32_t smem_a = pin_u32(tc::smem_u32(smem)), htab_a = smem_a + p.htab_base;
+  const uint32_t bar_full_a = pin_u32(tc::smem_u32(&bar_full[0])), bar_empty_a = pin_u32(tc::smem_u32(&bar_empty[0]));
+  const uint32_t bar_afull_a = pin_u32(tc::smem_u32(&bar_afull[0])), bar_aempty_a = pin_u32(tc::smem_u32(&bar_aempty[0]));
+  const uint32_t bar_tfull_a = pin_u32(tc::smem_u32(&bar_tfull[0])), bar_tempty_a = pin_u32(tc::smem_u32(&bar_tempty[0]));
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -469,7 +475,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
           ++epochs;
         }
         const int acc = lt & 1;
-        tc::mbar_wait(&bar_tempty[acc], (((uint32_t)lt >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
+        mbar_wait_a(bar_tempty_a + 8u * acc, (((uint32_t)lt >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
         tc::tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.acc_stride);
         if (p.halo) {
@@ -601,13 +607,20 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
       const TileCoord c = decode_tile(p, tile);
       const int acc = lt & 1;
       const int nsl = (min(p.block_n, p.out_c - c.n0) + kSlab - 1) / kSlab;
-      tc::mbar_wait(&bar_tfull[acc], ((uint32_t)lt >> 1) & 1u);
+      mbar_wait_a(bar_tfull_a + 8u * acc, ((uint32_t)lt >> 1) & 1u);
       tc::tc_fence_after();
+      bool released = false;
       for (int slab = half; slab < nsl; slab += ngrp) {
         if (p.has_aux) aux_issue();               // next job's aux while this one is processed
         float v[32];
         __syncwarp();
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride + slab * kSlab), v);
+        if (slab + ngrp >= nsl) {                 // this warp's last read of the accumulator: hand it back before the math
+          tc::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_a(bar_tempty_a + 8u * acc);
+          released = true;
+        }
         const int n = c.n0 + slab * kSlab;
         if (p.bias) {
 #pragma unroll
@@ -721,9 +734,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
         }
         stores_pending = true;
       }
-      tc::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&bar_tempty[acc]);
+      if (!released) {                            // a warp without a slab in this tile
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_a(bar_tempty_a + 8u * acc);
+      }
     }
     if (lane == 0) bulk_wait0();
   }
