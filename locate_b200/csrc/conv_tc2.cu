@@ -76,6 +76,7 @@ struct Tc2Params {
   int n_views;
   uint32_t htab_base;                 // view / tap tables of the halo mode (after the tap table)
   int resident;                       // 1: the weights of one output phase stay in shared memory (res_base), stages carry A only
+  int phase_inner;                    // tile order: output phase fastest after the channel tile (0 with resident weights)
   uint32_t res_base, b_tile_bytes;
   uint32_t epi_base, epi_per_warp, off_o32, off_o16, off_o16a, off_aux, aux_bytes;   // bytes; epi_base relative to the 1 KB aligned base
   const float* alpha; const float* bias;
@@ -86,10 +87,17 @@ __device__ __forceinline__ TileCoord decode_tile(const Tc2Params& p, int tile) {
   TileCoord c;
   int t = tile, nt, tw, th, tb;
   lb_fast_divmod(p.d_nt, t, t, nt);
-  lb_fast_divmod(p.d_tw, t, t, tw);
-  lb_fast_divmod(p.d_th, t, t, th);
-  lb_fast_divmod(p.d_tb, t, t, tb);
-  c.phase = t;
+  if (p.phase_inner) {               // the output phases of one source region run back to back: the region is read from DRAM once
+    c.phase = t & (p.sp * p.sp - 1);
+    t >>= (p.sp == 2 ? 2 : 0);           // sp is 1 or 2 (sh = log2(stride) also covers mode-0 stride-2 layers, whose sp is 1)
+    lb_fast_divmod(p.d_tw, t, t, tw);
+    lb_fast_divmod(p.d_th, t, tb, th);
+  } else {                           // resident weights: one phase's weight set at a time
+    lb_fast_divmod(p.d_tw, t, t, tw);
+    lb_fast_divmod(p.d_th, t, t, th);
+    lb_fast_divmod(p.d_tb, t, t, tb);
+    c.phase = t;
+  }
   c.x0 = tw * p.tile_w; c.y0 = th * p.tile_h; c.b0 = tb * p.tile_b; c.n0 = nt * p.block_n;
   c.py = c.phase >> p.sh; c.px = c.phase & (p.sp - 1);
   return c;
@@ -946,6 +954,8 @@ extern "C" int lb_conv_tc_gemm_ex(const void* in_bf16, const void* w_packed, con
   p.tmem_cols = (uint32_t)pow2_ceil(2 * p.acc_stride < 32 ? 32 : 2 * p.acc_stride);
   p.epi_base = (uint32_t)(stages * stage_bytes) + (uint32_t)p.a_stages * p.a_stage_bytes + (p.resident ? (uint32_t)(((g->mode == 1 ? ((g->kh + p.sp - 1) / p.sp) * ((g->kw + p.sp - 1) / p.sp) : g->kh * g->kw)) * p.kchunks) * p.b_tile_bytes : 0u);
   p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_b * p.n_tiles * p.sp * p.sp;
+  static const int env_phase_inner = getenv("LB_TC2_PHASE_INNER") ? atoi(getenv("LB_TC2_PHASE_INNER")) : 1;
+  p.phase_inner = (p.resident || !env_phase_inner) ? 0 : 1;
   p.d_nt = lb_make_fastdiv(p.n_tiles); p.d_tw = lb_make_fastdiv(p.tiles_w); p.d_th = lb_make_fastdiv(p.tiles_h); p.d_tb = lb_make_fastdiv(p.tiles_b);
 
   // source views: mode 0 with stride 2 -> 4 parity views; otherwise one dense view

@@ -7,7 +7,7 @@ n = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 print("value", round(r["value"], 1), r["unit"], "| ms/step", round(r["ms_per_step"], 2), "| e2e", round(r["e2e"]["value"], 1),
       "| launches", r.get("gpu_launches"), "| hbm GiB", r.get("hbm_peak_gib"), "| clocks", r.get("clocks"))
 pc = r.get("parity_check")
-if pc:
+if isinstance(pc, dict):
     print("parity", pc.get("ok"), "d_grad", pc.get("d_grad_rel_err"), "g_grad", pc.get("g_grad_rel_err"))
 rf = r["roofline"]
 print("roofline frac", round(rf["frac"], 4), rf["bound"], "achieved", round(rf["achieved"], 1), rf["unit"], "share", round(rf.get("share_of_step", 0), 3))
