@@ -78,6 +78,7 @@ struct Tc2Params {
   int resident;                       // 1: the weights of one output phase stay in shared memory (res_base), stages carry A only
   int phase_inner;                    // tile order: output phase fastest after the channel tile (0 with resident weights)
   uint32_t res_base, b_tile_bytes;
+  int slab;                           // columns per epilogue slab: 32, or 24 / 16 (bf16-only epilogues) when that spreads the tile over more warps
   uint32_t epi_base, epi_per_warp, off_o32, off_o16, off_o16a, off_aux, aux_bytes;   // bytes; epi_base relative to the 1 KB aligned base
   const float* alpha; const float* bias;
 };
@@ -192,6 +193,27 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+__device__ __forceinline__ void tmem_ld16_nw(uint32_t taddr, float* v) {      // no wait: the caller issues tmem_ld_wait()
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld8_nw(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   uint32_t r[32];
   asm volatile(
@@ -397,6 +419,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
         if (p.halo) {
           // per (view, channel chunk): one halo box, then the weight tile of every tap of that view
           const uint32_t hv_a = htab_a + (uint32_t)(c.phase * kMaxViews) * 16u, ht_a = htab_a + 4u * kMaxViews * 16u + (uint32_t)(c.phase * kMaxTapsPhase) * 8u;
+          if (p.resident && c.phase != res_phase) {
+            // single-phase layer whose whole weight set fits next to the halo ring: loaded once per CTA, in the order the
+            // MMA loop walks it (view, channel chunk, tap) -- no weight barrier or commit per tap afterwards
+            uint32_t cnt = 0;
+            for (int v = 0; v < p.n_views; ++v) cnt += (uint32_t)(lds_int4(hv_a + (uint32_t)v * 16u).z * p.kchunks);
+            tc::mbar_arrive_expect_tx(&bar_bfull, cnt * (uint32_t)b_bytes);
+            uint32_t dst = smem_a + p.res_base;
+            for (int v = 0; v < p.n_views; ++v) {
+              const int4 hv = lds_int4(hv_a + (uint32_t)v * 16u);
+              for (int kc = 0; kc < p.kchunks; ++kc)
+                for (int j = 0; j < hv.z; ++j, dst += p.b_tile_bytes)
+                  tma_load_2d_a(dst, &maps.b, tc::smem_u32(&bar_bfull), kc * kBlockK, lds_int2(ht_a + (uint32_t)(hv.w + j) * 8u).y + c.n0);
+            }
+            res_phase = c.phase;
+            ++epochs;
+          }
           for (int v = 0; v < p.n_views; ++v) {
             const int4 hv = lds_int4(hv_a + (uint32_t)v * 16u);
             if (hv.z == 0) continue;
@@ -407,6 +445,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
               mbar_expect_tx_a(bar_afull_a + 8u * ast, p.a_stage_bytes);
               tma_load_4d_a(smem_a + p.a_base + ast * p.a_stage_bytes, &maps.a[v], bar_afull_a + 8u * ast, kc * kBlockK, cx, cy, cb);
               if (++ast == p.a_stages) { ast = 0; aph ^= 1u; }
+              if (p.resident) continue;
               for (int j = 0; j < hv.z; ++j) {
                 const int2 ht = lds_int2(ht_a + (uint32_t)(hv.w + j) * 8u);
                 mbar_wait_a(bar_empty_a + 8u * st, ph ^ 1u);
@@ -490,6 +529,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
           uint32_t accum = 0;
           const uint32_t hv_a = htab_a + (uint32_t)(c.phase * kMaxViews) * 16u, ht_a = htab_a + 4u * kMaxViews * 16u + (uint32_t)(c.phase * kMaxTapsPhase) * 8u;
           const uint32_t a_hi = desc_hi(kHaloPitch * 128u), b_hi = desc_hi(1024u);
+          uint32_t b_res = desc_lo(smem_a + p.res_base);                       // resident weights: walked in load order
           for (int v = 0; v < p.n_views; ++v) {
             const int4 hv = lds_int4(hv_a + (uint32_t)v * 16u);
             if (hv.z == 0) continue;
@@ -500,10 +540,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
               const bool full_chunk = kc != p.kchunks - 1 || k16_last == kBlockK / 16;
               for (int j = 0; j < hv.z; ++j) {
                 const int2 ht = lds_int2(ht_a + (uint32_t)(hv.w + j) * 8u);
-                mbar_wait_a(bar_full_a + 8u * st, ph);
-                tc::tc_fence_after();
+                if (!p.resident) {
+                  mbar_wait_a(bar_full_a + 8u * st, ph);
+                  tc::tc_fence_after();
+                }
                 const uint32_t a_lo = a_lo0 + (uint32_t)ht.x * 8u;                  // + row * 128 B
-                const uint32_t b_lo = desc_lo(smem_a + st * stage_bytes);
+                const uint32_t b_lo = p.resident ? b_res : desc_lo(smem_a + st * stage_bytes);
+                b_res += p.b_tile_bytes >> 4;
                 if (full_chunk) {
                   umma_bf16_hl(tmem_d, a_hi, a_lo, b_hi, b_lo, idesc, accum);
                   umma_bf16_hl(tmem_d, a_hi, a_lo + 2u, b_hi, b_lo + 2u, idesc, 1u);
@@ -513,8 +556,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
                   for (int k = 0; k < k16_last; ++k) umma_bf16_hl(tmem_d, a_hi, a_lo + 2u * k, b_hi, b_lo + 2u * k, idesc, k ? 1u : accum);
                 }
                 accum = 1u;
-                umma_commit_a(bar_empty_a + 8u * st);
-                if (++st == p.stages) { st = 0; ph ^= 1u; }
+                if (!p.resident) {
+                  umma_commit_a(bar_empty_a + 8u * st);
+                  if (++st == p.stages) { st = 0; ph ^= 1u; }
+                }
               }
               umma_commit_a(bar_aempty_a + 8u * ast);
               if (++ast == p.a_stages) { ast = 0; aph ^= 1u; }
@@ -579,7 +624,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
     uint8_t* s_aux = ebase + p.off_aux;           // 2 x (4 KB fp32 | 2 KB bf16)
     const float alpha = p.alpha ? __ldg(p.alpha) : 1.0f;
     const int sw = lane & 7;                      // 128B swizzle: 16-byte chunk j of row r lives at chunk j ^ (r & 7)
-    const int sw64 = (lane >> 1) & 3;             // 64B swizzle: chunk j of row r lives at chunk j ^ ((r >> 1) & 3)
+    const int sw64 = p.slab == 32 ? (lane >> 1) & 3 : 0;   // 64B swizzle: chunk j of row r lives at chunk j ^ ((r >> 1) & 3); narrow slabs: dense rows
+    const int nch = p.slab >> 3;                  // 16-byte bf16 chunks (8 columns) per slab row: 4, 3 or 2
+    const int row16 = p.slab * 2;                 // bytes per bf16 staging row
 
     // aux prefetch runs one job ahead of the consumer
     int a_tile = blockIdx.x, a_slab = half;
@@ -589,7 +636,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
         int tq, nt;
         lb_fast_divmod(p.d_nt, a_tile, tq, nt);
         const int n0 = nt * p.block_n;
-        const int nsl = (min(p.block_n, p.out_c - n0) + kSlab - 1) / kSlab;
+        const int nsl = (min(p.block_n, p.out_c - n0) + p.slab - 1) / p.slab;
         if (a_slab < nsl) return;
         a_tile += gridDim.x; a_slab = half;
       }
@@ -601,7 +648,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
         const TileCoord c = decode_tile(p, a_tile);
         const uint32_t buf = a_issued & 1u;
         tc::mbar_arrive_expect_tx(&bar_aux[ew][buf], p.aux_bytes);
-        tc::tma_load_4d(s_aux + buf * p.aux_bytes, &maps.aux[c.phase], &bar_aux[ew][buf], c.n0 + a_slab * kSlab, c.x0 + w_off,
+        tc::tma_load_4d(s_aux + buf * p.aux_bytes, &maps.aux[c.phase], &bar_aux[ew][buf], c.n0 + a_slab * p.slab, c.x0 + w_off,
                         c.y0 + h_off, c.b0 + b_off);
       }
       ++a_issued;
@@ -614,7 +661,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
       const TileCoord c = decode_tile(p, tile);
       const int acc = lt & 1;
-      const int nsl = (min(p.block_n, p.out_c - c.n0) + kSlab - 1) / kSlab;
+      const int nsl = (min(p.block_n, p.out_c - c.n0) + p.slab - 1) / p.slab;
       mbar_wait_a(bar_tfull_a + 8u * acc, ((uint32_t)lt >> 1) & 1u);
       tc::tc_fence_after();
       bool released = false;
@@ -622,14 +669,25 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
         if (p.has_aux) aux_issue();               // next job's aux while this one is processed
         float v[32];
         __syncwarp();
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride + slab * kSlab), v);
+        {
+          const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride + slab * p.slab);
+          if (nch == 4) {
+            tmem_ld32(ta, v);
+          } else {                                // exact-width loads: the columns behind a narrow slab belong to other warps / nobody
+            tmem_ld16_nw(ta, v);
+            if (nch == 3) tmem_ld8_nw(ta + 16u, v + 16);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 16; i < 32; ++i) if (i >= 8 * nch) v[i] = 0.0f;
+          }
+        }
         if (slab + ngrp >= nsl) {                 // this warp's last read of the accumulator: hand it back before the math
           tc::tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_a(bar_tempty_a + 8u * acc);
           released = true;
         }
-        const int n = c.n0 + slab * kSlab;
+        const int n = c.n0 + slab * p.slab;
         if (p.bias) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], alpha, (n + i < p.out_c) ? __ldg(p.bias + n + i) : 0.0f);
@@ -641,9 +699,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
           const uint32_t buf = a_done & 1u;
           tc::mbar_wait(&bar_aux[ew][buf], (a_done >> 1) & 1u);
           if (p.aux_bf16) {
-            const uint8_t* row = s_aux + buf * 2048 + lane * 64;
+            const uint8_t* row = s_aux + buf * p.aux_bytes + lane * row16;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
+              if (j >= nch) break;
               const uint4 pk = *reinterpret_cast<const uint4*>(row + ((j ^ sw64) << 4));
               const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
 #pragma unroll
@@ -691,10 +750,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
             *reinterpret_cast<float4*>(row + ((j ^ sw) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
         if (p.has_o16 || p.has_o16a) {
-          uint8_t* row = s_o16 + lane * 64;
-          uint8_t* rowa = s_o16a + lane * 64;
+          uint8_t* row = s_o16 + lane * row16;
+          uint8_t* rowa = s_o16a + lane * row16;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
+            if (j >= nch) break;
             __nv_bfloat162 h[4], a[4];
             if (p.o16_dact) {                    // RootTanh -> out16a, RootTanh' -> out16, all intermediates shared
 #pragma unroll
@@ -873,30 +933,57 @@ extern "C" int lb_conv_tc_gemm_ex(const void* in_bf16, const void* w_packed, con
   p.aux_bf16 = aux_dtype == LB_BF16 ? 1 : 0;
   p.aux_factor = (flags & LB_EX_AUX_IS_FACTOR) ? 1 : 0;
   p.o16_dact = (flags & LB_EX_OUT16_IS_DACT) ? 1 : 0;
-  p.aux_bytes = p.aux_bf16 ? 32 * kSlab * 2 : 32 * kSlab * 4;
+  p.slab = kSlab;                      // narrowed below once the channel tile is known
 
-  // epilogue staging per warp: fp32 slab 4 KB, bf16 slabs 2 KB each, aux 2 x (4 | 2) KB (all 1 KB aligned for the swizzle)
-  uint32_t off = 0;
-  p.off_o32 = off; if (out32) off += 4096;
-  p.off_o16 = off; if (out16) off += 2048;
-  p.off_o16a = off; if (out16a) off += 2048;
-  p.off_aux = off; if (aux) off += 2 * p.aux_bytes;
-  p.epi_per_warp = (off + 1023) & ~1023u;
-  p.epi_warps = p.epi_per_warp * 16 <= 100 * 1024 ? 16 : 8;
+  // Slab width.  A warp reads only its own TMEM lane quarter, so a 128-row tile is spread over the 16 epilogue warps by
+  // COLUMN slabs: 4 warps per quarter.  With 32-column slabs a 96-channel tile keeps 12 warps busy and a 48-channel one 8;
+  // bf16-only epilogues may use 24 / 16-column slabs (dense 48 / 32-byte staging rows, exact-width tcgen05.ld), which puts
+  // 96 channels on 16 warps x 24 columns and 48 channels on 12 warps x 16 columns.  The epilogue (RootTanh + RootTanh' per
+  // element) is the critical path of exactly these small-channel layers.
+  {
+    static const int env_slab = getenv("LB_TC2_SLAB") ? atoi(getenv("LB_TC2_SLAB")) : 0;
+    const int bn1 = (g->out_c + 15) / 16 * 16;              // the single channel tile this applies to
+    if (!out32 && (!aux || p.aux_bf16) && g->out_c <= 256 && env_slab != 32) {
+      int best = kSlab, best_cols = kSlab * ((((bn1 + kSlab - 1) / kSlab) + 3) / 4);
+      const int cand[2] = {24, 16};
+      for (int i = 0; i < 2; ++i) {
+        const int cols = cand[i] * ((((bn1 + cand[i] - 1) / cand[i]) + 3) / 4);
+        if (cols < best_cols) { best = cand[i]; best_cols = cols; }
+      }
+      p.slab = best;
+      if (env_slab == 16 || env_slab == 24) p.slab = env_slab;
+    }
+  }
   const int tap_tab_bytes = 4 * kMaxTapsPhase * (int)(sizeof(int4) + sizeof(int2));  // 6 KB
   const int tab_bytes = tap_tab_bytes + 4096;                                         // + the halo-mode view / tap tables
-  const int epi_bytes = (int)p.epi_per_warp * p.epi_warps + tab_bytes;
   p.max_tp = g->mode == 1 ? ((g->kh + p.sp - 1) / p.sp) * ((g->kw + p.sp - 1) / p.sp) : g->kh * g->kw;
   if (p.max_tp > kMaxTapsPhase) return LB_EUNSUPPORTED;
+  int epi_bytes = 0, nt = 0, bn = 0, stage_bytes = 0, stages = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    p.aux_bytes = (uint32_t)(p.aux_bf16 ? 32 * p.slab * 2 : 32 * p.slab * 4);
+    // epilogue staging per warp: fp32 slab 4 KB, bf16 slabs 2 KB each (1 KB for 16 columns), aux 2 x (4 | 2) KB, all 1 KB aligned
+    const uint32_t o16_bytes = (uint32_t)((32 * p.slab * 2 + 1023) & ~1023);
+    const uint32_t aux_slot = (p.aux_bytes + 1023) & ~1023u;
+    uint32_t off = 0;
+    p.off_o32 = off; if (out32) off += 4096;
+    p.off_o16 = off; if (out16) off += o16_bytes;
+    p.off_o16a = off; if (out16a) off += o16_bytes;
+    p.off_aux = off; if (aux) off += 2 * aux_slot;
+    p.epi_per_warp = (off + 1023) & ~1023u;
+    p.epi_warps = p.epi_per_warp * 16 <= 100 * 1024 ? 16 : 8;
+    epi_bytes = (int)p.epi_per_warp * p.epi_warps + tab_bytes;
 
-  // channel tile: as wide as TMEM double buffering allows (<= 256) while leaving >= 3 ring stages
-  int nt = (g->out_c + 255) / 256, bn = 0, stage_bytes = 0, stages = 0;
-  for (;; ++nt) {
-    // several channel tiles: a multiple of the 32-column slab, so no tile's last store reaches into its neighbour
-    bn = nt > 1 ? ((g->out_c + nt - 1) / nt + 31) / 32 * 32 : (g->out_c + 15) / 16 * 16;
-    stage_bytes = kABytes + ((bn * kBlockK * 2 + 1023) & ~1023);
-    stages = (kSmemLimit - 1024 - epi_bytes) / stage_bytes;
-    if (stages >= 3 || bn <= 64) break;
+    // channel tile: as wide as TMEM double buffering allows (<= 256) while leaving >= 3 ring stages
+    nt = (g->out_c + 255) / 256;
+    for (;; ++nt) {
+      // several channel tiles: a multiple of the 32-column slab, so no tile's last store reaches into its neighbour
+      bn = nt > 1 ? ((g->out_c + nt - 1) / nt + 31) / 32 * 32 : (g->out_c + 15) / 16 * 16;
+      stage_bytes = kABytes + ((bn * kBlockK * 2 + 1023) & ~1023);
+      stages = (kSmemLimit - 1024 - epi_bytes) / stage_bytes;
+      if (stages >= 3 || bn <= 64) break;
+    }
+    if (nt == 1 || bn % p.slab == 0 || p.slab == kSlab) break;
+    p.slab = kSlab;                    // the tile had to be split and the narrow slab does not divide it: plan again with 32
   }
   if (stages < 2) return LB_EUNSUPPORTED;
   if (stages > 8) stages = 8;
@@ -930,7 +1017,26 @@ extern "C" int lb_conv_tc_gemm_ex(const void* in_bf16, const void* w_packed, con
     const int budget = kSmemLimit - 1024 - epi_bytes;
     int a_st = 3, b_st = (budget - a_st * (int)p.a_stage_bytes) / (int)p.b_tile_bytes;
     if (b_st < 4) { a_st = 2; b_st = (budget - a_st * (int)p.a_stage_bytes) / (int)p.b_tile_bytes; }
-    if (b_st < 3 || p.resident) {
+    bool halo_res = false;
+    {
+      // single-phase layers whose whole weight set fits next to >= 3 halo stages (3x3 48 -> 48: 54 KB): weights resident,
+      // the MMA thread's per-tap barrier wait + commit disappear (it is the critical path there: 9 taps x ~500 clocks of
+      // scalar issue work per 128-pixel tile against 650 clocks of tensor time)
+      static const int env_hres = getenv("LB_TC2_HALO_RESIDENT") ? atoi(getenv("LB_TC2_HALO_RESIDENT")) : 1;
+      const long long res_bytes = (long long)p.max_tp * p.kchunks * p.b_tile_bytes;
+      const long long a_fit = ((long long)budget - res_bytes) / (long long)p.a_stage_bytes;
+      if (env_hres && !p.resident && nt == 1 && p.sp == 1 && a_fit >= 3) {
+        halo_res = true;
+        p.resident = 1;
+        p.a_stages = a_fit > 4 ? 4 : (int)a_fit;
+        stages = 0; stage_bytes = 0;
+        p.a_base = 0;
+        p.res_base = (uint32_t)p.a_stages * p.a_stage_bytes;
+      }
+    }
+    if (halo_res) {
+      // layout: [halo ring][resident weights][epilogue staging]
+    } else if (b_st < 3 || p.resident) {
       p.halo = 0;                      // does not fit: back to per-tap boxes with the generic tile shape
       p.tile_w = pow2_ceil(dst_w) < kBlockM ? pow2_ceil(dst_w) : kBlockM;
       rest = kBlockM / p.tile_w;
@@ -950,7 +1056,7 @@ extern "C" int lb_conv_tc_gemm_ex(const void* in_bf16, const void* w_packed, con
     }
   }
   p.block_n = bn; p.n_tiles = (g->out_c + bn - 1) / bn; p.stages = stages;
-  p.acc_stride = (bn + 31) / 32 * 32;
+  p.acc_stride = ((bn + p.slab - 1) / p.slab * p.slab + 31) / 32 * 32;   // whole slabs, so that exact-width loads stay inside
   p.tmem_cols = (uint32_t)pow2_ceil(2 * p.acc_stride < 32 ? 32 : 2 * p.acc_stride);
   p.epi_base = (uint32_t)(stages * stage_bytes) + (uint32_t)p.a_stages * p.a_stage_bytes + (p.resident ? (uint32_t)(((g->mode == 1 ? ((g->kh + p.sp - 1) / p.sp) * ((g->kw + p.sp - 1) / p.sp) : g->kh * g->kw)) * p.kchunks) * p.b_tile_bytes : 0u);
   p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_b * p.n_tiles * p.sp * p.sp;
@@ -995,7 +1101,8 @@ extern "C" int lb_conv_tc_gemm_ex(const void* in_bf16, const void* w_packed, con
     if (vw < 1) vw = 1;
     if (vh < 1) vh = 1;
     const uint64_t dims[4] = {(uint64_t)g->out_c, (uint64_t)vw, (uint64_t)vh, (uint64_t)g->batch};
-    const uint32_t box[4] = {(uint32_t)kSlab, (uint32_t)p.ebw, (uint32_t)p.ebh, (uint32_t)p.ebb};
+    const uint32_t box[4] = {(uint32_t)p.slab, (uint32_t)p.ebw, (uint32_t)p.ebh, (uint32_t)p.ebb};
+    const CUtensorMapSwizzle sw16 = p.slab == kSlab ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE;   // narrow slabs: dense rows
     const size_t pix = empty ? 0 : (size_t)py * g->out_w + px;
     if (out32) {
       const uint64_t st[3] = {(uint64_t)p.sp * g->ld_out * 4, (uint64_t)p.sp * g->out_w * g->ld_out * 4,
@@ -1009,12 +1116,12 @@ extern "C" int lb_conv_tc_gemm_ex(const void* in_bf16, const void* w_packed, con
                               (uint64_t)g->out_h * g->out_w * ld_out16 * 2};
       if (out16) {
         int rc = tc::make_map(&maps.o16[v], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, reinterpret_cast<char*>(out16) + pix * ld_out16 * 2, 4,
-                              dims, st, box, CU_TENSOR_MAP_SWIZZLE_64B);
+                              dims, st, box, sw16);
         if (rc) return rc;
       }
       if (out16a) {
         int rc = tc::make_map(&maps.o16a[v], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, reinterpret_cast<char*>(out16a) + pix * ld_out16 * 2, 4,
-                              dims, st, box, CU_TENSOR_MAP_SWIZZLE_64B);
+                              dims, st, box, sw16);
         if (rc) return rc;
       }
     }
@@ -1024,7 +1131,7 @@ extern "C" int lb_conv_tc_gemm_ex(const void* in_bf16, const void* w_packed, con
                               (uint64_t)g->out_h * g->out_w * ld_aux * es};
       int rc = tc::make_map(&maps.aux[v], p.aux_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (int)es,
                             const_cast<char*>(reinterpret_cast<const char*>(aux)) + pix * ld_aux * es, 4, dims, st, box,
-                            p.aux_bf16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
+                            p.aux_bf16 ? sw16 : CU_TENSOR_MAP_SWIZZLE_128B);
       if (rc) return rc;
     }
   }
