@@ -396,6 +396,7 @@ def run_cuda(args):
             print(json.dumps({"error": "parity_check failed at the bench configuration", "parity_check": parity}), flush=True)
             return 3
         torch.cuda.empty_cache()
+        torch.cuda.reset_peak_memory_stats()                # `hbm_peak_gib` describes the measured bf16 step, not the gate's fp32 leg
 
     # warm-up: W eager steps; then (default) the step is captured into ONE CUDA graph
     graph_note = "eager launches"
@@ -575,7 +576,7 @@ def main():
     ap.add_argument("--batch", type=int, default=512, help="per-GPU batch (weak scaling: fixed per GPU)")
     ap.add_argument("--ref-batch", type=int, default=4, help="batch of the CPU reference sample")
     ap.add_argument("--eager-batch", type=int, default=64, help="batch of the PyTorch-eager-on-GPU baseline")
-    ap.add_argument("--attention-batch", type=int, default=128, help="batch of the isolated attention-block measurement")
+    ap.add_argument("--attention-batch", type=int, default=512, help="batch of the isolated attention-block measurement (capped by --batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-eager", action="store_true")
     ap.add_argument("--no-attention", action="store_true")
