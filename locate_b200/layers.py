@@ -40,8 +40,8 @@ class InPlaceNorm(nn.Module):
         self.weight = nn.Parameter(torch.ones((1, features, *[1] * dim)))
         self.bias = nn.Parameter(torch.zeros((1, features, *[1] * dim)))
 
-    def forward(self, function_input, scale=None, emit=None):
-        return ops.whole_norm(function_input, self.weight if scale is None else scale, self.bias, emit)
+    def forward(self, function_input, scale=None, emit=None, _mailbox=None):
+        return ops.whole_norm(function_input, self.weight if scale is None else scale, self.bias, emit, _mailbox)
 
 
 def _emit_mode(module):
@@ -69,8 +69,8 @@ class Norm(nn.Module):
         self.i_norm = InPlaceNorm(features, dim=dim)
         self.module = module
 
-    def forward(self, function_input, scale=None):
-        return self.module(self.i_norm(function_input, scale, emit=_emit_mode(self.module)))
+    def forward(self, function_input, scale=None, _mailbox=None):
+        return self.module(self.i_norm(function_input, scale, emit=_emit_mode(self.module), _mailbox=_mailbox))
 
 
 # ---- spectral norm (libs/spectral_norm.py:12-59) -----------------------------------------------
@@ -174,8 +174,8 @@ class CatModule(nn.Module):
         return ops.CatFn.apply(res, layer_out)
 
 
-def residual_function(x, attention, gamma):
-    return ops.gate(x, attention, gamma, CFG.STRICT_REFERENCE)
+def residual_function(x, attention, gamma, _mailbox=None):
+    return ops.gate(x, attention, gamma, CFG.STRICT_REFERENCE, _mailbox)
 
 
 class ResModule(nn.Module):
@@ -199,14 +199,20 @@ class ResModule(nn.Module):
         if scale is not None:
             args.append(scale)
         res = self.residual_module(function_input)
+        # the gate and the norm read the SAME tensor: their two gradients meet in the norm's backward kernel (ops.GradMailbox)
+        mb = None
+        if res is function_input and layer_input is None and isinstance(self.layer_module, Norm) and torch.is_grad_enabled():
+            mb = ops.GradMailbox()
         if self._broadcast_tail():
-            h = self.layer_module.i_norm(*args, emit=_emit_mode(self.layer_module.module))
+            h = self.layer_module.i_norm(*args, emit=_emit_mode(self.layer_module.module), _mailbox=mb)
             for layer in list(self.layer_module.module)[:-1]:
                 h = layer(h)
             layer_out = h                                  # [B,F,1,1] gate
+        elif mb is not None:
+            layer_out = self.layer_module(*args, _mailbox=mb)
         else:
             layer_out = self.layer_module(*args)
-        return residual_function(res, layer_out, self.gamma)
+        return residual_function(res, layer_out, self.gamma, mb)
 
 
 # ---- helpers (libs/util_modules.py:6-12, libs/utils.py:34-46) ----------------------------------

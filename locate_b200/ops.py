@@ -277,13 +277,26 @@ class HingeFn(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------
 # whole-tensor norm
 # ------------------------------------------------------------------------------------------
+class GradMailbox:
+    """A gated residual block out = (gamma * L(norm(x)) + 1) * x reads its input twice (merge.py:46-62 with block.py's
+    Norm-wrapped layer modules), so x receives two gradients: the gate's (gamma y + 1) g and the one that comes back through
+    the norm.  Autograd would add them with a kernel of its own; instead the gate's backward leaves its share here and the
+    norm's input-gradient kernel, which always runs later (its output feeds the gate's y), adds it while it writes dx
+    (`add` of lb_norm_bwd_apply).  Armed by the norm's forward only when its backward will produce dx."""
+    __slots__ = ("armed", "dx")
+
+    def __init__(self):
+        self.armed = False
+        self.dx = None
+
+
 class WholeNormFn(torch.autograd.Function):
     """libs/inplace_norm.py:7-45 (MeanSubMulDivAdd + x.std() folded into one op).
 
     gain: [1,C,1,1] parameter or [B,C,1,1] style tensor; bias: [1,C,1,1]."""
 
     @staticmethod
-    def forward(ctx, x, gain, bias, emit=None):
+    def forward(ctx, x, gain, bias, emit=None, mailbox=None):
         """emit == "act": the module that follows starts with RootTanh -> conv (conv.py:22-24) and nothing else reads the
         norm output.  In the tensor-core configuration the pass then writes RootTanh(y), that convolution's GEMM
         operand (`_lb_act16`), and -- when a backward pass will follow -- RootTanh'(y) (`_lb_dact16`), the factor its
@@ -317,6 +330,9 @@ class WholeNormFn(torch.autograd.Function):
         ctx.save_for_backward(x, gain_c, stats)
         ctx.per_sample = per_sample
         ctx.gain_param, ctx.bias_param = gain, bias
+        ctx.mailbox = mailbox if (mailbox is not None and ctx.needs_input_grad[0]) else None
+        if ctx.mailbox is not None:
+            mailbox.armed = True
         return y
 
     @staticmethod
@@ -350,9 +366,14 @@ class WholeNormFn(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
-            call("lb_norm_bwd_apply", ptr(x), ptr(g), ptr(stats), ptr(gain), c if ctx.per_sample else 0, ptr(sc), None, ptr(dx),
+            add = None
+            if ctx.mailbox is not None and ctx.mailbox.dx is not None:
+                add, ctx.mailbox.dx = ctx.mailbox.dx, None          # the gate's share of dL/dx (GradMailbox)
+                if add.shape != x.shape or add.stride() != x.stride() or add.dtype != x.dtype:
+                    raise RuntimeError("gradient mailbox: the gate and the norm of a residual block saw different inputs")
+            call("lb_norm_bwd_apply", ptr(x), ptr(g), ptr(stats), ptr(gain), c if ctx.per_sample else 0, ptr(sc), ptr(add), ptr(dx),
                  b, p, c, dt)
-        return dx, dgain_ret, dbias_ret, None
+        return dx, dgain_ret, dbias_ret, None, None
 
 
 # ------------------------------------------------------------------------------------------
@@ -362,7 +383,8 @@ class GateFn(torch.autograd.Function):
     """libs/merge.py:19-39.  y is full-shape, or a [B,C,1,1] gate broadcast over pixels."""
 
     @staticmethod
-    def forward(ctx, x, y, gamma, strict_reference):
+    def forward(ctx, x, y, gamma, strict_reference, mailbox=None):
+        ctx.mailbox = mailbox
         x = _as_act(x)
         dt = _dt(x)
         b, p, c = _bpc(x)
@@ -408,7 +430,9 @@ class GateFn(torch.autograd.Function):
             dist.grad_written(ctx.gamma_param)
         if ctx.bcast:
             dy = _cast(dyb, ctx.y_dtype).view(y.shape)
-        return dx, dy, dgamma_ret, None
+        if ctx.mailbox is not None and ctx.mailbox.armed and ctx.needs_input_grad[0]:
+            ctx.mailbox.dx, dx = dx, None            # added by the norm's input-gradient kernel (GradMailbox)
+        return dx, dy, dgamma_ret, None, None
 
 
 # ------------------------------------------------------------------------------------------
@@ -569,12 +593,12 @@ def roottanh(x, growth=4):
     return RootTanhFn.apply(x, growth)
 
 
-def whole_norm(x, gain, bias, emit=None):
-    return WholeNormFn.apply(x, gain, bias, emit)
+def whole_norm(x, gain, bias, emit=None, mailbox=None):
+    return WholeNormFn.apply(x, gain, bias, emit, mailbox)
 
 
-def gate(x, y, gamma, strict_reference=True):
-    return GateFn.apply(x, y, gamma, strict_reference)
+def gate(x, y, gamma, strict_reference=True, mailbox=None):
+    return GateFn.apply(x, y, gamma, strict_reference, mailbox)
 
 
 # the convolution family lives in conv_fn.py (imports helpers from this module, hence the late import)
