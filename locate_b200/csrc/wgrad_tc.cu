@@ -310,42 +310,74 @@ __global__ void __launch_bounds__(192, 1) k_wgrad_halo(const __grid_constant__ W
 // the same pass accumulates dot = sum dwn * w, reduced over the grid in fixed order: the spectral-norm correction
 // (lb_sn_weight_grad) then needs no pass of its own over dwn and w.
 constexpr int kRedTaps = 32;
+// fixed-order sum of one element over the splits, 8 loads in flight
+__device__ __forceinline__ float wg_split_sum(const float* __restrict__ src, int splits, size_t split_stride) {
+  if (splits == 1) return __ldcs(src);
+  float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  int sp = 0;
+  for (; sp + 8 <= splits; sp += 8) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] += __ldcs(src + (size_t)(sp + k) * split_stride);
+  }
+  for (int k = 0; sp < splits; ++sp, ++k) a[k] += __ldcs(src + (size_t)sp * split_stride);
+  return ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+}
+// kPerTap = false: unit of work = tile (one n, 32 m, every tap), turned through shared memory (large layers).
+// kPerTap = true : unit of work = (tile, tap): small layers with many splits, where the tile form would leave a handful of
+//                  warps walking hundreds of partials each; the 4-byte strided stores are a few KB in total.
+template <bool kPerTap>
 __global__ void __launch_bounds__(256) k_wgrad_reduce(const float* __restrict__ part, float* __restrict__ dwn, const float* __restrict__ w,
                                                       int splits, size_t split_stride, int taps, int d_c, int g_c, int m_chunks,
-                                                      int tiles, double* __restrict__ dot_out, double* __restrict__ stat_work) {
-  __shared__ float tile_s[8][32][kRedTaps + 1];
+                                                      int units, double* __restrict__ dot_out, double* __restrict__ stat_work) {
+  __shared__ float tile_s[kPerTap ? 1 : 8][kPerTap ? 1 : 32][kRedTaps + 1];
   __shared__ double scratch[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float (*tile)[kRedTaps + 1] = tile_s[warp];
+  const size_t tap_stride = (size_t)d_c * g_c;
   double dacc = 0.0;
-  for (int tl = blockIdx.x * 8 + warp; tl < tiles; tl += gridDim.x * 8) {
-    const int n = tl / m_chunks, m0 = (tl - n * m_chunks) * 32;
-    const int mm = min(32, g_c - m0);
+  for (int u = blockIdx.x * 8 + warp; u < units; u += gridDim.x * 8) {
     float fpart = 0.0f;
-    for (int t0 = 0; t0 < taps; t0 += kRedTaps) {
-      const int tc_ = min(kRedTaps, taps - t0);
-      if (lane < mm) {
-        const float* src = part + ((size_t)t0 * d_c + n) * g_c + m0 + lane;
-        const size_t tap_stride = (size_t)d_c * g_c;
-#pragma unroll 4
-        for (int t = 0; t < tc_; ++t) {
-          float acc = 0.0f;
-          for (int sp = 0; sp < splits; ++sp) acc += __ldcs(src + t * tap_stride + sp * split_stride);
-          tile[lane][t] = acc;
-        }
-      }
-      __syncwarp();
-      const size_t base = ((size_t)n * g_c + m0) * taps + t0;
-      for (int j = lane; j < mm * tc_; j += 32) {
-        const int m = j / tc_, t = j - m * tc_;
-        const float v = tile[m][t];
-        const size_t idx = base + (size_t)m * taps + t;
+    if (kPerTap) {
+      const int tl = u / taps, t = u - tl * taps;
+      const int n = tl / m_chunks, m0 = (tl - n * m_chunks) * 32;
+      if (m0 + lane < g_c) {
+        const float v = wg_split_sum(part + ((size_t)t * d_c + n) * g_c + m0 + lane, splits, split_stride);
+        const size_t idx = ((size_t)n * g_c + m0 + lane) * taps + t;
         dwn[idx] = v;
-        if (w) fpart = fmaf(v, __ldg(w + idx), fpart);
+        if (w) fpart = v * __ldg(w + idx);
       }
-      __syncwarp();
+    } else {
+      float (*tile)[kRedTaps + 1] = tile_s[warp];
+      const int n = u / m_chunks, m0 = (u - n * m_chunks) * 32;
+      const int mm = min(32, g_c - m0);
+      for (int t0 = 0; t0 < taps; t0 += kRedTaps) {
+        const int tc_ = min(kRedTaps, taps - t0);
+        if (lane < mm) {
+          const float* src = part + ((size_t)t0 * d_c + n) * g_c + m0 + lane;
+          // one pass per split with every tap's load in flight; splits are added in index order
+          float r[kRedTaps];
+#pragma unroll
+          for (int t = 0; t < kRedTaps; ++t) r[t] = t < tc_ ? __ldcs(src + t * tap_stride) : 0.0f;
+          for (int sp = 1; sp < splits; ++sp) {
+            const float* ss = src + (size_t)sp * split_stride;
+#pragma unroll
+            for (int t = 0; t < kRedTaps; ++t) if (t < tc_) r[t] += __ldcs(ss + t * tap_stride);
+          }
+#pragma unroll
+          for (int t = 0; t < kRedTaps; ++t) if (t < tc_) tile[lane][t] = r[t];
+        }
+        __syncwarp();
+        const size_t base = ((size_t)n * g_c + m0) * taps + t0;
+        for (int j = lane; j < mm * tc_; j += 32) {
+          const int m = j / tc_, t = j - m * tc_;
+          const float v = tile[m][t];
+          const size_t idx = base + (size_t)m * taps + t;
+          dwn[idx] = v;
+          if (w) fpart = fmaf(v, __ldg(w + idx), fpart);
+        }
+        __syncwarp();
+      }
     }
-    dacc += (double)fpart;                              // short fp32 runs (<= taps floats per lane), fp64 across tiles
+    dacc += (double)fpart;                              // short fp32 runs (<= taps floats per lane), fp64 across units
   }
   if (w) {
     dacc = lb_block_sum(dacc, scratch);
@@ -593,11 +625,17 @@ extern "C" int lb_wgrad_tc(const void* gathered_bf16, const void* dense_bf16, fl
   }
   const int m_chunks = (g->in_c + 31) / 32;
   const long long tiles = (long long)m_chunks * g->out_c;
-  LB_REQUIRE(tiles < (1ll << 31));
-  long long rblocks = (tiles + 7) / 8;
+  const bool per_tap = tiles < 4096 && pl.splits > 1;
+  const long long units = per_tap ? tiles * pl.taps : tiles;
+  LB_REQUIRE(units < (1ll << 31));
+  long long rblocks = (units + 7) / 8;
   if (rblocks > LB_SMS * 8) rblocks = LB_SMS * 8;       // <= the statistics workspace's grid bound
-  k_wgrad_reduce<<<(unsigned)rblocks, 256, 0, lb_s(s)>>>(work, dwn, w, pl.splits, numel, pl.taps, g->out_c, g->in_c, m_chunks, (int)tiles,
-                                                         dot_out, stat_work);
+  if (per_tap)
+    k_wgrad_reduce<true><<<(unsigned)rblocks, 256, 0, lb_s(s)>>>(work, dwn, w, pl.splits, numel, pl.taps, g->out_c, g->in_c, m_chunks,
+                                                                 (int)units, dot_out, stat_work);
+  else
+    k_wgrad_reduce<false><<<(unsigned)rblocks, 256, 0, lb_s(s)>>>(work, dwn, w, pl.splits, numel, pl.taps, g->out_c, g->in_c, m_chunks,
+                                                                  (int)units, dot_out, stat_work);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
