@@ -312,7 +312,21 @@ def attention_bench(res, batch, peaks, reps=5):
             e1.record()
             torch.cuda.synchronize()
             return e0.elapsed_time(e1) / reps
-        ms = timed(mine)
+        # the block as it runs inside the step: replayed from a CUDA graph (the step is one graph); eager launches of this
+        # library go through ctypes + autograd per kernel, which would dominate a 1 ms block
+        how = "cuda graph replay"
+        try:
+            for _ in range(2):
+                mine()
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                mine()
+            ms = timed(graph.replay)
+            del graph
+        except Exception as exc:                       # noqa: BLE001
+            how = f"eager launches (capture failed: {type(exc).__name__})"
+            ms = timed(mine)
         ms_eager = timed(eager)
         ms_autocast = timed(lambda: eager(True))
         pixels = batch * size * size
@@ -320,7 +334,7 @@ def attention_bench(res, batch, peaks, reps=5):
         tf = flops / (ms * 1e-3) / 1e12
         cap = min(1.0, feat / ridge)                   # fused pair: AI = F flop/B
         rows.append({"net": net, "features": feat, "hw": size * size, "batch": batch, "ms_fwd_bwd": ms,
-                     "tflops": tf, "frac_of_tc_peak": tf / peaks["tflops"], "roofline_cap": cap,
+                     "timed_as": how, "tflops": tf, "frac_of_tc_peak": tf / peaks["tflops"], "roofline_cap": cap,
                      "frac_of_cap": tf / peaks["tflops"] / cap,
                      "torch_eager_fp32_ms": ms_eager, "torch_eager_bf16_autocast_ms": ms_autocast,
                      "speedup_vs_eager_fp32": ms_eager / ms, "speedup_vs_eager_bf16": ms_autocast / ms})
