@@ -12,6 +12,7 @@ import torch
 import torch.distributed as td
 
 _STATE = {"group": None, "world": 1, "rank": 0, "sync_norm": True}
+GRAD_BUCKET_ELEMS = 8 * 1024 * 1024      # fp32 elements per gradient all-reduce bucket (32 MB)
 
 
 def init_from_env(backend=None):
@@ -84,7 +85,8 @@ class GradOverlap:
     received their learned number of contributions.  A contribution that arrives after its bucket was reduced raises --
     a silent wrong sum is never produced.  `finish()` reduces whatever did not fire and waits for everything."""
 
-    def __init__(self, flat, params, offsets, bucket_elems=8 * 1024 * 1024, reduce_fn=None):
+    def __init__(self, flat, params, offsets, bucket_elems=None, reduce_fn=None):
+        bucket_elems = bucket_elems or GRAD_BUCKET_ELEMS
         self.flat = flat
         self.bounds = bucket_bounds(flat.numel(), bucket_elems)
         self.buckets_of = {}
