@@ -310,63 +310,67 @@ __global__ void __launch_bounds__(192, 1) k_wgrad_halo(const __grid_constant__ W
 // the same pass accumulates dot = sum dwn * w, reduced over the grid in fixed order: the spectral-norm correction
 // (lb_sn_weight_grad) then needs no pass of its own over dwn and w.
 constexpr int kRedTaps = 32;
-// fixed-order sum of one element over the splits, 8 loads in flight
-__device__ __forceinline__ float wg_split_sum(const float* __restrict__ src, int splits, size_t split_stride) {
-  if (splits == 1) return __ldcs(src);
-  float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  int sp = 0;
-  for (; sp + 8 <= splits; sp += 8) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) a[k] += __ldcs(src + (size_t)(sp + k) * split_stride);
-  }
-  for (int k = 0; sp < splits; ++sp, ++k) a[k] += __ldcs(src + (size_t)sp * split_stride);
-  return ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
-}
-// kPerTap = false: unit of work = tile (one n, 32 m, every tap), turned through shared memory (large layers).
-// kPerTap = true : unit of work = (tile, tap): small layers with many splits, where the tile form would leave a handful of
-//                  warps walking hundreds of partials each; the 4-byte strided stores are a few KB in total.
-template <bool kPerTap>
-__global__ void __launch_bounds__(256) k_wgrad_reduce(const float* __restrict__ part, float* __restrict__ dwn, const float* __restrict__ w,
-                                                      int splits, size_t split_stride, int taps, int d_c, int g_c, int m_chunks,
-                                                      int units, double* __restrict__ dot_out, double* __restrict__ stat_work) {
-  __shared__ float tile_s[kPerTap ? 1 : 8][kPerTap ? 1 : 32][kRedTaps + 1];
+// Tile form (large layers): unit of work = one n, 32 m, every tap, per WARP, turned through shared memory.
+//   TC > 0: the taps are walked in chunks of exactly TC (taps % TC == 0), everything unrolled at compile time: the W loads
+//           and every tap's partial load of a chunk are in flight together (a W load inside the store loop serialised an
+//           earlier version on the memory latency; a run-time-unrolled one needed 255 registers and 1600 instructions per tile);
+//   TC == 0: run-time chunks of <= 32 taps, plain loops (odd tap counts).
+template <int TC>
+__global__ void __launch_bounds__(256, 2) k_wgrad_reduce_tile(const float* __restrict__ part, float* __restrict__ dwn, const float* __restrict__ w,
+                                                           int splits, size_t split_stride, int taps, int d_c, int g_c, int m_chunks,
+                                                           int units, double* __restrict__ dot_out, double* __restrict__ stat_work) {
+  constexpr int kChunk = TC ? TC : kRedTaps;
+  __shared__ float tile_s[8][32][kChunk + 1];
   __shared__ double scratch[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const size_t tap_stride = (size_t)d_c * g_c;
+  float (*tile)[kChunk + 1] = tile_s[warp];
   double dacc = 0.0;
   for (int u = blockIdx.x * 8 + warp; u < units; u += gridDim.x * 8) {
     float fpart = 0.0f;
-    if (kPerTap) {
-      const int tl = u / taps, t = u - tl * taps;
-      const int n = tl / m_chunks, m0 = (tl - n * m_chunks) * 32;
-      if (m0 + lane < g_c) {
-        const float v = wg_split_sum(part + ((size_t)t * d_c + n) * g_c + m0 + lane, splits, split_stride);
-        const size_t idx = ((size_t)n * g_c + m0 + lane) * taps + t;
-        dwn[idx] = v;
-        if (w) fpart = v * __ldg(w + idx);
-      }
-    } else {
-      float (*tile)[kRedTaps + 1] = tile_s[warp];
-      const int n = u / m_chunks, m0 = (u - n * m_chunks) * 32;
-      const int mm = min(32, g_c - m0);
-      for (int t0 = 0; t0 < taps; t0 += kRedTaps) {
-        const int tc_ = min(kRedTaps, taps - t0);
-        if (lane < mm) {
-          const float* src = part + ((size_t)t0 * d_c + n) * g_c + m0 + lane;
-          // one pass per split with every tap's load in flight; splits are added in index order
-          float r[kRedTaps];
+    const int n = u / m_chunks, m0 = (u - n * m_chunks) * 32;
+    const int mm = min(32, g_c - m0);
+    for (int t0 = 0; t0 < taps; t0 += kChunk) {
+      const size_t base = ((size_t)n * g_c + m0) * taps + t0;
+      const float* src = part + ((size_t)t0 * d_c + n) * g_c + m0 + lane;
+      if (TC) {
+        const int cnt = mm * TC;
+        float wv[kChunk], r[kChunk];
 #pragma unroll
-          for (int t = 0; t < kRedTaps; ++t) r[t] = t < tc_ ? __ldcs(src + t * tap_stride) : 0.0f;
-          for (int sp = 1; sp < splits; ++sp) {
-            const float* ss = src + (size_t)sp * split_stride;
+        for (int it = 0; it < kChunk; ++it) {
+          const int j = lane + 32 * it, m = j / kChunk, t = j - m * kChunk;
+          wv[it] = (w && j < cnt) ? __ldg(w + base + (size_t)m * taps + t) : 0.0f;
+        }
 #pragma unroll
-            for (int t = 0; t < kRedTaps; ++t) if (t < tc_) r[t] += __ldcs(ss + t * tap_stride);
+        for (int t = 0; t < kChunk; ++t) r[t] = lane < mm ? __ldcs(src + t * tap_stride) : 0.0f;
+        for (int sp = 1; sp < splits; ++sp) {            // splits in index order
+          const float* ss = src + (size_t)sp * split_stride;
+#pragma unroll
+          for (int t = 0; t < kChunk; ++t) if (lane < mm) r[t] += __ldcs(ss + t * tap_stride);
+        }
+#pragma unroll
+        for (int t = 0; t < kChunk; ++t) tile[lane][t] = r[t];
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < kChunk; ++it) {
+          const int j = lane + 32 * it, m = j / kChunk, t = j - m * kChunk;
+          if (j < cnt) {
+            const float v = tile[m][t];
+            dwn[base + (size_t)m * taps + t] = v;
+            fpart = fmaf(v, wv[it], fpart);
           }
-#pragma unroll
-          for (int t = 0; t < kRedTaps; ++t) if (t < tc_) tile[lane][t] = r[t];
         }
         __syncwarp();
-        const size_t base = ((size_t)n * g_c + m0) * taps + t0;
+      } else {
+        const int tc_ = min(kChunk, taps - t0);
+        if (lane < mm) {
+          for (int t = 0; t < tc_; ++t) {
+            float acc = 0.0f;
+            for (int sp = 0; sp < splits; ++sp) acc += __ldcs(src + t * tap_stride + (size_t)sp * split_stride);
+            tile[lane][t] = acc;
+          }
+        }
+        __syncwarp();
         for (int j = lane; j < mm * tc_; j += 32) {
           const int m = j / tc_, t = j - m * tc_;
           const float v = tile[m][t];
@@ -377,7 +381,48 @@ __global__ void __launch_bounds__(256) k_wgrad_reduce(const float* __restrict__ 
         __syncwarp();
       }
     }
-    dacc += (double)fpart;                              // short fp32 runs (<= taps floats per lane), fp64 across units
+    dacc += (double)fpart;                              // short fp32 runs (<= taps floats per lane), fp64 across tiles
+  }
+  if (w) {
+    dacc = lb_block_sum(dacc, scratch);
+    lb_grid_sum2_ordered(dacc, 0.0, stat_work, dot_out, scratch);
+  }
+}
+
+// Per-tap form (small layers with many splits): unit of work = (tile, tap) per CTA.  The 8 warps take every 8th split each
+// (8 loads in flight per lane) and their sums are combined in warp order -- a fixed association, so still
+// bit-reproducible; the 4-byte strided stores are a few KB in total.
+__global__ void __launch_bounds__(256) k_wgrad_reduce_tap(const float* __restrict__ part, float* __restrict__ dwn, const float* __restrict__ w,
+                                                          int splits, size_t split_stride, int taps, int d_c, int g_c, int m_chunks,
+                                                          int units, double* __restrict__ dot_out, double* __restrict__ stat_work) {
+  __shared__ float sums[8][32];
+  __shared__ double scratch[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double dacc = 0.0;
+  for (int u = blockIdx.x; u < units; u += gridDim.x) {
+    const int tl = u / taps, t = u - tl * taps;
+    const int n = tl / m_chunks, m0 = (tl - n * m_chunks) * 32;
+    const bool live = m0 + lane < g_c;
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (live) {
+      const float* src = part + ((size_t)t * d_c + n) * g_c + m0 + lane;
+      int sp = warp;
+      for (; sp + 56 < splits; sp += 64) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] += __ldcs(src + (size_t)(sp + 8 * k) * split_stride);
+      }
+      for (int k = 0; sp < splits; sp += 8, ++k) a[k] += __ldcs(src + (size_t)sp * split_stride);
+    }
+    sums[warp][lane] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+    __syncthreads();
+    if (warp == 0 && live) {
+      const float v = ((sums[0][lane] + sums[1][lane]) + (sums[2][lane] + sums[3][lane])) +
+                      ((sums[4][lane] + sums[5][lane]) + (sums[6][lane] + sums[7][lane]));
+      const size_t idx = ((size_t)n * g_c + m0 + lane) * taps + t;
+      dwn[idx] = v;
+      if (w) dacc += (double)(v * __ldg(w + idx));
+    }
+    __syncthreads();
   }
   if (w) {
     dacc = lb_block_sum(dacc, scratch);
@@ -625,17 +670,21 @@ extern "C" int lb_wgrad_tc(const void* gathered_bf16, const void* dense_bf16, fl
   }
   const int m_chunks = (g->in_c + 31) / 32;
   const long long tiles = (long long)m_chunks * g->out_c;
-  const bool per_tap = tiles < 4096 && pl.splits > 1;
+  const bool per_tap = tiles < 4096 && pl.splits >= 16;
   const long long units = per_tap ? tiles * pl.taps : tiles;
   LB_REQUIRE(units < (1ll << 31));
-  long long rblocks = (units + 7) / 8;
+  long long rblocks = per_tap ? units : (units + 7) / 8;
   if (rblocks > LB_SMS * 8) rblocks = LB_SMS * 8;       // <= the statistics workspace's grid bound
-  if (per_tap)
-    k_wgrad_reduce<true><<<(unsigned)rblocks, 256, 0, lb_s(s)>>>(work, dwn, w, pl.splits, numel, pl.taps, g->out_c, g->in_c, m_chunks,
-                                                                 (int)units, dot_out, stat_work);
-  else
-    k_wgrad_reduce<false><<<(unsigned)rblocks, 256, 0, lb_s(s)>>>(work, dwn, w, pl.splits, numel, pl.taps, g->out_c, g->in_c, m_chunks,
-                                                                  (int)units, dot_out, stat_work);
+#define LB_WG_REDUCE(KERNEL)                                                                                                   \
+  KERNEL<<<(unsigned)rblocks, 256, 0, lb_s(s)>>>(work, dwn, w, pl.splits, numel, pl.taps, g->out_c, g->in_c, m_chunks, (int)units, \
+                                                 dot_out, stat_work)
+  if (per_tap) LB_WG_REDUCE(k_wgrad_reduce_tap);
+  else if (pl.taps == 1) LB_WG_REDUCE(k_wgrad_reduce_tile<1>);
+  else if (pl.taps == 9) LB_WG_REDUCE(k_wgrad_reduce_tile<9>);
+  else if (pl.taps == 25) LB_WG_REDUCE(k_wgrad_reduce_tile<25>);
+  else if (pl.taps % 16 == 0) LB_WG_REDUCE(k_wgrad_reduce_tile<16>);
+  else LB_WG_REDUCE(k_wgrad_reduce_tile<0>);
+#undef LB_WG_REDUCE
   LB_LAUNCH_CHECK();
   return LB_OK;
 }

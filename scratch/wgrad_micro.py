@@ -29,17 +29,26 @@ def geom(b, ih, iw, ic, oh, ow, oc, kh, kw, s, p, mode, ld_in, ld_out, strides):
 
 
 def timeit(fn, n=10):
+    """GPU time of one call, replayed from a CUDA graph (host launch gaps excluded), L2 flushed before every replay."""
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
     fn(); torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        fn()
     tot = 0.0
     for _ in range(n):
         flush.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); fn(); b.record(); torch.cuda.synchronize()
+        a.record(); graph.replay(); b.record(); torch.cuda.synchronize()
         tot += a.elapsed_time(b)
     return tot / n
 
 
+if len(sys.argv) > 2 and sys.argv[2] == "weights":      # tiny batch: the time is the partial stores + k_wgrad_reduce (+ dot)
+    SHAPES = [("convT", 4, 1536, 1536, 4, 2, 1), ("conv", 4, 1024, 1024, 5, 2, 2), ("conv", 2, 1024, 1024, 3, 1, 1),
+              ("convT", 8, 768, 768, 4, 2, 1), ("conv", 8, 512, 512, 5, 2, 2), ("conv", 8, 768, 1536, 1, 1, 0)]
+stat_work = torch.zeros(_lib.lib().lb_stat_work_doubles(), dtype=torch.float64, device=DEV)
+dot = torch.zeros(2, dtype=torch.float64, device=DEV)
 for kind, h, cin, cout, k, s, p in SHAPES:
     t = k * k
     if kind == "conv":
@@ -57,7 +66,8 @@ for kind, h, cin, cout, k, s, p in SHAPES:
     need = _lib.lib().lb_wgrad_tc_workspace_floats(ctypes.byref(g))
     work = torch.empty(need, device=DEV)
     dwn = torch.empty(t * cin * cout, device=DEV)
-    ms = timeit(lambda: call("lb_wgrad_tc", ptr(ga), ptr(de), ptr(dwn), ctypes.byref(g), ptr(work), need, None, None, None))
+    wbar = torch.randn(t * cin * cout, device=DEV)
+    ms = timeit(lambda: call("lb_wgrad_tc", ptr(ga), ptr(de), ptr(dwn), ctypes.byref(g), ptr(work), need, ptr(wbar), ptr(dot), ptr(stat_work)))
     flops = 2.0 * px * t * cin * cout
     byts = (x.numel() + dy.numel()) * 2 + dwn.numel() * 4
     print(f"{kind:5s} {k}x{k}s{s} {cin:4d}->{cout:4d} in{h:3d}  {ms*1e3:8.1f} us  {flops/ms/1e9:7.1f} TF/s  {byts/ms/1e6:7.1f} GB/s  "
