@@ -496,17 +496,23 @@ bool wg_plan(const lb_conv_geom* g, WgPlan& pl) {
       if (w.box_tx > box_max) box_max = w.box_tx;
       if (pl.view_taps[v] > max_view_taps) max_view_taps = pl.view_taps[v];
     }
-    // accumulator columns: block_n per tap; prefer one group per view, never below 64 channels per tile for wide layers
+    // channel tile: the padded MMA work per pixel tile is proportional to n_tiles x block_n whatever the taps per group,
+    // and a 128 x 128 tile reads shared memory at the full 128 B/clk (A and B are both re-read per MMA), so wide tiles win:
+    // the widest of {256, 192, 128} that minimises the padding; taps per group = what still fits TMEM (512 columns).
     int bn = (g->out_c + 15) / 16 * 16;
-    if (bn > 256) bn = 256;
+    if (bn > 256) {
+      const int cand[3] = {256, 192, 128};
+      int best = 0;
+      long long best_cost = 0;
+      for (int i = 0; i < 3; ++i) {
+        const long long cost = (long long)((g->out_c + cand[i] - 1) / cand[i]) * cand[i];
+        if (!best || cost < best_cost) { best = cand[i]; best_cost = cost; }
+      }
+      bn = best;
+    }
     int gt = 512 / bn;
     if (gt > max_view_taps) gt = max_view_taps;
     if (gt > kMaxGroupTaps) gt = kMaxGroupTaps;
-    if (gt < max_view_taps && bn > 128) {                     // narrower tiles keep a whole view (<= 4 taps at 128) together
-      bn = 128;
-      gt = 512 / bn;
-      if (gt > max_view_taps) gt = max_view_taps;
-    }
     int ngroups = 0;
     for (int v = 0; v < vs * vs; ++v) ngroups += (pl.view_taps[v] + gt - 1) / gt;
     pl.block_n = bn; pl.n_boxes = (bn + kBox - 1) / kBox;
