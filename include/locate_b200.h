@@ -191,6 +191,16 @@ int lb_conv_small(const void* in, const float* w, const float* alpha, const floa
 int lb_conv_small_wgrad_supported(const lb_conv_geom* g);
 int lb_conv_small_wgrad(const void* gathered, const void* dense, float* dw, const lb_conv_geom* g, int growth_gathered,
                         int wide_dtype, lb_stream_t stream);
+/* ---- GPU-side input pipeline (SURVEY "next" row N4)                                  libs/utils.py:92-113, main.py:122-129
+ * RandomHorizontalFlip + ColorJitter(brightness, contrast, saturation) + RandomResizedCrop (antialiased bilinear) +
+ * ToTensor + Normalize(0.5, 0.5) for a batch of decoded uint8 images [B][Hs][Ws][3] resident in HBM (already resized
+ * to 2 x image size, as transforms.Resize does).  The random draws are the host's (torchvision's get_params), per sample
+ * 12 floats: crop top, left, height, width, flip, brightness / contrast / saturation factors, three operation codes in
+ * application order (0 brightness, 1 contrast, 2 saturation, -1 none), one spare.  torchvision's float-tensor arithmetic.
+ * mean_work: batch floats.  dst: fp32 channels-last [B][size][size][3] in [-1, 1]. */
+int lb_augment(const void* src_u8, const float* params, float* mean_work, float* dst, int batch, int src_h, int src_w,
+               int size, lb_stream_t stream);
+
 /* ---- SEPARABLE = True (config.py:53): the grouped convolutions of that configuration                libs/conv.py:17, libs/attention.py:15-21
  * Depthwise k x k conv / transposed conv (groups = channels): out[b,oy,ox,c] = alpha * sum_taps in[b,iy,ix,c] * w[c][ty][tx]
  * with the mode conventions above (forward of one = input gradient of the other, same weights); w is the fp32 master

@@ -18,3 +18,4 @@ __all__ = [
     "NonLinear", "BlockBlock", "penalty", "Discriminator", "Generator", "SpectralNorm", "get_model", "hinge",
     "parameter_count", "Nadam", "GanTrainer", "CFG", "configure",
 ]
+from .augment import GpuAugment  # noqa: E402,F401  (SURVEY "next" row N4: GPU-side input pipeline)

@@ -52,6 +52,7 @@ _SIGNATURES = {
     "lb_sn_weight_grad": ([P, P, P, P, P, P, c_int, c_int, c_int, P, P, P, P, P, P], c_int),
     "lb_sn_uv_grad_batched": ([P, c_int, P, c_int, P, P, P], c_int),
     "lb_wgrad_tc_supported": ([POINTER(ConvGeom)], c_int),
+    "lb_augment": ([P, P, P, P, c_int, c_int, c_int, c_int, P], c_int),
     "lb_wgrad_tc_workspace_floats": ([POINTER(ConvGeom)], c_size_t),
     "lb_wgrad_tc": ([P, P, P, POINTER(ConvGeom), P, c_size_t, P, P, P, P], c_int),
     "lb_conv_gemm": ([P, P, P, P, P, POINTER(ConvGeom), P], c_int),
