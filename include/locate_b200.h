@@ -43,6 +43,12 @@ int lb_version(void);
 int lb_sm_arch(void);
 int lb_last_launch_count(void);   /* kernels launched by this library since lb_reset_launch_count */
 void lb_reset_launch_count(void);
+/* Programmatic dependent launch of every kernel of the library (default on; environment LB_PDL=0 switches it off):
+ * kernels are launched with the programmatic-stream-serialization attribute and wait for their predecessor on the
+ * device (griddepcontrol.wait), so launch latency and kernel prologues overlap the predecessor's tail -- in a stream
+ * and, as programmatic edges, in a captured CUDA graph.  Returns the previous setting.  (No reference counterpart:
+ * the reference leaves launch scheduling to PyTorch eager mode, main.py:146-172.) */
+int lb_set_pdl(int on);
 
 /* ---- RootTanh activation: y = (x^2+1)^(1/growth) * tanh(x)          libs/activation.py:9-16
  *      bwd: dx = g * (2(x^2+1) sech^2 x + x tanh x) / (2 (x^2+1)^((growth-1)/growth))  :20-36 */

@@ -27,6 +27,7 @@ _SIGNATURES = {
     "lb_sm_arch": ([], c_int),
     "lb_last_launch_count": ([], c_int),
     "lb_reset_launch_count": ([], None),
+    "lb_set_pdl": ([c_int], c_int),
     "lb_roottanh_fwd": ([P, P, c_size_t, c_int, c_int, P], c_int),
     "lb_roottanh_bwd": ([P, P, P, c_size_t, c_int, c_int, P], c_int),
     "lb_tanh_fwd": ([P, P, c_size_t, c_int, P], c_int),
@@ -162,3 +163,10 @@ def launch_count():
 
 def reset_launch_count():
     lib().lb_reset_launch_count()
+
+
+def set_pdl(on):
+    """Programmatic dependent launch of the library's kernels on / off (include/locate_b200.h lb_set_pdl); returns
+    the previous setting.  Takes effect for launches made afterwards (a captured graph keeps the edges it was
+    captured with)."""
+    return bool(lib().lb_set_pdl(1 if on else 0))

@@ -40,6 +40,7 @@ __device__ __forceinline__ void aug_jitter(float& r, float& g, float& b, const f
 // one CTA per image, fixed-order block reduction (deterministic)
 __global__ void __launch_bounds__(512) k_aug_gray_mean(const uint8_t* __restrict__ src, const float* __restrict__ params, float* __restrict__ mean,
                                                       int hs, int ws) {
+  lb_pdl_enter();
   __shared__ double scratch[32];
   const int b = blockIdx.x;
   const float* prm = params + (size_t)b * kAugParams;
@@ -87,6 +88,7 @@ __device__ __forceinline__ void aug_axis(float crop0, float crop_len, int out_i,
 // one thread per output pixel: dst is channels-last fp32 [B][S][S][3]
 __global__ void __launch_bounds__(256) k_aug_apply(const uint8_t* __restrict__ src, const float* __restrict__ params, const float* __restrict__ mean,
                                                   float* __restrict__ dst, int batch, int hs, int ws, int size) {
+  lb_pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= batch * size * size) return;
   const int x = i % size, y = (i / size) % size, b = i / (size * size);
@@ -124,10 +126,10 @@ extern "C" int lb_augment(const void* src_u8, const float* params, float* mean_w
                           int size, lb_stream_t s) {
   LB_REQUIRE(src_u8 && params && mean_work && dst && batch > 0 && src_h > 0 && src_w > 0 && size > 0);
   LB_REQUIRE((long long)batch * size * size < (1ll << 31) && (long long)src_h * src_w < (1ll << 30));
-  k_aug_gray_mean<<<batch, 512, 0, lb_s(s)>>>(reinterpret_cast<const uint8_t*>(src_u8), params, mean_work, src_h, src_w);
+  lb_launch(k_aug_gray_mean, batch, 512, 0, lb_s(s), reinterpret_cast<const uint8_t*>(src_u8), params, mean_work, src_h, src_w);
   LB_LAUNCH_CHECK();
   const int n = batch * size * size;
-  k_aug_apply<<<(n + 255) / 256, 256, 0, lb_s(s)>>>(reinterpret_cast<const uint8_t*>(src_u8), params, mean_work, dst, batch, src_h, src_w,
+  lb_launch(k_aug_apply, (n + 255) / 256, 256, 0, lb_s(s), reinterpret_cast<const uint8_t*>(src_u8), params, mean_work, dst, batch, src_h, src_w,
                                                     size);
   LB_LAUNCH_CHECK();
   return LB_OK;

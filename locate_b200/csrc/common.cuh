@@ -3,6 +3,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <math.h>
 #include "locate_b200.h"
 
@@ -20,6 +21,44 @@ extern int g_lb_launches;              // kernels launched by the library (bench
 #define LB_REQUIRE(cond) do { if (!(cond)) return LB_EINVAL; } while (0)
 
 static inline cudaStream_t lb_s(lb_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ---- programmatic dependent launch ---------------------------------------------------------------------------------
+// A training step is ~1800 dependent launches; at the reference's own batch sizes (16, 64) most of them run for a few
+// microseconds, so the launch gap between two kernels is a visible share of the step.  Every kernel of the library is
+// launched with cudaLaunchAttributeProgrammaticStreamSerialization (a programmatic edge when the step is captured into
+// a CUDA graph) and waits for its predecessor ON THE DEVICE (griddepcontrol.wait) before it touches global memory: the
+// grid is scheduled, and the tensor-core kernels' barrier init / TMEM allocation / table building is done, while the
+// predecessor's last CTAs are still draining.  Nothing that reads or writes global memory may precede lb_pdl_wait().
+// Measured on B200 (profiles/r2_pdl_ab.txt, same lease, CUDA-graph replay): batch 16: +5.7 %, batch 64: +3.9 %, batch 512:
+// +0.3 % (noise).  An EARLY griddepcontrol.launch_dependents at the top of every kernel (successor CTAs resident and
+// parked while the whole predecessor runs) was measured too: -2.3 % at batch 512, +0.7 % at 64 -- compiled out
+// (LB_PDL_EARLY_TRIGGER=0): the predecessor's exit is the trigger.  LB_PDL=0 / lb_set_pdl(0): fully serialised launches.
+#ifndef LB_PDL_EARLY_TRIGGER
+#define LB_PDL_EARLY_TRIGGER 0
+#endif
+__device__ __forceinline__ void lb_pdl_trigger() {
+#if LB_PDL_EARLY_TRIGGER
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void lb_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void lb_pdl_enter() { lb_pdl_trigger(); lb_pdl_wait(); }
+extern int g_lb_pdl;                   // -1 = not read yet
+static inline bool lb_pdl_on() {
+  if (g_lb_pdl < 0) { const char* e = getenv("LB_PDL"); g_lb_pdl = (e && atoi(e) == 0) ? 0 : 1; }
+  return g_lb_pdl != 0;
+}
+template <typename... P, typename... A>
+static inline void lb_launch(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = lb_pdl_on() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);   // errors surface through cudaGetLastError (LB_LAUNCH_CHECK)
+}
 
 // grid for a grid-stride elementwise kernel: enough CTAs to cover n, capped at `waves` full waves
 static inline int lb_grid_1d(size_t work_items, int block, int waves = 8) {

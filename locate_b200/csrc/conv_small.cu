@@ -57,6 +57,7 @@ __device__ __forceinline__ bool small_src(int mode, int stride, int sh, int pad,
 // columns that copy the input), bsm the bias per column.
 template <int NCH, typename TO>
 __global__ void __launch_bounds__(SMALL_THREADS) k_small_narrow_in(const SmallP p) {
+  lb_pdl_enter();
   const float* p_in = reinterpret_cast<const float*>(p.in);
   TO* p_out = reinterpret_cast<TO*>(p.out);
   const TO* p_xpre = reinterpret_cast<const TO*>(p.xpre);
@@ -143,6 +144,7 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_small_narrow_in(const SmallP 
 // wsm[tap][k] = alpha * W(tap, k, 0..3) as one float4
 template <typename TI>
 __global__ void __launch_bounds__(SMALL_THREADS) k_small_narrow_out(const SmallP p) {
+  lb_pdl_enter();
   extern __shared__ float4 sm4[];
   const TI* p_in = reinterpret_cast<const TI*>(p.in);
   float* p_out = reinterpret_cast<float*>(p.out);
@@ -262,16 +264,16 @@ extern "C" int lb_conv_small(const void* in, const float* w, const float* alpha,
     const size_t smem = ((size_t)taps * g->in_c * 16 * nch + 16 * nch) * sizeof(float);
     LB_DISPATCH(wide_dtype, T, {
       switch (nch) {
-        case 1: k_small_narrow_in<1, T><<<grid, SMALL_THREADS, smem, lb_s(s)>>>(p); break;
-        case 2: k_small_narrow_in<2, T><<<grid, SMALL_THREADS, smem, lb_s(s)>>>(p); break;
-        case 3: k_small_narrow_in<3, T><<<grid, SMALL_THREADS, smem, lb_s(s)>>>(p); break;
-        default: k_small_narrow_in<4, T><<<grid, SMALL_THREADS, smem, lb_s(s)>>>(p); break;
+        case 1: lb_launch(k_small_narrow_in<1, T>, grid, SMALL_THREADS, smem, lb_s(s), p); break;
+        case 2: lb_launch(k_small_narrow_in<2, T>, grid, SMALL_THREADS, smem, lb_s(s), p); break;
+        case 3: lb_launch(k_small_narrow_in<3, T>, grid, SMALL_THREADS, smem, lb_s(s), p); break;
+        default: lb_launch(k_small_narrow_in<4, T>, grid, SMALL_THREADS, smem, lb_s(s), p); break;
       }
     });
   } else {
     if (p.cat) return LB_EUNSUPPORTED;
     const size_t smem = (size_t)taps * g->in_c * sizeof(float4);
-    LB_DISPATCH(wide_dtype, T, k_small_narrow_out<T><<<grid, SMALL_THREADS, smem, lb_s(s)>>>(p));
+    LB_DISPATCH(wide_dtype, T, lb_launch(k_small_narrow_out<T>, grid, SMALL_THREADS, smem, lb_s(s), p));
   }
   LB_LAUNCH_CHECK();
   return LB_OK;
@@ -293,6 +295,7 @@ struct SmallWgP {
 };
 template <bool kNarrowDense, typename TW>
 __global__ void __launch_bounds__(SMALL_THREADS) k_small_wgrad(const SmallWgP p) {
+  lb_pdl_enter();
   __shared__ float s_red[64];
   if (threadIdx.x < 64) s_red[threadIdx.x] = 0.0f;
   __syncthreads();
@@ -437,8 +440,8 @@ extern "C" int lb_conv_small_wgrad(const void* gathered, const void* dense, floa
   if (chunks > 65535) return LB_EUNSUPPORTED;
   dim3 grid(gx, chunks);
   LB_DISPATCH(wide_dtype, T, {
-    if (narrow_gathered) k_small_wgrad<false, T><<<grid, SMALL_THREADS, 0, lb_s(s)>>>(p);
-    else k_small_wgrad<true, T><<<grid, SMALL_THREADS, 0, lb_s(s)>>>(p);
+    if (narrow_gathered) lb_launch(k_small_wgrad<false, T>, grid, SMALL_THREADS, 0, lb_s(s), p);
+    else lb_launch(k_small_wgrad<true, T>, grid, SMALL_THREADS, 0, lb_s(s), p);
   });
   LB_LAUNCH_CHECK();
   return LB_OK;

@@ -102,6 +102,11 @@ __global__ void __launch_bounds__(192, 4) k_conv_tc(const __grid_constant__ TcMa
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  // programmatic dependent launch: the successor may be scheduled only now that this CTA owns its TMEM columns (a
+  // successor CTA allocating first, then waiting for this grid, would deadlock the SM's allocator); everything above ran
+  // while the predecessor was still draining, nothing below may start before it has completed
+  lb_pdl_trigger();
+  lb_pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -280,6 +285,7 @@ template <bool kVec4>
 __global__ void __launch_bounds__(256) k_pack_weight(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int taps_h, int taps_w,
                                                     int n_rows, int k, int kpad, long long w_sk, long long w_sn, long long w_sty,
                                                     long long w_stx, int items, LbFastDiv d_kpad) {
+  lb_pdl_enter();
   const int stride = gridDim.x * blockDim.x;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < items; i += stride) {
     int n, kk;
@@ -312,11 +318,11 @@ extern "C" int lb_conv_tc_pack(const float* w, void* packed, const lb_conv_geom*
   const bool vec = taps % 4 == 0 && g->w_stx == 1 && g->w_sty == g->kw && g->w_sk % 4 == 0 && g->w_sn % 4 == 0 &&
                    (reinterpret_cast<uintptr_t>(w) & 15) == 0;
   if (vec)
-    k_pack_weight<true><<<lb_grid_1d((size_t)items, 256), 256, 0, lb_s(s)>>>(w, reinterpret_cast<__nv_bfloat16*>(packed), g->kh, g->kw,
+    lb_launch(k_pack_weight<true>, lb_grid_1d((size_t)items, 256), 256, 0, lb_s(s), w, reinterpret_cast<__nv_bfloat16*>(packed), g->kh, g->kw,
                                                                             g->out_c, g->in_c, kpad, g->w_sk, g->w_sn, g->w_sty,
                                                                             g->w_stx, (int)items, lb_make_fastdiv(kpad));
   else
-    k_pack_weight<false><<<lb_grid_1d((size_t)items, 256), 256, 0, lb_s(s)>>>(w, reinterpret_cast<__nv_bfloat16*>(packed), g->kh, g->kw,
+    lb_launch(k_pack_weight<false>, lb_grid_1d((size_t)items, 256), 256, 0, lb_s(s), w, reinterpret_cast<__nv_bfloat16*>(packed), g->kh, g->kw,
                                                                              g->out_c, g->in_c, kpad, g->w_sk, g->w_sn, g->w_sty,
                                                                              g->w_stx, (int)items, lb_make_fastdiv(kpad));
   LB_LAUNCH_CHECK();
@@ -375,6 +381,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) k_splitk_reduce(const float* __restrict__ part, int splits, size_t rows, int out_c, int ld_out,
                                                       const float* __restrict__ alpha, const float* __restrict__ bias,
                                                       T* __restrict__ out) {
+  lb_pdl_enter();
   const float a = alpha ? __ldg(alpha) : 1.0f;
   const size_t n = rows * (size_t)out_c;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -513,10 +520,10 @@ extern "C" int lb_conv_tc_gemm_ws(const void* in_bf16, const void* w_packed, con
   p.part_rows = (long long)rows;
   dim3 grid(p.tiles_w * p.tiles_h * tiles_b, n_tiles, p.sp * p.sp * p.splits);
   LB_REQUIRE(grid.y <= 65535 && grid.z <= 65535);
-  k_conv_tc<<<grid, 192, smem_bytes, lb_s(s)>>>(maps, p);
+  lb_launch(k_conv_tc, grid, 192, smem_bytes, lb_s(s), maps, p);
   LB_LAUNCH_CHECK();
   if (p.splits > 1) {
-    LB_DISPATCH(out_dtype, T, k_splitk_reduce<<<lb_grid_1d(rows * g->out_c, 256), 256, 0, lb_s(s)>>>(p.part, p.splits, rows, g->out_c,
+    LB_DISPATCH(out_dtype, T, lb_launch(k_splitk_reduce<T>, lb_grid_1d(rows * g->out_c, 256), 256, 0, lb_s(s), p.part, p.splits, rows, g->out_c,
                                                                                                     g->ld_out, alpha, bias, lb_p<T>(out)));
     LB_LAUNCH_CHECK();
   }
@@ -526,6 +533,7 @@ extern "C" int lb_conv_tc_gemm_ws(const void* in_bf16, const void* w_packed, con
 // ---- fp32 -> bf16 producers ---------------------------------------------------------------------------
 template <typename F>
 __global__ void __launch_bounds__(256) k_to_bf16(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, size_t n, F f) {
+  lb_pdl_enter();
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const size_t n4 = n >> 2;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -546,7 +554,7 @@ extern "C" int lb_cast_bf16(const float* x, void* y, size_t n, lb_stream_t s) {
   LB_REQUIRE(x && y);
   if (n == 0) return LB_OK;
   if (!lb_aligned16(x) || (reinterpret_cast<uintptr_t>(y) & 7)) return LB_EALIGN;
-  k_to_bf16<<<lb_grid_1d((n + 3) / 4, 256), 256, 0, lb_s(s)>>>(x, reinterpret_cast<__nv_bfloat16*>(y), n, IdentF{});
+  lb_launch(k_to_bf16<IdentF>, lb_grid_1d((n + 3) / 4, 256), 256, 0, lb_s(s), x, reinterpret_cast<__nv_bfloat16*>(y), n, IdentF{});
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
@@ -555,6 +563,7 @@ extern "C" int lb_cast_bf16(const float* x, void* y, size_t n, lb_stream_t s) {
 template <typename F>
 __global__ void __launch_bounds__(256) k_rows_to_bf16(const float* __restrict__ src, int ld_src, __nv_bfloat16* __restrict__ dst,
                                                      int ld_dst, size_t rows, int cols, int vec, F f) {
+  lb_pdl_enter();
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   if (vec) {
     const int cols4 = cols >> 2;
@@ -585,9 +594,9 @@ extern "C" int lb_cast_bf16_rows(const float* src, int ld_src, void* dst, int ld
   const int vec = (!(cols & 3) && !(ld_src & 3) && !(ld_dst & 3) && lb_aligned16(src) && !(reinterpret_cast<uintptr_t>(dst) & 7)) ? 1 : 0;
   const int grid = lb_grid_1d((size_t)rows * (vec ? cols / 4 : cols), 256);
   __nv_bfloat16* d = reinterpret_cast<__nv_bfloat16*>(dst);
-  if (growth == 0) k_rows_to_bf16<<<grid, 256, 0, lb_s(s)>>>(src, ld_src, d, ld_dst, (size_t)rows, cols, vec, IdentF{});
-  else if (growth == 4) k_rows_to_bf16<<<grid, 256, 0, lb_s(s)>>>(src, ld_src, d, ld_dst, (size_t)rows, cols, vec, RootTanh4F{});
-  else k_rows_to_bf16<<<grid, 256, 0, lb_s(s)>>>(src, ld_src, d, ld_dst, (size_t)rows, cols, vec, RootTanhGF{1.0f / growth});
+  if (growth == 0) lb_launch(k_rows_to_bf16<IdentF>, grid, 256, 0, lb_s(s), src, ld_src, d, ld_dst, (size_t)rows, cols, vec, IdentF{});
+  else if (growth == 4) lb_launch(k_rows_to_bf16<RootTanh4F>, grid, 256, 0, lb_s(s), src, ld_src, d, ld_dst, (size_t)rows, cols, vec, RootTanh4F{});
+  else lb_launch(k_rows_to_bf16<RootTanhGF>, grid, 256, 0, lb_s(s), src, ld_src, d, ld_dst, (size_t)rows, cols, vec, RootTanhGF{1.0f / growth});
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
@@ -596,9 +605,9 @@ extern "C" int lb_roottanh_fwd_bf16(const float* x, void* y, size_t n, int growt
   if (n == 0) return LB_OK;
   if (!lb_aligned16(x) || (reinterpret_cast<uintptr_t>(y) & 7)) return LB_EALIGN;
   if (growth == 4)
-    k_to_bf16<<<lb_grid_1d((n + 3) / 4, 256), 256, 0, lb_s(s)>>>(x, reinterpret_cast<__nv_bfloat16*>(y), n, RootTanh4F{});
+    lb_launch(k_to_bf16<RootTanh4F>, lb_grid_1d((n + 3) / 4, 256), 256, 0, lb_s(s), x, reinterpret_cast<__nv_bfloat16*>(y), n, RootTanh4F{});
   else
-    k_to_bf16<<<lb_grid_1d((n + 3) / 4, 256), 256, 0, lb_s(s)>>>(x, reinterpret_cast<__nv_bfloat16*>(y), n, RootTanhGF{1.0f / growth});
+    lb_launch(k_to_bf16<RootTanhGF>, lb_grid_1d((n + 3) / 4, 256), 256, 0, lb_s(s), x, reinterpret_cast<__nv_bfloat16*>(y), n, RootTanhGF{1.0f / growth});
   LB_LAUNCH_CHECK();
   return LB_OK;
 }

@@ -400,6 +400,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  // programmatic dependent launch: the successor may be scheduled only now that this CTA owns its TMEM columns (a
+  // successor CTA allocating first, then waiting for this grid, would deadlock the SM's allocator); everything above ran
+  // while the predecessor was still draining, nothing below may start before it has completed
+  lb_pdl_trigger();
+  lb_pdl_wait();
   // shared-window addresses, computed once (the compiler otherwise re-derives them from generic pointers at every use)
   // (pinned: ptxas would rather rematerialise them -- S2UR SR_CgaCtaId + two ULEAs in front of every barrier operation of the
   // single-thread producer / MMA loops, which are the critical path of the small-channel layers)
@@ -1145,7 +1150,7 @@ extern "C" int lb_conv_tc_gemm_ex(const void* in_bf16, const void* w_packed, con
     attr_set = true;
   }
   const int grid = p.total_tiles < LB_SMS ? p.total_tiles : LB_SMS;
-  k_conv_tc2<<<grid, 64 + 32 * p.epi_warps, smem_bytes, lb_s(s)>>>(maps, p);
+  lb_launch(k_conv_tc2, grid, 64 + 32 * p.epi_warps, smem_bytes, lb_s(s), maps, p);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }

@@ -31,6 +31,7 @@ __device__ __forceinline__ bool dw_src(int mode, int stride, int pad, int o, int
 template <typename T>
 __global__ void __launch_bounds__(256) k_dw_conv(const T* __restrict__ in, const float* __restrict__ w, const float* __restrict__ alpha,
                                                  T* __restrict__ out, int n, const DwP p) {
+  lb_pdl_enter();
   const float a = alpha ? __ldg(alpha) : 1.0f;
   const int taps = p.kh * p.kw;
   const int stride_t = gridDim.x * blockDim.x;
@@ -60,6 +61,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) k_dw_wgrad(const T* __restrict__ gath, const T* __restrict__ dense, float* __restrict__ dw,
                                                   int g_h, int g_w, int d_h, int d_w, int batch, int c, int kh, int kw, int stride,
                                                   int pad, int rows_per_split) {
+  lb_pdl_enter();
   const int ch = blockIdx.x * blockDim.x + threadIdx.x;
   if (ch >= c) return;
   const int tap = blockIdx.y, ty = tap / kw, tx = tap % kw;
@@ -84,6 +86,7 @@ __global__ void __launch_bounds__(256) k_dw_wgrad(const T* __restrict__ gath, co
 template <typename T>
 __global__ void __launch_bounds__(1024) k_gfull_fwd(const T* __restrict__ in, const float* __restrict__ w, const float* __restrict__ alpha,
                                                     T* __restrict__ out, int pixels, int f, int r) {
+  lb_pdl_enter();
   extern __shared__ float s_acc[];
   const int b = blockIdx.x;
   const float a = alpha ? __ldg(alpha) : 1.0f;
@@ -105,6 +108,7 @@ __global__ void __launch_bounds__(1024) k_gfull_fwd(const T* __restrict__ in, co
 template <typename T>
 __global__ void __launch_bounds__(256) k_gfull_dgrad(const T* __restrict__ g, const float* __restrict__ w, const float* __restrict__ alpha,
                                                      T* __restrict__ din, size_t n, int pixels, int f, int r) {
+  lb_pdl_enter();
   const float a = alpha ? __ldg(alpha) : 1.0f;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -119,6 +123,7 @@ __global__ void __launch_bounds__(256) k_gfull_dgrad(const T* __restrict__ g, co
 template <typename T>
 __global__ void __launch_bounds__(256) k_gfull_wgrad(const T* __restrict__ in, const T* __restrict__ g, float* __restrict__ dw, int batch,
                                                      int pixels, int f, int r) {
+  lb_pdl_enter();
   const size_t n = (size_t)pixels * f;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -141,7 +146,7 @@ extern "C" int lb_dw_conv(const void* in, const float* w, const float* alpha, vo
   p.batch = batch; p.in_h = in_h; p.in_w = in_w; p.out_h = out_h; p.out_w = out_w; p.c = channels;
   p.kh = kh; p.kw = kw; p.stride = stride; p.pad = pad; p.mode = mode;
   p.d_c = lb_make_fastdiv(channels); p.d_w = lb_make_fastdiv(out_w); p.d_h = lb_make_fastdiv(out_h);
-  LB_DISPATCH(dtype, T, k_dw_conv<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(lb_cp<T>(in), w, alpha, lb_p<T>(out), (int)n, p));
+  LB_DISPATCH(dtype, T, lb_launch(k_dw_conv<T>, lb_grid_1d(n, 256), 256, 0, lb_s(s), lb_cp<T>(in), w, alpha, lb_p<T>(out), (int)n, p));
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
@@ -161,7 +166,7 @@ extern "C" int lb_dw_wgrad(const void* gathered, const void* dense, float* dw, i
   splits = (rows + rps - 1) / rps;
   LB_REQUIRE(kh * kw <= 65535);
   dim3 grid(cblocks, kh * kw, (unsigned)splits);
-  LB_DISPATCH(dtype, T, k_dw_wgrad<<<grid, 256, 0, lb_s(s)>>>(lb_cp<T>(gathered), lb_cp<T>(dense), dw, g_h, g_w, d_h, d_w, batch,
+  LB_DISPATCH(dtype, T, lb_launch(k_dw_wgrad<T>, grid, 256, 0, lb_s(s), lb_cp<T>(gathered), lb_cp<T>(dense), dw, g_h, g_w, d_h, d_w, batch,
                                                              channels, kh, kw, stride, pad, rps));
   LB_LAUNCH_CHECK();
   return LB_OK;
@@ -173,7 +178,7 @@ extern "C" int lb_gfull_fwd(const void* in, const float* w, const float* alpha, 
   LB_REQUIRE(in && w && out && batch > 0 && pixels > 0 && features > 0 && group_in > 0 && features % group_in == 0);
   LB_REQUIRE(features <= 12 * 1024);
   const int threads = features < 1024 ? (features + 31) / 32 * 32 : 1024;
-  LB_DISPATCH(dtype, T, k_gfull_fwd<<<batch, threads, (size_t)features * sizeof(float), lb_s(s)>>>(lb_cp<T>(in), w, alpha, lb_p<T>(out),
+  LB_DISPATCH(dtype, T, lb_launch(k_gfull_fwd<T>, batch, threads, (size_t)features * sizeof(float), lb_s(s), lb_cp<T>(in), w, alpha, lb_p<T>(out),
                                                                                                   pixels, features, group_in));
   LB_LAUNCH_CHECK();
   return LB_OK;
@@ -182,7 +187,7 @@ extern "C" int lb_gfull_dgrad(const void* g, const float* w, const float* alpha,
                               int group_in, int dtype, lb_stream_t s) {
   LB_REQUIRE(g && w && din && batch > 0 && pixels > 0 && features > 0 && group_in > 0 && features % group_in == 0);
   const size_t n = (size_t)batch * pixels * features;
-  LB_DISPATCH(dtype, T, k_gfull_dgrad<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(lb_cp<T>(g), w, alpha, lb_p<T>(din), n, pixels, features,
+  LB_DISPATCH(dtype, T, lb_launch(k_gfull_dgrad<T>, lb_grid_1d(n, 256), 256, 0, lb_s(s), lb_cp<T>(g), w, alpha, lb_p<T>(din), n, pixels, features,
                                                                               group_in));
   LB_LAUNCH_CHECK();
   return LB_OK;
@@ -191,7 +196,7 @@ extern "C" int lb_gfull_wgrad(const void* in, const void* g, float* dw, int batc
                               lb_stream_t s) {
   LB_REQUIRE(in && g && dw && batch > 0 && pixels > 0 && features > 0 && group_in > 0 && features % group_in == 0);
   const size_t n = (size_t)pixels * features;
-  LB_DISPATCH(dtype, T, k_gfull_wgrad<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(lb_cp<T>(in), lb_cp<T>(g), dw, batch, pixels, features,
+  LB_DISPATCH(dtype, T, lb_launch(k_gfull_wgrad<T>, lb_grid_1d(n, 256), 256, 0, lb_s(s), lb_cp<T>(in), lb_cp<T>(g), dw, batch, pixels, features,
                                                                               group_in));
   LB_LAUNCH_CHECK();
   return LB_OK;

@@ -3,17 +3,20 @@
 #include "common.cuh"
 
 int g_lb_launches = 0;
+int g_lb_pdl = -1;
 
 extern "C" int lb_version(void) { return 100; }
 extern "C" int lb_sm_arch(void) { return 100; }
 extern "C" int lb_last_launch_count(void) { return g_lb_launches; }
 extern "C" void lb_reset_launch_count(void) { g_lb_launches = 0; }
+extern "C" int lb_set_pdl(int on) { const int was = lb_pdl_on() ? 1 : 0; g_lb_pdl = on ? 1 : 0; return was; }
 
 // ------------------------------------------------------------------------------------------
 // generic unary / binary streaming kernels (storage type T: fp32 or bf16, fp32 arithmetic)
 // ------------------------------------------------------------------------------------------
 template <typename T, typename F>
 __global__ void __launch_bounds__(256) k_unary(const T* __restrict__ x, T* __restrict__ y, size_t n, F f) {
+  lb_pdl_enter();
   constexpr int N = LbV<T>::N;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const size_t nv = n / N;
@@ -29,6 +32,7 @@ __global__ void __launch_bounds__(256) k_unary(const T* __restrict__ x, T* __res
 
 template <typename T, typename F>
 __global__ void __launch_bounds__(256) k_binary(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ y, size_t n, F f) {
+  lb_pdl_enter();
   constexpr int N = LbV<T>::N;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const size_t nv = n / N;
@@ -47,11 +51,13 @@ __global__ void __launch_bounds__(256) k_binary(const T* __restrict__ a, const T
 // scalar fallbacks for unaligned views
 template <typename T, typename F>
 __global__ void k_unary_s(const T* __restrict__ x, T* __restrict__ y, size_t n, F f) {
+  lb_pdl_enter();
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) lb_st1(y + i, f(lb_ld1(x + i)));
 }
 template <typename T, typename F>
 __global__ void k_binary_s(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ y, size_t n, F f) {
+  lb_pdl_enter();
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) lb_st1(y + i, f(lb_ld1(a + i), lb_ld1(b + i)));
 }
@@ -61,9 +67,9 @@ static int launch_unary_t(const T* x, T* y, size_t n, F f, lb_stream_t s) {
   LB_REQUIRE(x && y);
   if (n == 0) return LB_OK;
   if (lb_vec_ok(x) && lb_vec_ok(y)) {
-    k_unary<<<lb_grid_1d((n + LbV<T>::N - 1) / LbV<T>::N, 256), 256, 0, lb_s(s)>>>(x, y, n, f);
+    lb_launch(k_unary<T, F>, lb_grid_1d((n + LbV<T>::N - 1) / LbV<T>::N, 256), 256, 0, lb_s(s), x, y, n, f);
   } else {
-    k_unary_s<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(x, y, n, f);
+    lb_launch(k_unary_s<T, F>, lb_grid_1d(n, 256), 256, 0, lb_s(s), x, y, n, f);
   }
   LB_LAUNCH_CHECK();
   return LB_OK;
@@ -73,9 +79,9 @@ static int launch_binary_t(const T* a, const T* b, T* y, size_t n, F f, lb_strea
   LB_REQUIRE(a && b && y);
   if (n == 0) return LB_OK;
   if (lb_vec_ok(a) && lb_vec_ok(b) && lb_vec_ok(y)) {
-    k_binary<<<lb_grid_1d((n + LbV<T>::N - 1) / LbV<T>::N, 256), 256, 0, lb_s(s)>>>(a, b, y, n, f);
+    lb_launch(k_binary<T, F>, lb_grid_1d((n + LbV<T>::N - 1) / LbV<T>::N, 256), 256, 0, lb_s(s), a, b, y, n, f);
   } else {
-    k_binary_s<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(a, b, y, n, f);
+    lb_launch(k_binary_s<T, F>, lb_grid_1d(n, 256), 256, 0, lb_s(s), a, b, y, n, f);
   }
   LB_LAUNCH_CHECK();
   return LB_OK;
@@ -130,13 +136,14 @@ extern "C" int lb_mul(const void* a, const void* b, void* y, size_t n, int dtype
 }
 
 __global__ void k_fill(float* __restrict__ x, size_t n, float v) {
+  lb_pdl_enter();
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) x[i] = v;
 }
 extern "C" int lb_fill(float* x, size_t n, float value, lb_stream_t s) {
   LB_REQUIRE(x);
   if (n == 0) return LB_OK;
-  k_fill<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(x, n, value);
+  lb_launch(k_fill, lb_grid_1d(n, 256), 256, 0, lb_s(s), x, n, value);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
@@ -148,6 +155,7 @@ extern "C" int lb_fill(float* x, size_t n, float value, lb_stream_t s) {
 template <typename T>
 __global__ void k_gate_fwd(const T* __restrict__ x, const T* __restrict__ y, const float* __restrict__ gamma,
                            T* __restrict__ out, size_t n, int pc, int channels, int y_bcast) {
+  lb_pdl_enter();
   const float gm = __ldg(gamma);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   if (!y_bcast) {
@@ -169,6 +177,7 @@ __global__ void k_gate_fwd(const T* __restrict__ x, const T* __restrict__ y, con
 template <typename T>
 __global__ void k_gate_fwd_s(const T* __restrict__ x, const T* __restrict__ y, const float* __restrict__ gamma,
                              T* __restrict__ out, size_t n) {
+  lb_pdl_enter();
   const float gm = __ldg(gamma);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
@@ -179,9 +188,9 @@ template <typename T>
 static int gate_fwd_t(const T* x, const T* y, const float* gamma, T* out, int batch, int pixels, int channels, int y_bcast, lb_stream_t s) {
   const size_t n = (size_t)batch * pixels * channels;
   if (!y_bcast && !((n & 3) == 0 && lb_vec4_ok(x) && lb_vec4_ok(y) && lb_vec4_ok(out))) {
-    k_gate_fwd_s<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(x, y, gamma, out, n);
+    lb_launch(k_gate_fwd_s<T>, lb_grid_1d(n, 256), 256, 0, lb_s(s), x, y, gamma, out, n);
   } else {
-    k_gate_fwd<<<lb_grid_1d(y_bcast ? n : n / 4, 256), 256, 0, lb_s(s)>>>(x, y, gamma, out, n, pixels * channels, channels, y_bcast);
+    lb_launch(k_gate_fwd<T>, lb_grid_1d(y_bcast ? n : n / 4, 256), 256, 0, lb_s(s), x, y, gamma, out, n, pixels * channels, channels, y_bcast);
   }
   LB_LAUNCH_CHECK();
   return LB_OK;
@@ -199,6 +208,7 @@ __global__ void __launch_bounds__(256) k_gate_fwd_stats(const T* __restrict__ x,
                                                        const float* __restrict__ gamma, T* __restrict__ out, int nv,
                                                        LbFastDiv d_pcv, LbFastDiv d_cv, int channels, int y_bcast,
                                                        double* __restrict__ sums, double* __restrict__ work) {
+  lb_pdl_enter();
   constexpr int N = LbV<T>::N;
   __shared__ double scratch[32];
   const float gm = __ldg(gamma);
@@ -241,7 +251,7 @@ extern "C" int lb_gate_fwd_stats(const void* x, const void* y, const float* gamm
     constexpr int N = LbV<T>::N;
     if ((channels % N) || n / N >= ((size_t)1 << 31) - ((size_t)1 << 24)) return LB_EALIGN;
     if (!lb_vec_ok(lb_cp<T>(x)) || !lb_vec_ok(lb_cp<T>(y)) || !lb_vec_ok(lb_cp<T>(out))) return LB_EALIGN;
-    k_gate_fwd_stats<<<lb_grid_1d(n / N, 256, 8), 256, 0, lb_s(s)>>>(lb_cp<T>(x), lb_cp<T>(y), gamma, lb_p<T>(out), (int)(n / N),
+    lb_launch(k_gate_fwd_stats<T>, lb_grid_1d(n / N, 256, 8), 256, 0, lb_s(s), lb_cp<T>(x), lb_cp<T>(y), gamma, lb_p<T>(out), (int)(n / N),
                                                                     lb_make_fastdiv((uint32_t)((size_t)pixels * channels / N)),
                                                                     lb_make_fastdiv(channels / N), channels, y_bcast, sums, work);
   });
@@ -256,6 +266,7 @@ __global__ void k_gate_bwd(const T* __restrict__ x, const T* __restrict__ y, con
                            const T* __restrict__ g, T* __restrict__ dx, T* __restrict__ dy, float* __restrict__ dy_bcast,
                            float* __restrict__ dgamma, int pixels, int channels, int chunk, int tc, int tp,
                            int y_bcast, int strict) {
+  lb_pdl_enter();
   __shared__ float scratch[32];
   const float gm = __ldg(gamma);
   const int cl = threadIdx.x % tc, pl = threadIdx.x / tc;
@@ -291,6 +302,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) k_gate_bwd4(const T* __restrict__ x, const T* __restrict__ y, const float* __restrict__ gamma,
                                                   const T* __restrict__ g, T* __restrict__ dx, T* __restrict__ dy,
                                                   float* __restrict__ dgamma, size_t nv, int strict) {
+  lb_pdl_enter();
   constexpr int N = LbV<T>::N;
   __shared__ float scratch[32];
   const float gm = __ldg(gamma);
@@ -324,7 +336,7 @@ static int gate_bwd_t(const T* x, const T* y, const float* gamma, const T* g, T*
                       int pixels, int channels, int y_bcast, int strict_reference, lb_stream_t s) {
   const size_t n = (size_t)batch * pixels * channels;
   if (!y_bcast && !(n % LbV<T>::N) && lb_vec_ok(x) && lb_vec_ok(y) && lb_vec_ok(g) && lb_vec_ok(dx) && lb_vec_ok(dy)) {
-    k_gate_bwd4<<<lb_grid_1d(n / LbV<T>::N, 256, 8), 256, 0, lb_s(s)>>>(x, y, gamma, g, dx, dy, dgamma, n / LbV<T>::N, strict_reference);
+    lb_launch(k_gate_bwd4<T>, lb_grid_1d(n / LbV<T>::N, 256, 8), 256, 0, lb_s(s), x, y, gamma, g, dx, dy, dgamma, n / LbV<T>::N, strict_reference);
     LB_LAUNCH_CHECK();
     return LB_OK;
   }
@@ -335,7 +347,7 @@ static int gate_bwd_t(const T* x, const T* y, const float* gamma, const T* g, T*
   if (chunk < sh.tp) chunk = sh.tp;
   chunks = (pixels + chunk - 1) / chunk;
   dim3 grid(chunks, batch);
-  k_gate_bwd<<<grid, sh.threads, 0, lb_s(s)>>>(x, y, gamma, g, dx, dy, dy_bcast, dgamma, pixels, channels, chunk, sh.tc, sh.tp,
+  lb_launch(k_gate_bwd<T>, grid, sh.threads, 0, lb_s(s), x, y, gamma, g, dx, dy, dy_bcast, dgamma, pixels, channels, chunk, sh.tc, sh.tp,
                                                   y_bcast, strict_reference);
   LB_LAUNCH_CHECK();
   return LB_OK;
@@ -357,6 +369,7 @@ extern "C" int lb_gate_bwd(const void* x, const void* y, const float* gamma, con
 // correctly: k_nadam_schedule advances state = {t, m_schedule} and writes hyper = {c_grad, c_mom, 1/bias2}
 // (nadam.py:62-73,78,82,85) in double precision; k_nadam reads them.
 __global__ void k_nadam_schedule(double* __restrict__ state, float* __restrict__ hyper, double lr, double b1, double b2, double decay) {
+  lb_pdl_enter();
   const double t = state[0] + 1.0;
   const double mu_t = b1 * (1.0 - 0.5 * pow(0.96, t * decay));
   const double mu_next = b1 * (1.0 - 0.5 * pow(0.96, (t + 1.0) * decay));
@@ -371,7 +384,7 @@ __global__ void k_nadam_schedule(double* __restrict__ state, float* __restrict__
 extern "C" int lb_nadam_schedule(double* state, float* hyper, double lr, double beta1, double beta2, double schedule_decay,
                                  lb_stream_t s) {
   LB_REQUIRE(state && hyper);
-  k_nadam_schedule<<<1, 1, 0, lb_s(s)>>>(state, hyper, lr, beta1, beta2, schedule_decay);
+  lb_launch(k_nadam_schedule, 1, 1, 0, lb_s(s), state, hyper, lr, beta1, beta2, schedule_decay);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
@@ -379,6 +392,7 @@ extern "C" int lb_nadam_schedule(double* state, float* hyper, double lr, double 
 __global__ void __launch_bounds__(256) k_nadam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                float* __restrict__ v, size_t n, float b1, float b2, float eps,
                                                const float* __restrict__ hyper) {
+  lb_pdl_enter();
   const float c_grad = __ldg(hyper), c_mom = __ldg(hyper + 1), inv_bias2 = __ldg(hyper + 2);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -398,7 +412,7 @@ extern "C" int lb_nadam_step(float* param, const float* grad, float* exp_avg, fl
                              float beta2, float eps, const float* hyper, lb_stream_t s) {
   LB_REQUIRE(param && grad && exp_avg && exp_avg_sq && hyper);
   if (n == 0) return LB_OK;
-  k_nadam<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(param, grad, exp_avg, exp_avg_sq, n, beta1, beta2, eps, hyper);
+  lb_launch(k_nadam, lb_grid_1d(n, 256), 256, 0, lb_s(s), param, grad, exp_avg, exp_avg_sq, n, beta1, beta2, eps, hyper);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
@@ -409,6 +423,7 @@ extern "C" int lb_nadam_step(float* param, const float* grad, float* exp_avg, fl
 template <typename TI, typename TO>
 __global__ void k_copy_rows(const TI* __restrict__ src, int ld_src, TO* __restrict__ dst, int ld_dst, size_t rows,
                             int cols, int accumulate) {
+  lb_pdl_enter();
   const size_t n = rows * (size_t)cols;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -423,6 +438,7 @@ __global__ void k_copy_rows(const TI* __restrict__ src, int ld_src, TO* __restri
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) k_copy_rows4(const TI* __restrict__ src, int ld_src, TO* __restrict__ dst, int ld_dst,
                                                    int n4, LbFastDiv d_c4, int accumulate) {
+  lb_pdl_enter();
   const int stride = gridDim.x * blockDim.x;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     int r, c4;
@@ -440,9 +456,9 @@ template <typename TI, typename TO>
 static int copy_rows_t(const TI* src, int ld_src, TO* dst, int ld_dst, int64_t rows, int cols, int accumulate, lb_stream_t s) {
   const size_t n = (size_t)rows * cols;
   if (!(cols & 3) && !(ld_src & 3) && !(ld_dst & 3) && lb_vec4_ok(src) && lb_vec4_ok(dst) && n / 4 < ((size_t)1 << 31) - ((size_t)1 << 24))
-    k_copy_rows4<<<lb_grid_1d(n / 4, 256), 256, 0, lb_s(s)>>>(src, ld_src, dst, ld_dst, (int)(n / 4), lb_make_fastdiv(cols / 4), accumulate);
+    lb_launch(k_copy_rows4<TI, TO>, lb_grid_1d(n / 4, 256), 256, 0, lb_s(s), src, ld_src, dst, ld_dst, (int)(n / 4), lb_make_fastdiv(cols / 4), accumulate);
   else
-    k_copy_rows<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(src, ld_src, dst, ld_dst, (size_t)rows, cols, accumulate);
+    lb_launch(k_copy_rows<TI, TO>, lb_grid_1d(n, 256), 256, 0, lb_s(s), src, ld_src, dst, ld_dst, (size_t)rows, cols, accumulate);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
@@ -458,6 +474,7 @@ extern "C" int lb_copy_rows(const void* src, int ld_src, void* dst, int ld_dst, 
 // [B][C][HW] <-> [B][HW][C] through a 32x33 shared tile (coalesced on both sides); TI / TO: storage of source / destination
 template <typename TI, typename TO>
 __global__ void k_transpose_batched(const TI* __restrict__ x, TO* __restrict__ y, int rows, int cols) {
+  lb_pdl_enter();
   __shared__ float tile[32][33];
   const size_t base = (size_t)blockIdx.z * rows * cols;
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
@@ -476,7 +493,7 @@ static int transpose_batched(const TI* x, TO* y, int batch, int rows, int cols, 
   LB_REQUIRE(x && y && batch > 0 && rows > 0 && cols > 0 && batch <= 65535);
   dim3 grid((cols + 31) / 32, (rows + 31) / 32, batch);
   LB_REQUIRE(grid.y <= 65535);
-  k_transpose_batched<<<grid, dim3(32, 8), 0, lb_s(s)>>>(x, y, rows, cols);
+  lb_launch(k_transpose_batched<TI, TO>, grid, dim3(32, 8), 0, lb_s(s), x, y, rows, cols);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
@@ -485,6 +502,7 @@ static int transpose_batched(const TI* x, TO* y, int batch, int rows, int cols, 
 template <bool kToNhwc>
 __global__ void __launch_bounds__(256) k_layout_small_c(const float* __restrict__ x, float* __restrict__ y, int c, int hw, size_t pixels,
                                                        LbFastDiv d_hw) {
+  lb_pdl_enter();
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < pixels; i += stride) {
     int b, p;
@@ -500,8 +518,8 @@ __global__ void __launch_bounds__(256) k_layout_small_c(const float* __restrict_
 static int layout_small_c(const float* x, float* y, int batch, int c, int hw, bool to_nhwc, lb_stream_t s) {
   const size_t pixels = (size_t)batch * hw;
   LB_REQUIRE(x && y && batch > 0 && c > 0 && hw > 0 && pixels < ((size_t)1 << 31) - ((size_t)1 << 24));
-  if (to_nhwc) k_layout_small_c<true><<<lb_grid_1d(pixels, 256), 256, 0, lb_s(s)>>>(x, y, c, hw, pixels, lb_make_fastdiv(hw));
-  else k_layout_small_c<false><<<lb_grid_1d(pixels, 256), 256, 0, lb_s(s)>>>(x, y, c, hw, pixels, lb_make_fastdiv(hw));
+  if (to_nhwc) lb_launch(k_layout_small_c<true>, lb_grid_1d(pixels, 256), 256, 0, lb_s(s), x, y, c, hw, pixels, lb_make_fastdiv(hw));
+  else lb_launch(k_layout_small_c<false>, lb_grid_1d(pixels, 256), 256, 0, lb_s(s), x, y, c, hw, pixels, lb_make_fastdiv(hw));
   LB_LAUNCH_CHECK();
   return LB_OK;
 }

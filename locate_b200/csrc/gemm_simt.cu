@@ -38,6 +38,7 @@ __device__ __forceinline__ void tap_range(int mode, int s, int pad, int k, int p
 }
 
 __global__ void __launch_bounds__(256) k_conv_gemm(const GemmP p) {
+  lb_pdl_enter();
   __shared__ __align__(16) float As[2][BK][BM + APAD];
   __shared__ __align__(16) float Bs[2][BK][BN];
   const int tid = threadIdx.x;
@@ -196,7 +197,7 @@ extern "C" int lb_conv_gemm(const float* in, const float* w, const float* alpha,
   p.b_kfast = g->w_sk <= g->w_sn ? 1 : 0;
   dim3 grid((p.m_phase + BM - 1) / BM, (g->out_c + BN - 1) / BN, p.sp * p.sp);
   LB_REQUIRE(grid.y <= 65535);
-  k_conv_gemm<<<grid, 256, 0, lb_s(s)>>>(p);
+  lb_launch(k_conv_gemm, grid, 256, 0, lb_s(s), p);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
@@ -212,6 +213,7 @@ struct WgradP {
 };
 
 __global__ void __launch_bounds__(256) k_conv_wgrad(const WgradP p) {
+  lb_pdl_enter();
   __shared__ __align__(16) float As[2][BK][BM];
   __shared__ __align__(16) float Bs[2][BK][BN];
   const int tid = threadIdx.x;
@@ -339,7 +341,7 @@ extern "C" int lb_conv_wgrad(const float* gathered, const float* dense, float* d
   p.vec_g = (g->in_c % 4 == 0 && g->ld_in % 4 == 0 && lb_aligned16(gathered)) ? 1 : 0;
   p.vec_d = (g->out_c % 4 == 0 && g->ld_out % 4 == 0 && lb_aligned16(dense)) ? 1 : 0;
   dim3 grid(p.tiles_g * tiles_d, taps, (unsigned)splits);
-  k_conv_wgrad<<<grid, 256, 0, lb_s(s)>>>(p);
+  lb_launch(k_conv_wgrad, grid, 256, 0, lb_s(s), p);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
@@ -347,6 +349,7 @@ extern "C" int lb_conv_wgrad(const float* gathered, const float* dense, float* d
 // ---- column sums (bias gradients) ---------------------------------------------------------------
 template <typename T>
 __global__ void k_colsum(const T* __restrict__ x, long long rows, int cols, int ld, float* __restrict__ out, int chunk, int tc, int tp) {
+  lb_pdl_enter();
   if (threadIdx.x >= tc * tp) return;
   const int cl = threadIdx.x % tc, pl = threadIdx.x / tc;
   const long long r0 = (long long)blockIdx.x * chunk, r1 = min(rows, r0 + chunk);
@@ -363,7 +366,7 @@ extern "C" int lb_colsum(const void* x, int64_t rows, int cols, int ld, float* o
   long long chunk = (rows + chunks - 1) / chunks;
   if (chunk < sh.tp) chunk = sh.tp;
   chunks = (rows + chunk - 1) / chunk;
-  LB_DISPATCH(dtype, T, k_colsum<<<(unsigned)chunks, sh.threads, 0, lb_s(s)>>>(lb_cp<T>(x), rows, cols, ld, out, (int)chunk, sh.tc, sh.tp));
+  LB_DISPATCH(dtype, T, lb_launch(k_colsum<T>, (unsigned)chunks, sh.threads, 0, lb_s(s), lb_cp<T>(x), rows, cols, ld, out, (int)chunk, sh.tc, sh.tp));
   LB_LAUNCH_CHECK();
   return LB_OK;
 }

@@ -4,6 +4,7 @@
 
 __global__ void __launch_bounds__(256) k_loss_sums(const float* __restrict__ d_true, const float* __restrict__ d_aug, int n,
                                                   double* __restrict__ sums) {
+  lb_pdl_enter();
   __shared__ double scratch[32];
   double a = 0.0, b = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) { a += d_true[i]; b += d_aug[i]; }
@@ -13,7 +14,7 @@ __global__ void __launch_bounds__(256) k_loss_sums(const float* __restrict__ d_t
 }
 extern "C" int lb_loss_sums(const float* d_true, const float* d_aug, int n_local, double* sums, lb_stream_t s) {
   LB_REQUIRE(d_true && d_aug && sums && n_local > 0);
-  k_loss_sums<<<1, 256, 0, lb_s(s)>>>(d_true, d_aug, n_local, sums);
+  lb_launch(k_loss_sums, 1, 256, 0, lb_s(s), d_true, d_aug, n_local, sums);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
@@ -24,6 +25,7 @@ __global__ void __launch_bounds__(256) k_d_loss(const float* __restrict__ t, con
                                                const double* __restrict__ sums, int n, double n_global, float gamma,
                                                float* __restrict__ out, float* __restrict__ gt, float* __restrict__ gf,
                                                float* __restrict__ ga) {
+  lb_pdl_enter();
   __shared__ double scratch[32];
   const double diff = (sums[0] - sums[1]) / n_global;
   const float inv_n = (float)(1.0 / n_global);
@@ -47,13 +49,14 @@ __global__ void __launch_bounds__(256) k_d_loss(const float* __restrict__ t, con
 extern "C" int lb_d_loss(const float* d_true, const float* d_fake, const float* d_aug, const double* sums, int n_local,
                          double n_global, float gamma, float* out, float* g_true, float* g_fake, float* g_aug, lb_stream_t s) {
   LB_REQUIRE(d_true && d_fake && d_aug && sums && out && g_true && g_fake && g_aug && n_local > 0 && n_global >= n_local);
-  k_d_loss<<<1, 256, 0, lb_s(s)>>>(d_true, d_fake, d_aug, sums, n_local, n_global, gamma, out, g_true, g_fake, g_aug);
+  lb_launch(k_d_loss, 1, 256, 0, lb_s(s), d_true, d_fake, d_aug, sums, n_local, n_global, gamma, out, g_true, g_fake, g_aug);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
 
 __global__ void __launch_bounds__(256) k_g_loss(const float* __restrict__ f, int n, double n_global, float* __restrict__ out,
                                                float* __restrict__ gf) {
+  lb_pdl_enter();
   __shared__ double scratch[32];
   const float inv_n = (float)(1.0 / n_global);
   double acc = 0.0;
@@ -67,7 +70,7 @@ __global__ void __launch_bounds__(256) k_g_loss(const float* __restrict__ f, int
 }
 extern "C" int lb_g_loss(const float* d_fake, int n_local, double n_global, float* out, float* g_fake, lb_stream_t s) {
   LB_REQUIRE(d_fake && out && g_fake && n_local > 0 && n_global >= n_local);
-  k_g_loss<<<1, 256, 0, lb_s(s)>>>(d_fake, n_local, n_global, out, g_fake);
+  lb_launch(k_g_loss, 1, 256, 0, lb_s(s), d_fake, n_local, n_global, out, g_fake);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }

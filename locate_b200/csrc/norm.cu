@@ -8,6 +8,7 @@
 template <typename T>
 __global__ void __launch_bounds__(256) k_norm_stats(const T* __restrict__ x, size_t n, double* __restrict__ sums,
                                                    double* __restrict__ work, int vec) {
+  lb_pdl_enter();
   __shared__ double scratch[32];
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   double s1 = 0.0, s2 = 0.0;
@@ -42,13 +43,14 @@ extern "C" size_t lb_stat_work_doubles(void) { return LB_STAT_WORK_DOUBLES; }
 
 extern "C" int lb_norm_stats(const void* x, size_t n, double* sums, double* work, int dtype, lb_stream_t s) {
   LB_REQUIRE(x && sums && work && n > 0);
-  LB_DISPATCH(dtype, T, k_norm_stats<<<lb_grid_1d((n + 3) / 4, 256, 8), 256, 0, lb_s(s)>>>(lb_cp<T>(x), n, sums, work,
+  LB_DISPATCH(dtype, T, lb_launch(k_norm_stats<T>, lb_grid_1d((n + 3) / 4, 256, 8), 256, 0, lb_s(s), lb_cp<T>(x), n, sums, work,
                                                                                           lb_vec_ok(lb_cp<T>(x)) ? 1 : 0));
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
 
 __global__ void k_norm_finalize(const double* __restrict__ sums, double n, float* __restrict__ stats) {
+  lb_pdl_enter();
   const double mean = sums[0] / n;
   double var = (sums[1] - sums[0] * mean) / (n - 1.0);      // unbiased, torch.std default
   if (var < 0.0) var = 0.0;
@@ -60,7 +62,7 @@ __global__ void k_norm_finalize(const double* __restrict__ sums, double n, float
 }
 extern "C" int lb_norm_finalize(const double* sums, double n_total, float* stats, lb_stream_t s) {
   LB_REQUIRE(sums && stats && n_total > 1.0);
-  k_norm_finalize<<<1, 1, 0, lb_s(s)>>>(sums, n_total, stats);
+  lb_launch(k_norm_finalize, 1, 1, 0, lb_s(s), sums, n_total, stats);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
@@ -72,6 +74,7 @@ __global__ void __launch_bounds__(256) k_norm_apply4(const T* __restrict__ x, co
                                                     const float* __restrict__ gain, int gain_bs, const float* __restrict__ bias,
                                                     T* __restrict__ y, T* __restrict__ act, T* __restrict__ dact, size_t nv,
                                                     LbFastDiv d_pcv, LbFastDiv d_cv) {
+  lb_pdl_enter();
   constexpr int N = LbV<T>::N;
   const float mean = __ldg(stats), rstd = __ldg(stats + 2);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -104,6 +107,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) k_norm_apply1(const T* __restrict__ x, const float* __restrict__ stats,
                                                     const float* __restrict__ gain, int gain_bs, const float* __restrict__ bias,
                                                     T* __restrict__ y, size_t n, int pc, int channels) {
+  lb_pdl_enter();
   const float mean = __ldg(stats), rstd = __ldg(stats + 2);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -120,11 +124,11 @@ static int norm_apply_t(const T* x, const float* stats, const float* gain, int g
   constexpr int N = LbV<T>::N;
   if ((channels % N) == 0 && n / N < ((size_t)1 << 31) - ((size_t)1 << 24) && lb_vec_ok(x) && lb_vec_ok(y) && lb_aligned16(gain) &&
       lb_aligned16(bias)) {
-    k_norm_apply4<T, false><<<lb_grid_1d(n / N, 256), 256, 0, lb_s(s)>>>(x, stats, gain, gbs, bias, y, nullptr, nullptr, n / N,
+    lb_launch(k_norm_apply4<T, false>, lb_grid_1d(n / N, 256), 256, 0, lb_s(s), x, stats, gain, gbs, bias, y, nullptr, nullptr, n / N,
                                                                         lb_make_fastdiv((uint32_t)((size_t)pixels * channels / N)),
                                                                         lb_make_fastdiv(channels / N));
   } else {
-    k_norm_apply1<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(x, stats, gain, gbs, bias, y, n, pixels * channels, channels);
+    lb_launch(k_norm_apply1<T>, lb_grid_1d(n, 256), 256, 0, lb_s(s), x, stats, gain, gbs, bias, y, n, pixels * channels, channels);
   }
   LB_LAUNCH_CHECK();
   return LB_OK;
@@ -144,7 +148,7 @@ static int norm_apply_ex_t(const T* x, const float* stats, const float* gain, in
   if ((channels % N) || n / N >= ((size_t)1 << 31) - ((size_t)1 << 24) || !lb_vec_ok(x) || (y && !lb_vec_ok(y)) || !lb_vec_ok(act) ||
       (dact && !lb_vec_ok(dact)) || !lb_aligned16(gain) || !lb_aligned16(bias))
     return LB_EALIGN;
-  k_norm_apply4<T, true><<<lb_grid_1d(n / N, 256), 256, 0, lb_s(s)>>>(x, stats, gain, gbs, bias, y, act, dact, n / N,
+  lb_launch(k_norm_apply4<T, true>, lb_grid_1d(n / N, 256), 256, 0, lb_s(s), x, stats, gain, gbs, bias, y, act, dact, n / N,
                                                                      lb_make_fastdiv((uint32_t)((size_t)pixels * channels / N)),
                                                                      lb_make_fastdiv(channels / N));
   LB_LAUNCH_CHECK();
@@ -163,6 +167,7 @@ extern "C" int lb_norm_apply_ex(const void* x, const float* stats, const float* 
 template <typename T>
 __global__ void k_norm_bwd_reduce(const T* __restrict__ x, const T* __restrict__ g, const float* __restrict__ stats,
                                   float* __restrict__ p1, float* __restrict__ p2, int pixels, int channels, int chunk, int tc, int tp) {
+  lb_pdl_enter();
   if (threadIdx.x >= tc * tp) return;
   const float mean = __ldg(stats);
   const int cl = threadIdx.x % tc, pl = threadIdx.x / tc;
@@ -190,7 +195,7 @@ extern "C" int lb_norm_bwd_reduce(const void* x, const void* g, const float* sta
   int chunk = (pixels + chunks - 1) / chunks;
   if (chunk < sh.tp) chunk = sh.tp;
   chunks = (pixels + chunk - 1) / chunk;
-  LB_DISPATCH(dtype, T, k_norm_bwd_reduce<<<dim3(chunks, batch), sh.threads, 0, lb_s(s)>>>(lb_cp<T>(x), lb_cp<T>(g), stats, p1, p2, pixels,
+  LB_DISPATCH(dtype, T, lb_launch(k_norm_bwd_reduce<T>, dim3(chunks, batch), sh.threads, 0, lb_s(s), lb_cp<T>(x), lb_cp<T>(g), stats, p1, p2, pixels,
                                                                                           channels, chunk, sh.tc, sh.tp));
   LB_LAUNCH_CHECK();
   return LB_OK;
@@ -203,6 +208,7 @@ __global__ void __launch_bounds__(256) k_norm_bwd_finalize(const float* __restri
                                                           const float* __restrict__ stats, int batch, int channels, int bchunk,
                                                           float* __restrict__ dgain, float* __restrict__ dbias,
                                                           double* __restrict__ sout) {
+  lb_pdl_enter();
   __shared__ double scratch[32];
   __shared__ float s_db[8][33], s_dg[8][33];
   const float rstd = stats[2];
@@ -248,7 +254,7 @@ extern "C" int lb_norm_bwd_finalize(const float* p1, const float* p2, const floa
   if (bchunks < 1) bchunks = 1;
   const int bchunk = (batch + bchunks - 1) / bchunks;
   bchunks = (batch + bchunk - 1) / bchunk;
-  k_norm_bwd_finalize<<<dim3(cblocks, bchunks), 256, 0, lb_s(s)>>>(p1, p2, gain, gain_batch_stride, stats, batch, channels, bchunk,
+  lb_launch(k_norm_bwd_finalize, dim3(cblocks, bchunks), 256, 0, lb_s(s), p1, p2, gain, gain_batch_stride, stats, batch, channels, bchunk,
                                                                    dgain, dbias, sout);
   LB_LAUNCH_CHECK();
   return LB_OK;
@@ -261,6 +267,7 @@ __global__ void __launch_bounds__(256) k_norm_bwd_apply(const T* __restrict__ x,
                                                        const float* __restrict__ stats, const float* __restrict__ gain,
                                                        int gain_bs, const double* __restrict__ sc, const T* __restrict__ add,
                                                        T* __restrict__ dx, size_t n, int pc, int channels) {
+  lb_pdl_enter();
   const float mean = __ldg(stats), rstd = __ldg(stats + 2);
   const double nn = (double)__ldg(stats + 3);
   const double r = (double)rstd;
@@ -283,6 +290,7 @@ __global__ void __launch_bounds__(256) k_norm_bwd_apply4(const T* __restrict__ x
                                                         const float* __restrict__ stats, const float* __restrict__ gain,
                                                         int gain_bs, const double* __restrict__ sc, const T* __restrict__ add,
                                                         T* __restrict__ dx, int nv, LbFastDiv d_pcv, LbFastDiv d_cv) {
+  lb_pdl_enter();
   constexpr int N = LbV<T>::N;
   const float mean = __ldg(stats), rstd = __ldg(stats + 2);
   const double nn = (double)__ldg(stats + 3);
@@ -315,11 +323,11 @@ static int norm_bwd_apply_t(const T* x, const T* g, const float* stats, const fl
   constexpr int N = LbV<T>::N;
   if (!(channels % N) && n / N < ((size_t)1 << 31) - ((size_t)1 << 24) && lb_vec_ok(x) && lb_vec_ok(g) && lb_vec_ok(dx) &&
       lb_aligned16(gain) && (!add || lb_vec_ok(add))) {
-    k_norm_bwd_apply4<<<lb_grid_1d(n / N, 256), 256, 0, lb_s(s)>>>(x, g, stats, gain, gbs, sc, add, dx, (int)(n / N),
+    lb_launch(k_norm_bwd_apply4<T>, lb_grid_1d(n / N, 256), 256, 0, lb_s(s), x, g, stats, gain, gbs, sc, add, dx, (int)(n / N),
                                                                   lb_make_fastdiv((uint32_t)((size_t)pixels * channels / N)),
                                                                   lb_make_fastdiv(channels / N));
   } else {
-    k_norm_bwd_apply<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(x, g, stats, gain, gbs, sc, add, dx, n, pixels * channels, channels);
+    lb_launch(k_norm_bwd_apply<T>, lb_grid_1d(n, 256), 256, 0, lb_s(s), x, g, stats, gain, gbs, sc, add, dx, n, pixels * channels, channels);
   }
   LB_LAUNCH_CHECK();
   return LB_OK;

@@ -18,6 +18,7 @@ __device__ __forceinline__ void lb_st2(float* p, float a, float b) { *reinterpre
 __device__ __forceinline__ void lb_st2(lb_bf16* p, float a, float b) { *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b); }
 template <typename T>
 __global__ void __launch_bounds__(256) k_featpool_fwd(const T* __restrict__ x, T* __restrict__ y, int n_out, const FeatPoolIdx q) {
+  lb_pdl_enter();
   const int stride = gridDim.x * blockDim.x;
   const float inv = 1.0f / q.r;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += stride) {
@@ -35,6 +36,7 @@ __global__ void __launch_bounds__(256) k_featpool_fwd(const T* __restrict__ x, T
 // stores (channels ci..ci+3 are outputs (o, o+1) of pixel groups pj = 0 and pj = 1).  d_c = c_in / 4 here.
 template <typename T>
 __global__ void __launch_bounds__(256) k_featpool_fwd_r2v4(const T* __restrict__ x, T* __restrict__ y, int n_items, const FeatPoolIdx q) {
+  lb_pdl_enter();
   const int stride = gridDim.x * blockDim.x;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += stride) {
     int t, c4, b, pm;
@@ -49,6 +51,7 @@ __global__ void __launch_bounds__(256) k_featpool_fwd_r2v4(const T* __restrict__
 }
 template <typename T>
 __global__ void __launch_bounds__(256) k_featpool_bwd(const T* __restrict__ g, T* __restrict__ dx, int n_in, const FeatPoolIdx q) {
+  lb_pdl_enter();
   const int stride = gridDim.x * blockDim.x;
   const float inv = 1.0f / q.r;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_in; i += stride) {
@@ -63,6 +66,7 @@ __global__ void __launch_bounds__(256) k_featpool_bwd(const T* __restrict__ g, T
 // generic fallbacks (r does not divide HW, or more than 2^31 items): 64-bit index arithmetic, any shape
 template <typename T>
 __global__ void k_featpool_fwd_generic(const T* __restrict__ x, T* __restrict__ y, size_t n_out, int hw, int c_in, int c_out, int r) {
+  lb_pdl_enter();
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const float inv = 1.0f / r;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += stride) {
@@ -81,6 +85,7 @@ __global__ void k_featpool_fwd_generic(const T* __restrict__ x, T* __restrict__ 
 }
 template <typename T>
 __global__ void k_featpool_bwd_generic(const T* __restrict__ g, T* __restrict__ dx, size_t n_in, int hw, int c_in, int c_out, int r) {
+  lb_pdl_enter();
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const float inv = 1.0f / r;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_in; i += stride) {
@@ -109,13 +114,13 @@ static int featpool_fwd_t(const T* x, T* y, int batch, int h, int w, int c_in, i
   if (featpool_idx(&q, batch, h, w, c_in, c_out, c_in, n) == LB_OK) {
     if (q.r == 2 && !(c_in & 3) && lb_vec4_ok(x) && !(reinterpret_cast<uintptr_t>(y) & (2 * sizeof(T) - 1))) {
       q.d_c = lb_make_fastdiv(c_in / 4);
-      k_featpool_fwd_r2v4<<<lb_grid_1d(n / 4, 256), 256, 0, lb_s(s)>>>(x, y, (int)(n / 4), q);     // n = B*m*c_in outputs, 4 per item
+      lb_launch(k_featpool_fwd_r2v4<T>, lb_grid_1d(n / 4, 256), 256, 0, lb_s(s), x, y, (int)(n / 4), q);     // n = B*m*c_in outputs, 4 per item
     } else {
-      k_featpool_fwd<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(x, y, (int)n, q);
+      lb_launch(k_featpool_fwd<T>, lb_grid_1d(n, 256), 256, 0, lb_s(s), x, y, (int)n, q);
     }
   }
   else
-    k_featpool_fwd_generic<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(x, y, n, h * w, c_in, c_out, c_in / c_out);
+    lb_launch(k_featpool_fwd_generic<T>, lb_grid_1d(n, 256), 256, 0, lb_s(s), x, y, n, h * w, c_in, c_out, c_in / c_out);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
@@ -124,9 +129,9 @@ static int featpool_bwd_t(const T* g, T* dx, int batch, int h, int w, int c_in, 
   const size_t n = (size_t)batch * h * w * c_in;
   FeatPoolIdx q;
   if (featpool_idx(&q, batch, h, w, c_in, c_out, c_in, n) == LB_OK)
-    k_featpool_bwd<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(g, dx, (int)n, q);
+    lb_launch(k_featpool_bwd<T>, lb_grid_1d(n, 256), 256, 0, lb_s(s), g, dx, (int)n, q);
   else
-    k_featpool_bwd_generic<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(g, dx, n, h * w, c_in, c_out, c_in / c_out);
+    lb_launch(k_featpool_bwd_generic<T>, lb_grid_1d(n, 256), 256, 0, lb_s(s), g, dx, n, h * w, c_in, c_out, c_in / c_out);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
@@ -185,6 +190,7 @@ template <> struct Acc<1> {
 
 template <typename T, int V>
 __global__ void __launch_bounds__(256) k_up2_fwd(const T* __restrict__ x, T* __restrict__ y, int n_out, int h, int w, int c, const PixIdx q) {
+  lb_pdl_enter();
   const int stride = gridDim.x * blockDim.x;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += stride) {
     int ch, ox, oy, b;
@@ -210,6 +216,7 @@ __device__ __forceinline__ float lb_up2_weight(int d, int n, int m) {
 // 1-D transposed taps of the x2 bilinear kernel: source m receives from destinations 2m-1 .. 2m+2
 template <typename T, int V>
 __global__ void __launch_bounds__(256) k_up2_bwd(const T* __restrict__ g, T* __restrict__ dx, int n_in, int h, int w, int c, const PixIdx q) {
+  lb_pdl_enter();
   const int stride = gridDim.x * blockDim.x;
   const int ow = 2 * w, oh = 2 * h;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_in; i += stride) {
@@ -241,9 +248,9 @@ static int up2_fwd_t(const T* x, T* y, int batch, int h, int w, int c, lb_stream
   LB_REQUIRE_INT_ITEMS(n);
   constexpr int N = LbV<T>::N;
   if ((c % N) == 0 && lb_vec_ok(x) && lb_vec_ok(y))
-    k_up2_fwd<T, N><<<lb_grid_1d(n / N, 256), 256, 0, lb_s(s)>>>(x, y, (int)(n / N), h, w, c, make_pix_idx(c / N, 2 * w, 2 * h));
+    lb_launch(k_up2_fwd<T, N>, lb_grid_1d(n / N, 256), 256, 0, lb_s(s), x, y, (int)(n / N), h, w, c, make_pix_idx(c / N, 2 * w, 2 * h));
   else
-    k_up2_fwd<T, 1><<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(x, y, (int)n, h, w, c, make_pix_idx(c, 2 * w, 2 * h));
+    lb_launch(k_up2_fwd<T, 1>, lb_grid_1d(n, 256), 256, 0, lb_s(s), x, y, (int)n, h, w, c, make_pix_idx(c, 2 * w, 2 * h));
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
@@ -253,9 +260,9 @@ static int up2_bwd_t(const T* g, T* dx, int batch, int h, int w, int c, lb_strea
   LB_REQUIRE_INT_ITEMS(n);
   constexpr int N = LbV<T>::N;
   if ((c % N) == 0 && lb_vec_ok(g) && lb_vec_ok(dx))
-    k_up2_bwd<T, N><<<lb_grid_1d(n / N, 256), 256, 0, lb_s(s)>>>(g, dx, (int)(n / N), h, w, c, make_pix_idx(c / N, w, h));
+    lb_launch(k_up2_bwd<T, N>, lb_grid_1d(n / N, 256), 256, 0, lb_s(s), g, dx, (int)(n / N), h, w, c, make_pix_idx(c / N, w, h));
   else
-    k_up2_bwd<T, 1><<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(g, dx, (int)n, h, w, c, make_pix_idx(c, w, h));
+    lb_launch(k_up2_bwd<T, 1>, lb_grid_1d(n, 256), 256, 0, lb_s(s), g, dx, (int)n, h, w, c, make_pix_idx(c, w, h));
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
@@ -271,6 +278,7 @@ extern "C" int lb_upsample2x_bwd(const void* g, void* dx, int batch, int h, int 
 // ---- AvgPool 2x2 / stride 2 (scale.py:40) ----------------------------------------------------
 template <typename T, int V>
 __global__ void __launch_bounds__(256) k_avgpool2_fwd(const T* __restrict__ x, T* __restrict__ y, int n_out, int h, int w, int c, const PixIdx q) {
+  lb_pdl_enter();
   const int stride = gridDim.x * blockDim.x;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += stride) {
     int ch, ox, oy, b;
@@ -283,6 +291,7 @@ __global__ void __launch_bounds__(256) k_avgpool2_fwd(const T* __restrict__ x, T
 }
 template <typename T, int V>
 __global__ void __launch_bounds__(256) k_avgpool2_bwd(const T* __restrict__ g, T* __restrict__ dx, int n_in, int h, int w, int c, const PixIdx q) {
+  lb_pdl_enter();
   const int stride = gridDim.x * blockDim.x;
   const int oh = h / 2, ow = w / 2;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_in; i += stride) {
@@ -300,9 +309,9 @@ static int avgpool2_fwd_t(const T* x, T* y, int batch, int h, int w, int c, lb_s
   LB_REQUIRE_INT_ITEMS(n);
   constexpr int N = LbV<T>::N;
   if ((c % N) == 0 && lb_vec_ok(x) && lb_vec_ok(y))
-    k_avgpool2_fwd<T, N><<<lb_grid_1d(n / N, 256), 256, 0, lb_s(s)>>>(x, y, (int)(n / N), h, w, c, make_pix_idx(c / N, w / 2, h / 2));
+    lb_launch(k_avgpool2_fwd<T, N>, lb_grid_1d(n / N, 256), 256, 0, lb_s(s), x, y, (int)(n / N), h, w, c, make_pix_idx(c / N, w / 2, h / 2));
   else
-    k_avgpool2_fwd<T, 1><<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(x, y, (int)n, h, w, c, make_pix_idx(c, w / 2, h / 2));
+    lb_launch(k_avgpool2_fwd<T, 1>, lb_grid_1d(n, 256), 256, 0, lb_s(s), x, y, (int)n, h, w, c, make_pix_idx(c, w / 2, h / 2));
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
@@ -312,9 +321,9 @@ static int avgpool2_bwd_t(const T* g, T* dx, int batch, int h, int w, int c, lb_
   LB_REQUIRE_INT_ITEMS(n);
   constexpr int N = LbV<T>::N;
   if ((c % N) == 0 && lb_vec_ok(g) && lb_vec_ok(dx))
-    k_avgpool2_bwd<T, N><<<lb_grid_1d(n / N, 256), 256, 0, lb_s(s)>>>(g, dx, (int)(n / N), h, w, c, make_pix_idx(c / N, w, h));
+    lb_launch(k_avgpool2_bwd<T, N>, lb_grid_1d(n / N, 256), 256, 0, lb_s(s), g, dx, (int)(n / N), h, w, c, make_pix_idx(c / N, w, h));
   else
-    k_avgpool2_bwd<T, 1><<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(g, dx, (int)n, h, w, c, make_pix_idx(c, w, h));
+    lb_launch(k_avgpool2_bwd<T, 1>, lb_grid_1d(n, 256), 256, 0, lb_s(s), g, dx, (int)n, h, w, c, make_pix_idx(c, w, h));
   LB_LAUNCH_CHECK();
   return LB_OK;
 }

@@ -60,6 +60,7 @@ __device__ __forceinline__ ML slab_stats(const T* __restrict__ x, size_t base, i
 template <typename T>
 __global__ void __launch_bounds__(kThreads) k_softmax_pixels_fwd(const T* __restrict__ x, T* __restrict__ y, int pixels, int channels,
                                                                  int splits, int chunk, int phase, float2* __restrict__ part) {
+  lb_pdl_enter();
   __shared__ float4 s_m[kPL][kCQ], s_l[kPL][kCQ];
   const int cq = threadIdx.x & (kCQ - 1), pl = threadIdx.x >> 3;
   const int c = blockIdx.x * (4 * kCQ) + 4 * cq;
@@ -104,6 +105,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads) k_softmax_pixels_bwd(const T* __restrict__ y, const T* __restrict__ g, T* __restrict__ dx,
                                                                  int pixels, int channels, int splits, int chunk, int phase,
                                                                  float* __restrict__ part) {
+  lb_pdl_enter();
   __shared__ float4 s_d[kPL][kCQ];
   const int cq = threadIdx.x & (kCQ - 1), pl = threadIdx.x >> 3;
   const int c = blockIdx.x * (4 * kCQ) + 4 * cq;
@@ -150,6 +152,7 @@ __global__ void __launch_bounds__(kThreads) k_softmax_pixels_bwd(const T* __rest
 constexpr int kWarpsS = 16;
 template <typename T>
 __global__ void __launch_bounds__(32 * kWarpsS) k_softmax_pixels_fwd_s(const T* __restrict__ x, T* __restrict__ y, int pixels, int channels) {
+  lb_pdl_enter();
   __shared__ float s_max[kWarpsS][33];
   __shared__ float s_sum[kWarpsS][33];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -175,6 +178,7 @@ __global__ void __launch_bounds__(32 * kWarpsS) k_softmax_pixels_fwd_s(const T* 
 template <typename T>
 __global__ void __launch_bounds__(32 * kWarpsS) k_softmax_pixels_bwd_s(const T* __restrict__ y, const T* __restrict__ g, T* __restrict__ dx,
                                                                        int pixels, int channels) {
+  lb_pdl_enter();
   __shared__ float s_dot[kWarpsS][33];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
@@ -214,7 +218,7 @@ int pixel_splits(int batch, int pixels, int channels, int* chunk) {
 template <typename T>
 int softmax_pixels_fwd_t(const T* x, T* y, int batch, int pixels, int channels, float* work, size_t work_floats, lb_stream_t s) {
   if ((channels & 3) || !lb_vec4_ok(x) || !lb_vec4_ok(y)) {
-    k_softmax_pixels_fwd_s<<<dim3((channels + 31) / 32, batch), 32 * kWarpsS, 0, lb_s(s)>>>(x, y, pixels, channels);
+    lb_launch(k_softmax_pixels_fwd_s<T>, dim3((channels + 31) / 32, batch), 32 * kWarpsS, 0, lb_s(s), x, y, pixels, channels);
     LB_LAUNCH_CHECK();
     return LB_OK;
   }
@@ -224,10 +228,10 @@ int softmax_pixels_fwd_t(const T* x, T* y, int batch, int pixels, int channels, 
   const dim3 grid((channels + 4 * kCQ - 1) / (4 * kCQ), batch, splits);
   LB_REQUIRE(grid.z <= 65535);
   float2* part = reinterpret_cast<float2*>(work);
-  k_softmax_pixels_fwd<<<grid, kThreads, 0, lb_s(s)>>>(x, y, pixels, channels, splits, chunk, 0, part);
+  lb_launch(k_softmax_pixels_fwd<T>, grid, kThreads, 0, lb_s(s), x, y, pixels, channels, splits, chunk, 0, part);
   LB_LAUNCH_CHECK();
   if (splits > 1) {
-    k_softmax_pixels_fwd<<<grid, kThreads, 0, lb_s(s)>>>(x, y, pixels, channels, splits, chunk, 1, part);
+    lb_launch(k_softmax_pixels_fwd<T>, grid, kThreads, 0, lb_s(s), x, y, pixels, channels, splits, chunk, 1, part);
     LB_LAUNCH_CHECK();
   }
   return LB_OK;
@@ -236,7 +240,7 @@ template <typename T>
 int softmax_pixels_bwd_t(const T* y, const T* g, T* dx, int batch, int pixels, int channels, float* work, size_t work_floats,
                          lb_stream_t s) {
   if ((channels & 3) || !lb_vec4_ok(y) || !lb_vec4_ok(g) || !lb_vec4_ok(dx)) {
-    k_softmax_pixels_bwd_s<<<dim3((channels + 31) / 32, batch), 32 * kWarpsS, 0, lb_s(s)>>>(y, g, dx, pixels, channels);
+    lb_launch(k_softmax_pixels_bwd_s<T>, dim3((channels + 31) / 32, batch), 32 * kWarpsS, 0, lb_s(s), y, g, dx, pixels, channels);
     LB_LAUNCH_CHECK();
     return LB_OK;
   }
@@ -247,10 +251,10 @@ int softmax_pixels_bwd_t(const T* y, const T* g, T* dx, int batch, int pixels, i
   }
   const dim3 grid((channels + 4 * kCQ - 1) / (4 * kCQ), batch, splits);
   LB_REQUIRE(grid.z <= 65535);
-  k_softmax_pixels_bwd<<<grid, kThreads, 0, lb_s(s)>>>(y, g, dx, pixels, channels, splits, chunk, 0, work);
+  lb_launch(k_softmax_pixels_bwd<T>, grid, kThreads, 0, lb_s(s), y, g, dx, pixels, channels, splits, chunk, 0, work);
   LB_LAUNCH_CHECK();
   if (splits > 1) {
-    k_softmax_pixels_bwd<<<grid, kThreads, 0, lb_s(s)>>>(y, g, dx, pixels, channels, splits, chunk, 1, work);
+    lb_launch(k_softmax_pixels_bwd<T>, grid, kThreads, 0, lb_s(s), y, g, dx, pixels, channels, splits, chunk, 1, work);
     LB_LAUNCH_CHECK();
   }
   return LB_OK;
@@ -279,6 +283,7 @@ extern "C" int lb_softmax_pixels_bwd(const void* y, const void* g, void* dx, int
 // contiguous rows: one warp per row
 template <typename T>
 __global__ void __launch_bounds__(128) k_softmax_rows_fwd(const T* __restrict__ x, T* __restrict__ y, int rows, int cols) {
+  lb_pdl_enter();
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
   const T* xr = x + (size_t)row * cols;
@@ -294,6 +299,7 @@ __global__ void __launch_bounds__(128) k_softmax_rows_fwd(const T* __restrict__ 
 template <typename T>
 __global__ void __launch_bounds__(128) k_softmax_rows_bwd(const T* __restrict__ y, const T* __restrict__ g, T* __restrict__ dx, int rows,
                                                          int cols) {
+  lb_pdl_enter();
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
   const size_t o = (size_t)row * cols;
@@ -304,13 +310,13 @@ __global__ void __launch_bounds__(128) k_softmax_rows_bwd(const T* __restrict__ 
 }
 extern "C" int lb_softmax_rows_fwd(const void* x, void* y, int rows, int cols, int dtype, lb_stream_t s) {
   LB_REQUIRE(x && y && rows > 0 && cols > 0);
-  LB_DISPATCH(dtype, T, k_softmax_rows_fwd<<<(rows + 3) / 4, 128, 0, lb_s(s)>>>(lb_cp<T>(x), lb_p<T>(y), rows, cols));
+  LB_DISPATCH(dtype, T, lb_launch(k_softmax_rows_fwd<T>, (rows + 3) / 4, 128, 0, lb_s(s), lb_cp<T>(x), lb_p<T>(y), rows, cols));
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
 extern "C" int lb_softmax_rows_bwd(const void* y, const void* g, void* dx, int rows, int cols, int dtype, lb_stream_t s) {
   LB_REQUIRE(y && g && dx && rows > 0 && cols > 0);
-  LB_DISPATCH(dtype, T, k_softmax_rows_bwd<<<(rows + 3) / 4, 128, 0, lb_s(s)>>>(lb_cp<T>(y), lb_cp<T>(g), lb_p<T>(dx), rows, cols));
+  LB_DISPATCH(dtype, T, lb_launch(k_softmax_rows_bwd<T>, (rows + 3) / 4, 128, 0, lb_s(s), lb_cp<T>(y), lb_cp<T>(g), lb_p<T>(dx), rows, cols));
   LB_LAUNCH_CHECK();
   return LB_OK;
 }

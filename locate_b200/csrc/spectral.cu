@@ -12,6 +12,7 @@
 // tpart[split][j] = sum_{i in row split} W[i][j] * u[i];   grid = (col tiles of 256, row splits)
 __global__ void __launch_bounds__(256) k_sn_wt_u(const float* __restrict__ w, const float* __restrict__ u, float* __restrict__ tpart,
                                                 int height, int width, int rows_per_split) {
+  lb_pdl_enter();
   const int j = blockIdx.x * 256 + threadIdx.x;
   if (j >= width) return;
   const int i0 = blockIdx.y * rows_per_split, i1 = min(height, i0 + rows_per_split);
@@ -23,6 +24,7 @@ __global__ void __launch_bounds__(256) k_sn_wt_u(const float* __restrict__ w, co
 // src[i] <- sum of its `nsplit` partials (stride n, fixed order); dst = src / (|src| + eps); also writes sigma if non-null.  One CTA.
 __global__ void __launch_bounds__(1024) k_sn_normalize(float* __restrict__ src, float* __restrict__ dst, int n, int nsplit,
                                                       float* __restrict__ sigma_out) {
+  lb_pdl_enter();
   __shared__ float scratch[32];
   __shared__ float s_norm;
   float acc = 0.0f;
@@ -48,6 +50,7 @@ __global__ void __launch_bounds__(1024) k_sn_normalize(float* __restrict__ src, 
 // s[i] = sum_j W[i][j] v[j]; one warp per row (rows are contiguous)
 __global__ void __launch_bounds__(256) k_sn_w_v(const float* __restrict__ w, const float* __restrict__ v, float* __restrict__ sv,
                                                int height, int width) {
+  lb_pdl_enter();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= height) return;
   const float* wr = w + (size_t)row * width;
@@ -80,13 +83,13 @@ extern "C" int lb_sn_power_iter(const float* w, int height, int width, float* u,
   float* t = work;                              // [splits][width]
   float* sv = work + (size_t)splits * width;    // [height]
   const int col_tiles = (width + 255) / 256;
-  k_sn_wt_u<<<dim3(col_tiles, splits), 256, 0, lb_s(s)>>>(w, u, t, height, width, rps);
+  lb_launch(k_sn_wt_u, dim3(col_tiles, splits), 256, 0, lb_s(s), w, u, t, height, width, rps);
   LB_LAUNCH_CHECK();
-  k_sn_normalize<<<1, 1024, 0, lb_s(s)>>>(t, v, width, splits, nullptr);
+  lb_launch(k_sn_normalize, 1, 1024, 0, lb_s(s), t, v, width, splits, nullptr);
   LB_LAUNCH_CHECK();
-  k_sn_w_v<<<(height + 7) / 8, 256, 0, lb_s(s)>>>(w, v, sv, height, width);
+  lb_launch(k_sn_w_v, (height + 7) / 8, 256, 0, lb_s(s), w, v, sv, height, width);
   LB_LAUNCH_CHECK();
-  k_sn_normalize<<<1, 1024, 0, lb_s(s)>>>(sv, u, height, 1, sigma_out);
+  lb_launch(k_sn_normalize, 1, 1024, 0, lb_s(s), sv, u, height, 1, sigma_out);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
@@ -106,6 +109,7 @@ __device__ __forceinline__ void sn_decode(const SnIdx& x, int k, int& i, int& j,
 }
 __global__ void __launch_bounds__(256) k_sn_dot(const float* __restrict__ a, const float* __restrict__ b, int n, const SnIdx x,
                                                double* __restrict__ out, double* __restrict__ stat_work) {
+  lb_pdl_enter();
   __shared__ double scratch[32];
   const int stride = gridDim.x * blockDim.x;
   float part = 0.0f;
@@ -127,6 +131,7 @@ __global__ void __launch_bounds__(256) k_sn_wgrad(const float* __restrict__ dwn,
                                                  const float* __restrict__ sigma, const double* __restrict__ dot,
                                                  float* __restrict__ grad, int n, const SnIdx x, const float* __restrict__ s_fwd,
                                                  float* __restrict__ du, float* __restrict__ cacc) {
+  lb_pdl_enter();
   const float inv = __ldg(sigma + 1);
   const float coef = (float)(dot[0] * (double)inv * (double)inv);
   const int stride = gridDim.x * blockDim.x;
@@ -141,6 +146,7 @@ __global__ void __launch_bounds__(256) k_sn_wgrad(const float* __restrict__ dwn,
 // contiguous (packed_taps = 0) fast paths: 4 consecutive elements of one matrix row per thread
 __global__ void __launch_bounds__(256) k_sn_dot4(const float4* __restrict__ a, const float4* __restrict__ b, int n4,
                                                 double* __restrict__ out, double* __restrict__ stat_work) {
+  lb_pdl_enter();
   __shared__ double scratch[32];
   const int stride = gridDim.x * blockDim.x;
   double acc = 0.0;
@@ -159,6 +165,7 @@ __global__ void __launch_bounds__(256) k_sn_wgrad4(const float4* __restrict__ dw
                                                   const float* __restrict__ sigma, const double* __restrict__ dot,
                                                   float4* __restrict__ grad, int n4, int height, LbFastDiv d_w4,
                                                   const float* __restrict__ s_fwd, float* __restrict__ du, float* __restrict__ cacc) {
+  lb_pdl_enter();
   const float inv = __ldg(sigma + 1);
   const float coef = (float)(dot[0] * (double)inv * (double)inv);
   const int stride = gridDim.x * blockDim.x;
@@ -196,18 +203,18 @@ extern "C" int lb_sn_weight_grad(const float* dwn, const float* w, const float* 
                       (w ? reinterpret_cast<uintptr_t>(w) : 0)) & 15);
   if (w) {
     if (vec)
-      k_sn_dot4<<<lb_grid_1d(n / 4, 256, 4), 256, 0, lb_s(s)>>>(reinterpret_cast<const float4*>(dwn), reinterpret_cast<const float4*>(w),
+      lb_launch(k_sn_dot4, lb_grid_1d(n / 4, 256, 4), 256, 0, lb_s(s), reinterpret_cast<const float4*>(dwn), reinterpret_cast<const float4*>(w),
                                                                   (int)(n / 4), dot_out, stat_work);
     else
-      k_sn_dot<<<lb_grid_1d(n, 256, 2), 256, 0, lb_s(s)>>>(dwn, w, (int)n, x, dot_out, stat_work);
+      lb_launch(k_sn_dot, lb_grid_1d(n, 256, 2), 256, 0, lb_s(s), dwn, w, (int)n, x, dot_out, stat_work);
     LB_LAUNCH_CHECK();
   }
   if (vec)
-    k_sn_wgrad4<<<lb_grid_1d(n / 4, 256), 256, 0, lb_s(s)>>>(reinterpret_cast<const float4*>(dwn), u, v, sigma, dot_out,
+    lb_launch(k_sn_wgrad4, lb_grid_1d(n / 4, 256), 256, 0, lb_s(s), reinterpret_cast<const float4*>(dwn), u, v, sigma, dot_out,
                                                               reinterpret_cast<float4*>(grad), (int)(n / 4), height,
                                                               lb_make_fastdiv(width / 4), s_fwd, du, cacc);
   else
-    k_sn_wgrad<<<lb_grid_1d(n, 256), 256, 0, lb_s(s)>>>(dwn, u, v, sigma, dot_out, grad, (int)n, x, s_fwd, du, cacc);
+    lb_launch(k_sn_wgrad, lb_grid_1d(n, 256), 256, 0, lb_s(s), dwn, u, v, sigma, dot_out, grad, (int)n, x, s_fwd, du, cacc);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
@@ -224,6 +231,7 @@ struct LbSnLayerDev {
 // partial tpart[split][j] = sum_rows W[i][j] u[i] (plain stores: deterministic, nothing to zero first)
 __global__ void __launch_bounds__(256) k_snb_wt_u(const LbSnLayerDev* __restrict__ layers, const int4* __restrict__ items,
                                                  float* __restrict__ scratch) {
+  lb_pdl_enter();
   const int4 it = items[blockIdx.x];
   const LbSnLayerDev L = layers[it.x];
   const int j = it.y + 4 * threadIdx.x;                    // 4 consecutive columns per thread
@@ -252,6 +260,7 @@ __global__ void __launch_bounds__(256) k_snb_wt_u(const LbSnLayerDev* __restrict
 // per layer: dst = src/(|src|+eps); phase 2 (v from t) and phase 4 (u from s, sigma)
 __global__ void __launch_bounds__(1024) k_snb_normalize(const LbSnLayerDev* __restrict__ layers, float* __restrict__ scratch,
                                                       float* __restrict__ s_out, int phase, float* __restrict__ sigma_out) {
+  lb_pdl_enter();
   __shared__ float red[32];
   __shared__ float s_norm;
   const LbSnLayerDev L = layers[blockIdx.x];
@@ -287,6 +296,7 @@ __global__ void __launch_bounds__(1024) k_snb_normalize(const LbSnLayerDev* __re
 // phase 3 item: (layer, first row); 8 rows per CTA, one warp per row.  s_out[s_off + i] = sum_j W[i][j] v[j]
 __global__ void __launch_bounds__(256) k_snb_w_v(const LbSnLayerDev* __restrict__ layers, const int2* __restrict__ items,
                                                 float* __restrict__ scratch) {
+  lb_pdl_enter();
   const int2 it = items[blockIdx.x];
   const LbSnLayerDev L = layers[it.x];
   const int row = it.y + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -312,13 +322,13 @@ extern "C" int lb_sn_power_iter_batched(const void* layers_dev, int n_layers, co
   LB_REQUIRE(layers_dev && items1_dev && items3_dev && scratch && s_out && sigma_out && n_layers > 0 && n_items1 > 0 && n_items3 > 0);
   // every partial slot is written before it is read: no zero fill
   const LbSnLayerDev* layers = reinterpret_cast<const LbSnLayerDev*>(layers_dev);
-  k_snb_wt_u<<<n_items1, 256, 0, lb_s(s)>>>(layers, reinterpret_cast<const int4*>(items1_dev), scratch);
+  lb_launch(k_snb_wt_u, n_items1, 256, 0, lb_s(s), layers, reinterpret_cast<const int4*>(items1_dev), scratch);
   LB_LAUNCH_CHECK();
-  k_snb_normalize<<<n_layers, 1024, 0, lb_s(s)>>>(layers, scratch, s_out, 2, sigma_out);
+  lb_launch(k_snb_normalize, n_layers, 1024, 0, lb_s(s), layers, scratch, s_out, 2, sigma_out);
   LB_LAUNCH_CHECK();
-  k_snb_w_v<<<n_items3, 256, 0, lb_s(s)>>>(layers, reinterpret_cast<const int2*>(items3_dev), s_out);
+  lb_launch(k_snb_w_v, n_items3, 256, 0, lb_s(s), layers, reinterpret_cast<const int2*>(items3_dev), s_out);
   LB_LAUNCH_CHECK();
-  k_snb_normalize<<<n_layers, 1024, 0, lb_s(s)>>>(layers, scratch, s_out, 4, sigma_out);
+  lb_launch(k_snb_normalize, n_layers, 1024, 0, lb_s(s), layers, scratch, s_out, 4, sigma_out);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }
@@ -329,6 +339,7 @@ extern "C" int lb_sn_power_iter_batched(const void* layers_dev, int n_layers, co
 // over the weights per optimizer step, reusing the pass-1 kernel of the power iteration.
 __global__ void __launch_bounds__(512) k_snb_dv(const LbSnLayerDev* __restrict__ layers, const float* __restrict__ scratch,
                                                float* __restrict__ cacc) {
+  lb_pdl_enter();
   const LbSnLayerDev L = layers[blockIdx.x];
   const float c = cacc[blockIdx.x];
   __syncthreads();
@@ -345,9 +356,9 @@ extern "C" int lb_sn_uv_grad_batched(const void* layers_dev, int n_layers, const
                                      float* cacc, lb_stream_t s) {
   LB_REQUIRE(layers_dev && items1_dev && scratch && cacc && n_layers > 0 && n_items1 > 0);
   const LbSnLayerDev* layers = reinterpret_cast<const LbSnLayerDev*>(layers_dev);
-  k_snb_wt_u<<<n_items1, 256, 0, lb_s(s)>>>(layers, reinterpret_cast<const int4*>(items1_dev), scratch);
+  lb_launch(k_snb_wt_u, n_items1, 256, 0, lb_s(s), layers, reinterpret_cast<const int4*>(items1_dev), scratch);
   LB_LAUNCH_CHECK();
-  k_snb_dv<<<n_layers, 512, 0, lb_s(s)>>>(layers, scratch, cacc);
+  lb_launch(k_snb_dv, n_layers, 512, 0, lb_s(s), layers, scratch, cacc);
   LB_LAUNCH_CHECK();
   return LB_OK;
 }

@@ -87,6 +87,11 @@ __global__ void __launch_bounds__(192, 2) k_wgrad_tc(const __grid_constant__ WgM
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  // programmatic dependent launch: the successor may be scheduled only now that this CTA owns its TMEM columns (a
+  // successor CTA allocating first, then waiting for this grid, would deadlock the SM's allocator); everything above ran
+  // while the predecessor was still draining, nothing below may start before it has completed
+  lb_pdl_trigger();
+  lb_pdl_wait();
 
   if (warp == 0) {
     if (tc::elect_one()) {
@@ -210,6 +215,11 @@ __global__ void __launch_bounds__(192, 1) k_wgrad_halo(const __grid_constant__ W
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  // programmatic dependent launch: the successor may be scheduled only now that this CTA owns its TMEM columns (a
+  // successor CTA allocating first, then waiting for this grid, would deadlock the SM's allocator); everything above ran
+  // while the predecessor was still draining, nothing below may start before it has completed
+  lb_pdl_trigger();
+  lb_pdl_wait();
 
   if (warp == 0) {
     if (tc::elect_one()) {
@@ -319,6 +329,7 @@ template <int TC>
 __global__ void __launch_bounds__(256, 2) k_wgrad_reduce_tile(const float* __restrict__ part, float* __restrict__ dwn, const float* __restrict__ w,
                                                            int splits, size_t split_stride, int taps, int d_c, int g_c, int m_chunks,
                                                            int units, double* __restrict__ dot_out, double* __restrict__ stat_work) {
+  lb_pdl_enter();
   constexpr int kChunk = TC ? TC : kRedTaps;
   __shared__ float tile_s[8][32][kChunk + 1];
   __shared__ double scratch[32];
@@ -395,6 +406,7 @@ __global__ void __launch_bounds__(256, 2) k_wgrad_reduce_tile(const float* __res
 __global__ void __launch_bounds__(256) k_wgrad_reduce_tap(const float* __restrict__ part, float* __restrict__ dwn, const float* __restrict__ w,
                                                           int splits, size_t split_stride, int taps, int d_c, int g_c, int m_chunks,
                                                           int units, double* __restrict__ dot_out, double* __restrict__ stat_work) {
+  lb_pdl_enter();
   __shared__ float sums[8][32];
   __shared__ double scratch[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -658,7 +670,7 @@ extern "C" int lb_wgrad_tc(const void* gathered_bf16, const void* dense_bf16, fl
     p.ngroups = ng;
     dim3 grid(pl.m_tiles * pl.n_tiles, ng, (unsigned)pl.splits);
     LB_REQUIRE(grid.z <= 65535);
-    k_wgrad_halo<<<grid, 192, pl.smem_bytes, lb_s(s)>>>(maps, p);
+    lb_launch(k_wgrad_halo, grid, 192, pl.smem_bytes, lb_s(s), maps, p);
     LB_LAUNCH_CHECK();
   } else {
     WgParams p;
@@ -671,7 +683,7 @@ extern "C" int lb_wgrad_tc(const void* gathered_bf16, const void* dense_bf16, fl
     p.part = work; p.split_stride = numel;
     dim3 grid(pl.m_tiles * pl.n_tiles, pl.taps, (unsigned)pl.splits);
     LB_REQUIRE(grid.y <= 65535 && grid.z <= 65535);
-    k_wgrad_tc<<<grid, 192, pl.smem_bytes, lb_s(s)>>>(maps, p);
+    lb_launch(k_wgrad_tc, grid, 192, pl.smem_bytes, lb_s(s), maps, p);
     LB_LAUNCH_CHECK();
   }
   const int m_chunks = (g->in_c + 31) / 32;
@@ -682,7 +694,7 @@ extern "C" int lb_wgrad_tc(const void* gathered_bf16, const void* dense_bf16, fl
   long long rblocks = per_tap ? units : (units + 7) / 8;
   if (rblocks > LB_SMS * 8) rblocks = LB_SMS * 8;       // <= the statistics workspace's grid bound
 #define LB_WG_REDUCE(KERNEL)                                                                                                   \
-  KERNEL<<<(unsigned)rblocks, 256, 0, lb_s(s)>>>(work, dwn, w, pl.splits, numel, pl.taps, g->out_c, g->in_c, m_chunks, (int)units, \
+  lb_launch(KERNEL, (unsigned)rblocks, 256, 0, lb_s(s), work, dwn, w, pl.splits, numel, pl.taps, g->out_c, g->in_c, m_chunks, (int)units, \
                                                  dot_out, stat_work)
   if (per_tap) LB_WG_REDUCE(k_wgrad_reduce_tap);
   else if (pl.taps == 1) LB_WG_REDUCE(k_wgrad_reduce_tile<1>);

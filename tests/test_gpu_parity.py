@@ -436,3 +436,41 @@ def test_layout_round_trip(b, c, h, w):
     assert torch.equal(cl.permute(0, 2, 3, 1).contiguous(), x.permute(0, 2, 3, 1).contiguous())
     back = ops.to_nchw(cl)
     assert back.is_contiguous() and torch.equal(back, x)
+
+
+def test_programmatic_dependent_launch_is_bit_identical_to_serialised_launches(golden):
+    """Every kernel of the library is launched with the programmatic-stream-serialization attribute and waits for its
+    predecessor on the device (griddepcontrol.wait) before touching global memory.  A kernel that read or wrote anything
+    ahead of that wait would race with its predecessor; the forward pass is deterministic, so the two launch modes must
+    agree bit for bit (images, logits, power-iteration vectors); the backward pass (whose norm / gate column sums use
+    float atomics) must agree to rounding noise."""
+    from locate_b200 import _lib
+    r = golden("step_s32_w2_b3.pt")
+    z, real = dev(r["z"]), dev(r["real"])
+    outs = []
+    was = _lib.set_pdl(True)
+    try:
+        for pdl in (False, True, True):
+            _lib.set_pdl(pdl)
+            L.config.reset()
+            L.configure(PRECISION="bf16", **r["overrides"])
+            gen, dis = L.Generator().to(DEV), L.Discriminator().to(DEV)
+            gen.load_state_dict(r["g_state"])
+            dis.load_state_dict(r["d_state"])
+            gen.noise = dev(r["const_noise"])
+            img = gen(z)
+            logit = dis(img)
+            logit.mean().backward()
+            torch.cuda.synchronize()
+            big = [p.grad.clone() for p in list(gen.parameters()) + list(dis.parameters())
+                   if p.grad is not None and p.dim() >= 2 and min(p.shape[:2]) > 4]
+            outs.append((img.detach().clone(), logit.detach().clone(), big,
+                         {k: v.clone() for k, v in dis.state_dict().items() if k.endswith(("_u", "_v"))}))
+    finally:
+        _lib.set_pdl(was)
+    for other in outs[1:]:
+        assert torch.equal(outs[0][0], other[0]) and torch.equal(outs[0][1], other[1])
+        assert all(torch.equal(a, b) for a, b in zip(outs[0][3].values(), other[3].values()))
+        assert len(other[2]) == len(outs[0][2]) > 10
+        for a, b in zip(outs[0][2], other[2]):
+            assert float((a - b).norm()) <= 1e-3 * float(a.norm()) + 1e-12
