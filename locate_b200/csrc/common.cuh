@@ -273,6 +273,39 @@ __device__ __forceinline__ void lb_roottanh_both(float x, float& f, float& df) {
   f = r4 * th;
   df = fmaf(2.0f * q, s2, x * th) * r4 * (0.5f * lb_rcp_fast(q));
 }
+// ---- bf16-storage variants ------------------------------------------------------------------------------------------
+// When the result is rounded to bf16 on its way to HBM (relative rounding error 2^-9), the few-ulp formulation above is
+// wasted work: 5 MUFU operations and ~40 instructions per element made the normalisation pass that emits RootTanh(y) and
+// RootTanh'(y) run at a third of the HBM rate (ncu: 2.3 TB/s).  These are the GEMM epilogue's formulas (conv_tc2.cu):
+// tanh.approx (relative error 2^-11), one rsqrt and one sqrt shared by function and derivative -- 3 MUFU operations.
+// sech^2 = 1 - tanh^2 carries twice tanh.approx's absolute error, harmless while the term matters (|x| < 4.5); beyond
+// that it contributes < 0.5 % of RootTanh' and is dropped (the reference's own 1/cosh^2 underflows to 0 for |x| > 44).
+__device__ __forceinline__ float lb_tanh_approx(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lb_rsqrt_approx(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lb_sqrt_approx(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lb_roottanh_fast(float x) {
+  return lb_sqrt_approx(lb_sqrt_approx(fmaf(x, x, 1.0f))) * lb_tanh_approx(x);
+}
+__device__ __forceinline__ void lb_roottanh_both_fast(float x, float& f, float& df) {
+  const float th = lb_tanh_approx(x);
+  const float q = fmaf(x, x, 1.0f);
+  const float rs = lb_rsqrt_approx(q);                                 // q^(-1/2)
+  const float q34 = rs * lb_sqrt_approx(rs);                           // q^(-3/4)
+  const float s2 = fabsf(x) > 4.5f ? 0.0f : fmaf(-th, th, 1.0f);
+  f = q * q34 * th;                                                    // q^(1/4) tanh
+  df = fmaf(q, s2, 0.5f * x * th) * q34;
+}
+__device__ __forceinline__ float lb_roottanh_grad_fast(float x) { float f, df; lb_roottanh_both_fast(x, f, df); return df; }
+// chosen by the storage type the result is rounded to: fp32 keeps the few-ulp formulas (golden-fixture tier)
+template <typename T> __device__ __forceinline__ float lb_roottanh_as(float x);
+template <> __device__ __forceinline__ float lb_roottanh_as<float>(float x) { return lb_roottanh(x); }
+template <> __device__ __forceinline__ float lb_roottanh_as<lb_bf16>(float x) { return lb_roottanh_fast(x); }
+template <typename T> __device__ __forceinline__ float lb_roottanh_grad_as(float x);
+template <> __device__ __forceinline__ float lb_roottanh_grad_as<float>(float x) { return lb_roottanh_grad(x); }
+template <> __device__ __forceinline__ float lb_roottanh_grad_as<lb_bf16>(float x) { return lb_roottanh_grad_fast(x); }
+template <typename T> __device__ __forceinline__ void lb_roottanh_both_as(float x, float& f, float& df);
+template <> __device__ __forceinline__ void lb_roottanh_both_as<float>(float x, float& f, float& df) { lb_roottanh_both(x, f, df); }
+template <> __device__ __forceinline__ void lb_roottanh_both_as<lb_bf16>(float x, float& f, float& df) { lb_roottanh_both_fast(x, f, df); }
 __device__ __forceinline__ float lb_roottanh_g(float x, float inv_growth) {
   float th, s2;
   lb_tanh_sech2(x, th, s2);

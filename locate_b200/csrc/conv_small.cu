@@ -53,15 +53,14 @@ __device__ __forceinline__ bool small_src(int mode, int stride, int sh, int pad,
 }
 
 // ---- narrow INPUT (in_c <= 4): forward of the stem layers, input gradient of a wide -> 3 layer -------------------
-// NCH x 16 output columns per thread.  Shared weight wsm[tap][k][16*NCH] holds alpha * W (and, for a concat, identity
-// columns that copy the input), bsm the bias per column.
-template <int NCH, typename TO>
+// NC output columns per thread (4 for the RGB -> RGB layers, else a multiple of 16).  Shared weight wsm[tap][k][NC] holds
+// alpha * W (and, for a concat, identity columns that copy the input), bsm the bias per column.
+template <int NC, typename TO>
 __global__ void __launch_bounds__(SMALL_THREADS) k_small_narrow_in(const SmallP p) {
   lb_pdl_enter();
   const float* p_in = reinterpret_cast<const float*>(p.in);
   TO* p_out = reinterpret_cast<TO*>(p.out);
   const TO* p_xpre = reinterpret_cast<const TO*>(p.xpre);
-  constexpr int NC = 16 * NCH;
   extern __shared__ float4 sm4[];
   float* wsm = reinterpret_cast<float*>(sm4);
   const int taps = p.kh * p.kw;
@@ -260,14 +259,17 @@ extern "C" int lb_conv_small(const void* in, const float* w, const float* alpha,
     if (p.cat) LB_REQUIRE(p.pointwise && growth_in == 0 && growth_out == 0 && g->ld_out >= g->in_c + g->out_c);
     const int cols = g->out_c + (p.cat ? g->in_c : 0);
     if (cols > 64) return LB_EUNSUPPORTED;
-    const int nch = (cols + 15) / 16;
-    const size_t smem = ((size_t)taps * g->in_c * 16 * nch + 16 * nch) * sizeof(float);
+    // columns per thread: 4 for an RGB -> RGB layer (16 accumulators and 4 weight loads per input value for 3 live
+    // columns made the 5x5 / stride-2 image convs instruction-bound at 0.3 TB/s), else whole 16-column groups
+    const int nc = cols <= 4 ? 4 : (cols + 15) / 16 * 16;
+    const size_t smem = ((size_t)taps * g->in_c * nc + nc) * sizeof(float);
     LB_DISPATCH(wide_dtype, T, {
-      switch (nch) {
-        case 1: lb_launch(k_small_narrow_in<1, T>, grid, SMALL_THREADS, smem, lb_s(s), p); break;
-        case 2: lb_launch(k_small_narrow_in<2, T>, grid, SMALL_THREADS, smem, lb_s(s), p); break;
-        case 3: lb_launch(k_small_narrow_in<3, T>, grid, SMALL_THREADS, smem, lb_s(s), p); break;
-        default: lb_launch(k_small_narrow_in<4, T>, grid, SMALL_THREADS, smem, lb_s(s), p); break;
+      switch (nc) {
+        case 4: lb_launch(k_small_narrow_in<4, T>, grid, SMALL_THREADS, smem, lb_s(s), p); break;
+        case 16: lb_launch(k_small_narrow_in<16, T>, grid, SMALL_THREADS, smem, lb_s(s), p); break;
+        case 32: lb_launch(k_small_narrow_in<32, T>, grid, SMALL_THREADS, smem, lb_s(s), p); break;
+        case 48: lb_launch(k_small_narrow_in<48, T>, grid, SMALL_THREADS, smem, lb_s(s), p); break;
+        default: lb_launch(k_small_narrow_in<64, T>, grid, SMALL_THREADS, smem, lb_s(s), p); break;
       }
     });
   } else {

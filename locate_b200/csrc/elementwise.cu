@@ -98,6 +98,9 @@ static int launch_binary(const void* a, const void* b, void* y, size_t n, F f, i
 struct RootTanh4 { __device__ float operator()(float x) const { return lb_roottanh(x); } };
 struct RootTanhG { float ig; __device__ float operator()(float x) const { return lb_roottanh_g(x, ig); } };
 struct RootTanhBwd4 { __device__ float operator()(float x, float g) const { return g * lb_roottanh_grad(x); } };
+// bf16 storage: the GEMM epilogue's 3-MUFU formulas (common.cuh), the result is rounded to bf16 anyway
+struct RootTanh4Fast { __device__ float operator()(float x) const { return lb_roottanh_fast(x); } };
+struct RootTanhBwd4Fast { __device__ float operator()(float x, float g) const { return g * lb_roottanh_grad_fast(x); } };
 struct RootTanhBwdG { float ig; __device__ float operator()(float x, float g) const { return g * lb_roottanh_grad_g(x, ig); } };
 struct TanhF { __device__ float operator()(float x) const { return tanhf(x); } };
 struct TanhB { __device__ float operator()(float y, float g) const { return g * (1.0f - y * y); } };
@@ -109,11 +112,13 @@ struct MulF { __device__ float operator()(float a, float b) const { return a * b
 
 extern "C" int lb_roottanh_fwd(const void* x, void* y, size_t n, int growth, int dtype, lb_stream_t s) {
   LB_REQUIRE(growth >= 1);
+  if (growth == 4 && dtype == LB_BF16) return launch_unary(x, y, n, RootTanh4Fast{}, dtype, s);
   if (growth == 4) return launch_unary(x, y, n, RootTanh4{}, dtype, s);
   return launch_unary(x, y, n, RootTanhG{1.0f / growth}, dtype, s);
 }
 extern "C" int lb_roottanh_bwd(const void* x, const void* g, void* dx, size_t n, int growth, int dtype, lb_stream_t s) {
   LB_REQUIRE(growth >= 1);
+  if (growth == 4 && dtype == LB_BF16) return launch_binary(x, g, dx, n, RootTanhBwd4Fast{}, dtype, s);
   if (growth == 4) return launch_binary(x, g, dx, n, RootTanhBwd4{}, dtype, s);
   return launch_binary(x, g, dx, n, RootTanhBwdG{1.0f / growth}, dtype, s);
 }
@@ -296,6 +301,62 @@ __global__ void k_gate_bwd(const T* __restrict__ x, const T* __restrict__ y, con
   }
 }
 
+// broadcast gate (feature attention: y is [B][C]), vector form: a thread owns one 16-byte channel vector (8 bf16 / 4 fp32)
+// and walks the CTA's pixel chunk; dy[b][c] = gamma * sum_p x*g is reduced over the CTA's pixel lanes in shared memory
+// before one atomic per (b, c).  (The scalar kernel above keeps 2 bytes per thread in flight: 1.5 TB/s.)
+template <typename T>
+__global__ void __launch_bounds__(256) k_gate_bwd_bcast_v(const T* __restrict__ x, const T* __restrict__ y, const float* __restrict__ gamma,
+                                                         const T* __restrict__ g, T* __restrict__ dx, float* __restrict__ dy_bcast,
+                                                         float* __restrict__ dgamma, int pixels, int channels, int chunk, int cv, int tp,
+                                                         int strict) {
+  lb_pdl_enter();
+  constexpr int N = LbV<T>::N;
+  extern __shared__ float s_dy[];                   // [tp][channels]
+  __shared__ float scratch[32];
+  const float gm = __ldg(gamma);
+  const int cl = threadIdx.x % cv, pl = threadIdx.x / cv;
+  const int b = blockIdx.y;
+  const int p0 = blockIdx.x * chunk, p1 = min(pixels, p0 + chunk);
+  const size_t base = (size_t)b * pixels * channels + (size_t)cl * N;
+  float acc_gamma = 0.0f;
+  if (pl < tp) {
+    float yb[N], fac[N], acc[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      yb[k] = lb_ld1(y + (size_t)b * channels + cl * N + k);
+      fac[k] = fmaf(gm, yb[k], 1.0f);
+      acc[k] = 0.0f;
+    }
+#pragma unroll 2
+    for (int p = p0 + pl; p < p1; p += tp) {
+      const size_t i = base + (size_t)p * channels;
+      float xv[N], gv[N];
+      lb_ldv(x + i, xv);
+      lb_ldv(g + i, gv);
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        const float xg = xv[k] * gv[k];
+        acc[k] += xg;
+        acc_gamma = fmaf(xg, strict ? xv[k] : yb[k], acc_gamma);
+        gv[k] *= fac[k];                             // dx
+      }
+      lb_stv(dx + i, gv);
+    }
+#pragma unroll
+    for (int k = 0; k < N; ++k) s_dy[pl * channels + cl * N + k] = acc[k];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < channels; c += blockDim.x) {
+    float t = 0.0f;
+    for (int q = 0; q < tp; ++q) t += s_dy[q * channels + c];
+    atomicAdd(dy_bcast + (size_t)b * channels + c, t * gm);
+  }
+  if (dgamma) {
+    const float tot = lb_block_sum(acc_gamma, scratch);
+    if (threadIdx.x == 0) atomicAdd(dgamma, tot);
+  }
+}
+
 // full-shape gate (y has the shape of x): everything is elementwise except d-gamma, so the kernel streams 4-vectors and
 // reduces one scalar per CTA
 template <typename T>
@@ -337,6 +398,17 @@ static int gate_bwd_t(const T* x, const T* y, const float* gamma, const T* g, T*
   const size_t n = (size_t)batch * pixels * channels;
   if (!y_bcast && !(n % LbV<T>::N) && lb_vec_ok(x) && lb_vec_ok(y) && lb_vec_ok(g) && lb_vec_ok(dx) && lb_vec_ok(dy)) {
     lb_launch(k_gate_bwd4<T>, lb_grid_1d(n / LbV<T>::N, 256, 8), 256, 0, lb_s(s), x, y, gamma, g, dx, dy, dgamma, n / LbV<T>::N, strict_reference);
+    LB_LAUNCH_CHECK();
+    return LB_OK;
+  }
+  if (y_bcast && !(channels % LbV<T>::N) && channels / LbV<T>::N <= 256 && lb_vec_ok(x) && lb_vec_ok(g) && lb_vec_ok(dx)) {
+    const int cv = channels / LbV<T>::N, tp = 256 / cv;
+    int chunks = (LB_SMS * 4 + batch - 1) / batch;
+    int chunk = (pixels + chunks - 1) / chunks;
+    if (chunk < 4 * tp) chunk = 4 * tp;
+    chunks = (pixels + chunk - 1) / chunk;
+    lb_launch(k_gate_bwd_bcast_v<T>, dim3(chunks, batch), 256, (size_t)tp * channels * sizeof(float), lb_s(s), x, y, gamma, g, dx, dy_bcast,
+              dgamma, pixels, channels, chunk, cv, tp, strict_reference);
     LB_LAUNCH_CHECK();
     return LB_OK;
   }

@@ -93,11 +93,11 @@ __global__ void __launch_bounds__(256) k_norm_apply4(const T* __restrict__ x, co
     if (kAct) {
       if (dact) {                               // RootTanh and its derivative from shared intermediates
 #pragma unroll
-        for (int k = 0; k < N; ++k) lb_roottanh_both(v[k], v[k], gn[k]);
+        for (int k = 0; k < N; ++k) lb_roottanh_both_as<T>(v[k], v[k], gn[k]);
         lb_stv(dact + N * i, gn);
       } else {
 #pragma unroll
-        for (int k = 0; k < N; ++k) v[k] = lb_roottanh(v[k]);
+        for (int k = 0; k < N; ++k) v[k] = lb_roottanh_as<T>(v[k]);
       }
       lb_stv(act + N * i, v);
     }

@@ -22,6 +22,11 @@ __device__ __forceinline__ void online1(float& m, float& l, float v) {
   l = l * __expf(m - nm) + __expf(v - nm);
   m = nm;
 }
+__device__ __forceinline__ void online4(float& m, float& l, float a, float b, float c, float d) {
+  const float nm = fmaxf(fmaxf(m, fmaxf(a, b)), fmaxf(c, d));
+  l = l * __expf(m - nm) + ((__expf(a - nm) + __expf(b - nm)) + (__expf(c - nm) + __expf(d - nm)));
+  m = nm;
+}
 __device__ __forceinline__ void merge1(float& m, float& l, float m2, float l2) {
   const float nm = fmaxf(m, m2);
   const float a = (m == -INFINITY) ? 0.0f : l * __expf(m - nm);
@@ -36,7 +41,16 @@ __device__ __forceinline__ ML slab_stats(const T* __restrict__ x, size_t base, i
                                          float4 (*s_m)[kCQ], float4 (*s_l)[kCQ]) {
   float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY), l = make_float4(0.f, 0.f, 0.f, 0.f);
   if (ok) {
-    for (int p = p0 + pl; p < p1; p += kPL) {
+    // 4 pixels per step: four independent loads in flight, ONE rescale of the running sum per step (the per-pixel online
+    // update is a loop-carried chain of two exps: 128 dependent steps per thread at 64x64 left the pass latency-bound)
+    int p = p0 + pl;
+    for (; p + 3 * kPL < p1; p += 4 * kPL) {
+      const float4 v0 = lb_ld4(x + base + (size_t)p * channels), v1 = lb_ld4(x + base + (size_t)(p + kPL) * channels);
+      const float4 v2 = lb_ld4(x + base + (size_t)(p + 2 * kPL) * channels), v3 = lb_ld4(x + base + (size_t)(p + 3 * kPL) * channels);
+      online4(m.x, l.x, v0.x, v1.x, v2.x, v3.x); online4(m.y, l.y, v0.y, v1.y, v2.y, v3.y);
+      online4(m.z, l.z, v0.z, v1.z, v2.z, v3.z); online4(m.w, l.w, v0.w, v1.w, v2.w, v3.w);
+    }
+    for (; p < p1; p += kPL) {
       const float4 v = lb_ld4(x + base + (size_t)p * channels);
       online1(m.x, l.x, v.x); online1(m.y, l.y, v.y); online1(m.z, l.z, v.z); online1(m.w, l.w, v.w);
     }
@@ -92,6 +106,7 @@ __global__ void __launch_bounds__(kThreads) k_softmax_pixels_fwd(const T* __rest
   }
   if (!ok) return;
   const float4 inv = make_float4(1.0f / r.l.x, 1.0f / r.l.y, 1.0f / r.l.z, 1.0f / r.l.w);
+#pragma unroll 4
   for (int p = p0 + pl; p < p1; p += kPL) {
     const size_t i = base + (size_t)p * channels;
     const float4 v = lb_ld4(x + i);
