@@ -237,6 +237,26 @@ __host__ __device__ static inline bool lb_vec4_ok(const T* p) { return (reinterp
 template <typename T> static inline const T* lb_cp(const void* p) { return reinterpret_cast<const T*>(p); }
 template <typename T> static inline T* lb_p(void* p) { return reinterpret_cast<T*>(p); }
 
+// Column sums over the pixels of a channels-last block, vector form: thread (cl, pl) owns the 16-byte channel vector cl
+// (N = LbV<T>::N channels) and walks pixels pl, pl + tp, ...; its N partial sums are combined over the CTA's pixel lanes
+// through `s_part` ([tp][channels] floats) and every channel costs ONE atomic per CTA.  Call from all threads of the CTA
+// (`active` = this thread holds sums); contains __syncthreads.
+template <int N>
+__device__ __forceinline__ void lb_colsum_flush(const float (&acc)[N], bool active, float* s_part, int cl, int pl, int tp, int channels,
+                                                float scale, float* __restrict__ out) {
+  __syncthreads();                                   // a previous flush may still be reading s_part
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) s_part[pl * channels + cl * N + k] = acc[k];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < channels; c += blockDim.x) {
+    float t = 0.0f;
+    for (int q = 0; q < tp; ++q) t += s_part[q * channels + c];
+    atomicAdd(out + c, t * scale);
+  }
+}
+
 // ---- RootTanh scalar math (libs/activation.py:9-36), fp32 ---------------------------------
 // tanh and sech^2 from one exp(-2|x|): exact limits, no cosh overflow (the reference's 1/cosh^2 -> 0 for |x| > 44 is
 // reproduced because e underflows to 0 there).  Cost matters: several kernels evaluate this per element next to a

@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_small_narrow_in(const SmallP 
   const int sh = p.stride == 2 ? 1 : 0;
   const int gi = p.growth_in, go = p.growth_out;
   const bool vec_out = !(p.ld_out & 3) && lb_vec4_ok(p_out);
+  const bool vec16_out = NC % LbV<TO>::N == 0 && !(cols % LbV<TO>::N) && !(p.ld_out % LbV<TO>::N) && lb_vec_ok(p_out);
   const int stride_t = gridDim.x * blockDim.x;
   for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < p.pixels; pix += stride_t) {
     float acc[NC];
@@ -123,7 +124,18 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_small_narrow_in(const SmallP 
         if (n < p.out_c) acc[n] *= small_dact(lb_ld1(xr + n), go);      // no concat on this path (checked by the host)
     }
     TO* dst = p_out + (size_t)pix * p.ld_out;
-    if (vec_out) {
+    if (vec16_out) {                                   // whole 16-byte stores (8 bf16): half the store transactions of the 4-wide form
+      constexpr int V = LbV<TO>::N;
+#pragma unroll
+      for (int j = 0; j < NC / V; ++j) {
+        if (V * j < cols) {                            // cols % V == 0 on this path
+          float o[V];
+#pragma unroll
+          for (int i = 0; i < V; ++i) o[i] = acc[V * j + i];
+          lb_stv(dst + V * j, o);
+        }
+      }
+    } else if (vec_out) {
 #pragma unroll
       for (int j = 0; j < NC / 4; ++j) {
         if (4 * j + 3 < cols) lb_st4(dst + 4 * j, make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]));

@@ -187,6 +187,39 @@ __global__ void k_norm_bwd_reduce(const T* __restrict__ x, const T* __restrict__
     atomicAdd(p2 + (size_t)b * channels + c, a2);
   }
 }
+// vector form: 16-byte loads of x and g, one atomic per (b, c) and CTA
+template <typename T>
+__global__ void __launch_bounds__(256) k_norm_bwd_reduce_v(const T* __restrict__ x, const T* __restrict__ g, const float* __restrict__ stats,
+                                                          float* __restrict__ p1, float* __restrict__ p2, int pixels, int channels,
+                                                          int chunk, int cv, int tp) {
+  lb_pdl_enter();
+  constexpr int N = LbV<T>::N;
+  extern __shared__ float s_part[];
+  const float mean = __ldg(stats);
+  const int cl = threadIdx.x % cv, pl = threadIdx.x / cv;
+  const int b = blockIdx.y;
+  const int q0 = blockIdx.x * chunk, q1 = min(pixels, q0 + chunk);
+  const size_t base = (size_t)b * pixels * channels + (size_t)cl * N;
+  float a1[N], a2[N];
+#pragma unroll
+  for (int k = 0; k < N; ++k) a1[k] = a2[k] = 0.0f;
+  const bool active = pl < tp;
+  if (active) {
+#pragma unroll 2
+    for (int p = q0 + pl; p < q1; p += tp) {
+      float xv[N], gv[N];
+      lb_ldv(x + base + (size_t)p * channels, xv);
+      lb_ldv(g + base + (size_t)p * channels, gv);
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        a1[k] += gv[k];
+        a2[k] = fmaf(xv[k] - mean, gv[k], a2[k]);
+      }
+    }
+  }
+  lb_colsum_flush<N>(a1, active, s_part, cl, pl, tp, channels, 1.0f, p1 + (size_t)b * channels);
+  lb_colsum_flush<N>(a2, active, s_part, cl, pl, tp, channels, 1.0f, p2 + (size_t)b * channels);
+}
 extern "C" int lb_norm_bwd_reduce(const void* x, const void* g, const float* stats, float* p1, float* p2, int batch,
                                   int pixels, int channels, int dtype, lb_stream_t s) {
   LB_REQUIRE(x && g && stats && p1 && p2 && batch > 0 && pixels > 0 && channels > 0);
@@ -195,8 +228,21 @@ extern "C" int lb_norm_bwd_reduce(const void* x, const void* g, const float* sta
   int chunk = (pixels + chunks - 1) / chunks;
   if (chunk < sh.tp) chunk = sh.tp;
   chunks = (pixels + chunk - 1) / chunk;
-  LB_DISPATCH(dtype, T, lb_launch(k_norm_bwd_reduce<T>, dim3(chunks, batch), sh.threads, 0, lb_s(s), lb_cp<T>(x), lb_cp<T>(g), stats, p1, p2, pixels,
-                                                                                          channels, chunk, sh.tc, sh.tp));
+  LB_DISPATCH(dtype, T, {
+    constexpr int N = LbV<T>::N;
+    if (!(channels % N) && channels / N <= 256 && lb_vec_ok(lb_cp<T>(x)) && lb_vec_ok(lb_cp<T>(g))) {
+      const int cv = channels / N, tp = 256 / cv;
+      chunks = (LB_SMS * 4 + batch - 1) / batch;
+      chunk = (pixels + chunks - 1) / chunks;
+      if (chunk < 4 * tp) chunk = 4 * tp;
+      chunks = (pixels + chunk - 1) / chunk;
+      lb_launch(k_norm_bwd_reduce_v<T>, dim3(chunks, batch), 256, (size_t)tp * channels * sizeof(float), lb_s(s), lb_cp<T>(x), lb_cp<T>(g),
+                stats, p1, p2, pixels, channels, chunk, cv, tp);
+    } else {
+      lb_launch(k_norm_bwd_reduce<T>, dim3(chunks, batch), sh.threads, 0, lb_s(s), lb_cp<T>(x), lb_cp<T>(g), stats, p1, p2, pixels,
+                channels, chunk, sh.tc, sh.tp);
+    }
+  });
   LB_LAUNCH_CHECK();
   return LB_OK;
 }

@@ -63,6 +63,24 @@ __global__ void __launch_bounds__(256) k_featpool_bwd(const T* __restrict__ g, T
     lb_st1(dx + i, lb_ld1(g + ((size_t)b * q.hw + (size_t)cr * q.m + pq) * q.c_out + o) * inv);
   }
 }
+// r == 2 with 8 input channels per thread: channels c..c+7 of pixel p take outputs o = c/2 .. c/2+3 of pixel group p/2 --
+// the even ones from output pixel p/2, the odd ones from output pixel m + p/2 -- so two 4-element loads and one 8-element
+// store replace eight 2-byte gathers (the scalar kernel ran at 1 TB/s).  d_c = c_in / 8 here.
+template <typename T>
+__global__ void __launch_bounds__(256) k_featpool_bwd_r2v8(const T* __restrict__ g, T* __restrict__ dx, int n_items, const FeatPoolIdx q) {
+  lb_pdl_enter();
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_items; i += stride) {
+    int bp, c8, b, p;
+    lb_fast_divmod(q.d_c, i, bp, c8);
+    lb_fast_divmod(q.d_hw, bp, b, p);
+    const T* src = g + ((size_t)b * q.hw + (p >> 1)) * q.c_out + 4 * c8;
+    const float4 e = lb_ld4(src), o = lb_ld4(src + (size_t)q.m * q.c_out);
+    T* dst = dx + (size_t)i * 8;
+    lb_st4(dst, make_float4(0.5f * e.x, 0.5f * o.x, 0.5f * e.y, 0.5f * o.y));
+    lb_st4(dst + 4, make_float4(0.5f * e.z, 0.5f * o.z, 0.5f * e.w, 0.5f * o.w));
+  }
+}
 // generic fallbacks (r does not divide HW, or more than 2^31 items): 64-bit index arithmetic, any shape
 template <typename T>
 __global__ void k_featpool_fwd_generic(const T* __restrict__ x, T* __restrict__ y, size_t n_out, int hw, int c_in, int c_out, int r) {
@@ -128,9 +146,14 @@ template <typename T>
 static int featpool_bwd_t(const T* g, T* dx, int batch, int h, int w, int c_in, int c_out, lb_stream_t s) {
   const size_t n = (size_t)batch * h * w * c_in;
   FeatPoolIdx q;
-  if (featpool_idx(&q, batch, h, w, c_in, c_out, c_in, n) == LB_OK)
-    lb_launch(k_featpool_bwd<T>, lb_grid_1d(n, 256), 256, 0, lb_s(s), g, dx, (int)n, q);
-  else
+  if (featpool_idx(&q, batch, h, w, c_in, c_out, c_in, n) == LB_OK) {
+    if (q.r == 2 && !(c_in & 7) && lb_vec4_ok(g) && lb_vec4_ok(dx)) {
+      q.d_c = lb_make_fastdiv(c_in / 8);
+      lb_launch(k_featpool_bwd_r2v8<T>, lb_grid_1d(n / 8, 256), 256, 0, lb_s(s), g, dx, (int)(n / 8), q);
+    } else {
+      lb_launch(k_featpool_bwd<T>, lb_grid_1d(n, 256), 256, 0, lb_s(s), g, dx, (int)n, q);
+    }
+  } else
     lb_launch(k_featpool_bwd_generic<T>, lb_grid_1d(n, 256), 256, 0, lb_s(s), g, dx, n, h * w, c_in, c_out, c_in / c_out);
   LB_LAUNCH_CHECK();
   return LB_OK;
@@ -207,6 +230,50 @@ __global__ void __launch_bounds__(256) k_up2_fwd(const T* __restrict__ x, T* __r
     acc.store(y + (size_t)i * V);
   }
 }
+// The same map, one thread per SOURCE pixel: its 2x2 output pixels need the 3x3 clamped neighbourhood (9 loads instead of
+// 16, one index decode instead of four).  out[2i] = .25 x[max(i-1,0)] + .75 x[i], out[2i+1] = .75 x[i] + .25 x[min(i+1,n-1)]
+// along each axis -- lb_up2_src()'s weights in closed form.  (The per-output kernel is issue-bound: ~120 instructions per
+// 16-byte store, 68 % issue-slot utilisation at 2.6 TB/s.)
+template <typename T, int V>
+__global__ void __launch_bounds__(256) k_up2_fwd_quad(const T* __restrict__ x, T* __restrict__ y, int n_in, int h, int w, int c, const PixIdx q) {
+  lb_pdl_enter();
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_in; i += stride) {
+    int ch, ix, iy, b;
+    pix_decode(q, i, ch, ix, iy, b);              // q over (c / V, w, h)
+    const int xs[3] = {max(ix - 1, 0), ix, min(ix + 1, w - 1)};
+    const int ys[3] = {max(iy - 1, 0), iy, min(iy + 1, h - 1)};
+    const T* xb = x + (size_t)b * h * w * c + ch * V;
+    float o[2][2][V];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const T* row = xb + (size_t)ys[r] * w * c;
+      float a[V], m[V], e[V], h0[V], h1[V];
+      lb_ldv(row + (size_t)xs[0] * c, a);
+      lb_ldv(row + (size_t)xs[1] * c, m);
+      lb_ldv(row + (size_t)xs[2] * c, e);
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        h0[k] = fmaf(0.75f, m[k], 0.25f * a[k]);
+        h1[k] = fmaf(0.75f, m[k], 0.25f * e[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        if (r == 0) { o[0][0][k] = 0.25f * h0[k]; o[0][1][k] = 0.25f * h1[k]; }
+        if (r == 1) {
+          o[0][0][k] = fmaf(0.75f, h0[k], o[0][0][k]); o[0][1][k] = fmaf(0.75f, h1[k], o[0][1][k]);
+          o[1][0][k] = 0.75f * h0[k]; o[1][1][k] = 0.75f * h1[k];
+        }
+        if (r == 2) { o[1][0][k] = fmaf(0.25f, h0[k], o[1][0][k]); o[1][1][k] = fmaf(0.25f, h1[k], o[1][1][k]); }
+      }
+    }
+    T* yb = y + (((size_t)b * 2 * h + 2 * iy) * 2 * w + 2 * ix) * c + ch * V;
+    lb_stv(yb, o[0][0]);
+    lb_stv(yb + c, o[0][1]);
+    lb_stv(yb + (size_t)2 * w * c, o[1][0]);
+    lb_stv(yb + (size_t)2 * w * c + c, o[1][1]);
+  }
+}
 // weight with which source index m receives from destination index d along one axis
 __device__ __forceinline__ float lb_up2_weight(int d, int n, int m) {
   int i0, i1; float lam;
@@ -222,13 +289,11 @@ __global__ void __launch_bounds__(256) k_up2_bwd(const T* __restrict__ g, T* __r
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_in; i += stride) {
     int ch, ix, iy, b;
     pix_decode(q, i, ch, ix, iy, b);              // q over (c / V, w, h)
-    float wy[4], wx[4];
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const int dy = 2 * iy - 1 + t, dxp = 2 * ix - 1 + t;
-      wy[t] = (dy >= 0 && dy < oh) ? lb_up2_weight(dy, h, iy) : 0.0f;
-      wx[t] = (dxp >= 0 && dxp < ow) ? lb_up2_weight(dxp, w, ix) : 0.0f;
-    }
+    // closed form of lb_up2_weight over destinations 2m-1 .. 2m+2: (.25, .75, .75, .25); at the borders the clamped tap
+    // folds onto its neighbour (weight 1) and the tap outside the map is 0
+    const float wy[4] = {iy > 0 ? 0.25f : 0.0f, iy > 0 ? 0.75f : 1.0f, iy < h - 1 ? 0.75f : 1.0f, iy < h - 1 ? 0.25f : 0.0f};
+    const float wx[4] = {ix > 0 ? 0.25f : 0.0f, ix > 0 ? 0.75f : 1.0f, ix < w - 1 ? 0.75f : 1.0f, ix < w - 1 ? 0.25f : 0.0f};
+    (void)oh; (void)ow;
     const T* gb = g + (size_t)b * oh * ow * c + ch * V;
     Acc<V> acc;
 #pragma unroll
@@ -248,7 +313,7 @@ static int up2_fwd_t(const T* x, T* y, int batch, int h, int w, int c, lb_stream
   LB_REQUIRE_INT_ITEMS(n);
   constexpr int N = LbV<T>::N;
   if ((c % N) == 0 && lb_vec_ok(x) && lb_vec_ok(y))
-    lb_launch(k_up2_fwd<T, N>, lb_grid_1d(n / N, 256), 256, 0, lb_s(s), x, y, (int)(n / N), h, w, c, make_pix_idx(c / N, 2 * w, 2 * h));
+    lb_launch(k_up2_fwd_quad<T, N>, lb_grid_1d(n / 4 / N, 256), 256, 0, lb_s(s), x, y, (int)(n / 4 / N), h, w, c, make_pix_idx(c / N, w, h));
   else
     lb_launch(k_up2_fwd<T, 1>, lb_grid_1d(n, 256), 256, 0, lb_s(s), x, y, (int)n, h, w, c, make_pix_idx(c, 2 * w, 2 * h));
   LB_LAUNCH_CHECK();
