@@ -63,6 +63,13 @@ struct Tc2Params {
   int rows_per_tap, view_empty;
   int ebw, ebh, ebb;                  // 32-row sub-box of one epilogue warp
   int epi_warps;                      // 8 or 16
+  // Epilogue warp GROUPS: a tile whose column slabs need only 4 or 8 warps (<= 64 channels) leaves the others idle, and one
+  // warp's trip through a slab (accumulator wait, tcgen05.ld, ~700 dependent instructions, fence, TMA store) is a ~2.5 us
+  // latency chain whatever the tile width -- with every warp visiting every tile, that chain WAS the tile period of all
+  // layers up to 96 channels.  Groups take tiles round robin (tile t -> group t % epi_groups, accumulator t % acc_depth),
+  // so 2 or 4 tiles drain at once.
+  int epi_groups;                     // 1, 2 or 4
+  int acc_shift;                      // log2 of the TMEM accumulator ring depth (2 or 4 stages)
   int has_o32, has_o16, has_o16a, has_aux;
   int aux_bf16;                       // aux slabs are bf16 (64-byte rows) instead of fp32 (128-byte rows)
   int aux_factor;                     // aux holds the factor itself (RootTanh' precomputed by the forward pass)
@@ -364,7 +371,7 @@ __device__ __forceinline__ bool tap_live(const Tc2Params& p, const TileCoord& c,
 
 __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant__ Tc2Maps maps, const Tc2Params p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bar_full[8], bar_empty[8], bar_tfull[2], bar_tempty[2], bar_aux[kEpiWarps][2];
+  __shared__ __align__(8) uint64_t bar_full[8], bar_empty[8], bar_tfull[4], bar_tempty[4], bar_aux[kEpiWarps][2];
   __shared__ __align__(8) uint64_t bar_bfull, bar_bfree;          // resident weights: loaded / no longer read
   __shared__ __align__(8) uint64_t bar_afull[4], bar_aempty[4];   // halo mode: ring of halo tiles
   __shared__ uint32_t tmem_slot;
@@ -386,7 +393,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
   if (threadIdx.x == 0) {
     for (int a = 0; a < 4; ++a) { tc::mbar_init(&bar_afull[a], 1); tc::mbar_init(&bar_aempty[a], 1); }
     for (int s = 0; s < p.stages; ++s) { tc::mbar_init(&bar_full[s], 1); tc::mbar_init(&bar_empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { tc::mbar_init(&bar_tfull[a], 1); tc::mbar_init(&bar_tempty[a], p.epi_warps); }
+    for (int a = 0; a < 4; ++a) { tc::mbar_init(&bar_tfull[a], 1); tc::mbar_init(&bar_tempty[a], p.epi_warps / p.epi_groups); }
     for (int w = 0; w < p.epi_warps; ++w) { tc::mbar_init(&bar_aux[w][0], 1); tc::mbar_init(&bar_aux[w][1], 1); }
     tc::mbar_init(&bar_bfull, 1); tc::mbar_init(&bar_bfree, 1);
     tc::fence_barrier_init();
@@ -526,8 +533,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
           res_phase = c.phase;
           ++epochs;
         }
-        const int acc = lt & 1;
-        mbar_wait_a(bar_tempty_a + 8u * acc, (((uint32_t)lt >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
+        const int acc = lt & ((1 << p.acc_shift) - 1);
+        mbar_wait_a(bar_tempty_a + 8u * acc, (((uint32_t)lt >> p.acc_shift) & 1u) ^ 1u);   // epilogue has drained this accumulator
         tc::tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.acc_stride);
         if (p.halo) {
@@ -618,8 +625,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
     // ===================== epilogue (warps 2..) =====================
     const int ew = warp - 2;
     const int q = warp & 3;                       // TMEM lane quarter this warp may read
-    const int half = ew >> 2;                     // this warp takes slabs half, half + ngrp, ...
-    const int ngrp = p.epi_warps >> 2;
+    const int wpg = p.epi_warps / p.epi_groups;   // warps per group: a multiple of 4, so a group covers the four lane quarters
+    const int grp = ew / wpg;                     // this warp's group takes tiles grp, grp + epi_groups, ... of the CTA's list
+    const int half = (ew - grp * wpg) >> 2;       // inside its group the warp takes slabs half, half + ngrp, ...
+    const int ngrp = wpg >> 2;
+    const int tile_step = p.epi_groups * (int)gridDim.x;
     const int r0 = q * 32;                        // first tile row of this warp
     const int w_off = r0 % p.tile_w, h_off = (r0 / p.tile_w) % p.tile_h, b_off = r0 / (p.tile_w * p.tile_h);
     uint8_t* ebase = smem + p.epi_base + (uint32_t)ew * p.epi_per_warp;
@@ -634,7 +644,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
     const int row16 = p.slab * 2;                 // bytes per bf16 staging row
 
     // aux prefetch runs one job ahead of the consumer
-    int a_tile = blockIdx.x, a_slab = half;
+    int a_tile = blockIdx.x + grp * (int)gridDim.x, a_slab = half;
     uint32_t a_issued = 0, a_done = 0;
     auto aux_advance = [&]() {                    // skip to the next (tile, slab) this warp owns
       while (a_tile < p.total_tiles) {
@@ -643,7 +653,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
         const int n0 = nt * p.block_n;
         const int nsl = (min(p.block_n, p.out_c - n0) + p.slab - 1) / p.slab;
         if (a_slab < nsl) return;
-        a_tile += gridDim.x; a_slab = half;
+        a_tile += tile_step; a_slab = half;
       }
     };
     auto aux_issue = [&]() {
@@ -661,13 +671,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_conv_tc2(const __grid_constant_
     };
     if (p.has_aux) aux_issue();
 
-    int lt = 0;
+    int lt = grp;
     bool stores_pending = false;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+    for (int tile = blockIdx.x + grp * (int)gridDim.x; tile < p.total_tiles; tile += tile_step, lt += p.epi_groups) {
       const TileCoord c = decode_tile(p, tile);
-      const int acc = lt & 1;
+      const int acc = lt & ((1 << p.acc_shift) - 1);
       const int nsl = (min(p.block_n, p.out_c - c.n0) + p.slab - 1) / p.slab;
-      mbar_wait_a(bar_tfull_a + 8u * acc, ((uint32_t)lt >> 1) & 1u);
+      mbar_wait_a(bar_tfull_a + 8u * acc, ((uint32_t)lt >> p.acc_shift) & 1u);
       tc::tc_fence_after();
       bool released = false;
       for (int slab = half; slab < nsl; slab += ngrp) {
@@ -949,11 +959,19 @@ extern "C" int lb_conv_tc_gemm_ex(const void* in_bf16, const void* w_packed, con
     static const int env_slab = getenv("LB_TC2_SLAB") ? atoi(getenv("LB_TC2_SLAB")) : 0;
     const int bn1 = (g->out_c + 15) / 16 * 16;              // the single channel tile this applies to
     if (!out32 && (!aux || p.aux_bf16) && g->out_c <= 256 && env_slab != 32) {
-      int best = kSlab, best_cols = kSlab * ((((bn1 + kSlab - 1) / kSlab) + 3) / 4);
+      // Single-tap layers (their tile period is the epilogue's latency chain): first the width that lets the most warp groups
+      // work on different tiles (1 slab: 4 groups, 2 slabs: 2), then the fewest columns per warp.  Multi-tap layers are
+      // paced by the MMA-issuing thread and want their shared memory for halo stages / resident weights (3x3 48 -> 48 lost
+      // its resident weights to 24-column staging and ran 18 % slower): fewest columns per warp, as before.
+      const int taps_phase = g->mode == 1 ? ((g->kh + p.sp - 1) / p.sp) * ((g->kw + p.sp - 1) / p.sp) : g->kh * g->kw;
+      const bool by_groups = taps_phase == 1;
+      auto groups_of = [&](int nsl) { return !by_groups ? 1 : nsl <= 1 ? 4 : nsl == 2 ? 2 : 1; };
+      int best = kSlab, best_grp = groups_of((bn1 + kSlab - 1) / kSlab), best_cols = kSlab * ((((bn1 + kSlab - 1) / kSlab) + 3) / 4);
       const int cand[2] = {24, 16};
       for (int i = 0; i < 2; ++i) {
-        const int cols = cand[i] * ((((bn1 + cand[i] - 1) / cand[i]) + 3) / 4);
-        if (cols < best_cols) { best = cand[i]; best_cols = cols; }
+        const int nsl = (bn1 + cand[i] - 1) / cand[i];
+        const int cols = cand[i] * ((nsl + 3) / 4), grp = groups_of(nsl);
+        if (grp > best_grp || (grp == best_grp && cols < best_cols)) { best = cand[i]; best_grp = grp; best_cols = cols; }
       }
       p.slab = best;
       if (env_slab == 16 || env_slab == 24) p.slab = env_slab;
@@ -1062,7 +1080,20 @@ extern "C" int lb_conv_tc_gemm_ex(const void* in_bf16, const void* w_packed, con
   }
   p.block_n = bn; p.n_tiles = (g->out_c + bn - 1) / bn; p.stages = stages;
   p.acc_stride = ((bn + p.slab - 1) / p.slab * p.slab + 31) / 32 * 32;   // whole slabs, so that exact-width loads stay inside
-  p.tmem_cols = (uint32_t)pow2_ceil(2 * p.acc_stride < 32 ? 32 : 2 * p.acc_stride);
+  // epilogue warp groups / accumulator ring depth (Tc2Params::epi_groups): only for a single channel tile whose slabs leave
+  // whole groups of 4 warps idle; the ring is 4 deep then, so that the MMA warp stays ahead of every group
+  {
+    static const int env_groups = getenv("LB_TC2_GROUPS") ? atoi(getenv("LB_TC2_GROUPS")) : 4;
+    const int nsl = (bn + p.slab - 1) / p.slab;
+    int groups = p.n_tiles == 1 ? p.epi_warps / (4 * nsl) : 1;
+    groups = groups >= 4 ? 4 : groups >= 2 ? 2 : 1;
+    if (groups > env_groups) groups = env_groups < 1 ? 1 : env_groups;
+    if (groups == 3) groups = 2;
+    p.acc_shift = groups > 1 ? 2 : 1;
+    if ((p.acc_stride << p.acc_shift) > 512) { p.acc_shift = 1; if (groups > 2) groups = 2; }
+    p.epi_groups = groups;
+  }
+  p.tmem_cols = (uint32_t)pow2_ceil((p.acc_stride << p.acc_shift) < 32 ? 32 : (p.acc_stride << p.acc_shift));
   p.epi_base = (uint32_t)(stages * stage_bytes) + (uint32_t)p.a_stages * p.a_stage_bytes + (p.resident ? (uint32_t)(((g->mode == 1 ? ((g->kh + p.sp - 1) / p.sp) * ((g->kw + p.sp - 1) / p.sp) : g->kh * g->kw)) * p.kchunks) * p.b_tile_bytes : 0u);
   p.total_tiles = p.tiles_w * p.tiles_h * p.tiles_b * p.n_tiles * p.sp * p.sp;
   static const int env_phase_inner = getenv("LB_TC2_PHASE_INNER") ? atoi(getenv("LB_TC2_PHASE_INNER")) : 1;
