@@ -235,6 +235,15 @@ int lb_gfull_wgrad(const void* in, const void* g, float* dw, int batch, int pixe
 int lb_conv_tc_supported(const lb_conv_geom* g);
 size_t lb_conv_tc_packed_elems(const lb_conv_geom* g);
 int lb_conv_tc_pack(const float* w, void* packed, const lb_conv_geom* g, lb_stream_t stream);
+/* Every weight pack of a model in one launch (the optimizer moves all weights at once, so all packs go stale at once; the
+ * reference re-reads its fp32 weights in every conv call, conv.py:14-20, and has no counterpart).  The host fills one
+ * opaque record of lb_pack_rec_bytes() bytes per (weight, direction) with lb_pack_rec_fill (returns the record's item
+ * count, < 0 on error), uploads the records and a list of int pairs (record index, first item) covering every record in
+ * chunks of lb_pack_chunk_items() items, and calls lb_conv_tc_pack_batched whenever the weights have moved. */
+int lb_pack_rec_bytes(void);
+int lb_pack_chunk_items(void);
+int lb_pack_rec_fill(const float* w, void* packed, const lb_conv_geom* g, void* rec_host);
+int lb_conv_tc_pack_batched(const void* recs_dev, const void* chunks_dev, int n_chunks, lb_stream_t stream);
 int lb_conv_tc_gemm(const void* in_bf16, const void* w_packed, const float* alpha, const float* bias, float* out,
                     const lb_conv_geom* g, lb_stream_t stream);
 /* Same with a caller-provided workspace of lb_conv_tc_workspace_bytes(g) bytes (0 for most shapes): weight-bound layers

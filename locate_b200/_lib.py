@@ -70,6 +70,10 @@ _SIGNATURES = {
     "lb_conv_tc_supported": ([POINTER(ConvGeom)], c_int),
     "lb_conv_tc_packed_elems": ([POINTER(ConvGeom)], c_size_t),
     "lb_conv_tc_pack": ([P, P, POINTER(ConvGeom), P], c_int),
+    "lb_pack_rec_bytes": ([], c_int),
+    "lb_pack_chunk_items": ([], c_int),
+    "lb_pack_rec_fill": ([P, P, POINTER(ConvGeom), P], c_int),
+    "lb_conv_tc_pack_batched": ([P, P, c_int, P], c_int),
     "lb_conv_tc_gemm": ([P, P, P, P, P, POINTER(ConvGeom), P], c_int),
     "lb_conv_tc_workspace_bytes": ([POINTER(ConvGeom)], c_size_t),
     "lb_conv_tc_gemm_ws": ([P, P, P, P, P, POINTER(ConvGeom), P, c_size_t, c_int, P], c_int),

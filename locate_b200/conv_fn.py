@@ -85,21 +85,85 @@ def power_iterate(w_bar, u, v, spec):
     return sigma
 
 
+class PackEpoch(list):
+    """[counter] of one optimizer arena (optim.Nadam bumps it in step()); carries the arena's pack plan."""
+    plan = None
+
+
+class _PackPlan:
+    """Every bf16 weight pack of one optimizer arena, re-packed by ONE launch (lb_conv_tc_pack_batched) when the
+    optimizer has moved the weights: entries are registered the first time a (weight, direction) is packed, the
+    device tables are built outside CUDA-graph capture, and the pack buffers are reused step after step."""
+
+    def __init__(self):
+        self.entries = []              # [weakref(w_bar), tag, ent] with ent = [key, pk, geom copy, w data_ptr in the table]
+        self.tables = None
+
+    def register(self, w_bar, tag, ent):
+        import weakref
+        self.entries.append((weakref.ref(w_bar), tag, ent))
+        self.tables = None
+
+    def _build(self, dev):
+        lib = _lib.lib()
+        rec_bytes, chunk = lib.lb_pack_rec_bytes(), lib.lb_pack_chunk_items()
+        live = [(r, t, e) for r, t, e in self.entries if r() is not None]
+        self.entries = live
+        buf = ctypes.create_string_buffer(rec_bytes * len(live))
+        chunks = []
+        for i, (ref, _tag, ent) in enumerate(live):
+            w = ref()
+            items = lib.lb_pack_rec_fill(ptr(w), ptr(ent[1]), ctypes.byref(ent[2]), ctypes.addressof(buf) + i * rec_bytes)
+            if items < 0:
+                raise _lib.LocateLibraryError("lb_pack_rec_fill failed")
+            ent[3] = w.data_ptr()
+            chunks.extend((i, first) for first in range(0, items, chunk))
+        import numpy as np
+        self.tables = (torch.from_numpy(np.frombuffer(buf.raw, dtype=np.uint8).copy()).to(dev),
+                       torch.tensor(chunks, dtype=torch.int32).to(dev), len(chunks))
+
+    def repack_all(self, epoch, dev):
+        """False when the batched launch cannot run now (tables to (re)build while a CUDA graph is being captured)."""
+        stale_table = self.tables is None or any(r() is None or r().data_ptr() != e[3] for r, _t, e in self.entries)
+        if stale_table:
+            if torch.cuda.is_current_stream_capturing():
+                return False
+            self._build(dev)
+        if not self.entries:
+            return False
+        recs, chunks, n_chunks = self.tables
+        call("lb_conv_tc_pack_batched", ptr(recs), ptr(chunks), n_chunks)
+        for ref, _tag, ent in self.entries:
+            w = ref()
+            ent[0] = (_PACK_EPOCH[0], epoch[0], w._version, w.data_ptr())
+        return True
+
+
 def _packed_weight(w_bar, g, tag):
     """bf16 [tap][n][k] copy of the master weight for geometry g (cached per weight version)."""
     epoch = getattr(w_bar, "_lb_epoch", _PACK_EPOCH)       # per-optimizer counter when the weight lives in a Nadam arena
     key = (_PACK_EPOCH[0], epoch[0], w_bar._version, w_bar.data_ptr())
     cache = getattr(w_bar, "_lb_pack", None)
-    if cache is None or cache[0] != key:
-        cache = (key, {})
-        w_bar._lb_pack = cache
-    pk = cache[1].get(tag)
-    if pk is None:
+    if cache is None:
+        cache = w_bar._lb_pack = {}
+    ent = cache.get(tag)
+    if ent is not None and ent[0] == key:
+        return ent[1]
+    plan = None
+    if isinstance(epoch, PackEpoch):
+        plan = epoch.plan
+        if plan is None:
+            plan = epoch.plan = _PackPlan()
+    if ent is None:
         n = _lib.lib().lb_conv_tc_packed_elems(ctypes.byref(g))
-        pk = torch.empty(n, dtype=torch.bfloat16, device=w_bar.device)
-        call("lb_conv_tc_pack", ptr(w_bar), ptr(pk), g)
-        cache[1][tag] = pk
-    return pk
+        ent = cache[tag] = [None, torch.empty(n, dtype=torch.bfloat16, device=w_bar.device), ConvGeom.from_buffer_copy(g), 0]
+        if plan is not None:
+            plan.register(w_bar, tag, ent)
+    elif plan is not None and plan.repack_all(epoch, w_bar.device) and ent[0] == key:
+        return ent[1]                  # the whole arena was re-packed by one launch
+    call("lb_conv_tc_pack", ptr(w_bar), ptr(ent[1]), g)
+    ent[0] = key
+    return ent[1]
 
 
 def _uv_extra(pre_sigma, u):

@@ -16,6 +16,7 @@
 //   epilogue, which reads TMEM with tcgen05.ld (lane = row) and writes fp32 rows.
 // Warp roles (192 threads): 0 = TMA producer, 1 = TMEM alloc + MMA issuer, 2-5 = epilogue.
 #include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -325,6 +326,77 @@ extern "C" int lb_conv_tc_pack(const float* w, void* packed, const lb_conv_geom*
     lb_launch(k_pack_weight<false>, lb_grid_1d((size_t)items, 256), 256, 0, lb_s(s), w, reinterpret_cast<__nv_bfloat16*>(packed), g->kh, g->kw,
                                                                              g->out_c, g->in_c, kpad, g->w_sk, g->w_sn, g->w_sty,
                                                                              g->w_stx, (int)items, lb_make_fastdiv(kpad));
+  LB_LAUNCH_CHECK();
+  return LB_OK;
+}
+
+// ---- every weight pack of a model in ONE launch ----------------------------------------------------------------------
+// The optimizer moves all weights of a model at once, so all of its packs go stale at once: ~125 k_pack_weight launches
+// of a few microseconds each per step (the launch-bound share of a step at the reference's own batch sizes).  The host
+// keeps one record per (weight, direction) in a device table plus a list of (record, first item) chunks; CTA = chunk.
+namespace {
+struct PackRec {
+  const float* w; __nv_bfloat16* out;
+  long long w_sk, w_sn, w_sty, w_stx;
+  int taps_h, taps_w, n_rows, k, kpad, items, vec;
+  LbFastDiv d_kpad;
+};
+constexpr int kPackChunk = 2048;       // items per CTA
+__global__ void __launch_bounds__(256) k_pack_weight_batched(const PackRec* __restrict__ recs, const int2* __restrict__ chunks) {
+  lb_pdl_enter();
+  __shared__ PackRec r;
+  const int2 ch = __ldg(chunks + blockIdx.x);
+  if (threadIdx.x == 0) r = recs[ch.x];
+  __syncthreads();
+  const int end = min(r.items, ch.y + kPackChunk);
+  const size_t tap_stride = (size_t)r.n_rows * r.kpad;
+  const int taps = r.taps_h * r.taps_w;
+  for (int i = ch.y + threadIdx.x; i < end; i += 256) {
+    int n, kk;
+    lb_fast_divmod(r.d_kpad, i, n, kk);
+    const float* src = r.w + kk * r.w_sk + n * r.w_sn;
+    __nv_bfloat16* dst = r.out + (size_t)n * r.kpad + kk;
+    if (r.vec) {
+      for (int t = 0; t < taps; t += 4) {
+        const float4 v = kk < r.k ? __ldcs(reinterpret_cast<const float4*>(src + t)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        dst[(size_t)t * tap_stride] = __float2bfloat16(v.x);
+        dst[(size_t)(t + 1) * tap_stride] = __float2bfloat16(v.y);
+        dst[(size_t)(t + 2) * tap_stride] = __float2bfloat16(v.z);
+        dst[(size_t)(t + 3) * tap_stride] = __float2bfloat16(v.w);
+      }
+    } else {
+      for (int ty = 0; ty < r.taps_h; ++ty)
+        for (int tx = 0; tx < r.taps_w; ++tx)
+          dst[(size_t)(ty * r.taps_w + tx) * tap_stride] = __float2bfloat16(kk < r.k ? __ldg(src + ty * r.w_sty + tx * r.w_stx) : 0.0f);
+    }
+  }
+}
+}  // namespace
+extern "C" int lb_pack_rec_bytes(void) { return (int)sizeof(PackRec); }
+extern "C" int lb_pack_chunk_items(void) { return kPackChunk; }
+// fills one host-side record (lb_pack_rec_bytes() bytes) for lb_conv_tc_pack_batched; returns the record's item count
+extern "C" int lb_pack_rec_fill(const float* w, void* packed, const lb_conv_geom* g, void* rec_host) {
+  if (!w || !packed || !g || !rec_host) return LB_EINVAL;
+  PackRec r;
+  memset(&r, 0, sizeof r);
+  r.kpad = (g->in_c + 7) / 8 * 8;
+  const long long items = (long long)g->out_c * r.kpad;
+  if (items >= (1ll << 31) - (1ll << 24)) return LB_EINVAL;
+  const int taps = g->kh * g->kw;
+  r.w = w; r.out = reinterpret_cast<__nv_bfloat16*>(packed);
+  r.w_sk = g->w_sk; r.w_sn = g->w_sn; r.w_sty = g->w_sty; r.w_stx = g->w_stx;
+  r.taps_h = g->kh; r.taps_w = g->kw; r.n_rows = g->out_c; r.k = g->in_c; r.items = (int)items;
+  r.vec = (taps % 4 == 0 && g->w_stx == 1 && g->w_sty == g->kw && g->w_sk % 4 == 0 && g->w_sn % 4 == 0 &&
+           (reinterpret_cast<uintptr_t>(w) & 15) == 0) ? 1 : 0;
+  r.d_kpad = lb_make_fastdiv(r.kpad);
+  memcpy(rec_host, &r, sizeof r);
+  return (int)items;
+}
+// recs_dev: n records as filled above; chunks_dev: n_chunks pairs (record index, first item), lb_pack_chunk_items() items each
+extern "C" int lb_conv_tc_pack_batched(const void* recs_dev, const void* chunks_dev, int n_chunks, lb_stream_t s) {
+  LB_REQUIRE(recs_dev && chunks_dev && n_chunks > 0);
+  lb_launch(k_pack_weight_batched, n_chunks, 256, 0, lb_s(s), reinterpret_cast<const PackRec*>(recs_dev),
+            reinterpret_cast<const int2*>(chunks_dev));
   LB_LAUNCH_CHECK();
   return LB_OK;
 }

@@ -10,7 +10,7 @@ import torch
 from torch.optim import Optimizer
 
 from ._lib import call, ptr
-from .conv_fn import invalidate_packs  # noqa: F401  (re-exported for manual weight edits)
+from .conv_fn import PackEpoch, invalidate_packs  # noqa: F401  (invalidate_packs re-exported for manual weight edits)
 
 _ALIGN = 4   # floats: keeps every view 16-byte aligned for the vectorised kernels
 
@@ -60,7 +60,7 @@ class Nadam(Optimizer):
             offsets.append(total)
             total += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
         dev = train[0].device
-        epoch = [0]                    # bumped by step(): invalidates the bf16 weight packs of THIS arena only
+        epoch = PackEpoch([0])         # bumped by step(): invalidates the bf16 weight packs of THIS arena only
         flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
         flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
         with torch.no_grad():

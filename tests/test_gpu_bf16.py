@@ -377,3 +377,44 @@ def test_reference_schedule_and_checkpoint_round_trip(tmp_path):
     # same checkpoint, same input -> same images, bit for bit (the forward pass has no floating-point atomics;
     # tests/test_gpu_parity.py::test_forward_is_bit_reproducible)
     assert torch.equal(a, b), rel_l2(a, b)
+
+
+def test_batched_weight_pack_equals_per_layer_packs():
+    """After the optimizer has moved the weights, ONE launch (lb_conv_tc_pack_batched) re-packs every bf16 weight pack of
+    the arena; each pack must be bit-identical to what lb_conv_tc_pack writes for the same weight and geometry, and
+    the per-layer pack launches must be gone from the second step on."""
+    import ctypes
+    from locate_b200 import _lib, conv_fn
+    from locate_b200._lib import call, ptr
+    L.configure(IMAGE_SIZE=32, BASE_FEATURE_FACTOR=4)
+    cfg = O.OracleConfig(IMAGE_SIZE=32, BASE_FEATURE_FACTOR=4)
+    real, aug, z = (t.to(DEV) for t in O.synthetic_batch(cfg, 4))
+    torch.manual_seed(5)
+    gen, g_opt = L.get_model(L.Generator(), L.CFG.GLR, DEV)
+    dis, d_opt = L.get_model(L.Discriminator(), L.CFG.DLR, DEV)
+    tr = L.GanTrainer(gen, dis, g_opt, d_opt)
+    tr.step(real, aug, z)                                   # registers every (weight, direction)
+    _lib.reset_launch_count()
+    tr.step(real, aug, z)
+    first = _lib.launch_count()
+    _lib.reset_launch_count()
+    tr.step(real, aug, z)                                   # batched from here on
+    torch.cuda.synchronize()
+    assert _lib.launch_count() <= first
+    plans = {id(p._lb_epoch.plan): p._lb_epoch.plan for m in (gen, dis) for p in m.parameters() if hasattr(p, "_lb_epoch")}
+    plans = [p for p in plans.values() if p is not None]
+    assert len(plans) == 2 and all(p.tables is not None and len(p.entries) > 10 for p in plans)
+    checked = 0
+    for plan in plans:
+        for ref, tag, ent in plan.entries:
+            w = ref()
+            epoch = w._lb_epoch
+            fresh = (conv_fn._PACK_EPOCH[0], epoch[0], w._version, w.data_ptr())
+            if ent[0] != fresh:
+                continue                                    # stale since the last optimizer step: re-packed at its next use
+            want = torch.full_like(ent[1], float("nan"))
+            call("lb_conv_tc_pack", ptr(w), ptr(want), ent[2])
+            torch.cuda.synchronize()
+            assert torch.equal(ent[1].view(torch.int16), want.view(torch.int16)), tag
+            checked += 1
+    assert checked > 10
