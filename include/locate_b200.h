@@ -291,7 +291,10 @@ int lb_cast_bf16_rows(const float* src, int ld_src, void* dst, int ld_dst, int64
                       lb_stream_t stream);
 int lb_roottanh_fwd_bf16(const float* x, void* y, size_t n, int growth, lb_stream_t stream);
 
-/* column sum: out[c] += sum_rows x[row*ld + c]  (bias gradients); x in storage `dtype`, out fp32 */
+/* column sum: out[c] += sum_rows x[row*ld + c]  (bias gradients; nn.Conv2d's bias of libs/spectral_norm.py-wrapped layers);
+ * x in storage `dtype`, out fp32.  x may be a column slice of ld-wide rows (a concat output): when ld is a multiple of
+ * the 16-byte vector width the kernel reads the slice's 16-byte aligned superset inside each row (up to 15 bytes before
+ * x and after x + cols of the SAME row) and discards the extra columns. */
 int lb_colsum(const void* x, int64_t rows, int cols, int ld, float* out, int dtype, lb_stream_t stream);
 
 /* ---- softmax                                                          libs/attention.py:35,47 */

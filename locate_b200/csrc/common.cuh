@@ -241,9 +241,11 @@ template <typename T> static inline T* lb_p(void* p) { return reinterpret_cast<T
 // (N = LbV<T>::N channels) and walks pixels pl, pl + tp, ...; its N partial sums are combined over the CTA's pixel lanes
 // through `s_part` ([tp][channels] floats) and every channel costs ONE atomic per CTA.  Call from all threads of the CTA
 // (`active` = this thread holds sums); contains __syncthreads.
+// `c_first`, `c_count`: only channels [c_first, c_first + c_count) of the `channels` the CTA summed are written, to
+// out[0 .. c_count) (a column slice summed through its 16-byte aligned superset).
 template <int N>
 __device__ __forceinline__ void lb_colsum_flush(const float (&acc)[N], bool active, float* s_part, int cl, int pl, int tp, int channels,
-                                                float scale, float* __restrict__ out) {
+                                                float scale, float* __restrict__ out, int c_first = 0, int c_count = 1 << 30) {
   __syncthreads();                                   // a previous flush may still be reading s_part
   if (active) {
 #pragma unroll
@@ -251,9 +253,10 @@ __device__ __forceinline__ void lb_colsum_flush(const float (&acc)[N], bool acti
   }
   __syncthreads();
   for (int c = threadIdx.x; c < channels; c += blockDim.x) {
+    if (c < c_first || c - c_first >= c_count) continue;
     float t = 0.0f;
     for (int q = 0; q < tp; ++q) t += s_part[q * channels + c];
-    atomicAdd(out + c, t * scale);
+    atomicAdd(out + c - c_first, t * scale);
   }
 }
 

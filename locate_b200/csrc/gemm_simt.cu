@@ -359,10 +359,13 @@ __global__ void k_colsum(const T* __restrict__ x, long long rows, int cols, int 
     atomicAdd(out + c, acc);
   }
 }
-// vector form (16-byte loads; the scalar kernel keeps 2 bytes per thread in flight and ran at a third of the HBM rate)
+// vector form (16-byte loads; the scalar kernel keeps 2 bytes per thread in flight and ran at a third of the HBM rate).
+// `x` is the 16-byte aligned start of the rows' summed span of `cols` columns (a multiple of the vector width); the wanted
+// columns are [c_first, c_first + c_count) of it -- a concat slice (the D stem's 29 channels at column 3 of 32-wide rows) is
+// summed through its aligned superset.
 template <typename T>
 __global__ void __launch_bounds__(256) k_colsum_v(const T* __restrict__ x, long long rows, int cols, int ld, float* __restrict__ out,
-                                                 int chunk, int cv, int tp) {
+                                                 int chunk, int cv, int tp, int c_first, int c_count) {
   lb_pdl_enter();
   constexpr int N = LbV<T>::N;
   extern __shared__ float s_part[];
@@ -381,12 +384,18 @@ __global__ void __launch_bounds__(256) k_colsum_v(const T* __restrict__ x, long 
       for (int k = 0; k < N; ++k) acc[k] += v[k];
     }
   }
-  lb_colsum_flush<N>(acc, active, s_part, cl, pl, tp, cols, 1.0f, out);
+  lb_colsum_flush<N>(acc, active, s_part, cl, pl, tp, cols, 1.0f, out, c_first, c_count);
 }
+// aligned superset of columns [0, cols) of rows starting at x: *shift elements before x, *span columns wide; false if none
 template <typename T>
-static bool colsum_vec_ok(const T* x, int cols, int ld) {
+static bool colsum_vec_span(const T* x, int cols, int ld, int* shift, int* span) {
   constexpr int N = LbV<T>::N;
-  return !(cols % N) && !(ld % N) && cols / N <= 256 && lb_vec_ok(x);
+  if (ld % N) return false;
+  const uintptr_t a = reinterpret_cast<uintptr_t>(x);
+  if (a % sizeof(T)) return false;
+  *shift = (int)((a & 15) / sizeof(T));
+  *span = (*shift + cols + N - 1) / N * N;
+  return *span <= ld && *span / N <= 256;          // the span never leaves the row it starts in (shift + cols <= ld by construction of a slice)
 }
 extern "C" int lb_colsum(const void* x, int64_t rows, int cols, int ld, float* out, int dtype, lb_stream_t s) {
   LB_REQUIRE(x && out && rows > 0 && cols > 0 && ld >= cols);
@@ -396,13 +405,15 @@ extern "C" int lb_colsum(const void* x, int64_t rows, int cols, int ld, float* o
   if (chunk < sh.tp) chunk = sh.tp;
   chunks = (rows + chunk - 1) / chunk;
   LB_DISPATCH(dtype, T, {
-    if (colsum_vec_ok(lb_cp<T>(x), cols, ld)) {
-      const int cv = cols / LbV<T>::N, tp = 256 / cv;
+    int shift = 0, span = 0;
+    if (colsum_vec_span(lb_cp<T>(x), cols, ld, &shift, &span)) {
+      const int cv = span / LbV<T>::N, tp = 256 / cv;
       chunks = LB_SMS * 4;
       chunk = (rows + chunks - 1) / chunks;
       if (chunk < 4 * tp) chunk = 4 * tp;
       chunks = (rows + chunk - 1) / chunk;
-      lb_launch(k_colsum_v<T>, (unsigned)chunks, 256, (size_t)tp * cols * sizeof(float), lb_s(s), lb_cp<T>(x), rows, cols, ld, out, (int)chunk, cv, tp);
+      lb_launch(k_colsum_v<T>, (unsigned)chunks, 256, (size_t)tp * span * sizeof(float), lb_s(s), lb_cp<T>(x) - shift, rows, span, ld, out,
+                (int)chunk, cv, tp, shift, cols);
     } else {
       lb_launch(k_colsum<T>, (unsigned)chunks, sh.threads, 0, lb_s(s), lb_cp<T>(x), rows, cols, ld, out, (int)chunk, sh.tc, sh.tp);
     }
