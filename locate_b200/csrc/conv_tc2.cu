@@ -1089,6 +1089,11 @@ extern "C" int lb_conv_tc_gemm_ex(const void* in_bf16, const void* w_packed, con
     groups = groups >= 4 ? 4 : groups >= 2 ? 2 : 1;
     if (groups > env_groups) groups = env_groups < 1 ? 1 : env_groups;
     if (groups == 3) groups = 2;
+    // wide tiles (3-4 slabs): two groups of 8 warps, every warp takes two slabs of every second tile -- the same work per
+    // warp, but the two groups' accumulator waits, TMEM loads and MUFU bursts are staggered instead of synchronous
+    static const int env_split = getenv("LB_TC2_SPLIT_GROUPS") ? atoi(getenv("LB_TC2_SPLIT_GROUPS")) : 1;   // measured: 1x1 48->96 -7 %, 96->96 -7..-10 %, step -0.8 %
+    if (env_split && groups == 1 && env_groups >= 2 && p.n_tiles == 1 && p.epi_warps == 16 && nsl >= 3 && nsl <= 4 && p.acc_stride * 4 <= 512)
+      groups = 2;
     p.acc_shift = groups > 1 ? 2 : 1;
     if ((p.acc_stride << p.acc_shift) > 512) { p.acc_shift = 1; if (groups > 2) groups = 2; }
     p.epi_groups = groups;
