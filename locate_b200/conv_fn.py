@@ -9,7 +9,9 @@ Two kernel paths, chosen per layer:
 `pre_act` fuses the RootTanh that precedes every conv of ActivatedBaseConv (conv.py:22-24) into this Function.
 """
 import ctypes
+import weakref
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -100,7 +102,6 @@ class _PackPlan:
         self.tables = None
 
     def register(self, w_bar, tag, ent):
-        import weakref
         self.entries.append((weakref.ref(w_bar), tag, ent))
         self.tables = None
 
@@ -118,7 +119,6 @@ class _PackPlan:
                 raise _lib.LocateLibraryError("lb_pack_rec_fill failed")
             ent[3] = w.data_ptr()
             chunks.extend((i, first) for first in range(0, items, chunk))
-        import numpy as np
         self.tables = (torch.from_numpy(np.frombuffer(buf.raw, dtype=np.uint8).copy()).to(dev),
                        torch.tensor(chunks, dtype=torch.int32).to(dev), len(chunks))
 
